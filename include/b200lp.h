@@ -1,0 +1,177 @@
+/*
+ * b200lp.h — C ABI of libb200lp.so, the sm_100a arithmetic behind the latent-pose-reenactment hot path.
+ *
+ * The reference (shrubb/latent-pose-reenactment) has NO native boundary: every FLOP on the path is a stock
+ * torch/torchvision operator called from Python plugin modules.  This header is therefore the
+ * boundary a maintainer would bind *instead of* those torch operators; each entry point names the reference
+ * call site(s) it replaces.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative B200LP_E* code on failure; b200lp_last_error() gives text.
+ *   - no exceptions, no torch types: raw device pointers, int32/int64 sizes, a cudaStream_t passed as void*.
+ *   - the library never allocates device memory and never synchronises; it launches only on the given stream.
+ *   - activations are NHWC fp32 ("pixels x channels"), weights are "packed" [Cout][tap][Cin] (see b200lp_pack_*).
+ *   - tensor-core operands are TF32 (10-bit mantissa), accumulation FP32 in TMEM.
+ */
+#ifndef B200LP_H_
+#define B200LP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200LP_ABI_VERSION 3
+
+#define B200LP_OK 0
+#define B200LP_EINVAL (-1)   /* bad shape / unsupported configuration */
+#define B200LP_ECUDA (-2)    /* a CUDA runtime / driver call failed   */
+#define B200LP_ENODEV (-3)   /* no sm_100 device                      */
+
+int32_t b200lp_abi_version(void);
+const char* b200lp_last_error(void);
+/* compute capability major*10+minor of the current device, or a negative error */
+int32_t b200lp_device_cc(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 tensor cores (TF32 x TF32 -> FP32), stride 1, "same" zero padding.
+ * Replaces nn.Conv2d forward at  generators/common/blocks.py:78-80,86-88,98-100 (G ResBlock convs + 1x1 skip),
+ * discriminators/no_landmarks.py:54-66 and blocks.py ResBlock(norm='none') (D convs),
+ * criterions/common/perceptual_loss.py:104 (VGG19 / VGG16 feature convs);
+ * and, with weights packed by b200lp_pack_conv_weight(..., transpose=1), the data-gradient of the same convs
+ * (torch autograd's conv backward-data).
+ *
+ *   y[n,h,w,co] = epilogue( sum_{kh,kw,ci} x[n,h+kh-p,w+kw-p,ci] * wp[co][kh*k+kw][ci] )
+ *   epilogue: (+ bias[co]) (+ residual) (relu) (round to tf32)
+ * Requirements: Cin % 32 == 0, Cout % 32 == 0, H and W powers of two >= 2, ksize in {1,3}.
+ */
+typedef struct {
+    const float* x;         /* [N,H,W,Cin] NHWC                                        */
+    const float* wp;        /* [Cout][ksize*ksize][Cin] packed, tf32-rounded           */
+    const float* bias;      /* [Cout] or NULL                                          */
+    const float* residual;  /* NULL, or [N,H,W,Cout] (mode 1), or [N,H/2,W/2,Cout] (mode 2: nearest-2x source) */
+    float* y;               /* [N,H,W,Cout]                                            */
+    int32_t N, H, W, Cin, Cout;
+    int32_t ksize;          /* 1 or 3                                                  */
+    int32_t residual_mode;  /* 0 none, 1 same resolution, 2 half resolution            */
+    int32_t relu;           /* 1: y = max(y, 0)                                        */
+    int32_t round_tf32;     /* 1: round y to tf32 (y only feeds further MMAs)          */
+    int32_t block_n;        /* 0 = auto; else 64 / 128 / 256                           */
+} b200lp_conv_args;
+
+int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Weight packing (every step: weights change with every optimizer update, and spectral norm rescales them).
+ * Replaces the `weight = weight_orig / sigma` materialisation of torch.nn.utils.spectral_norm
+ * (SpectralNorm.compute_weight; call sites blocks.py:78-100, generator :84-86, discriminator :54-66).
+ *   transpose = 0:  wp[co][tap][ci]      = tf32( w[co][ci][kh][kw] * (*scale) )          (forward)
+ *   transpose = 1:  wp[ci][T-1-tap][co]  = tf32( w[co][ci][kh][kw] * (*scale) )          (data-gradient)
+ * `scale` is a device pointer to one float (1/sigma) or NULL for 1.0.
+ */
+int32_t b200lp_pack_conv_weight(const float* w_oihw, const float* scale, float* wp, int32_t Cout, int32_t Cin,
+                                int32_t ksize, int32_t transpose, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Weight gradient of the same convolutions on tcgen05 (torch autograd's conv backward-filter).
+ *   dw[co][ci][kh][kw] (OIHW, fp32) = sum_{n,h,w} dy[n,h,w,co] * x[n,h+kh-p,w+kw-p,ci]
+ * `workspace` holds split-K partial sums; query its size with b200lp_conv_wgrad_workspace().
+ */
+typedef struct {
+    const float* x;   /* [N,H,W,Cin]  NHWC (the conv's forward input, tf32-rounded)   */
+    const float* dy;  /* [N,H,W,Cout] NHWC                                            */
+    float* dw;        /* [Cout][Cin][k][k] OIHW                                       */
+    float* workspace; /* >= b200lp_conv_wgrad_workspace() bytes                       */
+    int64_t workspace_bytes;
+    int32_t N, H, W, Cin, Cout;
+    int32_t ksize;
+    float scale;      /* dw *= scale (e.g. 1/sigma of the spectral norm)              */
+} b200lp_wgrad_args;
+
+int64_t b200lp_conv_wgrad_workspace(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize);
+int32_t b200lp_conv_wgrad(const b200lp_wgrad_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Instance-norm statistics, AdaIN affine + ReLU (+ nearest 2x upsample)  — HBM-bound.
+ * Replaces nn.InstanceNorm2d(eps, affine=False) + `out*gamma+beta` (generators/common/blocks.py:18-26),
+ * the following nn.ReLU(inplace) and nn.Upsample(scale_factor=2) (blocks.py:73-75).
+ *   mean[n,c], rstd[n,c] over the H*W plane (biased variance, rstd = (var+eps)^-1/2)
+ *   y = tf32( relu( (x-mean)*rstd*gamma[n,c] + beta[n,c] ) ),   optionally written 2x nearest-upsampled.
+ * gamma/beta are rows of the projector output: element (n,c) at gamma[n*affine_stride + c].
+ */
+int64_t b200lp_in_stats_workspace(int32_t N, int32_t HW, int32_t C);
+int32_t b200lp_in_stats(const float* x, float* mean, float* rstd, float* workspace, int64_t workspace_bytes,
+                        int32_t N, int32_t HW, int32_t C, float eps, void* stream);
+int32_t b200lp_adain_relu(const float* x, const float* mean, const float* rstd, const float* gamma,
+                          const float* beta, int64_t affine_stride, float* y, int32_t N, int32_t H, int32_t W,
+                          int32_t C, int32_t upsample2, int32_t round_tf32, void* stream);
+/* backward of the above: given dy (w.r.t. the post-ReLU, possibly 2x-upsampled output) produce
+ * dx, dgamma[n,c], dbeta[n,c].  The ReLU mask is recomputed from x (no saved activation needed). */
+int64_t b200lp_adain_relu_bwd_workspace(int32_t N, int32_t HW, int32_t C);
+int32_t b200lp_adain_relu_bwd(const float* x, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, int64_t affine_stride, const float* dy, float* dx, float* dgamma,
+                              float* dbeta, float* workspace, int64_t workspace_bytes, int32_t N, int32_t H,
+                              int32_t W, int32_t C, int32_t upsample2, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Small elementwise / reduction kernels (all NHWC unless stated).
+ */
+/* NCHW <-> NHWC (image boundary of the plugins: data_dict tensors are NCHW, reference layout) */
+int32_t b200lp_nchw_to_nhwc(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, void* stream);
+int32_t b200lp_nhwc_to_nchw(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, void* stream);
+/* y = tf32(relu(x)) (D's in-place ReLU, blocks.py:73 with norm='none'); mask variant for backward: dx = dy*[y>0] */
+int32_t b200lp_relu_round(const float* x, float* y, int64_t n, void* stream);
+int32_t b200lp_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, void* stream);
+/* 2x2 average pool / its backward (nn.AvgPool2d(2): blocks.py:89-90,101-102; perceptual_loss.py:77) */
+int32_t b200lp_avgpool2(const float* x, const float* addend, float* y, int32_t N, int32_t H, int32_t W, int32_t C,
+                        int32_t round_tf32, void* stream);
+int32_t b200lp_avgpool2_bwd(const float* dy, float* dx, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+/* backward of nearest 2x upsample: dx[n,h,w,c] = sum of the 2x2 block of dy */
+int32_t b200lp_upsample2_bwd(const float* dy, float* dx, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+/* sum |a-b| over n elements -> out[0] += result * scale (L1 feature losses: perceptual_loss.py:108, featmat.py:18-20)
+ * and its gradient wrt a: da = sign(a-b) * gscale[0]*scale2 (accumulated into da if accumulate) */
+int32_t b200lp_l1_sum(const float* a, const float* b, float* out, int64_t n, float scale, void* stream);
+int32_t b200lp_l1_bwd(const float* a, const float* b, const float* gscale, float scale2, float* da, int64_t n,
+                      int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Direct (CUDA-core) convolutions for the two degenerate, HBM-bound shapes (SURVEY §7 "Degenerate GEMM shapes").
+ */
+/* 3x3, Cin=3 (NCHW image in) -> Cout (NHWC out) (+bias)(relu)(round): D stem discriminators/no_landmarks.py:54,
+ * VGG features.0 perceptual_loss.py:104.  `pre_scale/pre_shift[3]`: x' = x*pre_scale[c] + pre_shift[c] is applied
+ * on the fly before zero padding (VGG input normalisation perceptual_loss.py:88-98). May be NULL. */
+int32_t b200lp_conv3x3_c3_fwd(const float* x_nchw, const float* w_oihw, const float* wscale, const float* bias,
+                              const float* pre_scale, const float* pre_shift, float* y_nhwc, int32_t N, int32_t H,
+                              int32_t W, int32_t Cout, int32_t relu, int32_t round_tf32, void* stream);
+/* its data gradient (NHWC dy -> NCHW dx, 3 channels) */
+int32_t b200lp_conv3x3_c3_dgrad(const float* dy_nhwc, const float* w_oihw, const float* wscale,
+                                const float* pre_scale, float* dx_nchw, int32_t N, int32_t H, int32_t W,
+                                int32_t Cout, void* stream);
+/* its weight gradient: dw[co][3][3][3] (+= if accumulate) and dbias */
+int32_t b200lp_conv3x3_c3_wgrad(const float* x_nchw, const float* dy_nhwc, float* dw_oihw, float wscale_host,
+                                int32_t N, int32_t H, int32_t W, int32_t Cout, void* stream);
+
+/* Generator tail (generators/vector_pose_unsupervised_segmentation_noBottleneck.py:84-88,165-181):
+ * a[n,h,w,0:4] = conv3x3(x[N,H,W,64] ; w[4][64][3][3]*(*wscale)) + bias ; t = tanh(a);
+ * rgb = t[0:3]*0.75+0.5 ; segm = t[3]*0.5+0.5 ; fake_rgbs = rgb*segm (NCHW [N,3,H,W]) ; fake_segm (NCHW [N,1,H,W]).
+ * `t_out` ([N,H,W,4]) keeps tanh for the backward. */
+int32_t b200lp_gen_tail_fwd(const float* x_nhwc, const float* w_oihw, const float* wscale, const float* bias,
+                            float* fake_rgbs_nchw, float* fake_segm_nchw, float* t_out, int32_t N, int32_t H,
+                            int32_t W, int32_t Cin, void* stream);
+/* backward: from d(fake_rgbs) [N,3,H,W], d(fake_segm) [N,1,H,W] (either may be NULL) and saved t:
+ * da [N,H,W,4] (pre-tanh gradient), then dx = conv-transpose, dw, dbias */
+int32_t b200lp_gen_tail_bwd_act(const float* t, const float* d_rgbs, const float* d_segm, float* da, int32_t N,
+                                int32_t H, int32_t W, void* stream);
+int32_t b200lp_gen_tail_bwd_data(const float* da, const float* w_oihw, const float* wscale, float* dx_nhwc,
+                                 int32_t N, int32_t H, int32_t W, int32_t Cin, void* stream);
+int32_t b200lp_gen_tail_bwd_weight(const float* x_nhwc, const float* da, float* dw_oihw, float* dbias, int32_t N,
+                                   int32_t H, int32_t W, int32_t Cin, void* stream);
+
+/* per-channel sum over pixels (bias gradients): db[c] = scale * sum_{n,h,w} dy[n,h,w,c] */
+int32_t b200lp_bias_grad(const float* dy, float* db, int64_t pixels, int32_t C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LP_H_ */

@@ -1,0 +1,248 @@
+"""Tensor-level wrappers over the C ABI: allocate outputs / workspaces with torch, pass raw pointers.
+
+No arithmetic happens in Python here.  Activations are NHWC float32 CUDA tensors of shape (N, H, W, C).
+"""
+from ctypes import byref, c_float, c_void_p
+
+import torch
+
+from . import lib as L
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes) // 4, 1), dtype=torch.float32, device=device)
+
+
+def pack_conv_weight(w_oihw, scale=None, transpose=False):
+    """OIHW fp32 -> packed [Cout][tap][Cin] (or [Cin][tap'][Cout] when transpose) tf32, times *scale (device scalar)."""
+    lib = L.load()
+    co, ci, kh, kw = w_oihw.shape
+    assert kh == kw and kh in (1, 3)
+    out = torch.empty((ci, kh * kw, co) if transpose else (co, kh * kw, ci), dtype=torch.float32, device=w_oihw.device)
+    L.check(lib.b200lp_pack_conv_weight(L.ptr(w_oihw.contiguous()), L.ptr(scale), L.ptr(out), co, ci, kh,
+                                        1 if transpose else 0, L.stream_ptr()), "pack_conv_weight")
+    return out
+
+
+def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False, round_tf32=False, block_n=0,
+             out=None):
+    """x (N,H,W,Cin) NHWC, wp packed (Cout, k*k, Cin) -> y (N,H,W,Cout)."""
+    lib = L.load()
+    n, h, w, cin = x.shape
+    cout = wp.shape[0]
+    assert wp.shape[1] == ksize * ksize and wp.shape[2] == cin, (wp.shape, ksize, cin)
+    y = out if out is not None else torch.empty((n, h, w, cout), dtype=torch.float32, device=x.device)
+    a = L.ConvArgs()
+    a.x = L.ptr(x); a.wp = L.ptr(wp); a.bias = L.ptr(bias); a.residual = L.ptr(residual); a.y = L.ptr(y)
+    a.N, a.H, a.W, a.Cin, a.Cout = n, h, w, cin, cout
+    a.ksize = ksize
+    a.residual_mode = residual_mode if residual is not None else 0
+    a.relu = int(relu)
+    a.round_tf32 = int(round_tf32)
+    a.block_n = block_n
+    L.check(lib.b200lp_conv_fwd(byref(a), L.stream_ptr()), "conv_fwd")
+    return y
+
+
+def conv_wgrad(x, dy, ksize, scale=1.0):
+    """x (N,H,W,Cin), dy (N,H,W,Cout) -> dw OIHW (Cout,Cin,k,k) * scale."""
+    lib = L.load()
+    n, h, w, cin = x.shape
+    cout = dy.shape[3]
+    nbytes = lib.b200lp_conv_wgrad_workspace(n, h, w, cin, cout, ksize)
+    if nbytes < 0:
+        raise L.B200lpError(f"conv_wgrad_workspace: {L.last_error()}")
+    ws = _ws(nbytes, x.device)
+    dw = torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
+    a = L.WgradArgs()
+    a.x = L.ptr(x); a.dy = L.ptr(dy); a.dw = L.ptr(dw); a.workspace = L.ptr(ws)
+    a.workspace_bytes = ws.numel() * 4
+    a.N, a.H, a.W, a.Cin, a.Cout = n, h, w, cin, cout
+    a.ksize = ksize
+    a.scale = float(scale)
+    L.check(lib.b200lp_conv_wgrad(byref(a), L.stream_ptr()), "conv_wgrad")
+    return dw
+
+
+def in_stats(x, eps):
+    """x (N,H,W,C) -> mean (N,C), rstd (N,C) of each (n,c) plane (biased variance)."""
+    lib = L.load()
+    n, h, w, c = x.shape
+    ws = _ws(lib.b200lp_in_stats_workspace(n, h * w, c), x.device)
+    mean = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    L.check(lib.b200lp_in_stats(L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(ws), ws.numel() * 4, n, h * w, c,
+                                c_float(eps), L.stream_ptr()), "in_stats")
+    return mean, rstd
+
+
+def _affine_views(gamma, beta):
+    # gamma / beta are (N, C) views into the projector output (row stride = affine_stride, unit column stride)
+    assert gamma.stride(1) == 1 and beta.stride(1) == 1 and gamma.stride(0) == beta.stride(0)
+    assert gamma.dtype == torch.float32 and gamma.is_cuda
+    return c_void_p(gamma.data_ptr()), c_void_p(beta.data_ptr()), gamma.stride(0)
+
+
+def adain_relu(x, mean, rstd, gamma, beta, upsample2=False, round_tf32=True):
+    lib = L.load()
+    n, h, w, c = x.shape
+    gp, bp, stride = _affine_views(gamma, beta)
+    s = 2 if upsample2 else 1
+    y = torch.empty((n, h * s, w * s, c), dtype=torch.float32, device=x.device)
+    L.check(lib.b200lp_adain_relu(L.ptr(x), L.ptr(mean), L.ptr(rstd), gp, bp, stride, L.ptr(y), n, h, w, c,
+                                  int(upsample2), int(round_tf32), L.stream_ptr()), "adain_relu")
+    return y
+
+
+def adain_relu_bwd(x, mean, rstd, gamma, beta, dy, upsample2=False):
+    lib = L.load()
+    n, h, w, c = x.shape
+    gp, bp, stride = _affine_views(gamma, beta)
+    ws = _ws(lib.b200lp_adain_relu_bwd_workspace(n, h * w, c), x.device)
+    dx = torch.empty_like(x)
+    dgamma = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    dbeta = torch.empty_like(dgamma)
+    L.check(lib.b200lp_adain_relu_bwd(L.ptr(x), L.ptr(mean), L.ptr(rstd), gp, bp, stride, L.ptr(dy), L.ptr(dx),
+                                      L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), ws.numel() * 4, n, h, w, c,
+                                      int(upsample2), L.stream_ptr()), "adain_relu_bwd")
+    return dx, dgamma, dbeta
+
+
+def nchw_to_nhwc(x):
+    lib = L.load()
+    n, c, h, w = x.shape
+    y = torch.empty((n, h, w, c), dtype=torch.float32, device=x.device)
+    L.check(lib.b200lp_nchw_to_nhwc(L.ptr(x), L.ptr(y), n, c, h, w, L.stream_ptr()), "nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw(x):
+    lib = L.load()
+    n, h, w, c = x.shape
+    y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    L.check(lib.b200lp_nhwc_to_nchw(L.ptr(x), L.ptr(y), n, c, h, w, L.stream_ptr()), "nhwc_to_nchw")
+    return y
+
+
+def relu_round(x):
+    lib = L.load()
+    y = torch.empty_like(x)
+    L.check(lib.b200lp_relu_round(L.ptr(x), L.ptr(y), x.numel(), L.stream_ptr()), "relu_round")
+    return y
+
+
+def relu_bwd(y, dy):
+    lib = L.load()
+    dx = torch.empty_like(dy)
+    L.check(lib.b200lp_relu_bwd(L.ptr(y), L.ptr(dy), L.ptr(dx), dy.numel(), L.stream_ptr()), "relu_bwd")
+    return dx
+
+
+def avgpool2(x, addend=None, round_tf32=False):
+    lib = L.load()
+    n, h2, w2, c = x.shape
+    y = torch.empty((n, h2 // 2, w2 // 2, c), dtype=torch.float32, device=x.device)
+    L.check(lib.b200lp_avgpool2(L.ptr(x), L.ptr(addend), L.ptr(y), n, h2 // 2, w2 // 2, c, int(round_tf32),
+                                L.stream_ptr()), "avgpool2")
+    return y
+
+
+def avgpool2_bwd(dy):
+    lib = L.load()
+    n, h, w, c = dy.shape
+    dx = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.float32, device=dy.device)
+    L.check(lib.b200lp_avgpool2_bwd(L.ptr(dy), L.ptr(dx), n, h, w, c, L.stream_ptr()), "avgpool2_bwd")
+    return dx
+
+
+def upsample2_bwd(dy):
+    lib = L.load()
+    n, h2, w2, c = dy.shape
+    dx = torch.empty((n, h2 // 2, w2 // 2, c), dtype=torch.float32, device=dy.device)
+    L.check(lib.b200lp_upsample2_bwd(L.ptr(dy), L.ptr(dx), n, h2 // 2, w2 // 2, c, L.stream_ptr()), "upsample2_bwd")
+    return dx
+
+
+def l1_sum(a, b, out, scale):
+    """out[0] += scale * sum|a-b| (out: 1-element device tensor, caller zeroes it)."""
+    lib = L.load()
+    L.check(lib.b200lp_l1_sum(L.ptr(a), L.ptr(b), L.ptr(out), a.numel(), c_float(scale), L.stream_ptr()), "l1_sum")
+
+
+def l1_bwd(a, b, gscale, scale2, da=None):
+    """da (+)= sign(a-b) * gscale[0] * scale2."""
+    lib = L.load()
+    acc = da is not None
+    if da is None:
+        da = torch.empty_like(a)
+    L.check(lib.b200lp_l1_bwd(L.ptr(a), L.ptr(b), L.ptr(gscale), c_float(scale2), L.ptr(da), a.numel(), int(acc),
+                              L.stream_ptr()), "l1_bwd")
+    return da
+
+
+def conv3x3_c3_fwd(x_nchw, w, wscale=None, bias=None, pre_scale=None, pre_shift=None, relu=False, round_tf32=False):
+    lib = L.load()
+    n, c, h, wd = x_nchw.shape
+    assert c == 3
+    cout = w.shape[0]
+    y = torch.empty((n, h, wd, cout), dtype=torch.float32, device=x_nchw.device)
+    L.check(lib.b200lp_conv3x3_c3_fwd(L.ptr(x_nchw), L.ptr(w), L.ptr(wscale), L.ptr(bias), L.ptr(pre_scale),
+                                      L.ptr(pre_shift), L.ptr(y), n, h, wd, cout, int(relu), int(round_tf32),
+                                      L.stream_ptr()), "conv3x3_c3_fwd")
+    return y
+
+
+def conv3x3_c3_dgrad(dy, w, wscale=None, pre_scale=None):
+    lib = L.load()
+    n, h, wd, cout = dy.shape
+    dx = torch.empty((n, 3, h, wd), dtype=torch.float32, device=dy.device)
+    L.check(lib.b200lp_conv3x3_c3_dgrad(L.ptr(dy), L.ptr(w), L.ptr(wscale), L.ptr(pre_scale), L.ptr(dx), n, h, wd,
+                                        cout, L.stream_ptr()), "conv3x3_c3_dgrad")
+    return dx
+
+
+def conv3x3_c3_wgrad(x_nchw, dy, scale=1.0):
+    lib = L.load()
+    n, h, wd, cout = dy.shape
+    dw = torch.empty((cout, 3, 3, 3), dtype=torch.float32, device=dy.device)
+    L.check(lib.b200lp_conv3x3_c3_wgrad(L.ptr(x_nchw), L.ptr(dy), L.ptr(dw), c_float(scale), n, h, wd, cout,
+                                        L.stream_ptr()), "conv3x3_c3_wgrad")
+    return dw
+
+
+def gen_tail_fwd(x, w, wscale, bias):
+    lib = L.load()
+    n, h, wd, cin = x.shape
+    rgbs = torch.empty((n, 3, h, wd), dtype=torch.float32, device=x.device)
+    segm = torch.empty((n, 1, h, wd), dtype=torch.float32, device=x.device)
+    t = torch.empty((n, h, wd, 4), dtype=torch.float32, device=x.device)
+    L.check(lib.b200lp_gen_tail_fwd(L.ptr(x), L.ptr(w), L.ptr(wscale), L.ptr(bias), L.ptr(rgbs), L.ptr(segm),
+                                    L.ptr(t), n, h, wd, cin, L.stream_ptr()), "gen_tail_fwd")
+    return rgbs, segm, t
+
+
+def gen_tail_bwd(x, t, w, wscale, d_rgbs, d_segm, need_dx=True, need_dw=True):
+    lib = L.load()
+    n, h, wd, cin = x.shape
+    da = torch.empty((n, h, wd, 4), dtype=torch.float32, device=x.device)
+    L.check(lib.b200lp_gen_tail_bwd_act(L.ptr(t), L.ptr(d_rgbs), L.ptr(d_segm), L.ptr(da), n, h, wd,
+                                        L.stream_ptr()), "gen_tail_bwd_act")
+    dx = dw = db = None
+    if need_dx:
+        dx = torch.empty_like(x)
+        L.check(lib.b200lp_gen_tail_bwd_data(L.ptr(da), L.ptr(w), L.ptr(wscale), L.ptr(dx), n, h, wd, cin,
+                                             L.stream_ptr()), "gen_tail_bwd_data")
+    if need_dw:
+        dw = torch.empty((4, cin, 3, 3), dtype=torch.float32, device=x.device)
+        db = torch.empty((4,), dtype=torch.float32, device=x.device)
+        L.check(lib.b200lp_gen_tail_bwd_weight(L.ptr(x), L.ptr(da), L.ptr(dw), L.ptr(db), n, h, wd, cin,
+                                               L.stream_ptr()), "gen_tail_bwd_weight")
+    return dx, dw, db
+
+
+def bias_grad(dy):
+    lib = L.load()
+    c = dy.shape[-1]
+    db = torch.empty((c,), dtype=torch.float32, device=dy.device)
+    L.check(lib.b200lp_bias_grad(L.ptr(dy), L.ptr(db), dy.numel() // c, c, L.stream_ptr()), "bias_grad")
+    return db

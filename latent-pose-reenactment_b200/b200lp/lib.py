@@ -1,0 +1,142 @@
+"""ctypes binding of libb200lp.so (the C ABI declared in include/b200lp.h).
+
+PyTorch is used here only as the owner of device memory and of the current CUDA stream; every call passes raw
+device pointers + sizes across the C ABI.  There is NO fallback: if the library is missing or the device is not
+sm_100, calls raise.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_void_p
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent.parent
+LIB_PATH = _PKG / "lib" / "libb200lp.so"
+ABI_VERSION = 3
+
+
+class B200lpError(RuntimeError):
+    pass
+
+
+class ConvArgs(Structure):
+    _fields_ = [
+        ("x", c_void_p), ("wp", c_void_p), ("bias", c_void_p), ("residual", c_void_p), ("y", c_void_p),
+        ("N", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("Cout", c_int32),
+        ("ksize", c_int32), ("residual_mode", c_int32), ("relu", c_int32), ("round_tf32", c_int32),
+        ("block_n", c_int32),
+    ]
+
+
+class WgradArgs(Structure):
+    _fields_ = [
+        ("x", c_void_p), ("dy", c_void_p), ("dw", c_void_p), ("workspace", c_void_p),
+        ("workspace_bytes", c_int64),
+        ("N", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("Cout", c_int32),
+        ("ksize", c_int32), ("scale", c_float),
+    ]
+
+
+_P = c_void_p
+_I = c_int32
+_L = c_int64
+_F = c_float
+
+# name -> (restype, argtypes); mirrors include/b200lp.h one to one (tests/test_abi.py checks the header against this)
+SIGNATURES = {
+    "b200lp_abi_version": (_I, []),
+    "b200lp_last_error": (c_char_p, []),
+    "b200lp_device_cc": (_I, []),
+    "b200lp_conv_fwd": (_I, [POINTER(ConvArgs), _P]),
+    "b200lp_pack_conv_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_conv_wgrad_workspace": (_L, [_I, _I, _I, _I, _I, _I]),
+    "b200lp_conv_wgrad": (_I, [POINTER(WgradArgs), _P]),
+    "b200lp_in_stats_workspace": (_L, [_I, _I, _I]),
+    "b200lp_in_stats": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _F, _P]),
+    "b200lp_adain_relu": (_I, [_P, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "b200lp_adain_relu_bwd_workspace": (_L, [_I, _I, _I]),
+    "b200lp_adain_relu_bwd": (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
+    "b200lp_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_relu_round": (_I, [_P, _P, _L, _P]),
+    "b200lp_relu_bwd": (_I, [_P, _P, _P, _L, _P]),
+    "b200lp_avgpool2": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200lp_avgpool2_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_upsample2_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_l1_sum": (_I, [_P, _P, _P, _L, _F, _P]),
+    "b200lp_l1_bwd": (_I, [_P, _P, _P, _F, _P, _L, _I, _P]),
+    "b200lp_conv3x3_c3_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "b200lp_conv3x3_c3_dgrad": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_conv3x3_c3_wgrad": (_I, [_P, _P, _P, _F, _I, _I, _I, _I, _P]),
+    "b200lp_gen_tail_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_gen_tail_bwd_act": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "b200lp_gen_tail_bwd_data": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_gen_tail_bwd_weight": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_bias_grad": (_I, [_P, _P, _L, _I, _P]),
+}
+
+_lib = None
+
+
+def load(build_if_missing=True):
+    """dlopen libb200lp.so, declare every signature, verify the ABI version.  Raises B200lpError if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        if build_if_missing:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("b200lp_build_ext", _PKG / "build_ext.py")
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        if not LIB_PATH.exists():
+            raise B200lpError(f"{LIB_PATH} not found: run `python __graft_entry__.py` (build) first")
+    lib = ctypes.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise B200lpError(f"libb200lp.so does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    v = lib.b200lp_abi_version()
+    if v != ABI_VERSION:
+        raise B200lpError(f"libb200lp.so ABI version {v} != binding version {ABI_VERSION}: rebuild")
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().b200lp_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        raise B200lpError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Raw device pointer of a contiguous fp32 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise B200lpError("b200lp kernels need CUDA tensors (there is no CPU fallback)")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise B200lpError(f"expected contiguous float32 tensor, got {t.dtype} contiguous={t.is_contiguous()}")
+    return c_void_p(t.data_ptr())
+
+
+def require_device():
+    """Fail loudly unless a CUDA device of compute capability 10.x is current."""
+    if not torch.cuda.is_available():
+        raise B200lpError("no CUDA device: the b200lp hot path has no CPU fallback")
+    cc = load().b200lp_device_cc()
+    if cc < 100 or cc >= 110:
+        raise B200lpError(f"device compute capability {cc} is not sm_100 (B200): kernels are sm_100a-only")
+    return cc

@@ -1,0 +1,79 @@
+"""Builds libb200lp.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc.
+
+The .so is git-ignored but travels to the GPU box with the repo snapshot.  nvcc cross-compiles without a GPU.
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+LIB_DIR = HERE / "lib"
+LIB_PATH = LIB_DIR / "libb200lp.so"
+SOURCES = ["common.cu", "conv_igemm.cu", "conv_wgrad.cu", "elementwise.cu", "direct_conv.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "-Xptxas=-v",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build libb200lp.so")
+
+
+def _stamp():
+    h = hashlib.sha256()
+    for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "b200lp.h"]):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu for sm_100a and link lib/libb200lp.so.  Returns the library path."""
+    LIB_DIR.mkdir(exist_ok=True)
+    stamp_file = LIB_DIR / "build.stamp"
+    stamp = _stamp()
+    if not force and LIB_PATH.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
+        return LIB_PATH
+    nvcc = _nvcc()
+    objs = []
+    obj_dir = LIB_DIR / "obj"
+    obj_dir.mkdir(exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = obj_dir / (src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(str(obj))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"== {src}\n{out}")
+        if p.returncode != 0:
+            sys.stderr.write("\n".join(log))
+            raise RuntimeError(f"nvcc failed on {src}")
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *objs]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    log.append(r.stdout)
+    if r.returncode != 0:
+        sys.stderr.write("\n".join(log))
+        raise RuntimeError("nvcc link failed")
+    (LIB_DIR / "build.log").write_text("\n".join(log))
+    stamp_file.write_text(stamp)
+    if verbose:
+        print("\n".join(log))
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

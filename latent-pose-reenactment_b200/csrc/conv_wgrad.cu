@@ -1,0 +1,316 @@
+// Weight gradient of the 3x3 / 1x1 convolutions on the sm_100a tensor cores.
+//
+//   dW[(tap,ci)][co] = sum_pixels  X[pixel + tap][ci] * dY[pixel][co]
+//   GEMM view:  M = (tap, ci) rows (128 per CTA = four 32-channel blocks, each with its own tap shift),
+//               N = Cout tile, K = pixels (split across CTAs: "split-K", deterministic two-pass reduction).
+//   Both operands are read straight from the NHWC tensors: a TMA box [32 pixels][32 channels] lands in shared
+//   memory as 32 rows (K) x 128 bytes (32 channels of M or N): the canonical MN-major SWIZZLE_128B UMMA operand,
+//   so no transposed copy of the activations or gradients ever exists in HBM.
+//   Zero padding = TMA out-of-bounds zero fill on the shifted X box.
+//
+// Replaces torch autograd's conv backward-filter for the convs listed in include/b200lp.h.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200lp {
+
+constexpr int kWgM = 128;          // (tap,ci) rows per CTA
+constexpr int kWgKStep = 32;       // pixels per pipeline stage
+constexpr int kWgThreads = 192;
+constexpr int kWgBlkBytes = kWgKStep * 128;  // one [32 pixels][32 ch] box = 4 KB
+
+struct WgradParams {
+    float* ws;            // [splits][rows_total][Cout]
+    int N, H, W, Cin, Cout;
+    int ksize;
+    int pw, ph, pn;       // pixel box: pw*ph*pn == 32
+    int steps_w, steps_h; // boxes per image row / column
+    int total_steps;      // K steps over the whole batch
+    int steps_per_split;
+    int cblks;            // Cin / 32
+    int rows_total;       // taps * Cin
+    int blocks_total;     // taps * cblks
+};
+
+template <int BLOCK_N>
+struct WgCfg {
+    static constexpr int kABytes = 4 * kWgBlkBytes;                // 16 KB
+    static constexpr int kBBytes = (BLOCK_N / 32) * kWgBlkBytes;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+    static constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                       const WgradParams p) {
+    using Cfg = WgCfg<BLOCK_N>;
+    constexpr int kStages = Cfg::kStages;
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ __align__(8) uint64_t empty_bar[kStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x;
+    const int m_tile = blockIdx.y;
+    const int split = blockIdx.z;
+
+    const int ks_begin = split * p.steps_per_split;
+    int ks_end = ks_begin + p.steps_per_split;
+    if (ks_end > p.total_steps) ks_end = p.total_steps;
+    const int nsteps = ks_end - ks_begin;   // >= 1 by construction of the grid
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmDY);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int pad = p.ksize >> 1;
+            // the four 32-row blocks of this M tile: (tap shift, channel block); blocks past the end are skipped
+            int blk_dx[4], blk_dy[4], blk_c[4];
+            int nvalid = 0;
+            for (int j = 0; j < 4; ++j) {
+                const int b = m_tile * 4 + j;
+                if (b < p.blocks_total) {
+                    const int tap = b / p.cblks;
+                    blk_c[j] = (b - tap * p.cblks) * 32;
+                    blk_dy[j] = tap / p.ksize - pad;
+                    blk_dx[j] = tap % p.ksize - pad;
+                    ++nvalid;
+                } else {
+                    blk_c[j] = 0; blk_dx[j] = 0; blk_dy[j] = 0;
+                }
+            }
+            const uint32_t tx_bytes = static_cast<uint32_t>(nvalid * kWgBlkBytes + Cfg::kBBytes);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < nsteps; ++i) {
+                int ks = ks_begin + i;
+                const int tw = ks % p.steps_w;
+                ks /= p.steps_w;
+                const int th = ks % p.steps_h;
+                const int tn = ks / p.steps_h;
+                const int w0 = tw * p.pw, h0 = th * p.ph, n0 = tn * p.pn;
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                uint8_t* sa = smem_al + stage * Cfg::kStageBytes;
+                uint8_t* sb = sa + Cfg::kABytes;
+                mbar_expect_tx(&full_bar[stage], tx_bytes);
+                for (int j = 0; j < nvalid; ++j)
+                    tma_load_4d(sa + j * kWgBlkBytes, &tmX, &full_bar[stage], blk_c[j], w0 + blk_dx[j],
+                                h0 + blk_dy[j], n0);
+#pragma unroll
+                for (int j = 0; j < BLOCK_N / 32; ++j)
+                    tma_load_4d(sb + j * kWgBlkBytes, &tmDY, &full_bar[stage], n_tile * BLOCK_N + j * 32, w0, h0,
+                                n0);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(kWgM, BLOCK_N, 1, 1);  // both operands MN-major
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < nsteps; ++i) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
+                const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+                for (int k = 0; k < kWgKStep / 8; ++k) {
+                    // MN-major SWIZZLE_128B: 32-channel blocks are kWgBlkBytes apart (LBO); 8 K rows = 1024 B
+                    const uint64_t da = make_smem_desc(a_addr + k * 1024, kWgBlkBytes, 1024, 2);
+                    const uint64_t db = make_smem_desc(b_addr + k * 1024, kWgBlkBytes, 1024, 2);
+                    umma_tf32_ss(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;
+        const int row = m_tile * kWgM + m;
+        const bool valid = row < p.rows_total;
+        float* orow = p.ws + (static_cast<size_t>(split) * p.rows_total + row) * p.Cout + n_tile * BLOCK_N;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                           __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    *reinterpret_cast<float4*>(orow + c0 + j) = o;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// dw[co][ci][tap] = scale * sum_s ws[s][tap*Cin+ci][co]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int rows,
+                                    int Cout, int Cin, int taps, float scale) {
+    // thread per (row, co) with co fastest for coalesced reads
+    const long total = static_cast<long>(rows) * Cout;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s) acc += ws[static_cast<long>(s) * total + i];
+        const int co = i % Cout;
+        const int row = i / Cout;
+        const int tap = row / Cin;
+        const int ci = row - tap * Cin;
+        dw[(static_cast<long>(co) * Cin + ci) * taps + tap] = acc * scale;
+    }
+}
+
+struct WgPlan {
+    int block_n, m_tiles, n_tiles, splits, steps_per_split, total_steps, pw, ph, pn;
+};
+
+static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int ksize, WgPlan* pl) {
+    if (!(ksize == 1 || ksize == 3) || Cin % 32 || Cout % 32 || Cin <= 0 || Cout <= 0 || N <= 0) return -1;
+    if (ilog2_exact(H) < 1 || ilog2_exact(W) < 1) return -1;
+    pl->pw = W < 32 ? W : 32;
+    pl->ph = (32 / pl->pw) < H ? (32 / pl->pw) : H;
+    pl->pn = 32 / (pl->pw * pl->ph);
+    const int steps_n = (N + pl->pn - 1) / pl->pn;
+    pl->total_steps = (W / pl->pw) * (H / pl->ph) * steps_n;
+    pl->block_n = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32));
+    pl->n_tiles = Cout / pl->block_n;
+    const int blocks_total = ksize * ksize * (Cin / 32);
+    pl->m_tiles = (blocks_total + 3) / 4;
+    const int base = pl->m_tiles * pl->n_tiles;
+    int splits = (2 * 148 + base - 1) / base;
+    if (splits > 64) splits = 64;
+    if (splits > pl->total_steps) splits = pl->total_steps;
+    if (splits < 1) splits = 1;
+    pl->steps_per_split = (pl->total_steps + splits - 1) / splits;
+    pl->splits = (pl->total_steps + pl->steps_per_split - 1) / pl->steps_per_split;  // no empty split
+    return 0;
+}
+
+template <int BLOCK_N>
+static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradParams& p, const WgPlan& pl,
+                        cudaStream_t stream) {
+    using Cfg = WgCfg<BLOCK_N>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200LP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_tf32_kernel<BLOCK_N>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
+    conv_wgrad_tf32_kernel<BLOCK_N><<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(tmX, tmDY, p);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+}  // namespace b200lp
+
+using namespace b200lp;
+
+extern "C" int64_t b200lp_conv_wgrad_workspace(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                                               int32_t ksize) {
+    WgPlan pl;
+    if (plan_wgrad(N, H, W, Cin, Cout, ksize, &pl)) {
+        set_error("conv_wgrad_workspace: unsupported shape N=%d H=%d W=%d Cin=%d Cout=%d k=%d", N, H, W, Cin, Cout,
+                  ksize);
+        return B200LP_EINVAL;
+    }
+    return static_cast<int64_t>(pl.splits) * ksize * ksize * Cin * Cout * 4;
+}
+
+extern "C" int32_t b200lp_conv_wgrad(const b200lp_wgrad_args* a, void* stream) {
+    B200LP_REQUIRE(a && a->x && a->dy && a->dw && a->workspace, "conv_wgrad: null pointer");
+    WgPlan pl;
+    B200LP_REQUIRE(plan_wgrad(a->N, a->H, a->W, a->Cin, a->Cout, a->ksize, &pl) == 0,
+                   "conv_wgrad: unsupported shape N=%d H=%d W=%d Cin=%d Cout=%d k=%d", a->N, a->H, a->W, a->Cin,
+                   a->Cout, a->ksize);
+    B200LP_REQUIRE(a->N % pl.pn == 0, "conv_wgrad: N=%d must be a multiple of %d for %dx%d planes", a->N, pl.pn,
+                   a->H, a->W);
+    const int taps = a->ksize * a->ksize;
+    const int64_t need = static_cast<int64_t>(pl.splits) * taps * a->Cin * a->Cout * 4;
+    B200LP_REQUIRE(a->workspace_bytes >= need, "conv_wgrad: workspace %lld < %lld bytes",
+                   (long long)a->workspace_bytes, (long long)need);
+
+    WgradParams p;
+    p.ws = a->workspace;
+    p.N = a->N; p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.Cout = a->Cout;
+    p.ksize = a->ksize;
+    p.pw = pl.pw; p.ph = pl.ph; p.pn = pl.pn;
+    p.steps_w = a->W / pl.pw;
+    p.steps_h = a->H / pl.ph;
+    p.total_steps = pl.total_steps;
+    p.steps_per_split = pl.steps_per_split;
+    p.cblks = a->Cin / 32;
+    p.rows_total = taps * a->Cin;
+    p.blocks_total = taps * p.cblks;
+
+    CUtensorMap tmX, tmDY;
+    const uint32_t box[4] = {32u, (uint32_t)pl.pw, (uint32_t)pl.ph, (uint32_t)pl.pn};
+    {
+        const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
+        const uint64_t strides[3] = {(uint64_t)a->Cin * 4, (uint64_t)a->W * a->Cin * 4,
+                                     (uint64_t)a->H * a->W * a->Cin * 4};
+        int r = encode_tmap_f32(&tmX, a->x, 4, dims, strides, box);
+        if (r) return r;
+    }
+    {
+        const uint64_t dims[4] = {(uint64_t)a->Cout, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
+        const uint64_t strides[3] = {(uint64_t)a->Cout * 4, (uint64_t)a->W * a->Cout * 4,
+                                     (uint64_t)a->H * a->W * a->Cout * 4};
+        int r = encode_tmap_f32(&tmDY, a->dy, 4, dims, strides, box);
+        if (r) return r;
+    }
+    cudaStream_t s = as_stream(stream);
+    int r;
+    switch (pl.block_n) {
+        case 256: r = launch_wgrad<256>(tmX, tmDY, p, pl, s); break;
+        case 128: r = launch_wgrad<128>(tmX, tmDY, p, pl, s); break;
+        case 64: r = launch_wgrad<64>(tmX, tmDY, p, pl, s); break;
+        default: r = launch_wgrad<32>(tmX, tmDY, p, pl, s); break;
+    }
+    if (r) return r;
+    const long total = static_cast<long>(p.rows_total) * a->Cout;
+    int blocks = static_cast<int>((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(a->workspace, a->dw, pl.splits, p.rows_total, a->Cout, a->Cin, taps,
+                                               a->scale);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}

@@ -1,0 +1,472 @@
+// CUDA-core direct convolutions for the two degenerate, HBM-bound shapes of the hot path:
+//   * 3x3 with Cin = 3 (image stems: discriminator down_block.0, VGG features.0)  — K = 27, not a tensor-core shape
+//   * the generator tail 3x3 Cin -> 4 with tanh / rgb*segm composition            — N = 4
+// plus their data / weight gradients.  Image-side tensors are NCHW (the plugin boundary), feature side NHWC.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200lp {
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ------------------------------------------------------------------------------------------------ Cin = 3 forward
+// block 256 threads = (Cout/16 channel groups) x (256/groups pixels); a warp = 32 consecutive pixels, one group.
+__global__ void __launch_bounds__(256)
+conv3x3_c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ wscale,
+                      const float* __restrict__ bias, const float* __restrict__ pre_scale,
+                      const float* __restrict__ pre_shift, float* __restrict__ y, int N, int H, int W, int Cout,
+                      int relu, int round_out) {
+    extern __shared__ float sm[];           // [27][Cout] weights, then [Cout] bias
+    float* sw = sm;
+    float* sb = sm + 27 * Cout;
+    const float s = wscale ? __ldg(wscale) : 1.f;
+    for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
+        const int co = i % Cout, t = i / Cout;          // t = c*9 + tap (OIHW inner order)
+        sw[i] = __ldg(w + co * 27 + t) * s;
+    }
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias ? __ldg(bias + i) : 0.f;
+    __syncthreads();
+
+    const int groups = Cout >> 4;
+    const int ppb = blockDim.x / groups;
+    const int g = threadIdx.x / ppb;
+    const int pl = threadIdx.x - g * ppb;
+    const long P = static_cast<long>(blockIdx.x) * ppb + pl;
+    const long total = static_cast<long>(N) * H * W;
+    if (P >= total) return;
+    const int wq = static_cast<int>(P % W);
+    const int hq = static_cast<int>((P / W) % H);
+    const long n = P / (static_cast<long>(W) * H);
+
+    float in[27];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float ps = pre_scale ? __ldg(pre_scale + c) : 1.f;
+        const float pb = pre_shift ? __ldg(pre_shift + c) : 0.f;
+        const float* xp = x + (n * 3 + c) * static_cast<long>(H) * W;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int hh = hq + kh - 1, ww = wq + kw - 1;
+                float v = 0.f;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(xp + static_cast<long>(hh) * W + ww) * ps + pb;
+                in[c * 9 + kh * 3 + kw] = v;
+            }
+        }
+    }
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = sb[g * 16 + j];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+        const float v = in[t];
+        const float4* wr = reinterpret_cast<const float4*>(sw + t * Cout + g * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 ww = wr[q];
+            acc[q * 4 + 0] += v * ww.x; acc[q * 4 + 1] += v * ww.y;
+            acc[q * 4 + 2] += v * ww.z; acc[q * 4 + 3] += v * ww.w;
+        }
+    }
+    float* yo = y + P * Cout + g * 16;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float4 o = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        *reinterpret_cast<float4*>(yo + q * 4) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ Cin = 3 dgrad
+// dx[n,c,h,w] = pre_scale[c] * sum_{kh,kw,co} dy[n,h-kh+1,w-kw+1,co] * w[co][c][kh][kw]
+__global__ void __launch_bounds__(256)
+conv3x3_c3_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ wscale,
+                        const float* __restrict__ pre_scale, float* __restrict__ dx, int N, int H, int W, int Cout) {
+    extern __shared__ float sm[];   // [9 taps][3][Cout]
+    const float s = wscale ? __ldg(wscale) : 1.f;
+    for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
+        const int co = i % Cout;
+        const int c = (i / Cout) % 3;
+        const int tap = i / (3 * Cout);
+        sm[i] = __ldg(w + (co * 3 + c) * 9 + tap) * s;
+    }
+    __syncthreads();
+    const long P = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long total = static_cast<long>(N) * H * W;
+    if (P >= total) return;
+    const int wq = static_cast<int>(P % W);
+    const int hq = static_cast<int>((P / W) % H);
+    const long n = P / (static_cast<long>(W) * H);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int kh = 0; kh < 3; ++kh) {
+        const int hh = hq - kh + 1;
+        if (hh < 0 || hh >= H) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+            const int ww = wq - kw + 1;
+            if (ww < 0 || ww >= W) continue;
+            const float* dp = dy + ((n * H + hh) * W + ww) * Cout;
+            const float* w0 = sm + (kh * 3 + kw) * 3 * Cout;
+            for (int co = 0; co < Cout; co += 4) {
+                const float4 d = ldg4(dp + co);
+                const float4 u0 = *reinterpret_cast<const float4*>(w0 + co);
+                const float4 u1 = *reinterpret_cast<const float4*>(w0 + Cout + co);
+                const float4 u2 = *reinterpret_cast<const float4*>(w0 + 2 * Cout + co);
+                a0 += d.x * u0.x + d.y * u0.y + d.z * u0.z + d.w * u0.w;
+                a1 += d.x * u1.x + d.y * u1.y + d.z * u1.z + d.w * u1.w;
+                a2 += d.x * u2.x + d.y * u2.y + d.z * u2.z + d.w * u2.w;
+            }
+        }
+    }
+    const long HW = static_cast<long>(H) * W;
+    const long o = n * 3 * HW + static_cast<long>(hq) * W + wq;
+    dx[o] = a0 * (pre_scale ? __ldg(pre_scale + 0) : 1.f);
+    dx[o + HW] = a1 * (pre_scale ? __ldg(pre_scale + 1) : 1.f);
+    dx[o + 2 * HW] = a2 * (pre_scale ? __ldg(pre_scale + 2) : 1.f);
+}
+
+// ------------------------------------------------------------------------------------------------ Cin = 3 wgrad
+// dw[co][c][tap] += scale * sum_p dy[p][co] * x[p+tap][c];  block = Cout channel lanes x (256/Cout) pixel lanes
+__global__ void __launch_bounds__(256)
+conv3x3_c3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                        float scale, int N, int H, int W, int Cout, int pix_per_block) {
+    extern __shared__ float sm[];   // [lanes][Cout][27]
+    const int co = threadIdx.x % Cout;
+    const int pl = threadIdx.x / Cout;
+    const int lanes = blockDim.x / Cout;
+    const long total = static_cast<long>(N) * H * W;
+    const long p0 = static_cast<long>(blockIdx.x) * pix_per_block;
+    long p1 = p0 + pix_per_block;
+    if (p1 > total) p1 = total;
+    float acc[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+    const long HW = static_cast<long>(H) * W;
+    for (long P = p0 + pl; P < p1; P += lanes) {
+        const int wq = static_cast<int>(P % W);
+        const int hq = static_cast<int>((P / W) % H);
+        const long n = P / HW;
+        const float d = __ldg(dy + P * Cout + co);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* xp = x + (n * 3 + c) * HW;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int hh = hq + kh - 1, ww = wq + kw - 1;
+                    float v = 0.f;
+                    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(xp + static_cast<long>(hh) * W + ww);
+                    acc[c * 9 + kh * 3 + kw] += d * v;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 27; ++t) sm[(pl * Cout + co) * 27 + t] = acc[t];
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += sm[l * Cout * 27 + i];
+        atomicAdd(dw + i, s * scale);   // i = co*27 + (c*9+tap) = OIHW order
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ generator tail
+// forward: thread per pixel; weights [tap][ci] as float4 over the 4 output channels in shared memory
+__global__ void __launch_bounds__(128)
+gen_tail_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ wscale,
+                    const float* __restrict__ bias, float* __restrict__ rgbs, float* __restrict__ segm,
+                    float* __restrict__ t_out, int N, int H, int W, int Cin) {
+    extern __shared__ float4 sw4[];   // [9][Cin]
+    const float s = wscale ? __ldg(wscale) : 1.f;
+    for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) {
+        const int ci = i % Cin, tap = i / Cin;
+        float4 v;
+        v.x = __ldg(w + (0 * Cin + ci) * 9 + tap) * s;
+        v.y = __ldg(w + (1 * Cin + ci) * 9 + tap) * s;
+        v.z = __ldg(w + (2 * Cin + ci) * 9 + tap) * s;
+        v.w = __ldg(w + (3 * Cin + ci) * 9 + tap) * s;
+        sw4[i] = v;
+    }
+    __syncthreads();
+    const long P = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long HW = static_cast<long>(H) * W;
+    if (P >= N * HW) return;
+    const int wq = static_cast<int>(P % W);
+    const int hq = static_cast<int>((P / W) % H);
+    const long n = P / HW;
+    float a0 = __ldg(bias + 0), a1 = __ldg(bias + 1), a2 = __ldg(bias + 2), a3 = __ldg(bias + 3);
+    for (int kh = 0; kh < 3; ++kh) {
+        const int hh = hq + kh - 1;
+        if (hh < 0 || hh >= H) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+            const int ww = wq + kw - 1;
+            if (ww < 0 || ww >= W) continue;
+            const float* xp = x + ((n * H + hh) * W + ww) * Cin;
+            const float4* wt = sw4 + (kh * 3 + kw) * Cin;
+#pragma unroll 4
+            for (int ci = 0; ci < Cin; ci += 4) {
+                const float4 v = ldg4(xp + ci);
+                const float4 u0 = wt[ci], u1 = wt[ci + 1], u2 = wt[ci + 2], u3 = wt[ci + 3];
+                a0 += v.x * u0.x + v.y * u1.x + v.z * u2.x + v.w * u3.x;
+                a1 += v.x * u0.y + v.y * u1.y + v.z * u2.y + v.w * u3.y;
+                a2 += v.x * u0.z + v.y * u1.z + v.z * u2.z + v.w * u3.z;
+                a3 += v.x * u0.w + v.y * u1.w + v.z * u2.w + v.w * u3.w;
+            }
+        }
+    }
+    const float t0 = tanhf(a0), t1 = tanhf(a1), t2 = tanhf(a2), t3 = tanhf(a3);
+    *reinterpret_cast<float4*>(t_out + P * 4) = make_float4(t0, t1, t2, t3);
+    // generators/vector_pose_unsupervised_segmentation_noBottleneck.py:170-181
+    const float sg = t3 * 0.5f + 0.5f;
+    const long hw = static_cast<long>(hq) * W + wq;
+    rgbs[(n * 3 + 0) * HW + hw] = (t0 * 0.75f + 0.5f) * sg;
+    rgbs[(n * 3 + 1) * HW + hw] = (t1 * 0.75f + 0.5f) * sg;
+    rgbs[(n * 3 + 2) * HW + hw] = (t2 * 0.75f + 0.5f) * sg;
+    segm[n * HW + hw] = sg;
+}
+
+// da = d(loss)/d(pre-tanh) from d(fake_rgbs), d(fake_segm)
+__global__ void gen_tail_bwd_act_kernel(const float* __restrict__ t, const float* __restrict__ d_rgbs,
+                                        const float* __restrict__ d_segm, float* __restrict__ da, long NP, long HW) {
+    const long P = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (P >= NP) return;
+    const long n = P / HW, hw = P - n * HW;
+    const float4 tv = ldg4(t + P * 4);
+    const float sg = tv.w * 0.5f + 0.5f;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, gs = 0.f;
+    if (d_rgbs) {
+        g0 = __ldg(d_rgbs + (n * 3 + 0) * HW + hw);
+        g1 = __ldg(d_rgbs + (n * 3 + 1) * HW + hw);
+        g2 = __ldg(d_rgbs + (n * 3 + 2) * HW + hw);
+    }
+    if (d_segm) gs = __ldg(d_segm + n * HW + hw);
+    const float r0 = tv.x * 0.75f + 0.5f, r1 = tv.y * 0.75f + 0.5f, r2 = tv.z * 0.75f + 0.5f;
+    const float dt0 = 0.75f * sg * g0, dt1 = 0.75f * sg * g1, dt2 = 0.75f * sg * g2;
+    const float dt3 = 0.5f * (r0 * g0 + r1 * g1 + r2 * g2 + gs);
+    float4 o;
+    o.x = (1.f - tv.x * tv.x) * dt0;
+    o.y = (1.f - tv.y * tv.y) * dt1;
+    o.z = (1.f - tv.z * tv.z) * dt2;
+    o.w = (1.f - tv.w * tv.w) * dt3;
+    *reinterpret_cast<float4*>(da + P * 4) = o;
+}
+
+// dx[p][ci] = sum_tap sum_j da[p - off(tap)][j] * w[j][ci][tap];   thread = (pixel, 16-channel group)
+__global__ void __launch_bounds__(256)
+gen_tail_bwd_data_kernel(const float* __restrict__ da, const float* __restrict__ w, const float* __restrict__ wscale,
+                         float* __restrict__ dx, int N, int H, int W, int Cin) {
+    extern __shared__ float4 sw4[];   // [9][Cin] float4 over j
+    const float s = wscale ? __ldg(wscale) : 1.f;
+    for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) {
+        const int ci = i % Cin, tap = i / Cin;
+        float4 v;
+        v.x = __ldg(w + (0 * Cin + ci) * 9 + tap) * s;
+        v.y = __ldg(w + (1 * Cin + ci) * 9 + tap) * s;
+        v.z = __ldg(w + (2 * Cin + ci) * 9 + tap) * s;
+        v.w = __ldg(w + (3 * Cin + ci) * 9 + tap) * s;
+        sw4[i] = v;
+    }
+    __syncthreads();
+    const int groups = Cin >> 4;
+    const int ppb = blockDim.x / groups;
+    const int g = threadIdx.x / ppb;
+    const int pl = threadIdx.x - g * ppb;
+    const long P = static_cast<long>(blockIdx.x) * ppb + pl;
+    const long HW = static_cast<long>(H) * W;
+    if (P >= N * HW) return;
+    const int wq = static_cast<int>(P % W);
+    const int hq = static_cast<int>((P / W) % H);
+    const long n = P / HW;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int kh = 0; kh < 3; ++kh) {
+        const int hh = hq - kh + 1;
+        if (hh < 0 || hh >= H) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+            const int ww = wq - kw + 1;
+            if (ww < 0 || ww >= W) continue;
+            const float4 d = ldg4(da + ((n * H + hh) * W + ww) * 4);
+            const float4* wt = sw4 + (kh * 3 + kw) * Cin + g * 16;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 u = wt[j];
+                acc[j] += d.x * u.x + d.y * u.y + d.z * u.z + d.w * u.w;
+            }
+        }
+    }
+    float* o = dx + P * Cin + g * 16;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(o + q * 4) = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+}
+
+// dw[j][ci][tap] += sum_p da[p][j] * x[p+off(tap)][ci];  db[j] += sum_p da[p][j]
+// block = Cin channel lanes x (256/Cin) pixel lanes
+__global__ void __launch_bounds__(256)
+gen_tail_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ da, float* __restrict__ dw,
+                           float* __restrict__ db, int N, int H, int W, int Cin, int pix_per_block) {
+    extern __shared__ float sm[];   // [lanes][Cin][36] + [lanes][4]
+    const int ci = threadIdx.x % Cin;
+    const int pl = threadIdx.x / Cin;
+    const int lanes = blockDim.x / Cin;
+    const long HW = static_cast<long>(H) * W;
+    const long total = N * HW;
+    const long p0 = static_cast<long>(blockIdx.x) * pix_per_block;
+    long p1 = p0 + pix_per_block;
+    if (p1 > total) p1 = total;
+    float acc[36];
+#pragma unroll
+    for (int t = 0; t < 36; ++t) acc[t] = 0.f;
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long P = p0 + pl; P < p1; P += lanes) {
+        const int wq = static_cast<int>(P % W);
+        const int hq = static_cast<int>((P / W) % H);
+        const long n = P / HW;
+        const float4 d = ldg4(da + P * 4);
+        bsum[0] += d.x; bsum[1] += d.y; bsum[2] += d.z; bsum[3] += d.w;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int hh = hq + kh - 1, ww = wq + kw - 1;
+                float v = 0.f;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + ((n * H + hh) * W + ww) * Cin + ci);
+                const int tap = kh * 3 + kw;
+                acc[0 * 9 + tap] += d.x * v;
+                acc[1 * 9 + tap] += d.y * v;
+                acc[2 * 9 + tap] += d.z * v;
+                acc[3 * 9 + tap] += d.w * v;
+            }
+        }
+    }
+    float* sacc = sm;
+    float* sbs = sm + static_cast<size_t>(lanes) * Cin * 36;
+#pragma unroll
+    for (int t = 0; t < 36; ++t) sacc[(static_cast<size_t>(pl) * Cin + ci) * 36 + t] = acc[t];
+    if (ci == 0) { sbs[pl * 4 + 0] = bsum[0]; sbs[pl * 4 + 1] = bsum[1]; sbs[pl * 4 + 2] = bsum[2]; sbs[pl * 4 + 3] = bsum[3]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cin * 36; i += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += sacc[static_cast<size_t>(l) * Cin * 36 + i];
+        const int c = i / 36, r = i - c * 36;       // r = j*9 + tap
+        const int j = r / 9, tap = r - j * 9;
+        atomicAdd(dw + (static_cast<size_t>(j) * Cin + c) * 9 + tap, s);
+    }
+    if (threadIdx.x < 4) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += sbs[l * 4 + threadIdx.x];
+        atomicAdd(db + threadIdx.x, s);
+    }
+}
+
+}  // namespace b200lp
+
+using namespace b200lp;
+
+extern "C" int32_t b200lp_conv3x3_c3_fwd(const float* x_nchw, const float* w_oihw, const float* wscale,
+                                         const float* bias, const float* pre_scale, const float* pre_shift,
+                                         float* y_nhwc, int32_t N, int32_t H, int32_t W, int32_t Cout, int32_t relu,
+                                         int32_t round_tf32, void* stream) {
+    B200LP_REQUIRE(x_nchw && w_oihw && y_nhwc, "conv3x3_c3_fwd: null pointer");
+    B200LP_REQUIRE(N > 0 && H > 0 && W > 0 && Cout % 16 == 0 && Cout >= 16 && Cout <= 128 && (256 % (Cout / 16)) == 0,
+                   "conv3x3_c3_fwd: bad shape (Cout=%d)", Cout);
+    const int groups = Cout / 16;
+    const int ppb = 256 / groups;
+    const long total = static_cast<long>(N) * H * W;
+    const int blocks = static_cast<int>((total + ppb - 1) / ppb);
+    conv3x3_c3_fwd_kernel<<<blocks, 256, (27 * Cout + Cout) * 4, as_stream(stream)>>>(
+        x_nchw, w_oihw, wscale, bias, pre_scale, pre_shift, y_nhwc, N, H, W, Cout, relu, round_tf32);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_conv3x3_c3_dgrad(const float* dy_nhwc, const float* w_oihw, const float* wscale,
+                                           const float* pre_scale, float* dx_nchw, int32_t N, int32_t H, int32_t W,
+                                           int32_t Cout, void* stream) {
+    B200LP_REQUIRE(dy_nhwc && w_oihw && dx_nchw && N > 0 && H > 0 && W > 0 && Cout % 4 == 0 && Cout <= 256,
+                   "conv3x3_c3_dgrad: bad args");
+    const long total = static_cast<long>(N) * H * W;
+    const int blocks = static_cast<int>((total + 255) / 256);
+    conv3x3_c3_dgrad_kernel<<<blocks, 256, 27 * Cout * 4, as_stream(stream)>>>(dy_nhwc, w_oihw, wscale, pre_scale,
+                                                                               dx_nchw, N, H, W, Cout);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_conv3x3_c3_wgrad(const float* x_nchw, const float* dy_nhwc, float* dw_oihw,
+                                           float wscale_host, int32_t N, int32_t H, int32_t W, int32_t Cout,
+                                           void* stream) {
+    B200LP_REQUIRE(x_nchw && dy_nhwc && dw_oihw && N > 0 && H > 0 && W > 0 && Cout > 0 && 256 % Cout == 0,
+                   "conv3x3_c3_wgrad: bad args (Cout=%d must divide 256)", Cout);
+    cudaStream_t s = as_stream(stream);
+    B200LP_CHECK_CUDA(cudaMemsetAsync(dw_oihw, 0, static_cast<size_t>(Cout) * 27 * 4, s));
+    const long total = static_cast<long>(N) * H * W;
+    const int lanes = 256 / Cout;
+    int ppb = 1024;
+    if (ppb < lanes) ppb = lanes;
+    const int blocks = static_cast<int>((total + ppb - 1) / ppb);
+    conv3x3_c3_wgrad_kernel<<<blocks, 256, static_cast<size_t>(lanes) * Cout * 27 * 4, s>>>(
+        x_nchw, dy_nhwc, dw_oihw, wscale_host, N, H, W, Cout, ppb);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_gen_tail_fwd(const float* x_nhwc, const float* w_oihw, const float* wscale,
+                                       const float* bias, float* fake_rgbs_nchw, float* fake_segm_nchw, float* t_out,
+                                       int32_t N, int32_t H, int32_t W, int32_t Cin, void* stream) {
+    B200LP_REQUIRE(x_nhwc && w_oihw && bias && fake_rgbs_nchw && fake_segm_nchw && t_out, "gen_tail_fwd: null pointer");
+    B200LP_REQUIRE(N > 0 && H > 0 && W > 0 && Cin % 4 == 0 && Cin <= 512, "gen_tail_fwd: bad shape");
+    const long total = static_cast<long>(N) * H * W;
+    const int blocks = static_cast<int>((total + 127) / 128);
+    gen_tail_fwd_kernel<<<blocks, 128, 9 * Cin * 16, as_stream(stream)>>>(x_nhwc, w_oihw, wscale, bias, fake_rgbs_nchw,
+                                                                          fake_segm_nchw, t_out, N, H, W, Cin);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_gen_tail_bwd_act(const float* t, const float* d_rgbs, const float* d_segm, float* da,
+                                           int32_t N, int32_t H, int32_t W, void* stream) {
+    B200LP_REQUIRE(t && da && N > 0 && H > 0 && W > 0, "gen_tail_bwd_act: bad args");
+    const long HW = static_cast<long>(H) * W;
+    const long NP = N * HW;
+    gen_tail_bwd_act_kernel<<<static_cast<int>((NP + 255) / 256), 256, 0, as_stream(stream)>>>(t, d_rgbs, d_segm, da,
+                                                                                               NP, HW);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_gen_tail_bwd_data(const float* da, const float* w_oihw, const float* wscale, float* dx_nhwc,
+                                            int32_t N, int32_t H, int32_t W, int32_t Cin, void* stream) {
+    B200LP_REQUIRE(da && w_oihw && dx_nhwc && N > 0 && H > 0 && W > 0 && Cin % 16 == 0 && Cin <= 128 &&
+                       256 % (Cin / 16) == 0,
+                   "gen_tail_bwd_data: bad args");
+    const int groups = Cin / 16;
+    const int ppb = 256 / groups;
+    const long total = static_cast<long>(N) * H * W;
+    const int blocks = static_cast<int>((total + ppb - 1) / ppb);
+    gen_tail_bwd_data_kernel<<<blocks, 256, 9 * Cin * 16, as_stream(stream)>>>(da, w_oihw, wscale, dx_nhwc, N, H, W,
+                                                                               Cin);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_gen_tail_bwd_weight(const float* x_nhwc, const float* da, float* dw_oihw, float* dbias,
+                                              int32_t N, int32_t H, int32_t W, int32_t Cin, void* stream) {
+    B200LP_REQUIRE(x_nhwc && da && dw_oihw && dbias && N > 0 && H > 0 && W > 0 && Cin > 0 && 256 % Cin == 0,
+                   "gen_tail_bwd_weight: bad args (Cin=%d must divide 256)", Cin);
+    cudaStream_t s = as_stream(stream);
+    B200LP_CHECK_CUDA(cudaMemsetAsync(dw_oihw, 0, static_cast<size_t>(4) * Cin * 9 * 4, s));
+    B200LP_CHECK_CUDA(cudaMemsetAsync(dbias, 0, 16, s));
+    const long total = static_cast<long>(N) * H * W;
+    const int lanes = 256 / Cin;
+    int ppb = 1024;
+    const int blocks = static_cast<int>((total + ppb - 1) / ppb);
+    const size_t smem = (static_cast<size_t>(lanes) * Cin * 36 + lanes * 4) * 4;
+    gen_tail_bwd_weight_kernel<<<blocks, 256, smem, s>>>(x_nhwc, da, dw_oihw, dbias, N, H, W, Cin, ppb);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}

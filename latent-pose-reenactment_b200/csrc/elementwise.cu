@@ -1,0 +1,700 @@
+// HBM-bound kernels of the hot path: instance-norm statistics, AdaIN+ReLU(+2x upsample) apply and backward,
+// ReLU / pooling / upsample-backward, L1 feature-loss reductions, layout conversion, bias gradients.
+// All activations are NHWC fp32; every kernel streams 16-byte vectors along the channel axis (coalesced),
+// keeps per-(n,c) scalars in registers, and sizes its grid as a multiple of the 148 SMs.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200lp {
+
+constexpr int kEwThreads = 256;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Instance-norm statistics.  x[N][HW][C];  pass 1: each block reduces a chunk of pixels for all channels to
+// (count, mean, M2) partials using shifted sums (no E[x^2]-E[x]^2 cancellation); pass 2 merges partials with
+// Chan's formula in fp64 and writes mean / rstd.
+// Replaces nn.InstanceNorm2d statistics (generators/common/blocks.py:12,19).
+// ---------------------------------------------------------------------------------------------------------------
+struct Moments { float cnt, mean, m2; };
+
+__device__ __forceinline__ Moments merge(Moments a, Moments b) {
+    if (b.cnt == 0.f) return a;
+    if (a.cnt == 0.f) return b;
+    Moments r;
+    r.cnt = a.cnt + b.cnt;
+    const float d = b.mean - a.mean;
+    const float f = b.cnt / r.cnt;
+    r.mean = a.mean + d * f;
+    r.m2 = a.m2 + b.m2 + d * d * a.cnt * f;
+    return r;
+}
+
+// grid (chunks, N); block 256 = (C/4 lanes) x (256/(C/4) pixel rows)   [C/4 <= 256]
+__global__ void in_stats_partial_kernel(const float* __restrict__ x, float* __restrict__ part, int HW, int C,
+                                        int pix_per_chunk) {
+    extern __shared__ float sm[];  // [rows][C][3]
+    const int cq = C >> 2;
+    const int lane_c = threadIdx.x % cq;
+    const int row = threadIdx.x / cq;
+    const int rows = blockDim.x / cq;
+    const int n = blockIdx.y;
+    const int p0 = blockIdx.x * pix_per_chunk;
+    int p1 = p0 + pix_per_chunk;
+    if (p1 > HW) p1 = HW;
+    const float* base = x + (static_cast<size_t>(n) * HW) * C + lane_c * 4;
+
+    float4 k = make_float4(0, 0, 0, 0), s = k, q = k;
+    float cnt = 0.f;
+    if (row < rows) {
+        int p = p0 + row;
+        if (p < p1) {
+            k = ld4(base + static_cast<size_t>(p) * C);
+            cnt = 1.f;
+            p += rows;
+            for (; p < p1; p += rows) {
+                const float4 v = ld4(base + static_cast<size_t>(p) * C);
+                const float dx = v.x - k.x, dy = v.y - k.y, dz = v.z - k.z, dw = v.w - k.w;
+                s.x += dx; s.y += dy; s.z += dz; s.w += dw;
+                q.x += dx * dx; q.y += dy * dy; q.z += dz * dz; q.w += dw * dw;
+                cnt += 1.f;
+            }
+        }
+    }
+    // to (cnt, mean, M2)
+    float mean[4], m2[4];
+    const float inv = cnt > 0.f ? 1.f / cnt : 0.f;
+    mean[0] = k.x + s.x * inv; m2[0] = q.x - s.x * s.x * inv;
+    mean[1] = k.y + s.y * inv; m2[1] = q.y - s.y * s.y * inv;
+    mean[2] = k.z + s.z * inv; m2[2] = q.z - s.z * s.z * inv;
+    mean[3] = k.w + s.w * inv; m2[3] = q.w - s.w * s.w * inv;
+    if (row < rows) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float* d = sm + (static_cast<size_t>(row) * C + lane_c * 4 + j) * 3;
+            d[0] = cnt; d[1] = mean[j]; d[2] = m2[j] > 0.f ? m2[j] : 0.f;
+        }
+    }
+    __syncthreads();
+    // merge rows: one thread per channel
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        Moments acc{0.f, 0.f, 0.f};
+        for (int r = 0; r < rows; ++r) {
+            const float* d = sm + (static_cast<size_t>(r) * C + c) * 3;
+            acc = merge(acc, Moments{d[0], d[1], d[2]});
+        }
+        float* o = part + ((static_cast<size_t>(n) * gridDim.x + blockIdx.x) * C + c) * 3;
+        o[0] = acc.cnt; o[1] = acc.mean; o[2] = acc.m2;
+    }
+}
+
+__global__ void in_stats_final_kernel(const float* __restrict__ part, float* __restrict__ mean,
+                                      float* __restrict__ rstd, int chunks, int C, int NC, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // n*C + c
+    if (i >= NC) return;
+    const int n = i / C, c = i - n * C;
+    double cnt = 0.0, mu = 0.0, m2 = 0.0;
+    for (int k = 0; k < chunks; ++k) {
+        const float* d = part + ((static_cast<size_t>(n) * chunks + k) * C + c) * 3;
+        const double bc = d[0], bm = d[1], b2 = d[2];
+        if (bc == 0.0) continue;
+        const double tot = cnt + bc;
+        const double dl = bm - mu;
+        mu += dl * (bc / tot);
+        m2 += b2 + dl * dl * cnt * (bc / tot);
+        cnt = tot;
+    }
+    const double var = cnt > 0.0 ? m2 / cnt : 0.0;   // biased variance, as nn.InstanceNorm2d
+    mean[i] = static_cast<float>(mu);
+    rstd[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+static void stats_plan(int N, int HW, int C, int* chunks, int* pix_per_chunk) {
+    const int rows = kEwThreads / (C / 4) > 0 ? kEwThreads / (C / 4) : 1;
+    int want = (4 * 148 + N - 1) / N;         // ~4 blocks per SM over the whole grid
+    int max_chunks = HW / (rows * 4);         // at least 4 pixels per thread
+    if (max_chunks < 1) max_chunks = 1;
+    if (want > max_chunks) want = max_chunks;
+    if (want < 1) want = 1;
+    *pix_per_chunk = (HW + want - 1) / want;
+    *chunks = (HW + *pix_per_chunk - 1) / *pix_per_chunk;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// AdaIN + ReLU (+ nearest 2x upsample) apply:  y = [tf32]( relu( (x-mean)*rstd*gamma + beta ) )
+// Replaces blocks.py:18-26 (AdaptiveNorm2d.forward), :73 (ReLU) and :75 (Upsample).
+// grid (chunks, N), block = (C/4 lanes) x rows
+// ---------------------------------------------------------------------------------------------------------------
+template <bool UP, bool ROUND>
+__global__ void adain_relu_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                  const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, long affine_stride, float* __restrict__ y, int H,
+                                  int W, int C, int pix_per_chunk) {
+    const int cq = C >> 2;
+    const int lane_c = threadIdx.x % cq;
+    const int row = threadIdx.x / cq;
+    const int rows = blockDim.x / cq;
+    if (row >= rows) return;
+    const int n = blockIdx.y;
+    const int HW = H * W;
+    const int p0 = blockIdx.x * pix_per_chunk;
+    int p1 = p0 + pix_per_chunk;
+    if (p1 > HW) p1 = HW;
+    const int c = lane_c * 4;
+    const float4 mu = ld4(mean + static_cast<size_t>(n) * C + c);
+    const float4 rs = ld4(rstd + static_cast<size_t>(n) * C + c);
+    float4 g, b;
+    {
+        const float* gp = gamma + n * affine_stride + c;
+        const float* bp = beta + n * affine_stride + c;
+        g = make_float4(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), __ldg(gp + 3));
+        b = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
+    }
+    const float* xb = x + static_cast<size_t>(n) * HW * C + c;
+    for (int p = p0 + row; p < p1; p += rows) {
+        const float4 v = ld4(xb + static_cast<size_t>(p) * C);
+        float4 o;
+        // same operation order as the reference: normalise, then scale, then shift
+        o.x = fmaxf(((v.x - mu.x) * rs.x) * g.x + b.x, 0.f);
+        o.y = fmaxf(((v.y - mu.y) * rs.y) * g.y + b.y, 0.f);
+        o.z = fmaxf(((v.z - mu.z) * rs.z) * g.z + b.z, 0.f);
+        o.w = fmaxf(((v.w - mu.w) * rs.w) * g.w + b.w, 0.f);
+        if (ROUND) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        if (!UP) {
+            st4(y + (static_cast<size_t>(n) * HW + p) * C + c, o);
+        } else {
+            const int h = p / W, w = p - h * W;
+            float* yb = y + ((static_cast<size_t>(n) * (2 * H) + 2 * h) * (2 * W) + 2 * w) * C + c;
+            st4(yb, o);
+            st4(yb + C, o);
+            st4(yb + static_cast<size_t>(2 * W) * C, o);
+            st4(yb + static_cast<size_t>(2 * W) * C + C, o);
+        }
+    }
+}
+
+// Backward pass 1: per-(n,c) partial sums of dz and dz*xhat, dz = dy_in * [z > 0], where dy_in is dy summed over
+// the 2x2 upsampled block when UP.  part[n][chunk][C][2]
+template <bool UP>
+__global__ void adain_bwd_partial_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                         const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, long affine_stride,
+                                         const float* __restrict__ dy, float* __restrict__ part, int H, int W, int C,
+                                         int pix_per_chunk) {
+    extern __shared__ float sm[];  // [rows][C][2]
+    const int cq = C >> 2;
+    const int lane_c = threadIdx.x % cq;
+    const int row = threadIdx.x / cq;
+    const int rows = blockDim.x / cq;
+    const int n = blockIdx.y;
+    const int HW = H * W;
+    const int p0 = blockIdx.x * pix_per_chunk;
+    int p1 = p0 + pix_per_chunk;
+    if (p1 > HW) p1 = HW;
+    const int c = lane_c * 4;
+    float sb[4] = {0, 0, 0, 0}, sg[4] = {0, 0, 0, 0};
+    if (row < rows) {
+        const float4 mu = ld4(mean + static_cast<size_t>(n) * C + c);
+        const float4 rs = ld4(rstd + static_cast<size_t>(n) * C + c);
+        const float* gp = gamma + n * affine_stride + c;
+        const float* bp = beta + n * affine_stride + c;
+        const float g[4] = {__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), __ldg(gp + 3)};
+        const float b[4] = {__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3)};
+        const float m_[4] = {mu.x, mu.y, mu.z, mu.w};
+        const float r_[4] = {rs.x, rs.y, rs.z, rs.w};
+        const float* xb = x + static_cast<size_t>(n) * HW * C + c;
+        for (int p = p0 + row; p < p1; p += rows) {
+            const float4 v4 = ld4(xb + static_cast<size_t>(p) * C);
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+            float d[4];
+            if (!UP) {
+                const float4 d4 = ld4(dy + (static_cast<size_t>(n) * HW + p) * C + c);
+                d[0] = d4.x; d[1] = d4.y; d[2] = d4.z; d[3] = d4.w;
+            } else {
+                const int h = p / W, w = p - h * W;
+                const float* db = dy + ((static_cast<size_t>(n) * (2 * H) + 2 * h) * (2 * W) + 2 * w) * C + c;
+                const float4 a0 = ld4(db), a1 = ld4(db + C), a2 = ld4(db + static_cast<size_t>(2 * W) * C),
+                             a3 = ld4(db + static_cast<size_t>(2 * W) * C + C);
+                d[0] = (a0.x + a1.x) + (a2.x + a3.x);
+                d[1] = (a0.y + a1.y) + (a2.y + a3.y);
+                d[2] = (a0.z + a1.z) + (a2.z + a3.z);
+                d[3] = (a0.w + a1.w) + (a2.w + a3.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float xh = (v[j] - m_[j]) * r_[j];
+                const float z = xh * g[j] + b[j];
+                const float dz = z > 0.f ? d[j] : 0.f;
+                sb[j] += dz;
+                sg[j] += dz * xh;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sm[(static_cast<size_t>(row) * C + c + j) * 2 + 0] = sb[j];
+            sm[(static_cast<size_t>(row) * C + c + j) * 2 + 1] = sg[j];
+        }
+    }
+    __syncthreads();
+    for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+        float a = 0.f, g2 = 0.f;
+        for (int r = 0; r < rows; ++r) {
+            a += sm[(static_cast<size_t>(r) * C + cc) * 2 + 0];
+            g2 += sm[(static_cast<size_t>(r) * C + cc) * 2 + 1];
+        }
+        float* o = part + ((static_cast<size_t>(n) * gridDim.x + blockIdx.x) * C + cc) * 2;
+        o[0] = a; o[1] = g2;
+    }
+}
+
+__global__ void adain_bwd_final_kernel(const float* __restrict__ part, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int chunks, int C, int NC) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NC) return;
+    const int n = i / C, c = i - n * C;
+    double a = 0.0, g = 0.0;
+    for (int k = 0; k < chunks; ++k) {
+        const float* d = part + ((static_cast<size_t>(n) * chunks + k) * C + c) * 2;
+        a += d[0]; g += d[1];
+    }
+    dbeta[i] = static_cast<float>(a);
+    dgamma[i] = static_cast<float>(g);
+}
+
+// Backward pass 2: dx = rstd*gamma*(dz - dbeta/HW - xhat*dgamma/HW)
+template <bool UP>
+__global__ void adain_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, long affine_stride,
+                                       const float* __restrict__ dy, const float* __restrict__ dgamma,
+                                       const float* __restrict__ dbeta, float* __restrict__ dx, int H, int W, int C,
+                                       int pix_per_chunk) {
+    const int cq = C >> 2;
+    const int lane_c = threadIdx.x % cq;
+    const int row = threadIdx.x / cq;
+    const int rows = blockDim.x / cq;
+    if (row >= rows) return;
+    const int n = blockIdx.y;
+    const int HW = H * W;
+    const int p0 = blockIdx.x * pix_per_chunk;
+    int p1 = p0 + pix_per_chunk;
+    if (p1 > HW) p1 = HW;
+    const int c = lane_c * 4;
+    const float4 mu = ld4(mean + static_cast<size_t>(n) * C + c);
+    const float4 rs = ld4(rstd + static_cast<size_t>(n) * C + c);
+    const float4 dg4 = ld4(dgamma + static_cast<size_t>(n) * C + c);
+    const float4 db4 = ld4(dbeta + static_cast<size_t>(n) * C + c);
+    const float* gp = gamma + n * affine_stride + c;
+    const float* bp = beta + n * affine_stride + c;
+    const float g[4] = {__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), __ldg(gp + 3)};
+    const float b[4] = {__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3)};
+    const float m_[4] = {mu.x, mu.y, mu.z, mu.w};
+    const float r_[4] = {rs.x, rs.y, rs.z, rs.w};
+    const float inv = 1.f / static_cast<float>(HW);
+    const float mg[4] = {dg4.x * inv, dg4.y * inv, dg4.z * inv, dg4.w * inv};
+    const float mb[4] = {db4.x * inv, db4.y * inv, db4.z * inv, db4.w * inv};
+    const float* xb = x + static_cast<size_t>(n) * HW * C + c;
+    for (int p = p0 + row; p < p1; p += rows) {
+        const float4 v4 = ld4(xb + static_cast<size_t>(p) * C);
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+        float d[4];
+        if (!UP) {
+            const float4 d4 = ld4(dy + (static_cast<size_t>(n) * HW + p) * C + c);
+            d[0] = d4.x; d[1] = d4.y; d[2] = d4.z; d[3] = d4.w;
+        } else {
+            const int h = p / W, w = p - h * W;
+            const float* dbp = dy + ((static_cast<size_t>(n) * (2 * H) + 2 * h) * (2 * W) + 2 * w) * C + c;
+            const float4 a0 = ld4(dbp), a1 = ld4(dbp + C), a2 = ld4(dbp + static_cast<size_t>(2 * W) * C),
+                         a3 = ld4(dbp + static_cast<size_t>(2 * W) * C + C);
+            d[0] = (a0.x + a1.x) + (a2.x + a3.x);
+            d[1] = (a0.y + a1.y) + (a2.y + a3.y);
+            d[2] = (a0.z + a1.z) + (a2.z + a3.z);
+            d[3] = (a0.w + a1.w) + (a2.w + a3.w);
+        }
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float xh = (v[j] - m_[j]) * r_[j];
+            const float z = xh * g[j] + b[j];
+            const float dz = z > 0.f ? d[j] : 0.f;
+            o[j] = r_[j] * g[j] * (dz - mb[j] - xh * mg[j]);
+        }
+        st4(dx + (static_cast<size_t>(n) * HW + p) * C + c, make_float4(o[0], o[1], o[2], o[3]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// simple streaming kernels
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void relu_round_kernel(const float4* __restrict__ x, float4* __restrict__ y, long n4) {
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        float4 v = __ldg(x + i);
+        v.x = round_tf32(fmaxf(v.x, 0.f)); v.y = round_tf32(fmaxf(v.y, 0.f));
+        v.z = round_tf32(fmaxf(v.z, 0.f)); v.w = round_tf32(fmaxf(v.w, 0.f));
+        y[i] = v;
+    }
+}
+__global__ void relu_bwd_kernel(const float4* __restrict__ y, const float4* __restrict__ dy, float4* __restrict__ dx,
+                                long n4) {
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const float4 m = __ldg(y + i);
+        float4 d = __ldg(dy + i);
+        d.x = m.x > 0.f ? d.x : 0.f; d.y = m.y > 0.f ? d.y : 0.f;
+        d.z = m.z > 0.f ? d.z : 0.f; d.w = m.w > 0.f ? d.w : 0.f;
+        dx[i] = d;
+    }
+}
+
+// y[n,h,w,:] = scale * (sum of the 2x2 block of x) (+ addend);  x is [N,2H,2W,C], y [N,H,W,C]
+template <bool ROUND>
+__global__ void pool2_kernel(const float* __restrict__ x, const float* __restrict__ addend, float* __restrict__ y,
+                             int H, int W, int C, long total4, float scale) {
+    const int cq = C >> 2;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total4;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % cq) * 4;
+        long p = i / cq;
+        const int w = static_cast<int>(p % W);
+        p /= W;
+        const int h = static_cast<int>(p % H);
+        const long n = p / H;
+        const float* xb = x + ((n * (2 * H) + 2 * h) * (2L * W) + 2 * w) * C + c;
+        const float4 a0 = ld4(xb), a1 = ld4(xb + C), a2 = ld4(xb + 2L * W * C), a3 = ld4(xb + 2L * W * C + C);
+        float4 o;
+        o.x = ((a0.x + a1.x) + (a2.x + a3.x)) * scale;
+        o.y = ((a0.y + a1.y) + (a2.y + a3.y)) * scale;
+        o.z = ((a0.z + a1.z) + (a2.z + a3.z)) * scale;
+        o.w = ((a0.w + a1.w) + (a2.w + a3.w)) * scale;
+        if (addend) {
+            const float4 ad = ld4(addend + i * 4);
+            o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+        }
+        if (ROUND) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        st4(y + i * 4, o);
+    }
+}
+
+// dx[n,h,w,:] = scale * dy[n,h/2,w/2,:]   dx is [N,2H,2W,C], dy [N,H,W,C]
+__global__ void unpool2_kernel(const float* __restrict__ dy, float* __restrict__ dx, int H, int W, int C,
+                               long total4, float scale) {
+    const int cq = C >> 2;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total4;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % cq) * 4;
+        long p = i / cq;
+        const int w = static_cast<int>(p % W);
+        p /= W;
+        const int h = static_cast<int>(p % H);
+        const long n = p / H;
+        float4 v = ld4(dy + i * 4);
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+        float* db = dx + ((n * (2 * H) + 2 * h) * (2L * W) + 2 * w) * C + c;
+        st4(db, v); st4(db + C, v); st4(db + 2L * W * C, v); st4(db + 2L * W * C + C, v);
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// out[0] += scale * sum |a-b|
+__global__ void l1_sum_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float* __restrict__ out,
+                              long n4, float scale) {
+    float acc = 0.f;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const float4 u = __ldg(a + i), v = __ldg(b + i);
+        acc += (fabsf(u.x - v.x) + fabsf(u.y - v.y)) + (fabsf(u.z - v.z) + fabsf(u.w - v.w));
+    }
+    __shared__ float ws[kEwThreads / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < kEwThreads / 32 ? ws[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(out, v * scale);
+    }
+}
+template <bool ACC>
+__global__ void l1_bwd_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
+                              const float* __restrict__ gscale, float scale2, float4* __restrict__ da, long n4) {
+    const float g = (gscale ? __ldg(gscale) : 1.f) * scale2;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const float4 u = __ldg(a + i), v = __ldg(b + i);
+        float4 d;
+        d.x = (u.x > v.x ? g : (u.x < v.x ? -g : 0.f));
+        d.y = (u.y > v.y ? g : (u.y < v.y ? -g : 0.f));
+        d.z = (u.z > v.z ? g : (u.z < v.z ? -g : 0.f));
+        d.w = (u.w > v.w ? g : (u.w < v.w ? -g : 0.f));
+        if (ACC) {
+            const float4 o = da[i];
+            d.x += o.x; d.y += o.y; d.z += o.z; d.w += o.w;
+        }
+        da[i] = d;
+    }
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, long total) {
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        const long p = i / C;             // n*HW + hw
+        const long n = p / HW;
+        const long hw = p - n * HW;
+        y[i] = __ldg(x + (n * C + c) * HW + hw);
+    }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, long total) {
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const long hw = i % HW;
+        const long nc = i / HW;
+        const int c = static_cast<int>(nc % C);
+        const long n = nc / C;
+        y[i] = __ldg(x + (n * HW + hw) * C + c);
+    }
+}
+
+// db[c] += sum over pixels of dy[p][c]   (db zeroed by the caller);  block = (C/4 lanes) x rows
+__global__ void bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, long pixels, int C,
+                                 long pix_per_block) {
+    extern __shared__ float sm[];  // [rows][C]
+    const int cq = C >> 2;
+    const int lane_c = threadIdx.x % cq;
+    const int row = threadIdx.x / cq;
+    const int rows = blockDim.x / cq;
+    const long p0 = blockIdx.x * pix_per_block;
+    long p1 = p0 + pix_per_block;
+    if (p1 > pixels) p1 = pixels;
+    float4 acc = make_float4(0, 0, 0, 0);
+    if (row < rows) {
+        for (long p = p0 + row; p < p1; p += rows) {
+            const float4 v = ld4(dy + p * C + lane_c * 4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        st4(sm + static_cast<size_t>(row) * C + lane_c * 4, acc);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r) s += sm[static_cast<size_t>(r) * C + c];
+        atomicAdd(db + c, s);
+    }
+}
+
+static int grid_for(long work_items, int threads) {
+    long b = (work_items + threads - 1) / threads;
+    const long cap = 148L * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<int>(b);
+}
+
+}  // namespace b200lp
+
+using namespace b200lp;
+
+extern "C" int64_t b200lp_in_stats_workspace(int32_t N, int32_t HW, int32_t C) {
+    if (N <= 0 || HW <= 0 || C <= 0 || C % 4 || C / 4 > kEwThreads) return B200LP_EINVAL;
+    int chunks, ppc;
+    stats_plan(N, HW, C, &chunks, &ppc);
+    return static_cast<int64_t>(N) * chunks * C * 3 * 4;
+}
+
+extern "C" int32_t b200lp_in_stats(const float* x, float* mean, float* rstd, float* workspace,
+                                   int64_t workspace_bytes, int32_t N, int32_t HW, int32_t C, float eps,
+                                   void* stream) {
+    B200LP_REQUIRE(x && mean && rstd && workspace, "in_stats: null pointer");
+    B200LP_REQUIRE(N > 0 && HW > 0 && C > 0 && C % 4 == 0 && C / 4 <= kEwThreads, "in_stats: bad shape N=%d HW=%d C=%d",
+                   N, HW, C);
+    int chunks, ppc;
+    stats_plan(N, HW, C, &chunks, &ppc);
+    B200LP_REQUIRE(workspace_bytes >= static_cast<int64_t>(N) * chunks * C * 12, "in_stats: workspace too small");
+    const int rows = kEwThreads / (C / 4);
+    const size_t smem = static_cast<size_t>(rows) * C * 3 * 4;
+    cudaStream_t s = as_stream(stream);
+    in_stats_partial_kernel<<<dim3(chunks, N), kEwThreads, smem, s>>>(x, workspace, HW, C, ppc);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    const int NC = N * C;
+    in_stats_final_kernel<<<(NC + 127) / 128, 128, 0, s>>>(workspace, mean, rstd, chunks, C, NC, eps);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_adain_relu(const float* x, const float* mean, const float* rstd, const float* gamma,
+                                     const float* beta, int64_t affine_stride, float* y, int32_t N, int32_t H,
+                                     int32_t W, int32_t C, int32_t upsample2, int32_t round_tf32, void* stream) {
+    B200LP_REQUIRE(x && mean && rstd && gamma && beta && y, "adain_relu: null pointer");
+    B200LP_REQUIRE(N > 0 && H > 0 && W > 0 && C % 4 == 0 && C / 4 <= kEwThreads, "adain_relu: bad shape");
+    int chunks, ppc;
+    stats_plan(N, H * W, C, &chunks, &ppc);
+    dim3 grid(chunks, N);
+    cudaStream_t s = as_stream(stream);
+#define LAUNCH(UP, RD)                                                                                              \
+    adain_relu_kernel<UP, RD><<<grid, kEwThreads, 0, s>>>(x, mean, rstd, gamma, beta, affine_stride, y, H, W, C, ppc)
+    if (upsample2) { if (round_tf32) LAUNCH(true, true); else LAUNCH(true, false); }
+    else { if (round_tf32) LAUNCH(false, true); else LAUNCH(false, false); }
+#undef LAUNCH
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+extern "C" int64_t b200lp_adain_relu_bwd_workspace(int32_t N, int32_t HW, int32_t C) {
+    if (N <= 0 || HW <= 0 || C <= 0 || C % 4 || C / 4 > kEwThreads) return B200LP_EINVAL;
+    int chunks, ppc;
+    stats_plan(N, HW, C, &chunks, &ppc);
+    return static_cast<int64_t>(N) * chunks * C * 2 * 4;
+}
+
+extern "C" int32_t b200lp_adain_relu_bwd(const float* x, const float* mean, const float* rstd, const float* gamma,
+                                         const float* beta, int64_t affine_stride, const float* dy, float* dx,
+                                         float* dgamma, float* dbeta, float* workspace, int64_t workspace_bytes,
+                                         int32_t N, int32_t H, int32_t W, int32_t C, int32_t upsample2,
+                                         void* stream) {
+    B200LP_REQUIRE(x && mean && rstd && gamma && beta && dy && dx && dgamma && dbeta && workspace,
+                   "adain_relu_bwd: null pointer");
+    B200LP_REQUIRE(N > 0 && H > 0 && W > 0 && C % 4 == 0 && C / 4 <= kEwThreads, "adain_relu_bwd: bad shape");
+    int chunks, ppc;
+    stats_plan(N, H * W, C, &chunks, &ppc);
+    B200LP_REQUIRE(workspace_bytes >= static_cast<int64_t>(N) * chunks * C * 8, "adain_relu_bwd: workspace too small");
+    const int rows = kEwThreads / (C / 4);
+    const size_t smem = static_cast<size_t>(rows) * C * 2 * 4;
+    dim3 grid(chunks, N);
+    cudaStream_t s = as_stream(stream);
+    if (upsample2)
+        adain_bwd_partial_kernel<true><<<grid, kEwThreads, smem, s>>>(x, mean, rstd, gamma, beta, affine_stride, dy,
+                                                                      workspace, H, W, C, ppc);
+    else
+        adain_bwd_partial_kernel<false><<<grid, kEwThreads, smem, s>>>(x, mean, rstd, gamma, beta, affine_stride, dy,
+                                                                       workspace, H, W, C, ppc);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    const int NC = N * C;
+    adain_bwd_final_kernel<<<(NC + 127) / 128, 128, 0, s>>>(workspace, dgamma, dbeta, chunks, C, NC);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    if (upsample2)
+        adain_bwd_apply_kernel<true><<<grid, kEwThreads, 0, s>>>(x, mean, rstd, gamma, beta, affine_stride, dy, dgamma,
+                                                                 dbeta, dx, H, W, C, ppc);
+    else
+        adain_bwd_apply_kernel<false><<<grid, kEwThreads, 0, s>>>(x, mean, rstd, gamma, beta, affine_stride, dy,
+                                                                  dgamma, dbeta, dx, H, W, C, ppc);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_relu_round(const float* x, float* y, int64_t n, void* stream) {
+    B200LP_REQUIRE(x && y && n > 0 && n % 4 == 0, "relu_round: bad args");
+    relu_round_kernel<<<grid_for(n / 4, kEwThreads), kEwThreads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n / 4);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, void* stream) {
+    B200LP_REQUIRE(y && dy && dx && n > 0 && n % 4 == 0, "relu_bwd: bad args");
+    relu_bwd_kernel<<<grid_for(n / 4, kEwThreads), kEwThreads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dx), n / 4);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+// x [N,2H,2W,C] -> y [N,H,W,C]; (H, W are the OUTPUT dims)
+extern "C" int32_t b200lp_avgpool2(const float* x, const float* addend, float* y, int32_t N, int32_t H, int32_t W,
+                                   int32_t C, int32_t round_tf32, void* stream) {
+    B200LP_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C % 4 == 0, "avgpool2: bad args");
+    const long total4 = static_cast<long>(N) * H * W * (C / 4);
+    const int g = grid_for(total4, kEwThreads);
+    if (round_tf32)
+        pool2_kernel<true><<<g, kEwThreads, 0, as_stream(stream)>>>(x, addend, y, H, W, C, total4, 0.25f);
+    else
+        pool2_kernel<false><<<g, kEwThreads, 0, as_stream(stream)>>>(x, addend, y, H, W, C, total4, 0.25f);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+// dy [N,H,W,C] -> dx [N,2H,2W,C]
+extern "C" int32_t b200lp_avgpool2_bwd(const float* dy, float* dx, int32_t N, int32_t H, int32_t W, int32_t C,
+                                       void* stream) {
+    B200LP_REQUIRE(dy && dx && N > 0 && H > 0 && W > 0 && C % 4 == 0, "avgpool2_bwd: bad args");
+    const long total4 = static_cast<long>(N) * H * W * (C / 4);
+    unpool2_kernel<<<grid_for(total4, kEwThreads), kEwThreads, 0, as_stream(stream)>>>(dy, dx, H, W, C, total4, 0.25f);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+// dy [N,2H,2W,C] -> dx [N,H,W,C]  (H, W are the low-resolution dims)
+extern "C" int32_t b200lp_upsample2_bwd(const float* dy, float* dx, int32_t N, int32_t H, int32_t W, int32_t C,
+                                        void* stream) {
+    B200LP_REQUIRE(dy && dx && N > 0 && H > 0 && W > 0 && C % 4 == 0, "upsample2_bwd: bad args");
+    const long total4 = static_cast<long>(N) * H * W * (C / 4);
+    pool2_kernel<false><<<grid_for(total4, kEwThreads), kEwThreads, 0, as_stream(stream)>>>(dy, nullptr, dx, H, W, C,
+                                                                                          total4, 1.0f);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_l1_sum(const float* a, const float* b, float* out, int64_t n, float scale, void* stream) {
+    B200LP_REQUIRE(a && b && out && n > 0 && n % 4 == 0, "l1_sum: bad args");
+    int g = grid_for(n / 4, kEwThreads);
+    if (g > 148 * 4) g = 148 * 4;
+    l1_sum_kernel<<<g, kEwThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a),
+                                                          reinterpret_cast<const float4*>(b), out, n / 4, scale);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_l1_bwd(const float* a, const float* b, const float* gscale, float scale2, float* da,
+                                 int64_t n, int32_t accumulate, void* stream) {
+    B200LP_REQUIRE(a && b && da && n > 0 && n % 4 == 0, "l1_bwd: bad args");
+    const int g = grid_for(n / 4, kEwThreads);
+    if (accumulate)
+        l1_bwd_kernel<true><<<g, kEwThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a),
+                                                                     reinterpret_cast<const float4*>(b), gscale, scale2,
+                                                                     reinterpret_cast<float4*>(da), n / 4);
+    else
+        l1_bwd_kernel<false><<<g, kEwThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a),
+                                                                      reinterpret_cast<const float4*>(b), gscale,
+                                                                      scale2, reinterpret_cast<float4*>(da), n / 4);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_nchw_to_nhwc(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W,
+                                       void* stream) {
+    B200LP_REQUIRE(x && y && N > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad args");
+    const long total = static_cast<long>(N) * C * H * W;
+    nchw_to_nhwc_kernel<<<grid_for(total, kEwThreads), kEwThreads, 0, as_stream(stream)>>>(x, y, C, H * W, total);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_nhwc_to_nchw(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W,
+                                       void* stream) {
+    B200LP_REQUIRE(x && y && N > 0 && C > 0 && H > 0 && W > 0, "nhwc_to_nchw: bad args");
+    const long total = static_cast<long>(N) * C * H * W;
+    nhwc_to_nchw_kernel<<<grid_for(total, kEwThreads), kEwThreads, 0, as_stream(stream)>>>(x, y, C, H * W, total);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_bias_grad(const float* dy, float* db, int64_t pixels, int32_t C, void* stream) {
+    B200LP_REQUIRE(dy && db && pixels > 0 && C > 0 && C % 4 == 0 && C / 4 <= kEwThreads, "bias_grad: bad args");
+    cudaStream_t s = as_stream(stream);
+    B200LP_CHECK_CUDA(cudaMemsetAsync(db, 0, static_cast<size_t>(C) * 4, s));
+    const int rows = kEwThreads / (C / 4);
+    long blocks = 148 * 4;
+    long ppb = (pixels + blocks - 1) / blocks;
+    if (ppb < rows) ppb = rows;
+    blocks = (pixels + ppb - 1) / ppb;
+    bias_grad_kernel<<<static_cast<int>(blocks), kEwThreads, static_cast<size_t>(rows) * C * 4, s>>>(dy, db, pixels, C,
+                                                                                                   ppb);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    return B200LP_OK;
+}

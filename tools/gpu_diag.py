@@ -1,0 +1,358 @@
+"""Kernel-level diagnostics on a real B200: each check runs in its own subprocess (a trapped kernel poisons the CUDA
+context) and compares one C-ABI entry point with plain torch ops in fp64/fp32.  Writes gpurun_out/diag.json.
+
+    python tools/gpu_diag.py            # all checks
+    python tools/gpu_diag.py conv wgrad # name filters
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "latent-pose-reenactment_b200"))
+
+CHECKS = {}
+
+
+def check(fn):
+    CHECKS[fn.__name__] = fn
+    return fn
+
+
+def tf32_round(t):
+    """Round-to-nearest (ties away) fp32 -> tf32, like cvt.rna.tf32.f32."""
+    import torch
+    i = t.contiguous().view(torch.int32)
+    i = (i + 0x1000) & ~0x1FFF
+    return i.view(torch.float32)
+
+
+def _err(a, b):
+    import torch
+    a = a.double(); b = b.double()
+    d = (a - b).abs()
+    return {"max_abs": d.max().item(), "ref_max": b.abs().max().item(),
+            "rel": (d.max() / (b.abs().max() + 1e-30)).item(), "nan": bool(torch.isnan(a).any().item())}
+
+
+def _conv_case(N, H, W, Cin, Cout, k, block_n=0, bias=False, residual_mode=0, relu=False):
+    import torch
+    import torch.nn.functional as F
+    from b200lp import kernels as K
+    torch.manual_seed(0)
+    dev = "cuda"
+    x = tf32_round(torch.randn(N, Cin, H, W, device=dev))
+    w = torch.randn(Cout, Cin, k, k, device=dev) * 0.05
+    b = torch.randn(Cout, device=dev) if bias else None
+    wp = K.pack_conv_weight(w)
+    w_r = wp.view(Cout, k, k, Cin).permute(0, 3, 1, 2).contiguous()   # tf32-rounded weights back in OIHW
+    ref = F.conv2d(x.double(), w_r.double(), b.double() if bias else None, padding=k // 2)
+    res = None
+    if residual_mode == 1:
+        res = torch.randn(N, H, W, Cout, device=dev)
+        ref = ref + res.permute(0, 3, 1, 2).double()
+    elif residual_mode == 2:
+        res = torch.randn(N, H // 2, W // 2, Cout, device=dev)
+        ref = ref + F.interpolate(res.permute(0, 3, 1, 2).double(), scale_factor=2, mode="nearest")
+    if relu:
+        ref = ref.relu()
+    xh = x.permute(0, 2, 3, 1).contiguous()
+    y = K.conv_fwd(xh, wp, k, bias=b, residual=res, residual_mode=residual_mode, relu=relu, block_n=block_n)
+    torch.cuda.synchronize()
+    e = _err(y.permute(0, 3, 1, 2), ref)
+    e["case"] = f"N{N} H{H} W{W} Cin{Cin} Cout{Cout} k{k} bn{block_n} bias{int(bias)} res{residual_mode} relu{int(relu)}"
+    e["ok"] = (not e["nan"]) and e["rel"] < 2e-5
+    return e
+
+
+@check
+def conv_basic():
+    # 1x1 conv = plain GEMM: isolates the UMMA/TMA descriptors from the tap shifting
+    return [_conv_case(1, 16, 16, 32, 32, 1), _conv_case(1, 16, 16, 64, 64, 1), _conv_case(2, 16, 16, 128, 128, 1)]
+
+
+@check
+def conv_3x3():
+    return [_conv_case(1, 16, 16, 32, 64, 3), _conv_case(2, 32, 32, 64, 128, 3), _conv_case(1, 64, 64, 128, 256, 3),
+            _conv_case(2, 16, 16, 256, 512, 3, block_n=256), _conv_case(2, 16, 16, 256, 512, 3, block_n=128)]
+
+
+@check
+def conv_small_planes():
+    return [_conv_case(8, 4, 4, 64, 64, 3), _conv_case(8, 8, 8, 64, 128, 3), _conv_case(3, 4, 4, 32, 32, 3),
+            _conv_case(1, 4, 4, 32, 32, 3), _conv_case(1, 8, 8, 64, 64, 1), _conv_case(5, 8, 8, 64, 64, 3)]
+
+
+@check
+def conv_epilogue():
+    return [_conv_case(2, 16, 16, 64, 64, 3, bias=True), _conv_case(2, 16, 16, 64, 64, 3, residual_mode=1),
+            _conv_case(2, 16, 16, 64, 64, 3, residual_mode=2, bias=True), _conv_case(2, 16, 16, 64, 64, 3, relu=True)]
+
+
+@check
+def conv_big():
+    return [_conv_case(8, 256, 256, 64, 64, 3), _conv_case(8, 128, 128, 128, 128, 3),
+            _conv_case(8, 32, 32, 512, 512, 3), _conv_case(8, 64, 64, 512, 256, 3)]
+
+
+@check
+def conv_dgrad_pack():
+    # data gradient through the same kernel with transposed packing, against autograd
+    import torch
+    import torch.nn.functional as F
+    from b200lp import kernels as K
+    torch.manual_seed(1)
+    out = []
+    for (N, H, W, Cin, Cout, k) in [(2, 16, 16, 64, 128, 3), (2, 8, 8, 128, 64, 1)]:
+        w = torch.randn(Cout, Cin, k, k, device="cuda") * 0.05
+        dy = tf32_round(torch.randn(N, Cout, H, W, device="cuda"))
+        wpt = K.pack_conv_weight(w, transpose=True)          # [Cin][k*k][Cout]
+        w_r = K.pack_conv_weight(w).view(Cout, k, k, Cin).permute(0, 3, 1, 2).contiguous()
+        x = torch.zeros(N, Cin, H, W, device="cuda", dtype=torch.float64, requires_grad=True)
+        F.conv2d(x, w_r.double(), padding=k // 2).backward(dy.double())
+        dx = K.conv_fwd(dy.permute(0, 2, 3, 1).contiguous(), wpt, k)
+        torch.cuda.synchronize()
+        e = _err(dx.permute(0, 3, 1, 2), x.grad)
+        e["case"] = f"dgrad N{N} H{H} Cin{Cin} Cout{Cout} k{k}"
+        e["ok"] = (not e["nan"]) and e["rel"] < 2e-5
+        out.append(e)
+    return out
+
+
+def _wgrad_case(N, H, W, Cin, Cout, k):
+    import torch
+    import torch.nn.functional as F
+    from b200lp import kernels as K
+    torch.manual_seed(2)
+    x = tf32_round(torch.randn(N, Cin, H, W, device="cuda"))
+    dy = tf32_round(torch.randn(N, Cout, H, W, device="cuda"))
+    w = torch.zeros(Cout, Cin, k, k, device="cuda", dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), w, padding=k // 2).backward(dy.double())
+    dw = K.conv_wgrad(x.permute(0, 2, 3, 1).contiguous(), dy.permute(0, 2, 3, 1).contiguous(), k)
+    torch.cuda.synchronize()
+    e = _err(dw, w.grad)
+    e["case"] = f"wgrad N{N} H{H} W{W} Cin{Cin} Cout{Cout} k{k}"
+    e["ok"] = (not e["nan"]) and e["rel"] < 2e-5
+    return e
+
+
+@check
+def wgrad_basic():
+    return [_wgrad_case(1, 32, 32, 32, 32, 1), _wgrad_case(2, 32, 32, 128, 64, 1), _wgrad_case(2, 32, 32, 128, 256, 1)]
+
+
+@check
+def wgrad_3x3():
+    return [_wgrad_case(2, 32, 32, 64, 64, 3), _wgrad_case(2, 16, 16, 128, 256, 3), _wgrad_case(8, 4, 4, 64, 64, 3),
+            _wgrad_case(8, 8, 8, 128, 128, 3), _wgrad_case(4, 64, 64, 64, 128, 3)]
+
+
+@check
+def wgrad_big():
+    return [_wgrad_case(8, 256, 256, 64, 64, 3), _wgrad_case(8, 32, 32, 512, 512, 3), _wgrad_case(8, 128, 128, 128, 64, 3)]
+
+
+@check
+def adain_fwd_bwd():
+    import torch
+    import torch.nn.functional as F
+    from b200lp import kernels as K
+    torch.manual_seed(3)
+    out = []
+    for (N, H, W, C, up) in [(2, 16, 16, 64, False), (2, 8, 8, 512, True), (3, 32, 32, 128, True), (2, 4, 4, 512, False),
+                             (2, 64, 64, 64, True)]:
+        x = (torch.randn(N, C, H, W, device="cuda") * 3 + 5).requires_grad_(False)
+        aff = torch.randn(N, 2 * C + 7, device="cuda")
+        beta, gamma = aff[:, :C], aff[:, C:2 * C]
+        xd = x.double().requires_grad_(True)
+        gd = gamma.double().clone().requires_grad_(True)
+        bd = beta.double().clone().requires_grad_(True)
+        o = F.instance_norm(xd, eps=1e-4) * gd[:, :, None, None] + bd[:, :, None, None]
+        o = o.relu()
+        if up:
+            o = F.interpolate(o, scale_factor=2, mode="nearest")
+        dy = torch.randn_like(o)
+        o.backward(dy)
+        xh = x.permute(0, 2, 3, 1).contiguous()
+        mean, rstd = K.in_stats(xh, 1e-4)
+        y = K.adain_relu(xh, mean, rstd, gamma, beta, upsample2=up, round_tf32=False)
+        dx, dg, db = K.adain_relu_bwd(xh, mean, rstd, gamma, beta, dy.float().permute(0, 2, 3, 1).contiguous(), upsample2=up)
+        torch.cuda.synchronize()
+        for name, a, b, tol in [("y", y.permute(0, 3, 1, 2), o, 2e-5), ("dx", dx.permute(0, 3, 1, 2), xd.grad, 1e-4),
+                                ("dgamma", dg, gd.grad, 1e-4), ("dbeta", db, bd.grad, 1e-4),
+                                ("mean", mean, x.double().mean((2, 3)), 1e-5)]:
+            e = _err(a, b)
+            e["case"] = f"adain {name} N{N} H{H} C{C} up{int(up)}"
+            e["ok"] = (not e["nan"]) and e["rel"] < tol
+            out.append(e)
+    return out
+
+
+@check
+def elementwise_misc():
+    import torch
+    import torch.nn.functional as F
+    from b200lp import kernels as K
+    torch.manual_seed(4)
+    out = []
+
+    def add(name, a, b, tol=1e-6):
+        e = _err(a, b); e["case"] = name; e["ok"] = (not e["nan"]) and e["rel"] < tol; out.append(e)
+
+    x = torch.randn(2, 5, 8, 12, device="cuda")
+    add("nchw_to_nhwc", K.nchw_to_nhwc(x), x.permute(0, 2, 3, 1))
+    add("nhwc_to_nchw", K.nhwc_to_nchw(x.permute(0, 2, 3, 1).contiguous()), x)
+    a = torch.randn(2, 16, 16, 64, device="cuda"); b = torch.randn_like(a)
+    add("relu_round", K.relu_round(a), tf32_round(a.relu()))
+    add("relu_bwd", K.relu_bwd(a, b), b * (a > 0))
+    add("avgpool2", K.avgpool2(a).permute(0, 3, 1, 2), F.avg_pool2d(a.permute(0, 3, 1, 2), 2))
+    ad = torch.randn(2, 8, 8, 64, device="cuda")
+    add("avgpool2+add", K.avgpool2(a, ad).permute(0, 3, 1, 2), F.avg_pool2d(a.permute(0, 3, 1, 2), 2) + ad.permute(0, 3, 1, 2))
+    add("avgpool2_bwd", K.avgpool2_bwd(ad).permute(0, 3, 1, 2), F.interpolate(ad.permute(0, 3, 1, 2), scale_factor=2) * 0.25)
+    add("upsample2_bwd", K.upsample2_bwd(a).permute(0, 3, 1, 2), F.avg_pool2d(a.permute(0, 3, 1, 2), 2) * 4)
+    o = torch.zeros(1, device="cuda")
+    K.l1_sum(a, b, o, 0.5)
+    add("l1_sum", o, ((a.double() - b.double()).abs().sum() * 0.5).reshape(1), 1e-5)
+    g = torch.tensor([2.0], device="cuda")
+    add("l1_bwd", K.l1_bwd(a, b, g, 0.25), torch.sign(a - b) * 0.5)
+    add("bias_grad", K.bias_grad(a), a.double().sum((0, 1, 2)), 1e-5)
+    return out
+
+
+@check
+def direct_convs():
+    import torch
+    import torch.nn.functional as F
+    from b200lp import kernels as K
+    torch.manual_seed(5)
+    out = []
+
+    def add(name, a, b, tol=2e-5):
+        e = _err(a, b); e["case"] = name; e["ok"] = (not e["nan"]) and e["rel"] < tol; out.append(e)
+
+    N, H, W, Co = 2, 32, 32, 64
+    x = torch.rand(N, 3, H, W, device="cuda")
+    w = torch.randn(Co, 3, 3, 3, device="cuda") * 0.2
+    b = torch.randn(Co, device="cuda")
+    sc = torch.tensor([0.7], device="cuda")
+    ps = torch.tensor([255.0, 254.0, 253.0], device="cuda"); pb = torch.tensor([-103.9, -116.7, -123.6], device="cuda")
+    xd = x.double().requires_grad_(True)
+    wd = w.double().requires_grad_(True)
+    xn = xd * ps.double()[None, :, None, None] + pb.double()[None, :, None, None]
+    ref = F.conv2d(xn, wd * 0.7, b.double(), padding=1).relu()
+    dy = torch.randn_like(ref)
+    ref.backward(dy)
+    y = K.conv3x3_c3_fwd(x, w, sc, b, ps, pb, relu=True)
+    add("c3_fwd", y.permute(0, 3, 1, 2), ref)
+    dyh = (dy * (ref > 0)).float().permute(0, 2, 3, 1).contiguous()
+    add("c3_dgrad", K.conv3x3_c3_dgrad(dyh, w, sc, ps), xd.grad)
+    # wgrad without pre-affine
+    xd2 = x.double(); wd2 = w.double().requires_grad_(True)
+    r2 = F.conv2d(xd2, wd2, padding=1); r2.backward(dy)
+    add("c3_wgrad", K.conv3x3_c3_wgrad(x, dy.float().permute(0, 2, 3, 1).contiguous(), 1.0), wd2.grad)
+
+    # generator tail
+    Cin = 64
+    xt = torch.randn(N, H, W, Cin, device="cuda").relu()
+    wt = torch.randn(4, Cin, 3, 3, device="cuda") * 0.05
+    bt = torch.randn(4, device="cuda") * 0.1
+    xtd = xt.double().permute(0, 3, 1, 2).requires_grad_(True)
+    wtd = wt.double().requires_grad_(True); btd = bt.double().requires_grad_(True)
+    t = torch.tanh(F.conv2d(xtd, wtd * 0.7, btd, padding=1))
+    rgb = t[:, :3] * 0.75 + 0.5
+    sg = t[:, 3:] * 0.5 + 0.5
+    fake = rgb * sg
+    g1 = torch.randn_like(fake); g2 = torch.randn_like(sg)
+    (fake * g1).sum().backward(retain_graph=True)
+    rgbs, segm, tt = K.gen_tail_fwd(xt, wt, sc, bt)
+    add("tail_rgbs", rgbs, fake); add("tail_segm", segm, sg)
+    gx1 = xtd.grad.clone(); gw1 = wtd.grad.clone(); gb1 = btd.grad.clone()
+    dx, dw, db = K.gen_tail_bwd(xt, tt, wt, sc, g1.float().contiguous(), None)
+    add("tail_dx(rgb)", dx.permute(0, 3, 1, 2), gx1, 1e-4)
+    add("tail_dw(rgb)", dw * 0.7, gw1, 1e-4)   # kernel returns d/d(w*scale)
+    add("tail_db(rgb)", db, gb1, 1e-4)
+    xtd.grad = None; wtd.grad = None; btd.grad = None
+    ((fake * g1).sum() + (sg * g2).sum()).backward()
+    dx, dw, db = K.gen_tail_bwd(xt, tt, wt, sc, g1.float().contiguous(), g2.float().contiguous())
+    add("tail_dx(rgb+segm)", dx.permute(0, 3, 1, 2), xtd.grad, 1e-4)
+    add("tail_dw(rgb+segm)", dw * 0.7, wtd.grad, 1e-4)
+    return out
+
+
+@check
+def conv_timing():
+    """Rough CUDA-event timings of the dominant conv shapes (fwd, wgrad) -> TFLOP/s."""
+    import torch
+    from b200lp import kernels as K
+    out = []
+    shapes = [(8, 256, 256, 64, 64, 3), (8, 256, 256, 128, 64, 3), (8, 128, 128, 128, 128, 3), (8, 128, 128, 256, 128, 3),
+              (8, 64, 64, 256, 256, 3), (8, 64, 64, 512, 256, 3), (8, 32, 32, 512, 512, 3), (8, 16, 16, 512, 512, 3),
+              (8, 4, 4, 512, 512, 3), (8, 256, 256, 128, 64, 1)]
+    for (N, H, W, Cin, Cout, k) in shapes:
+        x = torch.randn(N, H, W, Cin, device="cuda")
+        dy = torch.randn(N, H, W, Cout, device="cuda")
+        w = torch.randn(Cout, Cin, k, k, device="cuda")
+        wp = K.pack_conv_weight(w)
+        y = torch.empty(N, H, W, Cout, device="cuda")
+        flops = 2.0 * N * H * W * Cin * Cout * k * k
+        rec = {"case": f"N{N} H{H} Cin{Cin} Cout{Cout} k{k}", "ok": True}
+        for name, fn in [("fwd", lambda: K.conv_fwd(x, wp, k, out=y)), ("wgrad", lambda: K.conv_wgrad(x, dy, k))]:
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            rec[name + "_ms"] = ms
+            rec[name + "_tflops"] = flops / ms / 1e9
+        out.append(rec)
+    return out
+
+
+def _run_child(name):
+    res = CHECKS[name]()
+    print("@@RESULT@@" + json.dumps(res))
+
+
+def main():
+    if len(sys.argv) >= 3 and sys.argv[1] == "--child":
+        _run_child(sys.argv[2])
+        return
+    filters = sys.argv[1:]
+    outdir = ROOT / "gpurun_out"
+    outdir.mkdir(exist_ok=True)
+    results = {}
+    for name in CHECKS:
+        if filters and not any(f in name for f in filters):
+            continue
+        t0 = time.time()
+        try:
+            p = subprocess.run([sys.executable, __file__, "--child", name], capture_output=True, text=True, timeout=600)
+            rec = {"returncode": p.returncode, "seconds": round(time.time() - t0, 1)}
+            for line in p.stdout.splitlines():
+                if line.startswith("@@RESULT@@"):
+                    rec["results"] = json.loads(line[len("@@RESULT@@"):])
+            if "results" not in rec:
+                rec["stdout_tail"] = p.stdout[-3000:]
+                rec["stderr_tail"] = p.stderr[-3000:]
+        except subprocess.TimeoutExpired:
+            rec = {"returncode": "timeout", "seconds": round(time.time() - t0, 1)}
+        results[name] = rec
+        ok = all(r.get("ok", False) for r in rec.get("results", [])) if "results" in rec else False
+        print(f"[{'OK ' if ok else 'BAD'}] {name} ({rec['seconds']}s)")
+        for r in rec.get("results", []):
+            print("     ", json.dumps(r))
+        if "results" not in rec:
+            print(rec.get("stderr_tail", "")[-1500:])
+        sys.stdout.flush()
+        (outdir / "diag.json").write_text(json.dumps(results, indent=1))
+
+
+if __name__ == "__main__":
+    main()
