@@ -1,0 +1,319 @@
+"""torch.autograd.Function wrappers around the C-ABI kernels (b200lp.kernels).
+
+torch.autograd is used as the graph/plumbing layer only (the reference's runner calls `loss.backward()` twice with
+`retain_graph`, runners/holycow.py:239-252); every forward and backward computation below is a libb200lp kernel.
+Activations are NHWC (N, H, W, C) float32 CUDA tensors.
+"""
+import torch
+
+from . import kernels as K
+
+
+def _dot(a, b):
+    return (a * b).sum()
+
+
+class Conv2dFn(torch.autograd.Function):
+    """y = epilogue(conv_k(x, weight_orig * inv_sigma)).  Replaces nn.Conv2d under spectral_norm
+    (generators/common/blocks.py:78-100, discriminators/no_landmarks.py:54-66) and its autograd backward.
+
+    Gradients: dx (same tensor-core kernel, transposed packing), d(weight_orig) = G*inv_sigma and
+    d(inv_sigma) = <G, weight_orig> with G the tensor-core weight gradient; sigma's own dependence on weight_orig
+    (u^T W v) is left to autograd through `inv_sigma`.
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight_orig, inv_sigma, bias, residual, ksize, residual_mode, relu, round_out):
+        wp = K.pack_conv_weight(weight_orig, inv_sigma, transpose=False)
+        y = K.conv_fwd(x, wp, ksize, bias=bias, residual=residual, residual_mode=residual_mode, relu=relu,
+                       round_tf32=round_out)
+        ctx.ksize, ctx.residual_mode, ctx.relu = ksize, residual_mode, relu
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, weight_orig, inv_sigma, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight_orig, inv_sigma, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        if ctx.relu:
+            dy = K.relu_bwd(y, dy)
+        need_x, need_w, need_s, need_b, need_r = ctx.needs_input_grad[:5]
+        dx = dw = ds = db = dr = None
+        if need_x:
+            wpt = K.pack_conv_weight(weight_orig, inv_sigma, transpose=True)
+            dx = K.conv_fwd(dy, wpt, ctx.ksize)
+        if need_w or (need_s and inv_sigma is not None):
+            g = K.conv_wgrad(x, dy, ctx.ksize)
+            if inv_sigma is not None:
+                if need_s:
+                    ds = _dot(g, weight_orig).reshape(inv_sigma.shape)
+                if need_w:
+                    dw = g * inv_sigma
+            else:
+                dw = g
+        if ctx.has_bias and need_b:
+            db = K.bias_grad(dy)
+        if ctx.has_res and need_r:
+            dr = dy if ctx.residual_mode == 1 else K.upsample2_bwd(dy)
+        return dx, dw, ds, db, dr, None, None, None, None
+
+
+def conv2d(x, weight_orig, inv_sigma=None, bias=None, residual=None, ksize=3, residual_mode=0, relu=False,
+           round_out=False):
+    if residual is None:
+        residual_mode = 0
+    return Conv2dFn.apply(x, weight_orig, inv_sigma, bias, residual, ksize, residual_mode, relu, round_out)
+
+
+class AdaINReLUFn(torch.autograd.Function):
+    """relu(instance_norm(x) * gamma + beta) [nearest 2x] [tf32].  Replaces AdaptiveNorm2d.forward + ReLU + Upsample
+    (generators/common/blocks.py:18-26,73,75) and their backward."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, upsample2, round_out):
+        mean, rstd = K.in_stats(x, eps)
+        y = K.adain_relu(x, mean, rstd, gamma, beta, upsample2=upsample2, round_tf32=round_out)
+        ctx.upsample2 = upsample2
+        ctx.save_for_backward(x, mean, rstd, gamma, beta)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, gamma, beta = ctx.saved_tensors
+        dx, dg, db = K.adain_relu_bwd(x, mean, rstd, gamma, beta, dy.contiguous(), upsample2=ctx.upsample2)
+        return dx, dg, db, None, None, None
+
+
+def adain_relu(x, gamma, beta, eps=1e-4, upsample2=False, round_out=True):
+    return AdaINReLUFn.apply(x, gamma, beta, eps, upsample2, round_out)
+
+
+class GenTailFn(torch.autograd.Function):
+    """conv3x3(Cin->4)+bias -> tanh -> rgb*segm composition (generator :84-88,165-181), NHWC in, NCHW images out."""
+
+    @staticmethod
+    def forward(ctx, x, weight_orig, inv_sigma, bias):
+        rgbs, segm, t = K.gen_tail_fwd(x, weight_orig, inv_sigma, bias)
+        ctx.save_for_backward(x, weight_orig, inv_sigma, t)
+        ctx.mark_non_differentiable()
+        return rgbs, segm
+
+    @staticmethod
+    def backward(ctx, d_rgbs, d_segm):
+        x, weight_orig, inv_sigma, t = ctx.saved_tensors
+        d_rgbs = d_rgbs.contiguous() if d_rgbs is not None else None
+        d_segm = d_segm.contiguous() if d_segm is not None else None
+        need_x, need_w, need_s, need_b = ctx.needs_input_grad
+        dx, g, db = K.gen_tail_bwd(x, t, weight_orig, inv_sigma, d_rgbs, d_segm, need_dx=need_x,
+                                   need_dw=(need_w or need_s or need_b))
+        dw = ds = None
+        if g is not None:
+            if need_s:
+                ds = _dot(g, weight_orig).reshape(inv_sigma.shape)
+            if need_w:
+                dw = g * inv_sigma
+        return dx, dw, ds, (db if need_b else None)
+
+
+def gen_tail(x, weight_orig, inv_sigma, bias):
+    return GenTailFn.apply(x, weight_orig, inv_sigma, bias)
+
+
+class ReluRoundFn(torch.autograd.Function):
+    """tf32(relu(x)) — the discriminator blocks' leading ReLU(inplace) (blocks.py:73 with norm_layer='none')."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = K.relu_round(x)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return K.relu_bwd(y, dy.contiguous())
+
+
+def relu_round(x):
+    return ReluRoundFn.apply(x)
+
+
+class AvgPool2Fn(torch.autograd.Function):
+    """avg_pool2d(x, 2) (+ addend) — nn.AvgPool2d(2) at blocks.py:89-90,101-102, discriminator :62,66."""
+
+    @staticmethod
+    def forward(ctx, x, addend, round_out):
+        ctx.has_add = addend is not None
+        return K.avgpool2(x, addend, round_tf32=round_out)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        dx = K.avgpool2_bwd(dy) if ctx.needs_input_grad[0] else None
+        return dx, (dy if ctx.has_add and ctx.needs_input_grad[1] else None), None
+
+
+def avgpool2(x, addend=None, round_out=False):
+    return AvgPool2Fn.apply(x, addend, round_out)
+
+
+class ConvC3Fn(torch.autograd.Function):
+    """3x3 conv on a 3-channel NCHW image -> NHWC features (discriminator down_block.0, skip.0 via a centre-tap
+    embedding; VGG features.0 with the caffe input normalisation folded in)."""
+
+    @staticmethod
+    def forward(ctx, x_nchw, weight_orig, inv_sigma, bias, pre_scale, pre_shift, relu, round_out):
+        y = K.conv3x3_c3_fwd(x_nchw, weight_orig, inv_sigma, bias, pre_scale, pre_shift, relu=relu, round_tf32=round_out)
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x_nchw, weight_orig, inv_sigma, pre_scale, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight_orig, inv_sigma, pre_scale, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        if ctx.relu:
+            dy = K.relu_bwd(y, dy)
+        need_x, need_w, need_s, need_b = ctx.needs_input_grad[:4]
+        dx = dw = ds = db = None
+        if need_x:
+            dx = K.conv3x3_c3_dgrad(dy, weight_orig, inv_sigma, pre_scale)
+        if need_w or need_s:
+            assert pre_scale is None, "weight gradient with input pre-affine is not needed on this path"
+            g = K.conv3x3_c3_wgrad(x, dy, 1.0)
+            if inv_sigma is not None:
+                if need_s:
+                    ds = _dot(g, weight_orig).reshape(inv_sigma.shape)
+                if need_w:
+                    dw = g * inv_sigma
+            else:
+                dw = g
+        if ctx.has_bias and need_b:
+            db = K.bias_grad(dy)
+        return dx, dw, ds, db, None, None, None, None
+
+
+def conv_c3(x_nchw, weight_orig, inv_sigma=None, bias=None, pre_scale=None, pre_shift=None, relu=False,
+            round_out=False):
+    return ConvC3Fn.apply(x_nchw, weight_orig, inv_sigma, bias, pre_scale, pre_shift, relu, round_out)
+
+
+class L1MeanFn(torch.autograd.Function):
+    """F.l1_loss(a, b.detach()) (mean reduction) — criterions/featmat.py:18-20, perceptual_loss.py:108."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        out = torch.zeros(1, dtype=torch.float32, device=a.device)
+        K.l1_sum(a, b, out, 1.0 / a.numel())
+        ctx.save_for_backward(a, b)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        gs = g.reshape(1).contiguous().float()
+        return K.l1_bwd(a, b, gs, 1.0 / a.numel()), None
+
+
+def l1_mean(a, b):
+    return L1MeanFn.apply(a.contiguous(), b.detach().contiguous())
+
+
+class NchwToNhwcFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return K.nchw_to_nhwc(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.nhwc_to_nchw(dy.contiguous())
+
+
+class NhwcToNchwFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return K.nhwc_to_nchw(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.nchw_to_nhwc(dy.contiguous())
+
+
+def nchw_to_nhwc(x):
+    return NchwToNhwcFn.apply(x)
+
+
+def nhwc_to_nchw(x):
+    return NhwcToNchwFn.apply(x)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# VGG perceptual loss as ONE autograd node: frozen weights (packed once), fake and real pushed side by side, L1
+# reduced by kernel after every ReLU; backward = data-gradient chain only (criterions/common/perceptual_loss.py:91-110)
+# ----------------------------------------------------------------------------------------------------------------
+class VggPerceptualFn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, fake_nchw, real_nchw, packed, weight):
+        """packed: dict from VggFeatures.pack(): plan [(kind, idx)], first conv OIHW + bias, packed fwd/bwd weights,
+        biases, pre_scale/pre_shift of the fused input normalisation."""
+        plan = packed["plan"]
+        dev = fake_nchw.device
+        loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        a = b = None
+        saved = []          # per ReLU tap: (a_feat, b_feat)
+        fake = fake_nchw.contiguous()
+        real = real_nchw.contiguous()
+        n_taps = 0
+        for kind, idx in plan:
+            if kind == "conv0":   # conv + relu fused (every VGG conv is followed by a ReLU tap)
+                a = K.conv3x3_c3_fwd(fake, packed["w0"], None, packed["b0"], packed["pre_scale"], packed["pre_shift"],
+                                     relu=True, round_tf32=True)
+                b = K.conv3x3_c3_fwd(real, packed["w0"], None, packed["b0"], packed["pre_scale"], packed["pre_shift"],
+                                     relu=True, round_tf32=True)
+            elif kind == "conv":
+                a = K.conv_fwd(a, packed["wp"][idx], 3, bias=packed["bias"][idx], relu=True, round_tf32=True)
+                b = K.conv_fwd(b, packed["wp"][idx], 3, bias=packed["bias"][idx], relu=True, round_tf32=True)
+            elif kind == "pool":
+                a = K.avgpool2(a, None, round_tf32=True)
+                b = K.avgpool2(b, None, round_tf32=True)
+                continue
+            K.l1_sum(a, b, loss, weight / a.numel())
+            saved.append((a, b))
+            n_taps += 1
+        ctx.packed = packed
+        ctx.weight = weight
+        ctx.saved_feats = saved
+        ctx.fake = fake
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        packed, saved = ctx.packed, ctx.saved_feats
+        plan = packed["plan"]
+        gs = g.reshape(1).contiguous().float()
+        d = None                     # gradient w.r.t. the current activation (post-ReLU feature), NHWC
+        tap = len(saved) - 1
+        dx_img = None
+        for kind, idx in reversed(plan):
+            if kind == "pool":
+                d = K.avgpool2_bwd(d)
+                continue
+            a, b = saved[tap]
+            tap -= 1
+            # d(loss)/d(a) gets the L1 term of this tap, then passes the ReLU mask
+            d = K.l1_bwd(a, b, gs, ctx.weight / a.numel(), da=d)
+            d = K.relu_bwd(a, d)
+            if kind == "conv":
+                d = K.conv_fwd(d, packed["wpt"][idx], 3)
+            else:
+                dx_img = K.conv3x3_c3_dgrad(d, packed["w0"], None, packed["pre_scale"])
+        ctx.saved_feats = None
+        return dx_img, None, None, None
+
+
+def vgg_perceptual(fake_nchw, real_nchw, packed, weight):
+    return VggPerceptualFn.apply(fake_nchw, real_nchw.detach(), packed, float(weight))

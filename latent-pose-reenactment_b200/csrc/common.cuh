@@ -31,8 +31,11 @@ void set_error(const char* fmt, ...);
 
 // cuTensorMapEncodeTiled for an fp32 tensor of rank `rank` (dims innermost first), 128-byte swizzle,
 // zero fill for out-of-bounds elements.  strides_bytes has rank-1 entries (dim 1..rank-1).
+// swizzle_base32 = false: CU_TENSOR_MAP_SWIZZLE_128B (16-byte chunks, K-major UMMA operands);
+// swizzle_base32 = true : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (32-byte chunks; the only layout the tensor core accepts
+//                         for MN-major 32-bit operands, UMMA layout type SWIZZLE_128B_BASE32B).
 int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box);
+                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle_base32 = false);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -4,7 +4,8 @@
 //   GEMM view:  M = (tap, ci) rows (128 per CTA = four 32-channel blocks, each with its own tap shift),
 //               N = Cout tile, K = pixels (split across CTAs: "split-K", deterministic two-pass reduction).
 //   Both operands are read straight from the NHWC tensors: a TMA box [32 pixels][32 channels] lands in shared
-//   memory as 32 rows (K) x 128 bytes (32 channels of M or N): the canonical MN-major SWIZZLE_128B UMMA operand,
+//   memory as 32 rows (K) x 128 bytes (32 channels of M or N): the canonical MN-major SWIZZLE_128B_BASE32B UMMA operand
+//   (TMA swizzle mode 128B_ATOM_32B; the only MN-major layout the tensor core accepts for 32-bit operands),
 //   so no transposed copy of the activations or gradients ever exists in HBM.
 //   Zero padding = TMA out-of-bounds zero fill on the shifted X box.
 //
@@ -139,9 +140,11 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
                 for (int k = 0; k < kWgKStep / 8; ++k) {
-                    // MN-major SWIZZLE_128B: 32-channel blocks are kWgBlkBytes apart (LBO); 8 K rows = 1024 B
-                    const uint64_t da = make_smem_desc(a_addr + k * 1024, kWgBlkBytes, 1024, 2);
-                    const uint64_t db = make_smem_desc(b_addr + k * 1024, kWgBlkBytes, 1024, 2);
+                    // MN-major 32-bit operands must use SWIZZLE_128B_BASE32B (layout type 1): atoms of 4 K-rows x 128 B;
+                    // LBO = stride between 32-channel blocks, SBO = stride between 4-row K groups (512 B);
+                    // one K=8 MMA spans two atoms, so stepping K by 8 = +1024 bytes.
+                    const uint64_t da = make_smem_desc(a_addr + k * 1024, kWgBlkBytes, 512, 1);
+                    const uint64_t db = make_smem_desc(b_addr + k * 1024, kWgBlkBytes, 512, 1);
                     umma_tf32_ss(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[stage]);
@@ -287,14 +290,14 @@ extern "C" int32_t b200lp_conv_wgrad(const b200lp_wgrad_args* a, void* stream) {
         const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
         const uint64_t strides[3] = {(uint64_t)a->Cin * 4, (uint64_t)a->W * a->Cin * 4,
                                      (uint64_t)a->H * a->W * a->Cin * 4};
-        int r = encode_tmap_f32(&tmX, a->x, 4, dims, strides, box);
+        int r = encode_tmap_f32(&tmX, a->x, 4, dims, strides, box, true);
         if (r) return r;
     }
     {
         const uint64_t dims[4] = {(uint64_t)a->Cout, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
         const uint64_t strides[3] = {(uint64_t)a->Cout * 4, (uint64_t)a->W * a->Cout * 4,
                                      (uint64_t)a->H * a->W * a->Cout * 4};
-        int r = encode_tmap_f32(&tmDY, a->dy, 4, dims, strides, box);
+        int r = encode_tmap_f32(&tmDY, a->dy, 4, dims, strides, box, true);
         if (r) return r;
     }
     cudaStream_t s = as_stream(stream);

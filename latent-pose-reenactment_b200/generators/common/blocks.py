@@ -1,0 +1,161 @@
+"""Shared building blocks of the B200-native generator / discriminator plugins.
+
+Host-side mirror of the reference's `generators/common/blocks.py` (AdaptiveNorm2d :6-26, ResBlock :47-111) for the
+two configurations the shipped configs instantiate: `norm_layer='adain'` (generator) and `norm_layer='none'`
+(discriminator).  Modules here only *own parameters* (with the reference's state_dict names: `weight_orig`,
+`weight_u`, `weight_v`, `bias`) and sequence kernel calls from `b200lp.ops`; activations are NHWC.
+"""
+import math
+
+import torch
+from torch import nn
+
+from b200lp import ops
+
+
+class Slots(nn.Module):
+    """A container whose children are registered under explicit (numeric) names, so that state_dict keys line up
+    with the reference's nn.Sequential indices even though the parameter-free layers in between do not exist here."""
+
+    def __init__(self, **children):
+        super().__init__()
+        for name, child in children.items():
+            self.add_module(name, child)
+
+    def slot(self, index):
+        return self._modules[str(index)]
+
+
+class SpectralNormed(nn.Module):
+    """Owner of one spectral-normalised weight: parameters `bias` (optional, registered first like the reference's
+    nn.Conv2d/nn.Linear after torch.nn.utils.spectral_norm re-registers `weight_orig`), `weight_orig`; buffers
+    `weight_u`, `weight_v`.
+
+    `inv_sigma()` follows torch's SpectralNorm.compute_weight: in training mode one in-place power iteration on the
+    buffers, then sigma = u^T W v with u, v treated as constants; returns 1/sigma as a 1-element tensor attached to
+    `weight_orig`'s autograd graph.  The kernels consume (weight_orig, 1/sigma) directly — W/sigma is never
+    materialised.
+    """
+
+    def __init__(self, weight_shape, bias, eps=1e-4):
+        super().__init__()
+        out_features = weight_shape[0]
+        fan_in = int(math.prod(weight_shape[1:]))
+        if bias:
+            bound = 1 / math.sqrt(fan_in)
+            self.bias = nn.Parameter(torch.empty(out_features).uniform_(-bound, bound))
+        else:
+            self.bias = None
+        w = torch.empty(*weight_shape)
+        nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        self.weight_orig = nn.Parameter(w)
+        self.eps = eps
+        u = torch.randn(out_features)
+        v = torch.randn(fan_in)
+        self.register_buffer("weight_u", u / u.norm().clamp_min(eps))
+        self.register_buffer("weight_v", v / v.norm().clamp_min(eps))
+
+    def inv_sigma(self):
+        w = self.weight_orig
+        wm = w.reshape(w.shape[0], -1)
+        if self.training:
+            with torch.no_grad():
+                v = torch.mv(wm.t(), self.weight_u)
+                v = v / v.norm().clamp_min(self.eps)
+                u = torch.mv(wm, v)
+                u = u / u.norm().clamp_min(self.eps)
+                self.weight_v.copy_(v)
+                self.weight_u.copy_(u)
+        u = self.weight_u.clone()
+        v = self.weight_v.clone()
+        sigma = torch.dot(u, torch.mv(wm, v))
+        return (1.0 / sigma).reshape(1)
+
+
+class SNConv(SpectralNormed):
+    def __init__(self, in_channels, out_channels, ksize, bias, eps=1e-4):
+        super().__init__((out_channels, in_channels, ksize, ksize), bias, eps)
+        self.ksize = ksize
+
+
+class SNLinear(SpectralNormed):
+    def __init__(self, in_features, out_features, eps=1e-4):
+        super().__init__((out_features, in_features), True, eps)
+
+    def forward(self, x):
+        # (x W^T) / sigma + b  ==  F.linear(x, W / sigma, b) without materialising W / sigma
+        return torch.nn.functional.linear(x, self.weight_orig) * self.inv_sigma() + self.bias
+
+
+class AdaResBlock(nn.Module):
+    """ResBlock(norm_layer='adain') as built by the generator's get_res_block / get_up_block
+    (reference blocks.py:47-111, generator :45-51).  Children mirror the reference's Sequential indices:
+    block.{3,7} (plain) or block.{4,8} (upsampling), skip.1.
+
+        main: AdaIN -> ReLU -> [nearest 2x] -> conv3x3 -> AdaIN -> ReLU -> conv3x3      skip: [2x] -> conv1x1(+bias)
+
+    Kernel schedule (NHWC): adain_relu(+2x, tf32)  ->  conv  ->  adain_relu  ->  conv (+ residual in the epilogue).
+    The 1x1 skip conv is evaluated at the LOW resolution and nearest-upsampled inside the second conv's epilogue
+    (conv1x1 and nearest-upsample commute: 4x fewer MACs, identical values).
+    """
+
+    def __init__(self, in_channels, out_channels, upsample):
+        super().__init__()
+        i0, i1 = (4, 8) if upsample else (3, 7)
+        self.i0, self.i1 = i0, i1
+        self.in_channels, self.out_channels, self.upsample = in_channels, out_channels, upsample
+        self.block = Slots(**{str(i0): SNConv(in_channels, out_channels, 3, bias=False),
+                              str(i1): SNConv(out_channels, out_channels, 3, bias=False)})
+        self.skip = None
+        if in_channels != out_channels or upsample:
+            self.skip = Slots(**{"1": SNConv(in_channels, out_channels, 1, bias=True)})
+
+    def forward(self, x, gamma0, beta0, gamma1, beta1, round_out):
+        c0, c1 = self.block.slot(self.i0), self.block.slot(self.i1)
+        a0 = ops.adain_relu(x, gamma0, beta0, upsample2=self.upsample)
+        y1 = ops.conv2d(a0, c0.weight_orig, c0.inv_sigma(), ksize=3)
+        a1 = ops.adain_relu(y1, gamma1, beta1)
+        if self.skip is not None:
+            cs = self.skip.slot(1)
+            s = ops.conv2d(x, cs.weight_orig, cs.inv_sigma(), bias=cs.bias, ksize=1)
+            mode = 2 if self.upsample else 1
+        else:
+            s, mode = x, 1
+        return ops.conv2d(a1, c1.weight_orig, c1.inv_sigma(), residual=s, residual_mode=mode, ksize=3,
+                          round_out=round_out)
+
+
+class PlainResBlock(nn.Module):
+    """ResBlock(norm_layer='none') as built by the discriminator (reference blocks.py:47-111 via
+    discriminators/no_landmarks.py:37-43): children block.{2,5} (+bias), skip.0 (+bias).
+
+        r = relu(x) [in place in the reference: the skip branch and the stored feature both see r]
+        main: conv3x3(r)+b -> ReLU -> conv3x3+b -> [avgpool2]        skip: conv1x1(r)+b -> [avgpool2]
+
+    Kernel schedule: conv(+bias, relu, tf32) -> conv(+bias) -> avgpool2(+skip) with the 1x1 skip conv evaluated on
+    the pooled input (avg-pool and conv1x1 commute).
+    """
+
+    def __init__(self, in_channels, out_channels, downsample):
+        super().__init__()
+        self.in_channels, self.out_channels, self.downsample = in_channels, out_channels, downsample
+        self.block = Slots(**{"2": SNConv(in_channels, out_channels, 3, bias=True),
+                              "5": SNConv(out_channels, out_channels, 3, bias=True)})
+        self.skip = None
+        if in_channels != out_channels or downsample:
+            self.skip = Slots(**{"0": SNConv(in_channels, out_channels, 1, bias=True)})
+
+    def forward(self, r):
+        """r = tf32(relu(block input)).  Returns the block output (pre-ReLU)."""
+        c0, c1 = self.block.slot(2), self.block.slot(5)
+        h = ops.conv2d(r, c0.weight_orig, c0.inv_sigma(), bias=c0.bias, ksize=3, relu=True, round_out=True)
+        if self.skip is not None:
+            cs = self.skip.slot(0)
+            rs = ops.avgpool2(r, None, round_out=True) if self.downsample else r
+            s = ops.conv2d(rs, cs.weight_orig, cs.inv_sigma(), bias=cs.bias, ksize=1)
+        else:
+            s = r
+        if self.downsample:
+            h2 = ops.conv2d(h, c1.weight_orig, c1.inv_sigma(), bias=c1.bias, ksize=3)
+            return ops.avgpool2(h2, s)
+        return ops.conv2d(h, c1.weight_orig, c1.inv_sigma(), bias=c1.bias, residual=s, residual_mode=1, ksize=3)

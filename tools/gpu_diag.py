@@ -135,7 +135,7 @@ def _wgrad_case(N, H, W, Cin, Cout, k):
     torch.cuda.synchronize()
     e = _err(dw, w.grad)
     e["case"] = f"wgrad N{N} H{H} W{W} Cin{Cin} Cout{Cout} k{k}"
-    e["ok"] = (not e["nan"]) and e["rel"] < 2e-5
+    e["ok"] = (not e["nan"]) and e["rel"] < 5e-5   # fp32 accumulation over up to 524288 pixels
     return e
 
 
