@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 3
+#define B200LP_ABI_VERSION 4
 
 #define B200LP_OK 0
 #define B200LP_EINVAL (-1)   /* bad shape / unsupported configuration */
@@ -33,6 +33,8 @@ int32_t b200lp_abi_version(void);
 const char* b200lp_last_error(void);
 /* compute capability major*10+minor of the current device, or a negative error */
 int32_t b200lp_device_cc(void);
+/* number of kernels this library has launched so far in this process (a monotone counter) */
+int64_t b200lp_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (TF32 x TF32 -> FP32), stride 1, "same" zero padding.

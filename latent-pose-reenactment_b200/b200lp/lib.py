@@ -13,7 +13,7 @@ import torch
 
 _PKG = Path(__file__).resolve().parent.parent
 LIB_PATH = _PKG / "lib" / "libb200lp.so"
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class B200lpError(RuntimeError):
@@ -48,6 +48,7 @@ SIGNATURES = {
     "b200lp_abi_version": (_I, []),
     "b200lp_last_error": (c_char_p, []),
     "b200lp_device_cc": (_I, []),
+    "b200lp_launch_count": (_L, []),
     "b200lp_conv_fwd": (_I, [POINTER(ConvArgs), _P]),
     "b200lp_pack_conv_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "b200lp_conv_wgrad_workspace": (_L, [_I, _I, _I, _I, _I, _I]),

@@ -2,11 +2,16 @@
 
 #include <cudaTypedefs.h>
 #include <stdarg.h>
+
+#include <atomic>
 #include <string.h>
 
 namespace b200lp {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -62,6 +67,8 @@ int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t
 extern "C" {
 
 int32_t b200lp_abi_version(void) { return B200LP_ABI_VERSION; }
+
+int64_t b200lp_launch_count(void) { return b200lp::g_launches.load(std::memory_order_relaxed); }
 
 const char* b200lp_last_error(void) { return b200lp::g_err; }
 

@@ -11,6 +11,8 @@
 namespace b200lp {
 
 void set_error(const char* fmt, ...);
+// number of kernels this library has launched (bench.py's `gpu_launches`)
+void count_launch(int n = 1);
 
 #define B200LP_CHECK_CUDA(expr)                                                               \
     do {                                                                                      \

@@ -214,6 +214,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
     dim3 grid(p.Cout / BLOCK_N, m_tiles, 1);
     conv_igemm_tf32_kernel<BLOCK_N><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -324,5 +325,6 @@ extern "C" int32_t b200lp_pack_conv_weight(const float* w_oihw, const float* sca
     pack_conv_weight_kernel<<<(int)blocks, threads, 0, as_stream(stream)>>>(w_oihw, scale, wp, Cout, Cin,
                                                                             ksize * ksize, transpose);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }

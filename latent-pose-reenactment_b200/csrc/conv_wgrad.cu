@@ -240,6 +240,7 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const W
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
     conv_wgrad_tf32_kernel<BLOCK_N><<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(tmX, tmDY, p);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -315,5 +316,6 @@ extern "C" int32_t b200lp_conv_wgrad(const b200lp_wgrad_args* a, void* stream) {
     wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(a->workspace, a->dw, pl.splits, p.rows_total, a->Cout, a->Cin, taps,
                                                a->scale);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }

@@ -381,6 +381,7 @@ extern "C" int32_t b200lp_conv3x3_c3_fwd(const float* x_nchw, const float* w_oih
     conv3x3_c3_fwd_kernel<<<blocks, 256, (27 * Cout + Cout) * 4, as_stream(stream)>>>(
         x_nchw, w_oihw, wscale, bias, pre_scale, pre_shift, y_nhwc, N, H, W, Cout, relu, round_tf32);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -394,6 +395,7 @@ extern "C" int32_t b200lp_conv3x3_c3_dgrad(const float* dy_nhwc, const float* w_
     conv3x3_c3_dgrad_kernel<<<blocks, 256, 27 * Cout * 4, as_stream(stream)>>>(dy_nhwc, w_oihw, wscale, pre_scale,
                                                                                dx_nchw, N, H, W, Cout);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -412,6 +414,7 @@ extern "C" int32_t b200lp_conv3x3_c3_wgrad(const float* x_nchw, const float* dy_
     conv3x3_c3_wgrad_kernel<<<blocks, 256, static_cast<size_t>(lanes) * Cout * 27 * 4, s>>>(
         x_nchw, dy_nhwc, dw_oihw, wscale_host, N, H, W, Cout, ppb);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -425,6 +428,7 @@ extern "C" int32_t b200lp_gen_tail_fwd(const float* x_nhwc, const float* w_oihw,
     gen_tail_fwd_kernel<<<blocks, 128, 9 * Cin * 16, as_stream(stream)>>>(x_nhwc, w_oihw, wscale, bias, fake_rgbs_nchw,
                                                                           fake_segm_nchw, t_out, N, H, W, Cin);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -436,6 +440,7 @@ extern "C" int32_t b200lp_gen_tail_bwd_act(const float* t, const float* d_rgbs, 
     gen_tail_bwd_act_kernel<<<static_cast<int>((NP + 255) / 256), 256, 0, as_stream(stream)>>>(t, d_rgbs, d_segm, da,
                                                                                                NP, HW);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -451,6 +456,7 @@ extern "C" int32_t b200lp_gen_tail_bwd_data(const float* da, const float* w_oihw
     gen_tail_bwd_data_kernel<<<blocks, 256, 9 * Cin * 16, as_stream(stream)>>>(da, w_oihw, wscale, dx_nhwc, N, H, W,
                                                                                Cin);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -468,5 +474,6 @@ extern "C" int32_t b200lp_gen_tail_bwd_weight(const float* x_nhwc, const float* 
     const size_t smem = (static_cast<size_t>(lanes) * Cin * 36 + lanes * 4) * 4;
     gen_tail_bwd_weight_kernel<<<blocks, 256, smem, s>>>(x_nhwc, da, dw_oihw, dbias, N, H, W, Cin, ppb);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }

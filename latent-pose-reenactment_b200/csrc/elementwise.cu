@@ -523,9 +523,11 @@ extern "C" int32_t b200lp_in_stats(const float* x, float* mean, float* rstd, flo
     cudaStream_t s = as_stream(stream);
     in_stats_partial_kernel<<<dim3(chunks, N), kEwThreads, smem, s>>>(x, workspace, HW, C, ppc);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     const int NC = N * C;
     in_stats_final_kernel<<<(NC + 127) / 128, 128, 0, s>>>(workspace, mean, rstd, chunks, C, NC, eps);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -544,6 +546,7 @@ extern "C" int32_t b200lp_adain_relu(const float* x, const float* mean, const fl
     else { if (round_tf32) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -576,9 +579,11 @@ extern "C" int32_t b200lp_adain_relu_bwd(const float* x, const float* mean, cons
         adain_bwd_partial_kernel<false><<<grid, kEwThreads, smem, s>>>(x, mean, rstd, gamma, beta, affine_stride, dy,
                                                                        workspace, H, W, C, ppc);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     const int NC = N * C;
     adain_bwd_final_kernel<<<(NC + 127) / 128, 128, 0, s>>>(workspace, dgamma, dbeta, chunks, C, NC);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     if (upsample2)
         adain_bwd_apply_kernel<true><<<grid, kEwThreads, 0, s>>>(x, mean, rstd, gamma, beta, affine_stride, dy, dgamma,
                                                                  dbeta, dx, H, W, C, ppc);
@@ -586,6 +591,7 @@ extern "C" int32_t b200lp_adain_relu_bwd(const float* x, const float* mean, cons
         adain_bwd_apply_kernel<false><<<grid, kEwThreads, 0, s>>>(x, mean, rstd, gamma, beta, affine_stride, dy,
                                                                   dgamma, dbeta, dx, H, W, C, ppc);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -594,6 +600,7 @@ extern "C" int32_t b200lp_relu_round(const float* x, float* y, int64_t n, void* 
     relu_round_kernel<<<grid_for(n / 4, kEwThreads), kEwThreads, 0, as_stream(stream)>>>(
         reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n / 4);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -602,6 +609,7 @@ extern "C" int32_t b200lp_relu_bwd(const float* y, const float* dy, float* dx, i
     relu_bwd_kernel<<<grid_for(n / 4, kEwThreads), kEwThreads, 0, as_stream(stream)>>>(
         reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dx), n / 4);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -616,6 +624,7 @@ extern "C" int32_t b200lp_avgpool2(const float* x, const float* addend, float* y
     else
         pool2_kernel<false><<<g, kEwThreads, 0, as_stream(stream)>>>(x, addend, y, H, W, C, total4, 0.25f);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -626,6 +635,7 @@ extern "C" int32_t b200lp_avgpool2_bwd(const float* dy, float* dx, int32_t N, in
     const long total4 = static_cast<long>(N) * H * W * (C / 4);
     unpool2_kernel<<<grid_for(total4, kEwThreads), kEwThreads, 0, as_stream(stream)>>>(dy, dx, H, W, C, total4, 0.25f);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -637,6 +647,7 @@ extern "C" int32_t b200lp_upsample2_bwd(const float* dy, float* dx, int32_t N, i
     pool2_kernel<false><<<grid_for(total4, kEwThreads), kEwThreads, 0, as_stream(stream)>>>(dy, nullptr, dx, H, W, C,
                                                                                           total4, 1.0f);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -647,6 +658,7 @@ extern "C" int32_t b200lp_l1_sum(const float* a, const float* b, float* out, int
     l1_sum_kernel<<<g, kEwThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a),
                                                           reinterpret_cast<const float4*>(b), out, n / 4, scale);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -663,6 +675,7 @@ extern "C" int32_t b200lp_l1_bwd(const float* a, const float* b, const float* gs
                                                                       reinterpret_cast<const float4*>(b), gscale,
                                                                       scale2, reinterpret_cast<float4*>(da), n / 4);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -672,6 +685,7 @@ extern "C" int32_t b200lp_nchw_to_nhwc(const float* x, float* y, int32_t N, int3
     const long total = static_cast<long>(N) * C * H * W;
     nchw_to_nhwc_kernel<<<grid_for(total, kEwThreads), kEwThreads, 0, as_stream(stream)>>>(x, y, C, H * W, total);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -681,6 +695,7 @@ extern "C" int32_t b200lp_nhwc_to_nchw(const float* x, float* y, int32_t N, int3
     const long total = static_cast<long>(N) * C * H * W;
     nhwc_to_nchw_kernel<<<grid_for(total, kEwThreads), kEwThreads, 0, as_stream(stream)>>>(x, y, C, H * W, total);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }
 
@@ -696,5 +711,6 @@ extern "C" int32_t b200lp_bias_grad(const float* dy, float* db, int64_t pixels, 
     bias_grad_kernel<<<static_cast<int>(blocks), kEwThreads, static_cast<size_t>(rows) * C * 4, s>>>(dy, db, pixels, C,
                                                                                                    ppb);
     B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }

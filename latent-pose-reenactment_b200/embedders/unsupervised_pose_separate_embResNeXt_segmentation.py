@@ -1,0 +1,55 @@
+"""Identity / pose embedder plugin — drop-in for the reference's
+`embedders/unsupervised_pose_separate_embResNeXt_segmentation.py` (Wrapper :7-16, Embedder :19-63).
+
+identity = torchvision ResNeXt50-32x4d -> `embed_channels`, averaged over the K identity frames;
+pose     = torchvision MobileNetV2     -> `pose_embedding_size`.
+These two encoders are stock torchvision networks in the reference as well (grouped / depthwise convs with
+train-mode BatchNorm); they stay on torch/cuDNN in this round — SURVEY.md §8(f) next-3 — so the state_dict (634
+torchvision keys under `identity_encoder.` / `pose_encoder.`) and numerics are identical by construction.
+"""
+import torch
+from torch import nn
+
+
+class Wrapper:
+    @staticmethod
+    def get_args(parser):
+        parser.add('--average_function', type=str, default='sum', help='sum|max')
+
+    @staticmethod
+    def get_net(args):
+        net = Embedder(args.embed_channels, args.pose_embedding_size, args.average_function)
+        return net.to(args.device)
+
+
+class Embedder(nn.Module):
+    def __init__(self, identity_embedding_size, pose_embedding_size, average_function):
+        super().__init__()
+        import torchvision
+        self.identity_embedding_size = identity_embedding_size
+        self.pose_embedding_size = pose_embedding_size
+        self.identity_encoder = torchvision.models.resnext50_32x4d(num_classes=identity_embedding_size)
+        self.pose_encoder = torchvision.models.mobilenet_v2(num_classes=pose_embedding_size)
+        if average_function not in ('sum', 'max'):
+            raise ValueError("Incorrect `average_function` argument, expected `sum` or `max`")
+        self.average_function = average_function
+        self.finetuning = False
+
+    def enable_finetuning(self, data_dict=None):
+        self.finetuning = True
+
+    def get_identity_embedding(self, data_dict):
+        inputs = data_dict['enc_rgbs']
+        batch_size, num_faces, c, h, w = inputs.shape
+        per_frame = self.identity_encoder(inputs.reshape(-1, c, h, w)).view(batch_size, num_faces, -1)
+        assert per_frame.shape[2] == self.identity_embedding_size
+        data_dict['embeds'] = per_frame.mean(1) if self.average_function == 'sum' else per_frame.max(1)[0]
+        data_dict['embeds_elemwise'] = per_frame
+
+    def get_pose_embedding(self, data_dict):
+        data_dict['pose_embedding'] = self.pose_encoder(data_dict['pose_input_rgbs'][:, 0])
+
+    def forward(self, data_dict):
+        if not self.finetuning:
+            self.get_identity_embedding(data_dict)
+        self.get_pose_embedding(data_dict)

@@ -71,6 +71,15 @@ class SpectralNormed(nn.Module):
         sigma = torch.dot(u, torch.mv(wm, v))
         return (1.0 / sigma).reshape(1)
 
+    def operands(self, detach=False):
+        """(weight_orig, 1/sigma, bias) as the kernels consume them.  `detach=True` cuts the parameter gradients
+        (used for the discriminator pass whose weight gradients the training step discards anyway); the power
+        iteration still runs."""
+        s = self.inv_sigma()
+        if detach:
+            return self.weight_orig.detach(), s.detach(), (self.bias.detach() if self.bias is not None else None)
+        return self.weight_orig, s, self.bias
+
 
 class SNConv(SpectralNormed):
     def __init__(self, in_channels, out_channels, ksize, bias, eps=1e-4):
@@ -111,18 +120,18 @@ class AdaResBlock(nn.Module):
             self.skip = Slots(**{"1": SNConv(in_channels, out_channels, 1, bias=True)})
 
     def forward(self, x, gamma0, beta0, gamma1, beta1, round_out):
-        c0, c1 = self.block.slot(self.i0), self.block.slot(self.i1)
+        w0, s0, _ = self.block.slot(self.i0).operands()
         a0 = ops.adain_relu(x, gamma0, beta0, upsample2=self.upsample)
-        y1 = ops.conv2d(a0, c0.weight_orig, c0.inv_sigma(), ksize=3)
+        y1 = ops.conv2d(a0, w0, s0, ksize=3)
         a1 = ops.adain_relu(y1, gamma1, beta1)
+        w1, s1, _ = self.block.slot(self.i1).operands()
         if self.skip is not None:
-            cs = self.skip.slot(1)
-            s = ops.conv2d(x, cs.weight_orig, cs.inv_sigma(), bias=cs.bias, ksize=1)
+            ws, ss, bs = self.skip.slot(1).operands()
+            s = ops.conv2d(x, ws, ss, bias=bs, ksize=1)
             mode = 2 if self.upsample else 1
         else:
             s, mode = x, 1
-        return ops.conv2d(a1, c1.weight_orig, c1.inv_sigma(), residual=s, residual_mode=mode, ksize=3,
-                          round_out=round_out)
+        return ops.conv2d(a1, w1, s1, residual=s, residual_mode=mode, ksize=3, round_out=round_out)
 
 
 class PlainResBlock(nn.Module):
@@ -145,17 +154,18 @@ class PlainResBlock(nn.Module):
         if in_channels != out_channels or downsample:
             self.skip = Slots(**{"0": SNConv(in_channels, out_channels, 1, bias=True)})
 
-    def forward(self, r):
+    def forward(self, r, detach_params=False):
         """r = tf32(relu(block input)).  Returns the block output (pre-ReLU)."""
-        c0, c1 = self.block.slot(2), self.block.slot(5)
-        h = ops.conv2d(r, c0.weight_orig, c0.inv_sigma(), bias=c0.bias, ksize=3, relu=True, round_out=True)
+        w0, s0, b0 = self.block.slot(2).operands(detach_params)
+        h = ops.conv2d(r, w0, s0, bias=b0, ksize=3, relu=True, round_out=True)
+        w1, s1, b1 = self.block.slot(5).operands(detach_params)
         if self.skip is not None:
-            cs = self.skip.slot(0)
+            ws, ss, bs = self.skip.slot(0).operands(detach_params)
             rs = ops.avgpool2(r, None, round_out=True) if self.downsample else r
-            s = ops.conv2d(rs, cs.weight_orig, cs.inv_sigma(), bias=cs.bias, ksize=1)
+            s = ops.conv2d(rs, ws, ss, bias=bs, ksize=1)
         else:
             s = r
         if self.downsample:
-            h2 = ops.conv2d(h, c1.weight_orig, c1.inv_sigma(), bias=c1.bias, ksize=3)
+            h2 = ops.conv2d(h, w1, s1, bias=b1, ksize=3)
             return ops.avgpool2(h2, s)
-        return ops.conv2d(h, c1.weight_orig, c1.inv_sigma(), bias=c1.bias, residual=s, residual_mode=1, ksize=3)
+        return ops.conv2d(h, w1, s1, bias=b1, residual=s, residual_mode=1, ksize=3)

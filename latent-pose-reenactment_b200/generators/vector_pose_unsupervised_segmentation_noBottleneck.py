@@ -1,0 +1,152 @@
+"""B200-native generator plugin — drop-in for the reference's
+`generators/vector_pose_unsupervised_segmentation_noBottleneck.py` (Wrapper :8-28, Generator :40-181).
+
+Same plugin API (`Wrapper.get_args/get_net`, `forward(data_dict)`, `enable_finetuning`), same state_dict keys and
+shapes (checkpoints interchange), same parameter order (optimizer state interchanges).  The arithmetic is a
+schedule of libb200lp kernels: per decoder block  adain_relu -> tcgen05 conv -> adain_relu -> tcgen05 conv(+skip),
+with NHWC activations internally and NCHW images at the `data_dict` boundary.
+"""
+import math
+
+import torch
+from torch import nn
+
+from b200lp import lib as b200lp_lib
+from b200lp import ops
+from generators.common import blocks
+
+
+class Wrapper:
+    @staticmethod
+    def get_args(parser):
+        parser.add('--gen_constant_input_size', type=int, default=4)
+        parser.add('--gen_num_residual_blocks', type=int, default=2)
+        parser.add('--gen_padding', type=str, default='zero', help='zero|reflection')
+        parser.add('--norm_layer', type=str, default='in')
+
+    @staticmethod
+    def get_net(args):
+        if 'gen_constant_input_size' not in args:   # old checkpoints (reference :19-21)
+            args.gen_constant_input_size = 4
+        net = Generator(
+            args.gen_padding, args.in_channels, args.out_channels + 1,
+            args.num_channels, args.max_num_channels, args.embed_channels, args.pose_embedding_size,
+            args.norm_layer, args.gen_constant_input_size, args.gen_num_residual_blocks,
+            args.image_size)
+        return net.to(args.device)
+
+
+class Constant(nn.Module):
+    """Learned (1, C, s, s) input of the decoder (reference :31-37); stored NCHW for checkpoint compatibility."""
+
+    def __init__(self, *shape):
+        super().__init__()
+        self.constant = nn.Parameter(torch.ones(1, *shape))
+
+
+class Generator(nn.Module):
+    def __init__(self, padding, in_channels, out_channels, num_channels, max_num_channels, identity_embedding_size,
+                 pose_embedding_size, norm_layer, gen_constant_input_size, gen_num_residual_blocks,
+                 output_image_size):
+        super().__init__()
+        if padding != 'zero':
+            if padding == 'reflection':
+                raise NotImplementedError("B200 generator: only `gen_padding=zero` (the shipped configs) is native")
+            raise Exception('Incorrect `padding` argument, required `zero` or `reflection`')
+        if norm_layer != 'in':
+            raise NotImplementedError("B200 generator: only `norm_layer=in` (AdaIN over InstanceNorm) is native")
+        if out_channels != 4:
+            raise NotImplementedError("B200 generator: the fused tail kernel emits RGB + segmentation (4 channels)")
+        assert math.log2(output_image_size / gen_constant_input_size).is_integer(), \
+            "`gen_constant_input_size` must be `image_size` divided by a power of 2"
+        num_up = int(math.log2(output_image_size / gen_constant_input_size))
+        nonclamped = num_channels * (2 ** num_up)
+        c = min(nonclamped, max_num_channels)
+
+        self.constant = Constant(c, gen_constant_input_size, gen_constant_input_size)
+
+        children = {}
+        self.adain_sizes = []
+        idx = 0
+        for _ in range(gen_num_residual_blocks):
+            children[str(idx)] = blocks.AdaResBlock(c, c, upsample=False)
+            self.adain_sizes += [c, c]
+            idx += 1
+        for _ in range(num_up):
+            cin = c
+            nonclamped //= 2
+            c = min(nonclamped, max_num_channels)
+            children[str(idx)] = blocks.AdaResBlock(cin, c, upsample=True)
+            self.adain_sizes += [cin, c]
+            idx += 1
+        self.num_blocks = idx
+        self.adain_sizes.append(c)           # final AdaIN (reference decoder_blocks[num_blocks])
+        # reference Sequential: [blocks..., AdaIN, ReLU, conv, Tanh] -> the conv sits at index num_blocks + 2
+        children[str(idx + 2)] = blocks.SNConv(c, out_channels, 3, bias=True)
+        self.decoder_blocks = blocks.Slots(**children)
+
+        self.identity_embedding_size = identity_embedding_size
+        self.pose_embedding_size = pose_embedding_size
+        joint = identity_embedding_size + pose_embedding_size
+        hidden = max(joint, 512)
+        self.affine_params_projector = blocks.Slots(**{
+            "0": blocks.SNLinear(joint, hidden),
+            "2": blocks.SNLinear(hidden, self.get_num_affine_params())})
+        self.finetuning = False
+
+    def get_num_affine_params(self):
+        return sum(2 * c for c in self.adain_sizes)
+
+    def compute_affine_params(self, data_dict):
+        """assign_embeddings (reference :127-137): [identity | pose] -> SN-Linear -> ReLU -> SN-Linear."""
+        if self.finetuning:
+            identity = self.identity_embedding.expand(len(data_dict['pose_embedding']), -1)
+        else:
+            identity = data_dict['embeds']
+        joint = torch.cat((identity, data_dict['pose_embedding']), dim=1)
+        h = torch.relu(self.affine_params_projector.slot(0)(joint))
+        return self.affine_params_projector.slot(2)(h)
+
+    def enable_finetuning(self, data_dict=None):
+        """Reference :139-163: the identity embedding becomes a trainable parameter `identity_embedding` (1, E)."""
+        if data_dict is None:
+            some_parameter = next(iter(self.parameters()))
+            identity_embedding = torch.rand(1, self.identity_embedding_size).to(some_parameter)
+        else:
+            identity_embedding = data_dict['embeds']
+        if self.finetuning:
+            with torch.no_grad():
+                self.identity_embedding.copy_(identity_embedding)
+        else:
+            self.identity_embedding = nn.Parameter(identity_embedding)
+            self.finetuning = True
+
+    def forward(self, data_dict):
+        b200lp_lib.require_device()
+        affine = self.compute_affine_params(data_dict).contiguous()      # (B, sum 2C): per AdaIN [beta | gamma]
+        batch = affine.shape[0]
+
+        off = 0
+
+        def take(c):
+            nonlocal off
+            beta, gamma = affine[:, off:off + c], affine[:, off + c:off + 2 * c]
+            off += 2 * c
+            return gamma, beta
+
+        # constant (1,C,s,s) NCHW parameter -> (B,s,s,C) NHWC
+        x = self.constant.constant.permute(0, 2, 3, 1).expand(batch, -1, -1, -1).contiguous()
+        for i in range(self.num_blocks):
+            blk = self.decoder_blocks.slot(i)
+            g0, b0 = take(blk.in_channels)
+            g1, b1 = take(blk.out_channels)
+            # the next block's 1x1 skip conv reads this output as a tensor-core operand: round it once here
+            nxt = self.decoder_blocks.slot(i + 1) if i + 1 < self.num_blocks else None
+            round_out = nxt is not None and nxt.skip is not None
+            x = blk(x, g0, b0, g1, b1, round_out)
+        g, bt = take(self.adain_sizes[-1])
+        a = ops.adain_relu(x, g, bt, round_out=False)
+        tail = self.decoder_blocks.slot(self.num_blocks + 2)
+        fake_rgbs, fake_segm = ops.gen_tail(a, tail.weight_orig, tail.inv_sigma(), tail.bias)
+        data_dict['fake_rgbs'] = fake_rgbs
+        data_dict['fake_segm'] = fake_segm

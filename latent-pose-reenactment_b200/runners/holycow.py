@@ -1,0 +1,281 @@
+"""Training runner — drop-in for the reference's `runners/holycow.py` (get_args :18-31, get_optimizer :34-41,
+TrainingModule :44-210, run_epoch :212-402): same module-level API, same step protocol
+
+    forward E -> G -> D -> criteria;  loss_G.backward(retain_graph) ; [all-reduce] ; optimizer_G.step()
+    optimizer_D.zero_grad() ; loss_D.backward() ; [all-reduce] ; optimizer_D.step() ; EMA of E/G weights
+
+Differences that do not change results:
+  * data parallelism: gradients live as views into two flat fp32 buckets (E+G, D); after each backward ONE
+    NCCL all-reduce(AVG) over NVLink runs on the bucket that backward produced (the reference all-reduces all
+    83.6 M parameters twice through apex.Reducer, including gradients it then discards — SURVEY.md §2a C1/C2);
+  * the discriminator's fake-for-G pass runs on detached weights (`skip_discarded_wgrad`), because the reference
+    zeroes those weight gradients before they are ever used (runners/holycow.py:247);
+  * EMA and gradient zeroing are multi-tensor (_foreach) launches.
+"""
+import copy
+import itertools
+import logging
+import time
+
+import torch
+from torch import nn
+
+from utils import utils
+from utils.radam import RAdam
+from utils.utils import Meter
+
+torch.optim.RAdam = RAdam   # the reference installs its vendored RAdam the same way (:5-6)
+
+logger = logging.getLogger('runner')
+
+
+def get_args(parser):
+    parser.add('--iteration', type=int, default=0, help="Optional iteration number to start from")
+    parser.add('--log_frequency_loss', type=int, default=1)
+    parser.add('--log_frequency_images', type=int, default=100)
+    parser.add('--log_frequency_fixed_images', type=int, default=2500)
+    parser.add('--detailed_metrics', action='store_bool', default=True)
+    parser.add('--num_visuals_per_img', default=2, type=int)
+    parser.add('--fixed_val_ids', action='append', type=int, default=[50, 100, 200, 250, 300])
+    parser.add('--batch_size_inference', default=5, type=int)
+    return parser
+
+
+def get_optimizer(embedder, generator, args):
+    model_parameters = list(generator.parameters())
+    if 'finetune' not in args or not args.finetune:
+        model_parameters += list(embedder.parameters())
+    Optimizer = torch.optim.__dict__[args.optimizer]
+    return Optimizer(model_parameters, lr=args.lr_gen, betas=(args.beta1, 0.999), eps=1e-5)
+
+
+class GradBucket:
+    """All gradients of a parameter list as views into one flat fp32 buffer: zeroing is one memset, the data-parallel
+    exchange is one in-place NCCL all-reduce(AVG) with no flatten / unflatten copies."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        device = self.params[0].device if self.params else 'cpu'
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def attach(self):
+        """Re-point .grad at the bucket (an optimizer's zero_grad(set_to_none=True) or a fresh parameter drops it)."""
+        off = 0
+        for p in self.params:
+            g = self.flat[off:off + p.numel()].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+                if p.grad is not None:
+                    g.copy_(p.grad)
+                p.grad = g
+            off += p.numel()
+
+    def zero(self):
+        self.attach()
+        self.flat.zero_()
+
+    def all_reduce(self):
+        if torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            self.attach()
+            if self.flat.is_cuda:
+                torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.AVG)
+            else:   # gloo (CPU tests) has no AVG
+                torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.SUM)
+                self.flat.div_(torch.distributed.get_world_size())
+
+
+class TrainingModule(torch.nn.Module):
+    def __init__(self, embedder, generator, discriminator, criterion_list, metric_list, running_averages={}):
+        """`running_averages`: None (do not track) or {name: state_dict} initial values for 'embedder'/'generator'."""
+        super().__init__()
+        self.embedder = embedder
+        self.generator = generator
+        self.discriminator = discriminator
+        self.criterion_list = nn.ModuleList(criterion_list)
+        self.metric_list = nn.ModuleList(metric_list)
+        self.compute_losses = True
+        self.use_running_averages = False
+        self.initialize_running_averages(running_averages)
+        self._buckets = None
+
+    def initialize_running_averages(self, initial_values={}):
+        self.running_averages = {}
+        if initial_values is not None:
+            for name in 'embedder', 'generator':
+                model = getattr(self, name)
+                self.running_averages[name] = copy.deepcopy(model)
+                if name in initial_values:
+                    try:
+                        self.running_averages[name].load_state_dict(initial_values[name])
+                    except Exception:
+                        logger.warning(f"Parameters mismatch in {name} and the initial value of weights' "
+                                       f"running averages. Initializing by cloning")
+                        self.running_averages[name].load_state_dict(model.state_dict())
+                else:
+                    logger.info(f"No initial value of weights' running averages provided for {name}. "
+                                f"Initializing by cloning")
+        for module in self.running_averages.values():
+            module.eval()
+            module.requires_grad_(False)
+
+    def update_running_average(self, alpha=0.999):
+        """p_avg = p_avg*alpha + p*(1-alpha) for E and G parameters; buffers copied (reference :99-109)."""
+        with torch.no_grad():
+            for name, avg in self.running_averages.items():
+                cur = getattr(self, name)
+                p_avg, p_cur = list(avg.parameters()), list(cur.parameters())
+                if p_avg:
+                    torch._foreach_mul_(p_avg, alpha)
+                    torch._foreach_add_(p_avg, p_cur, alpha=1 - alpha)
+                b_avg, b_cur = list(avg.buffers()), list(cur.buffers())
+                if b_avg:
+                    torch._foreach_copy_(b_avg, b_cur)
+
+    class _Flag:
+        def __init__(self, owner, attr, value):
+            self.owner, self.attr, self.old = owner, attr, getattr(owner, attr)
+            setattr(owner, attr, value)
+
+        def __enter__(self):
+            pass
+
+        def __exit__(self, *args):
+            setattr(self.owner, self.attr, self.old)
+
+    def set_use_running_averages(self, use_running_averages=True):
+        """Usable as a plain call or as a context manager (restores the old value on exit)."""
+        return TrainingModule._Flag(self, 'use_running_averages', use_running_averages)
+
+    def set_compute_losses(self, compute_losses=True):
+        return TrainingModule._Flag(self, 'compute_losses', compute_losses)
+
+    def forward(self, data_dict, target_dict):
+        if self.running_averages and self.use_running_averages:
+            embedder, generator = self.running_averages['embedder'], self.running_averages['generator']
+        else:
+            embedder, generator = self.embedder, self.generator
+
+        data_dict = copy.copy(data_dict)
+        embedder(data_dict)
+        generator(data_dict)
+        data_dict.update(target_dict)
+        if self.compute_losses:
+            self.discriminator(data_dict)
+
+        losses_G_dict, losses_D_dict = {}, {}
+        for criterion in self.criterion_list:
+            try:
+                crit_out = criterion(data_dict)
+            except Exception:
+                if self.compute_losses:
+                    raise
+                continue
+            if isinstance(crit_out, tuple):
+                if len(crit_out) != 2:
+                    raise TypeError(f'Unexpected number of outputs in criterion {type(criterion)}: '
+                                    f'expected 2, got {len(crit_out)}')
+                losses_G_dict.update(crit_out[0])
+                losses_D_dict.update(crit_out[1])
+            elif isinstance(crit_out, dict):
+                losses_G_dict.update(crit_out)
+            else:
+                raise TypeError(f'Unexpected type of {type(criterion)} output: '
+                                f'expected dict or tuple of two dicts, got {type(crit_out)}')
+        return data_dict, losses_G_dict, losses_D_dict
+
+    def compute_metrics(self, data_dict):
+        metrics_meter = Meter()
+        for metric in self.metric_list:
+            metric_out, num_errors = metric(data_dict)
+            for name, value in metric_out.items():
+                metrics_meter.add(name, value, num_errors[name])
+        return metrics_meter
+
+    # ---------------------------------------------------------------- data parallel plumbing
+    def grad_buckets(self, optimizer_G, optimizer_D):
+        """(bucket_G, bucket_D) over exactly the parameters each optimizer owns; built lazily, rebuilt when the
+        optimizers are re-created (fine-tuning start)."""
+        key = (id(optimizer_G), id(optimizer_D))
+        if self._buckets is None or self._buckets[0] != key:
+            params_G = [p for g in optimizer_G.param_groups for p in g['params']]
+            params_D = [p for g in optimizer_D.param_groups for p in g['params']] if optimizer_D else []
+            self._buckets = (key, GradBucket(params_G), GradBucket(params_D) if params_D else None)
+            if hasattr(self.discriminator, 'skip_discarded_wgrad'):
+                self.discriminator.skip_discarded_wgrad = True
+        return self._buckets[1], self._buckets[2]
+
+    def broadcast_parameters(self):
+        """Rank 0's parameters and buffers to every rank (what apex.parallel.Reducer does at construction)."""
+        if torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            for t in itertools.chain(self.parameters(), self.buffers()):
+                torch.distributed.broadcast(t.data, src=0)
+
+
+def train_step(training_module, data_dict, target_dict, optimizer_G, optimizer_D, finetune=False):
+    """One optimisation step (reference run_epoch :230-257).  Returns (all_data_dict, losses_G, losses_D)."""
+    bucket_G, bucket_D = training_module.grad_buckets(optimizer_G, optimizer_D)
+    all_data_dict, losses_G_dict, losses_D_dict = training_module(data_dict, target_dict)
+    loss_G = sum(v for v in losses_G_dict.values() if isinstance(v, torch.Tensor))
+    loss_D = sum(v for v in losses_D_dict.values() if isinstance(v, torch.Tensor))
+
+    bucket_G.zero()
+    loss_G.backward(retain_graph=True)
+    bucket_G.all_reduce()
+    optimizer_G.step()
+
+    if losses_D_dict:
+        bucket_D.zero()
+        loss_D.backward()
+        bucket_D.all_reduce()
+        optimizer_D.step()
+
+    training_module.update_running_average(0.972 if finetune else 0.999)
+    return all_data_dict, losses_G_dict, losses_D_dict
+
+
+def run_epoch(dataloader, training_module, optimizer_G, optimizer_D, epoch, args, phase, writer=None, saver=None):
+    meter = Meter()
+    end = time.time()
+    for it, (data_dict, target_dict) in enumerate(dataloader):
+        meter.add('Data_time', time.time() - end)
+        utils.dict_to_device(data_dict, args.device)
+        utils.dict_to_device(target_dict, args.device)
+
+        if phase == 'train':
+            all_data_dict, losses_G_dict, losses_D_dict = train_step(
+                training_module, data_dict, target_dict, optimizer_G, optimizer_D, finetune=args.finetune)
+        else:
+            all_data_dict, losses_G_dict, losses_D_dict = training_module(data_dict, target_dict)
+            if saver is not None:
+                saver.save(epoch=epoch, data=all_data_dict)
+
+        if args.detailed_metrics:   # one device->host sync per loss, like the reference (:260-262)
+            for loss_name, loss_ in itertools.chain(losses_G_dict.items(), losses_D_dict.items()):
+                meter.add(f'Loss_{loss_name}', float(loss_))
+        del losses_G_dict, losses_D_dict
+
+        meter.add('Batch_time', time.time() - end)
+        if writer is not None and phase == 'train':
+            if args.iteration % args.log_frequency_loss == 0:
+                for name in meter.keys():
+                    writer.add_scalar(f'Metrics/{phase}/{name}', meter.get_last(name), args.iteration)
+            if args.log_frequency_images > 0 and args.iteration % args.log_frequency_images == 0:
+                try:
+                    from utils.visualize import make_visual
+                    writer.add_image(f'Images/{phase}/visual', make_visual(all_data_dict, args.num_visuals_per_img),
+                                     args.iteration, dataformats='HWC')
+                except Exception as err:
+                    logger.warning(f"Could not log images: {err}")
+            args.iteration += 1
+        del all_data_dict
+        end = time.time()
+
+    logger.info(f"{phase.capitalize()} epoch {epoch}: " +
+                ", ".join(f"{name}: {meter.get_average(name):.4g}" for name in meter.keys()))
+    return meter

@@ -1,0 +1,56 @@
+"""C-ABI library: loads without a GPU, exports every symbol include/b200lp.h declares, and the ctypes binding
+declares exactly those symbols (no compute calls here)."""
+import ctypes
+import re
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def header_symbols():
+    text = (ROOT / "include" / "b200lp.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200lp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    from b200lp import lib
+    handle = lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(handle, s), f"libb200lp.so does not export {s}"
+    assert handle.b200lp_abi_version() == lib.ABI_VERSION
+    m = re.search(r"#define\s+B200LP_ABI_VERSION\s+(\d+)", (ROOT / "include" / "b200lp.h").read_text())
+    assert int(m.group(1)) == lib.ABI_VERSION
+
+
+def test_binding_covers_header_exactly():
+    from b200lp import lib
+    assert sorted(lib.SIGNATURES.keys()) == header_symbols()
+
+
+def test_struct_layouts_match_header():
+    from b200lp import lib
+    # b200lp_conv_args: 5 pointers + 10 int32 ; b200lp_wgrad_args: 4 pointers + int64 + 6 int32 + float
+    assert ctypes.sizeof(lib.ConvArgs) == 5 * 8 + 10 * 4
+    assert ctypes.sizeof(lib.WgradArgs) == 4 * 8 + 8 + 6 * 4 + 4 + 4   # + tail padding to 8
+    assert lib.ConvArgs.block_n.offset == 5 * 8 + 9 * 4
+    assert lib.WgradArgs.scale.offset == 4 * 8 + 8 + 6 * 4
+
+
+def test_sass_contains_blackwell_tensor_core_and_tma_instructions():
+    """The shipped binary really is tcgen05 + TMA code (UTC*MMA / UTMALDG / LDTM), not a legacy mma.sync path."""
+    import shutil
+    import subprocess
+    from b200lp import lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        import pytest
+        pytest.skip("cuobjdump not available")
+    lib.load()
+    sass = subprocess.run([cuobjdump, "-sass", str(lib.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass or "UTCMMA" in sass or re.search(r"UTC\w*MMA", sass)
+    assert "UTMALDG" in sass
+    assert "LDTM" in sass
+    assert "HMMA.16816" not in sass and "HGMMA" not in sass

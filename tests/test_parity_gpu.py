@@ -1,0 +1,236 @@
+"""Parity of the CUDA path (plugins -> autograd ops -> C ABI -> sm_100a kernels) with the reference.
+
+Oracles: (1) golden vectors produced by the unmodified reference modules (tests/golden/*.pt, oracle/make_golden.py),
+(2) the CPU restatement oracle/reference_model.py in float64 on the same seeded weights and inputs.
+Tolerances (stated per test): generator RGB max-abs <= 1e-3 (BASELINE.json north_star); other quantities are
+relative errors consistent with TF32 operands / FP32 accumulation (2^-11 per operand rounding).
+"""
+import copy
+import importlib
+import tempfile
+
+import pytest
+import torch
+
+from helpers import StubEmbedder, make_args, max_abs, rel_err, to_dev, write_vgg_files
+from oracle import reference_model as R
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _G(cfg, sd, finetune_embeds=None):
+    args = make_args(cfg, device=DEV)
+    G = importlib.import_module("generators.vector_pose_unsupervised_segmentation_noBottleneck").Wrapper.get_net(args)
+    if finetune_embeds is not None:
+        G.enable_finetuning({"embeds": finetune_embeds.to(DEV)})
+        sd = dict(sd, identity_embedding=finetune_embeds)
+    G.load_state_dict(sd, strict=True)
+    return G
+
+
+def _D(cfg, sd):
+    args = make_args(cfg, device=DEV)
+    D = importlib.import_module("discriminators.no_landmarks").Wrapper.get_net(args)
+    D.load_state_dict(sd, strict=True)
+    return D
+
+
+@pytest.fixture(scope="module")
+def small():
+    cfg = synth.SMALL_CFG
+    data, target, emb = synth.make_inputs(cfg, batch=2, seed=4)
+    return dict(cfg=cfg, g_sd=synth.generator_state_dict(cfg, seed=1), d_sd=synth.discriminator_state_dict(cfg, seed=2),
+                data=data, target=target, emb=emb)
+
+
+def test_native_library_is_loaded():
+    from b200lp import lib
+    assert lib.require_device() // 10 == 10
+    assert lib.load().b200lp_abi_version() == lib.ABI_VERSION
+
+
+def test_generator_forward_eval_train(small, golden_small):
+    cfg, emb = small["cfg"], to_dev(small["emb"], DEV)
+    G = _G(cfg, small["g_sd"])
+    with torch.no_grad():
+        G.eval()
+        dd = dict(embeds=emb["embeds"], pose_embedding=emb["pose_embedding"])
+        G(dd)
+        assert dd["fake_rgbs"].shape == (2, 3, 32, 32) and dd["fake_segm"].shape == (2, 1, 32, 32)
+        assert max_abs(dd["fake_rgbs"], golden_small["g_eval.fake_rgbs"]) < 1e-3          # north_star tolerance
+        assert max_abs(dd["fake_segm"], golden_small["g_eval.fake_segm"]) < 1e-3
+        # float64 restatement as ground truth
+        sd64 = {k: v.double() for k, v in small["g_sd"].items()}
+        layout = R.generator_layout(cfg["num_channels"], cfg["max_num_channels"], cfg["image_size"])
+        rgb64, _, _ = R.generator_forward(sd64, small["emb"]["embeds"].double(), small["emb"]["pose_embedding"].double(),
+                                          layout, training=False)
+        assert max_abs(dd["fake_rgbs"], rgb64) < 1e-3
+        G.train()
+        dd = dict(embeds=emb["embeds"], pose_embedding=emb["pose_embedding"])
+        G(dd)
+        assert max_abs(dd["fake_rgbs"], golden_small["g_train.fake_rgbs"]) < 1e-3
+        sd = G.state_dict()
+        assert rel_err(sd["decoder_blocks.0.block.3.weight_u"], golden_small["g_train.u_after.decoder_blocks.0.block.3"]) < 1e-5
+        assert rel_err(sd["affine_params_projector.2.weight_v"], golden_small["g_train.v_after.affine_params_projector.2"]) < 1e-5
+
+
+def test_generator_finetune_mode(small, golden_small):
+    cfg, emb = small["cfg"], to_dev(small["emb"], DEV)
+    G = _G(cfg, small["g_sd"], finetune_embeds=small["emb"]["embeds"][:1].clone())
+    with torch.no_grad():
+        G.eval()
+        dd = dict(pose_embedding=emb["pose_embedding"])
+        G(dd)
+        assert max_abs(dd["fake_rgbs"], golden_small["ft.g_eval.fake_rgbs"]) < 1e-3
+
+
+def test_discriminator_three_passes(small, golden_small):
+    cfg = small["cfg"]
+    D = _D(cfg, small["d_sd"])
+    fake = golden_small["g_eval.fake_rgbs"].to(DEV)
+    with torch.no_grad():
+        D.train()
+        dd = dict(fake_rgbs=fake, target_rgbs=small["data"]["target_rgbs"].to(DEV), label=small["target"]["label"].to(DEV))
+        D(dd)
+        for k in ("fake_score_G", "fake_score_D", "real_score"):
+            # scores are sums of 16 x 64 post-ReLU features: TF32 relative error on the score scale
+            assert rel_err(dd[k], golden_small["d_train." + k]) < 3e-3, k
+        assert rel_err(dd["real_embedding"], golden_small["d_train.real_embedding"]) < 1e-5
+        for i in range(7):
+            f, r = dd["fake_features"][i], dd["real_features"][i]
+            assert f.shape == golden_small[f"d_train.fake_features.{i}"].shape
+            assert rel_err(f, golden_small[f"d_train.fake_features.{i}"]) < 3e-3, i
+            assert rel_err(r, golden_small[f"d_train.real_features.{i}"]) < 3e-3, i
+        assert all(float(dd["fake_features"][i].min()) >= 0 for i in range(6))       # in-place-ReLU aliasing kept
+        assert float(dd["fake_features"][6].min()) < 0
+        assert rel_err(D.state_dict()["blocks.0.block.2.weight_u"], golden_small["d_train.u_after.blocks.0.block.2"]) < 1e-5
+        D.load_state_dict(small["d_sd"]); D.eval()
+        dd = dict(fake_rgbs=fake, target_rgbs=small["data"]["target_rgbs"].to(DEV), label=small["target"]["label"].to(DEV))
+        D(dd)
+        for k in ("fake_score_G", "fake_score_D", "real_score"):
+            assert rel_err(dd[k], golden_small["d_eval." + k]) < 3e-3, k
+
+
+def test_criteria_values(small, golden_small):
+    cfg = small["cfg"]
+    with tempfile.TemporaryDirectory() as vgg_dir:
+        write_vgg_files(vgg_dir)
+        args = make_args(cfg, device=DEV, vgg_weights_dir=vgg_dir)
+        crit = {n: importlib.import_module(f"criterions.{n}").Wrapper.get_net(args)
+                for n in ("perceptual", "idt_embed", "adversarial", "featmat", "dice", "dis_embed")}
+    D = _D(cfg, small["d_sd"]).eval()
+    with torch.no_grad():
+        dd = dict(fake_rgbs=golden_small["g_eval.fake_rgbs"].to(DEV), target_rgbs=small["data"]["target_rgbs"].to(DEV),
+                  label=small["target"]["label"].to(DEV), fake_segm=golden_small["g_eval.fake_segm"].to(DEV),
+                  real_segm=small["target"]["real_segm"].to(DEV), embeds_elemwise=small["emb"]["embeds_elemwise"].to(DEV))
+        D(dd)
+        got = {}
+        got["VGG"] = crit["perceptual"](dd)["VGG"]
+        got["VGGFace"] = crit["idt_embed"](dd)["VGGFace"]
+        lg, ld = crit["adversarial"](dd)
+        got["adversarial_G"], got["adversarial_D"] = lg["adversarial_G"], ld["adversarial_D"]
+        got["feature_matching"] = crit["featmat"](dd)["feature_matching"]
+        got["segmentation_dice"] = crit["dice"](dd)["segmentation_dice"]
+        got["embedding_matching"] = crit["dis_embed"](dd)["embedding_matching"]
+    for k, v in got.items():
+        ref = float(golden_small["crit." + k])
+        assert abs(float(v) - ref) <= 3e-3 * abs(ref) + 1e-6, (k, float(v), ref)
+
+
+def _run_step(small, skip_discarded):
+    cfg = small["cfg"]
+    runner = importlib.import_module("runners.holycow")
+    with tempfile.TemporaryDirectory() as vgg_dir:
+        write_vgg_files(vgg_dir)
+        args = make_args(cfg, device=DEV, vgg_weights_dir=vgg_dir)
+        crit_list = [importlib.import_module(f"criterions.{n}").Wrapper.get_net(args)
+                     for n in ("idt_embed", "perceptual", "adversarial", "featmat", "dis_embed", "dice")]
+    G, D = _G(cfg, small["g_sd"]), _D(cfg, small["d_sd"])
+    E = StubEmbedder(to_dev(small["emb"], DEV)).to(DEV)
+    tm = runner.TrainingModule(E, G, D, crit_list, [], {})
+    tm.train()
+    opt_G = runner.get_optimizer(E, G, args)
+    opt_D = importlib.import_module("discriminators.no_landmarks").Wrapper.get_optimizer(D, args)
+    bucket_G, bucket_D = tm.grad_buckets(opt_G, opt_D)
+    D.skip_discarded_wgrad = skip_discarded
+    all_dd, lG, lD = tm(to_dev(small["data"], DEV), to_dev(small["target"], DEV))
+    loss_G, loss_D = sum(lG.values()), sum(lD.values())
+    bucket_G.zero()
+    if not skip_discarded:
+        bucket_D.zero()
+    loss_G.backward(retain_graph=True)
+    gradG = {k: p.grad.detach().clone() for k, p in G.named_parameters()}
+    gradE = E.scale.grad.detach().clone()
+    opt_G.step()
+    bucket_D.zero()
+    loss_D.backward()
+    gradD = {k: p.grad.detach().clone() for k, p in D.named_parameters()}
+    opt_D.step()
+    tm.update_running_average(0.999)
+    return dict(lG=lG, lD=lD, gradG=gradG, gradD=gradD, gradE=gradE, G=G, D=D, tm=tm)
+
+
+@pytest.mark.parametrize("skip_discarded", [True, False])
+def test_training_step_losses_and_gradients(small, golden_small, skip_discarded):
+    """One full runner step (all six criteria of configs/default.yaml) against the reference's runner."""
+    r = _run_step(small, skip_discarded)
+    for k, v in {**r["lG"], **r["lD"]}.items():
+        ref = float(golden_small["step.loss." + k])
+        assert abs(float(v) - ref) <= 3e-3 * abs(ref) + 1e-6, (k, float(v), ref)
+    # gradients: TF32 forward + TF32 backward chains; compare norms (all parameters) and full tensors (a selection)
+    for k, ref_norm in golden_small["step.gradG.norms"].items():
+        assert abs(float(r["gradG"][k].norm()) - ref_norm) <= 2e-2 * ref_norm + 1e-7, (k, float(r["gradG"][k].norm()), ref_norm)
+    for k, ref_norm in golden_small["step.gradD.norms"].items():
+        assert abs(float(r["gradD"][k].norm()) - ref_norm) <= 2e-2 * ref_norm + 1e-7, (k, float(r["gradD"][k].norm()), ref_norm)
+    for k, v in golden_small.items():
+        if k.startswith("step.gradG.") and k != "step.gradG.norms":
+            name = k[len("step.gradG."):]
+            assert rel_err(r["gradG"][name], v) < 2e-2, name
+        if k.startswith("step.gradD.") and k != "step.gradD.norms":
+            name = k[len("step.gradD."):]
+            assert rel_err(r["gradD"][name], v) < 2e-2, name
+    ref = float(golden_small["step.gradE.scale"])
+    assert abs(float(r["gradE"]) - ref) <= 2e-2 * abs(ref) + 1e-7
+    # parameters after Adam + EMA
+    g_after = dict(r["G"].named_parameters())["decoder_blocks.0.block.3.weight_orig"]
+    assert max_abs(g_after, golden_small["step.after.G.decoder_blocks.0.block.3.weight_orig"]) < 1.5e-4   # lr_gen * O(1)
+    ema = r["tm"].running_averages["generator"].state_dict()["decoder_blocks.0.block.3.weight_orig"]
+    assert max_abs(ema, golden_small["step.after.ema.G.decoder_blocks.0.block.3.weight_orig"]) < 1e-6
+
+
+def test_full_size_generator_vs_reference(golden_full):
+    """256x256, default channel widths (37.5 M parameters), batch 1, eval: generator RGB within 1e-3 max-abs of the
+    reference's fp32 output and of its float64 output."""
+    cfg = golden_full["cfg"]
+    G = _G(cfg, synth.generator_state_dict(cfg, seed=11)).eval()
+    _, _, emb = synth.make_inputs(cfg, batch=1, seed=14)
+    with torch.no_grad():
+        dd = dict(embeds=emb["embeds"].to(DEV), pose_embedding=emb["pose_embedding"].to(DEV))
+        G(dd)
+    rgb = dd["fake_rgbs"][:, :, ::4, ::4]
+    assert max_abs(rgb, golden_full["g_eval.fake_rgbs.sub4"]) < 1e-3
+    assert max_abs(rgb, golden_full["g_eval.fake_rgbs.sub4.fp64"]) < 1e-3
+    assert max_abs(dd["fake_segm"][:, :, ::4, ::4], golden_full["g_eval.fake_segm.sub4"]) < 1e-3
+    assert abs(float(dd["fake_rgbs"].mean()) - float(golden_full["g_eval.fake_rgbs.mean"])) < 1e-4
+
+
+def test_full_size_batch_properties():
+    """Size-independent properties at BASELINE's full size (bs=8, 256x256): determinism, per-sample independence
+    (InstanceNorm statistics are per sample), output range of the rgb*segm composition."""
+    cfg = synth.FULL_CFG
+    G = _G(cfg, synth.generator_state_dict(cfg, seed=11)).eval()
+    _, _, emb = synth.make_inputs(cfg, batch=8, seed=15)
+    with torch.no_grad():
+        dd = dict(embeds=emb["embeds"].to(DEV), pose_embedding=emb["pose_embedding"].to(DEV))
+        G(dd)
+        out8 = dd["fake_rgbs"].clone()
+        G(dd)
+        assert torch.equal(out8, dd["fake_rgbs"])                                   # bit-deterministic
+        d1 = dict(embeds=emb["embeds"][3:4].to(DEV), pose_embedding=emb["pose_embedding"][3:4].to(DEV))
+        G(d1)
+        assert max_abs(d1["fake_rgbs"][0], out8[3]) < 1e-4                           # sample 3 alone == sample 3 in batch
+    assert torch.isfinite(out8).all()
+    assert float(out8.min()) >= -0.25 - 1e-6 and float(out8.max()) <= 1.25 + 1e-6
+    assert float(dd["fake_segm"].min()) >= 0 and float(dd["fake_segm"].max()) <= 1
