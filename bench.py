@@ -1,0 +1,394 @@
+"""Benchmark of the hot path (BASELINE.json metric: 256x256 reenactment frames/s, train step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload finetune|metatrain|drive] [--impl reference]
+
+One "step" = one full optimisation step of the reference's runner (runners/holycow.py:224-257) on a batch of 8
+synthetic 256x256 samples per GPU: embedder -> generator -> discriminator x3 -> criteria -> loss_G.backward ->
+optimizer_G -> loss_D.backward -> optimizer_D -> EMA.  Default workload = BASELINE.json configs[1]
+(`finetuning-base`: criteria adversarial+featmat+idt_embed+perceptual+dice, RAdam, EMA 0.972, identity encoder off),
+per-GPU batch fixed as N grows (weak scaling, one NCCL all-reduce per backward).
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with the batches already resident in HBM; `e2e` = the same metric
+through the public plugin API with pinned HOST batches (H2D inside the timed region, loss values read back).
+`--impl reference` times the CPU port of the reference step (oracle/cpu_step.py) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+PKG = ROOT / "latent-pose-reenactment_b200"
+for _p in (str(PKG), str(ROOT)):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch
+
+METRIC = "256x256 reenactment frames/sec (train step)"
+UNIT = "frames/s"
+FULL = dict(num_channels=64, max_num_channels=512, embed_channels=512, pose_embedding_size=256, image_size=256,
+            dis_num_blocks=7)
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "finetune": dict(desc="configs[1] finetuning-base: bs=8/GPU 256x256, adversarial+featmat+idt_embed+perceptual+dice, "
+                          "RAdam, EMA 0.972, identity encoder off",
+                     finetune=True, criteria="adversarial, featmat, idt_embed, perceptual, dice", optimizer="RAdam",
+                     lr_gen=5e-4, lr_dis=8e-4, k_frames=1, num_labels=1),
+    # BASELINE.json configs[2]
+    "metatrain": dict(desc="configs[2] default: bs=8/GPU 256x256, K=8 identity frames, all six criteria, Adam, EMA 0.999",
+                      finetune=False, criteria="idt_embed, perceptual, adversarial, featmat, dis_embed, dice",
+                      optimizer="Adam", lr_gen=5e-5, lr_dis=2e-4, k_frames=8, num_labels=16),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="finetune", choices=list(WORKLOADS) + ["drive"])
+    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def make_namespace(wl, device, vgg_dir, batch):
+    from argparse import Namespace
+    return Namespace(
+        gen_padding="zero", in_channels=3, out_channels=3, norm_layer="in", gen_constant_input_size=4,
+        gen_num_residual_blocks=2, device=device, average_function="sum", dis_padding="zero",
+        num_labels=wl["num_labels"], gan_type="gan", fm_weight=10.0, dice_weight=1.0, perc_weight=3e-2,
+        idt_embed_weight=6e-3, dis_embed_weight=1e-2, vgg_weights_dir=vgg_dir, optimizer=wl["optimizer"],
+        lr_gen=wl["lr_gen"], lr_dis=wl["lr_dis"], beta1=0.0, finetune=wl["finetune"], num_gpus=1, batch_size=batch,
+        **FULL)
+
+
+def fabricate_vgg_files(dirname, seed=3):
+    """No network: VGG19 / VGG-Face weight files with He-initialised weights in the layout the criterion reads."""
+    g = torch.Generator().manual_seed(seed)
+    plans = {"vgg19": ((0, 2, 5, 7, 10, 12, 14, 16, 19, 21, 23, 25, 28), (64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512)),
+             "vgg16": ((0, 2, 5, 7, 10, 12, 14, 17, 19, 21, 24, 26, 28), (64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512))}
+    for arch, (idxs, chans) in plans.items():
+        sd, cin = {}, 3
+        for i, c in zip(idxs, chans):
+            w = torch.randn(c, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+            sd[f"{i}.weight"] = w / 64.0 if i == 0 else w
+            sd[f"{i}.bias"] = torch.randn(c, generator=g) * 0.05
+            cin = c
+        if arch == "vgg19":
+            torch.save({"features." + k: v for k, v in sd.items()}, os.path.join(dirname, "vgg19-d01eb7cb.pth"))
+        else:
+            torch.save(sd, os.path.join(dirname, "vgg_face_weights.pth"))
+
+
+def make_host_batches(n, batch, k_frames, num_labels, s=256, seed=123, rank=0):
+    """Pinned host batches with the dataloader's output contract (dataloaders/synthetic.py)."""
+    from dataloaders.synthetic import Dataset
+    ds = Dataset(n * batch * 64, s, k_frames, max(num_labels, 1), seed=seed)
+    out = []
+    for b in range(n):
+        items = [ds[(rank * n + b) * batch + i] for i in range(batch)]
+        data = {k: torch.stack([it[0][k] for it in items]) for k in items[0][0]}
+        target = {"real_segm": torch.stack([it[1]["real_segm"] for it in items]),
+                  "label": torch.tensor([it[1]["label"] for it in items], dtype=torch.long)}
+        if torch.cuda.is_available():
+            data = {k: v.pin_memory() for k, v in data.items()}
+            target = {k: v.pin_memory() for k, v in target.items()}
+        out.append((data, target))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi SM clock + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.stop_flag, self.thread = gpu_index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def timed(fn, steps, dist_on):
+    """K calls of fn(i) between barrier+synchronize on both sides; CUDA-event time, max over ranks (ms)."""
+    if dist_on:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist_on:
+        torch.distributed.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if dist_on:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    return float(ms.item())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(workload, sample_batch, steps, warmup):
+    """frames/s of the CPU port of the reference step (oracle/cpu_step.py) with all host threads."""
+    from oracle.cpu_step import OracleTrainer
+    from oracle import synth
+    wl = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = dict(synth.FULL_CFG)
+    cfg["num_labels"] = max(wl["num_labels"], 1)
+    crit = tuple(c.strip() for c in wl["criteria"].split(","))
+    tr = OracleTrainer(cfg, finetune=wl["finetune"], criteria=crit, optimizer=wl["optimizer"], lr_gen=wl["lr_gen"],
+                       lr_dis=wl["lr_dis"])
+    data, target, _ = synth.make_inputs(cfg, batch=sample_batch, seed=4, n_identity_frames=wl["k_frames"])
+    for _ in range(warmup):
+        tr.step(data, target)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step(data, target)
+    dt = (time.perf_counter() - t0) / steps
+    return sample_batch / dt, dt, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl_name = "finetune" if args.workload == "drive" else args.workload
+    sample_b = 1
+    steps, warmup = max(1, min(args.steps, 6)), max(0, min(args.warmup, 1))
+    rate, dt, cores = cpu_reference_rate(wl_name, sample_b, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[wl_name]["desc"], "global_batch": sample_b,
+                       "note": "reference's CPU implementation of the step (torch CPU operators, oracle port), "
+                               "each step a bounded sample: batch 1 of the same workload"},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{steps} step(s) at batch {sample_b}, fp32, {cores} torch threads"},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def build_training(wl, device, batch):
+    import importlib
+    from b200lp import lib
+    lib.require_device()
+    runner = importlib.import_module("runners.holycow")
+    vgg_dir = tempfile.mkdtemp(prefix="vgg_synth_")
+    fabricate_vgg_files(vgg_dir)
+    ns = make_namespace(wl, device, vgg_dir, batch)
+    torch.manual_seed(123)
+    G = importlib.import_module("generators.vector_pose_unsupervised_segmentation_noBottleneck").Wrapper.get_net(ns)
+    D = importlib.import_module("discriminators.no_landmarks").Wrapper.get_net(ns)
+    E = importlib.import_module("embedders.unsupervised_pose_separate_embResNeXt_segmentation").Wrapper.get_net(ns)
+    crits = [importlib.import_module(f"criterions.{c.strip()}").Wrapper.get_net(ns) for c in wl["criteria"].split(",")]
+    if wl["finetune"]:
+        e = torch.randn(1, FULL["embed_channels"], device=device)
+        G.enable_finetuning({"embeds": e.clone()})
+        D.enable_finetuning({"embeds": e.clone()})
+        E.enable_finetuning()
+        E.requires_grad_(False)      # not in optimizer_G when fine-tuning (runners/holycow.py:35-37)
+    with torch.no_grad():            # a fresh net's spectral-norm vectors are random: converge them
+        for net in (G, D):
+            net.train()
+            for m in net.modules():
+                if hasattr(m, "inv_sigma"):
+                    for _ in range(20):
+                        m.inv_sigma()
+        # AdaIN gains O(1) like a trained net
+        proj = G.affine_params_projector.slot(2)
+        off = 0
+        for c in G.adain_sizes:
+            proj.bias[off + c:off + 2 * c] += 1.0
+            off += 2 * c
+    tm = runner.TrainingModule(E, G, D, crits, [], {})
+    tm.train()
+    opt_G = runner.get_optimizer(E, G, ns)
+    opt_D = importlib.import_module("discriminators.no_landmarks").Wrapper.get_optimizer(D, ns)
+    return runner, tm, opt_G, opt_D, ns
+
+
+def roofline_pass(step_fn, peaks):
+    """One instrumented step: CUDA events around every libb200lp call on the launching stream -> per-family time,
+    algorithmic FLOPs / bytes -> achieved throughput of the dominant kernel family."""
+    from b200lp import kernels as K
+    rec = []
+    K.PROFILE = rec
+    step_fn(0)
+    torch.cuda.synchronize()
+    K.PROFILE = None
+    fam = {}
+    for name, work, e0, e1 in rec:
+        d = fam.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += work.get("flops", 0.0)
+        d["bytes"] += work.get("bytes", 0.0)
+        d["launches"] += 1
+    total_ms = sum(d["ms"] for d in fam.values()) or 1.0
+    table = {k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / total_ms, 3), "launches": v["launches"],
+                 "tflops": round(v["flops"] / v["ms"] / 1e9, 1) if v["flops"] else None,
+                 "gbs": round(v["bytes"] / v["ms"] / 1e6, 1) if v["bytes"] else None}
+             for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    out = {"families": table}
+    conv = fam.get("conv_igemm_tf32")
+    if conv:
+        tf32_peak = peaks.get("bf16_tflops_sustained", 1437.4) / 2.0
+        ach = conv["flops"] / conv["ms"] / 1e9
+        out["roofline"] = {"kernel": "conv_igemm_tf32 (tcgen05 fwd + dgrad)", "bound": "tensor", "achieved": round(ach, 1),
+                           "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": round(ach / tf32_peak, 3),
+                           "traffic": None,
+                           "peak_note": "TF32 dense = measured sustained bf16 cuBLAS TF/s / 2 (MEASURED_PEAKS.json); "
+                                        "frac of the bf16 figure itself = %.3f" % (ach / (2 * tf32_peak)),
+                           "avg_launch_ms": round(conv["ms"] / conv["launches"], 4), "launches_per_step": conv["launches"]}
+    hbm = fam.get("adain_relu")
+    if hbm:
+        ach = hbm["bytes"] / hbm["ms"] / 1e6
+        peak = peaks.get("hbm_gbs", 6580.3)
+        out["roofline_hbm"] = {"kernel": "adain_relu (IN apply + AdaIN + ReLU [+2x])", "bound": "hbm",
+                               "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 3),
+                               "traffic": None}
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    if args.workload == "drive":
+        raise SystemExit("use tools/bench_drive.py for the inference loop")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist_on = world > 1
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+    if dist_on:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group(backend="nccl", init_method="env://", rank=rank, world_size=world)
+    wl = WORKLOADS[args.workload]
+    B = args.batch
+    runner, tm, opt_G, opt_D, ns = build_training(wl, device, B)
+    tm.broadcast_parameters()
+
+    from b200lp import lib
+    from utils import utils as U
+    n_batches = 4
+    host = make_host_batches(n_batches, B, wl["k_frames"], wl["num_labels"], rank=rank)
+    dev_batches = [({k: v.to(device) for k, v in d.items()}, {k: v.to(device) for k, v in t.items()}) for d, t in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0][0].values()) + \
+        sum(v.numel() * v.element_size() for v in host[0][1].values())
+
+    def step_resident(i):
+        d, t = dev_batches[i % n_batches]
+        runner.train_step(tm, dict(d), dict(t), opt_G, opt_D, finetune=wl["finetune"])
+
+    n_losses = [0]
+
+    def step_e2e(i):
+        d, t = host[i % n_batches]
+        d, t = dict(d), dict(t)
+        U.dict_to_device(d, device)
+        U.dict_to_device(t, device)
+        _, lg, ld = runner.train_step(tm, d, t, opt_G, opt_D, finetune=wl["finetune"])
+        vals = torch.stack([v.detach().float().reshape(()) for v in list(lg.values()) + list(ld.values())])
+        n_losses[0] = vals.numel()
+        return vals.cpu()           # device -> host read of the step's result (the runner's Meter does the same)
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = lib.load().b200lp_launch_count()
+    ms = timed(step_resident, args.steps, dist_on)
+    launches = lib.load().b200lp_launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps, dist_on)
+
+    frames = B * world * args.steps
+    value = frames / (ms / 1e3)
+    e2e_value = frames / (ms_e2e / 1e3)
+
+    extra = {}
+    if rank == 0 and not args.no_roofline:
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        extra.update(roofline_pass(step_resident, peaks))
+        extra["peaks_source"] = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    if dist_on:
+        torch.distributed.barrier()
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            rate, dt, cores = cpu_reference_rate(args.workload, 1, 2, 1)
+            cpu_baseline = {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"2 steps at batch 1 of the same workload ({dt:.1f} s/step), fp32, {cores} torch threads"}
+        except Exception as err:   # the checker must never take the product number down with it
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {err}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "tf32 operands / f32 accumulate (f32 storage)",
+                "data": "synthetic",
+                "config": {"workload": wl["desc"], "global_batch": B * world, "per_gpu_batch": B, "image_size": 256,
+                           "parallelism": f"dp{world}", "weights": "random init, spectral norm converged",
+                           "l2": "per-step working set (activations, ~GBs) >> 126 MB L2; 4 distinct input batches cycled"},
+                "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": 4 * n_losses[0], "ms_per_step": round(ms_e2e / args.steps, 3)},
+                "gpu_launches": int(launches), "clocks": clocks}
+        line.update(extra)
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    if dist_on:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 4
+#define B200LP_ABI_VERSION 5
 
 #define B200LP_OK 0
 #define B200LP_EINVAL (-1)   /* bad shape / unsupported configuration */
@@ -49,17 +49,22 @@ int64_t b200lp_launch_count(void);
  * Requirements: Cin % 32 == 0, Cout % 32 == 0, H and W powers of two >= 2, ksize in {1,3}.
  */
 typedef struct {
-    const float* x;         /* [N,H,W,Cin] NHWC                                        */
-    const float* wp;        /* [Cout][ksize*ksize][Cin] packed, tf32-rounded           */
-    const float* bias;      /* [Cout] or NULL                                          */
-    const float* residual;  /* NULL, or [N,H,W,Cout] (mode 1), or [N,H/2,W/2,Cout] (mode 2: nearest-2x source) */
-    float* y;               /* [N,H,W,Cout]                                            */
+    const void* x;          /* precision 0: float [N,H,W,Cin] NHWC (tf32-rounded values)
+                               precision 1: bf16  [2][N,H,W,Cin] = (hi, lo) planes, hi + lo == value            */
+    const void* wp;         /* packed weights [Cout][ksize*ksize][Cin]: float (tf32) or bf16 [2][...] (hi, lo)   */
+    const float* bias;      /* [Cout] or NULL                                                                    */
+    const float* residual;  /* NULL, or [N,H,W,Cout] (mode 1), or [N,H/2,W/2,Cout] (mode 2: nearest-2x source)    */
+    float* y;               /* [N,H,W,Cout] fp32                                                                 */
+    void* y_split;          /* NULL, or bf16 [2][N,H,W,Cout]: the same result as (hi, lo) planes (operand of a
+                               following bf16x3 convolution)                                                    */
     int32_t N, H, W, Cin, Cout;
     int32_t ksize;          /* 1 or 3                                                  */
     int32_t residual_mode;  /* 0 none, 1 same resolution, 2 half resolution            */
     int32_t relu;           /* 1: y = max(y, 0)                                        */
-    int32_t round_tf32;     /* 1: round y to tf32 (y only feeds further MMAs)          */
-    int32_t block_n;        /* 0 = auto; else 64 / 128 / 256                           */
+    int32_t round_tf32;     /* 1: round y to tf32 (y only feeds further tf32 MMAs)     */
+    int32_t block_n;        /* 0 = auto; else 32 / 64 / 128 / 256 (256: tf32 only)     */
+    int32_t precision;      /* 0 = tf32 (1 MMA / K-step), 1 = bf16x3 (3 MMAs: Ah*Bh + Ah*Bl + Al*Bh, ~fp32 accuracy) */
+    int32_t reserved;
 } b200lp_conv_args;
 
 int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream);
@@ -71,9 +76,10 @@ int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream);
  *   transpose = 0:  wp[co][tap][ci]      = tf32( w[co][ci][kh][kw] * (*scale) )          (forward)
  *   transpose = 1:  wp[ci][T-1-tap][co]  = tf32( w[co][ci][kh][kw] * (*scale) )          (data-gradient)
  * `scale` is a device pointer to one float (1/sigma) or NULL for 1.0.
+ * precision 0: `wp` is float (tf32-rounded); precision 1: `wp` is bf16 [2][...] = (hi, lo) planes (bf16x3 operand).
  */
-int32_t b200lp_pack_conv_weight(const float* w_oihw, const float* scale, float* wp, int32_t Cout, int32_t Cin,
-                                int32_t ksize, int32_t transpose, void* stream);
+int32_t b200lp_pack_conv_weight(const float* w_oihw, const float* scale, void* wp, int32_t Cout, int32_t Cin,
+                                int32_t ksize, int32_t transpose, int32_t precision, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Weight gradient of the same convolutions on tcgen05 (torch autograd's conv backward-filter).
@@ -105,9 +111,11 @@ int32_t b200lp_conv_wgrad(const b200lp_wgrad_args* a, void* stream);
 int64_t b200lp_in_stats_workspace(int32_t N, int32_t HW, int32_t C);
 int32_t b200lp_in_stats(const float* x, float* mean, float* rstd, float* workspace, int64_t workspace_bytes,
                         int32_t N, int32_t HW, int32_t C, float eps, void* stream);
+/* `y` (fp32, tf32-rounded if round_tf32) and/or `y_split` (bf16 [2][...]: (hi, lo) planes of the UNROUNDED result, the
+ * operand of a bf16x3 convolution) may be given; at least one. */
 int32_t b200lp_adain_relu(const float* x, const float* mean, const float* rstd, const float* gamma,
-                          const float* beta, int64_t affine_stride, float* y, int32_t N, int32_t H, int32_t W,
-                          int32_t C, int32_t upsample2, int32_t round_tf32, void* stream);
+                          const float* beta, int64_t affine_stride, float* y, void* y_split, int32_t N, int32_t H,
+                          int32_t W, int32_t C, int32_t upsample2, int32_t round_tf32, void* stream);
 /* backward of the above: given dy (w.r.t. the post-ReLU, possibly 2x-upsampled output) produce
  * dx, dgamma[n,c], dbeta[n,c].  The ReLU mask is recomputed from x (no saved activation needed). */
 int64_t b200lp_adain_relu_bwd_workspace(int32_t N, int32_t HW, int32_t C);

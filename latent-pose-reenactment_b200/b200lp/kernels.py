@@ -9,39 +9,84 @@ import torch
 from . import lib as L
 
 
+# bench.py's roofline pass: when PROFILE is a list, every C-ABI call is bracketed by CUDA events on the launching
+# stream and recorded as (kernel family, algorithmic work {flops|bytes}, start event, end event).
+PROFILE = None
+
+
+class _timed:
+    def __init__(self, family, flops=0.0, nbytes=0.0):
+        self.family, self.work = family, {"flops": float(flops), "bytes": float(nbytes)}
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.family, self.work, self.e0, e1))
+        return False
+
+
 def _ws(nbytes, device):
     return torch.empty(max(int(nbytes) // 4, 1), dtype=torch.float32, device=device)
 
 
-def pack_conv_weight(w_oihw, scale=None, transpose=False):
-    """OIHW fp32 -> packed [Cout][tap][Cin] (or [Cin][tap'][Cout] when transpose) tf32, times *scale (device scalar)."""
+TF32, BF16X3 = 0, 1   # operand precisions of the tensor-core convolution (include/b200lp.h: `precision`)
+
+
+def pack_conv_weight(w_oihw, scale=None, transpose=False, precision=TF32):
+    """OIHW fp32 -> packed [Cout][tap][Cin] (or [Cin][tap'][Cout] when transpose), times *scale (device scalar):
+    float32 holding tf32 values (precision TF32) or bfloat16 (2, ...) = (hi, lo) planes (precision BF16X3)."""
     lib = L.load()
     co, ci, kh, kw = w_oihw.shape
     assert kh == kw and kh in (1, 3)
-    out = torch.empty((ci, kh * kw, co) if transpose else (co, kh * kw, ci), dtype=torch.float32, device=w_oihw.device)
-    L.check(lib.b200lp_pack_conv_weight(L.ptr(w_oihw.contiguous()), L.ptr(scale), L.ptr(out), co, ci, kh,
-                                        1 if transpose else 0, L.stream_ptr()), "pack_conv_weight")
+    shape = (ci, kh * kw, co) if transpose else (co, kh * kw, ci)
+    if precision == TF32:
+        out = torch.empty(shape, dtype=torch.float32, device=w_oihw.device)
+    else:
+        out = torch.empty((2,) + shape, dtype=torch.bfloat16, device=w_oihw.device)
+    with _timed("pack_conv_weight", nbytes=8.0 * w_oihw.numel()):
+        L.check(lib.b200lp_pack_conv_weight(L.ptr(w_oihw.contiguous()), L.ptr(scale), c_void_p(out.data_ptr()), co, ci,
+                                            kh, 1 if transpose else 0, precision, L.stream_ptr()), "pack_conv_weight")
     return out
 
 
 def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False, round_tf32=False, block_n=0,
-             out=None):
-    """x (N,H,W,Cin) NHWC, wp packed (Cout, k*k, Cin) -> y (N,H,W,Cout)."""
+             out=None, emit_split=False):
+    """x NHWC (N,H,W,Cin) float32 [TF32] or (2,N,H,W,Cin) bfloat16 (hi, lo) [BF16X3]; wp packed to match.
+    Returns y (N,H,W,Cout) float32, or (y, y_split) with y_split (2,N,H,W,Cout) bfloat16 when emit_split."""
     lib = L.load()
-    n, h, w, cin = x.shape
-    cout = wp.shape[0]
-    assert wp.shape[1] == ksize * ksize and wp.shape[2] == cin, (wp.shape, ksize, cin)
+    split_in = x.dtype == torch.bfloat16
+    if split_in:
+        assert x.dim() == 5 and wp.dtype == torch.bfloat16 and wp.dim() == 4, (x.shape, wp.shape)
+        _, n, h, w, cin = x.shape
+        cout = wp.shape[1]
+        assert wp.shape[2] == ksize * ksize and wp.shape[3] == cin, (wp.shape, ksize, cin)
+    else:
+        n, h, w, cin = x.shape
+        cout = wp.shape[0]
+        assert wp.dtype == torch.float32 and wp.shape[1] == ksize * ksize and wp.shape[2] == cin, (wp.shape, ksize, cin)
     y = out if out is not None else torch.empty((n, h, w, cout), dtype=torch.float32, device=x.device)
+    y_split = torch.empty((2, n, h, w, cout), dtype=torch.bfloat16, device=x.device) if emit_split else None
     a = L.ConvArgs()
-    a.x = L.ptr(x); a.wp = L.ptr(wp); a.bias = L.ptr(bias); a.residual = L.ptr(residual); a.y = L.ptr(y)
+    a.x = L.ptr(x, x.dtype); a.wp = L.ptr(wp, wp.dtype); a.bias = L.ptr(bias); a.residual = L.ptr(residual)
+    a.y = L.ptr(y); a.y_split = L.ptr(y_split, torch.bfloat16)
     a.N, a.H, a.W, a.Cin, a.Cout = n, h, w, cin, cout
     a.ksize = ksize
     a.residual_mode = residual_mode if residual is not None else 0
     a.relu = int(relu)
     a.round_tf32 = int(round_tf32)
     a.block_n = block_n
-    L.check(lib.b200lp_conv_fwd(byref(a), L.stream_ptr()), "conv_fwd")
-    return y
+    a.precision = BF16X3 if split_in else TF32
+    with _timed("conv_igemm_bf16x3" if split_in else "conv_igemm_tf32",
+                flops=2.0 * n * h * w * cin * cout * ksize * ksize):
+        L.check(lib.b200lp_conv_fwd(byref(a), L.stream_ptr()), "conv_fwd")
+    return (y, y_split) if emit_split else y
 
 
 def conv_wgrad(x, dy, ksize, scale=1.0):
@@ -60,7 +105,8 @@ def conv_wgrad(x, dy, ksize, scale=1.0):
     a.N, a.H, a.W, a.Cin, a.Cout = n, h, w, cin, cout
     a.ksize = ksize
     a.scale = float(scale)
-    L.check(lib.b200lp_conv_wgrad(byref(a), L.stream_ptr()), "conv_wgrad")
+    with _timed("conv_wgrad_tf32", flops=2.0 * n * h * w * cin * cout * ksize * ksize):
+        L.check(lib.b200lp_conv_wgrad(byref(a), L.stream_ptr()), "conv_wgrad")
     return dw
 
 
@@ -71,8 +117,9 @@ def in_stats(x, eps):
     ws = _ws(lib.b200lp_in_stats_workspace(n, h * w, c), x.device)
     mean = torch.empty((n, c), dtype=torch.float32, device=x.device)
     rstd = torch.empty_like(mean)
-    L.check(lib.b200lp_in_stats(L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(ws), ws.numel() * 4, n, h * w, c,
-                                c_float(eps), L.stream_ptr()), "in_stats")
+    with _timed("in_stats", nbytes=4.0 * x.numel()):
+        L.check(lib.b200lp_in_stats(L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(ws), ws.numel() * 4, n, h * w, c,
+                                    c_float(eps), L.stream_ptr()), "in_stats")
     return mean, rstd
 
 
@@ -83,15 +130,22 @@ def _affine_views(gamma, beta):
     return c_void_p(gamma.data_ptr()), c_void_p(beta.data_ptr()), gamma.stride(0)
 
 
-def adain_relu(x, mean, rstd, gamma, beta, upsample2=False, round_tf32=True):
+def adain_relu(x, mean, rstd, gamma, beta, upsample2=False, round_tf32=True, want_f32=True, want_split=False):
+    """Returns y (fp32) / (y, y_split) / y_split according to want_f32 / want_split; y_split is (2,N,H',W',C) bf16."""
     lib = L.load()
     n, h, w, c = x.shape
     gp, bp, stride = _affine_views(gamma, beta)
     s = 2 if upsample2 else 1
-    y = torch.empty((n, h * s, w * s, c), dtype=torch.float32, device=x.device)
-    L.check(lib.b200lp_adain_relu(L.ptr(x), L.ptr(mean), L.ptr(rstd), gp, bp, stride, L.ptr(y), n, h, w, c,
-                                  int(upsample2), int(round_tf32), L.stream_ptr()), "adain_relu")
-    return y
+    y = torch.empty((n, h * s, w * s, c), dtype=torch.float32, device=x.device) if want_f32 else None
+    ys = torch.empty((2, n, h * s, w * s, c), dtype=torch.bfloat16, device=x.device) if want_split else None
+    out_elems = n * h * s * w * s * c
+    with _timed("adain_relu", nbytes=4.0 * (x.numel() + out_elems * (int(want_f32) + int(want_split)))):
+        L.check(lib.b200lp_adain_relu(L.ptr(x), L.ptr(mean), L.ptr(rstd), gp, bp, stride, L.ptr(y),
+                                      L.ptr(ys, torch.bfloat16), n, h, w, c, int(upsample2), int(round_tf32),
+                                      L.stream_ptr()), "adain_relu")
+    if want_f32 and want_split:
+        return y, ys
+    return y if want_f32 else ys
 
 
 def adain_relu_bwd(x, mean, rstd, gamma, beta, dy, upsample2=False):
@@ -102,9 +156,10 @@ def adain_relu_bwd(x, mean, rstd, gamma, beta, dy, upsample2=False):
     dx = torch.empty_like(x)
     dgamma = torch.empty((n, c), dtype=torch.float32, device=x.device)
     dbeta = torch.empty_like(dgamma)
-    L.check(lib.b200lp_adain_relu_bwd(L.ptr(x), L.ptr(mean), L.ptr(rstd), gp, bp, stride, L.ptr(dy), L.ptr(dx),
-                                      L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), ws.numel() * 4, n, h, w, c,
-                                      int(upsample2), L.stream_ptr()), "adain_relu_bwd")
+    with _timed("adain_relu_bwd", nbytes=4.0 * (2 * x.numel() + dy.numel())):   # ideal: read x, dy once; write dx
+        L.check(lib.b200lp_adain_relu_bwd(L.ptr(x), L.ptr(mean), L.ptr(rstd), gp, bp, stride, L.ptr(dy), L.ptr(dx),
+                                          L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), ws.numel() * 4, n, h, w, c,
+                                          int(upsample2), L.stream_ptr()), "adain_relu_bwd")
     return dx, dgamma, dbeta
 
 
@@ -127,14 +182,16 @@ def nhwc_to_nchw(x):
 def relu_round(x):
     lib = L.load()
     y = torch.empty_like(x)
-    L.check(lib.b200lp_relu_round(L.ptr(x), L.ptr(y), x.numel(), L.stream_ptr()), "relu_round")
+    with _timed("elementwise", nbytes=8.0 * x.numel()):
+        L.check(lib.b200lp_relu_round(L.ptr(x), L.ptr(y), x.numel(), L.stream_ptr()), "relu_round")
     return y
 
 
 def relu_bwd(y, dy):
     lib = L.load()
     dx = torch.empty_like(dy)
-    L.check(lib.b200lp_relu_bwd(L.ptr(y), L.ptr(dy), L.ptr(dx), dy.numel(), L.stream_ptr()), "relu_bwd")
+    with _timed("elementwise", nbytes=12.0 * dy.numel()):
+        L.check(lib.b200lp_relu_bwd(L.ptr(y), L.ptr(dy), L.ptr(dx), dy.numel(), L.stream_ptr()), "relu_bwd")
     return dx
 
 
@@ -142,8 +199,9 @@ def avgpool2(x, addend=None, round_tf32=False):
     lib = L.load()
     n, h2, w2, c = x.shape
     y = torch.empty((n, h2 // 2, w2 // 2, c), dtype=torch.float32, device=x.device)
-    L.check(lib.b200lp_avgpool2(L.ptr(x), L.ptr(addend), L.ptr(y), n, h2 // 2, w2 // 2, c, int(round_tf32),
-                                L.stream_ptr()), "avgpool2")
+    with _timed("elementwise", nbytes=4.0 * (x.numel() + y.numel())):
+        L.check(lib.b200lp_avgpool2(L.ptr(x), L.ptr(addend), L.ptr(y), n, h2 // 2, w2 // 2, c, int(round_tf32),
+                                    L.stream_ptr()), "avgpool2")
     return y
 
 
@@ -151,7 +209,8 @@ def avgpool2_bwd(dy):
     lib = L.load()
     n, h, w, c = dy.shape
     dx = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.float32, device=dy.device)
-    L.check(lib.b200lp_avgpool2_bwd(L.ptr(dy), L.ptr(dx), n, h, w, c, L.stream_ptr()), "avgpool2_bwd")
+    with _timed("elementwise", nbytes=4.0 * (dy.numel() + dx.numel())):
+        L.check(lib.b200lp_avgpool2_bwd(L.ptr(dy), L.ptr(dx), n, h, w, c, L.stream_ptr()), "avgpool2_bwd")
     return dx
 
 
@@ -159,14 +218,16 @@ def upsample2_bwd(dy):
     lib = L.load()
     n, h2, w2, c = dy.shape
     dx = torch.empty((n, h2 // 2, w2 // 2, c), dtype=torch.float32, device=dy.device)
-    L.check(lib.b200lp_upsample2_bwd(L.ptr(dy), L.ptr(dx), n, h2 // 2, w2 // 2, c, L.stream_ptr()), "upsample2_bwd")
+    with _timed("elementwise", nbytes=4.0 * (dy.numel() + dx.numel())):
+        L.check(lib.b200lp_upsample2_bwd(L.ptr(dy), L.ptr(dx), n, h2 // 2, w2 // 2, c, L.stream_ptr()), "upsample2_bwd")
     return dx
 
 
 def l1_sum(a, b, out, scale):
     """out[0] += scale * sum|a-b| (out: 1-element device tensor, caller zeroes it)."""
     lib = L.load()
-    L.check(lib.b200lp_l1_sum(L.ptr(a), L.ptr(b), L.ptr(out), a.numel(), c_float(scale), L.stream_ptr()), "l1_sum")
+    with _timed("l1", nbytes=8.0 * a.numel()):
+        L.check(lib.b200lp_l1_sum(L.ptr(a), L.ptr(b), L.ptr(out), a.numel(), c_float(scale), L.stream_ptr()), "l1_sum")
 
 
 def l1_bwd(a, b, gscale, scale2, da=None):
@@ -175,8 +236,9 @@ def l1_bwd(a, b, gscale, scale2, da=None):
     acc = da is not None
     if da is None:
         da = torch.empty_like(a)
-    L.check(lib.b200lp_l1_bwd(L.ptr(a), L.ptr(b), L.ptr(gscale), c_float(scale2), L.ptr(da), a.numel(), int(acc),
-                              L.stream_ptr()), "l1_bwd")
+    with _timed("l1", nbytes=12.0 * a.numel()):
+        L.check(lib.b200lp_l1_bwd(L.ptr(a), L.ptr(b), L.ptr(gscale), c_float(scale2), L.ptr(da), a.numel(), int(acc),
+                                  L.stream_ptr()), "l1_bwd")
     return da
 
 
@@ -186,9 +248,10 @@ def conv3x3_c3_fwd(x_nchw, w, wscale=None, bias=None, pre_scale=None, pre_shift=
     assert c == 3
     cout = w.shape[0]
     y = torch.empty((n, h, wd, cout), dtype=torch.float32, device=x_nchw.device)
-    L.check(lib.b200lp_conv3x3_c3_fwd(L.ptr(x_nchw), L.ptr(w), L.ptr(wscale), L.ptr(bias), L.ptr(pre_scale),
-                                      L.ptr(pre_shift), L.ptr(y), n, h, wd, cout, int(relu), int(round_tf32),
-                                      L.stream_ptr()), "conv3x3_c3_fwd")
+    with _timed("direct_conv", nbytes=4.0 * (x_nchw.numel() + y.numel())):
+        L.check(lib.b200lp_conv3x3_c3_fwd(L.ptr(x_nchw), L.ptr(w), L.ptr(wscale), L.ptr(bias), L.ptr(pre_scale),
+                                          L.ptr(pre_shift), L.ptr(y), n, h, wd, cout, int(relu), int(round_tf32),
+                                          L.stream_ptr()), "conv3x3_c3_fwd")
     return y
 
 
@@ -196,8 +259,9 @@ def conv3x3_c3_dgrad(dy, w, wscale=None, pre_scale=None):
     lib = L.load()
     n, h, wd, cout = dy.shape
     dx = torch.empty((n, 3, h, wd), dtype=torch.float32, device=dy.device)
-    L.check(lib.b200lp_conv3x3_c3_dgrad(L.ptr(dy), L.ptr(w), L.ptr(wscale), L.ptr(pre_scale), L.ptr(dx), n, h, wd,
-                                        cout, L.stream_ptr()), "conv3x3_c3_dgrad")
+    with _timed("direct_conv", nbytes=4.0 * (dy.numel() + dx.numel())):
+        L.check(lib.b200lp_conv3x3_c3_dgrad(L.ptr(dy), L.ptr(w), L.ptr(wscale), L.ptr(pre_scale), L.ptr(dx), n, h, wd,
+                                            cout, L.stream_ptr()), "conv3x3_c3_dgrad")
     return dx
 
 
@@ -205,8 +269,9 @@ def conv3x3_c3_wgrad(x_nchw, dy, scale=1.0):
     lib = L.load()
     n, h, wd, cout = dy.shape
     dw = torch.empty((cout, 3, 3, 3), dtype=torch.float32, device=dy.device)
-    L.check(lib.b200lp_conv3x3_c3_wgrad(L.ptr(x_nchw), L.ptr(dy), L.ptr(dw), c_float(scale), n, h, wd, cout,
-                                        L.stream_ptr()), "conv3x3_c3_wgrad")
+    with _timed("direct_conv", nbytes=4.0 * (dy.numel() + x_nchw.numel())):
+        L.check(lib.b200lp_conv3x3_c3_wgrad(L.ptr(x_nchw), L.ptr(dy), L.ptr(dw), c_float(scale), n, h, wd, cout,
+                                            L.stream_ptr()), "conv3x3_c3_wgrad")
     return dw
 
 
@@ -216,8 +281,9 @@ def gen_tail_fwd(x, w, wscale, bias):
     rgbs = torch.empty((n, 3, h, wd), dtype=torch.float32, device=x.device)
     segm = torch.empty((n, 1, h, wd), dtype=torch.float32, device=x.device)
     t = torch.empty((n, h, wd, 4), dtype=torch.float32, device=x.device)
-    L.check(lib.b200lp_gen_tail_fwd(L.ptr(x), L.ptr(w), L.ptr(wscale), L.ptr(bias), L.ptr(rgbs), L.ptr(segm),
-                                    L.ptr(t), n, h, wd, cin, L.stream_ptr()), "gen_tail_fwd")
+    with _timed("direct_conv", nbytes=4.0 * (x.numel() + rgbs.numel() + segm.numel() + t.numel())):
+        L.check(lib.b200lp_gen_tail_fwd(L.ptr(x), L.ptr(w), L.ptr(wscale), L.ptr(bias), L.ptr(rgbs), L.ptr(segm),
+                                        L.ptr(t), n, h, wd, cin, L.stream_ptr()), "gen_tail_fwd")
     return rgbs, segm, t
 
 
@@ -225,18 +291,21 @@ def gen_tail_bwd(x, t, w, wscale, d_rgbs, d_segm, need_dx=True, need_dw=True):
     lib = L.load()
     n, h, wd, cin = x.shape
     da = torch.empty((n, h, wd, 4), dtype=torch.float32, device=x.device)
-    L.check(lib.b200lp_gen_tail_bwd_act(L.ptr(t), L.ptr(d_rgbs), L.ptr(d_segm), L.ptr(da), n, h, wd,
-                                        L.stream_ptr()), "gen_tail_bwd_act")
+    with _timed("direct_conv", nbytes=4.0 * 3 * da.numel()):
+        L.check(lib.b200lp_gen_tail_bwd_act(L.ptr(t), L.ptr(d_rgbs), L.ptr(d_segm), L.ptr(da), n, h, wd,
+                                            L.stream_ptr()), "gen_tail_bwd_act")
     dx = dw = db = None
     if need_dx:
         dx = torch.empty_like(x)
-        L.check(lib.b200lp_gen_tail_bwd_data(L.ptr(da), L.ptr(w), L.ptr(wscale), L.ptr(dx), n, h, wd, cin,
-                                             L.stream_ptr()), "gen_tail_bwd_data")
+        with _timed("direct_conv", nbytes=4.0 * (da.numel() + dx.numel())):
+            L.check(lib.b200lp_gen_tail_bwd_data(L.ptr(da), L.ptr(w), L.ptr(wscale), L.ptr(dx), n, h, wd, cin,
+                                                 L.stream_ptr()), "gen_tail_bwd_data")
     if need_dw:
         dw = torch.empty((4, cin, 3, 3), dtype=torch.float32, device=x.device)
         db = torch.empty((4,), dtype=torch.float32, device=x.device)
-        L.check(lib.b200lp_gen_tail_bwd_weight(L.ptr(x), L.ptr(da), L.ptr(dw), L.ptr(db), n, h, wd, cin,
-                                               L.stream_ptr()), "gen_tail_bwd_weight")
+        with _timed("direct_conv", nbytes=4.0 * (da.numel() + x.numel())):
+            L.check(lib.b200lp_gen_tail_bwd_weight(L.ptr(x), L.ptr(da), L.ptr(dw), L.ptr(db), n, h, wd, cin,
+                                                   L.stream_ptr()), "gen_tail_bwd_weight")
     return dx, dw, db
 
 
@@ -244,5 +313,6 @@ def bias_grad(dy):
     lib = L.load()
     c = dy.shape[-1]
     db = torch.empty((c,), dtype=torch.float32, device=dy.device)
-    L.check(lib.b200lp_bias_grad(L.ptr(dy), L.ptr(db), dy.numel() // c, c, L.stream_ptr()), "bias_grad")
+    with _timed("elementwise", nbytes=4.0 * dy.numel()):
+        L.check(lib.b200lp_bias_grad(L.ptr(dy), L.ptr(db), dy.numel() // c, c, L.stream_ptr()), "bias_grad")
     return db

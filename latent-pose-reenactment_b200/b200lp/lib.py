@@ -13,7 +13,7 @@ import torch
 
 _PKG = Path(__file__).resolve().parent.parent
 LIB_PATH = _PKG / "lib" / "libb200lp.so"
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class B200lpError(RuntimeError):
@@ -23,9 +23,10 @@ class B200lpError(RuntimeError):
 class ConvArgs(Structure):
     _fields_ = [
         ("x", c_void_p), ("wp", c_void_p), ("bias", c_void_p), ("residual", c_void_p), ("y", c_void_p),
+        ("y_split", c_void_p),
         ("N", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("Cout", c_int32),
         ("ksize", c_int32), ("residual_mode", c_int32), ("relu", c_int32), ("round_tf32", c_int32),
-        ("block_n", c_int32),
+        ("block_n", c_int32), ("precision", c_int32), ("reserved", c_int32),
     ]
 
 
@@ -50,12 +51,12 @@ SIGNATURES = {
     "b200lp_device_cc": (_I, []),
     "b200lp_launch_count": (_L, []),
     "b200lp_conv_fwd": (_I, [POINTER(ConvArgs), _P]),
-    "b200lp_pack_conv_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_pack_conv_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200lp_conv_wgrad_workspace": (_L, [_I, _I, _I, _I, _I, _I]),
     "b200lp_conv_wgrad": (_I, [POINTER(WgradArgs), _P]),
     "b200lp_in_stats_workspace": (_L, [_I, _I, _I]),
     "b200lp_in_stats": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _F, _P]),
-    "b200lp_adain_relu": (_I, [_P, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "b200lp_adain_relu": (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "b200lp_adain_relu_bwd_workspace": (_L, [_I, _I, _I]),
     "b200lp_adain_relu_bwd": (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "b200lp_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P]),
@@ -122,14 +123,14 @@ def stream_ptr():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def ptr(t):
-    """Raw device pointer of a contiguous fp32 CUDA tensor (None -> NULL)."""
+def ptr(t, dtype=torch.float32):
+    """Raw device pointer of a contiguous CUDA tensor of the given dtype (None -> NULL)."""
     if t is None:
         return None
     if not t.is_cuda:
         raise B200lpError("b200lp kernels need CUDA tensors (there is no CPU fallback)")
-    if t.dtype != torch.float32 or not t.is_contiguous():
-        raise B200lpError(f"expected contiguous float32 tensor, got {t.dtype} contiguous={t.is_contiguous()}")
+    if t.dtype != dtype or not t.is_contiguous():
+        raise B200lpError(f"expected contiguous {dtype} tensor, got {t.dtype} contiguous={t.is_contiguous()}")
     return c_void_p(t.data_ptr())
 
 

@@ -13,6 +13,24 @@ def _dot(a, b):
     return (a * b).sum()
 
 
+def _conv_backward(ctx_ksize, x_f32, weight_orig, inv_sigma, dy, need_x, need_w, need_s):
+    """Shared backward of the tensor-core convolutions (TF32 data / weight gradient kernels)."""
+    dx = dw = ds = None
+    if need_x:
+        wpt = K.pack_conv_weight(weight_orig, inv_sigma, transpose=True)
+        dx = K.conv_fwd(dy, wpt, ctx_ksize)
+    if need_w or (need_s and inv_sigma is not None):
+        g = K.conv_wgrad(x_f32, dy, ctx_ksize)
+        if inv_sigma is not None:
+            if need_s:
+                ds = _dot(g, weight_orig).reshape(inv_sigma.shape)
+            if need_w:
+                dw = g * inv_sigma
+        else:
+            dw = g
+    return dx, dw, ds
+
+
 class Conv2dFn(torch.autograd.Function):
     """y = epilogue(conv_k(x, weight_orig * inv_sigma)).  Replaces nn.Conv2d under spectral_norm
     (generators/common/blocks.py:78-100, discriminators/no_landmarks.py:54-66) and its autograd backward.
@@ -23,48 +41,102 @@ class Conv2dFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, weight_orig, inv_sigma, bias, residual, ksize, residual_mode, relu, round_out):
-        wp = K.pack_conv_weight(weight_orig, inv_sigma, transpose=False)
-        y = K.conv_fwd(x, wp, ksize, bias=bias, residual=residual, residual_mode=residual_mode, relu=relu,
-                       round_tf32=round_out)
+    def forward(ctx, x, weight_orig, inv_sigma, bias, residual, ksize, residual_mode, relu, round_out, x_split,
+                emit_split):
+        """`x_split` (optional, non-differentiable): the (hi, lo) bf16 planes of x — when given, the forward runs in
+        bf16x3 precision on them; gradients still flow to `x`.  `emit_split`: also return the (hi, lo) planes of y."""
+        if x_split is not None:
+            wp = K.pack_conv_weight(weight_orig, inv_sigma, transpose=False, precision=K.BF16X3)
+            src = x_split
+        else:
+            wp = K.pack_conv_weight(weight_orig, inv_sigma, transpose=False)
+            src = x
+        out = K.conv_fwd(src, wp, ksize, bias=bias, residual=residual, residual_mode=residual_mode, relu=relu,
+                         round_tf32=round_out, emit_split=emit_split)
+        y, y_split = out if emit_split else (out, None)
         ctx.ksize, ctx.residual_mode, ctx.relu = ksize, residual_mode, relu
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, weight_orig, inv_sigma, y if relu else None)
+        if emit_split:
+            ctx.mark_non_differentiable(y_split)
+            return y, y_split
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, *_unused):
         x, weight_orig, inv_sigma, y = ctx.saved_tensors
         dy = dy.contiguous()
         if ctx.relu:
             dy = K.relu_bwd(y, dy)
         need_x, need_w, need_s, need_b, need_r = ctx.needs_input_grad[:5]
-        dx = dw = ds = db = dr = None
-        if need_x:
-            wpt = K.pack_conv_weight(weight_orig, inv_sigma, transpose=True)
-            dx = K.conv_fwd(dy, wpt, ctx.ksize)
-        if need_w or (need_s and inv_sigma is not None):
-            g = K.conv_wgrad(x, dy, ctx.ksize)
-            if inv_sigma is not None:
-                if need_s:
-                    ds = _dot(g, weight_orig).reshape(inv_sigma.shape)
-                if need_w:
-                    dw = g * inv_sigma
-            else:
-                dw = g
+        dx, dw, ds = _conv_backward(ctx.ksize, x, weight_orig, inv_sigma, dy, need_x, need_w, need_s)
+        db = dr = None
         if ctx.has_bias and need_b:
             db = K.bias_grad(dy)
         if ctx.has_res and need_r:
             dr = dy if ctx.residual_mode == 1 else K.upsample2_bwd(dy)
-        return dx, dw, ds, db, dr, None, None, None, None
+        return dx, dw, ds, db, dr, None, None, None, None, None, None
 
 
 def conv2d(x, weight_orig, inv_sigma=None, bias=None, residual=None, ksize=3, residual_mode=0, relu=False,
-           round_out=False):
+           round_out=False, x_split=None, emit_split=False):
     if residual is None:
         residual_mode = 0
-    return Conv2dFn.apply(x, weight_orig, inv_sigma, bias, residual, ksize, residual_mode, relu, round_out)
+    return Conv2dFn.apply(x, weight_orig, inv_sigma, bias, residual, ksize, residual_mode, relu, round_out, x_split,
+                          emit_split)
+
+
+class AdaINConvFn(torch.autograd.Function):
+    """One generator half-block as ONE autograd node, bf16x3 precision:
+        y = conv3x3( relu( instance_norm(x)*gamma + beta ) [nearest 2x] ; W/sigma ) (+ residual)
+    (generators/common/blocks.py:70-88 + AdaptiveNorm2d :18-26).  Kernels: in_stats -> adain_relu (writes the
+    (hi, lo) bf16 operand planes, plus a tf32 fp32 copy when a backward pass will need it for the weight gradient)
+    -> pack (hi, lo) -> tcgen05 bf16x3 implicit GEMM with the residual / skip-upsample epilogue.
+    Backward: TF32 data- and weight-gradient kernels, then the AdaIN backward kernels."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, weight_orig, inv_sigma, residual, eps, upsample2, residual_mode, emit_split):
+        mean, rstd = K.in_stats(x, eps)
+        need_bwd = any(ctx.needs_input_grad)      # False under torch.no_grad() (drive.py, EMA forward)
+        if need_bwd:
+            a_f32, a_split = K.adain_relu(x, mean, rstd, gamma, beta, upsample2=upsample2, round_tf32=True,
+                                          want_f32=True, want_split=True)
+        else:
+            a_f32, a_split = None, K.adain_relu(x, mean, rstd, gamma, beta, upsample2=upsample2, want_f32=False,
+                                                want_split=True)
+        wp = K.pack_conv_weight(weight_orig, inv_sigma, transpose=False, precision=K.BF16X3)
+        out = K.conv_fwd(a_split, wp, 3, residual=residual, residual_mode=residual_mode, emit_split=emit_split)
+        y, y_split = out if emit_split else (out, None)
+        ctx.upsample2, ctx.residual_mode = upsample2, residual_mode
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, mean, rstd, gamma, beta, weight_orig, inv_sigma, a_f32)
+        if emit_split:
+            ctx.mark_non_differentiable(y_split)
+            return y, y_split
+        return y
+
+    @staticmethod
+    def backward(ctx, dy, *_unused):
+        x, mean, rstd, gamma, beta, weight_orig, inv_sigma, a_f32 = ctx.saved_tensors
+        dy = dy.contiguous()
+        need_x, need_g, need_b, need_w, need_s, need_r = ctx.needs_input_grad[:6]
+        da, dw, ds = _conv_backward(3, a_f32, weight_orig, inv_sigma, dy, need_x or need_g or need_b, need_w, need_s)
+        dx = dgm = dbt = None
+        if da is not None:
+            dx, dgm, dbt = K.adain_relu_bwd(x, mean, rstd, gamma, beta, da, upsample2=ctx.upsample2)
+        dr = None
+        if ctx.has_res and need_r:
+            dr = dy if ctx.residual_mode == 1 else K.upsample2_bwd(dy)
+        return dx, dgm, dbt, dw, ds, dr, None, None, None, None
+
+
+def adain_conv(x, gamma, beta, weight_orig, inv_sigma, residual=None, residual_mode=0, eps=1e-4, upsample2=False,
+               emit_split=False):
+    if residual is None:
+        residual_mode = 0
+    return AdaINConvFn.apply(x, gamma, beta, weight_orig, inv_sigma, residual, eps, upsample2, residual_mode,
+                             emit_split)
 
 
 class AdaINReLUFn(torch.autograd.Function):
@@ -97,7 +169,6 @@ class GenTailFn(torch.autograd.Function):
     def forward(ctx, x, weight_orig, inv_sigma, bias):
         rgbs, segm, t = K.gen_tail_fwd(x, weight_orig, inv_sigma, bias)
         ctx.save_for_backward(x, weight_orig, inv_sigma, t)
-        ctx.mark_non_differentiable()
         return rgbs, segm
 
     @staticmethod
@@ -311,7 +382,6 @@ class VggPerceptualFn(torch.autograd.Function):
                 d = K.conv_fwd(d, packed["wpt"][idx], 3)
             else:
                 dx_img = K.conv3x3_c3_dgrad(d, packed["w0"], None, packed["pre_scale"])
-        ctx.saved_feats = None
         return dx_img, None, None, None
 
 

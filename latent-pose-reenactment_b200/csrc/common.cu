@@ -34,8 +34,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
-int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle_base32) {
+int encode_tmap(CUtensorMap* out, const void* base, TmapDtype dtype, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, bool swizzle_base32) {
     auto fn = get_encode_fn();
     if (!fn) return B200LP_ECUDA;
     cuuint64_t gdim[5];
@@ -48,7 +48,7 @@ int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t
         estr[i] = 1;
         if (i + 1 < rank) gstr[i] = strides_bytes[i];
     }
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+    CUresult r = fn(out, dtype == kTmapF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
                     gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     swizzle_base32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -36,8 +36,13 @@ void count_launch(int n = 1);
 // swizzle_base32 = false: CU_TENSOR_MAP_SWIZZLE_128B (16-byte chunks, K-major UMMA operands);
 // swizzle_base32 = true : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (32-byte chunks; the only layout the tensor core accepts
 //                         for MN-major 32-bit operands, UMMA layout type SWIZZLE_128B_BASE32B).
-int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle_base32 = false);
+enum TmapDtype { kTmapF32 = 0, kTmapBF16 = 1 };
+int encode_tmap(CUtensorMap* out, const void* base, TmapDtype dtype, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, bool swizzle_base32);
+inline int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, bool swizzle_base32 = false) {
+    return encode_tmap(out, base, kTmapF32, rank, dims, strides_bytes, box, swizzle_base32);
+}
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

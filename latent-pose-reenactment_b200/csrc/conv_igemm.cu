@@ -11,27 +11,37 @@
 //   Warp roles (192 threads):  warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
 //   (tcgen05.ld -> bias / residual / relu / tf32 rounding -> 128-byte vector stores, one pixel row per thread).
 //
+// Two operand precisions share the kernel (template parameter MODE):
+//   MODE 0  "tf32"  : fp32 tensors holding TF32-rounded values, one tcgen05.mma.kind::tf32 per K=8 step.
+//   MODE 1  "bf16x3": every operand is a (hi, lo) pair of bf16 tensors with hi + lo == the fp32 value to 2^-17;
+//                     three tcgen05.mma.kind::f16 per K=16 step (Ah*Bh + Ah*Bl + Al*Bh) accumulate in the same
+//                     fp32 TMEM tile.  1.5x the tensor time of MODE 0, ~45x smaller operand-rounding error: this is
+//                     what keeps the generator output within 1e-3 of the fp32 reference.
+//
 // Replaces torch's nn.Conv2d forward (and, with transposed packing, conv backward-data) at the call sites listed
 // in include/b200lp.h.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace b200lp {
 
 constexpr int kBlockM = 128;      // pixels per CTA tile
-constexpr int kBlockK = 32;       // tf32 elements per pipeline stage row (= 128 bytes = swizzle span)
-constexpr int kUmmaK = 8;         // K of one tcgen05.mma.kind::tf32
+constexpr int kRowBytes = 128;    // one smem row = 128 bytes = swizzle span = 32 tf32 or 64 bf16 channels
 constexpr int kConvThreads = 192;
 
 struct ConvParams {
     const float* bias;
     const float* residual;
     float* y;
+    __nv_bfloat16* y_split;   // optional extra output: (hi, lo) bf16 planes of y, lo plane at +split_stride elements
+    long long split_stride;
     int N, H, W, Cin, Cout;
     int ksize;
     int bw, bh, bn;        // patch shape: bw*bh*bn == 128
     int tiles_w, tiles_h;  // patches per image row / column
-    int cblks;             // Cin / 32
+    int cblks;             // channel blocks per tap: ceil(Cin / channels-per-row)
     int num_kb;            // taps * cblks
     int residual_mode;
     int relu;
@@ -39,21 +49,28 @@ struct ConvParams {
     uint32_t a_bytes;      // bytes one A box delivers (may be < 16 KB when bn > N)
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE>
 struct ConvCfg {
-    static constexpr int kABytes = kBlockM * kBlockK * 4;   // 16 KB
-    static constexpr int kBBytes = BLOCK_N * kBlockK * 4;
-    static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int kParts = MODE == 0 ? 1 : 2;               // operand planes (tf32: 1, bf16 hi/lo: 2)
+    static constexpr int kChanPerRow = MODE == 0 ? 32 : 64;        // channels in one 128-byte row
+    static constexpr int kABytes = kBlockM * kRowBytes;            // 16 KB per plane
+    static constexpr int kBBytes = BLOCK_N * kRowBytes;
+    static constexpr int kStageBytes = kParts * (kABytes + kBBytes);
+    static constexpr int kStages = MODE == 0 ? ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8))
+                                             : ((BLOCK_N == 128) ? 3 : (BLOCK_N == 64 ? 4 : 5));
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + alignment slack
     static constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
-template <int BLOCK_N>
+struct ConvMaps {
+    CUtensorMap a[2];   // activation planes (hi, lo)
+    CUtensorMap b[2];   // weight planes
+};
+
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const ConvParams p) {
-    using Cfg = ConvCfg<BLOCK_N>;
+conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
+    using Cfg = ConvCfg<BLOCK_N, MODE>;
     constexpr int kStages = Cfg::kStages;
 
     extern __shared__ uint8_t smem_raw[];
@@ -78,8 +95,11 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
+#pragma unroll
+        for (int q = 0; q < Cfg::kParts; ++q) {
+            tma_prefetch_desc(&tm.a[q]);
+            tma_prefetch_desc(&tm.b[q]);
+        }
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -107,31 +127,47 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 const int dy = tap / p.ksize - pad;
                 const int dx = tap % p.ksize - pad;
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
+                // stage layout: [A plane 0][A plane 1]...[B plane 0][B plane 1]..., every plane 1024-byte aligned
                 uint8_t* sa = smem_al + stage * Cfg::kStageBytes;
-                uint8_t* sb = sa + Cfg::kABytes;
-                mbar_expect_tx(&full_bar[stage], p.a_bytes + Cfg::kBBytes);
-                tma_load_4d(sa, &tmA, &full_bar[stage], cb * kBlockK, w0 + dx, h0 + dy, n0);
-                tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N);
+                uint8_t* sb = sa + Cfg::kParts * Cfg::kABytes;
+                mbar_expect_tx(&full_bar[stage], Cfg::kParts * (p.a_bytes + Cfg::kBBytes));
+                const int kcoord = tap * p.Cin + cb * Cfg::kChanPerRow;   // column of the packed [Cout][tap*Cin+ci] matrix
+#pragma unroll
+                for (int q = 0; q < Cfg::kParts; ++q) {
+                    tma_load_4d(sa + q * Cfg::kABytes, &tm.a[q], &full_bar[stage], cb * Cfg::kChanPerRow, w0 + dx,
+                                h0 + dy, n0);
+                    tma_load_2d(sb + q * Cfg::kBBytes, &tm.b[q], &full_bar[stage], kcoord, n_tile * BLOCK_N);
+                }
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(kBlockM, BLOCK_N, 0, 0);
+            constexpr uint32_t idesc = MODE == 0 ? make_idesc_tf32(kBlockM, BLOCK_N, 0, 0)
+                                                 : make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
-                const uint32_t b_addr = a_addr + Cfg::kABytes;
+                const uint32_t b_addr = a_addr + Cfg::kParts * Cfg::kABytes;
 #pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                    // K-major SWIZZLE_128B: 8-row groups are 1024 B apart (SBO); stepping K by 8 tf32 = +32 bytes
-                    const uint64_t da = make_smem_desc(a_addr + k * (kUmmaK * 4), 16, 1024, 2);
-                    const uint64_t db = make_smem_desc(b_addr + k * (kUmmaK * 4), 16, 1024, 2);
-                    umma_tf32_ss(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {
+                    // K-major SWIZZLE_128B: 8-row groups are 1024 B apart (SBO); one MMA consumes 32 bytes of K
+                    // (8 tf32 or 16 bf16), so stepping K = +32 bytes inside the 128-byte swizzle span
+                    const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024, 2);
+                    const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, 2);
+                    if (MODE == 0) {
+                        umma_tf32_ss(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    } else {
+                        const uint64_t da_lo = make_smem_desc(a_addr + Cfg::kABytes + k * 32, 16, 1024, 2);
+                        const uint64_t db_lo = make_smem_desc(b_addr + Cfg::kBBytes + k * 32, 16, 1024, 2);
+                        umma_f16_ss(tmem_base, da_lo, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);   // Al * Bh
+                        umma_f16_ss(tmem_base, da, db_lo, idesc, 1u);                            // Ah * Bl
+                        umma_f16_ss(tmem_base, da, db, idesc, 1u);                               // Ah * Bh
+                    }
                 }
                 umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -188,6 +224,21 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
                     }
                     *reinterpret_cast<float4*>(yrow + c0 + j) = o;
+                    if (p.y_split) {   // (hi, lo) bf16 planes of the same values, for a following bf16x3 conv
+                        __nv_bfloat16* sp = p.y_split + pix * p.Cout + n_tile * BLOCK_N + c0 + j;
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(o.x), h1 = __float2bfloat16_rn(o.y),
+                                            h2 = __float2bfloat16_rn(o.z), h3 = __float2bfloat16_rn(o.w);
+                        __nv_bfloat162 hi01 = __halves2bfloat162(h0, h1), hi23 = __halves2bfloat162(h2, h3);
+                        __nv_bfloat162 lo01 = __halves2bfloat162(__float2bfloat16_rn(o.x - __bfloat162float(h0)),
+                                                                 __float2bfloat16_rn(o.y - __bfloat162float(h1)));
+                        __nv_bfloat162 lo23 = __halves2bfloat162(__float2bfloat16_rn(o.z - __bfloat162float(h2)),
+                                                                 __float2bfloat16_rn(o.w - __bfloat162float(h3)));
+                        uint2 hv, lv;
+                        hv.x = *reinterpret_cast<uint32_t*>(&hi01); hv.y = *reinterpret_cast<uint32_t*>(&hi23);
+                        lv.x = *reinterpret_cast<uint32_t*>(&lo01); lv.y = *reinterpret_cast<uint32_t*>(&lo23);
+                        *reinterpret_cast<uint2*>(sp) = hv;
+                        *reinterpret_cast<uint2*>(sp + p.split_stride) = lv;
+                    }
                 }
             }
         }
@@ -201,18 +252,17 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
 }
 
-template <int BLOCK_N>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int m_tiles,
-                       cudaStream_t stream) {
-    using Cfg = ConvCfg<BLOCK_N>;
+template <int BLOCK_N, int MODE>
+static int launch_conv(const ConvMaps& tm, const ConvParams& p, int m_tiles, cudaStream_t stream) {
+    using Cfg = ConvCfg<BLOCK_N, MODE>;
     static bool attr_set = false;
     if (!attr_set) {
-        B200LP_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_tf32_kernel<BLOCK_N>,
+        B200LP_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, MODE>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
     dim3 grid(p.Cout / BLOCK_N, m_tiles, 1);
-    conv_igemm_tf32_kernel<BLOCK_N><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+    conv_igemm_kernel<BLOCK_N, MODE><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tm, p);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;
@@ -231,11 +281,20 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
                    "conv_fwd: H=%d W=%d must be powers of two >= 2, N=%d > 0", a->H, a->W, a->N);
     B200LP_REQUIRE(a->residual_mode >= 0 && a->residual_mode <= 2 && (a->residual_mode == 0 || a->residual),
                    "conv_fwd: bad residual mode %d", a->residual_mode);
+    B200LP_REQUIRE(a->precision == 0 || a->precision == 1, "conv_fwd: precision %d not in {0 tf32, 1 bf16x3}",
+                   a->precision);
+    const int mode = a->precision;
+    const int chan_per_row = mode == 0 ? 32 : 64;
+    const int elem_bytes = mode == 0 ? 4 : 2;
+    B200LP_REQUIRE(mode == 0 || a->Cin % 64 == 0 || a->Cin == 32,
+                   "conv_fwd: bf16x3 needs Cin %% 64 == 0 (or Cin == 32), got %d", a->Cin);
 
     ConvParams p;
     p.bias = a->bias;
     p.residual = a->residual_mode ? a->residual : nullptr;
     p.y = a->y;
+    p.y_split = static_cast<__nv_bfloat16*>(a->y_split);
+    p.split_stride = static_cast<long long>(a->N) * a->H * a->W * a->Cout;
     p.N = a->N; p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.Cout = a->Cout;
     p.ksize = a->ksize;
     p.bw = a->W < 16 ? a->W : 16;
@@ -243,54 +302,70 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
     p.bn = kBlockM / (p.bw * p.bh);
     p.tiles_w = a->W / p.bw;
     p.tiles_h = a->H / p.bh;
-    p.cblks = a->Cin / kBlockK;
+    p.cblks = (a->Cin + chan_per_row - 1) / chan_per_row;
     p.num_kb = a->ksize * a->ksize * p.cblks;
     p.residual_mode = a->residual_mode;
     p.relu = a->relu;
     p.round_out = a->round_tf32;
     const int bn_box = p.bn < a->N ? p.bn : a->N;
-    p.a_bytes = static_cast<uint32_t>(kBlockK * 4 * p.bw * p.bh * bn_box);
+    p.a_bytes = static_cast<uint32_t>(kRowBytes * p.bw * p.bh * bn_box);
     const int tiles_n = (a->N + p.bn - 1) / p.bn;
     const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
 
     int block_n = a->block_n;
     if (block_n == 0) {
-        if (a->Cout % 256 == 0 && static_cast<long>(m_tiles) * (a->Cout / 256) >= 148) block_n = 256;
+        if (mode == 0 && a->Cout % 256 == 0 && static_cast<long>(m_tiles) * (a->Cout / 256) >= 148) block_n = 256;
         else if (a->Cout % 128 == 0) block_n = 128;
         else if (a->Cout % 64 == 0) block_n = 64;
         else block_n = 32;
     }
-    B200LP_REQUIRE((block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256) && a->Cout % block_n == 0,
-                   "conv_fwd: block_n=%d incompatible with Cout=%d", block_n, a->Cout);
+    B200LP_REQUIRE((block_n == 32 || block_n == 64 || block_n == 128 || (block_n == 256 && mode == 0)) &&
+                       a->Cout % block_n == 0,
+                   "conv_fwd: block_n=%d incompatible with Cout=%d (precision %d)", block_n, a->Cout, mode);
 
-    CUtensorMap tmA, tmB;
-    {
-        const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
-        const uint64_t strides[3] = {(uint64_t)a->Cin * 4, (uint64_t)a->W * a->Cin * 4,
-                                     (uint64_t)a->H * a->W * a->Cin * 4};
-        const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)bn_box};
-        int r = encode_tmap_f32(&tmA, a->x, 4, dims, strides, box);
-        if (r) return r;
+    ConvMaps tm;
+    const uint64_t ktot = (uint64_t)a->ksize * a->ksize * a->Cin;
+    const int parts = mode == 0 ? 1 : 2;
+    for (int q = 0; q < parts; ++q) {
+        {
+            const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
+            const uint64_t strides[3] = {(uint64_t)a->Cin * elem_bytes, (uint64_t)a->W * a->Cin * elem_bytes,
+                                         (uint64_t)a->H * a->W * a->Cin * elem_bytes};
+            const uint32_t box[4] = {(uint32_t)chan_per_row, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)bn_box};
+            const char* base = static_cast<const char*>(a->x) +
+                               (size_t)q * a->N * a->H * a->W * a->Cin * elem_bytes;   // lo plane follows hi plane
+            int r = encode_tmap(&tm.a[q], base, mode == 0 ? kTmapF32 : kTmapBF16, 4, dims, strides, box, false);
+            if (r) return r;
+        }
+        {
+            const uint64_t dims[2] = {ktot, (uint64_t)a->Cout};
+            const uint64_t strides[1] = {ktot * elem_bytes};
+            const uint32_t box[2] = {(uint32_t)chan_per_row, (uint32_t)block_n};
+            const char* base = static_cast<const char*>(a->wp) + (size_t)q * ktot * a->Cout * elem_bytes;
+            int r = encode_tmap(&tm.b[q], base, mode == 0 ? kTmapF32 : kTmapBF16, 2, dims, strides, box, false);
+            if (r) return r;
+        }
     }
-    {
-        const uint64_t ktot = (uint64_t)a->ksize * a->ksize * a->Cin;
-        const uint64_t dims[2] = {ktot, (uint64_t)a->Cout};
-        const uint64_t strides[1] = {ktot * 4};
-        const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)block_n};
-        int r = encode_tmap_f32(&tmB, a->wp, 2, dims, strides, box);
-        if (r) return r;
-    }
+    if (mode == 0) { tm.a[1] = tm.a[0]; tm.b[1] = tm.b[0]; }
     cudaStream_t s = as_stream(stream);
+    if (mode == 0) {
+        switch (block_n) {
+            case 256: return launch_conv<256, 0>(tm, p, m_tiles, s);
+            case 128: return launch_conv<128, 0>(tm, p, m_tiles, s);
+            case 64: return launch_conv<64, 0>(tm, p, m_tiles, s);
+            default: return launch_conv<32, 0>(tm, p, m_tiles, s);
+        }
+    }
     switch (block_n) {
-        case 256: return launch_conv<256>(tmA, tmB, p, m_tiles, s);
-        case 128: return launch_conv<128>(tmA, tmB, p, m_tiles, s);
-        case 64: return launch_conv<64>(tmA, tmB, p, m_tiles, s);
-        default: return launch_conv<32>(tmA, tmB, p, m_tiles, s);
+        case 128: return launch_conv<128, 1>(tm, p, m_tiles, s);
+        case 64: return launch_conv<64, 1>(tm, p, m_tiles, s);
+        default: return launch_conv<32, 1>(tm, p, m_tiles, s);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
 namespace b200lp {
+template <bool SPLIT>
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                         float* __restrict__ wp, int Cout, int Cin, int taps, int transpose) {
     const float s = scale ? __ldg(scale) : 1.0f;
@@ -310,20 +385,34 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, const float
             const int ci = i / (static_cast<long>(Cout) * taps);
             v = w[(static_cast<long>(co) * Cin + ci) * taps + (taps - 1 - tapf)];
         }
-        wp[i] = round_tf32(v * s);
+        if (!SPLIT) {
+            wp[i] = round_tf32(v * s);
+        } else {   // (hi, lo) bf16 planes: hi + lo == v*s to 2^-17
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(wp);
+            const float f = v * s;
+            const __nv_bfloat16 h = __float2bfloat16_rn(f);
+            out[i] = h;
+            out[total + i] = __float2bfloat16_rn(f - __bfloat162float(h));
+        }
     }
 }
 }  // namespace b200lp
 
-extern "C" int32_t b200lp_pack_conv_weight(const float* w_oihw, const float* scale, float* wp, int32_t Cout,
-                                           int32_t Cin, int32_t ksize, int32_t transpose, void* stream) {
+extern "C" int32_t b200lp_pack_conv_weight(const float* w_oihw, const float* scale, void* wp_out, int32_t Cout,
+                                           int32_t Cin, int32_t ksize, int32_t transpose, int32_t precision,
+                                           void* stream) {
+    float* wp = static_cast<float*>(wp_out);
     B200LP_REQUIRE(w_oihw && wp && Cout > 0 && Cin > 0 && (ksize == 1 || ksize == 3), "pack_conv_weight: bad args");
     const long total = static_cast<long>(Cout) * Cin * ksize * ksize;
     const int threads = 256;
     long blocks = (total + threads - 1) / threads;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    pack_conv_weight_kernel<<<(int)blocks, threads, 0, as_stream(stream)>>>(w_oihw, scale, wp, Cout, Cin,
-                                                                            ksize * ksize, transpose);
+    if (precision == 0)
+        pack_conv_weight_kernel<false><<<(int)blocks, threads, 0, as_stream(stream)>>>(w_oihw, scale, wp, Cout, Cin,
+                                                                                     ksize * ksize, transpose);
+    else
+        pack_conv_weight_kernel<true><<<(int)blocks, threads, 0, as_stream(stream)>>>(w_oihw, scale, wp, Cout, Cin,
+                                                                                    ksize * ksize, transpose);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

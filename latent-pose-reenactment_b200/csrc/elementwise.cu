@@ -2,6 +2,8 @@
 // ReLU / pooling / upsample-backward, L1 feature-loss reductions, layout conversion, bias gradients.
 // All activations are NHWC fp32; every kernel streams 16-byte vectors along the channel axis (coalesced),
 // keeps per-(n,c) scalars in registers, and sizes its grid as a multiple of the 148 SMs.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -127,11 +129,32 @@ static void stats_plan(int N, int HW, int C, int* chunks, int* pix_per_chunk) {
 // Replaces blocks.py:18-26 (AdaptiveNorm2d.forward), :73 (ReLU) and :75 (Upsample).
 // grid (chunks, N), block = (C/4 lanes) x rows
 // ---------------------------------------------------------------------------------------------------------------
+// write one float4 as fp32 (optional) and/or as (hi, lo) bf16 planes (optional; lo plane at +split_stride elements)
+__device__ __forceinline__ void store_f32_and_split(float* y, __nv_bfloat16* ys, long long split_stride, size_t off,
+                                                    float4 o) {
+    if (y) st4(y + off, o);
+    if (ys) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(o.x), h1 = __float2bfloat16_rn(o.y),
+                            h2 = __float2bfloat16_rn(o.z), h3 = __float2bfloat16_rn(o.w);
+        __nv_bfloat162 hi01 = __halves2bfloat162(h0, h1), hi23 = __halves2bfloat162(h2, h3);
+        __nv_bfloat162 lo01 = __halves2bfloat162(__float2bfloat16_rn(o.x - __bfloat162float(h0)),
+                                                 __float2bfloat16_rn(o.y - __bfloat162float(h1)));
+        __nv_bfloat162 lo23 = __halves2bfloat162(__float2bfloat16_rn(o.z - __bfloat162float(h2)),
+                                                 __float2bfloat16_rn(o.w - __bfloat162float(h3)));
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<uint32_t*>(&hi01); hv.y = *reinterpret_cast<uint32_t*>(&hi23);
+        lv.x = *reinterpret_cast<uint32_t*>(&lo01); lv.y = *reinterpret_cast<uint32_t*>(&lo23);
+        *reinterpret_cast<uint2*>(ys + off) = hv;
+        *reinterpret_cast<uint2*>(ys + split_stride + off) = lv;
+    }
+}
+
 template <bool UP, bool ROUND>
 __global__ void adain_relu_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                                   const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                  const float* __restrict__ beta, long affine_stride, float* __restrict__ y, int H,
-                                  int W, int C, int pix_per_chunk) {
+                                  const float* __restrict__ beta, long affine_stride, float* __restrict__ y,
+                                  __nv_bfloat16* __restrict__ ys, long long split_stride, int H, int W, int C,
+                                  int pix_per_chunk) {
     const int cq = C >> 2;
     const int lane_c = threadIdx.x % cq;
     const int row = threadIdx.x / cq;
@@ -161,16 +184,23 @@ __global__ void adain_relu_kernel(const float* __restrict__ x, const float* __re
         o.y = fmaxf(((v.y - mu.y) * rs.y) * g.y + b.y, 0.f);
         o.z = fmaxf(((v.z - mu.z) * rs.z) * g.z + b.z, 0.f);
         o.w = fmaxf(((v.w - mu.w) * rs.w) * g.w + b.w, 0.f);
-        if (ROUND) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        float4 of = o;   // fp32 copy: tf32-rounded when it feeds a TF32 MMA (weight gradient); split planes keep full o
+        if (ROUND) { of.x = round_tf32(o.x); of.y = round_tf32(o.y); of.z = round_tf32(o.z); of.w = round_tf32(o.w); }
         if (!UP) {
-            st4(y + (static_cast<size_t>(n) * HW + p) * C + c, o);
+            const size_t off = (static_cast<size_t>(n) * HW + p) * C + c;
+            if (y) st4(y + off, of);
+            if (ys) store_f32_and_split(nullptr, ys, split_stride, off, o);
         } else {
             const int h = p / W, w = p - h * W;
-            float* yb = y + ((static_cast<size_t>(n) * (2 * H) + 2 * h) * (2 * W) + 2 * w) * C + c;
-            st4(yb, o);
-            st4(yb + C, o);
-            st4(yb + static_cast<size_t>(2 * W) * C, o);
-            st4(yb + static_cast<size_t>(2 * W) * C + C, o);
+            const size_t off = ((static_cast<size_t>(n) * (2 * H) + 2 * h) * (2 * W) + 2 * w) * C + c;
+            const size_t row2 = static_cast<size_t>(2 * W) * C;
+            if (y) { st4(y + off, of); st4(y + off + C, of); st4(y + off + row2, of); st4(y + off + row2 + C, of); }
+            if (ys) {
+                store_f32_and_split(nullptr, ys, split_stride, off, o);
+                store_f32_and_split(nullptr, ys, split_stride, off + C, o);
+                store_f32_and_split(nullptr, ys, split_stride, off + row2, o);
+                store_f32_and_split(nullptr, ys, split_stride, off + row2 + C, o);
+            }
         }
     }
 }
@@ -532,16 +562,20 @@ extern "C" int32_t b200lp_in_stats(const float* x, float* mean, float* rstd, flo
 }
 
 extern "C" int32_t b200lp_adain_relu(const float* x, const float* mean, const float* rstd, const float* gamma,
-                                     const float* beta, int64_t affine_stride, float* y, int32_t N, int32_t H,
-                                     int32_t W, int32_t C, int32_t upsample2, int32_t round_tf32, void* stream) {
-    B200LP_REQUIRE(x && mean && rstd && gamma && beta && y, "adain_relu: null pointer");
+                                     const float* beta, int64_t affine_stride, float* y, void* y_split, int32_t N,
+                                     int32_t H, int32_t W, int32_t C, int32_t upsample2, int32_t round_tf32,
+                                     void* stream) {
+    B200LP_REQUIRE(x && mean && rstd && gamma && beta && (y || y_split), "adain_relu: null pointer");
     B200LP_REQUIRE(N > 0 && H > 0 && W > 0 && C % 4 == 0 && C / 4 <= kEwThreads, "adain_relu: bad shape");
     int chunks, ppc;
     stats_plan(N, H * W, C, &chunks, &ppc);
     dim3 grid(chunks, N);
     cudaStream_t s = as_stream(stream);
-#define LAUNCH(UP, RD)                                                                                              \
-    adain_relu_kernel<UP, RD><<<grid, kEwThreads, 0, s>>>(x, mean, rstd, gamma, beta, affine_stride, y, H, W, C, ppc)
+    __nv_bfloat16* ys = static_cast<__nv_bfloat16*>(y_split);
+    const long long split_stride = static_cast<long long>(N) * H * W * C * (upsample2 ? 4 : 1);
+#define LAUNCH(UP, RD)                                                                                             \
+    adain_relu_kernel<UP, RD><<<grid, kEwThreads, 0, s>>>(x, mean, rstd, gamma, beta, affine_stride, y, ys,        \
+                                                          split_stride, H, W, C, ppc)
     if (upsample2) { if (round_tf32) LAUNCH(true, true); else LAUNCH(true, false); }
     else { if (round_tf32) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH

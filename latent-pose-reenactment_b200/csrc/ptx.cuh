@@ -109,6 +109,16 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, u
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same for 16-bit operands (kind::f16; the instruction descriptor selects bf16), K = 16 per instruction.
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrive on an mbarrier once every MMA previously issued by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -153,6 +163,13 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N, u
            | (b_mn_major << 16)      // B major
            | ((N >> 3) << 17)        // N / 8
            | ((M >> 4) << 24);       // M / 16
+}
+
+// Instruction descriptor for kind::f16 with BF16 operands, fp32 accumulate.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major,
+                                                       uint32_t b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
+           ((M >> 4) << 24);
 }
 
 // round-to-nearest-even-away fp32 -> tf32 (10-bit mantissa), returned as an fp32 bit pattern

@@ -119,19 +119,37 @@ class AdaResBlock(nn.Module):
         if in_channels != out_channels or upsample:
             self.skip = Slots(**{"1": SNConv(in_channels, out_channels, 1, bias=True)})
 
-    def forward(self, x, gamma0, beta0, gamma1, beta1, round_out):
+    def forward(self, x, gamma0, beta0, gamma1, beta1, feeds_skip_conv, x_split=None, precision='bf16x3'):
+        """x: block input (NHWC fp32).  `feeds_skip_conv`: the NEXT block applies a 1x1 conv to this block's output,
+        i.e. the output is itself a tensor-core operand.  Returns (out, out_split) — out_split (bf16 hi/lo planes of
+        `out`) only in bf16x3 precision when feeds_skip_conv, else None.
+
+        precision 'tf32'  : adain_relu(tf32) -> conv -> adain_relu(tf32) -> conv(+skip), one TF32 MMA per K step;
+        precision 'bf16x3': the same schedule with (hi, lo) bf16 operand planes and three MMAs per K step — generator
+                            output within 1e-3 of the fp32 reference for O(1) AdaIN gains."""
         w0, s0, _ = self.block.slot(self.i0).operands()
+        w1, s1, _ = self.block.slot(self.i1).operands()
+        if precision == 'bf16x3':
+            y1 = ops.adain_conv(x, gamma0, beta0, w0, s0, upsample2=self.upsample)
+            if self.skip is not None:
+                ws, ss, bs = self.skip.slot(1).operands()
+                s = ops.conv2d(x, ws, ss, bias=bs, ksize=1, x_split=x_split)
+                mode = 2 if self.upsample else 1
+            else:
+                s, mode = x, 1
+            out = ops.adain_conv(y1, gamma1, beta1, w1, s1, residual=s, residual_mode=mode,
+                                 emit_split=feeds_skip_conv)
+            return out if feeds_skip_conv else (out, None)
         a0 = ops.adain_relu(x, gamma0, beta0, upsample2=self.upsample)
         y1 = ops.conv2d(a0, w0, s0, ksize=3)
         a1 = ops.adain_relu(y1, gamma1, beta1)
-        w1, s1, _ = self.block.slot(self.i1).operands()
         if self.skip is not None:
             ws, ss, bs = self.skip.slot(1).operands()
             s = ops.conv2d(x, ws, ss, bias=bs, ksize=1)
             mode = 2 if self.upsample else 1
         else:
             s, mode = x, 1
-        return ops.conv2d(a1, w1, s1, residual=s, residual_mode=mode, ksize=3, round_out=round_out)
+        return ops.conv2d(a1, w1, s1, residual=s, residual_mode=mode, ksize=3, round_out=feeds_skip_conv), None
 
 
 class PlainResBlock(nn.Module):

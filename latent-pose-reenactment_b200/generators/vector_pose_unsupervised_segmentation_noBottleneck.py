@@ -93,6 +93,10 @@ class Generator(nn.Module):
             "0": blocks.SNLinear(joint, hidden),
             "2": blocks.SNLinear(hidden, self.get_num_affine_params())})
         self.finetuning = False
+        # tensor-core operand precision of the decoder convolutions: 'bf16x3' (default; three bf16 MMAs per K step on
+        # (hi, lo) operand planes, ~fp32 accuracy, generator RGB within 1e-3 of the fp32 reference) or 'tf32' (one MMA
+        # per K step, 1.5x less tensor time, ~3e-3 max-abs on nets with O(1) AdaIN gains).  Not part of the state_dict.
+        self.precision = 'bf16x3'
 
     def get_num_affine_params(self):
         return sum(2 * c for c in self.adain_sizes)
@@ -136,14 +140,15 @@ class Generator(nn.Module):
 
         # constant (1,C,s,s) NCHW parameter -> (B,s,s,C) NHWC
         x = self.constant.constant.permute(0, 2, 3, 1).expand(batch, -1, -1, -1).contiguous()
+        x_split = None
         for i in range(self.num_blocks):
             blk = self.decoder_blocks.slot(i)
             g0, b0 = take(blk.in_channels)
             g1, b1 = take(blk.out_channels)
-            # the next block's 1x1 skip conv reads this output as a tensor-core operand: round it once here
+            # the next block's 1x1 skip conv reads this output as a tensor-core operand: produce it in operand form here
             nxt = self.decoder_blocks.slot(i + 1) if i + 1 < self.num_blocks else None
-            round_out = nxt is not None and nxt.skip is not None
-            x = blk(x, g0, b0, g1, b1, round_out)
+            feeds_skip_conv = nxt is not None and nxt.skip is not None
+            x, x_split = blk(x, g0, b0, g1, b1, feeds_skip_conv, x_split=x_split, precision=self.precision)
         g, bt = take(self.adain_sizes[-1])
         a = ops.adain_relu(x, g, bt, round_out=False)
         tail = self.decoder_blocks.slot(self.num_blocks + 2)

@@ -76,6 +76,18 @@ def test_generator_forward_eval_train(small, golden_small):
         assert rel_err(sd["affine_params_projector.2.weight_v"], golden_small["g_train.v_after.affine_params_projector.2"]) < 1e-5
 
 
+def test_generator_tf32_mode_is_close_but_not_within_1e3(small, golden_small):
+    """The single-pass TF32 mode (G.precision = 'tf32') is the fast path; its operand rounding (2^-11) costs ~3e-3
+    max-abs on this O(1)-gain net, which is why bf16x3 is the default.  Loose bound: catches real bugs only."""
+    cfg, emb = small["cfg"], to_dev(small["emb"], DEV)
+    G = _G(cfg, small["g_sd"]).eval()
+    G.precision = 'tf32'
+    with torch.no_grad():
+        dd = dict(embeds=emb["embeds"], pose_embedding=emb["pose_embedding"])
+        G(dd)
+    assert max_abs(dd["fake_rgbs"], golden_small["g_eval.fake_rgbs"]) < 1e-2
+
+
 def test_generator_finetune_mode(small, golden_small):
     cfg, emb = small["cfg"], to_dev(small["emb"], DEV)
     G = _G(cfg, small["g_sd"], finetune_embeds=small["emb"]["embeds"][:1].clone())
@@ -180,17 +192,21 @@ def test_training_step_losses_and_gradients(small, golden_small, skip_discarded)
         ref = float(golden_small["step.loss." + k])
         assert abs(float(v) - ref) <= 3e-3 * abs(ref) + 1e-6, (k, float(v), ref)
     # gradients: TF32 forward + TF32 backward chains; compare norms (all parameters) and full tensors (a selection)
+    # (some gradients are analytically ~0 — e.g. a skip-conv bias that the next InstanceNorm removes — so the absolute
+    #  floor is tied to the largest gradient norm of the network, not to the parameter's own norm)
+    g_floor = 1e-4 * max(golden_small["step.gradG.norms"].values())
+    d_floor = 1e-4 * max(golden_small["step.gradD.norms"].values())
     for k, ref_norm in golden_small["step.gradG.norms"].items():
-        assert abs(float(r["gradG"][k].norm()) - ref_norm) <= 2e-2 * ref_norm + 1e-7, (k, float(r["gradG"][k].norm()), ref_norm)
+        assert abs(float(r["gradG"][k].norm()) - ref_norm) <= 2e-2 * ref_norm + g_floor, (k, float(r["gradG"][k].norm()), ref_norm)
     for k, ref_norm in golden_small["step.gradD.norms"].items():
-        assert abs(float(r["gradD"][k].norm()) - ref_norm) <= 2e-2 * ref_norm + 1e-7, (k, float(r["gradD"][k].norm()), ref_norm)
+        assert abs(float(r["gradD"][k].norm()) - ref_norm) <= 2e-2 * ref_norm + d_floor, (k, float(r["gradD"][k].norm()), ref_norm)
     for k, v in golden_small.items():
         if k.startswith("step.gradG.") and k != "step.gradG.norms":
             name = k[len("step.gradG."):]
-            assert rel_err(r["gradG"][name], v) < 2e-2, name
+            assert max_abs(r["gradG"][name], v) <= 2e-2 * float(v.abs().max()) + g_floor, name
         if k.startswith("step.gradD.") and k != "step.gradD.norms":
             name = k[len("step.gradD."):]
-            assert rel_err(r["gradD"][name], v) < 2e-2, name
+            assert max_abs(r["gradD"][name], v) <= 2e-2 * float(v.abs().max()) + d_floor, name
     ref = float(golden_small["step.gradE.scale"])
     assert abs(float(r["gradE"]) - ref) <= 2e-2 * abs(ref) + 1e-7
     # parameters after Adam + EMA

@@ -98,6 +98,83 @@ def conv_big():
             _conv_case(8, 32, 32, 512, 512, 3), _conv_case(8, 64, 64, 512, 256, 3)]
 
 
+def split_bf16(t):
+    """(2, ...) bfloat16 (hi, lo) planes with hi + lo == t to ~2^-17 (the bf16x3 operand format)."""
+    import torch
+    hi = t.bfloat16()
+    lo = (t - hi.float()).bfloat16()
+    return torch.stack((hi, lo)).contiguous()
+
+
+def _conv_bf16x3_case(N, H, W, Cin, Cout, k, emit_split=False, residual_mode=0):
+    import torch
+    import torch.nn.functional as F
+    from b200lp import kernels as K
+    torch.manual_seed(7)
+    x = torch.randn(N, Cin, H, W, device="cuda") * 2 + 0.5          # NOT pre-rounded: full fp32 mantissas
+    w = torch.randn(Cout, Cin, k, k, device="cuda") * 0.05
+    sc = torch.tensor([0.37], device="cuda")
+    wp = K.pack_conv_weight(w, sc, precision=K.BF16X3)
+    ref = F.conv2d(x.double(), (w * sc).double(), padding=k // 2)
+    res = None
+    if residual_mode == 2:
+        res = torch.randn(N, H // 2, W // 2, Cout, device="cuda")
+        ref = ref + F.interpolate(res.permute(0, 3, 1, 2).double(), scale_factor=2, mode="nearest")
+    xs = split_bf16(x.permute(0, 2, 3, 1).contiguous())
+    out = K.conv_fwd(xs, wp, k, residual=res, residual_mode=residual_mode, emit_split=emit_split)
+    torch.cuda.synchronize()
+    y, ysp = out if emit_split else (out, None)
+    e = _err(y.permute(0, 3, 1, 2), ref)
+    e["case"] = f"bf16x3 N{N} H{H} Cin{Cin} Cout{Cout} k{k} res{residual_mode}"
+    e["ok"] = (not e["nan"]) and e["rel"] < 5e-5
+    outs = [e]
+    if emit_split:
+        rec = (ysp[0].float() + ysp[1].float())
+        e2 = _err(rec, y)
+        e2["case"] = e["case"] + " emitted (hi,lo) planes reconstruct y"
+        e2["ok"] = (not e2["nan"]) and e2["rel"] < 2e-5
+        outs.append(e2)
+    return outs
+
+
+@check
+def conv_bf16x3():
+    out = []
+    for args in [(1, 16, 16, 64, 64, 1), (2, 16, 16, 64, 128, 3), (2, 32, 32, 128, 64, 3), (8, 4, 4, 512, 512, 3),
+                 (2, 8, 8, 32, 32, 3), (2, 16, 16, 32, 64, 1)]:
+        out += _conv_bf16x3_case(*args)
+    out += _conv_bf16x3_case(2, 16, 16, 64, 64, 3, emit_split=True, residual_mode=2)
+    out += _conv_bf16x3_case(4, 64, 64, 256, 128, 3)
+    return out
+
+
+@check
+def adain_split():
+    import torch
+    import torch.nn.functional as F
+    from b200lp import kernels as K
+    torch.manual_seed(8)
+    out = []
+    for (N, H, W, C, up) in [(2, 16, 16, 64, False), (2, 8, 8, 128, True)]:
+        x = torch.randn(N, C, H, W, device="cuda") * 3 + 1
+        aff = torch.randn(N, 2 * C, device="cuda")
+        beta, gamma = aff[:, :C], aff[:, C:]
+        o = (F.instance_norm(x.double(), eps=1e-4) * gamma.double()[:, :, None, None] + beta.double()[:, :, None, None]).relu()
+        if up:
+            o = F.interpolate(o, scale_factor=2, mode="nearest")
+        xh = x.permute(0, 2, 3, 1).contiguous()
+        mean, rstd = K.in_stats(xh, 1e-4)
+        y, ys = K.adain_relu(xh, mean, rstd, gamma, beta, upsample2=up, round_tf32=True, want_f32=True, want_split=True)
+        ys_only = K.adain_relu(xh, mean, rstd, gamma, beta, upsample2=up, want_f32=False, want_split=True)
+        torch.cuda.synchronize()
+        e = _err((ys[0].float() + ys[1].float()).permute(0, 3, 1, 2), o); e["case"] = f"adain split N{N} C{C} up{int(up)}"
+        e["ok"] = (not e["nan"]) and e["rel"] < 2e-5; out.append(e)
+        e = _err(y.permute(0, 3, 1, 2), o); e["case"] = f"adain f32(tf32) copy N{N} C{C} up{int(up)}"
+        e["ok"] = (not e["nan"]) and e["rel"] < 6e-4; out.append(e)
+        e = _err(ys_only.float(), ys.float()); e["case"] = "split-only == split"; e["ok"] = e["max_abs"] == 0.0; out.append(e)
+    return out
+
+
 @check
 def conv_dgrad_pack():
     # data gradient through the same kernel with transposed packing, against autograd
@@ -299,7 +376,11 @@ def conv_timing():
         y = torch.empty(N, H, W, Cout, device="cuda")
         flops = 2.0 * N * H * W * Cin * Cout * k * k
         rec = {"case": f"N{N} H{H} Cin{Cin} Cout{Cout} k{k}", "ok": True}
-        for name, fn in [("fwd", lambda: K.conv_fwd(x, wp, k, out=y)), ("wgrad", lambda: K.conv_wgrad(x, dy, k))]:
+        fns = [("fwd", lambda: K.conv_fwd(x, wp, k, out=y)), ("wgrad", lambda: K.conv_wgrad(x, dy, k))]
+        if Cin % 64 == 0 and k == 3:
+            xs = split_bf16(x); wps = K.pack_conv_weight(w, precision=K.BF16X3)
+            fns.append(("fwd_bf16x3", lambda: K.conv_fwd(xs, wps, k, out=y)))
+        for name, fn in fns:
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
