@@ -64,7 +64,7 @@ typedef struct {
     int32_t round_tf32;     /* 1: round y to tf32 (y only feeds further tf32 MMAs)     */
     int32_t block_n;        /* 0 = auto; else 32 / 64 / 128 / 256 (256: tf32 only)     */
     int32_t precision;      /* 0 = tf32 (1 MMA / K-step), 1 = bf16x3 (3 MMAs: Ah*Bh + Ah*Bl + Al*Bh, ~fp32 accuracy) */
-    int32_t reserved;
+    int32_t stages;         /* 0 = auto; else depth of the shared-memory operand ring (tuning knob)                 */
 } b200lp_conv_args;
 
 int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream);

@@ -57,7 +57,7 @@ def pack_conv_weight(w_oihw, scale=None, transpose=False, precision=TF32):
 
 
 def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False, round_tf32=False, block_n=0,
-             out=None, emit_split=False):
+             out=None, emit_split=False, stages=0):
     """x NHWC (N,H,W,Cin) float32 [TF32] or (2,N,H,W,Cin) bfloat16 (hi, lo) [BF16X3]; wp packed to match.
     Returns y (N,H,W,Cout) float32, or (y, y_split) with y_split (2,N,H,W,Cout) bfloat16 when emit_split."""
     lib = L.load()
@@ -82,6 +82,7 @@ def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False
     a.relu = int(relu)
     a.round_tf32 = int(round_tf32)
     a.block_n = block_n
+    a.stages = stages
     a.precision = BF16X3 if split_in else TF32
     with _timed("conv_igemm_bf16x3" if split_in else "conv_igemm_tf32",
                 flops=2.0 * n * h * w * cin * cout * ksize * ksize):

@@ -26,7 +26,7 @@ class ConvArgs(Structure):
         ("y_split", c_void_p),
         ("N", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("Cout", c_int32),
         ("ksize", c_int32), ("residual_mode", c_int32), ("relu", c_int32), ("round_tf32", c_int32),
-        ("block_n", c_int32), ("precision", c_int32), ("reserved", c_int32),
+        ("block_n", c_int32), ("precision", c_int32), ("stages", c_int32),
     ]
 
 

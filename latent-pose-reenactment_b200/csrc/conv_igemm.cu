@@ -47,6 +47,7 @@ struct ConvParams {
     int relu;
     int round_out;
     uint32_t a_bytes;      // bytes one A box delivers (may be < 16 KB when bn > N)
+    int stages;            // depth of the smem ring (<= ConvCfg::kMaxStages)
 };
 
 template <int BLOCK_N, int MODE>
@@ -56,9 +57,12 @@ struct ConvCfg {
     static constexpr int kABytes = kBlockM * kRowBytes;            // 16 KB per plane
     static constexpr int kBBytes = BLOCK_N * kRowBytes;
     static constexpr int kStageBytes = kParts * (kABytes + kBBytes);
-    static constexpr int kStages = MODE == 0 ? ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8))
-                                             : ((BLOCK_N == 128) ? 3 : (BLOCK_N == 64 ? 4 : 5));
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + alignment slack
+    static constexpr int kMaxStages = 8;
+    // default ring depth.  Shallow rings for BLOCK_N <= 128 keep a CTA under ~100 KB so that TWO CTAs share an SM:
+    // one CTA's epilogue (TMEM -> registers -> HBM) then overlaps the other CTA's main loop.
+    static constexpr int kDefaultStages = MODE == 0 ? ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 3 : 4))
+                                                    : ((BLOCK_N == 128) ? 3 : (BLOCK_N == 64 ? 4 : 5));
+    static constexpr int kMaxSmemBytes = 227 * 1024;
     static constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
@@ -68,14 +72,14 @@ struct ConvMaps {
 };
 
 template <int BLOCK_N, int MODE>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 2)
 conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
     using Cfg = ConvCfg<BLOCK_N, MODE>;
-    constexpr int kStages = Cfg::kStages;
+    const int kStages = p.stages;
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kStages];
-    __shared__ __align__(8) uint64_t empty_bar[kStages];
+    __shared__ __align__(8) uint64_t full_bar[Cfg::kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[Cfg::kMaxStages];
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_slot;
 
@@ -253,16 +257,24 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
 }
 
 template <int BLOCK_N, int MODE>
-static int launch_conv(const ConvMaps& tm, const ConvParams& p, int m_tiles, cudaStream_t stream) {
+static int launch_conv(const ConvMaps& tm, ConvParams p, int m_tiles, int stages, cudaStream_t stream) {
     using Cfg = ConvCfg<BLOCK_N, MODE>;
     static bool attr_set = false;
     if (!attr_set) {
         B200LP_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, MODE>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmemBytes));
+        B200LP_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, MODE>,
+                                               cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
+    if (stages <= 0) stages = Cfg::kDefaultStages;
+    if (stages > Cfg::kMaxStages) stages = Cfg::kMaxStages;
+    while (stages > 1 && stages * Cfg::kStageBytes + 1024 > Cfg::kMaxSmemBytes) --stages;
+    if (stages > p.num_kb) stages = p.num_kb;
+    p.stages = stages;
+    const int smem_bytes = stages * Cfg::kStageBytes + 1024;   // + alignment slack
     dim3 grid(p.Cout / BLOCK_N, m_tiles, 1);
-    conv_igemm_kernel<BLOCK_N, MODE><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tm, p);
+    conv_igemm_kernel<BLOCK_N, MODE><<<grid, kConvThreads, smem_bytes, stream>>>(tm, p);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;
@@ -348,18 +360,19 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
     }
     if (mode == 0) { tm.a[1] = tm.a[0]; tm.b[1] = tm.b[0]; }
     cudaStream_t s = as_stream(stream);
+    const int st = a->stages;
     if (mode == 0) {
         switch (block_n) {
-            case 256: return launch_conv<256, 0>(tm, p, m_tiles, s);
-            case 128: return launch_conv<128, 0>(tm, p, m_tiles, s);
-            case 64: return launch_conv<64, 0>(tm, p, m_tiles, s);
-            default: return launch_conv<32, 0>(tm, p, m_tiles, s);
+            case 256: return launch_conv<256, 0>(tm, p, m_tiles, st, s);
+            case 128: return launch_conv<128, 0>(tm, p, m_tiles, st, s);
+            case 64: return launch_conv<64, 0>(tm, p, m_tiles, st, s);
+            default: return launch_conv<32, 0>(tm, p, m_tiles, st, s);
         }
     }
     switch (block_n) {
-        case 128: return launch_conv<128, 1>(tm, p, m_tiles, s);
-        case 64: return launch_conv<64, 1>(tm, p, m_tiles, s);
-        default: return launch_conv<32, 1>(tm, p, m_tiles, s);
+        case 128: return launch_conv<128, 1>(tm, p, m_tiles, st, s);
+        case 64: return launch_conv<64, 1>(tm, p, m_tiles, st, s);
+        default: return launch_conv<32, 1>(tm, p, m_tiles, st, s);
     }
 }
 

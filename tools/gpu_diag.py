@@ -396,6 +396,42 @@ def conv_timing():
     return out
 
 
+@check
+def conv_tune():
+    """Forward conv time vs (block_n, ring depth) for the shapes that dominate the step."""
+    import torch
+    from b200lp import kernels as K
+    out = []
+    shapes = [(8, 256, 256, 64, 64, 3), (8, 256, 256, 128, 64, 3), (8, 128, 128, 128, 128, 3), (8, 128, 128, 256, 128, 3),
+              (8, 64, 64, 256, 256, 3), (8, 64, 64, 512, 256, 3), (8, 32, 32, 512, 512, 3), (8, 16, 16, 512, 512, 3)]
+    for (N, H, W, Cin, Cout, k) in shapes:
+        x = torch.randn(N, H, W, Cin, device="cuda")
+        w = torch.randn(Cout, Cin, k, k, device="cuda")
+        wp = K.pack_conv_weight(w)
+        y = torch.empty(N, H, W, Cout, device="cuda")
+        flops = 2.0 * N * H * W * Cin * Cout * k * k
+        rec = {"case": f"N{N} H{H} Cin{Cin} Cout{Cout}", "ok": True}
+        for bn in (64, 128, 256):
+            if Cout % bn:
+                continue
+            for st in (2, 3, 4, 6, 8):
+                if st * (16384 + bn * 128) + 1024 > 227 * 1024:
+                    continue
+                fn = lambda: K.conv_fwd(x, wp, k, out=y, block_n=bn, stages=st)
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(8):
+                    fn()
+                e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 8
+                rec[f"bn{bn}_st{st}"] = round(flops / ms / 1e9, 0)
+        out.append(rec)
+    return out
+
+
 def _run_child(name):
     res = CHECKS[name]()
     print("@@RESULT@@" + json.dumps(res))
