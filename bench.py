@@ -166,12 +166,14 @@ def timed(fn, steps, dist_on):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(workload, sample_batch, steps, warmup):
+def cpu_reference_rate(workload, sample_batch, steps, warmup, budget_s=25.0):
     """frames/s of the CPU port of the reference step (oracle/cpu_step.py) with all host threads."""
     from oracle.cpu_step import OracleTrainer
     from oracle import synth
     wl = WORKLOADS[workload]
-    cores = os.cpu_count() or 1
+    # torch CPU convolutions stop scaling (and then thrash) well below the 128 hardware threads of the GPU box's host:
+    # 132.8 s/step with 128 threads (profiles/r01_bench_first_run.json) — use at most 32 and say so
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     cfg = dict(synth.FULL_CFG)
     cfg["num_labels"] = max(wl["num_labels"], 1)
@@ -182,9 +184,13 @@ def cpu_reference_rate(workload, sample_batch, steps, warmup):
     for _ in range(warmup):
         tr.step(data, target)
     t0 = time.perf_counter()
+    done = 0
     for _ in range(steps):
         tr.step(data, target)
-    dt = (time.perf_counter() - t0) / steps
+        done += 1
+        if time.perf_counter() - t0 > budget_s:      # bounded sample: stop after ~budget_s seconds of CPU work
+            break
+    dt = (time.perf_counter() - t0) / done
     return sample_batch / dt, dt, cores
 
 
@@ -194,8 +200,8 @@ def run_reference_arm(args):
         return
     wl_name = "finetune" if args.workload == "drive" else args.workload
     sample_b = 1
-    steps, warmup = max(1, min(args.steps, 6)), max(0, min(args.warmup, 1))
-    rate, dt, cores = cpu_reference_rate(wl_name, sample_b, steps, warmup)
+    steps, warmup = max(1, min(args.steps, 6)), 0
+    rate, dt, cores = cpu_reference_rate(wl_name, sample_b, steps, warmup, budget_s=60.0)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -290,6 +296,39 @@ def roofline_pass(step_fn, peaks):
     return out
 
 
+def drive_benchmark(device, batch=64, n_batches=6):
+    """BASELINE configs[3]: drive.py inner loop (drive.py:84-98) batched — pinned host frames -> pose embedder ->
+    generator forward (eval, fine-tuned) -> clamp/uint8 -> asynchronous D2H.  Returns frames/s (end to end)."""
+    import importlib
+    import drive
+    wl = WORKLOADS["finetune"]
+    ns = make_namespace(wl, device, "/nonexistent", batch)
+    torch.manual_seed(7)
+    G = importlib.import_module("generators.vector_pose_unsupervised_segmentation_noBottleneck").Wrapper.get_net(ns)
+    E = importlib.import_module("embedders.unsupervised_pose_separate_embResNeXt_segmentation").Wrapper.get_net(ns)
+    G.enable_finetuning({"embeds": torch.randn(1, FULL["embed_channels"], device=device)})
+    E.enable_finetuning()
+    with torch.no_grad():
+        G.train()
+        for m in G.modules():
+            if hasattr(m, "inv_sigma"):
+                for _ in range(20):
+                    m.inv_sigma()
+    G.eval(); E.eval()
+    g = torch.Generator().manual_seed(5)
+    frames = [torch.rand(batch, 3, 256, 256, generator=g) for _ in range(2)]
+    with torch.no_grad():
+        drive.render(E, G, (frames[i % 2] for i in range(2)), device, sink=None, with_driver=False)   # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = drive.render(E, G, (frames[i % 2] for i in range(n_batches)), device, sink=None, with_driver=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    return {"value": round(n / dt, 1), "unit": "frames/s", "batch": batch, "frames": n,
+            "what": "drive.py loop, bs=64: pinned H2D of driver frames, MobileNetV2 pose embed, generator forward "
+                    "(bf16x3), clamp+uint8, async D2H of the frames"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -360,14 +399,20 @@ def main():
             peaks = json.loads(pk.read_text())
         extra.update(roofline_pass(step_resident, peaks))
         extra["peaks_source"] = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    if rank == 0 and world == 1:
+        try:
+            with torch.no_grad():
+                extra["drive"] = drive_benchmark(device)
+        except Exception as err:
+            extra["drive"] = {"error": str(err)[:200]}
     if dist_on:
         torch.distributed.barrier()
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            rate, dt, cores = cpu_reference_rate(args.workload, 1, 2, 1)
+            rate, dt, cores = cpu_reference_rate(args.workload, 1, 2, 0, budget_s=20.0)
             cpu_baseline = {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": f"2 steps at batch 1 of the same workload ({dt:.1f} s/step), fp32, {cores} torch threads"}
+                            "sample": f"<=2 steps at batch 1 of the same workload ({dt:.1f} s/step), fp32, {cores} torch threads"}
         except Exception as err:   # the checker must never take the product number down with it
             cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {err}"}
 

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 5
+#define B200LP_ABI_VERSION 7
 
 #define B200LP_OK 0
 #define B200LP_EINVAL (-1)   /* bad shape / unsupported configuration */
@@ -45,13 +45,16 @@ int64_t b200lp_launch_count(void);
  * (torch autograd's conv backward-data).
  *
  *   y[n,h,w,co] = epilogue( sum_{kh,kw,ci} x[n,h+kh-p,w+kw-p,ci] * wp[co][kh*k+kw][ci] )
- *   epilogue: (+ bias[co]) (+ residual) (relu) (round to tf32)
+ *   epilogue: (* out_scale) (+ bias[co]) (+ residual) (relu) (round to tf32)
  * Requirements: Cin % 32 == 0, Cout % 32 == 0, H and W powers of two >= 2, ksize in {1,3}.
  */
 typedef struct {
     const void* x;          /* precision 0: float [N,H,W,Cin] NHWC (tf32-rounded values)
                                precision 1: bf16  [2][N,H,W,Cin] = (hi, lo) planes, hi + lo == value            */
     const void* wp;         /* packed weights [Cout][ksize*ksize][Cin]: float (tf32) or bf16 [2][...] (hi, lo)   */
+    const float* out_scale; /* NULL, or device pointer to ONE float s: y = s * conv(x, wp) (+bias...).  With s = 1/sigma
+                               the spectral-norm division costs nothing and `wp` is packed once per weight update
+                               instead of once per forward call (3 discriminator passes share one packing).       */
     const float* bias;      /* [Cout] or NULL                                                                    */
     const float* residual;  /* NULL, or [N,H,W,Cout] (mode 1), or [N,H/2,W/2,Cout] (mode 2: nearest-2x source)    */
     float* y;               /* [N,H,W,Cout] fp32                                                                 */
@@ -95,6 +98,10 @@ typedef struct {
     int32_t N, H, W, Cin, Cout;
     int32_t ksize;
     float scale;      /* dw *= scale (e.g. 1/sigma of the spectral norm)              */
+    int32_t kstep;    /* tuning: pixels per pipeline stage, 0 = auto, else 32 / 64    */
+    int32_t stages;   /* tuning: smem ring depth, 0 = auto                            */
+    int32_t splits;   /* tuning: split-K factor, 0 = auto (workspace must hold splits * |dw| floats) */
+    int32_t reserved;
 } b200lp_wgrad_args;
 
 int64_t b200lp_conv_wgrad_workspace(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize);

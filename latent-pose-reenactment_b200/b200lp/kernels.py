@@ -57,8 +57,9 @@ def pack_conv_weight(w_oihw, scale=None, transpose=False, precision=TF32):
 
 
 def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False, round_tf32=False, block_n=0,
-             out=None, emit_split=False, stages=0):
+             out=None, emit_split=False, stages=0, scale=None):
     """x NHWC (N,H,W,Cin) float32 [TF32] or (2,N,H,W,Cin) bfloat16 (hi, lo) [BF16X3]; wp packed to match.
+    `scale`: optional 1-element device tensor s, y = s * conv(x, wp) (+ bias ...).
     Returns y (N,H,W,Cout) float32, or (y, y_split) with y_split (2,N,H,W,Cout) bfloat16 when emit_split."""
     lib = L.load()
     split_in = x.dtype == torch.bfloat16
@@ -74,7 +75,8 @@ def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False
     y = out if out is not None else torch.empty((n, h, w, cout), dtype=torch.float32, device=x.device)
     y_split = torch.empty((2, n, h, w, cout), dtype=torch.bfloat16, device=x.device) if emit_split else None
     a = L.ConvArgs()
-    a.x = L.ptr(x, x.dtype); a.wp = L.ptr(wp, wp.dtype); a.bias = L.ptr(bias); a.residual = L.ptr(residual)
+    a.x = L.ptr(x, x.dtype); a.wp = L.ptr(wp, wp.dtype); a.out_scale = L.ptr(scale); a.bias = L.ptr(bias)
+    a.residual = L.ptr(residual)
     a.y = L.ptr(y); a.y_split = L.ptr(y_split, torch.bfloat16)
     a.N, a.H, a.W, a.Cin, a.Cout = n, h, w, cin, cout
     a.ksize = ksize
@@ -90,7 +92,7 @@ def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False
     return (y, y_split) if emit_split else y
 
 
-def conv_wgrad(x, dy, ksize, scale=1.0):
+def conv_wgrad(x, dy, ksize, scale=1.0, kstep=0, stages=0, splits=0):
     """x (N,H,W,Cin), dy (N,H,W,Cout) -> dw OIHW (Cout,Cin,k,k) * scale."""
     lib = L.load()
     n, h, w, cin = x.shape
@@ -98,6 +100,8 @@ def conv_wgrad(x, dy, ksize, scale=1.0):
     nbytes = lib.b200lp_conv_wgrad_workspace(n, h, w, cin, cout, ksize)
     if nbytes < 0:
         raise L.B200lpError(f"conv_wgrad_workspace: {L.last_error()}")
+    if splits:
+        nbytes = max(nbytes, splits * ksize * ksize * cin * cout * 4)
     ws = _ws(nbytes, x.device)
     dw = torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
     a = L.WgradArgs()
@@ -106,6 +110,7 @@ def conv_wgrad(x, dy, ksize, scale=1.0):
     a.N, a.H, a.W, a.Cin, a.Cout = n, h, w, cin, cout
     a.ksize = ksize
     a.scale = float(scale)
+    a.kstep, a.stages, a.splits = kstep, stages, splits
     with _timed("conv_wgrad_tf32", flops=2.0 * n * h * w * cin * cout * ksize * ksize):
         L.check(lib.b200lp_conv_wgrad(byref(a), L.stream_ptr()), "conv_wgrad")
     return dw
@@ -249,7 +254,7 @@ def conv3x3_c3_fwd(x_nchw, w, wscale=None, bias=None, pre_scale=None, pre_shift=
     assert c == 3
     cout = w.shape[0]
     y = torch.empty((n, h, wd, cout), dtype=torch.float32, device=x_nchw.device)
-    with _timed("direct_conv", nbytes=4.0 * (x_nchw.numel() + y.numel())):
+    with _timed("conv3x3_c3_fwd", nbytes=4.0 * (x_nchw.numel() + y.numel())):
         L.check(lib.b200lp_conv3x3_c3_fwd(L.ptr(x_nchw), L.ptr(w), L.ptr(wscale), L.ptr(bias), L.ptr(pre_scale),
                                           L.ptr(pre_shift), L.ptr(y), n, h, wd, cout, int(relu), int(round_tf32),
                                           L.stream_ptr()), "conv3x3_c3_fwd")
@@ -260,7 +265,7 @@ def conv3x3_c3_dgrad(dy, w, wscale=None, pre_scale=None):
     lib = L.load()
     n, h, wd, cout = dy.shape
     dx = torch.empty((n, 3, h, wd), dtype=torch.float32, device=dy.device)
-    with _timed("direct_conv", nbytes=4.0 * (dy.numel() + dx.numel())):
+    with _timed("conv3x3_c3_dgrad", nbytes=4.0 * (dy.numel() + dx.numel())):
         L.check(lib.b200lp_conv3x3_c3_dgrad(L.ptr(dy), L.ptr(w), L.ptr(wscale), L.ptr(pre_scale), L.ptr(dx), n, h, wd,
                                             cout, L.stream_ptr()), "conv3x3_c3_dgrad")
     return dx
@@ -270,7 +275,7 @@ def conv3x3_c3_wgrad(x_nchw, dy, scale=1.0):
     lib = L.load()
     n, h, wd, cout = dy.shape
     dw = torch.empty((cout, 3, 3, 3), dtype=torch.float32, device=dy.device)
-    with _timed("direct_conv", nbytes=4.0 * (dy.numel() + x_nchw.numel())):
+    with _timed("conv3x3_c3_wgrad", nbytes=4.0 * (dy.numel() + x_nchw.numel())):
         L.check(lib.b200lp_conv3x3_c3_wgrad(L.ptr(x_nchw), L.ptr(dy), L.ptr(dw), c_float(scale), n, h, wd, cout,
                                             L.stream_ptr()), "conv3x3_c3_wgrad")
     return dw
@@ -282,7 +287,7 @@ def gen_tail_fwd(x, w, wscale, bias):
     rgbs = torch.empty((n, 3, h, wd), dtype=torch.float32, device=x.device)
     segm = torch.empty((n, 1, h, wd), dtype=torch.float32, device=x.device)
     t = torch.empty((n, h, wd, 4), dtype=torch.float32, device=x.device)
-    with _timed("direct_conv", nbytes=4.0 * (x.numel() + rgbs.numel() + segm.numel() + t.numel())):
+    with _timed("gen_tail_fwd", nbytes=4.0 * (x.numel() + rgbs.numel() + segm.numel() + t.numel())):
         L.check(lib.b200lp_gen_tail_fwd(L.ptr(x), L.ptr(w), L.ptr(wscale), L.ptr(bias), L.ptr(rgbs), L.ptr(segm),
                                         L.ptr(t), n, h, wd, cin, L.stream_ptr()), "gen_tail_fwd")
     return rgbs, segm, t
@@ -292,19 +297,19 @@ def gen_tail_bwd(x, t, w, wscale, d_rgbs, d_segm, need_dx=True, need_dw=True):
     lib = L.load()
     n, h, wd, cin = x.shape
     da = torch.empty((n, h, wd, 4), dtype=torch.float32, device=x.device)
-    with _timed("direct_conv", nbytes=4.0 * 3 * da.numel()):
+    with _timed("gen_tail_bwd_act", nbytes=4.0 * 3 * da.numel()):
         L.check(lib.b200lp_gen_tail_bwd_act(L.ptr(t), L.ptr(d_rgbs), L.ptr(d_segm), L.ptr(da), n, h, wd,
                                             L.stream_ptr()), "gen_tail_bwd_act")
     dx = dw = db = None
     if need_dx:
         dx = torch.empty_like(x)
-        with _timed("direct_conv", nbytes=4.0 * (da.numel() + dx.numel())):
+        with _timed("gen_tail_bwd_data", nbytes=4.0 * (da.numel() + dx.numel())):
             L.check(lib.b200lp_gen_tail_bwd_data(L.ptr(da), L.ptr(w), L.ptr(wscale), L.ptr(dx), n, h, wd, cin,
                                                  L.stream_ptr()), "gen_tail_bwd_data")
     if need_dw:
         dw = torch.empty((4, cin, 3, 3), dtype=torch.float32, device=x.device)
         db = torch.empty((4,), dtype=torch.float32, device=x.device)
-        with _timed("direct_conv", nbytes=4.0 * (da.numel() + x.numel())):
+        with _timed("gen_tail_bwd_weight", nbytes=4.0 * (da.numel() + x.numel())):
             L.check(lib.b200lp_gen_tail_bwd_weight(L.ptr(x), L.ptr(da), L.ptr(dw), L.ptr(db), n, h, wd, cin,
                                                    L.stream_ptr()), "gen_tail_bwd_weight")
     return dx, dw, db

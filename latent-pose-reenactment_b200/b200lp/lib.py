@@ -13,7 +13,7 @@ import torch
 
 _PKG = Path(__file__).resolve().parent.parent
 LIB_PATH = _PKG / "lib" / "libb200lp.so"
-ABI_VERSION = 5
+ABI_VERSION = 7
 
 
 class B200lpError(RuntimeError):
@@ -22,8 +22,8 @@ class B200lpError(RuntimeError):
 
 class ConvArgs(Structure):
     _fields_ = [
-        ("x", c_void_p), ("wp", c_void_p), ("bias", c_void_p), ("residual", c_void_p), ("y", c_void_p),
-        ("y_split", c_void_p),
+        ("x", c_void_p), ("wp", c_void_p), ("out_scale", c_void_p), ("bias", c_void_p), ("residual", c_void_p),
+        ("y", c_void_p), ("y_split", c_void_p),
         ("N", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("Cout", c_int32),
         ("ksize", c_int32), ("residual_mode", c_int32), ("relu", c_int32), ("round_tf32", c_int32),
         ("block_n", c_int32), ("precision", c_int32), ("stages", c_int32),
@@ -36,6 +36,7 @@ class WgradArgs(Structure):
         ("workspace_bytes", c_int64),
         ("N", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("Cout", c_int32),
         ("ksize", c_int32), ("scale", c_float),
+        ("kstep", c_int32), ("stages", c_int32), ("splits", c_int32), ("reserved", c_int32),
     ]
 
 

@@ -13,12 +13,42 @@ def _dot(a, b):
     return (a * b).sum()
 
 
-def _conv_backward(ctx_ksize, x_f32, weight_orig, inv_sigma, dy, need_x, need_w, need_s):
-    """Shared backward of the tensor-core convolutions (TF32 data / weight gradient kernels)."""
+class PackCache:
+    """Packed (tensor-core layout) copies of one weight, keyed by (transpose, precision) and validated by the weight
+    tensor's autograd version counter: optimizer / EMA / load_state_dict updates are in-place and bump it, so a weight
+    is re-packed once per update instead of once per forward call (the three discriminator passes of a step and the
+    backward passes share the copies).  Lives on the owning module; deep copies start empty."""
+
+    def __init__(self):
+        self.entries = {}
+
+    def __deepcopy__(self, memo):
+        return PackCache()
+
+    def get(self, weight, transpose, precision):
+        key = (transpose, precision)
+        hit = self.entries.get(key)
+        ver = weight._version
+        if hit is not None and hit[0] == ver and hit[1] == weight.data_ptr():
+            return hit[2]
+        packed = K.pack_conv_weight(weight.detach(), None, transpose=transpose, precision=precision)
+        self.entries[key] = (ver, weight.data_ptr(), packed)
+        return packed
+
+
+def _packed(weight, cache, transpose, precision=K.TF32):
+    if cache is not None:
+        return cache.get(weight, transpose, precision)
+    return K.pack_conv_weight(weight.detach(), None, transpose=transpose, precision=precision)
+
+
+def _conv_backward(ctx_ksize, x_f32, weight_orig, inv_sigma, dy, need_x, need_w, need_s, cache=None):
+    """Shared backward of the tensor-core convolutions (TF32 data / weight gradient kernels).
+    y = s * conv(x, W):  dx = s * conv_T(dy, W);  dW = s * wgrad(x, dy);  ds = <wgrad(x, dy), W>."""
     dx = dw = ds = None
     if need_x:
-        wpt = K.pack_conv_weight(weight_orig, inv_sigma, transpose=True)
-        dx = K.conv_fwd(dy, wpt, ctx_ksize)
+        wpt = _packed(weight_orig, cache, True)
+        dx = K.conv_fwd(dy, wpt, ctx_ksize, scale=inv_sigma)
     if need_w or (need_s and inv_sigma is not None):
         g = K.conv_wgrad(x_f32, dy, ctx_ksize)
         if inv_sigma is not None:
@@ -42,19 +72,20 @@ class Conv2dFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight_orig, inv_sigma, bias, residual, ksize, residual_mode, relu, round_out, x_split,
-                emit_split):
+                emit_split, cache):
         """`x_split` (optional, non-differentiable): the (hi, lo) bf16 planes of x — when given, the forward runs in
         bf16x3 precision on them; gradients still flow to `x`.  `emit_split`: also return the (hi, lo) planes of y."""
         if x_split is not None:
-            wp = K.pack_conv_weight(weight_orig, inv_sigma, transpose=False, precision=K.BF16X3)
+            wp = _packed(weight_orig, cache, False, K.BF16X3)
             src = x_split
         else:
-            wp = K.pack_conv_weight(weight_orig, inv_sigma, transpose=False)
+            wp = _packed(weight_orig, cache, False)
             src = x
         out = K.conv_fwd(src, wp, ksize, bias=bias, residual=residual, residual_mode=residual_mode, relu=relu,
-                         round_tf32=round_out, emit_split=emit_split)
+                         round_tf32=round_out, emit_split=emit_split, scale=inv_sigma)
         y, y_split = out if emit_split else (out, None)
         ctx.ksize, ctx.residual_mode, ctx.relu = ksize, residual_mode, relu
+        ctx.cache = cache
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, weight_orig, inv_sigma, y if relu else None)
@@ -70,21 +101,21 @@ class Conv2dFn(torch.autograd.Function):
         if ctx.relu:
             dy = K.relu_bwd(y, dy)
         need_x, need_w, need_s, need_b, need_r = ctx.needs_input_grad[:5]
-        dx, dw, ds = _conv_backward(ctx.ksize, x, weight_orig, inv_sigma, dy, need_x, need_w, need_s)
+        dx, dw, ds = _conv_backward(ctx.ksize, x, weight_orig, inv_sigma, dy, need_x, need_w, need_s, ctx.cache)
         db = dr = None
         if ctx.has_bias and need_b:
             db = K.bias_grad(dy)
         if ctx.has_res and need_r:
             dr = dy if ctx.residual_mode == 1 else K.upsample2_bwd(dy)
-        return dx, dw, ds, db, dr, None, None, None, None, None, None
+        return dx, dw, ds, db, dr, None, None, None, None, None, None, None
 
 
 def conv2d(x, weight_orig, inv_sigma=None, bias=None, residual=None, ksize=3, residual_mode=0, relu=False,
-           round_out=False, x_split=None, emit_split=False):
+           round_out=False, x_split=None, emit_split=False, cache=None):
     if residual is None:
         residual_mode = 0
     return Conv2dFn.apply(x, weight_orig, inv_sigma, bias, residual, ksize, residual_mode, relu, round_out, x_split,
-                          emit_split)
+                          emit_split, cache)
 
 
 class AdaINConvFn(torch.autograd.Function):
@@ -96,7 +127,8 @@ class AdaINConvFn(torch.autograd.Function):
     Backward: TF32 data- and weight-gradient kernels, then the AdaIN backward kernels."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, weight_orig, inv_sigma, residual, eps, upsample2, residual_mode, emit_split):
+    def forward(ctx, x, gamma, beta, weight_orig, inv_sigma, residual, eps, upsample2, residual_mode, emit_split,
+                cache):
         mean, rstd = K.in_stats(x, eps)
         need_bwd = any(ctx.needs_input_grad)      # False under torch.no_grad() (drive.py, EMA forward)
         if need_bwd:
@@ -105,10 +137,12 @@ class AdaINConvFn(torch.autograd.Function):
         else:
             a_f32, a_split = None, K.adain_relu(x, mean, rstd, gamma, beta, upsample2=upsample2, want_f32=False,
                                                 want_split=True)
-        wp = K.pack_conv_weight(weight_orig, inv_sigma, transpose=False, precision=K.BF16X3)
-        out = K.conv_fwd(a_split, wp, 3, residual=residual, residual_mode=residual_mode, emit_split=emit_split)
+        wp = _packed(weight_orig, cache, False, K.BF16X3)
+        out = K.conv_fwd(a_split, wp, 3, residual=residual, residual_mode=residual_mode, emit_split=emit_split,
+                         scale=inv_sigma)
         y, y_split = out if emit_split else (out, None)
         ctx.upsample2, ctx.residual_mode = upsample2, residual_mode
+        ctx.cache = cache
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, mean, rstd, gamma, beta, weight_orig, inv_sigma, a_f32)
         if emit_split:
@@ -121,22 +155,23 @@ class AdaINConvFn(torch.autograd.Function):
         x, mean, rstd, gamma, beta, weight_orig, inv_sigma, a_f32 = ctx.saved_tensors
         dy = dy.contiguous()
         need_x, need_g, need_b, need_w, need_s, need_r = ctx.needs_input_grad[:6]
-        da, dw, ds = _conv_backward(3, a_f32, weight_orig, inv_sigma, dy, need_x or need_g or need_b, need_w, need_s)
+        da, dw, ds = _conv_backward(3, a_f32, weight_orig, inv_sigma, dy, need_x or need_g or need_b, need_w, need_s,
+                                    ctx.cache)
         dx = dgm = dbt = None
         if da is not None:
             dx, dgm, dbt = K.adain_relu_bwd(x, mean, rstd, gamma, beta, da, upsample2=ctx.upsample2)
         dr = None
         if ctx.has_res and need_r:
             dr = dy if ctx.residual_mode == 1 else K.upsample2_bwd(dy)
-        return dx, dgm, dbt, dw, ds, dr, None, None, None, None
+        return dx, dgm, dbt, dw, ds, dr, None, None, None, None, None
 
 
 def adain_conv(x, gamma, beta, weight_orig, inv_sigma, residual=None, residual_mode=0, eps=1e-4, upsample2=False,
-               emit_split=False):
+               emit_split=False, cache=None):
     if residual is None:
         residual_mode = 0
     return AdaINConvFn.apply(x, gamma, beta, weight_orig, inv_sigma, residual, eps, upsample2, residual_mode,
-                             emit_split)
+                             emit_split, cache)
 
 
 class AdaINReLUFn(torch.autograd.Function):

@@ -32,6 +32,7 @@ constexpr int kRowBytes = 128;    // one smem row = 128 bytes = swizzle span = 3
 constexpr int kConvThreads = 192;
 
 struct ConvParams {
+    const float* out_scale;   // optional device scalar: accumulator *= *out_scale before bias (1/sigma of spectral norm)
     const float* bias;
     const float* residual;
     float* y;
@@ -60,9 +61,9 @@ struct ConvCfg {
     static constexpr int kMaxStages = 8;
     // default ring depth.  Shallow rings for BLOCK_N <= 128 keep a CTA under ~100 KB so that TWO CTAs share an SM:
     // one CTA's epilogue (TMEM -> registers -> HBM) then overlaps the other CTA's main loop.
-    static constexpr int kDefaultStages = MODE == 0 ? ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 3 : 4))
+    static constexpr int kDefaultStages = MODE == 0 ? ((BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 3 : 4))
                                                     : ((BLOCK_N == 128) ? 3 : (BLOCK_N == 64 ? 4 : 5));
-    static constexpr int kMaxSmemBytes = 227 * 1024;
+    static constexpr int kMaxSmemBytes = 226 * 1024;   // 227 KB opt-in limit minus the static barriers
     static constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
@@ -197,6 +198,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
             rrow = p.residual + rp * p.Cout + n_tile * BLOCK_N;
         }
         const float* brow = p.bias ? p.bias + n_tile * BLOCK_N : nullptr;
+        const float oscale = p.out_scale ? __ldg(p.out_scale) : 1.0f;
 
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
@@ -209,10 +211,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 o;
-                    o.x = __uint_as_float(v[j + 0]);
-                    o.y = __uint_as_float(v[j + 1]);
-                    o.z = __uint_as_float(v[j + 2]);
-                    o.w = __uint_as_float(v[j + 3]);
+                    o.x = __uint_as_float(v[j + 0]) * oscale;
+                    o.y = __uint_as_float(v[j + 1]) * oscale;
+                    o.z = __uint_as_float(v[j + 2]) * oscale;
+                    o.w = __uint_as_float(v[j + 3]) * oscale;
                     if (brow) {
                         const float4 b = __ldg(reinterpret_cast<const float4*>(brow + c0 + j));
                         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
@@ -302,6 +304,7 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
                    "conv_fwd: bf16x3 needs Cin %% 64 == 0 (or Cin == 32), got %d", a->Cin);
 
     ConvParams p;
+    p.out_scale = a->out_scale;
     p.bias = a->bias;
     p.residual = a->residual_mode ? a->residual : nullptr;
     p.y = a->y;

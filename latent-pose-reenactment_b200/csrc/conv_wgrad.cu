@@ -16,15 +16,18 @@
 namespace b200lp {
 
 constexpr int kWgM = 128;          // (tap,ci) rows per CTA
-constexpr int kWgKStep = 32;       // pixels per pipeline stage
 constexpr int kWgThreads = 192;
-constexpr int kWgBlkBytes = kWgKStep * 128;  // one [32 pixels][32 ch] box = 4 KB
+constexpr int kWgMaxStages = 8;
+constexpr int kWgMaxSmem = 226 * 1024;   // 227 KB opt-in limit minus the static barriers
 
 struct WgradParams {
     float* ws;            // [splits][rows_total][Cout]
     int N, H, W, Cin, Cout;
     int ksize;
-    int pw, ph, pn;       // pixel box: pw*ph*pn == 32
+    int pw, ph, pn;       // pixel box: pw*ph*pn == kstep
+    int kstep;            // pixels per pipeline stage (32 or 64)
+    int blk_bytes;        // one [kstep pixels][32 ch] box = kstep * 128 bytes
+    int stages;           // smem ring depth
     int steps_w, steps_h; // boxes per image row / column
     int total_steps;      // K steps over the whole batch
     int steps_per_split;
@@ -35,24 +38,24 @@ struct WgradParams {
 
 template <int BLOCK_N>
 struct WgCfg {
-    static constexpr int kABytes = 4 * kWgBlkBytes;                // 16 KB
-    static constexpr int kBBytes = (BLOCK_N / 32) * kWgBlkBytes;
-    static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+    static constexpr int kBlocks = 4 + BLOCK_N / 32;               // [kstep][32 ch] boxes per stage (A: 4, B: N/32)
     static constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(kWgThreads, 1)
+__global__ void __launch_bounds__(kWgThreads, 2)
 conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                        const WgradParams p) {
     using Cfg = WgCfg<BLOCK_N>;
-    constexpr int kStages = Cfg::kStages;
+    const int kStages = p.stages;
+    const int kWgBlkBytes = p.blk_bytes;
+    const int kABytes = 4 * kWgBlkBytes;
+    const int kBBytes = (BLOCK_N / 32) * kWgBlkBytes;
+    const int kStageBytes = kABytes + kBBytes;
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kStages];
-    __shared__ __align__(8) uint64_t empty_bar[kStages];
+    __shared__ __align__(8) uint64_t full_bar[kWgMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kWgMaxStages];
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_slot;
 
@@ -104,7 +107,7 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     blk_c[j] = 0; blk_dx[j] = 0; blk_dy[j] = 0;
                 }
             }
-            const uint32_t tx_bytes = static_cast<uint32_t>(nvalid * kWgBlkBytes + Cfg::kBBytes);
+            const uint32_t tx_bytes = static_cast<uint32_t>(nvalid * kWgBlkBytes + kBBytes);
             int stage = 0;
             uint32_t phase = 0;
             for (int i = 0; i < nsteps; ++i) {
@@ -115,8 +118,8 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 const int tn = ks / p.steps_h;
                 const int w0 = tw * p.pw, h0 = th * p.ph, n0 = tn * p.pn;
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
-                uint8_t* sa = smem_al + stage * Cfg::kStageBytes;
-                uint8_t* sb = sa + Cfg::kABytes;
+                uint8_t* sa = smem_al + stage * kStageBytes;
+                uint8_t* sb = sa + kABytes;
                 mbar_expect_tx(&full_bar[stage], tx_bytes);
                 for (int j = 0; j < nvalid; ++j)
                     tma_load_4d(sa + j * kWgBlkBytes, &tmX, &full_bar[stage], blk_c[j], w0 + blk_dx[j],
@@ -136,10 +139,10 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             for (int i = 0; i < nsteps; ++i) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
-                const uint32_t b_addr = a_addr + Cfg::kABytes;
-#pragma unroll
-                for (int k = 0; k < kWgKStep / 8; ++k) {
+                const uint32_t a_addr = smem_base + stage * kStageBytes;
+                const uint32_t b_addr = a_addr + kABytes;
+                const int kiters = p.kstep >> 3;
+                for (int k = 0; k < kiters; ++k) {
                     // MN-major 32-bit operands must use SWIZZLE_128B_BASE32B (layout type 1): atoms of 4 K-rows x 128 B;
                     // LBO = stride between 32-channel blocks, SBO = stride between 4-row K groups (512 B);
                     // one K=8 MMA spans two atoms, so stepping K by 8 = +1024 bytes.
@@ -202,23 +205,40 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
 }
 
 struct WgPlan {
-    int block_n, m_tiles, n_tiles, splits, steps_per_split, total_steps, pw, ph, pn;
+    int block_n, m_tiles, n_tiles, splits, steps_per_split, total_steps, pw, ph, pn, kstep, stages;
 };
 
-static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int ksize, WgPlan* pl) {
+static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int ksize, WgPlan* pl, int kstep_req = 0,
+                      int stages_req = 0, int splits_req = 0) {
     if (!(ksize == 1 || ksize == 3) || Cin % 32 || Cout % 32 || Cin <= 0 || Cout <= 0 || N <= 0) return -1;
     if (ilog2_exact(H) < 1 || ilog2_exact(W) < 1) return -1;
-    pl->pw = W < 32 ? W : 32;
-    pl->ph = (32 / pl->pw) < H ? (32 / pl->pw) : H;
-    pl->pn = 32 / (pl->pw * pl->ph);
-    const int steps_n = (N + pl->pn - 1) / pl->pn;
-    pl->total_steps = (W / pl->pw) * (H / pl->ph) * steps_n;
     pl->block_n = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32));
     pl->n_tiles = Cout / pl->block_n;
+    // pixels per pipeline stage: 64 amortises the per-stage TMA issue / barrier cost when the whole batch offers
+    // enough K (and the tile is not already 48 KB per 32 pixels)
+    // (measured on B200, profiles/r01_conv_wgrad_tuning_sweep.log: 32-pixel stages with shallow rings — more CTAs per
+    //  SM — beat 64-pixel stages on every shape of the step except one tie)
+    int kstep = kstep_req ? kstep_req : 32;
+    if (kstep != 32 && kstep != 64) return -1;
+    if (static_cast<long>(N) * H * W < kstep) kstep = 32;
+    pl->kstep = kstep;
+    pl->pw = W < kstep ? W : kstep;
+    pl->ph = (kstep / pl->pw) < H ? (kstep / pl->pw) : H;
+    pl->pn = kstep / (pl->pw * pl->ph);
+    const int steps_n = (N + pl->pn - 1) / pl->pn;
+    pl->total_steps = (W / pl->pw) * (H / pl->ph) * steps_n;
+    const int stage_bytes = (4 + pl->block_n / 32) * kstep * 128;
+    int stages = stages_req ? stages_req : (pl->block_n == 256 ? 2 : 3);   // <= ~100 KB per CTA: two CTAs share an SM
+    if (stages > kWgMaxStages) stages = kWgMaxStages;
+    while (stages > 1 && stages * stage_bytes + 1024 > kWgMaxSmem) --stages;
+    pl->stages = stages;
     const int blocks_total = ksize * ksize * (Cin / 32);
     pl->m_tiles = (blocks_total + 3) / 4;
     const int base = pl->m_tiles * pl->n_tiles;
-    int splits = (2 * 148 + base - 1) / base;
+    // split-K so that the grid is at most one full wave of 2 CTAs x 148 SMs (one CTA over the wave costs a whole
+    // extra wave), with at least 4 K steps per CTA
+    int splits = splits_req ? splits_req : (2 * 148) / base;
+    if (!splits_req && splits > pl->total_steps / 4) splits = pl->total_steps / 4;
     if (splits > 64) splits = 64;
     if (splits > pl->total_steps) splits = pl->total_steps;
     if (splits < 1) splits = 1;
@@ -230,15 +250,17 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int ksize, WgPlan*
 template <int BLOCK_N>
 static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradParams& p, const WgPlan& pl,
                         cudaStream_t stream) {
-    using Cfg = WgCfg<BLOCK_N>;
     static bool attr_set = false;
     if (!attr_set) {
         B200LP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_tf32_kernel<BLOCK_N>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, kWgMaxSmem));
+        B200LP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_tf32_kernel<BLOCK_N>,
+                                               cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
+    const int smem_bytes = pl.stages * (4 + BLOCK_N / 32) * pl.kstep * 128 + 1024;
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
-    conv_wgrad_tf32_kernel<BLOCK_N><<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(tmX, tmDY, p);
+    conv_wgrad_tf32_kernel<BLOCK_N><<<grid, kWgThreads, smem_bytes, stream>>>(tmX, tmDY, p);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;
@@ -256,13 +278,13 @@ extern "C" int64_t b200lp_conv_wgrad_workspace(int32_t N, int32_t H, int32_t W, 
                   ksize);
         return B200LP_EINVAL;
     }
-    return static_cast<int64_t>(pl.splits) * ksize * ksize * Cin * Cout * 4;
+    return static_cast<int64_t>(pl.splits) * ksize * ksize * Cin * Cout * 4;   // default plan (tuning knobs = auto)
 }
 
 extern "C" int32_t b200lp_conv_wgrad(const b200lp_wgrad_args* a, void* stream) {
     B200LP_REQUIRE(a && a->x && a->dy && a->dw && a->workspace, "conv_wgrad: null pointer");
     WgPlan pl;
-    B200LP_REQUIRE(plan_wgrad(a->N, a->H, a->W, a->Cin, a->Cout, a->ksize, &pl) == 0,
+    B200LP_REQUIRE(plan_wgrad(a->N, a->H, a->W, a->Cin, a->Cout, a->ksize, &pl, a->kstep, a->stages, a->splits) == 0,
                    "conv_wgrad: unsupported shape N=%d H=%d W=%d Cin=%d Cout=%d k=%d", a->N, a->H, a->W, a->Cin,
                    a->Cout, a->ksize);
     B200LP_REQUIRE(a->N % pl.pn == 0, "conv_wgrad: N=%d must be a multiple of %d for %dx%d planes", a->N, pl.pn,
@@ -277,6 +299,9 @@ extern "C" int32_t b200lp_conv_wgrad(const b200lp_wgrad_args* a, void* stream) {
     p.N = a->N; p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.Cout = a->Cout;
     p.ksize = a->ksize;
     p.pw = pl.pw; p.ph = pl.ph; p.pn = pl.pn;
+    p.kstep = pl.kstep;
+    p.blk_bytes = pl.kstep * 128;
+    p.stages = pl.stages;
     p.steps_w = a->W / pl.pw;
     p.steps_h = a->H / pl.ph;
     p.total_steps = pl.total_steps;

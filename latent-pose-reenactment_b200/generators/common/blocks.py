@@ -54,6 +54,7 @@ class SpectralNormed(nn.Module):
         v = torch.randn(fan_in)
         self.register_buffer("weight_u", u / u.norm().clamp_min(eps))
         self.register_buffer("weight_v", v / v.norm().clamp_min(eps))
+        self.pack_cache = ops.PackCache()   # tensor-core layouts of weight_orig, re-made when the weight changes
 
     def inv_sigma(self):
         w = self.weight_orig
@@ -72,13 +73,14 @@ class SpectralNormed(nn.Module):
         return (1.0 / sigma).reshape(1)
 
     def operands(self, detach=False):
-        """(weight_orig, 1/sigma, bias) as the kernels consume them.  `detach=True` cuts the parameter gradients
-        (used for the discriminator pass whose weight gradients the training step discards anyway); the power
-        iteration still runs."""
+        """(weight_orig, 1/sigma, bias, pack cache) as the kernels consume them.  `detach=True` cuts the parameter
+        gradients (used for the discriminator pass whose weight gradients the training step discards anyway); the
+        power iteration still runs."""
         s = self.inv_sigma()
         if detach:
-            return self.weight_orig.detach(), s.detach(), (self.bias.detach() if self.bias is not None else None)
-        return self.weight_orig, s, self.bias
+            return (self.weight_orig.detach(), s.detach(), (self.bias.detach() if self.bias is not None else None),
+                    self.pack_cache)
+        return self.weight_orig, s, self.bias, self.pack_cache
 
 
 class SNConv(SpectralNormed):
@@ -127,29 +129,30 @@ class AdaResBlock(nn.Module):
         precision 'tf32'  : adain_relu(tf32) -> conv -> adain_relu(tf32) -> conv(+skip), one TF32 MMA per K step;
         precision 'bf16x3': the same schedule with (hi, lo) bf16 operand planes and three MMAs per K step — generator
                             output within 1e-3 of the fp32 reference for O(1) AdaIN gains."""
-        w0, s0, _ = self.block.slot(self.i0).operands()
-        w1, s1, _ = self.block.slot(self.i1).operands()
+        w0, s0, _, c0 = self.block.slot(self.i0).operands()
+        w1, s1, _, c1 = self.block.slot(self.i1).operands()
         if precision == 'bf16x3':
-            y1 = ops.adain_conv(x, gamma0, beta0, w0, s0, upsample2=self.upsample)
+            y1 = ops.adain_conv(x, gamma0, beta0, w0, s0, upsample2=self.upsample, cache=c0)
             if self.skip is not None:
-                ws, ss, bs = self.skip.slot(1).operands()
-                s = ops.conv2d(x, ws, ss, bias=bs, ksize=1, x_split=x_split)
+                ws, ss, bs, cs = self.skip.slot(1).operands()
+                s = ops.conv2d(x, ws, ss, bias=bs, ksize=1, x_split=x_split, cache=cs)
                 mode = 2 if self.upsample else 1
             else:
                 s, mode = x, 1
             out = ops.adain_conv(y1, gamma1, beta1, w1, s1, residual=s, residual_mode=mode,
-                                 emit_split=feeds_skip_conv)
+                                 emit_split=feeds_skip_conv, cache=c1)
             return out if feeds_skip_conv else (out, None)
         a0 = ops.adain_relu(x, gamma0, beta0, upsample2=self.upsample)
-        y1 = ops.conv2d(a0, w0, s0, ksize=3)
+        y1 = ops.conv2d(a0, w0, s0, ksize=3, cache=c0)
         a1 = ops.adain_relu(y1, gamma1, beta1)
         if self.skip is not None:
-            ws, ss, bs = self.skip.slot(1).operands()
-            s = ops.conv2d(x, ws, ss, bias=bs, ksize=1)
+            ws, ss, bs, cs = self.skip.slot(1).operands()
+            s = ops.conv2d(x, ws, ss, bias=bs, ksize=1, cache=cs)
             mode = 2 if self.upsample else 1
         else:
             s, mode = x, 1
-        return ops.conv2d(a1, w1, s1, residual=s, residual_mode=mode, ksize=3, round_out=feeds_skip_conv), None
+        return ops.conv2d(a1, w1, s1, residual=s, residual_mode=mode, ksize=3, round_out=feeds_skip_conv,
+                          cache=c1), None
 
 
 class PlainResBlock(nn.Module):
@@ -174,16 +177,16 @@ class PlainResBlock(nn.Module):
 
     def forward(self, r, detach_params=False):
         """r = tf32(relu(block input)).  Returns the block output (pre-ReLU)."""
-        w0, s0, b0 = self.block.slot(2).operands(detach_params)
-        h = ops.conv2d(r, w0, s0, bias=b0, ksize=3, relu=True, round_out=True)
-        w1, s1, b1 = self.block.slot(5).operands(detach_params)
+        w0, s0, b0, c0 = self.block.slot(2).operands(detach_params)
+        h = ops.conv2d(r, w0, s0, bias=b0, ksize=3, relu=True, round_out=True, cache=c0)
+        w1, s1, b1, c1 = self.block.slot(5).operands(detach_params)
         if self.skip is not None:
-            ws, ss, bs = self.skip.slot(0).operands(detach_params)
+            ws, ss, bs, cs = self.skip.slot(0).operands(detach_params)
             rs = ops.avgpool2(r, None, round_out=True) if self.downsample else r
-            s = ops.conv2d(rs, ws, ss, bias=bs, ksize=1)
+            s = ops.conv2d(rs, ws, ss, bias=bs, ksize=1, cache=cs)
         else:
             s = r
         if self.downsample:
-            h2 = ops.conv2d(h, w1, s1, bias=b1, ksize=3)
+            h2 = ops.conv2d(h, w1, s1, bias=b1, ksize=3, cache=c1)
             return ops.avgpool2(h2, s)
-        return ops.conv2d(h, w1, s1, bias=b1, residual=s, residual_mode=1, ksize=3)
+        return ops.conv2d(h, w1, s1, bias=b1, residual=s, residual_mode=1, ksize=3, cache=c1)

@@ -415,7 +415,7 @@ def conv_tune():
             if Cout % bn:
                 continue
             for st in (2, 3, 4, 6, 8):
-                if st * (16384 + bn * 128) + 1024 > 227 * 1024:
+                if st * (16384 + bn * 128) + 1024 > 226 * 1024:
                     continue
                 fn = lambda: K.conv_fwd(x, wp, k, out=y, block_n=bn, stages=st)
                 for _ in range(2):
@@ -428,6 +428,42 @@ def conv_tune():
                 e1.record(); torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / 8
                 rec[f"bn{bn}_st{st}"] = round(flops / ms / 1e9, 0)
+        out.append(rec)
+    return out
+
+
+@check
+def wgrad_tune():
+    """Weight-gradient time vs (pixels per stage, ring depth, split-K)."""
+    import torch
+    from b200lp import kernels as K
+    out = []
+    shapes = [(8, 256, 256, 64, 64, 3), (8, 256, 256, 128, 64, 3), (8, 128, 128, 128, 128, 3), (8, 128, 128, 256, 128, 3),
+              (8, 64, 64, 256, 256, 3), (8, 64, 64, 512, 256, 3), (8, 32, 32, 512, 512, 3), (8, 16, 16, 512, 512, 3)]
+    for (N, H, W, Cin, Cout, k) in shapes:
+        x = torch.randn(N, H, W, Cin, device="cuda")
+        dy = torch.randn(N, H, W, Cout, device="cuda")
+        flops = 2.0 * N * H * W * Cin * Cout * k * k
+        rec = {"case": f"N{N} H{H} Cin{Cin} Cout{Cout}", "ok": True}
+        bn = 256 if Cout % 256 == 0 else (128 if Cout % 128 == 0 else 64)
+        for ks in (32, 64):
+            for st in (2, 3, 4, 6):
+                if st * (4 + bn // 32) * ks * 128 + 1024 > 226 * 1024:
+                    continue
+                for sp in (0, 16, 64):
+                    try:
+                        fn = lambda: K.conv_wgrad(x, dy, k, kstep=ks, stages=st, splits=sp)
+                        for _ in range(2):
+                            fn()
+                        torch.cuda.synchronize()
+                        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        for _ in range(6):
+                            fn()
+                        e1.record(); torch.cuda.synchronize()
+                        rec[f"ks{ks}_st{st}_sp{sp}"] = round(flops / (e0.elapsed_time(e1) / 6) / 1e9, 0)
+                    except Exception as err:
+                        rec[f"ks{ks}_st{st}_sp{sp}"] = str(err)[:60]
         out.append(rec)
     return out
 
