@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--workload", default="finetune", choices=list(WORKLOADS) + ["drive"])
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
 
@@ -358,18 +359,37 @@ def main():
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0][0].values()) + \
         sum(v.numel() * v.element_size() for v in host[0][1].values())
 
-    def step_resident(i):
+    def step_eager(i):
         d, t = dev_batches[i % n_batches]
         runner.train_step(tm, dict(d), dict(t), opt_G, opt_D, finetune=wl["finetune"])
+
+    graphed, graph_note = None, "off (--no-graph)"
+    if not args.no_graph:
+        try:
+            graphed = runner.GraphedTrainStep(tm, opt_G, opt_D, wl["finetune"], dev_batches[0][0], dev_batches[0][1])
+            graph_note = "whole step captured once, replayed per batch"
+        except Exception as err:      # keep measuring (eagerly) and say why
+            graph_note = f"capture failed, eager launches: {type(err).__name__}: {str(err)[:160]}"
+            torch.cuda.synchronize()
+
+    def step_resident(i):
+        d, t = dev_batches[i % n_batches]
+        if graphed is not None:
+            graphed(d, t)           # device->device copy into the graph's static inputs + replay
+        else:
+            runner.train_step(tm, dict(d), dict(t), opt_G, opt_D, finetune=wl["finetune"])
 
     n_losses = [0]
 
     def step_e2e(i):
         d, t = host[i % n_batches]
-        d, t = dict(d), dict(t)
-        U.dict_to_device(d, device)
-        U.dict_to_device(t, device)
-        _, lg, ld = runner.train_step(tm, d, t, opt_G, opt_D, finetune=wl["finetune"])
+        if graphed is not None:
+            _, lg, ld = graphed(d, t)          # pinned host -> static device inputs (H2D) + replay
+        else:
+            d, t = dict(d), dict(t)
+            U.dict_to_device(d, device)
+            U.dict_to_device(t, device)
+            _, lg, ld = runner.train_step(tm, d, t, opt_G, opt_D, finetune=wl["finetune"])
         vals = torch.stack([v.detach().float().reshape(()) for v in list(lg.values()) + list(ld.values())])
         n_losses[0] = vals.numel()
         return vals.cpu()           # device -> host read of the step's result (the runner's Meter does the same)
@@ -397,7 +417,7 @@ def main():
         pk = ROOT / "MEASURED_PEAKS.json"
         if pk.exists():
             peaks = json.loads(pk.read_text())
-        extra.update(roofline_pass(step_resident, peaks))
+        extra.update(roofline_pass(step_eager, peaks))
         extra["peaks_source"] = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
     if rank == 0 and world == 1:
         try:
@@ -423,7 +443,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": wl["desc"], "global_batch": B * world, "per_gpu_batch": B, "image_size": 256,
                            "parallelism": f"dp{world}", "weights": "random init, spectral norm converged",
-                           "l2": "per-step working set (activations, ~GBs) >> 126 MB L2; 4 distinct input batches cycled"},
+                           "l2": "per-step working set (activations, ~GBs) >> 126 MB L2; 4 distinct input batches cycled",
+                           "cuda_graph": graph_note},
                 "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 4 * n_losses[0], "ms_per_step": round(ms_e2e / args.steps, 3)},
                 "gpu_launches": int(launches), "clocks": clocks}

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 7
+#define B200LP_ABI_VERSION 8
 
 #define B200LP_OK 0
 #define B200LP_EINVAL (-1)   /* bad shape / unsupported configuration */
@@ -83,6 +83,40 @@ int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream);
  */
 int32_t b200lp_pack_conv_weight(const float* w_oihw, const float* scale, void* wp, int32_t Cout, int32_t Cin,
                                 int32_t ksize, int32_t transpose, int32_t precision, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Spectral normalisation, batched over all weights of a network pass (3 launches instead of ~14 per weight).
+ * Replaces torch.nn.utils.spectral_norm's SpectralNorm.compute_weight (one power iteration per forward call in
+ * training mode; call sites generators/common/blocks.py:78-100, discriminators/no_landmarks.py:54-66):
+ *   training: v <- normalize(W^T u), u <- normalize(W v), sigma = u^T W v   (u, v updated in place)
+ *   eval:     sigma = u^T W v with the stored u, v
+ * Writes 1/sigma (consumed by b200lp_conv_fwd as `out_scale`) and, if snap_u / snap_v are given, a copy of the
+ * vectors this sigma was computed with (the backward pass needs them after later passes overwrote the buffers).
+ * `scratch` must hold b200lp_sn_scratch_floats(rows, cols) floats per item.  count <= b200lp_sn_max_tensors().
+ */
+typedef struct {
+    const float* w;      /* weight_orig viewed as [rows = Cout][cols = Cin*k*k]        */
+    float* u;            /* weight_u [rows]                                            */
+    float* v;            /* weight_v [cols]                                            */
+    float* snap_u;       /* [rows] or NULL                                             */
+    float* snap_v;       /* [cols] or NULL                                             */
+    float* scratch;      /* b200lp_sn_scratch_floats(rows, cols) floats                */
+    float* inv_sigma;    /* [1] out                                                    */
+    int32_t rows, cols;
+    float eps;           /* torch's normalize eps (1e-4 on the hot path)               */
+    int32_t reserved;
+} b200lp_sn_item;
+
+int32_t b200lp_sn_max_tensors(void);
+int64_t b200lp_sn_scratch_floats(int32_t rows, int32_t cols);
+int32_t b200lp_sn_sigma_multi(const b200lp_sn_item* items /* host array */, int32_t count, int32_t training,
+                              void* stream);
+/* Spectral-norm correction of a weight gradient (autograd through `weight_orig / sigma`):
+ *   dw = s*g - s^2 <g, w> u v^T,  s = *inv_sigma, g = gradient w.r.t. the normalised weight (b200lp_conv_wgrad output),
+ *   all [rows][cols].  workspace: b200lp_sn_wgrad_fix_workspace(rows*cols) bytes. */
+int64_t b200lp_sn_wgrad_fix_workspace(int64_t n);
+int32_t b200lp_sn_wgrad_fix(const float* g, const float* w, const float* inv_sigma, const float* u, const float* v,
+                            float* dw, float* workspace, int32_t rows, int32_t cols, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Weight gradient of the same convolutions on tcgen05 (torch autograd's conv backward-filter).
@@ -184,6 +218,25 @@ int32_t b200lp_gen_tail_bwd_data(const float* da, const float* w_oihw, const flo
                                  int32_t N, int32_t H, int32_t W, int32_t Cin, void* stream);
 int32_t b200lp_gen_tail_bwd_weight(const float* x_nhwc, const float* da, float* dw_oihw, float* dbias, int32_t N,
                                    int32_t H, int32_t W, int32_t Cin, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused multi-tensor optimizer step + weight running average (HBM-bound; graph-capturable: the step counter and the
+ * step-dependent scalars live on the device).  Replaces torch.optim.Adam.step / the vendored RAdam.step
+ * (utils/radam.py:29-95; runners/holycow.py:244,252) and TrainingModule.update_running_average's parameter loop
+ * (runners/holycow.py:99-105).
+ *   table_dev        : device array of {float* p; const float* g; float* m; float* v; float* ema (or NULL); int64 n}
+ *   chunk_tensor_dev / chunk_off_dev : work list, chunk i covers table[chunk_tensor[i]] elements
+ *                      [chunk_off[i], chunk_off[i] + chunk_elems)
+ *   state_dev        : 4 floats {step, step_size, rectified flag, 1/sqrt(bias_correction2)}; step advances by 1 per call
+ *   mode 0 = torch.optim.Adam semantics, 1 = RAdam (utils/radam.py) semantics;  ema = ema*ema_alpha + p*(1-ema_alpha)
+ */
+int32_t b200lp_adam_ema_multi(const void* table_dev, const int32_t* chunk_tensor_dev, const int64_t* chunk_off_dev,
+                              int32_t n_chunks, int64_t chunk_elems, float* state_dev, float lr, float beta1,
+                              float beta2, float eps, float ema_alpha, int32_t mode, int32_t degenerated_to_sgd,
+                              void* stream);
+/* ema = ema*ema_alpha + p*(1-ema_alpha) over the same kind of table (entries with ema == NULL are skipped) */
+int32_t b200lp_ema_multi(const void* table_dev, const int32_t* chunk_tensor_dev, const int64_t* chunk_off_dev,
+                         int32_t n_chunks, int64_t chunk_elems, float ema_alpha, void* stream);
 
 /* per-channel sum over pixels (bias gradients): db[c] = scale * sum_{n,h,w} dy[n,h,w,c] */
 int32_t b200lp_bias_grad(const float* dy, float* db, int64_t pixels, int32_t C, void* stream);

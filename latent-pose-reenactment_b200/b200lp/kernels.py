@@ -322,3 +322,48 @@ def bias_grad(dy):
     with _timed("elementwise", nbytes=4.0 * dy.numel()):
         L.check(lib.b200lp_bias_grad(L.ptr(dy), L.ptr(db), dy.numel() // c, c, L.stream_ptr()), "bias_grad")
     return db
+
+
+def sn_sigma_multi(layers, training):
+    """Batched spectral-norm pass over `layers` = list of (weight_orig, weight_u, weight_v, eps, scratch) with
+    weight viewed as [rows][cols].  Returns (inv_sigma (T,), [(snap_u, snap_v)]) — one launch triple for all of them."""
+    lib = L.load()
+    dev = layers[0][0].device
+    total = sum(w.shape[0] + w[0].numel() for w, *_ in layers)
+    snap = torch.empty(total, dtype=torch.float32, device=dev)
+    inv = torch.empty(len(layers), dtype=torch.float32, device=dev)
+    items = (L.SnItem * len(layers))()
+    snaps = []
+    off = 0
+    for i, (w, u, v, eps, scratch) in enumerate(layers):
+        rows, cols = w.shape[0], w[0].numel()
+        su, sv = snap[off:off + rows], snap[off + rows:off + rows + cols]
+        off += rows + cols
+        it = items[i]
+        it.w, it.u, it.v = w.data_ptr(), u.data_ptr(), v.data_ptr()
+        it.snap_u, it.snap_v = su.data_ptr(), sv.data_ptr()
+        it.scratch = scratch.data_ptr()
+        it.inv_sigma = inv.data_ptr() + 4 * i
+        it.rows, it.cols, it.eps = rows, cols, eps
+        snaps.append((su, sv))
+    with _timed("spectral_norm", nbytes=8.0 * sum(w.numel() for w, *_ in layers)):
+        L.check(lib.b200lp_sn_sigma_multi(items, len(layers), int(training), L.stream_ptr()), "sn_sigma_multi")
+    return inv, snaps
+
+
+def sn_scratch(w):
+    lib = L.load()
+    n = lib.b200lp_sn_scratch_floats(w.shape[0], w[0].numel())
+    return torch.empty(n, dtype=torch.float32, device=w.device)
+
+
+def sn_wgrad_fix(g, w, inv_sigma, u, v):
+    """dw = s*g - s^2 <g,w> u v^T (all tensors shaped like w)."""
+    lib = L.load()
+    rows, cols = w.shape[0], w[0].numel()
+    ws = _ws(lib.b200lp_sn_wgrad_fix_workspace(w.numel()), w.device)
+    dw = torch.empty_like(w)
+    with _timed("spectral_norm", nbytes=16.0 * w.numel()):
+        L.check(lib.b200lp_sn_wgrad_fix(L.ptr(g), L.ptr(w.detach().contiguous()), L.ptr(inv_sigma), L.ptr(u), L.ptr(v),
+                                        L.ptr(dw), L.ptr(ws), rows, cols, L.stream_ptr()), "sn_wgrad_fix")
+    return dw

@@ -13,7 +13,7 @@ import torch
 
 _PKG = Path(__file__).resolve().parent.parent
 LIB_PATH = _PKG / "lib" / "libb200lp.so"
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class B200lpError(RuntimeError):
@@ -40,6 +40,14 @@ class WgradArgs(Structure):
     ]
 
 
+class SnItem(Structure):
+    _fields_ = [
+        ("w", c_void_p), ("u", c_void_p), ("v", c_void_p), ("snap_u", c_void_p), ("snap_v", c_void_p),
+        ("scratch", c_void_p), ("inv_sigma", c_void_p),
+        ("rows", c_int32), ("cols", c_int32), ("eps", c_float), ("reserved", c_int32),
+    ]
+
+
 _P = c_void_p
 _I = c_int32
 _L = c_int64
@@ -53,6 +61,11 @@ SIGNATURES = {
     "b200lp_launch_count": (_L, []),
     "b200lp_conv_fwd": (_I, [POINTER(ConvArgs), _P]),
     "b200lp_pack_conv_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200lp_sn_max_tensors": (_I, []),
+    "b200lp_sn_scratch_floats": (_L, [_I, _I]),
+    "b200lp_sn_sigma_multi": (_I, [POINTER(SnItem), _I, _I, _P]),
+    "b200lp_sn_wgrad_fix_workspace": (_L, [_L]),
+    "b200lp_sn_wgrad_fix": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "b200lp_conv_wgrad_workspace": (_L, [_I, _I, _I, _I, _I, _I]),
     "b200lp_conv_wgrad": (_I, [POINTER(WgradArgs), _P]),
     "b200lp_in_stats_workspace": (_L, [_I, _I, _I]),
@@ -77,9 +90,12 @@ SIGNATURES = {
     "b200lp_gen_tail_bwd_data": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200lp_gen_tail_bwd_weight": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200lp_bias_grad": (_I, [_P, _P, _L, _I, _P]),
+    "b200lp_adam_ema_multi": (_I, [_P, _P, _P, _I, _L, _P, _F, _F, _F, _F, _F, _I, _I, _P]),
+    "b200lp_ema_multi": (_I, [_P, _P, _P, _I, _L, _F, _P]),
 }
 
 _lib = None
+c_void_p = c_void_p   # re-exported for callers that pass raw pointers
 
 
 def load(build_if_missing=True):
@@ -135,11 +151,19 @@ def ptr(t, dtype=torch.float32):
     return c_void_p(t.data_ptr())
 
 
+_device_ok = {}
+
+
 def require_device():
-    """Fail loudly unless a CUDA device of compute capability 10.x is current."""
+    """Fail loudly unless a CUDA device of compute capability 10.x is current (checked once per device: the query is
+    not something to repeat inside a CUDA-graph capture)."""
     if not torch.cuda.is_available():
         raise B200lpError("no CUDA device: the b200lp hot path has no CPU fallback")
-    cc = load().b200lp_device_cc()
-    if cc < 100 or cc >= 110:
-        raise B200lpError(f"device compute capability {cc} is not sm_100 (B200): kernels are sm_100a-only")
+    dev = torch.cuda.current_device()
+    cc = _device_ok.get(dev)
+    if cc is None:
+        cc = load().b200lp_device_cc()
+        if cc < 100 or cc >= 110:
+            raise B200lpError(f"device compute capability {cc} is not sm_100 (B200): kernels are sm_100a-only")
+        _device_ok[dev] = cc
     return cc

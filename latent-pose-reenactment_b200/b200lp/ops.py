@@ -13,11 +13,20 @@ def _dot(a, b):
     return (a * b).sum()
 
 
+_GENERATION = [0]
+
+
+def bump_generation():
+    """Call after weights were modified through raw pointers (fused optimizer / EMA kernels, CUDA-graph replays):
+    those writes do not touch torch's per-tensor version counters, so every cached packed copy is invalidated here."""
+    _GENERATION[0] += 1
+
+
 class PackCache:
     """Packed (tensor-core layout) copies of one weight, keyed by (transpose, precision) and validated by the weight
-    tensor's autograd version counter: optimizer / EMA / load_state_dict updates are in-place and bump it, so a weight
-    is re-packed once per update instead of once per forward call (the three discriminator passes of a step and the
-    backward passes share the copies).  Lives on the owning module; deep copies start empty."""
+    tensor's autograd version counter plus a global generation (see bump_generation): a weight is re-packed once per
+    update instead of once per forward call (the three discriminator passes of a step and the backward passes share
+    the copies).  Lives on the owning module; deep copies start empty."""
 
     def __init__(self):
         self.entries = {}
@@ -28,11 +37,11 @@ class PackCache:
     def get(self, weight, transpose, precision):
         key = (transpose, precision)
         hit = self.entries.get(key)
-        ver = weight._version
-        if hit is not None and hit[0] == ver and hit[1] == weight.data_ptr():
-            return hit[2]
+        stamp = (_GENERATION[0], weight._version, weight.data_ptr())
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
         packed = K.pack_conv_weight(weight.detach(), None, transpose=transpose, precision=precision)
-        self.entries[key] = (ver, weight.data_ptr(), packed)
+        self.entries[key] = (stamp, packed)
         return packed
 
 
@@ -42,16 +51,20 @@ def _packed(weight, cache, transpose, precision=K.TF32):
     return K.pack_conv_weight(weight.detach(), None, transpose=transpose, precision=precision)
 
 
-def _conv_backward(ctx_ksize, x_f32, weight_orig, inv_sigma, dy, need_x, need_w, need_s, cache=None):
+def _conv_backward(ctx_ksize, x_f32, weight_orig, inv_sigma, dy, need_x, need_w, need_s, cache=None, sn=None):
     """Shared backward of the tensor-core convolutions (TF32 data / weight gradient kernels).
-    y = s * conv(x, W):  dx = s * conv_T(dy, W);  dW = s * wgrad(x, dy);  ds = <wgrad(x, dy), W>."""
+    y = s * conv(x, W):  dx = s * conv_T(dy, W);  dW = s * wgrad(x, dy);  ds = <wgrad(x, dy), W>.
+    `sn` = (u, v) snapshots of the spectral-norm vectors behind s = 1/sigma: then s carries no autograd edge and the
+    full gradient  dW = s*G - s^2 <G, W> u v^T   is produced here by one fused kernel pair."""
     dx = dw = ds = None
     if need_x:
         wpt = _packed(weight_orig, cache, True)
         dx = K.conv_fwd(dy, wpt, ctx_ksize, scale=inv_sigma)
-    if need_w or (need_s and inv_sigma is not None):
+    if need_w or (need_s and inv_sigma is not None and sn is None):
         g = K.conv_wgrad(x_f32, dy, ctx_ksize)
-        if inv_sigma is not None:
+        if sn is not None:
+            dw = K.sn_wgrad_fix(g, weight_orig, inv_sigma, sn[0], sn[1])
+        elif inv_sigma is not None:
             if need_s:
                 ds = _dot(g, weight_orig).reshape(inv_sigma.shape)
             if need_w:
@@ -72,7 +85,7 @@ class Conv2dFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight_orig, inv_sigma, bias, residual, ksize, residual_mode, relu, round_out, x_split,
-                emit_split, cache):
+                emit_split, cache, sn):
         """`x_split` (optional, non-differentiable): the (hi, lo) bf16 planes of x — when given, the forward runs in
         bf16x3 precision on them; gradients still flow to `x`.  `emit_split`: also return the (hi, lo) planes of y."""
         if x_split is not None:
@@ -85,7 +98,7 @@ class Conv2dFn(torch.autograd.Function):
                          round_tf32=round_out, emit_split=emit_split, scale=inv_sigma)
         y, y_split = out if emit_split else (out, None)
         ctx.ksize, ctx.residual_mode, ctx.relu = ksize, residual_mode, relu
-        ctx.cache = cache
+        ctx.cache, ctx.sn = cache, sn
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, weight_orig, inv_sigma, y if relu else None)
@@ -101,21 +114,21 @@ class Conv2dFn(torch.autograd.Function):
         if ctx.relu:
             dy = K.relu_bwd(y, dy)
         need_x, need_w, need_s, need_b, need_r = ctx.needs_input_grad[:5]
-        dx, dw, ds = _conv_backward(ctx.ksize, x, weight_orig, inv_sigma, dy, need_x, need_w, need_s, ctx.cache)
+        dx, dw, ds = _conv_backward(ctx.ksize, x, weight_orig, inv_sigma, dy, need_x, need_w, need_s, ctx.cache, ctx.sn)
         db = dr = None
         if ctx.has_bias and need_b:
             db = K.bias_grad(dy)
         if ctx.has_res and need_r:
             dr = dy if ctx.residual_mode == 1 else K.upsample2_bwd(dy)
-        return dx, dw, ds, db, dr, None, None, None, None, None, None, None
+        return dx, dw, ds, db, dr, None, None, None, None, None, None, None, None
 
 
 def conv2d(x, weight_orig, inv_sigma=None, bias=None, residual=None, ksize=3, residual_mode=0, relu=False,
-           round_out=False, x_split=None, emit_split=False, cache=None):
+           round_out=False, x_split=None, emit_split=False, cache=None, sn=None):
     if residual is None:
         residual_mode = 0
     return Conv2dFn.apply(x, weight_orig, inv_sigma, bias, residual, ksize, residual_mode, relu, round_out, x_split,
-                          emit_split, cache)
+                          emit_split, cache, sn)
 
 
 class AdaINConvFn(torch.autograd.Function):
@@ -128,7 +141,7 @@ class AdaINConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, weight_orig, inv_sigma, residual, eps, upsample2, residual_mode, emit_split,
-                cache):
+                cache, sn):
         mean, rstd = K.in_stats(x, eps)
         need_bwd = any(ctx.needs_input_grad)      # False under torch.no_grad() (drive.py, EMA forward)
         if need_bwd:
@@ -142,7 +155,7 @@ class AdaINConvFn(torch.autograd.Function):
                          scale=inv_sigma)
         y, y_split = out if emit_split else (out, None)
         ctx.upsample2, ctx.residual_mode = upsample2, residual_mode
-        ctx.cache = cache
+        ctx.cache, ctx.sn = cache, sn
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, mean, rstd, gamma, beta, weight_orig, inv_sigma, a_f32)
         if emit_split:
@@ -156,22 +169,22 @@ class AdaINConvFn(torch.autograd.Function):
         dy = dy.contiguous()
         need_x, need_g, need_b, need_w, need_s, need_r = ctx.needs_input_grad[:6]
         da, dw, ds = _conv_backward(3, a_f32, weight_orig, inv_sigma, dy, need_x or need_g or need_b, need_w, need_s,
-                                    ctx.cache)
+                                    ctx.cache, ctx.sn)
         dx = dgm = dbt = None
         if da is not None:
             dx, dgm, dbt = K.adain_relu_bwd(x, mean, rstd, gamma, beta, da, upsample2=ctx.upsample2)
         dr = None
         if ctx.has_res and need_r:
             dr = dy if ctx.residual_mode == 1 else K.upsample2_bwd(dy)
-        return dx, dgm, dbt, dw, ds, dr, None, None, None, None, None
+        return dx, dgm, dbt, dw, ds, dr, None, None, None, None, None, None
 
 
 def adain_conv(x, gamma, beta, weight_orig, inv_sigma, residual=None, residual_mode=0, eps=1e-4, upsample2=False,
-               emit_split=False, cache=None):
+               emit_split=False, cache=None, sn=None):
     if residual is None:
         residual_mode = 0
     return AdaINConvFn.apply(x, gamma, beta, weight_orig, inv_sigma, residual, eps, upsample2, residual_mode,
-                             emit_split, cache)
+                             emit_split, cache, sn)
 
 
 class AdaINReLUFn(torch.autograd.Function):

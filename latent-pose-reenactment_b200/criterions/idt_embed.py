@@ -22,6 +22,7 @@ class Criterion(torch.nn.Module):
     def __init__(self, idt_embed_weight, vgg_weights_dir):
         super().__init__()
         self.idt_embed_crit = PerceptualLoss(idt_embed_weight, vgg_weights_dir, net='face').eval()
+        self._center_grid = {}      # (batch, H, W, device) -> sampling grid of the constant centre crop
 
     def forward(self, data_dict):
         fake_rgb = data_dict['fake_rgbs']
@@ -36,32 +37,47 @@ class Criterion(torch.nn.Module):
             h, w = real_rgb.shape[2:]
             bboxes[:, 0:2] *= h
             bboxes[:, 2:4] *= w
+            fake_cropped = crop_and_resize(fake_rgb, bboxes)
+            real_cropped = crop_and_resize(real_rgb, bboxes)
         else:
-            crop_factor = 1 / 1.8
-            h, w = real_rgb.shape[2:]
-            t = h * (1 - crop_factor) / 2
-            l = w * (1 - crop_factor) / 2
-            bboxes = torch.tensor([[t, h - t, l, w - l]], dtype=torch.float32, device=real_rgb.device)
-            bboxes = bboxes.expand(len(real_rgb), 4)
-
-        fake_cropped = crop_and_resize(fake_rgb, bboxes)
-        real_cropped = crop_and_resize(real_rgb, bboxes)
+            # the centre crop (factor 1/1.8) is the same for every batch: build its sampling grid once
+            # (host->device tensor construction is not something to repeat per step, nor capturable in a CUDA graph)
+            key = (len(real_rgb),) + tuple(real_rgb.shape[2:]) + (str(real_rgb.device),)
+            grid = self._center_grid.get(key)
+            if grid is None:
+                crop_factor = 1 / 1.8
+                h, w = real_rgb.shape[2:]
+                t = h * (1 - crop_factor) / 2
+                l = w * (1 - crop_factor) / 2
+                bboxes = torch.tensor([[t, h - t, l, w - l]], dtype=torch.float32, device=real_rgb.device)
+                grid = sampling_grid(bboxes.expand(len(real_rgb), 4), real_rgb.shape)
+                self._center_grid[key] = grid
+            fake_cropped = sample(fake_rgb, grid)
+            real_cropped = sample(real_rgb, grid)
         return {'VGGFace': self.idt_embed_crit(fake_cropped, real_cropped)}
 
 
-def crop_and_resize(images, bboxes, target_size=None):
-    """images B x C x H x W; bboxes B x 4 = [t, b, l, r] in pixels -> crops resized to `target_size` (default H x W)."""
+def sampling_grid(bboxes, image_shape, target_size=None):
+    """bboxes B x 4 = [t, b, l, r] in pixels -> affine sampling grid (B, h, w, 2) for images of `image_shape`."""
     t, b, l, r = bboxes.t().float()
-    batch_size, num_channels, h, w = images.shape
-    theta = torch.zeros(batch_size, 2, 3, dtype=torch.float32, device=images.device)
+    batch_size, num_channels, h, w = image_shape
+    theta = torch.zeros(batch_size, 2, 3, dtype=torch.float32, device=bboxes.device)
     theta[:, 0, 0] = (r - l) / w
     theta[:, 1, 1] = (b - t) / h
     theta[:, 0, 2] = (l + r) / w - 1
     theta[:, 1, 2] = (t + b) / h - 1
-    grid = torch.nn.functional.affine_grid(theta, (batch_size, num_channels) + (target_size or (h, w)),
+    return torch.nn.functional.affine_grid(theta, (batch_size, num_channels) + tuple(target_size or (h, w)),
                                            align_corners=False)
+
+
+def sample(images, grid):
     return torch.nn.functional.grid_sample(images, grid, mode='bilinear', padding_mode='reflection',
                                            align_corners=False)
+
+
+def crop_and_resize(images, bboxes, target_size=None):
+    """images B x C x H x W; bboxes B x 4 = [t, b, l, r] in pixels -> crops resized to `target_size` (default H x W)."""
+    return sample(images, sampling_grid(bboxes, images.shape, target_size))
 
 
 def compute_bboxes_from_keypoints(keypoints):

@@ -381,34 +381,44 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
 
 // ------------------------------------------------------------------------------------------------ weight packing
 namespace b200lp {
+// One block = a 32 (co) x 32 (ci) x taps tile: reads are runs of 32*taps contiguous floats per co (OIHW), writes are
+// 128-byte runs along ci (forward layout) or along co (transposed layout); the transposition happens in shared memory.
 template <bool SPLIT>
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                        float* __restrict__ wp, int Cout, int Cin, int taps, int transpose) {
+__global__ void __launch_bounds__(256)
+pack_conv_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale, float* __restrict__ wp,
+                        int Cout, int Cin, int taps, int transpose) {
+    __shared__ float tile[32][32 * 9 + 1];
     const float s = scale ? __ldg(scale) : 1.0f;
+    const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+    const int run = 32 * taps;                       // contiguous floats per co inside this tile
+    for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
+        const int co = i / run, r = i - co * run;    // r = ci_local * taps + tap
+        float v = 0.f;
+        if (co0 + co < Cout && ci0 + r / taps < Cin)
+            v = __ldg(w + (static_cast<long>(co0 + co) * Cin + ci0) * taps + r);
+        tile[co][r] = v * s;
+    }
+    __syncthreads();
     const long total = static_cast<long>(Cout) * Cin * taps;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long>(gridDim.x) * blockDim.x) {
-        // i indexes the packed destination so that writes are coalesced
-        float v;
-        if (!transpose) {
-            const int ci = i % Cin;
-            const int tap = (i / Cin) % taps;
-            const int co = i / (static_cast<long>(Cin) * taps);
-            v = w[(static_cast<long>(co) * Cin + ci) * taps + tap];
-        } else {
-            const int co = i % Cout;
-            const int tapf = (i / Cout) % taps;
-            const int ci = i / (static_cast<long>(Cout) * taps);
-            v = w[(static_cast<long>(co) * Cin + ci) * taps + (taps - 1 - tapf)];
+    for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
+        int co, ci, tap;
+        long dst;
+        if (!transpose) {                            // dst [co][tap][ci]: ci fastest
+            ci = i % 32; tap = (i / 32) % taps; co = i / (32 * taps);
+            dst = (static_cast<long>(co0 + co) * taps + tap) * Cin + ci0 + ci;
+        } else {                                     // dst [ci][taps-1-tap][co]: co fastest
+            co = i % 32; tap = (i / 32) % taps; ci = i / (32 * taps);
+            dst = (static_cast<long>(ci0 + ci) * taps + (taps - 1 - tap)) * Cout + co0 + co;
         }
+        if (co0 + co >= Cout || ci0 + ci >= Cin) continue;
+        const float f = tile[co][ci * taps + tap];
         if (!SPLIT) {
-            wp[i] = round_tf32(v * s);
-        } else {   // (hi, lo) bf16 planes: hi + lo == v*s to 2^-17
+            wp[dst] = round_tf32(f);
+        } else {                                     // (hi, lo) bf16 planes: hi + lo == f to 2^-17
             __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(wp);
-            const float f = v * s;
             const __nv_bfloat16 h = __float2bfloat16_rn(f);
-            out[i] = h;
-            out[total + i] = __float2bfloat16_rn(f - __bfloat162float(h));
+            out[dst] = h;
+            out[total + dst] = __float2bfloat16_rn(f - __bfloat162float(h));
         }
     }
 }
@@ -419,16 +429,13 @@ extern "C" int32_t b200lp_pack_conv_weight(const float* w_oihw, const float* sca
                                            void* stream) {
     float* wp = static_cast<float*>(wp_out);
     B200LP_REQUIRE(w_oihw && wp && Cout > 0 && Cin > 0 && (ksize == 1 || ksize == 3), "pack_conv_weight: bad args");
-    const long total = static_cast<long>(Cout) * Cin * ksize * ksize;
-    const int threads = 256;
-    long blocks = (total + threads - 1) / threads;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    dim3 grid((Cin + 31) / 32, (Cout + 31) / 32);
     if (precision == 0)
-        pack_conv_weight_kernel<false><<<(int)blocks, threads, 0, as_stream(stream)>>>(w_oihw, scale, wp, Cout, Cin,
-                                                                                     ksize * ksize, transpose);
+        pack_conv_weight_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(w_oihw, scale, wp, Cout, Cin, ksize * ksize,
+                                                                            transpose);
     else
-        pack_conv_weight_kernel<true><<<(int)blocks, threads, 0, as_stream(stream)>>>(w_oihw, scale, wp, Cout, Cin,
-                                                                                    ksize * ksize, transpose);
+        pack_conv_weight_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(w_oihw, scale, wp, Cout, Cin, ksize * ksize,
+                                                                           transpose);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

@@ -36,7 +36,8 @@ class Wrapper:
 
     @staticmethod
     def get_optimizer(discriminator, args):
-        Optimizer = torch.optim.__dict__[args.optimizer]
+        from runners.holycow import optimizer_class      # Adam / RAdam, fused multi-tensor kernel on CUDA
+        Optimizer = optimizer_class(args.optimizer, args.device)
         return Optimizer(discriminator.parameters(), lr=args.lr_dis, betas=(args.beta1, 0.999), eps=1e-5)
 
 
@@ -94,10 +95,11 @@ class Discriminator(nn.Module):
         """input: (B,3,S,S) NCHW image.  Returns (score (B,), [7 feature maps])  — reference :90-108.
         `detach_params`: run this pass on detached weights (no weight gradients; see `skip_discarded_wgrad`)."""
         x = input.contiguous()
+        blocks.spectral_sigmas(self._tensor_core_convs())      # one batched power iteration for the 20 MMA convs
         w0, s0, b0, _ = self.down_block.slot(0).operands(detach_params)
         h = ops.conv_c3(x, w0, s0, b0, relu=True, round_out=True)
-        w2, s2, b2, c2 = self.down_block.slot(2).operands(detach_params)
-        h2 = ops.conv2d(h, w2, s2, bias=b2, ksize=3, cache=c2)
+        w2, s2, b2, e2 = self.down_block.slot(2).operands(detach_params)
+        h2 = ops.conv2d(h, w2, s2, bias=b2, ksize=3, **e2)
         # skip: AvgPool2(conv1x1(x)) == conv1x1(AvgPool2(x)); the 1x1 weights ride the centre tap of the 3x3 stem kernel
         ws, ss, bs, _ = self.skip.slot(0).operands(detach_params)
         xs = torch.nn.functional.avg_pool2d(x, 2)
@@ -115,6 +117,13 @@ class Discriminator(nn.Module):
         out_linear = (torch.nn.functional.linear(o, wl) * sl + bl)[:, 0]
         score = (o * embed).sum(1) + out_linear if embed is not None else out_linear
         return score, [f.permute(0, 3, 1, 2) for f in feats]
+
+    def _tensor_core_convs(self):
+        """The spectral-normalised convs that run on the tensor cores (everything except the two Cin=3 stem convs)."""
+        convs = [self.down_block.slot(2)]
+        for block in self.blocks:
+            convs += block.tensor_core_convs()
+        return convs
 
     def enable_finetuning(self, data_dict=None):
         """Reference :110-136: the embedding matrix W is replaced by one row initialised from `embeds`."""

@@ -55,6 +55,8 @@ class SpectralNormed(nn.Module):
         self.register_buffer("weight_u", u / u.norm().clamp_min(eps))
         self.register_buffer("weight_v", v / v.norm().clamp_min(eps))
         self.pack_cache = ops.PackCache()   # tensor-core layouts of weight_orig, re-made when the weight changes
+        self._sn_scratch = None             # device scratch of the batched power iteration (lazily allocated)
+        self._pre = None                    # (1/sigma, (u, v) snapshots) deposited by spectral_sigmas() for the next use
 
     def inv_sigma(self):
         w = self.weight_orig
@@ -73,14 +75,45 @@ class SpectralNormed(nn.Module):
         return (1.0 / sigma).reshape(1)
 
     def operands(self, detach=False):
-        """(weight_orig, 1/sigma, bias, pack cache) as the kernels consume them.  `detach=True` cuts the parameter
-        gradients (used for the discriminator pass whose weight gradients the training step discards anyway); the
-        power iteration still runs."""
-        s = self.inv_sigma()
+        """(weight_orig, 1/sigma, bias, extras) as the kernels consume them; extras = dict(cache=PackCache, sn=(u, v) or
+        None).  If spectral_sigmas() deposited a batched result for this layer it is consumed here (sigma then has no
+        autograd edge; the rank-1 gradient term is applied by the kernel using the (u, v) snapshots); otherwise the
+        per-layer autograd path `inv_sigma()` is used.  `detach=True` cuts the parameter gradients (the discriminator
+        pass whose weight gradients the training step discards anyway); the power iteration still runs."""
+        if self._pre is not None:
+            s, sn = self._pre
+            self._pre = None
+        else:
+            s, sn = self.inv_sigma(), None
+        extras = dict(cache=self.pack_cache, sn=sn)
         if detach:
             return (self.weight_orig.detach(), s.detach(), (self.bias.detach() if self.bias is not None else None),
-                    self.pack_cache)
-        return self.weight_orig, s, self.bias, self.pack_cache
+                    extras)
+        return self.weight_orig, s, self.bias, extras
+
+
+def spectral_sigmas(layers):
+    """One batched spectral-norm pass (3 kernel launches) for a list of SpectralNormed conv layers: power iteration in
+    training mode (buffers updated in place), 1/sigma and (u, v) snapshots deposited on each layer for its next
+    `operands()` call.  Replaces len(layers) x ~14 tiny launches of torch's spectral_norm hooks per network pass."""
+    from b200lp import kernels as K
+    from b200lp import lib as L
+    if not layers:
+        return
+    max_t = L.load().b200lp_sn_max_tensors()
+    training = layers[0].training
+    with torch.no_grad():
+        for i in range(0, len(layers), max_t):
+            chunk = layers[i:i + max_t]
+            packed = []
+            for m in chunk:
+                w = m.weight_orig
+                if m._sn_scratch is None or m._sn_scratch.device != w.device:
+                    m._sn_scratch = K.sn_scratch(w)
+                packed.append((w.detach(), m.weight_u, m.weight_v, float(m.eps), m._sn_scratch))
+            inv, snaps = K.sn_sigma_multi(packed, training)
+            for j, m in enumerate(chunk):
+                m._pre = (inv[j:j + 1], snaps[j])
 
 
 class SNConv(SpectralNormed):
@@ -129,30 +162,33 @@ class AdaResBlock(nn.Module):
         precision 'tf32'  : adain_relu(tf32) -> conv -> adain_relu(tf32) -> conv(+skip), one TF32 MMA per K step;
         precision 'bf16x3': the same schedule with (hi, lo) bf16 operand planes and three MMAs per K step — generator
                             output within 1e-3 of the fp32 reference for O(1) AdaIN gains."""
-        w0, s0, _, c0 = self.block.slot(self.i0).operands()
-        w1, s1, _, c1 = self.block.slot(self.i1).operands()
+        w0, s0, _, e0 = self.block.slot(self.i0).operands()
+        w1, s1, _, e1 = self.block.slot(self.i1).operands()
         if precision == 'bf16x3':
-            y1 = ops.adain_conv(x, gamma0, beta0, w0, s0, upsample2=self.upsample, cache=c0)
+            y1 = ops.adain_conv(x, gamma0, beta0, w0, s0, upsample2=self.upsample, **e0)
             if self.skip is not None:
-                ws, ss, bs, cs = self.skip.slot(1).operands()
-                s = ops.conv2d(x, ws, ss, bias=bs, ksize=1, x_split=x_split, cache=cs)
+                ws, ss, bs, es = self.skip.slot(1).operands()
+                s = ops.conv2d(x, ws, ss, bias=bs, ksize=1, x_split=x_split, **es)
                 mode = 2 if self.upsample else 1
             else:
                 s, mode = x, 1
             out = ops.adain_conv(y1, gamma1, beta1, w1, s1, residual=s, residual_mode=mode,
-                                 emit_split=feeds_skip_conv, cache=c1)
+                                 emit_split=feeds_skip_conv, **e1)
             return out if feeds_skip_conv else (out, None)
         a0 = ops.adain_relu(x, gamma0, beta0, upsample2=self.upsample)
-        y1 = ops.conv2d(a0, w0, s0, ksize=3, cache=c0)
+        y1 = ops.conv2d(a0, w0, s0, ksize=3, **e0)
         a1 = ops.adain_relu(y1, gamma1, beta1)
         if self.skip is not None:
-            ws, ss, bs, cs = self.skip.slot(1).operands()
-            s = ops.conv2d(x, ws, ss, bias=bs, ksize=1, cache=cs)
+            ws, ss, bs, es = self.skip.slot(1).operands()
+            s = ops.conv2d(x, ws, ss, bias=bs, ksize=1, **es)
             mode = 2 if self.upsample else 1
         else:
             s, mode = x, 1
-        return ops.conv2d(a1, w1, s1, residual=s, residual_mode=mode, ksize=3, round_out=feeds_skip_conv,
-                          cache=c1), None
+        return ops.conv2d(a1, w1, s1, residual=s, residual_mode=mode, ksize=3, round_out=feeds_skip_conv, **e1), None
+
+    def tensor_core_convs(self):
+        return [m for m in (self.block.slot(self.i0), self.block.slot(self.i1),
+                            self.skip.slot(1) if self.skip is not None else None) if m is not None]
 
 
 class PlainResBlock(nn.Module):
@@ -177,16 +213,20 @@ class PlainResBlock(nn.Module):
 
     def forward(self, r, detach_params=False):
         """r = tf32(relu(block input)).  Returns the block output (pre-ReLU)."""
-        w0, s0, b0, c0 = self.block.slot(2).operands(detach_params)
-        h = ops.conv2d(r, w0, s0, bias=b0, ksize=3, relu=True, round_out=True, cache=c0)
-        w1, s1, b1, c1 = self.block.slot(5).operands(detach_params)
+        w0, s0, b0, e0 = self.block.slot(2).operands(detach_params)
+        h = ops.conv2d(r, w0, s0, bias=b0, ksize=3, relu=True, round_out=True, **e0)
+        w1, s1, b1, e1 = self.block.slot(5).operands(detach_params)
         if self.skip is not None:
-            ws, ss, bs, cs = self.skip.slot(0).operands(detach_params)
+            ws, ss, bs, es = self.skip.slot(0).operands(detach_params)
             rs = ops.avgpool2(r, None, round_out=True) if self.downsample else r
-            s = ops.conv2d(rs, ws, ss, bias=bs, ksize=1, cache=cs)
+            s = ops.conv2d(rs, ws, ss, bias=bs, ksize=1, **es)
         else:
             s = r
         if self.downsample:
-            h2 = ops.conv2d(h, w1, s1, bias=b1, ksize=3, cache=c1)
+            h2 = ops.conv2d(h, w1, s1, bias=b1, ksize=3, **e1)
             return ops.avgpool2(h2, s)
-        return ops.conv2d(h, w1, s1, bias=b1, residual=s, residual_mode=1, ksize=3, cache=c1)
+        return ops.conv2d(h, w1, s1, bias=b1, residual=s, residual_mode=1, ksize=3, **e1)
+
+    def tensor_core_convs(self):
+        return [m for m in (self.block.slot(2), self.block.slot(5), self.skip.slot(0) if self.skip is not None else None)
+                if m is not None]

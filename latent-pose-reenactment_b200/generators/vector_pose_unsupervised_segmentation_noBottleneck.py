@@ -141,6 +141,10 @@ class Generator(nn.Module):
         # constant (1,C,s,s) NCHW parameter -> (B,s,s,C) NHWC
         x = self.constant.constant.permute(0, 2, 3, 1).expand(batch, -1, -1, -1).contiguous()
         x_split = None
+        convs = []
+        for i in range(self.num_blocks):
+            convs += self.decoder_blocks.slot(i).tensor_core_convs()
+        blocks.spectral_sigmas(convs)          # one batched power iteration / sigma evaluation for the 22 decoder convs
         for i in range(self.num_blocks):
             blk = self.decoder_blocks.slot(i)
             g0, b0 = take(blk.in_channels)

@@ -38,14 +38,27 @@ def get_args(parser):
     parser.add('--num_visuals_per_img', default=2, type=int)
     parser.add('--fixed_val_ids', action='append', type=int, default=[50, 100, 200, 250, 300])
     parser.add('--batch_size_inference', default=5, type=int)
+    parser.add('--cuda_graph', action='store_bool', default=True,
+               help="capture the optimisation step in a CUDA graph and replay it (static batch shapes)")
     return parser
+
+
+def optimizer_class(name, device):
+    """`torch.optim.<name>` as the reference resolves it (Adam, or RAdam = the vendored rule), or — for CUDA
+    parameters — the fused multi-tensor kernel version with identical update rule and state layout."""
+    if str(device).startswith('cuda'):
+        from utils.fused_optim import FusedAdamEMA, FusedRAdamEMA
+        fused = {'Adam': FusedAdamEMA, 'RAdam': FusedRAdamEMA}
+        if name in fused:
+            return fused[name]
+    return torch.optim.__dict__[name]
 
 
 def get_optimizer(embedder, generator, args):
     model_parameters = list(generator.parameters())
     if 'finetune' not in args or not args.finetune:
         model_parameters += list(embedder.parameters())
-    Optimizer = torch.optim.__dict__[args.optimizer]
+    Optimizer = optimizer_class(args.optimizer, args.device)
     return Optimizer(model_parameters, lr=args.lr_gen, betas=(args.beta1, 0.999), eps=1e-5)
 
 
@@ -124,12 +137,16 @@ class TrainingModule(torch.nn.Module):
             module.requires_grad_(False)
 
     def update_running_average(self, alpha=0.999):
-        """p_avg = p_avg*alpha + p*(1-alpha) for E and G parameters; buffers copied (reference :99-109)."""
+        """p_avg = p_avg*alpha + p*(1-alpha) for E and G parameters; buffers copied (reference :99-109).
+        Parameters whose running average is maintained inside the fused optimizer kernel (see grad_buckets) are
+        skipped here — they were averaged in the same pass that updated them."""
+        fused = getattr(self, '_ema_in_optimizer', set())
         with torch.no_grad():
             for name, avg in self.running_averages.items():
                 cur = getattr(self, name)
-                p_avg, p_cur = list(avg.parameters()), list(cur.parameters())
-                if p_avg:
+                pairs = [(a, c) for a, c in zip(avg.parameters(), cur.parameters()) if id(c) not in fused]
+                if pairs:
+                    p_avg, p_cur = [a for a, _ in pairs], [c for _, c in pairs]
                     torch._foreach_mul_(p_avg, alpha)
                     torch._foreach_add_(p_avg, p_cur, alpha=1 - alpha)
                 b_avg, b_cur = list(avg.buffers()), list(cur.buffers())
@@ -207,6 +224,17 @@ class TrainingModule(torch.nn.Module):
             self._buckets = (key, GradBucket(params_G), GradBucket(params_D) if params_D else None)
             if hasattr(self.discriminator, 'skip_discarded_wgrad'):
                 self.discriminator.skip_discarded_wgrad = True
+            # running averages of the parameters optimizer_G owns ride along in its fused kernel
+            self._ema_in_optimizer = set()
+            if hasattr(optimizer_G, 'attach_ema') and self.running_averages:
+                owned = {id(p) for p in params_G}
+                pairs = []
+                for name, avg in self.running_averages.items():
+                    for a, c in zip(avg.parameters(), getattr(self, name).parameters()):
+                        if id(c) in owned:
+                            pairs.append((c, a))
+                            self._ema_in_optimizer.add(id(c))
+                optimizer_G.attach_ema(pairs, optimizer_G.ema_alpha)
         return self._buckets[1], self._buckets[2]
 
     def broadcast_parameters(self):
@@ -220,6 +248,9 @@ class TrainingModule(torch.nn.Module):
 def train_step(training_module, data_dict, target_dict, optimizer_G, optimizer_D, finetune=False):
     """One optimisation step (reference run_epoch :230-257).  Returns (all_data_dict, losses_G, losses_D)."""
     bucket_G, bucket_D = training_module.grad_buckets(optimizer_G, optimizer_D)
+    alpha = 0.972 if finetune else 0.999
+    if hasattr(optimizer_G, 'ema_alpha'):
+        optimizer_G.ema_alpha = alpha
     all_data_dict, losses_G_dict, losses_D_dict = training_module(data_dict, target_dict)
     loss_G = sum(v for v in losses_G_dict.values() if isinstance(v, torch.Tensor))
     loss_D = sum(v for v in losses_D_dict.values() if isinstance(v, torch.Tensor))
@@ -235,19 +266,67 @@ def train_step(training_module, data_dict, target_dict, optimizer_G, optimizer_D
         bucket_D.all_reduce()
         optimizer_D.step()
 
-    training_module.update_running_average(0.972 if finetune else 0.999)
+    training_module.update_running_average(alpha)
     return all_data_dict, losses_G_dict, losses_D_dict
+
+
+class GraphedTrainStep:
+    """The whole optimisation step (forward, both backward passes, gradient exchange, both optimizer updates, EMA)
+    captured ONCE in a CUDA graph and replayed per batch: the step is ~7000 kernel launches, which is host-launch
+    bound when issued one by one.  Everything in the step is capture-safe: libb200lp launches on the current stream
+    and never allocates or synchronises, the fused optimizer keeps its step counter on the device, and the gradient
+    all-reduce is a single in-place NCCL collective on a static buffer.
+
+    Usage:  step = GraphedTrainStep(tm, opt_G, opt_D, finetune, example_data, example_target)
+            all_data, losses_G, losses_D = step(data_dict, target_dict)      # tensors are static: read before next call
+    Batches must keep the example's shapes (the reference's train loader uses drop_last=True)."""
+
+    def __init__(self, training_module, optimizer_G, optimizer_D, finetune, data_dict, target_dict, warmup=3):
+        self.static_data = {k: v.clone() for k, v in data_dict.items() if torch.is_tensor(v)}
+        self.static_target = {k: v.clone() for k, v in target_dict.items() if torch.is_tensor(v)}
+        args = (training_module, self.static_data, self.static_target, optimizer_G, optimizer_D, finetune)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):         # lazy initialisation (buckets, optimizer tables, packed VGG weights, ...)
+                train_step(training_module, dict(self.static_data), dict(self.static_target), optimizer_G, optimizer_D,
+                           finetune)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = train_step(training_module, dict(self.static_data), dict(self.static_target), optimizer_G,
+                                      optimizer_D, finetune)
+
+    def __call__(self, data_dict, target_dict):
+        from b200lp import ops
+        for k, v in self.static_data.items():
+            v.copy_(data_dict[k], non_blocking=True)
+        for k, v in self.static_target.items():
+            v.copy_(target_dict[k], non_blocking=True)
+        self.graph.replay()
+        ops.bump_generation()        # weights were rewritten by the replayed optimizer kernels
+        return self.outputs
 
 
 def run_epoch(dataloader, training_module, optimizer_G, optimizer_D, epoch, args, phase, writer=None, saver=None):
     meter = Meter()
     end = time.time()
+    use_graph = phase == 'train' and getattr(args, 'cuda_graph', False) and str(args.device).startswith('cuda')
     for it, (data_dict, target_dict) in enumerate(dataloader):
         meter.add('Data_time', time.time() - end)
         utils.dict_to_device(data_dict, args.device)
         utils.dict_to_device(target_dict, args.device)
 
-        if phase == 'train':
+        if use_graph:
+            key = (id(optimizer_G), id(optimizer_D))
+            graphed = getattr(training_module, '_graphed_step', None)
+            if graphed is None or graphed[0] != key:
+                graphed = (key, GraphedTrainStep(training_module, optimizer_G, optimizer_D, args.finetune, data_dict,
+                                                 target_dict))
+                training_module._graphed_step = graphed
+            all_data_dict, losses_G_dict, losses_D_dict = graphed[1](data_dict, target_dict)
+        elif phase == 'train':
             all_data_dict, losses_G_dict, losses_D_dict = train_step(
                 training_module, data_dict, target_dict, optimizer_G, optimizer_D, finetune=args.finetune)
         else:

@@ -166,6 +166,7 @@ def _run_step(small, skip_discarded):
     opt_G = runner.get_optimizer(E, G, args)
     opt_D = importlib.import_module("discriminators.no_landmarks").Wrapper.get_optimizer(D, args)
     bucket_G, bucket_D = tm.grad_buckets(opt_G, opt_D)
+    opt_G.ema_alpha = 0.999          # runner.train_step sets this; this test drives the step by hand
     D.skip_discarded_wgrad = skip_discarded
     all_dd, lG, lD = tm(to_dev(small["data"], DEV), to_dev(small["target"], DEV))
     loss_G, loss_D = sum(lG.values()), sum(lD.values())
@@ -214,6 +215,50 @@ def test_training_step_losses_and_gradients(small, golden_small, skip_discarded)
     assert max_abs(g_after, golden_small["step.after.G.decoder_blocks.0.block.3.weight_orig"]) < 1.5e-4   # lr_gen * O(1)
     ema = r["tm"].running_averages["generator"].state_dict()["decoder_blocks.0.block.3.weight_orig"]
     assert max_abs(ema, golden_small["step.after.ema.G.decoder_blocks.0.block.3.weight_orig"]) < 1e-6
+
+
+def test_graphed_step_equals_eager_step(small):
+    """The CUDA-graph replay of the step (runner.GraphedTrainStep) produces the same losses and the same weights as the
+    kernel-by-kernel step, over several optimizer updates (device-side step counter, in-place spectral-norm buffers)."""
+    cfg = small["cfg"]
+    runner = importlib.import_module("runners.holycow")
+    results = []
+    for use_graph in (False, True):
+        with tempfile.TemporaryDirectory() as vgg_dir:
+            write_vgg_files(vgg_dir)
+            args = make_args(cfg, device=DEV, vgg_weights_dir=vgg_dir, optimizer="RAdam", lr_gen=5e-4, lr_dis=8e-4)
+            crit_list = [importlib.import_module(f"criterions.{n}").Wrapper.get_net(args)
+                         for n in ("adversarial", "featmat", "idt_embed", "perceptual", "dice")]
+        G, D = _G(cfg, small["g_sd"]), _D(cfg, small["d_sd"])
+        E = StubEmbedder(to_dev(small["emb"], DEV)).to(DEV)
+        tm = runner.TrainingModule(E, G, D, crit_list, [], {})
+        tm.train()
+        opt_G = runner.get_optimizer(E, G, args)
+        opt_D = importlib.import_module("discriminators.no_landmarks").Wrapper.get_optimizer(D, args)
+        data, target = to_dev(small["data"], DEV), to_dev(small["target"], DEV)
+        losses = []
+        if use_graph:
+            step = runner.GraphedTrainStep(tm, opt_G, opt_D, False, data, target, warmup=2)
+            n_before = 3            # 2 warm-up + 1 capture pass executed eagerly... capture does not execute
+            for _ in range(3):
+                _, lg, ld = step(data, target)
+                losses.append({k: float(v) for k, v in {**lg, **ld}.items()})
+        else:
+            for _ in range(5):
+                _, lg, ld = runner.train_step(tm, dict(data), dict(target), opt_G, opt_D, finetune=False)
+                losses.append({k: float(v) for k, v in {**lg, **ld}.items()})
+        results.append((losses, {k: v.detach().clone() for k, v in G.state_dict().items()},
+                        tm.running_averages["generator"].state_dict()["decoder_blocks.0.block.3.weight_orig"].clone()))
+    eager_losses, eager_sd, eager_ema = results[0]
+    graph_losses, graph_sd, graph_ema = results[1]
+    # graph path: 2 eager warm-up steps + 3 replays = 5 updates; its replay k corresponds to eager step 2 + k
+    for k in range(3):
+        for name, v in graph_losses[k].items():
+            ref = eager_losses[2 + k][name]
+            assert abs(v - ref) <= 2e-3 * abs(ref) + 1e-5, (k, name, v, ref)
+    w = "decoder_blocks.3.block.4.weight_orig"
+    assert max_abs(graph_sd[w], eager_sd[w]) < 5e-4 * float(eager_sd[w].abs().max()) + 1e-6
+    assert max_abs(graph_ema, eager_ema) < 1e-4
 
 
 def test_full_size_generator_vs_reference(golden_full):

@@ -397,6 +397,94 @@ def conv_timing():
 
 
 @check
+def sn_kernels():
+    """Batched spectral-norm kernels vs torch's formula (float64), and the weight-gradient correction vs autograd."""
+    import torch
+    from b200lp import kernels as K
+    torch.manual_seed(11)
+    out = []
+    shapes = [(64, 3, 3, 64), (512, 3, 3, 512), (128, 1, 1, 256), (256, 3, 3, 128), (32, 3, 3, 32)]
+    ws = [torch.randn(co, ci, k, k2, device="cuda") * 0.1 for (co, k, k2, ci) in shapes]
+    for training in (True, False):
+        us = [torch.nn.functional.normalize(torch.randn(w.shape[0], device="cuda"), dim=0) for w in ws]
+        vs = [torch.nn.functional.normalize(torch.randn(w[0].numel(), device="cuda"), dim=0) for w in ws]
+        u0 = [u.clone() for u in us]; v0 = [v.clone() for v in vs]
+        layers = [(w, u, v, 1e-4, K.sn_scratch(w)) for w, u, v in zip(ws, us, vs)]
+        inv, snaps = K.sn_sigma_multi(layers, training)
+        torch.cuda.synchronize()
+        for i, w in enumerate(ws):
+            wm = w.reshape(w.shape[0], -1).double()
+            u, v = u0[i].double(), v0[i].double()
+            if training:
+                v = torch.mv(wm.t(), u); v = v / v.norm().clamp_min(1e-4)
+                u = torch.mv(wm, v); u = u / u.norm().clamp_min(1e-4)
+            sigma = torch.dot(u, torch.mv(wm, v))
+            for name, a, b in [("inv_sigma", inv[i:i + 1], (1 / sigma).reshape(1)), ("u", us[i], u), ("v", vs[i], v),
+                               ("snap_u", snaps[i][0], u), ("snap_v", snaps[i][1], v)]:
+                e = _err(a, b); e["case"] = f"sn {name} train{int(training)} shape{tuple(w.shape)}"
+                e["ok"] = (not e["nan"]) and e["rel"] < 2e-5; out.append(e)
+    # gradient correction: L = sum(G0 * W/sigma(W)) with u, v constants  =>  dL/dW = s*G0 - s^2 <G0,W> u v^T
+    w = ws[3]; wm = w.reshape(w.shape[0], -1)
+    u = torch.nn.functional.normalize(torch.randn(w.shape[0], device="cuda"), dim=0)
+    v = torch.nn.functional.normalize(torch.randn(wm.shape[1], device="cuda"), dim=0)
+    g0 = torch.randn_like(w)
+    wd = w.double().requires_grad_(True)
+    sigma = torch.dot(u.double(), torch.mv(wd.reshape(w.shape[0], -1), v.double()))
+    (g0.double() * wd / sigma).sum().backward()
+    inv_sigma = (1 / sigma.detach()).float().reshape(1)
+    dw = K.sn_wgrad_fix(g0, w, inv_sigma, u, v)
+    torch.cuda.synchronize()
+    e = _err(dw, wd.grad); e["case"] = "sn_wgrad_fix vs autograd"; e["ok"] = (not e["nan"]) and e["rel"] < 2e-5
+    out.append(e)
+    return out
+
+
+@check
+def fused_optim():
+    """Fused Adam / RAdam + EMA kernel vs torch.optim.Adam and a per-tensor RAdam port, 8 steps."""
+    import torch
+    sys.path.insert(0, str(ROOT))
+    from oracle.cpu_step import RAdamPort
+    from utils.fused_optim import FusedAdamEMA, FusedRAdamEMA
+    out = []
+    for kind in ("Adam", "RAdam"):
+        torch.manual_seed(12)
+        shapes = [(70000,), (33, 17), (5,), (128, 64, 3, 3)]
+        ps = [torch.randn(*s, device="cuda").requires_grad_(True) for s in shapes]
+        ref = [p.detach().clone().double().requires_grad_(True) for p in ps]
+        ema = [p.detach().clone() for p in ps]
+        ema_ref = [p.detach().clone().double() for p in ps]
+        cls = FusedAdamEMA if kind == "Adam" else FusedRAdamEMA
+        opt = cls(ps, lr=5e-3, betas=(0.0, 0.999) if kind == "RAdam" else (0.5, 0.999), eps=1e-5)
+        opt.attach_ema(zip(ps, ema), 0.9)
+        if kind == "Adam":
+            oref = torch.optim.Adam(ref, lr=5e-3, betas=(0.5, 0.999), eps=1e-5)
+        else:
+            oref = RAdamPort(ref, lr=5e-3, betas=(0.0, 0.999), eps=1e-5)
+        for p in ps:
+            p.grad = torch.zeros_like(p)
+        for step in range(8):
+            for p, r in zip(ps, ref):
+                g = torch.randn_like(p)
+                p.grad.copy_(g)
+                r.grad = g.double()
+            opt.step(); oref.step()
+            for e_, r in zip(ema_ref, ref):
+                e_.mul_(0.9).add_(r.detach(), alpha=0.1)
+        torch.cuda.synchronize()
+        for i, (p, r) in enumerate(zip(ps, ref)):
+            e = _err(p.detach(), r.detach()); e["case"] = f"{kind} param {shapes[i]}"
+            e["ok"] = (not e["nan"]) and e["rel"] < 1e-5; out.append(e)
+            e = _err(ema[i], ema_ref[i]); e["case"] = f"{kind} ema {shapes[i]}"
+            e["ok"] = (not e["nan"]) and e["rel"] < 1e-5; out.append(e)
+        st = opt.state[ps[0]]
+        e = {"case": f"{kind} state keys/step", "ok": set(st.keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(st["step"]) == 8.0,
+             "max_abs": 0.0, "rel": 0.0, "nan": False, "ref_max": 8.0}
+        out.append(e)
+    return out
+
+
+@check
 def conv_tune():
     """Forward conv time vs (block_n, ring depth) for the shapes that dominate the step."""
     import torch
