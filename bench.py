@@ -402,6 +402,8 @@ def main():
     l0 = lib.load().b200lp_launch_count()
     ms = timed(step_resident, args.steps, dist_on)
     launches = lib.load().b200lp_launch_count() - l0
+    if graphed is not None:      # replays do not pass through the library's host-side counter
+        launches = graphed.kernels_per_replay * args.steps
     clocks = sampler.stop() if sampler else None
     for i in range(2):
         step_e2e(i)

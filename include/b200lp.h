@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 8
+#define B200LP_ABI_VERSION 11
 
 #define B200LP_OK 0
 #define B200LP_EINVAL (-1)   /* bad shape / unsupported configuration */
@@ -68,6 +68,7 @@ typedef struct {
     int32_t block_n;        /* 0 = auto; else 32 / 64 / 128 / 256 (256: tf32 only)     */
     int32_t precision;      /* 0 = tf32 (1 MMA / K-step), 1 = bf16x3 (3 MMAs: Ah*Bh + Ah*Bl + Al*Bh, ~fp32 accuracy) */
     int32_t stages;         /* 0 = auto; else depth of the shared-memory operand ring (tuning knob)                 */
+    int32_t ctas_per_sm;    /* 0 = auto; else 1 / 2 persistent CTAs per SM (tuning knob)                            */
 } b200lp_conv_args;
 
 int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream);
@@ -185,6 +186,10 @@ int32_t b200lp_upsample2_bwd(const float* dy, float* dx, int32_t N, int32_t H, i
 int32_t b200lp_l1_sum(const float* a, const float* b, float* out, int64_t n, float scale, void* stream);
 int32_t b200lp_l1_bwd(const float* a, const float* b, const float* gscale, float scale2, float* da, int64_t n,
                       int32_t accumulate, void* stream);
+/* one VGG backward tap in one pass (perceptual_loss.py:104-108 backward): `a` is a post-ReLU feature, so
+ *   d_out = [a > 0] * ( (d_in or 0) + sign(a-b) * gscale[0]*scale2 )      = l1_bwd followed by relu_bwd */
+int32_t b200lp_l1_relu_bwd(const float* a, const float* b, const float* gscale, float scale2, const float* d_in,
+                           float* d_out, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Direct (CUDA-core) convolutions for the two degenerate, HBM-bound shapes (SURVEY §7 "Degenerate GEMM shapes").
@@ -203,6 +208,15 @@ int32_t b200lp_conv3x3_c3_dgrad(const float* dy_nhwc, const float* w_oihw, const
 int32_t b200lp_conv3x3_c3_wgrad(const float* x_nchw, const float* dy_nhwc, float* dw_oihw, float wscale_host,
                                 int32_t N, int32_t H, int32_t W, int32_t Cout, void* stream);
 
+/* The gradients of those Cin=3 convs as tensor-core GEMMs over an explicit 27(+5 zero)-column patch matrix:
+ *   col[n,h,w, c*9+kh*3+kw] = tf32(x[n,c,h+kh-1,w+kw-1]) (0 outside the image; columns 27..31 are 0)
+ *   weight gradient = b200lp_conv_wgrad(col, dy, ksize=1)[:, :27];
+ *   data gradient   = col2im( b200lp_conv_fwd(dy, W^T as a 1x1 conv 64 -> 32) ):
+ *   dx[n,c,h,w] = pre_scale[c] * sum_{kh,kw} dcol[n,h-kh+1,w-kw+1, c*9+kh*3+kw] */
+int32_t b200lp_im2col3x3_c3(const float* x_nchw, float* col_nhwc32, int32_t N, int32_t H, int32_t W, void* stream);
+int32_t b200lp_col2im3x3_c3(const float* dcol_nhwc32, const float* pre_scale, float* dx_nchw, int32_t N, int32_t H,
+                            int32_t W, void* stream);
+
 /* Generator tail (generators/vector_pose_unsupervised_segmentation_noBottleneck.py:84-88,165-181):
  * a[n,h,w,0:4] = conv3x3(x[N,H,W,64] ; w[4][64][3][3]*(*wscale)) + bias ; t = tanh(a);
  * rgb = t[0:3]*0.75+0.5 ; segm = t[3]*0.5+0.5 ; fake_rgbs = rgb*segm (NCHW [N,3,H,W]) ; fake_segm (NCHW [N,1,H,W]).
@@ -212,10 +226,12 @@ int32_t b200lp_gen_tail_fwd(const float* x_nhwc, const float* w_oihw, const floa
                             int32_t W, int32_t Cin, void* stream);
 /* backward: from d(fake_rgbs) [N,3,H,W], d(fake_segm) [N,1,H,W] (either may be NULL) and saved t:
  * da [N,H,W,4] (pre-tanh gradient), then dx = conv-transpose, dw, dbias */
+/* da has `da_stride` (4 or 32) floats per pixel; with 32 the 28 extra channels are written as zeros so that `da` is a
+ * 32-channel NHWC tensor the tensor-core weight-gradient kernel (b200lp_conv_wgrad) accepts. */
 int32_t b200lp_gen_tail_bwd_act(const float* t, const float* d_rgbs, const float* d_segm, float* da, int32_t N,
-                                int32_t H, int32_t W, void* stream);
+                                int32_t H, int32_t W, int32_t da_stride, void* stream);
 int32_t b200lp_gen_tail_bwd_data(const float* da, const float* w_oihw, const float* wscale, float* dx_nhwc,
-                                 int32_t N, int32_t H, int32_t W, int32_t Cin, void* stream);
+                                 int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t da_stride, void* stream);
 int32_t b200lp_gen_tail_bwd_weight(const float* x_nhwc, const float* da, float* dw_oihw, float* dbias, int32_t N,
                                    int32_t H, int32_t W, int32_t Cin, void* stream);
 

@@ -57,7 +57,7 @@ def pack_conv_weight(w_oihw, scale=None, transpose=False, precision=TF32):
 
 
 def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False, round_tf32=False, block_n=0,
-             out=None, emit_split=False, stages=0, scale=None):
+             out=None, emit_split=False, stages=0, scale=None, ctas_per_sm=0):
     """x NHWC (N,H,W,Cin) float32 [TF32] or (2,N,H,W,Cin) bfloat16 (hi, lo) [BF16X3]; wp packed to match.
     `scale`: optional 1-element device tensor s, y = s * conv(x, wp) (+ bias ...).
     Returns y (N,H,W,Cout) float32, or (y, y_split) with y_split (2,N,H,W,Cout) bfloat16 when emit_split."""
@@ -85,6 +85,7 @@ def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False
     a.round_tf32 = int(round_tf32)
     a.block_n = block_n
     a.stages = stages
+    a.ctas_per_sm = ctas_per_sm
     a.precision = BF16X3 if split_in else TF32
     with _timed("conv_igemm_bf16x3" if split_in else "conv_igemm_tf32",
                 flops=2.0 * n * h * w * cin * cout * ksize * ksize):
@@ -248,6 +249,16 @@ def l1_bwd(a, b, gscale, scale2, da=None):
     return da
 
 
+def l1_relu_bwd(a, b, gscale, scale2, d_in=None):
+    """d_out = [a > 0] * (d_in + sign(a-b) * gscale[0]*scale2): one VGG backward tap (L1 term + ReLU mask) in one pass."""
+    lib = L.load()
+    d_out = torch.empty_like(a)
+    with _timed("l1", nbytes=(16.0 if d_in is not None else 12.0) * a.numel()):
+        L.check(lib.b200lp_l1_relu_bwd(L.ptr(a), L.ptr(b), L.ptr(gscale), c_float(scale2), L.ptr(d_in), L.ptr(d_out),
+                                       a.numel(), L.stream_ptr()), "l1_relu_bwd")
+    return d_out
+
+
 def conv3x3_c3_fwd(x_nchw, w, wscale=None, bias=None, pre_scale=None, pre_shift=None, relu=False, round_tf32=False):
     lib = L.load()
     n, c, h, wd = x_nchw.shape
@@ -294,25 +305,70 @@ def gen_tail_fwd(x, w, wscale, bias):
 
 
 def gen_tail_bwd(x, t, w, wscale, d_rgbs, d_segm, need_dx=True, need_dw=True):
+    """Backward of the generator tail.  Returns (dx, g, db): g = gradient w.r.t. the scaled weight (w*wscale), OIHW.
+    The weight gradient runs on the tensor cores: the 4-channel pre-tanh gradient is written as a zero-padded
+    32-channel NHWC tensor and handed to conv_wgrad."""
     lib = L.load()
     n, h, wd, cin = x.shape
-    da = torch.empty((n, h, wd, 4), dtype=torch.float32, device=x.device)
-    with _timed("gen_tail_bwd_act", nbytes=4.0 * 3 * da.numel()):
-        L.check(lib.b200lp_gen_tail_bwd_act(L.ptr(t), L.ptr(d_rgbs), L.ptr(d_segm), L.ptr(da), n, h, wd,
+    stride = 32 if need_dw else 4
+    da = torch.empty((n, h, wd, stride), dtype=torch.float32, device=x.device)
+    with _timed("gen_tail_bwd_act", nbytes=4.0 * (da.numel() + 2 * t.numel())):
+        L.check(lib.b200lp_gen_tail_bwd_act(L.ptr(t), L.ptr(d_rgbs), L.ptr(d_segm), L.ptr(da), n, h, wd, stride,
                                             L.stream_ptr()), "gen_tail_bwd_act")
     dx = dw = db = None
     if need_dx:
         dx = torch.empty_like(x)
         with _timed("gen_tail_bwd_data", nbytes=4.0 * (da.numel() + dx.numel())):
-            L.check(lib.b200lp_gen_tail_bwd_data(L.ptr(da), L.ptr(w), L.ptr(wscale), L.ptr(dx), n, h, wd, cin,
+            L.check(lib.b200lp_gen_tail_bwd_data(L.ptr(da), L.ptr(w), L.ptr(wscale), L.ptr(dx), n, h, wd, cin, stride,
                                                  L.stream_ptr()), "gen_tail_bwd_data")
     if need_dw:
-        dw = torch.empty((4, cin, 3, 3), dtype=torch.float32, device=x.device)
-        db = torch.empty((4,), dtype=torch.float32, device=x.device)
-        with _timed("gen_tail_bwd_weight", nbytes=4.0 * (da.numel() + x.numel())):
-            L.check(lib.b200lp_gen_tail_bwd_weight(L.ptr(x), L.ptr(da), L.ptr(dw), L.ptr(db), n, h, wd, cin,
-                                                   L.stream_ptr()), "gen_tail_bwd_weight")
+        dw = conv_wgrad(x, da, 3)[:4].contiguous()
+        db = bias_grad(da)[:4].contiguous()
     return dx, dw, db
+
+
+def im2col3x3_c3(x_nchw):
+    """(N,3,H,W) image -> (N,H,W,32) patch matrix (27 columns c*9+kh*3+kw, 5 zero columns), tf32-rounded."""
+    lib = L.load()
+    n, c, h, w = x_nchw.shape
+    assert c == 3
+    col = torch.empty((n, h, w, 32), dtype=torch.float32, device=x_nchw.device)
+    with _timed("c3_im2col", nbytes=4.0 * (x_nchw.numel() + col.numel())):
+        L.check(lib.b200lp_im2col3x3_c3(L.ptr(x_nchw), L.ptr(col), n, h, w, L.stream_ptr()), "im2col3x3_c3")
+    return col
+
+
+def col2im3x3_c3(dcol, pre_scale=None):
+    lib = L.load()
+    n, h, w, c = dcol.shape
+    assert c == 32
+    dx = torch.empty((n, 3, h, w), dtype=torch.float32, device=dcol.device)
+    with _timed("c3_col2im", nbytes=4.0 * (dcol.numel() + dx.numel())):
+        L.check(lib.b200lp_col2im3x3_c3(L.ptr(dcol), L.ptr(pre_scale), L.ptr(dx), n, h, w, L.stream_ptr()),
+                "col2im3x3_c3")
+    return dx
+
+
+def conv3x3_c3_dgrad_tc(dy, w_t_packed, wscale=None, pre_scale=None):
+    """Data gradient of a Cin=3 conv on the tensor cores: dcol = conv1x1(dy; W^T) (Cout -> 32), dx = col2im(dcol).
+    `w_t_packed` = pack_conv_weight of the (32, Cout, 1, 1) matrix made by c3_transposed_weight()."""
+    dcol = conv_fwd(dy, w_t_packed, 1, scale=wscale)
+    return col2im3x3_c3(dcol, pre_scale)
+
+
+def c3_transposed_weight(w_oihw):
+    """(Cout,3,3,3) -> (32, Cout, 1, 1): row t = c*9+kh*3+kw holds w[:, c, kh, kw]; rows 27..31 are zero."""
+    cout = w_oihw.shape[0]
+    wt = torch.zeros((32, cout), dtype=torch.float32, device=w_oihw.device)
+    wt[:27] = w_oihw.detach().reshape(cout, 27).t()
+    return pack_conv_weight(wt.reshape(32, cout, 1, 1))
+
+
+def conv3x3_c3_wgrad_tc(x_nchw, dy):
+    """Weight gradient of a Cin=3 conv on the tensor cores: conv_wgrad(im2col(x), dy, 1x1)[:, :27]."""
+    cout = dy.shape[-1]
+    g = conv_wgrad(im2col3x3_c3(x_nchw), dy, 1)          # (Cout, 32, 1, 1)
+    return g.reshape(cout, 32)[:, :27].reshape(cout, 3, 3, 3).contiguous()
 
 
 def bias_grad(dy):

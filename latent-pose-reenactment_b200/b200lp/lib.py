@@ -13,7 +13,7 @@ import torch
 
 _PKG = Path(__file__).resolve().parent.parent
 LIB_PATH = _PKG / "lib" / "libb200lp.so"
-ABI_VERSION = 8
+ABI_VERSION = 11
 
 
 class B200lpError(RuntimeError):
@@ -26,7 +26,7 @@ class ConvArgs(Structure):
         ("y", c_void_p), ("y_split", c_void_p),
         ("N", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("Cout", c_int32),
         ("ksize", c_int32), ("residual_mode", c_int32), ("relu", c_int32), ("round_tf32", c_int32),
-        ("block_n", c_int32), ("precision", c_int32), ("stages", c_int32),
+        ("block_n", c_int32), ("precision", c_int32), ("stages", c_int32), ("ctas_per_sm", c_int32),
     ]
 
 
@@ -82,12 +82,15 @@ SIGNATURES = {
     "b200lp_upsample2_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b200lp_l1_sum": (_I, [_P, _P, _P, _L, _F, _P]),
     "b200lp_l1_bwd": (_I, [_P, _P, _P, _F, _P, _L, _I, _P]),
+    "b200lp_l1_relu_bwd": (_I, [_P, _P, _P, _F, _P, _P, _L, _P]),
     "b200lp_conv3x3_c3_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "b200lp_conv3x3_c3_dgrad": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200lp_conv3x3_c3_wgrad": (_I, [_P, _P, _P, _F, _I, _I, _I, _I, _P]),
     "b200lp_gen_tail_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "b200lp_gen_tail_bwd_act": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
-    "b200lp_gen_tail_bwd_data": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_gen_tail_bwd_act": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_gen_tail_bwd_data": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200lp_im2col3x3_c3": (_I, [_P, _P, _I, _I, _I, _P]),
+    "b200lp_col2im3x3_c3": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "b200lp_gen_tail_bwd_weight": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200lp_bias_grad": (_I, [_P, _P, _L, _I, _P]),
     "b200lp_adam_ema_multi": (_I, [_P, _P, _P, _I, _L, _P, _F, _F, _F, _F, _F, _I, _I, _P]),

@@ -299,10 +299,10 @@ class ConvC3Fn(torch.autograd.Function):
         need_x, need_w, need_s, need_b = ctx.needs_input_grad[:4]
         dx = dw = ds = db = None
         if need_x:
-            dx = K.conv3x3_c3_dgrad(dy, weight_orig, inv_sigma, pre_scale)
+            dx = K.conv3x3_c3_dgrad_tc(dy, K.c3_transposed_weight(weight_orig), inv_sigma, pre_scale)
         if need_w or need_s:
             assert pre_scale is None, "weight gradient with input pre-affine is not needed on this path"
-            g = K.conv3x3_c3_wgrad(x, dy, 1.0)
+            g = K.conv3x3_c3_wgrad_tc(x, dy)
             if inv_sigma is not None:
                 if need_s:
                     ds = _dot(g, weight_orig).reshape(inv_sigma.shape)
@@ -423,13 +423,12 @@ class VggPerceptualFn(torch.autograd.Function):
                 continue
             a, b = saved[tap]
             tap -= 1
-            # d(loss)/d(a) gets the L1 term of this tap, then passes the ReLU mask
-            d = K.l1_bwd(a, b, gs, ctx.weight / a.numel(), da=d)
-            d = K.relu_bwd(a, d)
+            # d(loss)/d(a) gets the L1 term of this tap, then passes the ReLU mask (one fused pass)
+            d = K.l1_relu_bwd(a, b, gs, ctx.weight / a.numel(), d_in=d)
             if kind == "conv":
                 d = K.conv_fwd(d, packed["wpt"][idx], 3)
             else:
-                dx_img = K.conv3x3_c3_dgrad(d, packed["w0"], None, packed["pre_scale"])
+                dx_img = K.conv3x3_c3_dgrad_tc(d, packed["w0t"], None, packed["pre_scale"])
         return dx_img, None, None, None
 
 

@@ -80,6 +80,7 @@ class PerceptualLoss(nn.Module):
             w, b = getattr(self, f'w{i}', None), getattr(self, f'b{i}', None)
             if kind == 'conv0':
                 packed['w0'], packed['b0'] = w, b
+                packed['w0t'] = K.c3_transposed_weight(w)        # for the tensor-core data gradient of the stem
             elif kind == 'conv':
                 packed['wp'][i] = K.pack_conv_weight(w, None, transpose=False)
                 packed['wpt'][i] = K.pack_conv_weight(w, None, transpose=True)

@@ -49,6 +49,7 @@ struct ConvParams {
     int round_out;
     uint32_t a_bytes;      // bytes one A box delivers (may be < 16 KB when bn > N)
     int stages;            // depth of the smem ring (<= ConvCfg::kMaxStages)
+    int total_tiles;       // pixel patches x Cout tiles
 };
 
 template <int BLOCK_N, int MODE>
@@ -59,12 +60,10 @@ struct ConvCfg {
     static constexpr int kBBytes = BLOCK_N * kRowBytes;
     static constexpr int kStageBytes = kParts * (kABytes + kBBytes);
     static constexpr int kMaxStages = 8;
-    // default ring depth.  Shallow rings for BLOCK_N <= 128 keep a CTA under ~100 KB so that TWO CTAs share an SM:
-    // one CTA's epilogue (TMEM -> registers -> HBM) then overlaps the other CTA's main loop.
-    static constexpr int kDefaultStages = MODE == 0 ? ((BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 3 : 4))
-                                                    : ((BLOCK_N == 128) ? 3 : (BLOCK_N == 64 ? 4 : 5));
     static constexpr int kMaxSmemBytes = 226 * 1024;   // 227 KB opt-in limit minus the static barriers
-    static constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+    // two accumulators in TMEM: the epilogue drains one while the MMAs of the next tile fill the other
+    static constexpr uint32_t kAccCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+    static constexpr uint32_t kTmemCols = 2 * kAccCols;
 };
 
 struct ConvMaps {
@@ -72,6 +71,10 @@ struct ConvMaps {
     CUtensorMap b[2];   // weight planes
 };
 
+// Persistent, warp-specialised: every CTA walks the tile list  tile = blockIdx.x, blockIdx.x + gridDim.x, ...
+// (consecutive tiles = the N tiles of one pixel patch, so co-resident CTAs share the activation tile in L2).
+// The shared-memory ring and the two TMEM accumulators stay live across tiles: no per-tile prologue, and the
+// epilogue of tile i overlaps the main loop of tile i+1.
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
@@ -81,23 +84,16 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[Cfg::kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[Cfg::kMaxStages];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_slot;
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-    // stage s: A at s*kStageBytes, B right after it (both 1024-byte aligned)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    const int n_tile = blockIdx.x;
-    int m_tile = blockIdx.y;
-    const int tw = m_tile % p.tiles_w;
-    m_tile /= p.tiles_w;
-    const int th = m_tile % p.tiles_h;
-    const int tn = m_tile / p.tiles_h;
-    const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+    const int n_tiles = p.Cout / BLOCK_N;
 
     if (warp == 0 && lane == 0) {
 #pragma unroll
@@ -109,7 +105,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(&tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 4);      // one arrival per epilogue warp
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -126,24 +125,33 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
             const int pad = p.ksize >> 1;
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                const int tap = kb / p.cblks;
-                const int cb = kb - tap * p.cblks;
-                const int dy = tap / p.ksize - pad;
-                const int dx = tap % p.ksize - pad;
-                mbar_wait(&empty_bar[stage], phase ^ 1u);
-                // stage layout: [A plane 0][A plane 1]...[B plane 0][B plane 1]..., every plane 1024-byte aligned
-                uint8_t* sa = smem_al + stage * Cfg::kStageBytes;
-                uint8_t* sb = sa + Cfg::kParts * Cfg::kABytes;
-                mbar_expect_tx(&full_bar[stage], Cfg::kParts * (p.a_bytes + Cfg::kBBytes));
-                const int kcoord = tap * p.Cin + cb * Cfg::kChanPerRow;   // column of the packed [Cout][tap*Cin+ci] matrix
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % n_tiles;
+                int m_tile = tile / n_tiles;
+                const int tw = m_tile % p.tiles_w;
+                m_tile /= p.tiles_w;
+                const int th = m_tile % p.tiles_h;
+                const int tn = m_tile / p.tiles_h;
+                const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    const int tap = kb / p.cblks;
+                    const int cb = kb - tap * p.cblks;
+                    const int dy = tap / p.ksize - pad;
+                    const int dx = tap % p.ksize - pad;
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    // stage layout: [A plane 0][A plane 1]...[B plane 0][B plane 1]..., every plane 1024-byte aligned
+                    uint8_t* sa = smem_al + stage * Cfg::kStageBytes;
+                    uint8_t* sb = sa + Cfg::kParts * Cfg::kABytes;
+                    mbar_expect_tx(&full_bar[stage], Cfg::kParts * (p.a_bytes + Cfg::kBBytes));
+                    const int kcoord = tap * p.Cin + cb * Cfg::kChanPerRow;   // column of the packed weight matrix
 #pragma unroll
-                for (int q = 0; q < Cfg::kParts; ++q) {
-                    tma_load_4d(sa + q * Cfg::kABytes, &tm.a[q], &full_bar[stage], cb * Cfg::kChanPerRow, w0 + dx,
-                                h0 + dy, n0);
-                    tma_load_2d(sb + q * Cfg::kBBytes, &tm.b[q], &full_bar[stage], kcoord, n_tile * BLOCK_N);
+                    for (int q = 0; q < Cfg::kParts; ++q) {
+                        tma_load_4d(sa + q * Cfg::kABytes, &tm.a[q], &full_bar[stage], cb * Cfg::kChanPerRow, w0 + dx,
+                                    h0 + dy, n0);
+                        tma_load_2d(sb + q * Cfg::kBBytes, &tm.b[q], &full_bar[stage], kcoord, n_tile * BLOCK_N);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -151,33 +159,42 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
         if (lane == 0) {
             constexpr uint32_t idesc = MODE == 0 ? make_idesc_tf32(kBlockM, BLOCK_N, 0, 0)
                                                  : make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+            // K-major SWIZZLE_128B descriptors: 8-row groups 1024 B apart (SBO); only the start address changes
+            const uint64_t desc_hi = make_smem_desc(0, 16, 1024, 2);
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);      // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
-                const uint32_t b_addr = a_addr + Cfg::kParts * Cfg::kABytes;
+                const uint32_t tmem_acc = tmem_base + acc * Cfg::kAccCols;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
+                    const uint32_t b_addr = a_addr + Cfg::kParts * Cfg::kABytes;
+                    const uint64_t da0 = desc_hi | ((a_addr >> 4) & 0x3FFFu);
+                    const uint64_t db0 = desc_hi | ((b_addr >> 4) & 0x3FFFu);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // K-major SWIZZLE_128B: 8-row groups are 1024 B apart (SBO); one MMA consumes 32 bytes of K
-                    // (8 tf32 or 16 bf16), so stepping K = +32 bytes inside the 128-byte swizzle span
-                    const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024, 2);
-                    const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, 2);
-                    if (MODE == 0) {
-                        umma_tf32_ss(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    } else {
-                        const uint64_t da_lo = make_smem_desc(a_addr + Cfg::kABytes + k * 32, 16, 1024, 2);
-                        const uint64_t db_lo = make_smem_desc(b_addr + Cfg::kBBytes + k * 32, 16, 1024, 2);
-                        umma_f16_ss(tmem_base, da_lo, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);   // Al * Bh
-                        umma_f16_ss(tmem_base, da, db_lo, idesc, 1u);                            // Ah * Bl
-                        umma_f16_ss(tmem_base, da, db, idesc, 1u);                               // Ah * Bh
+                    for (int k = 0; k < 4; ++k) {
+                        // one MMA consumes 32 bytes of K (8 tf32 or 16 bf16): +32 B inside the 128-byte swizzle span
+                        const uint64_t da = da0 + 2 * k, db = db0 + 2 * k;
+                        if (MODE == 0) {
+                            umma_tf32_ss(tmem_acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        } else {
+                            const uint64_t da_lo = da + (Cfg::kABytes >> 4), db_lo = db + (Cfg::kBBytes >> 4);
+                            umma_f16_ss(tmem_acc, da_lo, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);   // Al * Bh
+                            umma_f16_ss(tmem_acc, da, db_lo, idesc, 1u);                            // Ah * Bl
+                            umma_f16_ss(tmem_acc, da, db, idesc, 1u);                               // Ah * Bh
+                        }
                     }
+                    umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                umma_commit(&tmem_full_bar[acc]);    // accumulator complete
             }
-            umma_commit(&tmem_full_bar);  // accumulator complete
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
@@ -186,64 +203,82 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
         const int wl = m % p.bw;
         const int hl = (m / p.bw) % p.bh;
         const int nl = m / (p.bw * p.bh);
-        const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
-        const bool valid = n < p.N;
-        const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
-        float* yrow = p.y + pix * p.Cout + n_tile * BLOCK_N;
-        const float* rrow = nullptr;
-        if (p.residual_mode == 1) {
-            rrow = p.residual + pix * p.Cout + n_tile * BLOCK_N;
-        } else if (p.residual_mode == 2) {
-            const size_t rp = (static_cast<size_t>(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
-            rrow = p.residual + rp * p.Cout + n_tile * BLOCK_N;
-        }
-        const float* brow = p.bias ? p.bias + n_tile * BLOCK_N : nullptr;
         const float oscale = p.out_scale ? __ldg(p.out_scale) : 1.0f;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int n_tile = tile % n_tiles;
+            int m_tile = tile / n_tiles;
+            const int tw = m_tile % p.tiles_w;
+            m_tile /= p.tiles_w;
+            const int th = m_tile % p.tiles_h;
+            const int tn = m_tile / p.tiles_h;
+            const int n = tn * p.bn + nl, h = th * p.bh + hl, w = tw * p.bw + wl;
+            const bool valid = n < p.N;
+            const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
+            float* yrow = p.y + pix * p.Cout + n_tile * BLOCK_N;
+            const float* rrow = nullptr;
+            if (p.residual_mode == 1) {
+                rrow = p.residual + pix * p.Cout + n_tile * BLOCK_N;
+            } else if (p.residual_mode == 2) {
+                const size_t rp = (static_cast<size_t>(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+                rrow = p.residual + rp * p.Cout + n_tile * BLOCK_N;
+            }
+            const float* brow = p.bias ? p.bias + n_tile * BLOCK_N : nullptr;
 
-        mbar_wait(&tmem_full_bar, 0);
-        tc_fence_after();
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
-            tmem_ld_wait();
-            if (valid) {
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_acc + c0, v);
+                tmem_ld_wait();
+                if (c0 + 32 >= BLOCK_N) {
+                    // all of this warp's TMEM reads of the accumulator are done: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                }
+                if (valid) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o;
-                    o.x = __uint_as_float(v[j + 0]) * oscale;
-                    o.y = __uint_as_float(v[j + 1]) * oscale;
-                    o.z = __uint_as_float(v[j + 2]) * oscale;
-                    o.w = __uint_as_float(v[j + 3]) * oscale;
-                    if (brow) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(brow + c0 + j));
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                    }
-                    if (rrow) {
-                        const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + c0 + j));
-                        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                    }
-                    if (p.relu) {
-                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                    }
-                    if (p.round_out) {
-                        o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
-                    }
-                    *reinterpret_cast<float4*>(yrow + c0 + j) = o;
-                    if (p.y_split) {   // (hi, lo) bf16 planes of the same values, for a following bf16x3 conv
-                        __nv_bfloat16* sp = p.y_split + pix * p.Cout + n_tile * BLOCK_N + c0 + j;
-                        const __nv_bfloat16 h0 = __float2bfloat16_rn(o.x), h1 = __float2bfloat16_rn(o.y),
-                                            h2 = __float2bfloat16_rn(o.z), h3 = __float2bfloat16_rn(o.w);
-                        __nv_bfloat162 hi01 = __halves2bfloat162(h0, h1), hi23 = __halves2bfloat162(h2, h3);
-                        __nv_bfloat162 lo01 = __halves2bfloat162(__float2bfloat16_rn(o.x - __bfloat162float(h0)),
-                                                                 __float2bfloat16_rn(o.y - __bfloat162float(h1)));
-                        __nv_bfloat162 lo23 = __halves2bfloat162(__float2bfloat16_rn(o.z - __bfloat162float(h2)),
-                                                                 __float2bfloat16_rn(o.w - __bfloat162float(h3)));
-                        uint2 hv, lv;
-                        hv.x = *reinterpret_cast<uint32_t*>(&hi01); hv.y = *reinterpret_cast<uint32_t*>(&hi23);
-                        lv.x = *reinterpret_cast<uint32_t*>(&lo01); lv.y = *reinterpret_cast<uint32_t*>(&lo23);
-                        *reinterpret_cast<uint2*>(sp) = hv;
-                        *reinterpret_cast<uint2*>(sp + p.split_stride) = lv;
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o;
+                        o.x = __uint_as_float(v[j + 0]) * oscale;
+                        o.y = __uint_as_float(v[j + 1]) * oscale;
+                        o.z = __uint_as_float(v[j + 2]) * oscale;
+                        o.w = __uint_as_float(v[j + 3]) * oscale;
+                        if (brow) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(brow + c0 + j));
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        if (rrow) {
+                            const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + c0 + j));
+                            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                        }
+                        if (p.relu) {
+                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                        }
+                        if (p.round_out) {
+                            o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+                        }
+                        *reinterpret_cast<float4*>(yrow + c0 + j) = o;
+                        if (p.y_split) {   // (hi, lo) bf16 planes of the same values, for a following bf16x3 conv
+                            __nv_bfloat16* sp = p.y_split + pix * p.Cout + n_tile * BLOCK_N + c0 + j;
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(o.x), h1 = __float2bfloat16_rn(o.y),
+                                                h2 = __float2bfloat16_rn(o.z), h3 = __float2bfloat16_rn(o.w);
+                            __nv_bfloat162 hi01 = __halves2bfloat162(h0, h1), hi23 = __halves2bfloat162(h2, h3);
+                            __nv_bfloat162 lo01 = __halves2bfloat162(__float2bfloat16_rn(o.x - __bfloat162float(h0)),
+                                                                     __float2bfloat16_rn(o.y - __bfloat162float(h1)));
+                            __nv_bfloat162 lo23 = __halves2bfloat162(__float2bfloat16_rn(o.z - __bfloat162float(h2)),
+                                                                     __float2bfloat16_rn(o.w - __bfloat162float(h3)));
+                            uint2 hv, lv;
+                            hv.x = *reinterpret_cast<uint32_t*>(&hi01); hv.y = *reinterpret_cast<uint32_t*>(&hi23);
+                            lv.x = *reinterpret_cast<uint32_t*>(&lo01); lv.y = *reinterpret_cast<uint32_t*>(&lo23);
+                            *reinterpret_cast<uint2*>(sp) = hv;
+                            *reinterpret_cast<uint2*>(sp + p.split_stride) = lv;
+                        }
                     }
                 }
             }
@@ -259,7 +294,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
 }
 
 template <int BLOCK_N, int MODE>
-static int launch_conv(const ConvMaps& tm, ConvParams p, int m_tiles, int stages, cudaStream_t stream) {
+static int launch_conv(const ConvMaps& tm, ConvParams p, int m_tiles, int stages, int ctas_per_sm, cudaStream_t stream) {
     using Cfg = ConvCfg<BLOCK_N, MODE>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -269,13 +304,30 @@ static int launch_conv(const ConvMaps& tm, ConvParams p, int m_tiles, int stages
                                                cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
-    if (stages <= 0) stages = Cfg::kDefaultStages;
-    if (stages > Cfg::kMaxStages) stages = Cfg::kMaxStages;
-    while (stages > 1 && stages * Cfg::kStageBytes + 1024 > Cfg::kMaxSmemBytes) --stages;
-    if (stages > p.num_kb) stages = p.num_kb;
+    // CTAs per SM: two when the double accumulators (2*BLOCK_N columns each) of two CTAs fit the 512 TMEM columns AND
+    // half of the shared memory still holds a ring of >= 3 stages; otherwise one CTA with the deepest ring that fits.
+    const int max_cpsm = (2 * Cfg::kTmemCols <= 512) ? 2 : 1;
+    auto ring = [](int cpsm) {
+        const int budget = (cpsm == 2 ? 113 * 1024 : Cfg::kMaxSmemBytes) - 1024;
+        int st = budget / Cfg::kStageBytes;
+        return st > Cfg::kMaxStages ? Cfg::kMaxStages : st;
+    };
+    if (ctas_per_sm <= 0) ctas_per_sm = (max_cpsm == 2 && ring(2) >= 3) ? 2 : 1;
+    if (ctas_per_sm > max_cpsm) ctas_per_sm = max_cpsm;
+    int max_stages = ring(ctas_per_sm);
+    if (max_stages < 1) max_stages = 1;
+    if (stages <= 0 || stages > max_stages) stages = max_stages;
     p.stages = stages;
+    p.total_tiles = m_tiles * (p.Cout / BLOCK_N);
     const int smem_bytes = stages * Cfg::kStageBytes + 1024;   // + alignment slack
-    dim3 grid(p.Cout / BLOCK_N, m_tiles, 1);
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        B200LP_CHECK_CUDA(cudaGetDevice(&dev));
+        B200LP_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int grid = num_sms * ctas_per_sm;
+    if (grid > p.total_tiles) grid = p.total_tiles;
     conv_igemm_kernel<BLOCK_N, MODE><<<grid, kConvThreads, smem_bytes, stream>>>(tm, p);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
@@ -363,62 +415,54 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
     }
     if (mode == 0) { tm.a[1] = tm.a[0]; tm.b[1] = tm.b[0]; }
     cudaStream_t s = as_stream(stream);
-    const int st = a->stages;
+    const int st = a->stages, cps = a->ctas_per_sm;
     if (mode == 0) {
         switch (block_n) {
-            case 256: return launch_conv<256, 0>(tm, p, m_tiles, st, s);
-            case 128: return launch_conv<128, 0>(tm, p, m_tiles, st, s);
-            case 64: return launch_conv<64, 0>(tm, p, m_tiles, st, s);
-            default: return launch_conv<32, 0>(tm, p, m_tiles, st, s);
+            case 256: return launch_conv<256, 0>(tm, p, m_tiles, st, cps, s);
+            case 128: return launch_conv<128, 0>(tm, p, m_tiles, st, cps, s);
+            case 64: return launch_conv<64, 0>(tm, p, m_tiles, st, cps, s);
+            default: return launch_conv<32, 0>(tm, p, m_tiles, st, cps, s);
         }
     }
     switch (block_n) {
-        case 128: return launch_conv<128, 1>(tm, p, m_tiles, st, s);
-        case 64: return launch_conv<64, 1>(tm, p, m_tiles, st, s);
-        default: return launch_conv<32, 1>(tm, p, m_tiles, st, s);
+        case 128: return launch_conv<128, 1>(tm, p, m_tiles, st, cps, s);
+        case 64: return launch_conv<64, 1>(tm, p, m_tiles, st, cps, s);
+        default: return launch_conv<32, 1>(tm, p, m_tiles, st, cps, s);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
 namespace b200lp {
-// One block = a 32 (co) x 32 (ci) x taps tile: reads are runs of 32*taps contiguous floats per co (OIHW), writes are
-// 128-byte runs along ci (forward layout) or along co (transposed layout); the transposition happens in shared memory.
+// One thread per packed element, indexed by DESTINATION (coalesced writes); the strided reads of the OIHW source are
+// served by L2 (a weight tensor is at most 9.4 MB).  A shared-memory-transposing variant was measured slower on the
+// small tensors (too few blocks) — profiles/r01_bench_graph_first.json.
 template <bool SPLIT>
-__global__ void __launch_bounds__(256)
-pack_conv_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale, float* __restrict__ wp,
-                        int Cout, int Cin, int taps, int transpose) {
-    __shared__ float tile[32][32 * 9 + 1];
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                        float* __restrict__ wp, int Cout, int Cin, int taps, int transpose) {
     const float s = scale ? __ldg(scale) : 1.0f;
-    const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
-    const int run = 32 * taps;                       // contiguous floats per co inside this tile
-    for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
-        const int co = i / run, r = i - co * run;    // r = ci_local * taps + tap
-        float v = 0.f;
-        if (co0 + co < Cout && ci0 + r / taps < Cin)
-            v = __ldg(w + (static_cast<long>(co0 + co) * Cin + ci0) * taps + r);
-        tile[co][r] = v * s;
-    }
-    __syncthreads();
     const long total = static_cast<long>(Cout) * Cin * taps;
-    for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
-        int co, ci, tap;
-        long dst;
-        if (!transpose) {                            // dst [co][tap][ci]: ci fastest
-            ci = i % 32; tap = (i / 32) % taps; co = i / (32 * taps);
-            dst = (static_cast<long>(co0 + co) * taps + tap) * Cin + ci0 + ci;
-        } else {                                     // dst [ci][taps-1-tap][co]: co fastest
-            co = i % 32; tap = (i / 32) % taps; ci = i / (32 * taps);
-            dst = (static_cast<long>(ci0 + ci) * taps + (taps - 1 - tap)) * Cout + co0 + co;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        float v;
+        if (!transpose) {
+            const int ci = i % Cin;
+            const int tap = (i / Cin) % taps;
+            const int co = i / (static_cast<long>(Cin) * taps);
+            v = w[(static_cast<long>(co) * Cin + ci) * taps + tap];
+        } else {
+            const int co = i % Cout;
+            const int tapf = (i / Cout) % taps;
+            const int ci = i / (static_cast<long>(Cout) * taps);
+            v = w[(static_cast<long>(co) * Cin + ci) * taps + (taps - 1 - tapf)];
         }
-        if (co0 + co >= Cout || ci0 + ci >= Cin) continue;
-        const float f = tile[co][ci * taps + tap];
+        const float f = v * s;
         if (!SPLIT) {
-            wp[dst] = round_tf32(f);
-        } else {                                     // (hi, lo) bf16 planes: hi + lo == f to 2^-17
+            wp[i] = round_tf32(f);
+        } else {   // (hi, lo) bf16 planes: hi + lo == f to 2^-17
             __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(wp);
             const __nv_bfloat16 h = __float2bfloat16_rn(f);
-            out[dst] = h;
-            out[total + dst] = __float2bfloat16_rn(f - __bfloat162float(h));
+            out[i] = h;
+            out[total + i] = __float2bfloat16_rn(f - __bfloat162float(h));
         }
     }
 }
@@ -429,13 +473,16 @@ extern "C" int32_t b200lp_pack_conv_weight(const float* w_oihw, const float* sca
                                            void* stream) {
     float* wp = static_cast<float*>(wp_out);
     B200LP_REQUIRE(w_oihw && wp && Cout > 0 && Cin > 0 && (ksize == 1 || ksize == 3), "pack_conv_weight: bad args");
-    dim3 grid((Cin + 31) / 32, (Cout + 31) / 32);
+    const long total = static_cast<long>(Cout) * Cin * ksize * ksize;
+    const int threads = 256;
+    long blocks = (total + threads - 1) / threads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
     if (precision == 0)
-        pack_conv_weight_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(w_oihw, scale, wp, Cout, Cin, ksize * ksize,
-                                                                            transpose);
+        pack_conv_weight_kernel<false><<<(int)blocks, threads, 0, as_stream(stream)>>>(w_oihw, scale, wp, Cout, Cin,
+                                                                                     ksize * ksize, transpose);
     else
-        pack_conv_weight_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(w_oihw, scale, wp, Cout, Cin, ksize * ksize,
-                                                                           transpose);
+        pack_conv_weight_kernel<true><<<(int)blocks, threads, 0, as_stream(stream)>>>(w_oihw, scale, wp, Cout, Cin,
+                                                                                    ksize * ksize, transpose);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

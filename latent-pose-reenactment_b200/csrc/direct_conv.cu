@@ -230,7 +230,8 @@ gen_tail_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
 
 // da = d(loss)/d(pre-tanh) from d(fake_rgbs), d(fake_segm)
 __global__ void gen_tail_bwd_act_kernel(const float* __restrict__ t, const float* __restrict__ d_rgbs,
-                                        const float* __restrict__ d_segm, float* __restrict__ da, long NP, long HW) {
+                                        const float* __restrict__ d_segm, float* __restrict__ da, long NP, long HW,
+                                        int da_stride) {
     const long P = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (P >= NP) return;
     const long n = P / HW, hw = P - n * HW;
@@ -251,13 +252,16 @@ __global__ void gen_tail_bwd_act_kernel(const float* __restrict__ t, const float
     o.y = (1.f - tv.y * tv.y) * dt1;
     o.z = (1.f - tv.z * tv.z) * dt2;
     o.w = (1.f - tv.w * tv.w) * dt3;
-    *reinterpret_cast<float4*>(da + P * 4) = o;
+    float* dst = da + P * da_stride;
+    *reinterpret_cast<float4*>(dst) = o;
+    // da_stride 32: zero-padded to a 32-channel NHWC tensor so that the tensor-core weight-gradient kernel can take it
+    for (int j = 4; j < da_stride; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // dx[p][ci] = sum_tap sum_j da[p - off(tap)][j] * w[j][ci][tap];   thread = (pixel, 16-channel group)
 __global__ void __launch_bounds__(256)
 gen_tail_bwd_data_kernel(const float* __restrict__ da, const float* __restrict__ w, const float* __restrict__ wscale,
-                         float* __restrict__ dx, int N, int H, int W, int Cin) {
+                         float* __restrict__ dx, int N, int H, int W, int Cin, int da_stride) {
     extern __shared__ float4 sw4[];   // [9][Cin] float4 over j
     const float s = wscale ? __ldg(wscale) : 1.f;
     for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) {
@@ -289,7 +293,7 @@ gen_tail_bwd_data_kernel(const float* __restrict__ da, const float* __restrict__
         for (int kw = 0; kw < 3; ++kw) {
             const int ww = wq - kw + 1;
             if (ww < 0 || ww >= W) continue;
-            const float4 d = ldg4(da + ((n * H + hh) * W + ww) * 4);
+            const float4 d = ldg4(da + ((n * H + hh) * W + ww) * da_stride);
             const float4* wt = sw4 + (kh * 3 + kw) * Cin + g * 16;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -363,9 +367,97 @@ gen_tail_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------ Cin = 3 via GEMM
+// The weight- and data-gradient of the 3-channel stem convs are tiny-K GEMMs over 524288 pixels; as CUDA-core loops
+// they were the slowest kernels of the step (profiles/r01_bench_graph_first.json).  They run on the tensor cores
+// instead, through an explicit 27(+5 zero)-column patch matrix:
+//   col[p][c*9 + kh*3 + kw] = x[n, c, h+kh-1, w+kw-1]         (im2col, NHWC with 32 "channels", tf32-rounded)
+//   dW = conv_wgrad(col, dy, 1x1)[:, :27]                     dcol = conv1x1(dy, W^T) ;  dx = col2im(dcol)
+__global__ void __launch_bounds__(256)
+im2col3x3_c3_kernel(const float* __restrict__ x, float* __restrict__ col, int N, int H, int W) {
+    const long P = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long HW = static_cast<long>(H) * W;
+    if (P >= N * HW) return;
+    const int wq = static_cast<int>(P % W);
+    const int hq = static_cast<int>((P / W) % H);
+    const long n = P / HW;
+    float v[32];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* xp = x + (n * 3 + c) * HW;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int hh = hq + kh - 1, ww = wq + kw - 1;
+                float t = 0.f;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) t = __ldg(xp + static_cast<long>(hh) * W + ww);
+                v[c * 9 + kh * 3 + kw] = round_tf32(t);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 27; j < 32; ++j) v[j] = 0.f;
+    float4* dst = reinterpret_cast<float4*>(col + P * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
+// dx[n,c,h,w] = pre_scale[c] * sum_{kh,kw} dcol[n, h-kh+1, w-kw+1][c*9 + kh*3 + kw]
+__global__ void __launch_bounds__(256)
+col2im3x3_c3_kernel(const float* __restrict__ dcol, const float* __restrict__ pre_scale, float* __restrict__ dx, int N,
+                    int H, int W) {
+    const long P = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long HW = static_cast<long>(H) * W;
+    if (P >= N * HW) return;
+    const int wq = static_cast<int>(P % W);
+    const int hq = static_cast<int>((P / W) % H);
+    const long n = P / HW;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int hh = hq - kh + 1;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int ww = wq - kw + 1;
+            if (ww < 0 || ww >= W) continue;
+            const float* r = dcol + ((n * H + hh) * W + ww) * 32 + kh * 3 + kw;
+            a0 += __ldg(r);
+            a1 += __ldg(r + 9);
+            a2 += __ldg(r + 18);
+        }
+    }
+    const long o = n * 3 * HW + static_cast<long>(hq) * W + wq;
+    dx[o] = a0 * (pre_scale ? __ldg(pre_scale + 0) : 1.f);
+    dx[o + HW] = a1 * (pre_scale ? __ldg(pre_scale + 1) : 1.f);
+    dx[o + 2 * HW] = a2 * (pre_scale ? __ldg(pre_scale + 2) : 1.f);
+}
+
 }  // namespace b200lp
 
 using namespace b200lp;
+
+extern "C" int32_t b200lp_im2col3x3_c3(const float* x_nchw, float* col_nhwc32, int32_t N, int32_t H, int32_t W,
+                                       void* stream) {
+    B200LP_REQUIRE(x_nchw && col_nhwc32 && N > 0 && H > 0 && W > 0, "im2col3x3_c3: bad args");
+    const long total = static_cast<long>(N) * H * W;
+    im2col3x3_c3_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, as_stream(stream)>>>(x_nchw, col_nhwc32, N, H, W);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_col2im3x3_c3(const float* dcol_nhwc32, const float* pre_scale, float* dx_nchw, int32_t N,
+                                       int32_t H, int32_t W, void* stream) {
+    B200LP_REQUIRE(dcol_nhwc32 && dx_nchw && N > 0 && H > 0 && W > 0, "col2im3x3_c3: bad args");
+    const long total = static_cast<long>(N) * H * W;
+    col2im3x3_c3_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, as_stream(stream)>>>(dcol_nhwc32, pre_scale,
+                                                                                              dx_nchw, N, H, W);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
 
 extern "C" int32_t b200lp_conv3x3_c3_fwd(const float* x_nchw, const float* w_oihw, const float* wscale,
                                          const float* bias, const float* pre_scale, const float* pre_shift,
@@ -433,28 +525,29 @@ extern "C" int32_t b200lp_gen_tail_fwd(const float* x_nhwc, const float* w_oihw,
 }
 
 extern "C" int32_t b200lp_gen_tail_bwd_act(const float* t, const float* d_rgbs, const float* d_segm, float* da,
-                                           int32_t N, int32_t H, int32_t W, void* stream) {
-    B200LP_REQUIRE(t && da && N > 0 && H > 0 && W > 0, "gen_tail_bwd_act: bad args");
+                                           int32_t N, int32_t H, int32_t W, int32_t da_stride, void* stream) {
+    B200LP_REQUIRE(t && da && N > 0 && H > 0 && W > 0 && (da_stride == 4 || da_stride == 32), "gen_tail_bwd_act: bad args");
     const long HW = static_cast<long>(H) * W;
     const long NP = N * HW;
     gen_tail_bwd_act_kernel<<<static_cast<int>((NP + 255) / 256), 256, 0, as_stream(stream)>>>(t, d_rgbs, d_segm, da,
-                                                                                               NP, HW);
+                                                                                               NP, HW, da_stride);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;
 }
 
 extern "C" int32_t b200lp_gen_tail_bwd_data(const float* da, const float* w_oihw, const float* wscale, float* dx_nhwc,
-                                            int32_t N, int32_t H, int32_t W, int32_t Cin, void* stream) {
+                                            int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t da_stride,
+                                            void* stream) {
     B200LP_REQUIRE(da && w_oihw && dx_nhwc && N > 0 && H > 0 && W > 0 && Cin % 16 == 0 && Cin <= 128 &&
-                       256 % (Cin / 16) == 0,
+                       256 % (Cin / 16) == 0 && (da_stride == 4 || da_stride == 32),
                    "gen_tail_bwd_data: bad args");
     const int groups = Cin / 16;
     const int ppb = 256 / groups;
     const long total = static_cast<long>(N) * H * W;
     const int blocks = static_cast<int>((total + ppb - 1) / ppb);
     gen_tail_bwd_data_kernel<<<blocks, 256, 9 * Cin * 16, as_stream(stream)>>>(da, w_oihw, wscale, dx_nhwc, N, H, W,
-                                                                               Cin);
+                                                                               Cin, da_stride);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

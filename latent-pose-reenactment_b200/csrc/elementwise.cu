@@ -56,13 +56,25 @@ __global__ void in_stats_partial_kernel(const float* __restrict__ x, float* __re
             k = ld4(base + static_cast<size_t>(p) * C);
             cnt = 1.f;
             p += rows;
+#define B200LP_ACC(v)                                                                        \
+    {                                                                                        \
+        const float dx = (v).x - k.x, dy = (v).y - k.y, dz = (v).z - k.z, dw = (v).w - k.w;  \
+        s.x += dx; s.y += dy; s.z += dz; s.w += dw;                                          \
+        q.x += dx * dx; q.y += dy * dy; q.z += dz * dz; q.w += dw * dw;                      \
+        cnt += 1.f;                                                                          \
+    }
+            for (; p + 3 * rows < p1; p += 4 * rows) {      // four independent 16-byte loads in flight per thread
+                const float4 v0 = ld4(base + static_cast<size_t>(p) * C);
+                const float4 v1 = ld4(base + static_cast<size_t>(p + rows) * C);
+                const float4 v2 = ld4(base + static_cast<size_t>(p + 2 * rows) * C);
+                const float4 v3 = ld4(base + static_cast<size_t>(p + 3 * rows) * C);
+                B200LP_ACC(v0) B200LP_ACC(v1) B200LP_ACC(v2) B200LP_ACC(v3)
+            }
             for (; p < p1; p += rows) {
                 const float4 v = ld4(base + static_cast<size_t>(p) * C);
-                const float dx = v.x - k.x, dy = v.y - k.y, dz = v.z - k.z, dw = v.w - k.w;
-                s.x += dx; s.y += dy; s.z += dz; s.w += dw;
-                q.x += dx * dx; q.y += dy * dy; q.z += dz * dz; q.w += dw * dw;
-                cnt += 1.f;
+                B200LP_ACC(v)
             }
+#undef B200LP_ACC
         }
     }
     // to (cnt, mean, M2)
@@ -472,6 +484,25 @@ __global__ void l1_bwd_kernel(const float4* __restrict__ a, const float4* __rest
     }
 }
 
+// VGG backward tap: d_out = [a > 0] * (d_in + sign(a - b) * g)   (a = post-ReLU feature, so [a>0] is the ReLU mask)
+// = l1_bwd (accumulating) followed by relu_bwd, in one pass over a, b, d.
+template <bool HAS_IN>
+__global__ void l1_relu_bwd_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
+                                   const float* __restrict__ gscale, float scale2, const float4* __restrict__ d_in,
+                                   float4* __restrict__ d_out, long n4) {
+    const float g = (gscale ? __ldg(gscale) : 1.f) * scale2;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const float4 u = __ldg(a + i), v = __ldg(b + i);
+        float4 d = HAS_IN ? __ldg(d_in + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        d.x = u.x > 0.f ? d.x + (u.x > v.x ? g : (u.x < v.x ? -g : 0.f)) : 0.f;
+        d.y = u.y > 0.f ? d.y + (u.y > v.y ? g : (u.y < v.y ? -g : 0.f)) : 0.f;
+        d.z = u.z > 0.f ? d.z + (u.z > v.z ? g : (u.z < v.z ? -g : 0.f)) : 0.f;
+        d.w = u.w > 0.f ? d.w + (u.w > v.w ? g : (u.w < v.w ? -g : 0.f)) : 0.f;
+        d_out[i] = d;
+    }
+}
+
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, long total) {
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -708,6 +739,23 @@ extern "C" int32_t b200lp_l1_bwd(const float* a, const float* b, const float* gs
         l1_bwd_kernel<false><<<g, kEwThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a),
                                                                       reinterpret_cast<const float4*>(b), gscale,
                                                                       scale2, reinterpret_cast<float4*>(da), n / 4);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_l1_relu_bwd(const float* a, const float* b, const float* gscale, float scale2,
+                                      const float* d_in, float* d_out, int64_t n, void* stream) {
+    B200LP_REQUIRE(a && b && d_out && n > 0 && n % 4 == 0, "l1_relu_bwd: bad args");
+    const int g = grid_for(n / 4, kEwThreads);
+    if (d_in)
+        l1_relu_bwd_kernel<true><<<g, kEwThreads, 0, as_stream(stream)>>>(
+            reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), gscale, scale2,
+            reinterpret_cast<const float4*>(d_in), reinterpret_cast<float4*>(d_out), n / 4);
+    else
+        l1_relu_bwd_kernel<false><<<g, kEwThreads, 0, as_stream(stream)>>>(
+            reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), gscale, scale2, nullptr,
+            reinterpret_cast<float4*>(d_out), n / 4);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

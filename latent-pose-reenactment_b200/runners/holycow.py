@@ -293,10 +293,14 @@ class GraphedTrainStep:
                            finetune)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from b200lp import lib as b200lp_lib
+        launched = b200lp_lib.load().b200lp_launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.outputs = train_step(training_module, dict(self.static_data), dict(self.static_target), optimizer_G,
                                       optimizer_D, finetune)
+        # libb200lp kernels recorded in the graph = launched by every replay
+        self.kernels_per_replay = int(b200lp_lib.load().b200lp_launch_count() - launched)
 
     def __call__(self, data_dict, target_dict):
         from b200lp import ops
