@@ -1,0 +1,53 @@
+"""Short launch sequence of the dominant kernels at the step's dominant shapes, for `ncu --set full` (kept short: ncu
+replays every kernel ~40 times).  Order of launches after the warm-up (each shape: 2 warm-up + 1 profiled launch):
+    conv_igemm tf32  : 64->64 @256^2, 128->128 @128^2, 512->256 @64^2          (bs 8)
+    conv_igemm bf16x3: 128->128 @128^2
+    conv_wgrad tf32  : 64->64 @256^2, 128->128 @128^2
+    adain_relu       : 64 ch @256^2 (no upsample), 128 ch @128^2 -> 256^2 (upsample)
+    in_stats         : 64 ch @256^2
+"""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "latent-pose-reenactment_b200"))
+sys.path.insert(0, str(ROOT / "tools"))
+
+import torch  # noqa: E402
+from b200lp import kernels as K  # noqa: E402
+from gpu_diag import split_bf16  # noqa: E402
+
+
+def main():
+    dev = "cuda"
+    torch.manual_seed(0)
+    for (H, Cin, Cout) in [(256, 64, 64), (128, 128, 128), (64, 512, 256)]:
+        x = torch.randn(8, H, H, Cin, device=dev)
+        wp = K.pack_conv_weight(torch.randn(Cout, Cin, 3, 3, device=dev))
+        y = torch.empty(8, H, H, Cout, device=dev)
+        for _ in range(3):
+            K.conv_fwd(x, wp, 3, out=y)
+    x = torch.randn(8, 128, 128, 128, device=dev)
+    xs = split_bf16(x)
+    wps = K.pack_conv_weight(torch.randn(128, 128, 3, 3, device=dev), precision=K.BF16X3)
+    for _ in range(3):
+        K.conv_fwd(xs, wps, 3)
+    for (H, C) in [(256, 64), (128, 128)]:
+        x = torch.randn(8, H, H, C, device=dev)
+        dy = torch.randn(8, H, H, C, device=dev)
+        for _ in range(3):
+            K.conv_wgrad(x, dy, 3)
+    aff = torch.randn(8, 256, device=dev)
+    x = torch.randn(8, 256, 256, 64, device=dev)
+    for _ in range(3):
+        mean, rstd = K.in_stats(x, 1e-4)
+        K.adain_relu(x, mean, rstd, aff[:, 64:128], aff[:, :64])
+    x = torch.randn(8, 128, 128, 128, device=dev)
+    mean, rstd = K.in_stats(x, 1e-4)
+    for _ in range(3):
+        K.adain_relu(x, mean, rstd, aff[:, 128:256], aff[:, :128], upsample2=True)
+    torch.cuda.synchronize()
+
+
+if __name__ == "__main__":
+    main()
