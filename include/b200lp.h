@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 11
+#define B200LP_ABI_VERSION 12
 
 #define B200LP_OK 0
 #define B200LP_EINVAL (-1)   /* bad shape / unsupported configuration */
@@ -69,8 +69,14 @@ typedef struct {
     int32_t precision;      /* 0 = tf32 (1 MMA / K-step), 1 = bf16x3 (3 MMAs: Ah*Bh + Ah*Bl + Al*Bh, ~fp32 accuracy) */
     int32_t stages;         /* 0 = auto; else depth of the shared-memory operand ring (tuning knob)                 */
     int32_t ctas_per_sm;    /* 0 = auto; else 1 / 2 persistent CTAs per SM (tuning knob)                            */
+    int32_t splits;         /* 0 = auto split-K for layers with too few tiles to fill the GPU, 1 = never, >1 forced  */
+    int32_t reserved;
+    float* workspace;       /* split-K partial sums; NULL = never split.  Size: b200lp_conv_fwd_workspace(args)      */
+    int64_t workspace_bytes;
 } b200lp_conv_args;
 
+/* bytes of split-K workspace the call described by `a` would use (0 if it will not split; pointers in `a` are ignored) */
+int64_t b200lp_conv_fwd_workspace(const b200lp_conv_args* a);
 int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

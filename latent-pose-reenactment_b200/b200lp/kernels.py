@@ -57,7 +57,7 @@ def pack_conv_weight(w_oihw, scale=None, transpose=False, precision=TF32):
 
 
 def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False, round_tf32=False, block_n=0,
-             out=None, emit_split=False, stages=0, scale=None, ctas_per_sm=0):
+             out=None, emit_split=False, stages=0, scale=None, ctas_per_sm=0, splits=0):
     """x NHWC (N,H,W,Cin) float32 [TF32] or (2,N,H,W,Cin) bfloat16 (hi, lo) [BF16X3]; wp packed to match.
     `scale`: optional 1-element device tensor s, y = s * conv(x, wp) (+ bias ...).
     Returns y (N,H,W,Cout) float32, or (y, y_split) with y_split (2,N,H,W,Cout) bfloat16 when emit_split."""
@@ -87,6 +87,11 @@ def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False
     a.stages = stages
     a.ctas_per_sm = ctas_per_sm
     a.precision = BF16X3 if split_in else TF32
+    a.splits = splits
+    need = lib.b200lp_conv_fwd_workspace(byref(a))
+    if need > 0:                      # few-tile layer: split-K partial sums
+        ws = _ws(need, x.device)
+        a.workspace, a.workspace_bytes = L.ptr(ws), ws.numel() * 4
     with _timed("conv_igemm_bf16x3" if split_in else "conv_igemm_tf32",
                 flops=2.0 * n * h * w * cin * cout * ksize * ksize):
         L.check(lib.b200lp_conv_fwd(byref(a), L.stream_ptr()), "conv_fwd")

@@ -49,7 +49,11 @@ struct ConvParams {
     int round_out;
     uint32_t a_bytes;      // bytes one A box delivers (may be < 16 KB when bn > N)
     int stages;            // depth of the smem ring (<= ConvCfg::kMaxStages)
-    int total_tiles;       // pixel patches x Cout tiles
+    int total_tiles;       // pixel patches x Cout tiles x K splits
+    int splits;            // split-K factor (1 = none): small-plane layers have too few tiles to fill 148 SMs
+    int kb_per_split;      // K blocks per split
+    float* ws;             // split-K partial sums [splits][N*H*W][Cout] (raw accumulators), NULL when splits == 1
+    long long ws_stride;   // N*H*W*Cout
 };
 
 template <int BLOCK_N, int MODE>
@@ -126,14 +130,18 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int n_tile = tile % n_tiles;
-                int m_tile = tile / n_tiles;
+                const int ks = tile % p.splits;
+                const int mn = tile / p.splits;
+                const int n_tile = mn % n_tiles;
+                int m_tile = mn / n_tiles;
                 const int tw = m_tile % p.tiles_w;
                 m_tile /= p.tiles_w;
                 const int th = m_tile % p.tiles_h;
                 const int tn = m_tile / p.tiles_h;
                 const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int kb0 = ks * p.kb_per_split;
+                const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     const int tap = kb / p.cblks;
                     const int cb = kb - tap * p.cblks;
                     const int dy = tap / p.ksize - pad;
@@ -170,7 +178,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);      // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_acc = tmem_base + acc * Cfg::kAccCols;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int nkb = min(p.num_kb, (tile % p.splits + 1) * p.kb_per_split) - (tile % p.splits) * p.kb_per_split;
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
@@ -208,8 +217,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int n_tile = tile % n_tiles;
-            int m_tile = tile / n_tiles;
+            const int ks = tile % p.splits;
+            const int mn = tile / p.splits;
+            const int n_tile = mn % n_tiles;
+            int m_tile = mn / n_tiles;
             const int tw = m_tile % p.tiles_w;
             m_tile /= p.tiles_w;
             const int th = m_tile % p.tiles_h;
@@ -218,6 +229,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
             const bool valid = n < p.N;
             const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
             float* yrow = p.y + pix * p.Cout + n_tile * BLOCK_N;
+            float* wsrow = p.ws ? p.ws + ks * p.ws_stride + pix * p.Cout + n_tile * BLOCK_N : nullptr;
             const float* rrow = nullptr;
             if (p.residual_mode == 1) {
                 rrow = p.residual + pix * p.Cout + n_tile * BLOCK_N;
@@ -241,7 +253,13 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
                 }
-                if (valid) {
+                if (valid && wsrow) {          // split-K: raw partial sums; the epilogue runs in splitk_epilogue_kernel
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(wsrow + c0 + j) =
+                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                        __uint_as_float(v[j + 3]));
+                } else if (valid) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 o;
@@ -293,6 +311,66 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
     }
 }
 
+// Split-K second pass: y = epilogue( sum_s ws[s] ), the same epilogue as the main kernel, deterministic summation order.
+__global__ void __launch_bounds__(256)
+splitk_epilogue_kernel(const ConvParams p, long long total4) {
+    const float oscale = p.out_scale ? __ldg(p.out_scale) : 1.0f;
+    const int c4 = p.Cout >> 2;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total4; i += gridDim.x * 256LL) {
+        const int c = static_cast<int>(i % c4) * 4;
+        const long long pix = i / c4;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < p.splits; ++s) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.ws + s * p.ws_stride + i * 4));
+            o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+        }
+        o.x *= oscale; o.y *= oscale; o.z *= oscale; o.w *= oscale;
+        if (p.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        }
+        if (p.residual_mode == 1) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + i * 4));
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        } else if (p.residual_mode == 2) {
+            const int w = static_cast<int>(pix % p.W);
+            const int h = static_cast<int>((pix / p.W) % p.H);
+            const long long n = pix / (static_cast<long long>(p.W) * p.H);
+            const long long rp = (n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+            const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + rp * p.Cout + c));
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        *reinterpret_cast<float4*>(p.y + i * 4) = o;
+        if (p.y_split) {
+            __nv_bfloat16* sp = p.y_split + i * 4;
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(o.x), h1 = __float2bfloat16_rn(o.y),
+                                h2 = __float2bfloat16_rn(o.z), h3 = __float2bfloat16_rn(o.w);
+            __nv_bfloat162 hi01 = __halves2bfloat162(h0, h1), hi23 = __halves2bfloat162(h2, h3);
+            __nv_bfloat162 lo01 = __halves2bfloat162(__float2bfloat16_rn(o.x - __bfloat162float(h0)),
+                                                     __float2bfloat16_rn(o.y - __bfloat162float(h1)));
+            __nv_bfloat162 lo23 = __halves2bfloat162(__float2bfloat16_rn(o.z - __bfloat162float(h2)),
+                                                     __float2bfloat16_rn(o.w - __bfloat162float(h3)));
+            uint2 hv, lv;
+            hv.x = *reinterpret_cast<uint32_t*>(&hi01); hv.y = *reinterpret_cast<uint32_t*>(&hi23);
+            lv.x = *reinterpret_cast<uint32_t*>(&lo01); lv.y = *reinterpret_cast<uint32_t*>(&lo23);
+            *reinterpret_cast<uint2*>(sp) = hv;
+            *reinterpret_cast<uint2*>(sp + p.split_stride) = lv;
+        }
+    }
+}
+
+// K splits so that a layer with few (pixel patch x Cout) tiles still fills the machine: at most one wave of 2 x #SM CTAs,
+// at least 4 K blocks per split, at most 32 splits.
+static int choose_splits(int mn_tiles, int num_kb) {
+    if (mn_tiles >= 100) return 1;
+    int s = (2 * 148) / mn_tiles;
+    if (s > num_kb / 4) s = num_kb / 4;
+    if (s > 32) s = 32;
+    return s < 1 ? 1 : s;
+}
+
 template <int BLOCK_N, int MODE>
 static int launch_conv(const ConvMaps& tm, ConvParams p, int m_tiles, int stages, int ctas_per_sm, cudaStream_t stream) {
     using Cfg = ConvCfg<BLOCK_N, MODE>;
@@ -318,7 +396,7 @@ static int launch_conv(const ConvMaps& tm, ConvParams p, int m_tiles, int stages
     if (max_stages < 1) max_stages = 1;
     if (stages <= 0 || stages > max_stages) stages = max_stages;
     p.stages = stages;
-    p.total_tiles = m_tiles * (p.Cout / BLOCK_N);
+    p.total_tiles = m_tiles * (p.Cout / BLOCK_N) * p.splits;
     const int smem_bytes = stages * Cfg::kStageBytes + 1024;   // + alignment slack
     static int num_sms = 0;
     if (num_sms == 0) {
@@ -331,12 +409,56 @@ static int launch_conv(const ConvMaps& tm, ConvParams p, int m_tiles, int stages
     conv_igemm_kernel<BLOCK_N, MODE><<<grid, kConvThreads, smem_bytes, stream>>>(tm, p);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
+    if (p.splits > 1) {
+        const long long total4 = p.ws_stride / 4;
+        long long blocks = (total4 + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        splitk_epilogue_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p, total4);
+        B200LP_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+    }
     return B200LP_OK;
 }
 
 }  // namespace b200lp
 
 using namespace b200lp;
+
+// geometry shared by b200lp_conv_fwd and b200lp_conv_fwd_workspace
+static int conv_pick_block_n(const b200lp_conv_args* a, int m_tiles) {
+    int block_n = a->block_n;
+    if (block_n == 0) {
+        if (a->precision == 0 && a->Cout % 256 == 0 && static_cast<long>(m_tiles) * (a->Cout / 256) >= 100) block_n = 256;
+        else if (a->Cout % 128 == 0) block_n = 128;
+        else if (a->Cout % 64 == 0) block_n = 64;
+        else block_n = 32;
+    }
+    return block_n;
+}
+static int conv_m_tiles(const b200lp_conv_args* a) {
+    const int bw = a->W < 16 ? a->W : 16;
+    const int bh = (kBlockM / bw) < a->H ? (kBlockM / bw) : a->H;
+    const int bn = kBlockM / (bw * bh);
+    return (a->W / bw) * (a->H / bh) * ((a->N + bn - 1) / bn);
+}
+static int conv_splits(const b200lp_conv_args* a, int block_n, int m_tiles) {
+    if (a->splits == 1) return 1;
+    const int chan_per_row = a->precision == 0 ? 32 : 64;
+    const int num_kb = a->ksize * a->ksize * ((a->Cin + chan_per_row - 1) / chan_per_row);
+    int s = a->splits > 1 ? a->splits : choose_splits(m_tiles * (a->Cout / block_n), num_kb);
+    if (s > num_kb) s = num_kb;
+    const int per = (num_kb + s - 1) / s;
+    return (num_kb + per - 1) / per;      // no empty split
+}
+
+extern "C" int64_t b200lp_conv_fwd_workspace(const b200lp_conv_args* a) {
+    if (!a || a->Cout <= 0 || a->N <= 0 || a->H <= 0 || a->W <= 0 || (a->ksize != 1 && a->ksize != 3)) return B200LP_EINVAL;
+    const int m_tiles = conv_m_tiles(a);
+    const int block_n = conv_pick_block_n(a, m_tiles);
+    if (a->Cout % block_n) return B200LP_EINVAL;
+    const int s = conv_splits(a, block_n, m_tiles);
+    return s > 1 ? static_cast<int64_t>(s) * a->N * a->H * a->W * a->Cout * 4 : 0;
+}
 
 extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
     B200LP_REQUIRE(a && a->x && a->wp && a->y, "conv_fwd: null pointer");
@@ -379,16 +501,20 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
     const int tiles_n = (a->N + p.bn - 1) / p.bn;
     const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
 
-    int block_n = a->block_n;
-    if (block_n == 0) {
-        if (mode == 0 && a->Cout % 256 == 0 && static_cast<long>(m_tiles) * (a->Cout / 256) >= 148) block_n = 256;
-        else if (a->Cout % 128 == 0) block_n = 128;
-        else if (a->Cout % 64 == 0) block_n = 64;
-        else block_n = 32;
-    }
+    const int block_n = conv_pick_block_n(a, m_tiles);
     B200LP_REQUIRE((block_n == 32 || block_n == 64 || block_n == 128 || (block_n == 256 && mode == 0)) &&
                        a->Cout % block_n == 0,
                    "conv_fwd: block_n=%d incompatible with Cout=%d (precision %d)", block_n, a->Cout, mode);
+
+    p.splits = conv_splits(a, block_n, m_tiles);
+    p.ws = nullptr;
+    p.ws_stride = static_cast<long long>(a->N) * a->H * a->W * a->Cout;
+    if (p.splits > 1) {
+        const int64_t need = static_cast<int64_t>(p.splits) * p.ws_stride * 4;
+        if (a->workspace && a->workspace_bytes >= need) p.ws = a->workspace;
+        else p.splits = 1;                      // no (or too small a) workspace: run unsplit
+    }
+    p.kb_per_split = (p.num_kb + p.splits - 1) / p.splits;
 
     ConvMaps tm;
     const uint64_t ktot = (uint64_t)a->ksize * a->ksize * a->Cin;

@@ -104,13 +104,15 @@ __global__ void in_stats_partial_kernel(const float* __restrict__ x, float* __re
     }
 }
 
+// one warp per (n, c): lanes stride over the chunk partials, then a shuffle tree of Chan merges (fp64)
 __global__ void in_stats_final_kernel(const float* __restrict__ part, float* __restrict__ mean,
                                       float* __restrict__ rstd, int chunks, int C, int NC, float eps) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // n*C + c
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // n*C + c
+    const int lane = threadIdx.x & 31;
     if (i >= NC) return;
     const int n = i / C, c = i - n * C;
     double cnt = 0.0, mu = 0.0, m2 = 0.0;
-    for (int k = 0; k < chunks; ++k) {
+    for (int k = lane; k < chunks; k += 32) {
         const float* d = part + ((static_cast<size_t>(n) * chunks + k) * C + c) * 3;
         const double bc = d[0], bm = d[1], b2 = d[2];
         if (bc == 0.0) continue;
@@ -120,9 +122,27 @@ __global__ void in_stats_final_kernel(const float* __restrict__ part, float* __r
         m2 += b2 + dl * dl * cnt * (bc / tot);
         cnt = tot;
     }
-    const double var = cnt > 0.0 ? m2 / cnt : 0.0;   // biased variance, as nn.InstanceNorm2d
-    mean[i] = static_cast<float>(mu);
-    rstd[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oc = __shfl_xor_sync(0xffffffffu, cnt, o);
+        const double om = __shfl_xor_sync(0xffffffffu, mu, o);
+        const double o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+        const double tot = cnt + oc;
+        if (tot > 0.0) {
+            const double dl = om - mu;
+            // symmetric merge: every lane ends with the same value (operands enter the formula identically on both sides
+            // up to the sign of dl, which is squared / multiplied by the partner's weight)
+            const double nm = (cnt * mu + oc * om) / tot;
+            m2 = m2 + o2 + dl * dl * (cnt * oc / tot);
+            mu = nm;
+            cnt = tot;
+        }
+    }
+    if (lane == 0) {
+        const double var = cnt > 0.0 ? m2 / cnt : 0.0;   // biased variance, as nn.InstanceNorm2d
+        mean[i] = static_cast<float>(mu);
+        rstd[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
 }
 
 static void stats_plan(int N, int HW, int C, int* chunks, int* pix_per_chunk) {
@@ -586,7 +606,7 @@ extern "C" int32_t b200lp_in_stats(const float* x, float* mean, float* rstd, flo
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     const int NC = N * C;
-    in_stats_final_kernel<<<(NC + 127) / 128, 128, 0, s>>>(workspace, mean, rstd, chunks, C, NC, eps);
+    in_stats_final_kernel<<<(NC + 3) / 4, 128, 0, s>>>(workspace, mean, rstd, chunks, C, NC, eps);   // 4 warps = 4 planes / block
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

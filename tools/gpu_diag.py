@@ -93,6 +93,33 @@ def conv_epilogue():
 
 
 @check
+def conv_splitk():
+    """Few-tile layers run split-K (auto) — same results; also forced splits with every epilogue option."""
+    import torch
+    from b200lp import kernels as K
+    out = [_conv_case(8, 4, 4, 512, 512, 3), _conv_case(8, 8, 8, 512, 512, 3, bias=True, relu=True),
+           _conv_case(8, 16, 16, 512, 512, 3, residual_mode=1), _conv_case(2, 16, 16, 64, 64, 3, residual_mode=2, bias=True),
+           _conv_case(8, 8, 8, 512, 512, 1, bias=True)]
+    out += _conv_bf16x3_case(8, 4, 4, 512, 512, 3, emit_split=True) + _conv_bf16x3_case(8, 8, 8, 512, 512, 3, residual_mode=2)
+    # timing: split vs unsplit on the 4x4 / 8x8 / 16x16 512-channel layers
+    for H in (4, 8, 16):
+        x = torch.randn(8, H, H, 512, device="cuda"); wp = K.pack_conv_weight(torch.randn(512, 512, 3, 3, device="cuda"))
+        rec = {"case": f"timing 512->512 @{H}x{H}", "ok": True, "max_abs": 0.0, "rel": 0.0, "nan": False, "ref_max": 0.0}
+        for name, sp in (("auto", 0), ("unsplit", 1)):
+            for _ in range(3):
+                K.conv_fwd(x, wp, 3, splits=sp)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                K.conv_fwd(x, wp, 3, splits=sp)
+            e1.record(); torch.cuda.synchronize()
+            rec[name + "_us"] = round(e0.elapsed_time(e1) / 20 * 1e3, 1)
+        out.append(rec)
+    return out
+
+
+@check
 def conv_big():
     return [_conv_case(8, 256, 256, 64, 64, 3), _conv_case(8, 128, 128, 128, 128, 3),
             _conv_case(8, 32, 32, 512, 512, 3), _conv_case(8, 64, 64, 512, 256, 3)]
