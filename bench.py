@@ -428,13 +428,16 @@ def main():
     e2e_value = frames / (ms_e2e / 1e3)
 
     extra = {}
-    if rank == 0 and not args.no_roofline:
+    if not args.no_roofline:
+        # every rank runs the instrumented step (it contains the gradient all-reduces); rank 0 reports
         peaks = {}
         pk = ROOT / "MEASURED_PEAKS.json"
         if pk.exists():
             peaks = json.loads(pk.read_text())
-        extra.update(roofline_pass(step_eager, peaks))
-        extra["peaks_source"] = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+        prof = roofline_pass(step_eager, peaks)
+        if rank == 0:
+            extra.update(prof)
+            extra["peaks_source"] = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
     if rank == 0 and world == 1:
         try:
             with torch.no_grad():
