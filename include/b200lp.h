@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 12
+#define B200LP_ABI_VERSION 13
 
 #define B200LP_OK 0
 #define B200LP_EINVAL (-1)   /* bad shape / unsupported configuration */
@@ -70,7 +70,12 @@ typedef struct {
     int32_t stages;         /* 0 = auto; else depth of the shared-memory operand ring (tuning knob)                 */
     int32_t ctas_per_sm;    /* 0 = auto; else 1 / 2 persistent CTAs per SM (tuning knob)                            */
     int32_t splits;         /* 0 = auto split-K for layers with too few tiles to fill the GPU, 1 = never, >1 forced  */
-    int32_t reserved;
+    int32_t variant;        /* 0 = auto; -1 = per-tap kernel (one activation box per filter tap);
+                               1 / 2 / 4 = halo kernel (3x3, H >= 16*variant, W >= 8): 8 x 16*variant pixel tiles, three
+                               column-shifted activation slabs per channel block shared by the 3 row taps, `variant`
+                               accumulators sharing every weight tile.  In the halo kernel `stages` is the depth of the
+                               weight-tile ring and `a_stages` that of the slab ring.                               */
+    int32_t a_stages;       /* 0 = auto (halo kernel only)                                                          */
     float* workspace;       /* split-K partial sums; NULL = never split.  Size: b200lp_conv_fwd_workspace(args)      */
     int64_t workspace_bytes;
 } b200lp_conv_args;
@@ -90,6 +95,14 @@ int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream);
  */
 int32_t b200lp_pack_conv_weight(const float* w_oihw, const float* scale, void* wp, int32_t Cout, int32_t Cin,
                                 int32_t ksize, int32_t transpose, int32_t precision, void* stream);
+
+/* Multi-tensor form: ONE launch re-packs every (weight, transpose, precision) copy of a network after its optimizer
+ * update (scale = 1: the spectral-norm 1/sigma is applied by the conv epilogue).  `table` (device): one row of
+ * 8 int64 per copy = { w_oihw pointer, wp pointer, Cout, Cin, taps (1 or 9), transpose, precision, Cout*Cin*taps };
+ * work is cut into chunks of `chunk_elems` packed elements: chunk c covers row chunk_item[c], elements
+ * [chunk_off[c], chunk_off[c] + chunk_elems). */
+int32_t b200lp_pack_conv_weight_multi(const void* table, const int32_t* chunk_item, const int64_t* chunk_off,
+                                      int32_t n_chunks, int64_t chunk_elems, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Spectral normalisation, batched over all weights of a network pass (3 launches instead of ~14 per weight).

@@ -56,8 +56,34 @@ def pack_conv_weight(w_oihw, scale=None, transpose=False, precision=TF32):
     return out
 
 
+PACK_CHUNK = 16384
+
+
+def pack_plan(rows, device):
+    """Device-side table for `pack_conv_weight_multi`: rows = [(w_ptr, wp_ptr, Cout, Cin, taps, transpose, precision,
+    numel), ...] (include/b200lp.h)."""
+    chunk_item, chunk_off = [], []
+    for i, r in enumerate(rows):
+        for o in range(0, r[7], PACK_CHUNK):
+            chunk_item.append(i)
+            chunk_off.append(o)
+    return dict(table=torch.tensor(rows, dtype=torch.int64, device=device),
+                chunk_item=torch.tensor(chunk_item, dtype=torch.int32, device=device),
+                chunk_off=torch.tensor(chunk_off, dtype=torch.int64, device=device), n_chunks=len(chunk_item),
+                nbytes=8.0 * sum(r[7] for r in rows))
+
+
+def pack_conv_weight_multi(plan):
+    lib = L.load()
+    with _timed("pack_conv_weight", nbytes=plan["nbytes"]):
+        L.check(lib.b200lp_pack_conv_weight_multi(c_void_p(plan["table"].data_ptr()),
+                                                  c_void_p(plan["chunk_item"].data_ptr()),
+                                                  c_void_p(plan["chunk_off"].data_ptr()), plan["n_chunks"], PACK_CHUNK,
+                                                  L.stream_ptr()), "pack_conv_weight_multi")
+
+
 def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False, round_tf32=False, block_n=0,
-             out=None, emit_split=False, stages=0, scale=None, ctas_per_sm=0, splits=0):
+             out=None, emit_split=False, stages=0, scale=None, ctas_per_sm=0, splits=0, variant=0, a_stages=0):
     """x NHWC (N,H,W,Cin) float32 [TF32] or (2,N,H,W,Cin) bfloat16 (hi, lo) [BF16X3]; wp packed to match.
     `scale`: optional 1-element device tensor s, y = s * conv(x, wp) (+ bias ...).
     Returns y (N,H,W,Cout) float32, or (y, y_split) with y_split (2,N,H,W,Cout) bfloat16 when emit_split."""
@@ -88,6 +114,7 @@ def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False
     a.ctas_per_sm = ctas_per_sm
     a.precision = BF16X3 if split_in else TF32
     a.splits = splits
+    a.variant, a.a_stages = variant, a_stages
     need = lib.b200lp_conv_fwd_workspace(byref(a))
     if need > 0:                      # few-tile layer: split-K partial sums
         ws = _ws(need, x.device)

@@ -13,7 +13,7 @@ import torch
 
 _PKG = Path(__file__).resolve().parent.parent
 LIB_PATH = _PKG / "lib" / "libb200lp.so"
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 
 class B200lpError(RuntimeError):
@@ -27,7 +27,8 @@ class ConvArgs(Structure):
         ("N", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("Cout", c_int32),
         ("ksize", c_int32), ("residual_mode", c_int32), ("relu", c_int32), ("round_tf32", c_int32),
         ("block_n", c_int32), ("precision", c_int32), ("stages", c_int32), ("ctas_per_sm", c_int32),
-        ("splits", c_int32), ("reserved", c_int32), ("workspace", c_void_p), ("workspace_bytes", c_int64),
+        ("splits", c_int32), ("variant", c_int32), ("a_stages", c_int32), ("workspace", c_void_p),
+        ("workspace_bytes", c_int64),
     ]
 
 
@@ -63,6 +64,7 @@ SIGNATURES = {
     "b200lp_conv_fwd_workspace": (_L, [POINTER(ConvArgs)]),
     "b200lp_conv_fwd": (_I, [POINTER(ConvArgs), _P]),
     "b200lp_pack_conv_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200lp_pack_conv_weight_multi": (_I, [_P, _P, _P, _I, _L, _P]),
     "b200lp_sn_max_tensors": (_I, []),
     "b200lp_sn_scratch_floats": (_L, [_I, _I]),
     "b200lp_sn_sigma_multi": (_I, [POINTER(SnItem), _I, _I, _P]),

@@ -4,6 +4,8 @@ torch.autograd is used as the graph/plumbing layer only (the reference's runner 
 `retain_graph`, runners/holycow.py:239-252); every forward and backward computation below is a libb200lp kernel.
 Activations are NHWC (N, H, W, C) float32 CUDA tensors.
 """
+import weakref
+
 import torch
 
 from . import kernels as K
@@ -26,10 +28,14 @@ class PackCache:
     """Packed (tensor-core layout) copies of one weight, keyed by (transpose, precision) and validated by the weight
     tensor's autograd version counter plus a global generation (see bump_generation): a weight is re-packed once per
     update instead of once per forward call (the three discriminator passes of a step and the backward passes share
-    the copies).  Lives on the owning module; deep copies start empty."""
+    the copies).  Lives on the owning module; deep copies start empty.  Live caches are tracked so that
+    `repack_weights` can refresh every copy of a network with one launch after its optimizer step."""
+
+    _live = weakref.WeakSet()
 
     def __init__(self):
         self.entries = {}
+        PackCache._live.add(self)
 
     def __deepcopy__(self, memo):
         return PackCache()
@@ -41,8 +47,42 @@ class PackCache:
         if hit is not None and hit[0] == stamp:
             return hit[1]
         packed = K.pack_conv_weight(weight.detach(), None, transpose=transpose, precision=precision)
-        self.entries[key] = (stamp, packed)
+        self.entries[key] = (stamp, packed, tuple(weight.shape))
         return packed
+
+
+_REPACK_PLANS = {}
+
+
+def repack_weights(params, owner=None):
+    """Refresh, with ONE multi-tensor launch, every packed copy that exists of the weights in `params` (call right after
+    the optimizer kernel that rewrote them, after bump_generation).  Copies are created lazily by PackCache.get on first
+    use; from the second step on all of them are known and this replaces ~50 single-tensor pack launches per network.
+    `owner`: key under which the device-side table is cached (the optimizer)."""
+    by_ptr = {p.data_ptr(): p for p in params if p.is_cuda}
+    rows, hits = [], []
+    for cache in list(PackCache._live):
+        for key, (stamp, packed, shape) in cache.entries.items():
+            w = by_ptr.get(stamp[2])
+            if w is None or tuple(w.shape) != shape:
+                continue
+            co, ci, kh, kw = shape
+            rows.append((stamp[2], packed.data_ptr(), co, ci, kh * kw, int(key[0]), int(key[1]), w.numel()))
+            hits.append((cache, key, packed, shape, w))
+    if not rows:
+        return 0
+    sig = tuple(rows)
+    plan = _REPACK_PLANS.get(owner)
+    if plan is None or plan["sig"] != sig:
+        if torch.cuda.is_current_stream_capturing():
+            return 0                     # table upload is not capturable: the lazy per-tensor path packs on first use
+        plan = K.pack_plan(rows, hits[0][4].device)
+        plan["sig"] = sig
+        _REPACK_PLANS[owner] = plan
+    K.pack_conv_weight_multi(plan)
+    for cache, key, packed, shape, w in hits:
+        cache.entries[key] = ((_GENERATION[0], w._version, w.data_ptr()), packed, shape)
+    return len(rows)
 
 
 def _packed(weight, cache, transpose, precision=K.TF32):

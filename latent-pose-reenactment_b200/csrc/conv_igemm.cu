@@ -54,6 +54,7 @@ struct ConvParams {
     int kb_per_split;      // K blocks per split
     float* ws;             // split-K partial sums [splits][N*H*W][Cout] (raw accumulators), NULL when splits == 1
     long long ws_stride;   // N*H*W*Cout
+    int a_stages, b_stages;   // halo kernel: depths of the activation-slab ring and of the weight-tile ring
 };
 
 template <int BLOCK_N, int MODE>
@@ -74,6 +75,60 @@ struct ConvMaps {
     CUtensorMap a[2];   // activation planes (hi, lo)
     CUtensorMap b[2];   // weight planes
 };
+
+// Epilogue of one 32-column chunk of one pixel row: v = raw accumulators of channels [c0, c0+32) of this thread's pixel.
+// Either raw partial sums into the split-K workspace, or  y = round(relu(acc * oscale + bias + residual))  (+ the (hi, lo)
+// bf16 planes of y for a following bf16x3 conv).  `elem` = pix * Cout + first channel of the tile.
+__device__ __forceinline__ void epilogue_store_chunk(const ConvParams& p, const uint32_t (&v)[32], float oscale,
+                                                     float* yrow, float* wsrow, const float* rrow, const float* brow,
+                                                     size_t elem, int c0) {
+    if (wsrow) {          // split-K: raw partial sums; the epilogue runs in splitk_epilogue_kernel
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(wsrow + c0 + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                            __uint_as_float(v[j + 3]));
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        float4 o;
+        o.x = __uint_as_float(v[j + 0]) * oscale;
+        o.y = __uint_as_float(v[j + 1]) * oscale;
+        o.z = __uint_as_float(v[j + 2]) * oscale;
+        o.w = __uint_as_float(v[j + 3]) * oscale;
+        if (brow) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(brow + c0 + j));
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        }
+        if (rrow) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + c0 + j));
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (p.relu) {
+            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+        }
+        if (p.round_out) {
+            o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+        }
+        *reinterpret_cast<float4*>(yrow + c0 + j) = o;
+        if (p.y_split) {   // (hi, lo) bf16 planes of the same values, for a following bf16x3 conv
+            __nv_bfloat16* sp = p.y_split + elem + c0 + j;
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(o.x), h1 = __float2bfloat16_rn(o.y),
+                                h2 = __float2bfloat16_rn(o.z), h3 = __float2bfloat16_rn(o.w);
+            __nv_bfloat162 hi01 = __halves2bfloat162(h0, h1), hi23 = __halves2bfloat162(h2, h3);
+            __nv_bfloat162 lo01 = __halves2bfloat162(__float2bfloat16_rn(o.x - __bfloat162float(h0)),
+                                                     __float2bfloat16_rn(o.y - __bfloat162float(h1)));
+            __nv_bfloat162 lo23 = __halves2bfloat162(__float2bfloat16_rn(o.z - __bfloat162float(h2)),
+                                                     __float2bfloat16_rn(o.w - __bfloat162float(h3)));
+            uint2 hv, lv;
+            hv.x = *reinterpret_cast<uint32_t*>(&hi01); hv.y = *reinterpret_cast<uint32_t*>(&hi23);
+            lv.x = *reinterpret_cast<uint32_t*>(&lo01); lv.y = *reinterpret_cast<uint32_t*>(&lo23);
+            *reinterpret_cast<uint2*>(sp) = hv;
+            *reinterpret_cast<uint2*>(sp + p.split_stride) = lv;
+        }
+    }
+}
 
 // Persistent, warp-specialised: every CTA walks the tile list  tile = blockIdx.x, blockIdx.x + gridDim.x, ...
 // (consecutive tiles = the N tiles of one pixel patch, so co-resident CTAs share the activation tile in L2).
@@ -125,7 +180,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // The whole warp walks the loop (warp-uniform control flow) and one elected lane issues: under a divergent
+        // `if (lane == 0)` ptxas wraps every TMA / MMA / commit in an ELECT + BRA.U.ANY loop (~8 extra instructions
+        // per MMA on the single issuing thread, measured 76 clk per MMA against a 64-clk N=128 instruction).
+        const bool leader = elect_one();
+        {
             const int pad = p.ksize >> 1;
             int stage = 0;
             uint32_t phase = 0;
@@ -150,21 +209,24 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
                     // stage layout: [A plane 0][A plane 1]...[B plane 0][B plane 1]..., every plane 1024-byte aligned
                     uint8_t* sa = smem_al + stage * Cfg::kStageBytes;
                     uint8_t* sb = sa + Cfg::kParts * Cfg::kABytes;
-                    mbar_expect_tx(&full_bar[stage], Cfg::kParts * (p.a_bytes + Cfg::kBBytes));
                     const int kcoord = tap * p.Cin + cb * Cfg::kChanPerRow;   // column of the packed weight matrix
+                    if (leader) {
+                        mbar_expect_tx(&full_bar[stage], Cfg::kParts * (p.a_bytes + Cfg::kBBytes));
 #pragma unroll
-                    for (int q = 0; q < Cfg::kParts; ++q) {
-                        tma_load_4d(sa + q * Cfg::kABytes, &tm.a[q], &full_bar[stage], cb * Cfg::kChanPerRow, w0 + dx,
-                                    h0 + dy, n0);
-                        tma_load_2d(sb + q * Cfg::kBBytes, &tm.b[q], &full_bar[stage], kcoord, n_tile * BLOCK_N);
+                        for (int q = 0; q < Cfg::kParts; ++q) {
+                            tma_load_4d(sa + q * Cfg::kABytes, &tm.a[q], &full_bar[stage], cb * Cfg::kChanPerRow,
+                                        w0 + dx, h0 + dy, n0);
+                            tma_load_2d(sb + q * Cfg::kBBytes, &tm.b[q], &full_bar[stage], kcoord, n_tile * BLOCK_N);
+                        }
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (warp-uniform loop, elected lane issues) =====================
+        const bool leader = elect_one();
+        {
             constexpr uint32_t idesc = MODE == 0 ? make_idesc_tf32(kBlockM, BLOCK_N, 0, 0)
                                                  : make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
             // K-major SWIZZLE_128B descriptors: 8-row groups 1024 B apart (SBO); only the start address changes
@@ -186,23 +248,25 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
                     const uint32_t b_addr = a_addr + Cfg::kParts * Cfg::kABytes;
                     const uint64_t da0 = desc_hi | ((a_addr >> 4) & 0x3FFFu);
                     const uint64_t db0 = desc_hi | ((b_addr >> 4) & 0x3FFFu);
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        // one MMA consumes 32 bytes of K (8 tf32 or 16 bf16): +32 B inside the 128-byte swizzle span
-                        const uint64_t da = da0 + 2 * k, db = db0 + 2 * k;
-                        if (MODE == 0) {
-                            umma_tf32_ss(tmem_acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        } else {
-                            const uint64_t da_lo = da + (Cfg::kABytes >> 4), db_lo = db + (Cfg::kBBytes >> 4);
-                            umma_f16_ss(tmem_acc, da_lo, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);   // Al * Bh
-                            umma_f16_ss(tmem_acc, da, db_lo, idesc, 1u);                            // Ah * Bl
-                            umma_f16_ss(tmem_acc, da, db, idesc, 1u);                               // Ah * Bh
+                        for (int k = 0; k < 4; ++k) {
+                            // one MMA consumes 32 bytes of K (8 tf32 or 16 bf16): +32 B inside the 128-byte swizzle span
+                            const uint64_t da = da0 + 2 * k, db = db0 + 2 * k;
+                            if (MODE == 0) {
+                                umma_tf32_ss(tmem_acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            } else {
+                                const uint64_t da_lo = da + (Cfg::kABytes >> 4), db_lo = db + (Cfg::kBBytes >> 4);
+                                umma_f16_ss(tmem_acc, da_lo, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);   // Al * Bh
+                                umma_f16_ss(tmem_acc, da, db_lo, idesc, 1u);                            // Ah * Bl
+                                umma_f16_ss(tmem_acc, da, db, idesc, 1u);                               // Ah * Bh
+                            }
                         }
+                        umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
                     }
-                    umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(&tmem_full_bar[acc]);    // accumulator complete
+                if (leader) umma_commit(&tmem_full_bar[acc]);    // accumulator complete
             }
         }
     } else {
@@ -253,51 +317,250 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
                 }
-                if (valid && wsrow) {          // split-K: raw partial sums; the epilogue runs in splitk_epilogue_kernel
+                if (valid) epilogue_store_chunk(p, v, oscale, yrow, wsrow, rrow, brow, pix * p.Cout + n_tile * BLOCK_N, c0);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ====================================================================================================================
+// Halo variant for 3x3 layers on planes >= 16 x 8 (all the FLOP-heavy layers of the step).
+//
+// The per-tap kernel above re-fetches the activation patch once per filter tap (9x) and the weight tile once per
+// 128-pixel patch; every instantiation of it measured at the L2->SM fabric limit (~40 B/clk/SM, ncu: tensor pipe 32 % /
+// 50 % / 72 % active at BLOCK_N 64 / 128 / 256 == bytes-per-FLOP of the tile).  This variant cuts the bytes:
+//   * a CTA tile is 8 pixels wide and PH = 16*MT rows tall (MT accumulators of 128 pixels each share every weight tile);
+//   * per 32-channel block the activations arrive as THREE column-shifted slabs (dx = -1, 0, +1), each
+//     8 x (PH + 2) pixels = (PH + 2) KB.  A slab row is one 8-pixel x 128-byte swizzle atom (1024 B), so the A operand
+//     of tap (dy, dx) for sub-tile mt is the same slab at byte offset (16*mt + dy + 1) * 1024: 1024-byte aligned, the
+//     plain K-major SWIZZLE_128B descriptor with SBO = 1024 — only the start address moves.
+//   Activation bytes per 128 pixels and channel block: 3*(16*MT+2)/MT KB instead of 144 KB; weight bytes / MT.
+// Two independent rings (activation slabs, weight tiles) with one producer warp each; the MMA warp walks
+// channel block -> dx -> dy -> sub-tile -> 4 K steps.
+template <int BLOCK_N, int MT, int MODE>
+struct HaloCfg {
+    static constexpr int kParts = MODE == 0 ? 1 : 2;
+    static constexpr int kChanPerRow = MODE == 0 ? 32 : 64;
+    static constexpr int kPH = 16 * MT;                               // patch height
+    static constexpr int kSlabBytes = (kPH + 2) * 1024;               // one plane of one dx slab
+    static constexpr int kAUnitBytes = kParts * kSlabBytes;
+    static constexpr int kBPlaneBytes = BLOCK_N * kRowBytes;
+    static constexpr int kBUnitBytes = kParts * kBPlaneBytes;
+    static constexpr int kMaxAStages = 6, kMaxBStages = 8;
+    static constexpr int kMaxSmemBytes = 226 * 1024;
+    static constexpr uint32_t kTileCols = MT * BLOCK_N;               // accumulator columns of one CTA tile
+    static constexpr int kAccBufs = 2 * kTileCols <= 512 ? 2 : 1;     // double-buffer when TMEM allows
+    static constexpr uint32_t kTmemCols = kAccBufs * kTileCols < 32 ? 32 : kAccBufs * kTileCols;
+    static_assert(kTileCols <= 512, "accumulators exceed TMEM");
+};
+
+constexpr int kHaloThreads = 224;   // warp 0: slab producer, 1: MMA, 2..5: epilogue, 6: weight producer
+
+template <int BLOCK_N, int MT, int MODE>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
+    using Cfg = HaloCfg<BLOCK_N, MT, MODE>;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t a_full[Cfg::kMaxAStages];
+    __shared__ __align__(8) uint64_t a_empty[Cfg::kMaxAStages];
+    __shared__ __align__(8) uint64_t b_full[Cfg::kMaxBStages];
+    __shared__ __align__(8) uint64_t b_empty[Cfg::kMaxBStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_slot;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int SA = p.a_stages, SB = p.b_stages;
+    const uint32_t b_ring_off = SA * Cfg::kAUnitBytes;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tiles = p.Cout / BLOCK_N;
+
+    if (warp == 0 && lane == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(wsrow + c0 + j) =
-                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                        __uint_as_float(v[j + 3]));
-                } else if (valid) {
+        for (int q = 0; q < Cfg::kParts; ++q) {
+            tma_prefetch_desc(&tm.a[q]);
+            tma_prefetch_desc(&tm.b[q]);
+        }
+        for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ===================== activation-slab producer =====================
+        const bool leader = elect_one();
+        {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int m_tile = tile / n_tiles;
+                const int tw = m_tile % p.tiles_w;
+                m_tile /= p.tiles_w;
+                const int th = m_tile % p.tiles_h;
+                const int n = m_tile / p.tiles_h;
+                const int w0 = tw * 8, h0 = th * Cfg::kPH;
+                for (int cb = 0; cb < p.cblks; ++cb) {
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        mbar_wait(&a_empty[stage], phase ^ 1u);
+                        uint8_t* sa = smem_al + stage * Cfg::kAUnitBytes;
+                        if (leader) {
+                            mbar_expect_tx(&a_full[stage], Cfg::kAUnitBytes);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 o;
-                        o.x = __uint_as_float(v[j + 0]) * oscale;
-                        o.y = __uint_as_float(v[j + 1]) * oscale;
-                        o.z = __uint_as_float(v[j + 2]) * oscale;
-                        o.w = __uint_as_float(v[j + 3]) * oscale;
-                        if (brow) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(brow + c0 + j));
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                            for (int q = 0; q < Cfg::kParts; ++q)
+                                tma_load_4d(sa + q * Cfg::kSlabBytes, &tm.a[q], &a_full[stage], cb * Cfg::kChanPerRow,
+                                            w0 + dx, h0 - 1, n);
                         }
-                        if (rrow) {
-                            const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + c0 + j));
-                            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                        }
-                        if (p.relu) {
-                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                        }
-                        if (p.round_out) {
-                            o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
-                        }
-                        *reinterpret_cast<float4*>(yrow + c0 + j) = o;
-                        if (p.y_split) {   // (hi, lo) bf16 planes of the same values, for a following bf16x3 conv
-                            __nv_bfloat16* sp = p.y_split + pix * p.Cout + n_tile * BLOCK_N + c0 + j;
-                            const __nv_bfloat16 h0 = __float2bfloat16_rn(o.x), h1 = __float2bfloat16_rn(o.y),
-                                                h2 = __float2bfloat16_rn(o.z), h3 = __float2bfloat16_rn(o.w);
-                            __nv_bfloat162 hi01 = __halves2bfloat162(h0, h1), hi23 = __halves2bfloat162(h2, h3);
-                            __nv_bfloat162 lo01 = __halves2bfloat162(__float2bfloat16_rn(o.x - __bfloat162float(h0)),
-                                                                     __float2bfloat16_rn(o.y - __bfloat162float(h1)));
-                            __nv_bfloat162 lo23 = __halves2bfloat162(__float2bfloat16_rn(o.z - __bfloat162float(h2)),
-                                                                     __float2bfloat16_rn(o.w - __bfloat162float(h3)));
-                            uint2 hv, lv;
-                            hv.x = *reinterpret_cast<uint32_t*>(&hi01); hv.y = *reinterpret_cast<uint32_t*>(&hi23);
-                            lv.x = *reinterpret_cast<uint32_t*>(&lo01); lv.y = *reinterpret_cast<uint32_t*>(&lo23);
-                            *reinterpret_cast<uint2*>(sp) = hv;
-                            *reinterpret_cast<uint2*>(sp + p.split_stride) = lv;
+                        if (++stage == SA) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ===================== weight-tile producer =====================
+        const bool leader = elect_one();
+        {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % n_tiles;
+                for (int cb = 0; cb < p.cblks; ++cb) {
+                    for (int dxi = 0; dxi < 3; ++dxi) {
+                        for (int dyi = 0; dyi < 3; ++dyi) {
+                            mbar_wait(&b_empty[stage], phase ^ 1u);
+                            uint8_t* sb = smem_al + b_ring_off + stage * Cfg::kBUnitBytes;
+                            const int kcoord = (dyi * 3 + dxi) * p.Cin + cb * Cfg::kChanPerRow;
+                            if (leader) {
+                                mbar_expect_tx(&b_full[stage], Cfg::kBUnitBytes);
+#pragma unroll
+                                for (int q = 0; q < Cfg::kParts; ++q)
+                                    tma_load_2d(sb + q * Cfg::kBPlaneBytes, &tm.b[q], &b_full[stage], kcoord,
+                                                n_tile * BLOCK_N);
+                            }
+                            if (++stage == SB) { stage = 0; phase ^= 1u; }
                         }
                     }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const bool leader = elect_one();
+        {
+            constexpr uint32_t idesc = MODE == 0 ? make_idesc_tf32(kBlockM, BLOCK_N, 0, 0)
+                                                 : make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+            const uint64_t desc_hi = make_smem_desc(0, 16, 1024, 2);
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int acc = Cfg::kAccBufs == 2 ? (it & 1) : 0;
+                const uint32_t acc_phase = Cfg::kAccBufs == 2 ? ((it >> 1) & 1) : (it & 1);
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_acc = tmem_base + acc * Cfg::kTileCols;
+                for (int cb = 0; cb < p.cblks; ++cb) {
+                    for (int dxi = 0; dxi < 3; ++dxi) {
+                        mbar_wait(&a_full[sa], pa);
+                        const uint32_t a_addr = smem_base + sa * Cfg::kAUnitBytes;
+                        for (int dyi = 0; dyi < 3; ++dyi) {
+                            mbar_wait(&b_full[sb], pb);
+                            tc_fence_after();
+                            const uint32_t b_addr = smem_base + b_ring_off + sb * Cfg::kBUnitBytes;
+                            const uint64_t db0 = desc_hi | ((b_addr >> 4) & 0x3FFFu);
+                            const uint32_t first = (cb | dxi | dyi) == 0 ? 0u : 1u;
+                            if (leader) {
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt) {
+                                const uint32_t a_tap = a_addr + (16 * mt + dyi) * 1024;
+                                const uint64_t da0 = desc_hi | ((a_tap >> 4) & 0x3FFFu);
+                                const uint32_t d = tmem_acc + mt * BLOCK_N;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint64_t da = da0 + 2 * k, db = db0 + 2 * k;
+                                    const uint32_t accum = k > 0 ? 1u : first;
+                                    if (MODE == 0) {
+                                        umma_tf32_ss(d, da, db, idesc, accum);
+                                    } else {
+                                        const uint64_t da_lo = da + (Cfg::kSlabBytes >> 4);
+                                        const uint64_t db_lo = db + (Cfg::kBPlaneBytes >> 4);
+                                        umma_f16_ss(d, da_lo, db, idesc, accum);   // Al * Bh
+                                        umma_f16_ss(d, da, db_lo, idesc, 1u);      // Ah * Bl
+                                        umma_f16_ss(d, da, db, idesc, 1u);         // Ah * Bh
+                                    }
+                                }
+                            }
+                            umma_commit(&b_empty[sb]);
+                            }
+                            if (++sb == SB) { sb = 0; pb ^= 1u; }
+                        }
+                        if (leader) umma_commit(&a_empty[sa]);
+                        if (++sa == SA) { sa = 0; pa ^= 1u; }
+                    }
+                }
+                if (leader) umma_commit(&tmem_full_bar[acc]);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;          // row of a 128-pixel sub-tile: 8 wide x 16 tall
+        const int wl = m & 7;
+        const int hl = m >> 3;
+        const float oscale = p.out_scale ? __ldg(p.out_scale) : 1.0f;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int acc = Cfg::kAccBufs == 2 ? (it & 1) : 0;
+            const uint32_t acc_phase = Cfg::kAccBufs == 2 ? ((it >> 1) & 1) : (it & 1);
+            const int n_tile = tile % n_tiles;
+            int m_tile = tile / n_tiles;
+            const int tw = m_tile % p.tiles_w;
+            m_tile /= p.tiles_w;
+            const int th = m_tile % p.tiles_h;
+            const int n = m_tile / p.tiles_h;
+            const float* brow = p.bias ? p.bias + n_tile * BLOCK_N : nullptr;
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt) {
+                const int h = th * Cfg::kPH + mt * 16 + hl, w = tw * 8 + wl;
+                const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
+                float* yrow = p.y + pix * p.Cout + n_tile * BLOCK_N;
+                const float* rrow = nullptr;
+                if (p.residual_mode == 1) {
+                    rrow = p.residual + pix * p.Cout + n_tile * BLOCK_N;
+                } else if (p.residual_mode == 2) {
+                    const size_t rp = (static_cast<size_t>(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+                    rrow = p.residual + rp * p.Cout + n_tile * BLOCK_N;
+                }
+                const uint32_t tmem_acc = tmem_base + acc * Cfg::kTileCols + mt * BLOCK_N +
+                                          (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_acc + c0, v);
+                    tmem_ld_wait();
+                    if (mt == MT - 1 && c0 + 32 >= BLOCK_N) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                    }
+                    epilogue_store_chunk(p, v, oscale, yrow, nullptr, rrow, brow, pix * p.Cout + n_tile * BLOCK_N, c0);
                 }
             }
         }
@@ -420,6 +683,58 @@ static int launch_conv(const ConvMaps& tm, ConvParams p, int m_tiles, int stages
     return B200LP_OK;
 }
 
+// ring depths of the halo kernel: the deepest slab ring (<= 4 slabs when they are small, else 3) that leaves room for
+// >= 4 weight tiles; returns false when even 2 + 2 do not fit.
+template <int BLOCK_N, int MT, int MODE>
+static bool halo_pick_stages(int& a_stages, int& b_stages) {
+    using Cfg = HaloCfg<BLOCK_N, MT, MODE>;
+    const int budget = Cfg::kMaxSmemBytes - 1024;
+    auto b_fit = [&](int a) {
+        int b = (budget - a * Cfg::kAUnitBytes) / Cfg::kBUnitBytes;
+        return b > Cfg::kMaxBStages ? Cfg::kMaxBStages : b;
+    };
+    if (a_stages <= 0) {
+        a_stages = 2;
+        for (int a = (Cfg::kAUnitBytes <= 20 * 1024 ? 4 : 3); a >= 2; --a)
+            if (b_fit(a) >= 4) { a_stages = a; break; }   // a deep weight ring matters more than a third slab (halo_tune)
+    }
+    if (a_stages > Cfg::kMaxAStages) a_stages = Cfg::kMaxAStages;
+    const int bmax = b_fit(a_stages);
+    if (bmax < 2) return false;
+    if (b_stages <= 0 || b_stages > bmax) b_stages = bmax;
+    return true;
+}
+
+template <int BLOCK_N, int MT, int MODE>
+static int launch_halo(const ConvMaps& tm, ConvParams p, int a_stages, int b_stages, cudaStream_t stream) {
+    using Cfg = HaloCfg<BLOCK_N, MT, MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200LP_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, MT, MODE>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmemBytes));
+        attr_set = true;
+    }
+    B200LP_REQUIRE((halo_pick_stages<BLOCK_N, MT, MODE>(a_stages, b_stages)),
+                   "conv_fwd: halo rings (%d slabs, block_n %d, variant %d) do not fit shared memory", a_stages, BLOCK_N, MT);
+    p.a_stages = a_stages;
+    p.b_stages = b_stages;
+    p.tiles_w = p.W / 8;
+    p.tiles_h = p.H / Cfg::kPH;
+    p.total_tiles = p.tiles_w * p.tiles_h * p.N * (p.Cout / BLOCK_N);
+    const int smem_bytes = a_stages * Cfg::kAUnitBytes + b_stages * Cfg::kBUnitBytes + 1024;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        B200LP_CHECK_CUDA(cudaGetDevice(&dev));
+        B200LP_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int grid = num_sms < p.total_tiles ? num_sms : p.total_tiles;
+    conv_halo_kernel<BLOCK_N, MT, MODE><<<grid, kHaloThreads, smem_bytes, stream>>>(tm, p);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
+
 }  // namespace b200lp
 
 using namespace b200lp;
@@ -449,6 +764,26 @@ static int conv_splits(const b200lp_conv_args* a, int block_n, int m_tiles) {
     if (s > num_kb) s = num_kb;
     const int per = (num_kb + s - 1) / s;
     return (num_kb + per - 1) / per;      // no empty split
+}
+
+// Halo-kernel sub-tiles per CTA (0 = use the per-tap kernel).  Auto: 3x3 layers on planes >= 16 x 8 that are not split
+// along K; the largest MT whose accumulators fit TMEM (MT x block_n <= 512 columns, double-buffered when <= 256; bf16x3:
+// slab pairs must fit the shared memory too) while the layer still has >= 3 tiles per SM, so that wave quantisation
+// stays below ~25 %.
+static int conv_halo_mt(const b200lp_conv_args* a, int block_n, int splits) {
+    if (a->variant < 0 || a->ksize != 3 || a->W < 8 || a->H < 16 || splits != 1) return 0;
+    if (a->variant > 0) {
+        const int mt = a->variant;
+        if ((mt != 1 && mt != 2 && mt != 4) || a->H % (16 * mt)) return -1;
+        return mt;
+    }
+    int mt_max;
+    if (a->precision == 0) mt_max = block_n >= 128 ? 2 : 4;   // block_n 256 x 2: one (not double-buffered) accumulator set
+    else mt_max = block_n >= 128 ? 1 : 2;
+    const long tiles128 = static_cast<long>(a->N) * (a->H / 16) * (a->W / 8) * (a->Cout / block_n);
+    int mt = mt_max;
+    while (mt > 1 && (a->H % (16 * mt) || tiles128 / mt < 3 * 148)) mt >>= 1;
+    return mt;
 }
 
 extern "C" int64_t b200lp_conv_fwd_workspace(const b200lp_conv_args* a) {
@@ -516,6 +851,10 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
     }
     p.kb_per_split = (p.num_kb + p.splits - 1) / p.splits;
 
+    const int halo_mt = conv_halo_mt(a, block_n, p.splits);
+    B200LP_REQUIRE(halo_mt >= 0, "conv_fwd: variant %d needs a 3x3 layer with W >= 8, H %% (16 * variant) == 0, no split-K",
+                   a->variant);
+
     ConvMaps tm;
     const uint64_t ktot = (uint64_t)a->ksize * a->ksize * a->Cin;
     const int parts = mode == 0 ? 1 : 2;
@@ -524,7 +863,10 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
             const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
             const uint64_t strides[3] = {(uint64_t)a->Cin * elem_bytes, (uint64_t)a->W * a->Cin * elem_bytes,
                                          (uint64_t)a->H * a->W * a->Cin * elem_bytes};
-            const uint32_t box[4] = {(uint32_t)chan_per_row, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)bn_box};
+            // per-tap kernel: one 128-pixel patch per box; halo kernel: one 8 x (16*MT + 2) column-shifted slab
+            const uint32_t box_tap[4] = {(uint32_t)chan_per_row, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)bn_box};
+            const uint32_t box_halo[4] = {(uint32_t)chan_per_row, 8u, (uint32_t)(16 * halo_mt + 2), 1u};
+            const uint32_t* box = halo_mt ? box_halo : box_tap;
             const char* base = static_cast<const char*>(a->x) +
                                (size_t)q * a->N * a->H * a->W * a->Cin * elem_bytes;   // lo plane follows hi plane
             int r = encode_tmap(&tm.a[q], base, mode == 0 ? kTmapF32 : kTmapBF16, 4, dims, strides, box, false);
@@ -542,6 +884,20 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
     if (mode == 0) { tm.a[1] = tm.a[0]; tm.b[1] = tm.b[0]; }
     cudaStream_t s = as_stream(stream);
     const int st = a->stages, cps = a->ctas_per_sm;
+    if (halo_mt) {
+        const int ast = a->a_stages;
+#define B200LP_HALO_CASE(BN, MT, MODE) \
+    if (block_n == BN && halo_mt == MT && mode == MODE) return launch_halo<BN, MT, MODE>(tm, p, ast, st, s);
+        B200LP_HALO_CASE(256, 1, 0) B200LP_HALO_CASE(256, 2, 0)
+        B200LP_HALO_CASE(128, 1, 0) B200LP_HALO_CASE(128, 2, 0)
+        B200LP_HALO_CASE(64, 1, 0) B200LP_HALO_CASE(64, 2, 0) B200LP_HALO_CASE(64, 4, 0)
+        B200LP_HALO_CASE(32, 1, 0) B200LP_HALO_CASE(32, 2, 0) B200LP_HALO_CASE(32, 4, 0)
+        B200LP_HALO_CASE(128, 1, 1) B200LP_HALO_CASE(128, 2, 1)
+        B200LP_HALO_CASE(64, 1, 1) B200LP_HALO_CASE(64, 2, 1)
+        B200LP_HALO_CASE(32, 1, 1) B200LP_HALO_CASE(32, 2, 1)
+#undef B200LP_HALO_CASE
+        B200LP_REQUIRE(false, "conv_fwd: no halo kernel for block_n %d, variant %d, precision %d", block_n, halo_mt, mode);
+    }
     if (mode == 0) {
         switch (block_n) {
             case 256: return launch_conv<256, 0>(tm, p, m_tiles, st, cps, s);
@@ -592,6 +948,48 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, const float
         }
     }
 }
+
+// Multi-tensor variant: every conv weight of a network re-packed by ONE launch after the optimizer step (the step has
+// ~100 packed copies: forward + transposed, tf32 + bf16 planes; one 16-us launch each was 5 % of the step).
+struct PackItem {
+    const float* w;     // OIHW source
+    void* wp;           // packed destination
+    long long Cout, Cin, taps, transpose, precision, total;
+};
+
+__device__ __forceinline__ float pack_gather(const float* __restrict__ w, long i, int Cout, int Cin, int taps, int transpose) {
+    if (!transpose) {
+        const int ci = i % Cin;
+        const int tap = (i / Cin) % taps;
+        const int co = i / (static_cast<long>(Cin) * taps);
+        return w[(static_cast<long>(co) * Cin + ci) * taps + tap];
+    }
+    const int co = i % Cout;
+    const int tapf = (i / Cout) % taps;
+    const int ci = i / (static_cast<long>(Cout) * taps);
+    return w[(static_cast<long>(co) * Cin + ci) * taps + (taps - 1 - tapf)];
+}
+
+__global__ void __launch_bounds__(256)
+pack_conv_weight_multi_kernel(const PackItem* __restrict__ table, const int* __restrict__ chunk_item,
+                              const long long* __restrict__ chunk_off, long long chunk_elems) {
+    const PackItem it = table[chunk_item[blockIdx.x]];
+    const long off = chunk_off[blockIdx.x];
+    long end = off + chunk_elems;
+    if (end > it.total) end = it.total;
+    const int Cout = static_cast<int>(it.Cout), Cin = static_cast<int>(it.Cin), taps = static_cast<int>(it.taps);
+    for (long i = off + threadIdx.x; i < end; i += 256) {
+        const float f = pack_gather(it.w, i, Cout, Cin, taps, static_cast<int>(it.transpose));
+        if (it.precision == 0) {
+            static_cast<float*>(it.wp)[i] = round_tf32(f);
+        } else {
+            __nv_bfloat16* out = static_cast<__nv_bfloat16*>(it.wp);
+            const __nv_bfloat16 h = __float2bfloat16_rn(f);
+            out[i] = h;
+            out[it.total + i] = __float2bfloat16_rn(f - __bfloat162float(h));
+        }
+    }
+}
 }  // namespace b200lp
 
 extern "C" int32_t b200lp_pack_conv_weight(const float* w_oihw, const float* scale, void* wp_out, int32_t Cout,
@@ -609,6 +1007,19 @@ extern "C" int32_t b200lp_pack_conv_weight(const float* w_oihw, const float* sca
     else
         pack_conv_weight_kernel<true><<<(int)blocks, threads, 0, as_stream(stream)>>>(w_oihw, scale, wp, Cout, Cin,
                                                                                     ksize * ksize, transpose);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_pack_conv_weight_multi(const void* table_dev, const int32_t* chunk_item_dev,
+                                                 const int64_t* chunk_off_dev, int32_t n_chunks, int64_t chunk_elems,
+                                                 void* stream) {
+    B200LP_REQUIRE(table_dev && chunk_item_dev && chunk_off_dev && n_chunks > 0 && chunk_elems > 0,
+                   "pack_conv_weight_multi: bad args");
+    pack_conv_weight_multi_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(
+        static_cast<const PackItem*>(table_dev), chunk_item_dev, reinterpret_cast<const long long*>(chunk_off_dev),
+        chunk_elems);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

@@ -90,7 +90,10 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     const uint32_t tmem_base = tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        // warp-uniform loop, one elected lane issues (see conv_igemm.cu: a divergent `if (lane == 0)` costs an
+        // ELECT/branch loop per TMA and MMA instruction)
+        const bool leader = elect_one();
+        {
             const int pad = p.ksize >> 1;
             // the four 32-row blocks of this M tile: (tap shift, channel block); blocks past the end are skipped
             int blk_dx[4], blk_dy[4], blk_c[4];
@@ -120,19 +123,22 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
                 uint8_t* sa = smem_al + stage * kStageBytes;
                 uint8_t* sb = sa + kABytes;
-                mbar_expect_tx(&full_bar[stage], tx_bytes);
-                for (int j = 0; j < nvalid; ++j)
-                    tma_load_4d(sa + j * kWgBlkBytes, &tmX, &full_bar[stage], blk_c[j], w0 + blk_dx[j],
-                                h0 + blk_dy[j], n0);
+                if (leader) {
+                    mbar_expect_tx(&full_bar[stage], tx_bytes);
+                    for (int j = 0; j < nvalid; ++j)
+                        tma_load_4d(sa + j * kWgBlkBytes, &tmX, &full_bar[stage], blk_c[j], w0 + blk_dx[j],
+                                    h0 + blk_dy[j], n0);
 #pragma unroll
-                for (int j = 0; j < BLOCK_N / 32; ++j)
-                    tma_load_4d(sb + j * kWgBlkBytes, &tmDY, &full_bar[stage], n_tile * BLOCK_N + j * 32, w0, h0,
-                                n0);
+                    for (int j = 0; j < BLOCK_N / 32; ++j)
+                        tma_load_4d(sb + j * kWgBlkBytes, &tmDY, &full_bar[stage], n_tile * BLOCK_N + j * 32, w0, h0,
+                                    n0);
+                }
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        const bool leader = elect_one();
+        {
             constexpr uint32_t idesc = make_idesc_tf32(kWgM, BLOCK_N, 1, 1);  // both operands MN-major
             int stage = 0;
             uint32_t phase = 0;
@@ -142,7 +148,7 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 const uint32_t a_addr = smem_base + stage * kStageBytes;
                 const uint32_t b_addr = a_addr + kABytes;
                 const int kiters = p.kstep >> 3;
-                for (int k = 0; k < kiters; ++k) {
+                for (int k = 0; leader && k < kiters; ++k) {
                     // MN-major 32-bit operands must use SWIZZLE_128B_BASE32B (layout type 1): atoms of 4 K-rows x 128 B;
                     // LBO = stride between 32-channel blocks, SBO = stride between 4-row K groups (512 B);
                     // one K=8 MMA spans two atoms, so stepping K by 8 = +1024 bytes.
@@ -150,10 +156,10 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     const uint64_t db = make_smem_desc(b_addr + k * 1024, kWgBlkBytes, 512, 1);
                     umma_tf32_ss(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit(&empty_bar[stage]);
+                if (leader) umma_commit(&empty_bar[stage]);
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
-            umma_commit(&tmem_full_bar);
+            if (leader) umma_commit(&tmem_full_bar);
         }
     } else {
         const int quarter = warp & 3;
@@ -218,9 +224,12 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int ksize, WgPlan*
     // enough K (and the tile is not already 48 KB per 32 pixels)
     // (measured on B200, profiles/r01_conv_wgrad_tuning_sweep.log: 32-pixel stages with shallow rings — more CTAs per
     //  SM — beat 64-pixel stages on every shape of the step except one tie)
-    int kstep = kstep_req ? kstep_req : 32;
+    //  After the elected-lane issue fix (profiles/r01_kernel_diag_elect_issue.log) Cout <= 64 tiles prefer 64-pixel stages in
+    //  a 2-deep ring (336 vs 277 TFLOP/s at 64->64 @256x256); the wider tiles keep 32-pixel stages.
+    int kstep = kstep_req ? kstep_req : (pl->block_n <= 64 ? 64 : 32);
     if (kstep != 32 && kstep != 64) return -1;
     if (static_cast<long>(N) * H * W < kstep) kstep = 32;
+    if (!kstep_req && kstep == 64 && static_cast<long>(H) * W < 64 && N % (64 / (H * W))) kstep = 32;   // ragged batch
     pl->kstep = kstep;
     pl->pw = W < kstep ? W : kstep;
     pl->ph = (kstep / pl->pw) < H ? (kstep / pl->pw) : H;
@@ -228,7 +237,7 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int ksize, WgPlan*
     const int steps_n = (N + pl->pn - 1) / pl->pn;
     pl->total_steps = (W / pl->pw) * (H / pl->ph) * steps_n;
     const int stage_bytes = (4 + pl->block_n / 32) * kstep * 128;
-    int stages = stages_req ? stages_req : (pl->block_n == 256 ? 2 : 3);   // <= ~100 KB per CTA: two CTAs share an SM
+    int stages = stages_req ? stages_req : ((pl->block_n == 256 || kstep == 64) ? 2 : 3);   // <= ~100 KB per CTA: two CTAs share an SM
     if (stages > kWgMaxStages) stages = kWgMaxStages;
     while (stages > 1 && stages * stage_bytes + 1024 > kWgMaxSmem) --stages;
     pl->stages = stages;

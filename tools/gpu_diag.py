@@ -38,7 +38,7 @@ def _err(a, b):
             "rel": (d.max() / (b.abs().max() + 1e-30)).item(), "nan": bool(torch.isnan(a).any().item())}
 
 
-def _conv_case(N, H, W, Cin, Cout, k, block_n=0, bias=False, residual_mode=0, relu=False):
+def _conv_case(N, H, W, Cin, Cout, k, block_n=0, bias=False, residual_mode=0, relu=False, **kw):
     import torch
     import torch.nn.functional as F
     from b200lp import kernels as K
@@ -60,10 +60,10 @@ def _conv_case(N, H, W, Cin, Cout, k, block_n=0, bias=False, residual_mode=0, re
     if relu:
         ref = ref.relu()
     xh = x.permute(0, 2, 3, 1).contiguous()
-    y = K.conv_fwd(xh, wp, k, bias=b, residual=res, residual_mode=residual_mode, relu=relu, block_n=block_n)
+    y = K.conv_fwd(xh, wp, k, bias=b, residual=res, residual_mode=residual_mode, relu=relu, block_n=block_n, **kw)
     torch.cuda.synchronize()
     e = _err(y.permute(0, 3, 1, 2), ref)
-    e["case"] = f"N{N} H{H} W{W} Cin{Cin} Cout{Cout} k{k} bn{block_n} bias{int(bias)} res{residual_mode} relu{int(relu)}"
+    e["case"] = f"N{N} H{H} W{W} Cin{Cin} Cout{Cout} k{k} bn{block_n} bias{int(bias)} res{residual_mode} relu{int(relu)} {kw or ''}"
     e["ok"] = (not e["nan"]) and e["rel"] < 2e-5
     return e
 
@@ -133,7 +133,7 @@ def split_bf16(t):
     return torch.stack((hi, lo)).contiguous()
 
 
-def _conv_bf16x3_case(N, H, W, Cin, Cout, k, emit_split=False, residual_mode=0):
+def _conv_bf16x3_case(N, H, W, Cin, Cout, k, emit_split=False, residual_mode=0, **kw):
     import torch
     import torch.nn.functional as F
     from b200lp import kernels as K
@@ -148,11 +148,11 @@ def _conv_bf16x3_case(N, H, W, Cin, Cout, k, emit_split=False, residual_mode=0):
         res = torch.randn(N, H // 2, W // 2, Cout, device="cuda")
         ref = ref + F.interpolate(res.permute(0, 3, 1, 2).double(), scale_factor=2, mode="nearest")
     xs = split_bf16(x.permute(0, 2, 3, 1).contiguous())
-    out = K.conv_fwd(xs, wp, k, residual=res, residual_mode=residual_mode, emit_split=emit_split)
+    out = K.conv_fwd(xs, wp, k, residual=res, residual_mode=residual_mode, emit_split=emit_split, **kw)
     torch.cuda.synchronize()
     y, ysp = out if emit_split else (out, None)
     e = _err(y.permute(0, 3, 1, 2), ref)
-    e["case"] = f"bf16x3 N{N} H{H} Cin{Cin} Cout{Cout} k{k} res{residual_mode}"
+    e["case"] = f"bf16x3 N{N} H{H} Cin{Cin} Cout{Cout} k{k} res{residual_mode} {kw or ''}"
     e["ok"] = (not e["nan"]) and e["rel"] < 5e-5
     outs = [e]
     if emit_split:
@@ -515,6 +515,127 @@ def fused_optim():
              "max_abs": 0.0, "rel": 0.0, "nan": False, "ref_max": 8.0}
         out.append(e)
     return out
+
+
+@check
+def conv_halo():
+    """Halo kernel (column-shifted slabs, MT accumulators per weight tile) forced on small and full-size layers: every
+    (block_n, MT, precision) instantiation, image borders, non-square planes, every epilogue option, ring depths."""
+    out = []
+    h = dict(splits=1)
+    for mt in (1, 2, 4):
+        out.append(_conv_case(2, 64, 32, 64, 64, 3, variant=mt, **h))
+        out.append(_conv_case(1, 64, 8, 32, 32, 3, variant=mt, bias=True, relu=True, **h))
+        out.append(_conv_case(3, 64, 16, 96, 64, 3, block_n=32, variant=mt, residual_mode=2, **h))
+    for mt in (1, 2):
+        out.append(_conv_case(2, 32, 32, 128, 128, 3, variant=mt, residual_mode=1, bias=True, **h))
+        out += _conv_bf16x3_case(2, 32, 16, 128, 64, 3, emit_split=True, residual_mode=2, variant=mt, **h)
+        out += _conv_bf16x3_case(1, 32, 32, 64, 128, 3, variant=mt, **h)
+        out += _conv_bf16x3_case(1, 32, 8, 64, 32, 3, variant=mt, **h)
+    out.append(_conv_case(1, 16, 16, 256, 256, 3, variant=1, **h))
+    out.append(_conv_case(2, 16, 8, 64, 512, 3, block_n=256, variant=1, bias=True, **h))
+    out.append(_conv_case(3, 64, 8, 64, 256, 3, block_n=256, variant=2, residual_mode=1, relu=True, **h))
+    out.append(_conv_case(2, 32, 32, 64, 64, 3, variant=2, a_stages=2, stages=2, **h))
+    out.append(_conv_case(2, 32, 32, 64, 128, 3, variant=1, a_stages=6, stages=8, **h))
+    # full-size layers through the automatic choice (halo), vs the per-tap kernel on the same inputs
+    out += [_conv_case(8, 256, 256, 64, 64, 3), _conv_case(8, 128, 128, 128, 128, 3, relu=True, bias=True),
+            _conv_case(8, 64, 64, 512, 256, 3), _conv_case(8, 32, 32, 512, 512, 3, residual_mode=2)]
+    out += _conv_bf16x3_case(8, 128, 128, 128, 128, 3) + _conv_bf16x3_case(4, 256, 256, 128, 64, 3, emit_split=True)
+    return out
+
+
+def _time_us(fn, reps=8, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+@check
+def halo_tune():
+    """TFLOP/s of the halo kernel vs (block_n, MT, slab ring, weight ring) and of the per-tap kernel, dominant shapes."""
+    import torch
+    from b200lp import kernels as K
+    out = []
+    shapes = [(8, 256, 256, 64, 64), (8, 256, 256, 128, 64), (8, 128, 128, 128, 128), (8, 128, 128, 256, 128),
+              (8, 64, 64, 256, 256), (8, 64, 64, 512, 256), (8, 32, 32, 512, 512)]
+    for (N, H, W, Cin, Cout) in shapes:
+        x = torch.randn(N, H, W, Cin, device="cuda")
+        wp = K.pack_conv_weight(torch.randn(Cout, Cin, 3, 3, device="cuda"))
+        y = torch.empty(N, H, W, Cout, device="cuda")
+        flops = 2.0 * N * H * W * Cin * Cout * 9
+        rec = {"case": f"tf32 N{N} H{H} Cin{Cin} Cout{Cout}", "ok": True}
+        rec["per_tap"] = round(flops / _time_us(lambda: K.conv_fwd(x, wp, 3, out=y, variant=-1)) / 1e6, 0)
+        rec["auto"] = round(flops / _time_us(lambda: K.conv_fwd(x, wp, 3, out=y)) / 1e6, 0)
+        for bn in (64, 128, 256):
+            if Cout % bn:
+                continue
+            for mt in (1, 2, 4):
+                if bn * mt > 512:
+                    continue
+                for (sa, sb) in ((0, 0), (2, 0), (3, 0), (4, 0)):
+                    try:
+                        us = _time_us(lambda: K.conv_fwd(x, wp, 3, out=y, block_n=bn, variant=mt, a_stages=sa, stages=sb,
+                                                         splits=1))
+                        rec[f"bn{bn}_mt{mt}_a{sa}"] = round(flops / us / 1e6, 0)
+                    except Exception as err:
+                        rec[f"bn{bn}_mt{mt}_a{sa}"] = "n/a"
+        out.append(rec)
+    for (N, H, W, Cin, Cout) in [(8, 256, 256, 128, 64), (8, 256, 256, 64, 64), (8, 128, 128, 128, 128), (8, 128, 128, 256, 128),
+                                 (8, 64, 64, 256, 256)]:
+        xs = split_bf16(torch.randn(N, H, W, Cin, device="cuda"))
+        wp = K.pack_conv_weight(torch.randn(Cout, Cin, 3, 3, device="cuda"), precision=K.BF16X3)
+        y = torch.empty(N, H, W, Cout, device="cuda")
+        flops = 2.0 * N * H * W * Cin * Cout * 9
+        rec = {"case": f"bf16x3 N{N} H{H} Cin{Cin} Cout{Cout}", "ok": True}
+        rec["per_tap"] = round(flops / _time_us(lambda: K.conv_fwd(xs, wp, 3, out=y, variant=-1)) / 1e6, 0)
+        rec["auto"] = round(flops / _time_us(lambda: K.conv_fwd(xs, wp, 3, out=y)) / 1e6, 0)
+        for bn in (64, 128):
+            if Cout % bn:
+                continue
+            for mt in (1, 2):
+                for sa in (0, 2, 3):
+                    try:
+                        us = _time_us(lambda: K.conv_fwd(xs, wp, 3, out=y, block_n=bn, variant=mt, a_stages=sa, splits=1))
+                        rec[f"bn{bn}_mt{mt}_a{sa}"] = round(flops / us / 1e6, 0)
+                    except Exception as err:
+                        rec[f"bn{bn}_mt{mt}_a{sa}"] = "n/a"
+        out.append(rec)
+    return out
+
+
+@check
+def pack_multi():
+    """One multi-tensor launch == the per-tensor packing kernel, bit for bit (forward / transposed, tf32 / bf16 planes)."""
+    import torch
+    from b200lp import kernels as K
+    torch.manual_seed(3)
+    ws = [torch.randn(64, 32, 3, 3, device="cuda"), torch.randn(128, 64, 1, 1, device="cuda"),
+          torch.randn(512, 256, 3, 3, device="cuda"), torch.randn(32, 96, 3, 3, device="cuda")]
+    rows, refs, outs = [], [], []
+    for w in ws:
+        for tr in (False, True):
+            for prec in (K.TF32, K.BF16X3):
+                ref = K.pack_conv_weight(w, None, transpose=tr, precision=prec)
+                out = torch.zeros_like(ref)
+                co, ci, kh, kw = w.shape
+                rows.append((w.data_ptr(), out.data_ptr(), co, ci, kh * kw, int(tr), prec, w.numel()))
+                refs.append(ref); outs.append(out)
+    K.pack_conv_weight_multi(K.pack_plan(rows, "cuda"))
+    torch.cuda.synchronize()
+    res = []
+    for r, ref, out in zip(rows, refs, outs):
+        same = bool(torch.equal(ref.view(torch.int16 if ref.dtype == torch.bfloat16 else torch.int32),
+                                out.view(torch.int16 if out.dtype == torch.bfloat16 else torch.int32)))
+        res.append({"case": f"Cout{r[2]} Cin{r[3]} taps{r[4]} transpose{r[5]} precision{r[6]}", "ok": same,
+                    "max_abs": 0.0 if same else 1.0, "rel": 0.0 if same else 1.0, "nan": False, "ref_max": 1.0})
+    return res
 
 
 @check
