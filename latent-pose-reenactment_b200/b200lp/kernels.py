@@ -39,17 +39,19 @@ def _ws(nbytes, device):
 TF32, BF16X3 = 0, 1   # operand precisions of the tensor-core convolution (include/b200lp.h: `precision`)
 
 
-def pack_conv_weight(w_oihw, scale=None, transpose=False, precision=TF32):
+def pack_conv_weight(w_oihw, scale=None, transpose=False, precision=TF32, out=None):
     """OIHW fp32 -> packed [Cout][tap][Cin] (or [Cin][tap'][Cout] when transpose), times *scale (device scalar):
-    float32 holding tf32 values (precision TF32) or bfloat16 (2, ...) = (hi, lo) planes (precision BF16X3)."""
+    float32 holding tf32 values (precision TF32) or bfloat16 (2, ...) = (hi, lo) planes (precision BF16X3).
+    `out`: re-pack into an existing buffer of the right shape."""
     lib = L.load()
     co, ci, kh, kw = w_oihw.shape
     assert kh == kw and kh in (1, 3)
     shape = (ci, kh * kw, co) if transpose else (co, kh * kw, ci)
-    if precision == TF32:
-        out = torch.empty(shape, dtype=torch.float32, device=w_oihw.device)
-    else:
-        out = torch.empty((2,) + shape, dtype=torch.bfloat16, device=w_oihw.device)
+    if precision != TF32:
+        shape = (2,) + shape
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32 if precision == TF32 else torch.bfloat16, device=w_oihw.device)
+    assert tuple(out.shape) == shape and out.is_contiguous(), (out.shape, shape)
     with _timed("pack_conv_weight", nbytes=8.0 * w_oihw.numel()):
         L.check(lib.b200lp_pack_conv_weight(L.ptr(w_oihw.contiguous()), L.ptr(scale), c_void_p(out.data_ptr()), co, ci,
                                             kh, 1 if transpose else 0, precision, L.stream_ptr()), "pack_conv_weight")

@@ -16,12 +16,24 @@ def _dot(a, b):
 
 
 _GENERATION = [0]
+_PTR_GENERATION = {}
 
 
-def bump_generation():
+def bump_generation(params=None):
     """Call after weights were modified through raw pointers (fused optimizer / EMA kernels, CUDA-graph replays):
-    those writes do not touch torch's per-tensor version counters, so every cached packed copy is invalidated here."""
-    _GENERATION[0] += 1
+    those writes do not touch torch's per-tensor version counters, so the cached packed copies are invalidated here —
+    those of `params` (keyed by storage pointer) or, without arguments, all of them."""
+    if params is None:
+        _GENERATION[0] += 1
+        return
+    for p in params:
+        ptr = p.data_ptr()
+        _PTR_GENERATION[ptr] = _PTR_GENERATION.get(ptr, 0) + 1
+
+
+def _stamp(weight):
+    ptr = weight.data_ptr()
+    return (_GENERATION[0], _PTR_GENERATION.get(ptr, 0), weight._version, ptr)
 
 
 class PackCache:
@@ -43,10 +55,12 @@ class PackCache:
     def get(self, weight, transpose, precision):
         key = (transpose, precision)
         hit = self.entries.get(key)
-        stamp = (_GENERATION[0], weight._version, weight.data_ptr())
+        stamp = _stamp(weight)
         if hit is not None and hit[0] == stamp:
             return hit[1]
-        packed = K.pack_conv_weight(weight.detach(), None, transpose=transpose, precision=precision)
+        # a stale copy is refreshed IN PLACE: its address is baked into captured CUDA graphs and repack tables
+        reuse = hit[1] if hit is not None and hit[2] == tuple(weight.shape) and hit[1].device == weight.device else None
+        packed = K.pack_conv_weight(weight.detach(), None, transpose=transpose, precision=precision, out=reuse)
         self.entries[key] = (stamp, packed, tuple(weight.shape))
         return packed
 
@@ -63,11 +77,11 @@ def repack_weights(params, owner=None):
     rows, hits = [], []
     for cache in list(PackCache._live):
         for key, (stamp, packed, shape) in cache.entries.items():
-            w = by_ptr.get(stamp[2])
+            w = by_ptr.get(stamp[3])
             if w is None or tuple(w.shape) != shape:
                 continue
             co, ci, kh, kw = shape
-            rows.append((stamp[2], packed.data_ptr(), co, ci, kh * kw, int(key[0]), int(key[1]), w.numel()))
+            rows.append((stamp[3], packed.data_ptr(), co, ci, kh * kw, int(key[0]), int(key[1]), w.numel()))
             hits.append((cache, key, packed, shape, w))
     if not rows:
         return 0
@@ -75,13 +89,17 @@ def repack_weights(params, owner=None):
     plan = _REPACK_PLANS.get(owner)
     if plan is None or plan["sig"] != sig:
         if torch.cuda.is_current_stream_capturing():
-            return 0                     # table upload is not capturable: the lazy per-tensor path packs on first use
+            # the table upload is not capturable: refresh copy by copy (same kernels as the lazy path)
+            for cache, key, packed, shape, w in hits:
+                K.pack_conv_weight(w.detach(), None, transpose=key[0], precision=key[1], out=packed)
+                cache.entries[key] = (_stamp(w), packed, shape)
+            return len(rows)
         plan = K.pack_plan(rows, hits[0][4].device)
         plan["sig"] = sig
         _REPACK_PLANS[owner] = plan
     K.pack_conv_weight_multi(plan)
     for cache, key, packed, shape, w in hits:
-        cache.entries[key] = ((_GENERATION[0], w._version, w.data_ptr()), packed, shape)
+        cache.entries[key] = (_stamp(w), packed, shape)
     return len(rows)
 
 

@@ -107,7 +107,7 @@ class FusedAdamEMA(Optimizer):
             t['n_chunks'], CHUNK, L.ptr(t['state']), float(g['lr']), float(g['betas'][0]), float(g['betas'][1]),
             float(g['eps']), float(self.ema_alpha), self.MODE, int(self.degenerated_to_sgd), L.stream_ptr()),
             "adam_ema_multi")
-        ops.bump_generation()            # parameters changed behind torch's back: packed weight copies are stale
+        ops.bump_generation(t['params'])  # parameters changed behind torch's back: their packed copies are stale
         ops.repack_weights(t['params'], owner=id(self))   # ... and refreshed here by one multi-tensor launch
         return loss
 

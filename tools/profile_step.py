@@ -41,7 +41,7 @@ def main():
     n_kernels = sum(e.count for e in ka if e.self_device_time_total > 0)
     txt = [f"wall per step (no profiler): {wall * 1e3:.2f} ms", f"sum of device kernel time in one step: {cuda_total:.2f} ms",
            f"device-side launches in one step: {n_kernels}", "",
-           ka.table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=70)]
+           ka.table(sort_by="self_cuda_time_total", row_limit=80, max_name_column_width=90)]
     (out / "step_profile.txt").write_text("\n".join(txt))
     print("\n".join(txt[:3]))
 
