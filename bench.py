@@ -336,6 +336,19 @@ def drive_benchmark(device, batch=64, n_batches=6):
                     "(bf16x3), clamp+uint8, async D2H of the frames"}
 
 
+def shutdown_distributed():
+    """Leave a multi-rank run without touching NCCL again: the step's CUDA graph holds the communicator's captured
+    all-reduces, and tearing the process group down under it was observed to hang (2-GPU run, profiles/README.md).
+    Everything has been printed and synchronised by now, so the ranks just meet once more and exit."""
+    import sys
+    torch.cuda.synchronize()
+    torch.distributed.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -417,7 +430,7 @@ def main():
                               "ms_per_step": round(ms / args.steps, 3), "gpu_launches": int(launches),
                               "note": "timed-only run (profiling aid, not a bench line)"}))
         if dist_on:
-            torch.distributed.destroy_process_group()
+            shutdown_distributed()
         return
     for i in range(2):
         step_e2e(i)
@@ -470,9 +483,9 @@ def main():
         line.update(extra)
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist_on:
-        torch.distributed.destroy_process_group()
+        shutdown_distributed()
 
 
 if __name__ == "__main__":

@@ -359,12 +359,18 @@ struct HaloCfg {
     static constexpr int kAccBufs = 2 * kTileCols <= 512 ? 2 : 1;     // double-buffer when TMEM allows
     static constexpr uint32_t kTmemCols = kAccBufs * kTileCols < 32 ? 32 : kAccBufs * kTileCols;
     static_assert(kTileCols <= 512, "accumulators exceed TMEM");
+    // MMA-issuing warps: the issue loop (barrier wait, ~3 uniform-datapath instructions per descriptor, commit) costs about
+    // as many cycles as a 64-column MMA executes (ncu: the issuing warp never waits on data, 22 % MIO-queue stalls), so
+    // with MT >= 2 the sub-tiles are split between two issuing warps, each owning its accumulators (+12..23 %; four
+    // issuers at MT = 4 measured no further gain — profiles/r01_kernel_diag_halo_issuers.log).
+    static constexpr int kIssuers = MT >= 2 ? 2 : 1;
+    static constexpr int kThreads = 224 + 32 * (kIssuers - 1);
 };
 
-constexpr int kHaloThreads = 224;   // warp 0: slab producer, 1: MMA, 2..5: epilogue, 6: weight producer
+// warp 0: slab producer, 1: MMA issuer, 2..5: epilogue, 6: weight producer, 7: second MMA issuer (MT >= 2)
 
 template <int BLOCK_N, int MT, int MODE>
-__global__ void __launch_bounds__(kHaloThreads, 1)
+__global__ void __launch_bounds__(HaloCfg<BLOCK_N, MT, MODE>::kThreads, 1)
 conv_halo_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
     using Cfg = HaloCfg<BLOCK_N, MT, MODE>;
     extern __shared__ uint8_t smem_raw[];
@@ -391,9 +397,12 @@ conv_halo_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
             tma_prefetch_desc(&tm.a[q]);
             tma_prefetch_desc(&tm.b[q]);
         }
-        for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+        for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], Cfg::kIssuers); }
+        for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], Cfg::kIssuers); }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], Cfg::kIssuers);   // one commit per issuing warp
+            mbar_init(&tmem_empty_bar[a], 4);              // one arrival per epilogue warp
+        }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<Cfg::kTmemCols>(&tmem_slot);
@@ -458,9 +467,11 @@ conv_halo_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 || warp == 7) {
+        // ===================== MMA issuer(s) =====================
         const bool leader = elect_one();
+        constexpr int kMtPer = MT / Cfg::kIssuers;          // sub-tiles (accumulators) owned by this issuing warp
+        const int mt_first = warp == 1 ? 0 : kMtPer;
         {
             constexpr uint32_t idesc = MODE == 0 ? make_idesc_tf32(kBlockM, BLOCK_N, 0, 0)
                                                  : make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
@@ -486,7 +497,8 @@ conv_halo_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
                             const uint32_t first = (cb | dxi | dyi) == 0 ? 0u : 1u;
                             if (leader) {
 #pragma unroll
-                            for (int mt = 0; mt < MT; ++mt) {
+                            for (int j = 0; j < kMtPer; ++j) {
+                                const int mt = mt_first + j;
                                 const uint32_t a_tap = a_addr + (16 * mt + dyi) * 1024;
                                 const uint64_t da0 = desc_hi | ((a_tap >> 4) & 0x3FFFu);
                                 const uint32_t d = tmem_acc + mt * BLOCK_N;
@@ -729,7 +741,7 @@ static int launch_halo(const ConvMaps& tm, ConvParams p, int a_stages, int b_sta
         B200LP_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const int grid = num_sms < p.total_tiles ? num_sms : p.total_tiles;
-    conv_halo_kernel<BLOCK_N, MT, MODE><<<grid, kHaloThreads, smem_bytes, stream>>>(tm, p);
+    conv_halo_kernel<BLOCK_N, MT, MODE><<<grid, Cfg::kThreads, smem_bytes, stream>>>(tm, p);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;
@@ -767,9 +779,7 @@ static int conv_splits(const b200lp_conv_args* a, int block_n, int m_tiles) {
 }
 
 // Halo-kernel sub-tiles per CTA (0 = use the per-tap kernel).  Auto: 3x3 layers on planes >= 16 x 8 that are not split
-// along K; the largest MT whose accumulators fit TMEM (MT x block_n <= 512 columns, double-buffered when <= 256; bf16x3:
-// slab pairs must fit the shared memory too) while the layer still has >= 3 tiles per SM, so that wave quantisation
-// stays below ~25 %.
+// along K.
 static int conv_halo_mt(const b200lp_conv_args* a, int block_n, int splits) {
     if (a->variant < 0 || a->ksize != 3 || a->W < 8 || a->H < 16 || splits != 1) return 0;
     if (a->variant > 0) {
@@ -777,12 +787,16 @@ static int conv_halo_mt(const b200lp_conv_args* a, int block_n, int splits) {
         if ((mt != 1 && mt != 2 && mt != 4) || a->H % (16 * mt)) return -1;
         return mt;
     }
-    int mt_max;
-    if (a->precision == 0) mt_max = block_n >= 128 ? 2 : 4;   // block_n 256 x 2: one (not double-buffered) accumulator set
-    else mt_max = block_n >= 128 ? 1 : 2;
+    // measured (halo_tune): two sub-tiles sharing every weight tile win whenever >= ~100 CTA tiles remain (even below one
+    // tile per SM: 512->256 @64x64 runs 774 vs 742 TFLOP/s); four sub-tiles never beat two once both have two issuers.
+    // bf16x3 with block_n 128: the 68-KB slab pairs leave only a 2-deep ring, one sub-tile is faster.
+    // block_n 256 x 2 sub-tiles fills TMEM (no double buffering: the epilogue is exposed), which only pays with a long K
+    // loop: 512->256 yes (774 vs 742), 256->256 no (the step's VGG / discriminator 256-channel layers got 16 % slower).
+    int mt_max = (a->precision == 0 || block_n <= 64) ? 2 : 1;
+    if (block_n == 256 && a->Cin < 512) mt_max = 1;
     const long tiles128 = static_cast<long>(a->N) * (a->H / 16) * (a->W / 8) * (a->Cout / block_n);
     int mt = mt_max;
-    while (mt > 1 && (a->H % (16 * mt) || tiles128 / mt < 3 * 148)) mt >>= 1;
+    while (mt > 1 && (a->H % (16 * mt) || tiles128 / mt < 100)) mt >>= 1;
     return mt;
 }
 

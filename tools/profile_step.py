@@ -12,7 +12,7 @@ from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
 
 def main():
-    wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "finetune"]
+    wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "finetune"]
     device = "cuda:0"
     torch.cuda.set_device(0)
     runner, tm, opt_G, opt_D, ns = bench.build_training(wl, device, 8)
@@ -31,9 +31,22 @@ def main():
         step(i)
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / 5
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    stacks = "--stacks" in sys.argv
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=stacks, record_shapes=stacks) as prof:
         step(0)
         torch.cuda.synchronize()
+    if stacks:      # who issues the small torch glue ops (copy_, add_, mul, fill_)?
+        rows = []
+        for e in prof.key_averages(group_by_stack_n=12):
+            if e.key in ("aten::copy_", "aten::add_", "aten::mul", "aten::fill_", "aten::add", "aten::zero_", "aten::clone"):
+                user = [f for f in e.stack if "site-packages" not in f and "profile_step" not in f][:3]
+                rows.append((e.count, e.key, " <- ".join(x.strip()[-90:] for x in user)))
+        for e in prof.key_averages(group_by_input_shape=True):
+            if e.key in ("aten::copy_", "aten::add_", "aten::mul", "aten::fill_", "aten::add", "aten::zero_", "aten::clone"):
+                rows.append((e.count, e.key, "shapes " + str(e.input_shapes)[:120]))
+        rows.sort(reverse=True)
+        (ROOT / "gpurun_out").mkdir(exist_ok=True)
+        (ROOT / "gpurun_out" / "step_glue_stacks.txt").write_text("\n".join(f"{c:5d} {k:14s} {s}" for c, k, s in rows[:80]))
     out = ROOT / "gpurun_out"
     out.mkdir(exist_ok=True)
     ka = prof.key_averages()
