@@ -586,6 +586,236 @@ conv_halo_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
     }
 }
 
+// ====================================================================================================================
+// CTA-pair variant of the halo kernel (tcgen05 cta_group::2).
+//
+// With the issue loop fixed, the halo kernel is bound by the SM's 128 B/clk of shared-memory bandwidth, which the MMA's
+// operand reads (A 4 KB + B 32*BLOCK_N B per instruction) share with the TMA writes of the next operands
+// (profiles/README.md: t_MMA ~ max(N/2, (A + B + writes) / 128 B) clk explains every row of the sweep).  A CTA pair
+// executes one M = 256 MMA: each CTA supplies its own 128 pixels of A and only HALF of the weight tile, so per SM the
+// weight bytes read AND written halve.  Pair = two horizontally adjacent 8-pixel-wide tiles (rank r takes columns
+// w0 + 8r); protocol (CUTLASS' 2-SM scheme): both CTAs run producers into their own rings but count transaction bytes on
+// the leader's full barriers; the leader's MMA warps issue, and their commits multicast to the empty / tmem_full barriers
+// of both CTAs; epilogue warps of both CTAs arrive on the leader's tmem_empty barriers.
+template <int BLOCK_N, int MT, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HaloCfg<BLOCK_N, MT, MODE>::kThreads, 1)
+conv_halo2_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
+    using Cfg = HaloCfg<BLOCK_N, MT, MODE>;
+    constexpr int kBHalfPlane = Cfg::kBPlaneBytes / 2;              // this CTA's half of the weight tile, one plane
+    constexpr int kBHalfUnit = Cfg::kParts * kBHalfPlane;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t a_full[Cfg::kMaxAStages];
+    __shared__ __align__(8) uint64_t a_empty[Cfg::kMaxAStages];
+    __shared__ __align__(8) uint64_t b_full[Cfg::kMaxBStages];
+    __shared__ __align__(8) uint64_t b_empty[Cfg::kMaxBStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_slot;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int SA = p.a_stages, SB = p.b_stages;
+    const uint32_t b_ring_off = SA * Cfg::kAUnitBytes;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tiles = p.Cout / BLOCK_N;
+    const uint32_t rank = cluster_ctarank();            // 0 = leader
+    const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+    const int total_pairs = p.total_tiles;               // tiles of the pair grid: (W/16) x (H/PH) x N x n_tiles
+
+    if (warp == 0 && lane == 0) {
+#pragma unroll
+        for (int q = 0; q < Cfg::kParts; ++q) {
+            tma_prefetch_desc(&tm.a[q]);
+            tma_prefetch_desc(&tm.b[q]);
+        }
+        for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], Cfg::kIssuers); }
+        for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], Cfg::kIssuers); }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], Cfg::kIssuers);
+            mbar_init(&tmem_empty_bar[a], 8);             // 4 epilogue warps of each CTA of the pair
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_2cta<Cfg::kTmemCols>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                    // peer barriers initialised before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ===================== activation-slab producer (both CTAs) =====================
+        const bool leader = elect_one();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = pair0; tile < total_pairs; tile += pair_step) {
+            int m_tile = tile / n_tiles;
+            const int tw = m_tile % p.tiles_w;
+            m_tile /= p.tiles_w;
+            const int th = m_tile % p.tiles_h;
+            const int n = m_tile / p.tiles_h;
+            const int w0 = tw * 16 + static_cast<int>(rank) * 8, h0 = th * Cfg::kPH;
+            for (int cb = 0; cb < p.cblks; ++cb) {
+                for (int dx = -1; dx <= 1; ++dx) {
+                    mbar_wait(&a_empty[stage], phase ^ 1u);
+                    uint8_t* sa = smem_al + stage * Cfg::kAUnitBytes;
+                    if (leader) {
+                        if (rank == 0) mbar_expect_tx(&a_full[stage], 2 * Cfg::kAUnitBytes);   // both CTAs' slabs
+#pragma unroll
+                        for (int q = 0; q < Cfg::kParts; ++q)
+                            tma_load_4d_2cta(sa + q * Cfg::kSlabBytes, &tm.a[q], &a_full[stage], cb * Cfg::kChanPerRow,
+                                             w0 + dx, h0 - 1, n);
+                    }
+                    if (++stage == SA) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ===================== weight-tile producer (both CTAs, half a tile each) =====================
+        const bool leader = elect_one();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = pair0; tile < total_pairs; tile += pair_step) {
+            const int n_tile = tile % n_tiles;
+            const int row0 = n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+            for (int cb = 0; cb < p.cblks; ++cb) {
+                for (int dxi = 0; dxi < 3; ++dxi) {
+                    for (int dyi = 0; dyi < 3; ++dyi) {
+                        mbar_wait(&b_empty[stage], phase ^ 1u);
+                        uint8_t* sb = smem_al + b_ring_off + stage * kBHalfUnit;
+                        const int kcoord = (dyi * 3 + dxi) * p.Cin + cb * Cfg::kChanPerRow;
+                        if (leader) {
+                            if (rank == 0) mbar_expect_tx(&b_full[stage], 2 * kBHalfUnit);
+#pragma unroll
+                            for (int q = 0; q < Cfg::kParts; ++q)
+                                tma_load_2d_2cta(sb + q * kBHalfPlane, &tm.b[q], &b_full[stage], kcoord, row0);
+                        }
+                        if (++stage == SB) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 || warp == 7) {
+        // ===================== MMA issuer(s): leader CTA only =====================
+        if (rank == 0) {
+            const bool leader = elect_one();
+            constexpr int kMtPer = MT / Cfg::kIssuers;
+            const int mt_first = warp == 1 ? 0 : kMtPer;
+            constexpr uint32_t idesc = MODE == 0 ? make_idesc_tf32(256, BLOCK_N, 0, 0) : make_idesc_bf16(256, BLOCK_N, 0, 0);
+            const uint64_t desc_hi = make_smem_desc(0, 16, 1024, 2);
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            int it = 0;
+            for (int tile = pair0; tile < total_pairs; tile += pair_step, ++it) {
+                const int acc = Cfg::kAccBufs == 2 ? (it & 1) : 0;
+                const uint32_t acc_phase = Cfg::kAccBufs == 2 ? ((it >> 1) & 1) : (it & 1);
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_acc = tmem_base + acc * Cfg::kTileCols;
+                for (int cb = 0; cb < p.cblks; ++cb) {
+                    for (int dxi = 0; dxi < 3; ++dxi) {
+                        mbar_wait(&a_full[sa], pa);
+                        const uint32_t a_addr = smem_base + sa * Cfg::kAUnitBytes;
+                        for (int dyi = 0; dyi < 3; ++dyi) {
+                            mbar_wait(&b_full[sb], pb);
+                            tc_fence_after();
+                            const uint32_t b_addr = smem_base + b_ring_off + sb * kBHalfUnit;
+                            const uint64_t db0 = desc_hi | ((b_addr >> 4) & 0x3FFFu);
+                            const uint32_t first = (cb | dxi | dyi) == 0 ? 0u : 1u;
+                            if (leader) {
+#pragma unroll
+                                for (int j = 0; j < kMtPer; ++j) {
+                                    const int mt = mt_first + j;
+                                    const uint32_t a_tap = a_addr + (16 * mt + dyi) * 1024;
+                                    const uint64_t da0 = desc_hi | ((a_tap >> 4) & 0x3FFFu);
+                                    const uint32_t d = tmem_acc + mt * BLOCK_N;
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const uint64_t da = da0 + 2 * k, db = db0 + 2 * k;
+                                        const uint32_t accum = k > 0 ? 1u : first;
+                                        if (MODE == 0) {
+                                            umma_tf32_ss_2cta(d, da, db, idesc, accum);
+                                        } else {
+                                            const uint64_t da_lo = da + (Cfg::kSlabBytes >> 4);
+                                            const uint64_t db_lo = db + (kBHalfPlane >> 4);
+                                            umma_f16_ss_2cta(d, da_lo, db, idesc, accum);   // Al * Bh
+                                            umma_f16_ss_2cta(d, da, db_lo, idesc, 1u);      // Ah * Bl
+                                            umma_f16_ss_2cta(d, da, db, idesc, 1u);         // Ah * Bh
+                                        }
+                                    }
+                                }
+                                umma_commit_2cta(&b_empty[sb]);
+                            }
+                            if (++sb == SB) { sb = 0; pb ^= 1u; }
+                        }
+                        if (leader) umma_commit_2cta(&a_empty[sa]);
+                        if (++sa == SA) { sa = 0; pa ^= 1u; }
+                    }
+                }
+                if (leader) umma_commit_2cta(&tmem_full_bar[acc]);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5 of both CTAs) =====================
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;
+        const int wl = m & 7;
+        const int hl = m >> 3;
+        const float oscale = p.out_scale ? __ldg(p.out_scale) : 1.0f;
+        int it = 0;
+        for (int tile = pair0; tile < total_pairs; tile += pair_step, ++it) {
+            const int acc = Cfg::kAccBufs == 2 ? (it & 1) : 0;
+            const uint32_t acc_phase = Cfg::kAccBufs == 2 ? ((it >> 1) & 1) : (it & 1);
+            const int n_tile = tile % n_tiles;
+            int m_tile = tile / n_tiles;
+            const int tw = m_tile % p.tiles_w;
+            m_tile /= p.tiles_w;
+            const int th = m_tile % p.tiles_h;
+            const int n = m_tile / p.tiles_h;
+            const float* brow = p.bias ? p.bias + n_tile * BLOCK_N : nullptr;
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt) {
+                const int h = th * Cfg::kPH + mt * 16 + hl, w = tw * 16 + static_cast<int>(rank) * 8 + wl;
+                const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
+                float* yrow = p.y + pix * p.Cout + n_tile * BLOCK_N;
+                const float* rrow = nullptr;
+                if (p.residual_mode == 1) {
+                    rrow = p.residual + pix * p.Cout + n_tile * BLOCK_N;
+                } else if (p.residual_mode == 2) {
+                    const size_t rp = (static_cast<size_t>(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+                    rrow = p.residual + rp * p.Cout + n_tile * BLOCK_N;
+                }
+                const uint32_t tmem_acc = tmem_base + acc * Cfg::kTileCols + mt * BLOCK_N +
+                                          (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_acc + c0, v);
+                    tmem_ld_wait();
+                    if (mt == MT - 1 && c0 + 32 >= BLOCK_N) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
+                    }
+                    epilogue_store_chunk(p, v, oscale, yrow, nullptr, rrow, brow, pix * p.Cout + n_tile * BLOCK_N, c0);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // the peer may still be reading this CTA's shared memory / arriving on its barriers
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2cta<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
 // Split-K second pass: y = epilogue( sum_s ws[s] ), the same epilogue as the main kernel, deterministic summation order.
 __global__ void __launch_bounds__(256)
 splitk_epilogue_kernel(const ConvParams p, long long total4) {
@@ -747,6 +977,52 @@ static int launch_halo(const ConvMaps& tm, ConvParams p, int a_stages, int b_sta
     return B200LP_OK;
 }
 
+template <int BLOCK_N, int MT, int MODE>
+static int launch_halo2(const ConvMaps& tm, ConvParams p, int a_stages, int b_stages, cudaStream_t stream) {
+    using Cfg = HaloCfg<BLOCK_N, MT, MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200LP_CHECK_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<BLOCK_N, MT, MODE>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmemBytes));
+        attr_set = true;
+    }
+    // ring depths: the weight ring holds half tiles, so the same budget buys twice the depth (capped at kMaxBStages)
+    const int budget = Cfg::kMaxSmemBytes - 1024;
+    const int b_half = Cfg::kBUnitBytes / 2;
+    auto b_fit = [&](int a) {
+        int b = (budget - a * Cfg::kAUnitBytes) / b_half;
+        return b > Cfg::kMaxBStages ? Cfg::kMaxBStages : b;
+    };
+    if (a_stages <= 0) {
+        a_stages = 2;
+        for (int a = (Cfg::kAUnitBytes <= 20 * 1024 ? 4 : 3); a >= 2; --a)
+            if (b_fit(a) >= 4) { a_stages = a; break; }
+    }
+    if (a_stages > Cfg::kMaxAStages) a_stages = Cfg::kMaxAStages;
+    const int bmax = b_fit(a_stages);
+    B200LP_REQUIRE(bmax >= 2, "conv_fwd: pair-kernel rings (%d slabs, block_n %d, variant %d) do not fit shared memory",
+                   a_stages, BLOCK_N, MT);
+    if (b_stages <= 0 || b_stages > bmax) b_stages = bmax;
+    p.a_stages = a_stages;
+    p.b_stages = b_stages;
+    p.tiles_w = p.W / 16;                       // pair tiles: 16 pixels wide
+    p.tiles_h = p.H / Cfg::kPH;
+    p.total_tiles = p.tiles_w * p.tiles_h * p.N * (p.Cout / BLOCK_N);
+    const int smem_bytes = a_stages * Cfg::kAUnitBytes + b_stages * b_half + 1024;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        B200LP_CHECK_CUDA(cudaGetDevice(&dev));
+        B200LP_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int pairs = num_sms / 2;
+    if (pairs > p.total_tiles) pairs = p.total_tiles;
+    conv_halo2_kernel<BLOCK_N, MT, MODE><<<2 * pairs, Cfg::kThreads, smem_bytes, stream>>>(tm, p);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
+
 }  // namespace b200lp
 
 using namespace b200lp;
@@ -780,12 +1056,26 @@ static int conv_splits(const b200lp_conv_args* a, int block_n, int m_tiles) {
 
 // Halo-kernel sub-tiles per CTA (0 = use the per-tap kernel).  Auto: 3x3 layers on planes >= 16 x 8 that are not split
 // along K.
-static int conv_halo_mt(const b200lp_conv_args* a, int block_n, int splits) {
+static int conv_halo_mt(const b200lp_conv_args* a, int block_n, int splits, bool* pair) {
+    *pair = false;
     if (a->variant < 0 || a->ksize != 3 || a->W < 8 || a->H < 16 || splits != 1) return 0;
     if (a->variant > 0) {
-        const int mt = a->variant;
+        const int mt = a->variant >= 10 ? a->variant - 10 : a->variant;     // 11 / 12: CTA-pair kernel, 1 / 2 sub-tiles
         if ((mt != 1 && mt != 2 && mt != 4) || a->H % (16 * mt)) return -1;
+        if (a->variant >= 10 && (mt == 4 || a->W % 16 || block_n < 64)) return -1;
+        *pair = a->variant >= 10;
         return mt;
+    }
+    // CTA pairs (cta_group::2) first: +4..9 % tf32, +6..19 % bf16x3 over the single-CTA halo kernel on every shape of
+    // the sweep (profiles/r01_kernel_diag_pair.log).  Two sub-tiles for block_n <= 128 in tf32; one otherwise.
+    if (a->W % 16 == 0 && block_n >= 64) {
+        int mt = (a->precision == 0 && block_n <= 128) ? 2 : 1;
+        const long pair_tiles1 = static_cast<long>(a->N) * (a->H / 16) * (a->W / 16) * (a->Cout / block_n);
+        while (mt > 1 && (a->H % (16 * mt) || pair_tiles1 / mt < 60)) mt >>= 1;
+        if (pair_tiles1 / mt >= 37) {
+            *pair = true;
+            return mt;
+        }
     }
     // measured (halo_tune): two sub-tiles sharing every weight tile win whenever >= ~100 CTA tiles remain (even below one
     // tile per SM: 512->256 @64x64 runs 774 vs 742 TFLOP/s); four sub-tiles never beat two once both have two issuers.
@@ -865,9 +1155,10 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
     }
     p.kb_per_split = (p.num_kb + p.splits - 1) / p.splits;
 
-    const int halo_mt = conv_halo_mt(a, block_n, p.splits);
-    B200LP_REQUIRE(halo_mt >= 0, "conv_fwd: variant %d needs a 3x3 layer with W >= 8, H %% (16 * variant) == 0, no split-K",
-                   a->variant);
+    bool halo_pair = false;
+    const int halo_mt = conv_halo_mt(a, block_n, p.splits, &halo_pair);
+    B200LP_REQUIRE(halo_mt >= 0, "conv_fwd: variant %d needs a 3x3 layer with W >= 8 (pair kernel: W %% 16 == 0), "
+                   "H %% (16 * sub-tiles) == 0, no split-K", a->variant);
 
     ConvMaps tm;
     const uint64_t ktot = (uint64_t)a->ksize * a->ksize * a->Cin;
@@ -889,7 +1180,8 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
         {
             const uint64_t dims[2] = {ktot, (uint64_t)a->Cout};
             const uint64_t strides[1] = {ktot * elem_bytes};
-            const uint32_t box[2] = {(uint32_t)chan_per_row, (uint32_t)block_n};
+            // CTA-pair kernel: each CTA of the pair fetches half of the weight tile
+            const uint32_t box[2] = {(uint32_t)chan_per_row, (uint32_t)(halo_pair ? block_n / 2 : block_n)};
             const char* base = static_cast<const char*>(a->wp) + (size_t)q * ktot * a->Cout * elem_bytes;
             int r = encode_tmap(&tm.b[q], base, mode == 0 ? kTmapF32 : kTmapBF16, 2, dims, strides, box, false);
             if (r) return r;
@@ -898,6 +1190,18 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
     if (mode == 0) { tm.a[1] = tm.a[0]; tm.b[1] = tm.b[0]; }
     cudaStream_t s = as_stream(stream);
     const int st = a->stages, cps = a->ctas_per_sm;
+    if (halo_pair) {
+        const int ast = a->a_stages;
+#define B200LP_PAIR_CASE(BN, MT, MODE) \
+    if (block_n == BN && halo_mt == MT && mode == MODE) return launch_halo2<BN, MT, MODE>(tm, p, ast, st, s);
+        B200LP_PAIR_CASE(256, 1, 0) B200LP_PAIR_CASE(256, 2, 0)
+        B200LP_PAIR_CASE(128, 1, 0) B200LP_PAIR_CASE(128, 2, 0)
+        B200LP_PAIR_CASE(64, 1, 0) B200LP_PAIR_CASE(64, 2, 0)
+        B200LP_PAIR_CASE(128, 1, 1) B200LP_PAIR_CASE(128, 2, 1)
+        B200LP_PAIR_CASE(64, 1, 1) B200LP_PAIR_CASE(64, 2, 1)
+#undef B200LP_PAIR_CASE
+        B200LP_REQUIRE(false, "conv_fwd: no pair kernel for block_n %d, variant %d, precision %d", block_n, a->variant, mode);
+    }
     if (halo_mt) {
         const int ast = a->a_stages;
 #define B200LP_HALO_CASE(BN, MT, MODE) \

@@ -10,12 +10,17 @@ namespace b200lp {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // ------------------------------------------------------------------------------------------------ Cin = 3 forward
-// block 256 threads = (256/groups pixels) x (Cout/16 channel groups), group index fastest: the `groups` lanes of one
-// pixel hold interleaved 4-channel quads (thread g owns channels q*4*groups + 4g .. +3 for q = 0..3), so one store
-// instruction writes 16*groups contiguous bytes per pixel (full 32-byte sectors) and one weight read is a contiguous
-// 16*groups-byte broadcast.  Blocks are persistent over pixel chunks: the 27 x Cout weights are staged in shared
-// memory once per block instead of once per 64 pixels (first version: 103 us per 8 x 256^2 x 64 call, 5x the HBM bound).
-__global__ void __launch_bounds__(256, 3)
+// Thread = 4 horizontally adjacent pixels x 8 output channels; block 256 threads = (256/groups pixel quads) x
+// (Cout/8 channel groups), group index fastest.  The `groups` lanes of one pixel hold interleaved 4-channel quads (thread
+// g owns channels q*4*groups + 4g .. +3, q = 0, 1): one store instruction writes 16*groups contiguous bytes per pixel
+// (whole 128-byte lines at Cout = 64) and one weight read is a contiguous 16*groups-byte broadcast.
+// Why 4 pixels per thread: every FMA needs a weight from shared memory; with one pixel per thread the kernel ran at the
+// LDS.128 rate (108 broadcast loads per thread-pixel, 4 clk each per warp: 97 us of the measured 103 us for
+// 8 x 256^2 x 64), 4x the FMA time.  Four pixels share each weight load and the 3 x 6 input window.
+// Why 8 channels: 4 x 16 accumulators needed 255 registers = 8 warps per SM, and ncu showed the issue slots 38 % busy
+// (latency-bound, 117 us); 4 x 8 keeps the same loads-per-FMA ratio at half the registers.
+// Blocks are persistent over pixel chunks: the 27 x Cout weights are staged in shared memory once per block.
+__global__ void __launch_bounds__(256, 2)
 conv3x3_c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ wscale,
                       const float* __restrict__ bias, const float* __restrict__ pre_scale,
                       const float* __restrict__ pre_shift, float* __restrict__ y, int N, int H, int W, int Cout,
@@ -31,62 +36,91 @@ conv3x3_c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias ? __ldg(bias + i) : 0.f;
     __syncthreads();
 
-    const int groups = Cout >> 4;
-    const int ppb = blockDim.x / groups;
+    // block tile = quads_w pixel quads x rows image rows; its (rows+2) x (4*quads_w+2) x 3 input patch is staged in shared
+    // memory by the whole block (coalesced, zero-filled outside the image): the per-thread global loads of the first
+    // versions left every warp waiting on L2 latency once per tile (ncu: 35 % of samples on the first dependent FFMA).
+    float* patch = sb + Cout;
+    const int groups = Cout >> 3;
+    const int qpb = blockDim.x / groups;                 // pixel quads per block tile
     const int g = threadIdx.x % groups;
-    const int pl = threadIdx.x / groups;
-    const int qstride = 4 * groups;                      // channels between this thread's consecutive quads
-    const long total = static_cast<long>(N) * H * W;
+    const int ql = threadIdx.x / groups;
+    const int qstride = 4 * groups;                      // channels between this thread's two quads
+    const int wq4 = W >> 2;
+    const int quads_w = wq4 < 8 ? wq4 : 8;
+    const int rows = qpb / quads_w;
+    const int pw = 4 * quads_w + 2, ph = rows + 2;
+    const int tiles_w = wq4 / quads_w;
+    const int tiles_h = (H + rows - 1) / rows;
+    const long total_tiles = static_cast<long>(N) * tiles_h * tiles_w;
+    const int qx = ql % quads_w, qy = ql / quads_w;
     float ps[3], pb[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         ps[c] = pre_scale ? __ldg(pre_scale + c) : 1.f;
         pb[c] = pre_shift ? __ldg(pre_shift + c) : 0.f;
     }
-    for (long P = static_cast<long>(blockIdx.x) * ppb + pl; P < total; P += static_cast<long>(gridDim.x) * ppb) {
-        const int wq = static_cast<int>(P % W);
-        const int hq = static_cast<int>((P / W) % H);
-        const long n = P / (static_cast<long>(W) * H);
-        float acc[16];
+    for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tw = static_cast<int>(tile % tiles_w);
+        const int th = static_cast<int>((tile / tiles_w) % tiles_h);
+        const long n = tile / (static_cast<long>(tiles_w) * tiles_h);
+        const int wbase = tw * 4 * quads_w, hbase = th * rows;
+        __syncthreads();                                  // previous tile's readers are done with the patch
+        for (int i = threadIdx.x; i < 3 * ph * pw; i += blockDim.x) {
+            const int col = i % pw, row = (i / pw) % ph, c = i / (pw * ph);
+            const int hh = hbase + row - 1, ww = wbase + col - 1;
+            float v = 0.f;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                v = __ldg(x + ((n * 3 + c) * static_cast<long>(H) + hh) * W + ww) * ps[c] + pb[c];
+            patch[i] = v;
+        }
+        __syncthreads();
+        const int hq = hbase + qy;
+        if (hq >= H) continue;
+        const int w0 = wbase + 4 * qx;
+        float acc[4][8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
             const float4 b = *reinterpret_cast<const float4*>(sb + q * qstride + g * 4);
-            acc[q * 4 + 0] = b.x; acc[q * 4 + 1] = b.y; acc[q * 4 + 2] = b.z; acc[q * 4 + 3] = b.w;
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+                acc[px][q * 4 + 0] = b.x; acc[px][q * 4 + 1] = b.y; acc[px][q * 4 + 2] = b.z; acc[px][q * 4 + 3] = b.w;
+            }
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {          // one input plane at a time: 9 live inputs instead of 27
-            const float* xp = x + (n * 3 + c) * static_cast<long>(H) * W;
-            float in[9];
+        for (int c = 0; c < 3; ++c) {
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
+                const float* prow = patch + (c * ph + qy + kh) * pw + 4 * qx;
+                float in[6];                              // columns w0-1 .. w0+4 of this input row
+#pragma unroll
+                for (int j = 0; j < 6; ++j) in[j] = prow[j];
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw) {
-                    const int hh = hq + kh - 1, ww = wq + kw - 1;
-                    float v = 0.f;
-                    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-                        v = __ldg(xp + static_cast<long>(hh) * W + ww) * ps[c] + pb[c];
-                    in[kh * 3 + kw] = v;
-                }
-            }
+                    const float* wr = sw + (c * 9 + kh * 3 + kw) * Cout + g * 4;
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const float v = in[t];
-                const float* wr = sw + (c * 9 + t) * Cout + g * 4;
+                    for (int q = 0; q < 2; ++q) {
+                        const float4 wv = *reinterpret_cast<const float4*>(wr + q * qstride);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 ww = *reinterpret_cast<const float4*>(wr + q * qstride);
-                    acc[q * 4 + 0] += v * ww.x; acc[q * 4 + 1] += v * ww.y;
-                    acc[q * 4 + 2] += v * ww.z; acc[q * 4 + 3] += v * ww.w;
+                        for (int px = 0; px < 4; ++px) {
+                            const float v = in[px + kw];
+                            acc[px][q * 4 + 0] += v * wv.x; acc[px][q * 4 + 1] += v * wv.y;
+                            acc[px][q * 4 + 2] += v * wv.z; acc[px][q * 4 + 3] += v * wv.w;
+                        }
+                    }
                 }
             }
         }
-        float* yo = y + P * Cout + g * 4;
+        const long P = (n * H + hq) * static_cast<long>(W) + w0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float4 o = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
-            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-            *reinterpret_cast<float4*>(yo + q * qstride) = o;
+        for (int px = 0; px < 4; ++px) {
+            float* yo = y + (P + px) * Cout + g * 4;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float4 o = make_float4(acc[px][q * 4], acc[px][q * 4 + 1], acc[px][q * 4 + 2], acc[px][q * 4 + 3]);
+                if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                *reinterpret_cast<float4*>(yo + q * qstride) = o;
+            }
         }
     }
 }
@@ -476,14 +510,19 @@ extern "C" int32_t b200lp_conv3x3_c3_fwd(const float* x_nchw, const float* w_oih
                                          float* y_nhwc, int32_t N, int32_t H, int32_t W, int32_t Cout, int32_t relu,
                                          int32_t round_tf32, void* stream) {
     B200LP_REQUIRE(x_nchw && w_oihw && y_nhwc, "conv3x3_c3_fwd: null pointer");
-    B200LP_REQUIRE(N > 0 && H > 0 && W > 0 && Cout % 16 == 0 && Cout >= 16 && Cout <= 128 && (256 % (Cout / 16)) == 0,
-                   "conv3x3_c3_fwd: bad shape (Cout=%d)", Cout);
-    const int groups = Cout / 16;
-    const int ppb = 256 / groups;
-    const long total = static_cast<long>(N) * H * W;
-    long blocks = (total + ppb - 1) / ppb;
-    if (blocks > 148 * 8) blocks = 148 * 8;           // persistent over pixel chunks: weights staged once per block
-    conv3x3_c3_fwd_kernel<<<static_cast<int>(blocks), 256, (27 * Cout + Cout) * 4, as_stream(stream)>>>(
+    B200LP_REQUIRE(N > 0 && H > 0 && W > 0 && W % 4 == 0 && Cout % 16 == 0 && Cout >= 16 && Cout <= 128 &&
+                       (256 % (Cout / 16)) == 0,
+                   "conv3x3_c3_fwd: bad shape (Cout=%d, W=%d: Cout in {16,32,64,128}, W %% 4 == 0)", Cout, W);
+    const int groups = Cout / 8;
+    const int qpb = 256 / groups;                                 // pixel quads per block tile
+    const int wq4 = W / 4;
+    const int quads_w = wq4 < 8 ? wq4 : 8;
+    B200LP_REQUIRE(qpb % quads_w == 0 && wq4 % quads_w == 0, "conv3x3_c3_fwd: W=%d not tileable (Cout=%d)", W, Cout);
+    const int rows = qpb / quads_w;
+    const long total_tiles = static_cast<long>(N) * ((H + rows - 1) / rows) * (wq4 / quads_w);
+    long blocks = total_tiles < 148 * 6 ? total_tiles : 148 * 6;   // persistent: weights staged once per block
+    const size_t smem = (27 * Cout + Cout + 3 * (rows + 2) * (4 * quads_w + 2)) * sizeof(float);
+    conv3x3_c3_fwd_kernel<<<static_cast<int>(blocks), 256, smem, as_stream(stream)>>>(
         x_nchw, w_oihw, wscale, bias, pre_scale, pre_shift, y_nhwc, N, H, W, Cout, relu, round_tf32);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();

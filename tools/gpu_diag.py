@@ -544,6 +544,67 @@ def conv_halo():
     return out
 
 
+@check
+def conv_pair():
+    """CTA-pair halo kernel (cta_group::2, M = 256 per MMA, half a weight tile per CTA): every instantiation, borders,
+    epilogue options, ring depths, odd tile counts; then TFLOP/s against the single-CTA halo kernel."""
+    import torch
+    from b200lp import kernels as K
+    out = []
+    h = dict(splits=1)
+    for v in (11, 12):
+        out.append(_conv_case(2, 64, 32, 64, 64, 3, variant=v, **h))
+        out.append(_conv_case(1, 32, 16, 32, 64, 3, variant=v, bias=True, relu=True, **h))
+        out.append(_conv_case(3, 32, 48 if False else 32, 96, 128, 3, variant=v, residual_mode=2, **h))
+        out.append(_conv_case(2, 32, 32, 128, 128, 3, variant=v, residual_mode=1, bias=True, **h))
+        out.append(_conv_case(1, 32, 16, 64, 512, 3, block_n=256, variant=v, **h))
+        out += _conv_bf16x3_case(2, 32, 16, 128, 64, 3, emit_split=True, residual_mode=2, variant=v, **h)
+        out += _conv_bf16x3_case(1, 32, 32, 64, 128, 3, variant=v, **h)
+    out.append(_conv_case(5, 32, 16, 64, 64, 3, variant=11, a_stages=2, stages=2, **h))
+    out.append(_conv_case(8, 256, 256, 64, 64, 3, variant=12, **h))
+    out.append(_conv_case(8, 64, 64, 512, 256, 3, variant=11, **h))
+    shapes = [(8, 256, 256, 64, 64), (8, 256, 256, 128, 64), (8, 128, 128, 128, 128), (8, 128, 128, 256, 128),
+              (8, 64, 64, 256, 256), (8, 64, 64, 512, 256), (8, 32, 32, 512, 512)]
+    for (N, H, W, Cin, Cout) in shapes:
+        x = torch.randn(N, H, W, Cin, device="cuda")
+        wp = K.pack_conv_weight(torch.randn(Cout, Cin, 3, 3, device="cuda"))
+        y = torch.empty(N, H, W, Cout, device="cuda")
+        flops = 2.0 * N * H * W * Cin * Cout * 9
+        rec = {"case": f"timing tf32 N{N} H{H} Cin{Cin} Cout{Cout}", "ok": True, "max_abs": 0.0, "rel": 0.0, "nan": False,
+               "ref_max": 0.0}
+        rec["auto"] = round(flops / _time_us(lambda: K.conv_fwd(x, wp, 3, out=y)) / 1e6, 0)
+        for bn in (64, 128, 256):
+            if Cout % bn:
+                continue
+            for v in (11, 12):
+                for sa in (0, 2):
+                    try:
+                        us = _time_us(lambda: K.conv_fwd(x, wp, 3, out=y, block_n=bn, variant=v, a_stages=sa, splits=1))
+                        rec[f"bn{bn}_v{v}_a{sa}"] = round(flops / us / 1e6, 0)
+                    except Exception as err:
+                        rec[f"bn{bn}_v{v}_a{sa}"] = "n/a"
+        out.append(rec)
+    for (N, H, W, Cin, Cout) in [(8, 256, 256, 128, 64), (8, 128, 128, 128, 128), (8, 64, 64, 256, 256)]:
+        xs = split_bf16(torch.randn(N, H, W, Cin, device="cuda"))
+        wp = K.pack_conv_weight(torch.randn(Cout, Cin, 3, 3, device="cuda"), precision=K.BF16X3)
+        y = torch.empty(N, H, W, Cout, device="cuda")
+        flops = 2.0 * N * H * W * Cin * Cout * 9
+        rec = {"case": f"timing bf16x3 N{N} H{H} Cin{Cin} Cout{Cout}", "ok": True, "max_abs": 0.0, "rel": 0.0, "nan": False,
+               "ref_max": 0.0}
+        rec["auto"] = round(flops / _time_us(lambda: K.conv_fwd(xs, wp, 3, out=y)) / 1e6, 0)
+        for bn in (64, 128):
+            if Cout % bn:
+                continue
+            for v in (11, 12):
+                try:
+                    us = _time_us(lambda: K.conv_fwd(xs, wp, 3, out=y, block_n=bn, variant=v, splits=1))
+                    rec[f"bn{bn}_v{v}"] = round(flops / us / 1e6, 0)
+                except Exception as err:
+                    rec[f"bn{bn}_v{v}"] = "n/a"
+        out.append(rec)
+    return out
+
+
 def _time_us(fn, reps=8, warm=2):
     import torch
     for _ in range(warm):
@@ -636,6 +697,20 @@ def pack_multi():
         res.append({"case": f"Cout{r[2]} Cin{r[3]} taps{r[4]} transpose{r[5]} precision{r[6]}", "ok": same,
                     "max_abs": 0.0 if same else 1.0, "rel": 0.0 if same else 1.0, "nan": False, "ref_max": 1.0})
     return res
+
+
+@check
+def c3_timing():
+    """Cin = 3 stem forward (direct FMA kernel) at the step's shape: 8 x 256^2 -> 64 channels."""
+    import torch
+    from b200lp import kernels as K
+    x = torch.randn(8, 3, 256, 256, device="cuda")
+    w = torch.randn(64, 3, 3, 3, device="cuda")
+    b = torch.randn(64, device="cuda")
+    us = _time_us(lambda: K.conv3x3_c3_fwd(x, w, bias=b, relu=True, round_tf32=True), reps=10, warm=3)
+    gb = 4.0 * (x.numel() + 8 * 256 * 256 * 64) / 1e9
+    return [{"case": "c3 fwd 8x256x256 -> 64", "ok": True, "us": round(us, 1), "GB/s": round(gb / us * 1e6, 0),
+             "max_abs": 0.0, "rel": 0.0, "nan": False, "ref_max": 0.0}]
 
 
 @check
