@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 13
+#define B200LP_ABI_VERSION 14
 
 #define B200LP_OK 0
 #define B200LP_EINVAL (-1)   /* bad shape / unsupported configuration */
@@ -56,13 +56,15 @@ typedef struct {
                                the spectral-norm division costs nothing and `wp` is packed once per weight update
                                instead of once per forward call (3 discriminator passes share one packing).       */
     const float* bias;      /* [Cout] or NULL                                                                    */
-    const float* residual;  /* NULL, or [N,H,W,Cout] (mode 1), or [N,H/2,W/2,Cout] (mode 2: nearest-2x source)    */
+    const float* residual;  /* NULL, or [N,H,W,Cout] (mode 1), or [N,H/2,W/2,Cout] (mode 2: nearest-2x source), or
+                               [N,H,W,Cout] used as a ReLU-backward mask (mode 3: y = residual > 0 ? y : 0 — the
+                               data-gradient of a conv whose input was a ReLU output, relu_bwd fused)                */
     float* y;               /* [N,H,W,Cout] fp32                                                                 */
     void* y_split;          /* NULL, or bf16 [2][N,H,W,Cout]: the same result as (hi, lo) planes (operand of a
                                following bf16x3 convolution)                                                    */
     int32_t N, H, W, Cin, Cout;
     int32_t ksize;          /* 1 or 3                                                  */
-    int32_t residual_mode;  /* 0 none, 1 same resolution, 2 half resolution            */
+    int32_t residual_mode;  /* 0 none, 1 same resolution, 2 half resolution, 3 relu mask */
     int32_t relu;           /* 1: y = max(y, 0)                                        */
     int32_t round_tf32;     /* 1: round y to tf32 (y only feeds further tf32 MMAs)     */
     int32_t block_n;        /* 0 = auto; else 32 / 64 / 128 / 256 (256: tf32 only)     */
@@ -160,6 +162,17 @@ typedef struct {
 
 int64_t b200lp_conv_wgrad_workspace(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize);
 int32_t b200lp_conv_wgrad(const b200lp_wgrad_args* a, void* stream);
+
+/* The same weight gradient delivered straight into the parameter's gradient buffer (the `.grad` view inside the
+ * data-parallel bucket, runners/holycow.py GradBucket), with the spectral-norm rank-1 term fused:
+ *   G = wgrad(x, dy);   grad (+)= s*G - s^2 <G, w> u v^T,   s = *inv_sigma       (a->dw = grad, OIHW; a->scale unused)
+ * inv_sigma == NULL: grad (+)= G (w, u, v ignored).  Three launches: tensor-core split-K kernel, tiled reduction
+ * (+ accumulate + <G, w> partials; coalesced on both sides), rank-1 update.  Replaces conv backward-filter + the autograd
+ * of `weight_orig / sigma` + AccumulateGrad's add_.  Tuning knobs of `a` must be 0.
+ * Workspace: b200lp_conv_wgrad_sn_acc_workspace() bytes. */
+int64_t b200lp_conv_wgrad_sn_acc_workspace(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize);
+int32_t b200lp_conv_wgrad_sn_acc(const b200lp_wgrad_args* a, const float* w, const float* inv_sigma, const float* u,
+                                 const float* v, int32_t accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Instance-norm statistics, AdaIN affine + ReLU (+ nearest 2x upsample)  — HBM-bound.
@@ -275,6 +288,14 @@ int32_t b200lp_ema_multi(const void* table_dev, const int32_t* chunk_tensor_dev,
 
 /* per-channel sum over pixels (bias gradients): db[c] = scale * sum_{n,h,w} dy[n,h,w,c] */
 int32_t b200lp_bias_grad(const float* dy, float* db, int64_t pixels, int32_t C, void* stream);
+
+/* the same, accumulated into db (db += ...): db is the bias parameter's gradient buffer */
+int32_t b200lp_bias_grad_acc(const float* dy, float* db, int64_t pixels, int32_t C, void* stream);
+
+/* dst <- src for `count` small buffers in ONE launch.  table_dev: device array of {void* dst; const void* src;
+ * int64 nbytes}.  Replaces the per-buffer copies of TrainingModule.update_running_average (runners/holycow.py:106-109:
+ * BatchNorm statistics and spectral-norm vectors of E and G, ~370 tensors per step). */
+int32_t b200lp_copy_multi(const void* table_dev, int32_t count, void* stream);
 
 #ifdef __cplusplus
 }

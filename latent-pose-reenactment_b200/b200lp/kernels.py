@@ -151,6 +151,50 @@ def conv_wgrad(x, dy, ksize, scale=1.0, kstep=0, stages=0, splits=0):
     return dw
 
 
+def conv_wgrad_sn_acc(x, dy, ksize, grad, weight=None, inv_sigma=None, u=None, v=None, accumulate=True):
+    """grad (+)= s*G - s^2 <G, W> u v^T with G = wgrad(x, dy) (s = inv_sigma[0]; without inv_sigma: grad (+)= G).
+    `grad`: contiguous OIHW fp32 buffer (the parameter's .grad view inside the gradient bucket) — written in place."""
+    lib = L.load()
+    n, h, w, cin = x.shape
+    cout = dy.shape[3]
+    assert tuple(grad.shape) == (cout, cin, ksize, ksize), (grad.shape, cout, cin, ksize)
+    nbytes = lib.b200lp_conv_wgrad_sn_acc_workspace(n, h, w, cin, cout, ksize)
+    if nbytes < 0:
+        raise L.B200lpError(f"conv_wgrad_sn_acc_workspace: {L.last_error()}")
+    ws = _ws(nbytes, x.device)
+    a = L.WgradArgs()
+    a.x = L.ptr(x); a.dy = L.ptr(dy); a.dw = L.ptr(grad); a.workspace = L.ptr(ws)
+    a.workspace_bytes = ws.numel() * 4
+    a.N, a.H, a.W, a.Cin, a.Cout = n, h, w, cin, cout
+    a.ksize = ksize
+    a.scale = 1.0
+    wq = weight.detach() if weight is not None else None
+    with _timed("conv_wgrad_tf32", flops=2.0 * n * h * w * cin * cout * ksize * ksize):
+        L.check(lib.b200lp_conv_wgrad_sn_acc(byref(a), L.ptr(wq), L.ptr(inv_sigma), L.ptr(u), L.ptr(v), int(accumulate),
+                                             L.stream_ptr()), "conv_wgrad_sn_acc")
+    return grad
+
+
+def copy_plan(pairs):
+    """Device table for copy_multi: pairs = [(dst, src), ...] of equally sized contiguous tensors on one device."""
+    rows = []
+    for d, s_ in pairs:
+        assert d.is_contiguous() and s_.is_contiguous() and d.numel() * d.element_size() == s_.numel() * s_.element_size()
+        if d.numel():
+            rows.append((d.data_ptr(), s_.data_ptr(), d.numel() * d.element_size()))
+    dev = pairs[0][0].device
+    return dict(table=torch.tensor(rows, dtype=torch.int64, device=dev), count=len(rows), sig=tuple(rows),
+                nbytes=2.0 * sum(r[2] for r in rows))
+
+
+def copy_multi(plan):
+    lib = L.load()
+    if plan["count"] == 0:
+        return
+    with _timed("elementwise", nbytes=plan["nbytes"]):
+        L.check(lib.b200lp_copy_multi(c_void_p(plan["table"].data_ptr()), plan["count"], L.stream_ptr()), "copy_multi")
+
+
 def in_stats(x, eps):
     """x (N,H,W,C) -> mean (N,C), rstd (N,C) of each (n,c) plane (biased variance)."""
     lib = L.load()
@@ -405,9 +449,16 @@ def conv3x3_c3_wgrad_tc(x_nchw, dy):
     return g.reshape(cout, 32)[:, :27].reshape(cout, 3, 3, 3).contiguous()
 
 
-def bias_grad(dy):
+def bias_grad(dy, acc_into=None):
+    """db[c] = sum over pixels of dy[..., c]; with `acc_into` (the bias parameter's gradient buffer) db is added there."""
     lib = L.load()
     c = dy.shape[-1]
+    if acc_into is not None:
+        assert acc_into.numel() == c
+        with _timed("elementwise", nbytes=4.0 * dy.numel()):
+            L.check(lib.b200lp_bias_grad_acc(L.ptr(dy), L.ptr(acc_into), dy.numel() // c, c, L.stream_ptr()),
+                    "bias_grad_acc")
+        return acc_into
     db = torch.empty((c,), dtype=torch.float32, device=dy.device)
     with _timed("elementwise", nbytes=4.0 * dy.numel()):
         L.check(lib.b200lp_bias_grad(L.ptr(dy), L.ptr(db), dy.numel() // c, c, L.stream_ptr()), "bias_grad")

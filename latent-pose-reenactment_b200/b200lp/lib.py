@@ -13,7 +13,7 @@ import torch
 
 _PKG = Path(__file__).resolve().parent.parent
 LIB_PATH = _PKG / "lib" / "libb200lp.so"
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 
 class B200lpError(RuntimeError):
@@ -72,6 +72,8 @@ SIGNATURES = {
     "b200lp_sn_wgrad_fix": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "b200lp_conv_wgrad_workspace": (_L, [_I, _I, _I, _I, _I, _I]),
     "b200lp_conv_wgrad": (_I, [POINTER(WgradArgs), _P]),
+    "b200lp_conv_wgrad_sn_acc_workspace": (_L, [_I, _I, _I, _I, _I, _I]),
+    "b200lp_conv_wgrad_sn_acc": (_I, [POINTER(WgradArgs), _P, _P, _P, _P, _I, _P]),
     "b200lp_in_stats_workspace": (_L, [_I, _I, _I]),
     "b200lp_in_stats": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _F, _P]),
     "b200lp_adain_relu": (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
@@ -97,6 +99,8 @@ SIGNATURES = {
     "b200lp_col2im3x3_c3": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "b200lp_gen_tail_bwd_weight": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200lp_bias_grad": (_I, [_P, _P, _L, _I, _P]),
+    "b200lp_bias_grad_acc": (_I, [_P, _P, _L, _I, _P]),
+    "b200lp_copy_multi": (_I, [_P, _I, _P]),
     "b200lp_adam_ema_multi": (_I, [_P, _P, _P, _I, _L, _P, _F, _F, _F, _F, _F, _I, _I, _P]),
     "b200lp_ema_multi": (_I, [_P, _P, _P, _I, _L, _F, _P]),
 }

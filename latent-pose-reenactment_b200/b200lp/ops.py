@@ -103,13 +103,51 @@ def repack_weights(params, owner=None):
     return len(rows)
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# Gradient sinks: while `direct_grads(...)` is active, the backward of the tensor-core convolutions adds a parameter's
+# gradient straight into its `.grad` buffer (a view into the runner's flat gradient bucket) from inside the kernel
+# that produces it, and hands autograd `None` for that input — instead of: temporary dW tensor -> spectral-norm fix
+# kernel pair -> AccumulateGrad's `add_`.  Keyed by the parameter's storage pointer (saved tensors / detached aliases
+# of a parameter share it).
+# ----------------------------------------------------------------------------------------------------------------
+_SINKS = {}
+
+
+class direct_grads:
+    """Context manager: `sinks` = {param.data_ptr(): contiguous fp32 gradient buffer shaped like the parameter}, already
+    zeroed (or holding the gradient accumulated so far); autograd hooks of those parameters do not fire."""
+
+    def __init__(self, sinks):
+        self.sinks = sinks or {}
+
+    def __enter__(self):
+        self.old = dict(_SINKS)
+        _SINKS.update(self.sinks)
+        return self
+
+    def __exit__(self, *exc):
+        _SINKS.clear()
+        _SINKS.update(self.old)
+        return False
+
+
+def _sink(t):
+    if t is None or not _SINKS:
+        return None
+    g = _SINKS.get(t.data_ptr())
+    if g is None or g.shape != t.shape or g.device != t.device:
+        return None
+    return g
+
+
 def _packed(weight, cache, transpose, precision=K.TF32):
     if cache is not None:
         return cache.get(weight, transpose, precision)
     return K.pack_conv_weight(weight.detach(), None, transpose=transpose, precision=precision)
 
 
-def _conv_backward(ctx_ksize, x_f32, weight_orig, inv_sigma, dy, need_x, need_w, need_s, cache=None, sn=None):
+def _conv_backward(ctx_ksize, x_f32, weight_orig, inv_sigma, dy, need_x, need_w, need_s, cache=None, sn=None,
+                   dx_mask=None):
     """Shared backward of the tensor-core convolutions (TF32 data / weight gradient kernels).
     y = s * conv(x, W):  dx = s * conv_T(dy, W);  dW = s * wgrad(x, dy);  ds = <wgrad(x, dy), W>.
     `sn` = (u, v) snapshots of the spectral-norm vectors behind s = 1/sigma: then s carries no autograd edge and the
@@ -117,8 +155,17 @@ def _conv_backward(ctx_ksize, x_f32, weight_orig, inv_sigma, dy, need_x, need_w,
     dx = dw = ds = None
     if need_x:
         wpt = _packed(weight_orig, cache, True)
-        dx = K.conv_fwd(dy, wpt, ctx_ksize, scale=inv_sigma)
-    if need_w or (need_s and inv_sigma is not None and sn is None):
+        # dx_mask: the conv's input was produced by a ReLU whose backward is applied here, in the epilogue
+        dx = K.conv_fwd(dy, wpt, ctx_ksize, scale=inv_sigma, residual=dx_mask, residual_mode=3 if dx_mask is not None else 0)
+    sink = _sink(weight_orig) if need_w and (sn is not None or inv_sigma is None) else None
+    if sink is not None:
+        # gradient goes straight into the parameter's .grad buffer: wgrad -> tiled reduce (+= s*G, <G,W> partials)
+        # -> rank-1 spectral-norm term; autograd gets None for this input
+        if sn is not None:
+            K.conv_wgrad_sn_acc(x_f32, dy, ctx_ksize, sink, weight_orig, inv_sigma, sn[0], sn[1])
+        else:
+            K.conv_wgrad_sn_acc(x_f32, dy, ctx_ksize, sink)
+    elif need_w or (need_s and inv_sigma is not None and sn is None):
         g = K.conv_wgrad(x_f32, dy, ctx_ksize)
         if sn is not None:
             dw = K.sn_wgrad_fix(g, weight_orig, inv_sigma, sn[0], sn[1])
@@ -132,6 +179,29 @@ def _conv_backward(ctx_ksize, x_f32, weight_orig, inv_sigma, dy, need_x, need_w,
     return dx, dw, ds
 
 
+class InvSigmaFn(torch.autograd.Function):
+    """Gives a batched-kernel 1/sigma (b200lp_sn_sigma_multi: no autograd history) its edge to `weight_orig`:
+    sigma = u^T W v with u, v constants (torch's SpectralNorm.compute_weight)  =>  d(1/sigma)/dW = -(1/sigma)^2 u v^T.
+    For the spectral-normalised layers whose consumers differentiate through plain autograd (linear / embedding layers,
+    the Cin=3 stems, the generator tail); the tensor-core convs fuse this term into their weight-gradient kernels."""
+
+    @staticmethod
+    def forward(ctx, weight_orig, inv_sigma, u, v):
+        ctx.save_for_backward(inv_sigma, u, v)
+        ctx.shape = weight_orig.shape
+        return inv_sigma.clone()
+
+    @staticmethod
+    def backward(ctx, ds):
+        inv_sigma, u, v = ctx.saved_tensors
+        coef = -(ds.reshape(1) * inv_sigma * inv_sigma)
+        return ((u * coef).unsqueeze(1) * v.unsqueeze(0)).reshape(ctx.shape), None, None, None
+
+
+def inv_sigma_edge(weight_orig, inv_sigma, u, v):
+    return InvSigmaFn.apply(weight_orig, inv_sigma, u, v)
+
+
 class Conv2dFn(torch.autograd.Function):
     """y = epilogue(conv_k(x, weight_orig * inv_sigma)).  Replaces nn.Conv2d under spectral_norm
     (generators/common/blocks.py:78-100, discriminators/no_landmarks.py:54-66) and its autograd backward.
@@ -143,9 +213,12 @@ class Conv2dFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight_orig, inv_sigma, bias, residual, ksize, residual_mode, relu, round_out, x_split,
-                emit_split, cache, sn):
+                emit_split, cache, sn, relu_bwd, mask_dx):
         """`x_split` (optional, non-differentiable): the (hi, lo) bf16 planes of x — when given, the forward runs in
-        bf16x3 precision on them; gradients still flow to `x`.  `emit_split`: also return the (hi, lo) planes of y."""
+        bf16x3 precision on them; gradients still flow to `x`.  `emit_split`: also return the (hi, lo) planes of y.
+        `relu_bwd=False` (with relu): this conv's ReLU mask is NOT applied to the incoming gradient here because the single
+        consumer of y applies it in its data-gradient epilogue — that consumer is called with `mask_dx=True` (its x is a
+        ReLU output: dx = [x > 0] * conv_T(dy), fused, no separate relu_bwd pass)."""
         if x_split is not None:
             wp = _packed(weight_orig, cache, False, K.BF16X3)
             src = x_split
@@ -157,9 +230,11 @@ class Conv2dFn(torch.autograd.Function):
         y, y_split = out if emit_split else (out, None)
         ctx.ksize, ctx.residual_mode, ctx.relu = ksize, residual_mode, relu
         ctx.cache, ctx.sn = cache, sn
+        ctx.relu_bwd, ctx.mask_dx = relu_bwd, mask_dx
         ctx.has_bias = bias is not None
+        ctx.bias_ref = bias.detach() if bias is not None else None      # alias only: identifies the gradient sink
         ctx.has_res = residual is not None
-        ctx.save_for_backward(x, weight_orig, inv_sigma, y if relu else None)
+        ctx.save_for_backward(x, weight_orig, inv_sigma, y if (relu and relu_bwd) else None)
         if emit_split:
             ctx.mark_non_differentiable(y_split)
             return y, y_split
@@ -169,24 +244,29 @@ class Conv2dFn(torch.autograd.Function):
     def backward(ctx, dy, *_unused):
         x, weight_orig, inv_sigma, y = ctx.saved_tensors
         dy = dy.contiguous()
-        if ctx.relu:
+        if ctx.relu and ctx.relu_bwd:
             dy = K.relu_bwd(y, dy)
         need_x, need_w, need_s, need_b, need_r = ctx.needs_input_grad[:5]
-        dx, dw, ds = _conv_backward(ctx.ksize, x, weight_orig, inv_sigma, dy, need_x, need_w, need_s, ctx.cache, ctx.sn)
+        dx, dw, ds = _conv_backward(ctx.ksize, x, weight_orig, inv_sigma, dy, need_x, need_w, need_s, ctx.cache, ctx.sn,
+                                    dx_mask=x if ctx.mask_dx else None)
         db = dr = None
         if ctx.has_bias and need_b:
-            db = K.bias_grad(dy)
+            bsink = _sink(ctx.bias_ref)
+            if bsink is not None:
+                K.bias_grad(dy, acc_into=bsink)
+            else:
+                db = K.bias_grad(dy)
         if ctx.has_res and need_r:
             dr = dy if ctx.residual_mode == 1 else K.upsample2_bwd(dy)
-        return dx, dw, ds, db, dr, None, None, None, None, None, None, None, None
+        return dx, dw, ds, db, dr, None, None, None, None, None, None, None, None, None, None
 
 
 def conv2d(x, weight_orig, inv_sigma=None, bias=None, residual=None, ksize=3, residual_mode=0, relu=False,
-           round_out=False, x_split=None, emit_split=False, cache=None, sn=None):
+           round_out=False, x_split=None, emit_split=False, cache=None, sn=None, relu_bwd=True, mask_dx=False):
     if residual is None:
         residual_mode = 0
     return Conv2dFn.apply(x, weight_orig, inv_sigma, bias, residual, ksize, residual_mode, relu, round_out, x_split,
-                          emit_split, cache, sn)
+                          emit_split, cache, sn, relu_bwd, mask_dx)
 
 
 class AdaINConvFn(torch.autograd.Function):

@@ -210,6 +210,107 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
     }
 }
 
+
+// Tiled form of the reduction for the fused "weight gradient -> parameter .grad" path (b200lp_conv_wgrad_sn_acc):
+//   G[co][ci][tap] = sum_s ws[s][tap*Cin+ci][co]                    (deterministic order over the K splits)
+//   grad[co][ci][tap] += (*inv_sigma) * G                           (or = when !accumulate)
+//   dot_part[block]   = sum over the block's elements of G * w      (partials of <G, W>, summed in order by sn_rank1)
+// A block owns a 32(ci) x 32(co) tile for TPB taps: workspace rows are read coalesced along co, transposed through
+// shared memory, and grad / w are accessed along their contiguous (ci, tap) axis — wgrad_reduce_kernel's OIHW
+// stores are one 4-byte element per 32-byte sector.
+template <int TPB>
+__global__ void __launch_bounds__(256)
+wgrad_reduce_acc_kernel(const float* __restrict__ ws, float* __restrict__ grad, const float* __restrict__ w,
+                        const float* __restrict__ inv_sigma, float* __restrict__ dot_part, int splits, int Cin,
+                        int Cout, int taps, int accumulate) {
+    constexpr int kStride = 32 * TPB + 1;
+    __shared__ float tile[32 * kStride];
+    __shared__ float red[8];
+    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32, tap0 = blockIdx.z * TPB;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long total = static_cast<long>(taps) * Cin * Cout;
+    // phase 1: lane = co, (ci, tap) pairs over the warps
+    for (int r = warp; r < 32 * TPB; r += 8) {
+        const int t = r / 32, cl = r - t * 32;
+        const long row = static_cast<long>(tap0 + t) * Cin + ci0 + cl;
+        const float* src = ws + row * Cout + co0 + lane;
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s) acc += __ldg(src + static_cast<long>(s) * total);
+        tile[lane * kStride + cl * TPB + t] = acc;
+    }
+    __syncthreads();
+    // phase 2: one output channel per warp pass, lanes along the (ci, tap) axis
+    const float sc = inv_sigma ? __ldg(inv_sigma) : 1.f;
+    float dot = 0.f;
+    for (int col = warp; col < 32; col += 8) {
+        const long base = (static_cast<long>(co0 + col) * Cin + ci0) * taps + tap0;
+        for (int j = lane; j < 32 * TPB; j += 32) {
+            const int cl = j / TPB, t = j - cl * TPB;
+            const long idx = base + static_cast<long>(cl) * taps + t;
+            const float g = tile[col * kStride + j];
+            if (w) dot += g * __ldg(w + idx);
+            grad[idx] = accumulate ? grad[idx] + sc * g : sc * g;
+        }
+    }
+    if (dot_part) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (lane == 0) red[warp] = dot;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tsum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tsum += red[k];
+            dot_part[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tsum;
+        }
+    }
+}
+
+// grad[r][c] -= s^2 * <G, W> * u[r] * v[c]   (the rank-1 term of the spectral-norm gradient);
+// <G, W> = sum of `nparts` partials in index order.  grid = (column chunks of 1024, row groups of 8)
+__global__ void __launch_bounds__(256)
+sn_rank1_acc_kernel(float* __restrict__ grad, const float* __restrict__ part, int nparts,
+                    const float* __restrict__ inv_sigma, const float* __restrict__ u, const float* __restrict__ v,
+                    int rows, int cols) {
+    __shared__ float sh[8];
+    __shared__ float kk;
+    // every block sums the same partials in the same order: identical k everywhere, no atomics
+    float a = 0.f;
+    for (int i = threadIdx.x; i < nparts; i += 256) a += part[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tsum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tsum += sh[k];
+        const float s = __ldg(inv_sigma);
+        kk = tsum * s * s;
+    }
+    __syncthreads();
+    const float k = kk;
+    const int c = blockIdx.x * 1024 + threadIdx.x * 4;
+    if (c >= cols) return;
+    const int r0 = blockIdx.y * 8;
+    const bool vec = (cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    if (vec) {
+        const float4 vv = *reinterpret_cast<const float4*>(v + c);
+        for (int r = r0; r < r0 + 8 && r < rows; ++r) {
+            const float ku = k * __ldg(u + r);
+            float4* gp = reinterpret_cast<float4*>(grad + static_cast<long>(r) * cols + c);
+            float4 g = *gp;
+            g.x -= ku * vv.x; g.y -= ku * vv.y; g.z -= ku * vv.z; g.w -= ku * vv.w;
+            *gp = g;
+        }
+    } else {
+        for (int r = r0; r < r0 + 8 && r < rows; ++r) {
+            const float ku = k * __ldg(u + r);
+            for (int j = c; j < c + 4 && j < cols; ++j) grad[static_cast<long>(r) * cols + j] -= ku * __ldg(v + j);
+        }
+    }
+}
+
 struct WgPlan {
     int block_n, m_tiles, n_tiles, splits, steps_per_split, total_steps, pw, ph, pn, kstep, stages;
 };
@@ -290,16 +391,17 @@ extern "C" int64_t b200lp_conv_wgrad_workspace(int32_t N, int32_t H, int32_t W, 
     return static_cast<int64_t>(pl.splits) * ksize * ksize * Cin * Cout * 4;   // default plan (tuning knobs = auto)
 }
 
-extern "C" int32_t b200lp_conv_wgrad(const b200lp_wgrad_args* a, void* stream) {
+// plans and launches the tensor-core kernel (split-K partial sums -> a->workspace); the caller adds the reduction
+static int wgrad_main(const b200lp_wgrad_args* a, void* stream, WgPlan* pl_out, int64_t extra_ws_bytes) {
     B200LP_REQUIRE(a && a->x && a->dy && a->dw && a->workspace, "conv_wgrad: null pointer");
-    WgPlan pl;
+    WgPlan& pl = *pl_out;
     B200LP_REQUIRE(plan_wgrad(a->N, a->H, a->W, a->Cin, a->Cout, a->ksize, &pl, a->kstep, a->stages, a->splits) == 0,
                    "conv_wgrad: unsupported shape N=%d H=%d W=%d Cin=%d Cout=%d k=%d", a->N, a->H, a->W, a->Cin,
                    a->Cout, a->ksize);
     B200LP_REQUIRE(a->N % pl.pn == 0, "conv_wgrad: N=%d must be a multiple of %d for %dx%d planes", a->N, pl.pn,
                    a->H, a->W);
     const int taps = a->ksize * a->ksize;
-    const int64_t need = static_cast<int64_t>(pl.splits) * taps * a->Cin * a->Cout * 4;
+    const int64_t need = static_cast<int64_t>(pl.splits) * taps * a->Cin * a->Cout * 4 + extra_ws_bytes;
     B200LP_REQUIRE(a->workspace_bytes >= need, "conv_wgrad: workspace %lld < %lld bytes",
                    (long long)a->workspace_bytes, (long long)need);
 
@@ -343,13 +445,71 @@ extern "C" int32_t b200lp_conv_wgrad(const b200lp_wgrad_args* a, void* stream) {
         case 64: r = launch_wgrad<64>(tmX, tmDY, p, pl, s); break;
         default: r = launch_wgrad<32>(tmX, tmDY, p, pl, s); break;
     }
+    return r;
+}
+
+extern "C" int32_t b200lp_conv_wgrad(const b200lp_wgrad_args* a, void* stream) {
+    WgPlan pl;
+    int r = wgrad_main(a, stream, &pl, 0);
     if (r) return r;
-    const long total = static_cast<long>(p.rows_total) * a->Cout;
+    const int taps = a->ksize * a->ksize;
+    const int rows_total = taps * a->Cin;
+    const long total = static_cast<long>(rows_total) * a->Cout;
     int blocks = static_cast<int>((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(a->workspace, a->dw, pl.splits, p.rows_total, a->Cout, a->Cin, taps,
-                                               a->scale);
+    wgrad_reduce_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a->workspace, a->dw, pl.splits, rows_total, a->Cout,
+                                                               a->Cin, taps, a->scale);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
+    return B200LP_OK;
+}
+
+// number of <G, W> partial sums wgrad_reduce_acc_kernel writes, and whether a block takes all taps of its tile
+static int wgrad_acc_parts(int Cin, int Cout, int ksize, bool* all_taps) {
+    const int tiles = (Cin / 32) * (Cout / 32);
+    const int taps = ksize * ksize;
+    // few tiles (64- / 128-channel layers): one block per tap keeps >= 36 blocks busy; the strided OIHW accesses of
+    // that form touch at most a few hundred KB
+    *all_taps = taps == 1 || tiles >= 64;
+    return *all_taps ? tiles : tiles * taps;
+}
+
+extern "C" int64_t b200lp_conv_wgrad_sn_acc_workspace(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                                                      int32_t ksize) {
+    const int64_t base = b200lp_conv_wgrad_workspace(N, H, W, Cin, Cout, ksize);
+    if (base < 0) return base;
+    bool all_taps;
+    return base + static_cast<int64_t>(wgrad_acc_parts(Cin, Cout, ksize, &all_taps)) * 4;
+}
+
+extern "C" int32_t b200lp_conv_wgrad_sn_acc(const b200lp_wgrad_args* a, const float* w, const float* inv_sigma,
+                                            const float* u, const float* v, int32_t accumulate, void* stream) {
+    B200LP_REQUIRE(a && (inv_sigma == nullptr || (w && u && v)), "conv_wgrad_sn_acc: w, u, v are required with inv_sigma");
+    B200LP_REQUIRE(a->splits == 0 && a->kstep == 0 && a->stages == 0, "conv_wgrad_sn_acc: tuning knobs are not supported");
+    bool all_taps;
+    const int taps = a->ksize * a->ksize;
+    const int nparts = (a->Cin > 0 && a->Cout > 0) ? wgrad_acc_parts(a->Cin, a->Cout, a->ksize, &all_taps) : 0;
+    WgPlan pl;
+    int r = wgrad_main(a, stream, &pl, static_cast<int64_t>(nparts) * 4);
+    if (r) return r;
+    cudaStream_t s = as_stream(stream);
+    float* parts = a->workspace + static_cast<size_t>(pl.splits) * taps * a->Cin * a->Cout;
+    const bool sn = inv_sigma != nullptr;
+    dim3 grid(a->Cin / 32, a->Cout / 32, all_taps ? 1 : taps);
+    if (taps == 9 && all_taps)
+        wgrad_reduce_acc_kernel<9><<<grid, 256, 0, s>>>(a->workspace, a->dw, sn ? w : nullptr, inv_sigma,
+                                                        sn ? parts : nullptr, pl.splits, a->Cin, a->Cout, taps, accumulate);
+    else
+        wgrad_reduce_acc_kernel<1><<<grid, 256, 0, s>>>(a->workspace, a->dw, sn ? w : nullptr, inv_sigma,
+                                                        sn ? parts : nullptr, pl.splits, a->Cin, a->Cout, taps, accumulate);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    if (sn) {
+        const int rows = a->Cout, cols = a->Cin * taps;
+        dim3 g2((cols + 1023) / 1024, (rows + 7) / 8);
+        sn_rank1_acc_kernel<<<g2, 256, 0, s>>>(a->dw, parts, nparts, inv_sigma, u, v, rows, cols);
+        B200LP_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+    }
     return B200LP_OK;
 }

@@ -571,6 +571,30 @@ __global__ void bias_grad_kernel(const float* __restrict__ dy, float* __restrict
     }
 }
 
+// dst[i] <- src[i] for a table of small buffers (one block per buffer): the running-average copies of BatchNorm /
+// spectral-norm buffers (runners/holycow.py:106-109) are ~370 tiny tensors per step
+struct CopyItem {
+    void* dst;
+    const void* src;
+    long long nbytes;
+};
+__global__ void __launch_bounds__(256)
+copy_multi_kernel(const CopyItem* __restrict__ table) {
+    const CopyItem it = table[blockIdx.x];
+    const bool words = ((reinterpret_cast<uintptr_t>(it.dst) | reinterpret_cast<uintptr_t>(it.src) |
+                         static_cast<uintptr_t>(it.nbytes)) & 3) == 0;
+    if (words) {
+        const long long n = it.nbytes >> 2;
+        const uint32_t* s = static_cast<const uint32_t*>(it.src);
+        uint32_t* d = static_cast<uint32_t*>(it.dst);
+        for (long long i = threadIdx.x; i < n; i += 256) d[i] = s[i];
+    } else {
+        const uint8_t* s = static_cast<const uint8_t*>(it.src);
+        uint8_t* d = static_cast<uint8_t*>(it.dst);
+        for (long long i = threadIdx.x; i < it.nbytes; i += 256) d[i] = s[i];
+    }
+}
+
 static int grid_for(long work_items, int threads) {
     long b = (work_items + threads - 1) / threads;
     const long cap = 148L * 8;
@@ -801,10 +825,28 @@ extern "C" int32_t b200lp_nhwc_to_nchw(const float* x, float* y, int32_t N, int3
     return B200LP_OK;
 }
 
+extern "C" int32_t b200lp_copy_multi(const void* table_dev, int32_t count, void* stream) {
+    B200LP_REQUIRE(table_dev && count > 0, "copy_multi: bad args");
+    copy_multi_kernel<<<count, 256, 0, as_stream(stream)>>>(static_cast<const CopyItem*>(table_dev));
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
+
+static int32_t bias_grad_impl(const float* dy, float* db, int64_t pixels, int32_t C, int32_t accumulate, void* stream);
+
 extern "C" int32_t b200lp_bias_grad(const float* dy, float* db, int64_t pixels, int32_t C, void* stream) {
+    return bias_grad_impl(dy, db, pixels, C, 0, stream);
+}
+
+extern "C" int32_t b200lp_bias_grad_acc(const float* dy, float* db, int64_t pixels, int32_t C, void* stream) {
+    return bias_grad_impl(dy, db, pixels, C, 1, stream);
+}
+
+static int32_t bias_grad_impl(const float* dy, float* db, int64_t pixels, int32_t C, int32_t accumulate, void* stream) {
     B200LP_REQUIRE(dy && db && pixels > 0 && C > 0 && C % 4 == 0 && C / 4 <= kEwThreads, "bias_grad: bad args");
     cudaStream_t s = as_stream(stream);
-    B200LP_CHECK_CUDA(cudaMemsetAsync(db, 0, static_cast<size_t>(C) * 4, s));
+    if (!accumulate) B200LP_CHECK_CUDA(cudaMemsetAsync(db, 0, static_cast<size_t>(C) * 4, s));
     const int rows = kEwThreads / (C / 4);
     long blocks = 148 * 4;
     long ppb = (pixels + blocks - 1) / blocks;

@@ -60,7 +60,48 @@ adam_ema_multi_kernel(const OptTensor* __restrict__ table, const int* __restrict
     const bool rect = state[2] != 0.f;
     const float inv_bc2_sqrt = state[3];
     const float one_m_b1 = 1.f - beta1, one_m_b2 = 1.f - beta2, one_m_a = 1.f - ema_alpha;
-    for (long long i = off + threadIdx.x; i < end; i += blockDim.x) {
+    // 16-byte path when every stream of this chunk is aligned (gradients / moments are views into flat buffers, so
+    // alignment depends on the sizes of the tensors before this one); the scalar loop takes the rest
+    long long vec_end = off;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(t.p + off) | reinterpret_cast<uintptr_t>(t.g + off) |
+                         reinterpret_cast<uintptr_t>(t.m + off) | reinterpret_cast<uintptr_t>(t.v + off) |
+                         (t.ema ? reinterpret_cast<uintptr_t>(t.ema + off) : 0);
+    if ((al & 15) == 0) {
+        const long long n4 = (end - off) >> 2;
+        vec_end = off + (n4 << 2);
+        const float4* g4 = reinterpret_cast<const float4*>(t.g + off);
+        float4* m4 = reinterpret_cast<float4*>(t.m + off);
+        float4* v4 = reinterpret_cast<float4*>(t.v + off);
+        float4* p4 = reinterpret_cast<float4*>(t.p + off);
+        float4* e4 = t.ema ? reinterpret_cast<float4*>(t.ema + off) : nullptr;
+        for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+            const float4 gq = g4[i];
+            float4 mq = m4[i], vq = v4[i], pq = p4[i];
+            const float gg[4] = {gq.x, gq.y, gq.z, gq.w};
+            float mm[4] = {mq.x, mq.y, mq.z, mq.w}, vv[4] = {vq.x, vq.y, vq.z, vq.w}, pp[4] = {pq.x, pq.y, pq.z, pq.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                vv[k] = vv[k] * beta2 + one_m_b2 * gg[k] * gg[k];
+                if (mode == 0) {
+                    mm[k] = mm[k] + (gg[k] - mm[k]) * one_m_b1;
+                    pp[k] -= step_size * mm[k] / (sqrtf(vv[k]) * inv_bc2_sqrt + eps);
+                } else {
+                    mm[k] = mm[k] * beta1 + one_m_b1 * gg[k];
+                    pp[k] -= rect ? step_size * mm[k] / (sqrtf(vv[k]) + eps) : step_size * mm[k];
+                }
+            }
+            m4[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+            v4[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            p4[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+            if (e4) {
+                float4 eq = e4[i];
+                eq.x = eq.x * ema_alpha + pp[0] * one_m_a; eq.y = eq.y * ema_alpha + pp[1] * one_m_a;
+                eq.z = eq.z * ema_alpha + pp[2] * one_m_a; eq.w = eq.w * ema_alpha + pp[3] * one_m_a;
+                e4[i] = eq;
+            }
+        }
+    }
+    for (long long i = vec_end + threadIdx.x; i < end; i += blockDim.x) {
         const float g = t.g[i];
         float m = t.m[i], v = t.v[i], p = t.p[i];
         v = v * beta2 + one_m_b2 * g * g;

@@ -50,7 +50,9 @@ class SNEmbedding(blocks.SpectralNormed):
             self.weight_orig.uniform_(-0.1, 0.1)
 
     def forward(self, label):
-        return torch.nn.functional.embedding(label, self.weight_orig) * self.inv_sigma()
+        if self.weight_orig.is_cuda:
+            blocks.spectral_sigmas([self])      # batched kernels (3 launches) instead of torch's ~14 per call
+        return torch.nn.functional.embedding(label, self.weight_orig) * self.scale()
 
 
 class Discriminator(nn.Module):
@@ -95,13 +97,14 @@ class Discriminator(nn.Module):
         """input: (B,3,S,S) NCHW image.  Returns (score (B,), [7 feature maps])  — reference :90-108.
         `detach_params`: run this pass on detached weights (no weight gradients; see `skip_discarded_wgrad`)."""
         x = input.contiguous()
-        blocks.spectral_sigmas(self._tensor_core_convs())      # one batched power iteration for the 20 MMA convs
-        w0, s0, b0, _ = self.down_block.slot(0).operands(detach_params)
+        # one batched power iteration for the 20 MMA convs, the two Cin=3 stem convs and the final linear layer
+        blocks.spectral_sigmas(self._tensor_core_convs() + [self.down_block.slot(0), self.skip.slot(0), self.linear])
+        w0, s0, b0 = self.down_block.slot(0).operands_edge(detach_params)
         h = ops.conv_c3(x, w0, s0, b0, relu=True, round_out=True)
         w2, s2, b2, e2 = self.down_block.slot(2).operands(detach_params)
         h2 = ops.conv2d(h, w2, s2, bias=b2, ksize=3, **e2)
         # skip: AvgPool2(conv1x1(x)) == conv1x1(AvgPool2(x)); the 1x1 weights ride the centre tap of the 3x3 stem kernel
-        ws, ss, bs, _ = self.skip.slot(0).operands(detach_params)
+        ws, ss, bs = self.skip.slot(0).operands_edge(detach_params)
         xs = torch.nn.functional.avg_pool2d(x, 2)
         s = ops.conv_c3(xs, torch.nn.functional.pad(ws, (1, 1, 1, 1)), ss, bs)
         out = ops.avgpool2(h2, s)
@@ -113,7 +116,7 @@ class Discriminator(nn.Module):
             out = block(r, detach_params)
         feats.append(out)                  # the last feature stays pre-ReLU (reference :100 is out of place)
         o = torch.relu(out).sum(dim=(1, 2))                       # (B, C): spatial sum of the NHWC map
-        wl, sl, bl, _ = self.linear.operands(detach_params)
+        wl, sl, bl = self.linear.operands_edge(detach_params)
         out_linear = (torch.nn.functional.linear(o, wl) * sl + bl)[:, 0]
         score = (o * embed).sum(1) + out_linear if embed is not None else out_linear
         return score, [f.permute(0, 3, 1, 2) for f in feats]

@@ -74,6 +74,26 @@ class SpectralNormed(nn.Module):
         sigma = torch.dot(u, torch.mv(wm, v))
         return (1.0 / sigma).reshape(1)
 
+    def scale(self, detach=False):
+        """1/sigma WITH its autograd edge to `weight_orig`, for consumers that differentiate through plain autograd
+        (linear / embedding layers, Cin=3 stems, generator tail): the batched kernel result deposited by
+        spectral_sigmas() wrapped in ops.InvSigmaFn, else torch's per-layer formula `inv_sigma()`."""
+        if self._pre is not None:
+            s, (su, sv) = self._pre
+            self._pre = None
+            if detach or not (torch.is_grad_enabled() and self.weight_orig.requires_grad):
+                return s
+            return ops.inv_sigma_edge(self.weight_orig, s, su, sv)
+        s = self.inv_sigma()
+        return s.detach() if detach else s
+
+    def operands_edge(self, detach=False):
+        """(weight_orig, 1/sigma with autograd edge, bias) — see scale()."""
+        s = self.scale(detach)
+        if detach:
+            return self.weight_orig.detach(), s, (self.bias.detach() if self.bias is not None else None)
+        return self.weight_orig, s, self.bias
+
     def operands(self, detach=False):
         """(weight_orig, 1/sigma, bias, extras) as the kernels consume them; extras = dict(cache=PackCache, sn=(u, v) or
         None).  If spectral_sigmas() deposited a batched result for this layer it is consumed here (sigma then has no
@@ -128,7 +148,7 @@ class SNLinear(SpectralNormed):
 
     def forward(self, x):
         # (x W^T) / sigma + b  ==  F.linear(x, W / sigma, b) without materialising W / sigma
-        return torch.nn.functional.linear(x, self.weight_orig) * self.inv_sigma() + self.bias
+        return torch.nn.functional.linear(x, self.weight_orig) * self.scale() + self.bias
 
 
 class AdaResBlock(nn.Module):
@@ -214,7 +234,8 @@ class PlainResBlock(nn.Module):
     def forward(self, r, detach_params=False):
         """r = tf32(relu(block input)).  Returns the block output (pre-ReLU)."""
         w0, s0, b0, e0 = self.block.slot(2).operands(detach_params)
-        h = ops.conv2d(r, w0, s0, bias=b0, ksize=3, relu=True, round_out=True, **e0)
+        # h has exactly one consumer (the second conv): its ReLU backward runs in that conv's data-gradient epilogue
+        h = ops.conv2d(r, w0, s0, bias=b0, ksize=3, relu=True, round_out=True, relu_bwd=False, **e0)
         w1, s1, b1, e1 = self.block.slot(5).operands(detach_params)
         if self.skip is not None:
             ws, ss, bs, es = self.skip.slot(0).operands(detach_params)
@@ -223,9 +244,9 @@ class PlainResBlock(nn.Module):
         else:
             s = r
         if self.downsample:
-            h2 = ops.conv2d(h, w1, s1, bias=b1, ksize=3, **e1)
+            h2 = ops.conv2d(h, w1, s1, bias=b1, ksize=3, mask_dx=True, **e1)
             return ops.avgpool2(h2, s)
-        return ops.conv2d(h, w1, s1, bias=b1, residual=s, residual_mode=1, ksize=3, **e1)
+        return ops.conv2d(h, w1, s1, bias=b1, residual=s, residual_mode=1, ksize=3, mask_dx=True, **e1)
 
     def tensor_core_convs(self):
         return [m for m in (self.block.slot(2), self.block.slot(5), self.skip.slot(0) if self.skip is not None else None)

@@ -127,6 +127,13 @@ class Generator(nn.Module):
 
     def forward(self, data_dict):
         b200lp_lib.require_device()
+        # one batched power iteration / sigma evaluation for all 25 spectral-normalised weights of the generator
+        # (22 decoder convs, the tail conv, the two projector layers): 3 launches instead of ~14 per weight
+        convs = []
+        for i in range(self.num_blocks):
+            convs += self.decoder_blocks.slot(i).tensor_core_convs()
+        tail = self.decoder_blocks.slot(self.num_blocks + 2)
+        blocks.spectral_sigmas(convs + [tail, self.affine_params_projector.slot(0), self.affine_params_projector.slot(2)])
         affine = self.compute_affine_params(data_dict).contiguous()      # (B, sum 2C): per AdaIN [beta | gamma]
         batch = affine.shape[0]
 
@@ -141,10 +148,6 @@ class Generator(nn.Module):
         # constant (1,C,s,s) NCHW parameter -> (B,s,s,C) NHWC
         x = self.constant.constant.permute(0, 2, 3, 1).expand(batch, -1, -1, -1).contiguous()
         x_split = None
-        convs = []
-        for i in range(self.num_blocks):
-            convs += self.decoder_blocks.slot(i).tensor_core_convs()
-        blocks.spectral_sigmas(convs)          # one batched power iteration / sigma evaluation for the 22 decoder convs
         for i in range(self.num_blocks):
             blk = self.decoder_blocks.slot(i)
             g0, b0 = take(blk.in_channels)
@@ -155,7 +158,6 @@ class Generator(nn.Module):
             x, x_split = blk(x, g0, b0, g1, b1, feeds_skip_conv, x_split=x_split, precision=self.precision)
         g, bt = take(self.adain_sizes[-1])
         a = ops.adain_relu(x, g, bt, round_out=False)
-        tail = self.decoder_blocks.slot(self.num_blocks + 2)
-        fake_rgbs, fake_segm = ops.gen_tail(a, tail.weight_orig, tail.inv_sigma(), tail.bias)
+        fake_rgbs, fake_segm = ops.gen_tail(a, tail.weight_orig, tail.scale(), tail.bias)
         data_dict['fake_rgbs'] = fake_rgbs
         data_dict['fake_segm'] = fake_segm

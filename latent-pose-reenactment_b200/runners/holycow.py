@@ -91,6 +91,13 @@ class GradBucket:
         self.attach()
         self.flat.zero_()
 
+    def sinks(self):
+        """{parameter storage pointer: its gradient view} for b200lp.ops.direct_grads (CUDA buckets only)."""
+        if not self.flat.is_cuda:
+            return {}
+        self.attach()
+        return {p.data_ptr(): p.grad for p in self.params}
+
     def all_reduce(self):
         if torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
@@ -150,8 +157,33 @@ class TrainingModule(torch.nn.Module):
                     torch._foreach_mul_(p_avg, alpha)
                     torch._foreach_add_(p_avg, p_cur, alpha=1 - alpha)
                 b_avg, b_cur = list(avg.buffers()), list(cur.buffers())
-                if b_avg:
+                if b_avg and b_avg[0].is_cuda:
+                    self._copy_buffers(name, b_avg, b_cur)
+                elif b_avg:
                     torch._foreach_copy_(b_avg, b_cur)
+
+    def _copy_buffers(self, name, b_avg, b_cur):
+        """All buffer copies of one module (BatchNorm statistics, spectral-norm vectors: ~370 tiny tensors for E + G) as
+        ONE multi-tensor launch; the device-side table is cached while the buffers stay where they are."""
+        from b200lp import kernels as K
+        pairs = [(a, c) for a, c in zip(b_avg, b_cur)
+                 if a.is_contiguous() and c.is_contiguous() and a.dtype == c.dtype and a.shape == c.shape]
+        rest = [(a, c) for a, c in zip(b_avg, b_cur)
+                if not (a.is_contiguous() and c.is_contiguous() and a.dtype == c.dtype and a.shape == c.shape)]
+        for a, c in rest:
+            a.copy_(c)
+        if not pairs:
+            return
+        sig = tuple((a.data_ptr(), c.data_ptr(), a.numel() * a.element_size()) for a, c in pairs if a.numel())
+        plans = self.__dict__.setdefault('_copy_plans', {})
+        plan = plans.get(name)
+        if plan is None or plan['sig'] != sig:
+            if torch.cuda.is_current_stream_capturing():     # the table upload is not capturable
+                torch._foreach_copy_([a for a, _ in pairs], [c for _, c in pairs])
+                return
+            plan = K.copy_plan(pairs)
+            plans[name] = plan
+        K.copy_multi(plan)
 
     class _Flag:
         def __init__(self, owner, attr, value):
@@ -255,14 +287,17 @@ def train_step(training_module, data_dict, target_dict, optimizer_G, optimizer_D
     loss_G = sum(v for v in losses_G_dict.values() if isinstance(v, torch.Tensor))
     loss_D = sum(v for v in losses_D_dict.values() if isinstance(v, torch.Tensor))
 
+    from b200lp import ops
     bucket_G.zero()
-    loss_G.backward(retain_graph=True)
+    with ops.direct_grads(bucket_G.sinks()):      # conv weight / bias gradients are accumulated in place by the kernels
+        loss_G.backward(retain_graph=True)
     bucket_G.all_reduce()
     optimizer_G.step()
 
     if losses_D_dict:
         bucket_D.zero()
-        loss_D.backward()
+        with ops.direct_grads(bucket_D.sinks()):
+            loss_D.backward()
         bucket_D.all_reduce()
         optimizer_D.step()
 

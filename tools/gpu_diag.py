@@ -57,6 +57,9 @@ def _conv_case(N, H, W, Cin, Cout, k, block_n=0, bias=False, residual_mode=0, re
     elif residual_mode == 2:
         res = torch.randn(N, H // 2, W // 2, Cout, device=dev)
         ref = ref + F.interpolate(res.permute(0, 3, 1, 2).double(), scale_factor=2, mode="nearest")
+    elif residual_mode == 3:      # ReLU-backward mask
+        res = torch.randn(N, H, W, Cout, device=dev)
+        ref = ref * (res.permute(0, 3, 1, 2) > 0)
     if relu:
         ref = ref.relu()
     xh = x.permute(0, 2, 3, 1).contiguous()
@@ -89,7 +92,9 @@ def conv_small_planes():
 @check
 def conv_epilogue():
     return [_conv_case(2, 16, 16, 64, 64, 3, bias=True), _conv_case(2, 16, 16, 64, 64, 3, residual_mode=1),
-            _conv_case(2, 16, 16, 64, 64, 3, residual_mode=2, bias=True), _conv_case(2, 16, 16, 64, 64, 3, relu=True)]
+            _conv_case(2, 16, 16, 64, 64, 3, residual_mode=2, bias=True), _conv_case(2, 16, 16, 64, 64, 3, relu=True),
+            _conv_case(2, 16, 16, 64, 64, 3, residual_mode=3), _conv_case(8, 64, 64, 128, 128, 3, residual_mode=3),
+            _conv_case(8, 4, 4, 512, 512, 3, residual_mode=3), _conv_case(8, 128, 128, 64, 64, 3, residual_mode=3)]
 
 
 @check
@@ -469,6 +474,55 @@ def sn_kernels():
     torch.cuda.synchronize()
     e = _err(dw, wd.grad); e["case"] = "sn_wgrad_fix vs autograd"; e["ok"] = (not e["nan"]) and e["rel"] < 2e-5
     out.append(e)
+    return out
+
+
+@check
+def wgrad_sn_acc():
+    """conv_wgrad_sn_acc: grad += s*G - s^2 <G,W> u v^T (fused reduce / rank-1 kernels) vs float64 autograd through
+    conv2d(x, W / sigma(W)); plain accumulate form; bias_grad_acc; copy_multi."""
+    import torch
+    import torch.nn.functional as F
+    from b200lp import kernels as K
+    torch.manual_seed(5)
+    out = []
+    for (N, H, W_, Cin, Cout, k) in [(2, 32, 32, 64, 64, 3), (8, 4, 4, 512, 512, 3), (2, 32, 32, 128, 64, 1),
+                                      (8, 16, 16, 256, 512, 3), (4, 64, 64, 64, 128, 3), (8, 64, 64, 32, 32, 3)]:
+        x = tf32_round(torch.randn(N, Cin, H, W_, device="cuda"))
+        dy = tf32_round(torch.randn(N, Cout, H, W_, device="cuda"))
+        w = torch.randn(Cout, Cin, k, k, device="cuda") * 0.05
+        u = F.normalize(torch.randn(Cout, device="cuda"), dim=0)
+        v = F.normalize(torch.randn(Cin * k * k, device="cuda"), dim=0)
+        wd = w.double().requires_grad_(True)
+        sigma = torch.dot(u.double(), torch.mv(wd.reshape(Cout, -1), v.double()))
+        F.conv2d(x.double(), wd / sigma, padding=k // 2).backward(dy.double())
+        inv_sigma = (1 / sigma.detach()).float().reshape(1)
+        g_prev = torch.randn_like(w)
+        grad = g_prev.clone()
+        xh, dyh = x.permute(0, 2, 3, 1).contiguous(), dy.permute(0, 2, 3, 1).contiguous()
+        K.conv_wgrad_sn_acc(xh, dyh, k, grad, w, inv_sigma, u, v)
+        torch.cuda.synchronize()
+        e = _err(grad - g_prev, wd.grad); e["case"] = f"wgrad_sn_acc N{N} H{H} Cin{Cin} Cout{Cout} k{k}"
+        e["ok"] = (not e["nan"]) and e["rel"] < 5e-5; out.append(e)
+        # no spectral norm, overwrite
+        w0 = torch.zeros(Cout, Cin, k, k, device="cuda", dtype=torch.float64, requires_grad=True)
+        F.conv2d(x.double(), w0, padding=k // 2).backward(dy.double())
+        grad2 = torch.full_like(w, 7.0)
+        K.conv_wgrad_sn_acc(xh, dyh, k, grad2, accumulate=False)
+        torch.cuda.synchronize()
+        e = _err(grad2, w0.grad); e["case"] = f"wgrad_acc(plain, overwrite) N{N} H{H} Cin{Cin} Cout{Cout} k{k}"
+        e["ok"] = (not e["nan"]) and e["rel"] < 5e-5; out.append(e)
+    dy = torch.randn(8, 32, 32, 64, device="cuda")
+    db = torch.randn(64, device="cuda"); db0 = db.clone()
+    K.bias_grad(dy, acc_into=db)
+    e = _err(db, db0.double() + dy.double().sum((0, 1, 2))); e["case"] = "bias_grad_acc"; e["ok"] = e["rel"] < 1e-5; out.append(e)
+    srcs = [torch.randn(n, device="cuda") for n in (1, 7, 512, 4608)] + [torch.arange(3, device="cuda"),
+                                                                         torch.randint(0, 255, (13,), device="cuda", dtype=torch.uint8)]
+    dsts = [torch.zeros_like(t) for t in srcs]
+    K.copy_multi(K.copy_plan(list(zip(dsts, srcs))))
+    torch.cuda.synchronize()
+    ok = all(torch.equal(a, b) for a, b in zip(dsts, srcs))
+    out.append({"case": "copy_multi (float / int64 / uint8 buffers)", "ok": bool(ok)})
     return out
 
 
