@@ -56,15 +56,13 @@ typedef struct {
                                the spectral-norm division costs nothing and `wp` is packed once per weight update
                                instead of once per forward call (3 discriminator passes share one packing).       */
     const float* bias;      /* [Cout] or NULL                                                                    */
-    const float* residual;  /* NULL, or [N,H,W,Cout] (mode 1), or [N,H/2,W/2,Cout] (mode 2: nearest-2x source), or
-                               [N,H,W,Cout] used as a ReLU-backward mask (mode 3: y = residual > 0 ? y : 0 — the
-                               data-gradient of a conv whose input was a ReLU output, relu_bwd fused)                */
+    const float* residual;  /* NULL, or [N,H,W,Cout] (mode 1), or [N,H/2,W/2,Cout] (mode 2: nearest-2x source)    */
     float* y;               /* [N,H,W,Cout] fp32                                                                 */
     void* y_split;          /* NULL, or bf16 [2][N,H,W,Cout]: the same result as (hi, lo) planes (operand of a
                                following bf16x3 convolution)                                                    */
     int32_t N, H, W, Cin, Cout;
     int32_t ksize;          /* 1 or 3                                                  */
-    int32_t residual_mode;  /* 0 none, 1 same resolution, 2 half resolution, 3 relu mask */
+    int32_t residual_mode;  /* 0 none, 1 same resolution, 2 half resolution            */
     int32_t relu;           /* 1: y = max(y, 0)                                        */
     int32_t round_tf32;     /* 1: round y to tf32 (y only feeds further tf32 MMAs)     */
     int32_t block_n;        /* 0 = auto; else 32 / 64 / 128 / 256 (256: tf32 only)     */

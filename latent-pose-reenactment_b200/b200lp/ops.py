@@ -146,8 +146,7 @@ def _packed(weight, cache, transpose, precision=K.TF32):
     return K.pack_conv_weight(weight.detach(), None, transpose=transpose, precision=precision)
 
 
-def _conv_backward(ctx_ksize, x_f32, weight_orig, inv_sigma, dy, need_x, need_w, need_s, cache=None, sn=None,
-                   dx_mask=None):
+def _conv_backward(ctx_ksize, x_f32, weight_orig, inv_sigma, dy, need_x, need_w, need_s, cache=None, sn=None):
     """Shared backward of the tensor-core convolutions (TF32 data / weight gradient kernels).
     y = s * conv(x, W):  dx = s * conv_T(dy, W);  dW = s * wgrad(x, dy);  ds = <wgrad(x, dy), W>.
     `sn` = (u, v) snapshots of the spectral-norm vectors behind s = 1/sigma: then s carries no autograd edge and the
@@ -155,8 +154,7 @@ def _conv_backward(ctx_ksize, x_f32, weight_orig, inv_sigma, dy, need_x, need_w,
     dx = dw = ds = None
     if need_x:
         wpt = _packed(weight_orig, cache, True)
-        # dx_mask: the conv's input was produced by a ReLU whose backward is applied here, in the epilogue
-        dx = K.conv_fwd(dy, wpt, ctx_ksize, scale=inv_sigma, residual=dx_mask, residual_mode=3 if dx_mask is not None else 0)
+        dx = K.conv_fwd(dy, wpt, ctx_ksize, scale=inv_sigma)
     sink = _sink(weight_orig) if need_w and (sn is not None or inv_sigma is None) else None
     if sink is not None:
         # gradient goes straight into the parameter's .grad buffer: wgrad -> tiled reduce (+= s*G, <G,W> partials)
@@ -213,12 +211,9 @@ class Conv2dFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight_orig, inv_sigma, bias, residual, ksize, residual_mode, relu, round_out, x_split,
-                emit_split, cache, sn, relu_bwd, mask_dx):
+                emit_split, cache, sn):
         """`x_split` (optional, non-differentiable): the (hi, lo) bf16 planes of x — when given, the forward runs in
-        bf16x3 precision on them; gradients still flow to `x`.  `emit_split`: also return the (hi, lo) planes of y.
-        `relu_bwd=False` (with relu): this conv's ReLU mask is NOT applied to the incoming gradient here because the single
-        consumer of y applies it in its data-gradient epilogue — that consumer is called with `mask_dx=True` (its x is a
-        ReLU output: dx = [x > 0] * conv_T(dy), fused, no separate relu_bwd pass)."""
+        bf16x3 precision on them; gradients still flow to `x`.  `emit_split`: also return the (hi, lo) planes of y."""
         if x_split is not None:
             wp = _packed(weight_orig, cache, False, K.BF16X3)
             src = x_split
@@ -230,11 +225,10 @@ class Conv2dFn(torch.autograd.Function):
         y, y_split = out if emit_split else (out, None)
         ctx.ksize, ctx.residual_mode, ctx.relu = ksize, residual_mode, relu
         ctx.cache, ctx.sn = cache, sn
-        ctx.relu_bwd, ctx.mask_dx = relu_bwd, mask_dx
         ctx.has_bias = bias is not None
         ctx.bias_ref = bias.detach() if bias is not None else None      # alias only: identifies the gradient sink
         ctx.has_res = residual is not None
-        ctx.save_for_backward(x, weight_orig, inv_sigma, y if (relu and relu_bwd) else None)
+        ctx.save_for_backward(x, weight_orig, inv_sigma, y if relu else None)
         if emit_split:
             ctx.mark_non_differentiable(y_split)
             return y, y_split
@@ -244,11 +238,10 @@ class Conv2dFn(torch.autograd.Function):
     def backward(ctx, dy, *_unused):
         x, weight_orig, inv_sigma, y = ctx.saved_tensors
         dy = dy.contiguous()
-        if ctx.relu and ctx.relu_bwd:
+        if ctx.relu:
             dy = K.relu_bwd(y, dy)
         need_x, need_w, need_s, need_b, need_r = ctx.needs_input_grad[:5]
-        dx, dw, ds = _conv_backward(ctx.ksize, x, weight_orig, inv_sigma, dy, need_x, need_w, need_s, ctx.cache, ctx.sn,
-                                    dx_mask=x if ctx.mask_dx else None)
+        dx, dw, ds = _conv_backward(ctx.ksize, x, weight_orig, inv_sigma, dy, need_x, need_w, need_s, ctx.cache, ctx.sn)
         db = dr = None
         if ctx.has_bias and need_b:
             bsink = _sink(ctx.bias_ref)
@@ -258,15 +251,15 @@ class Conv2dFn(torch.autograd.Function):
                 db = K.bias_grad(dy)
         if ctx.has_res and need_r:
             dr = dy if ctx.residual_mode == 1 else K.upsample2_bwd(dy)
-        return dx, dw, ds, db, dr, None, None, None, None, None, None, None, None, None, None
+        return dx, dw, ds, db, dr, None, None, None, None, None, None, None, None
 
 
 def conv2d(x, weight_orig, inv_sigma=None, bias=None, residual=None, ksize=3, residual_mode=0, relu=False,
-           round_out=False, x_split=None, emit_split=False, cache=None, sn=None, relu_bwd=True, mask_dx=False):
+           round_out=False, x_split=None, emit_split=False, cache=None, sn=None):
     if residual is None:
         residual_mode = 0
     return Conv2dFn.apply(x, weight_orig, inv_sigma, bias, residual, ksize, residual_mode, relu, round_out, x_split,
-                          emit_split, cache, sn, relu_bwd, mask_dx)
+                          emit_split, cache, sn)
 
 
 class AdaINConvFn(torch.autograd.Function):

@@ -103,12 +103,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvParams& p, const 
         }
         if (rrow) {
             const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + c0 + j));
-            if (p.residual_mode == 3) {   // ReLU-backward mask: `residual` is the forward output of the ReLU
-                o.x = r.x > 0.f ? o.x : 0.f; o.y = r.y > 0.f ? o.y : 0.f;
-                o.z = r.z > 0.f ? o.z : 0.f; o.w = r.w > 0.f ? o.w : 0.f;
-            } else {
-                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-            }
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         if (p.relu) {
             o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
@@ -300,7 +295,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
             float* yrow = p.y + pix * p.Cout + n_tile * BLOCK_N;
             float* wsrow = p.ws ? p.ws + ks * p.ws_stride + pix * p.Cout + n_tile * BLOCK_N : nullptr;
             const float* rrow = nullptr;
-            if (p.residual_mode == 1 || p.residual_mode == 3) {
+            if (p.residual_mode == 1) {
                 rrow = p.residual + pix * p.Cout + n_tile * BLOCK_N;
             } else if (p.residual_mode == 2) {
                 const size_t rp = (static_cast<size_t>(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
@@ -559,7 +554,7 @@ conv_halo_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
                 const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
                 float* yrow = p.y + pix * p.Cout + n_tile * BLOCK_N;
                 const float* rrow = nullptr;
-                if (p.residual_mode == 1 || p.residual_mode == 3) {
+                if (p.residual_mode == 1) {
                     rrow = p.residual + pix * p.Cout + n_tile * BLOCK_N;
                 } else if (p.residual_mode == 2) {
                     const size_t rp = (static_cast<size_t>(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
@@ -788,7 +783,7 @@ conv_halo2_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
                 const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
                 float* yrow = p.y + pix * p.Cout + n_tile * BLOCK_N;
                 const float* rrow = nullptr;
-                if (p.residual_mode == 1 || p.residual_mode == 3) {
+                if (p.residual_mode == 1) {
                     rrow = p.residual + pix * p.Cout + n_tile * BLOCK_N;
                 } else if (p.residual_mode == 2) {
                     const size_t rp = (static_cast<size_t>(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
@@ -842,10 +837,6 @@ splitk_epilogue_kernel(const ConvParams p, long long total4) {
         if (p.residual_mode == 1) {
             const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + i * 4));
             o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        } else if (p.residual_mode == 3) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + i * 4));
-            o.x = r.x > 0.f ? o.x : 0.f; o.y = r.y > 0.f ? o.y : 0.f;
-            o.z = r.z > 0.f ? o.z : 0.f; o.w = r.w > 0.f ? o.w : 0.f;
         } else if (p.residual_mode == 2) {
             const int w = static_cast<int>(pix % p.W);
             const int h = static_cast<int>((pix / p.W) % p.H);
@@ -1115,7 +1106,7 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
                    "conv_fwd: Cin=%d Cout=%d must be positive multiples of 32", a->Cin, a->Cout);
     B200LP_REQUIRE(ilog2_exact(a->H) >= 1 && ilog2_exact(a->W) >= 1 && a->N > 0,
                    "conv_fwd: H=%d W=%d must be powers of two >= 2, N=%d > 0", a->H, a->W, a->N);
-    B200LP_REQUIRE(a->residual_mode >= 0 && a->residual_mode <= 3 && (a->residual_mode == 0 || a->residual),
+    B200LP_REQUIRE(a->residual_mode >= 0 && a->residual_mode <= 2 && (a->residual_mode == 0 || a->residual),
                    "conv_fwd: bad residual mode %d", a->residual_mode);
     B200LP_REQUIRE(a->precision == 0 || a->precision == 1, "conv_fwd: precision %d not in {0 tf32, 1 bf16x3}",
                    a->precision);

@@ -219,7 +219,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
 // shared memory, and grad / w are accessed along their contiguous (ci, tap) axis — wgrad_reduce_kernel's OIHW
 // stores are one 4-byte element per 32-byte sector.
 template <int TPB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 wgrad_reduce_acc_kernel(const float* __restrict__ ws, float* __restrict__ grad, const float* __restrict__ w,
                         const float* __restrict__ inv_sigma, float* __restrict__ dot_part, int splits, int Cin,
                         int Cout, int taps, int accumulate) {
@@ -229,27 +229,53 @@ wgrad_reduce_acc_kernel(const float* __restrict__ ws, float* __restrict__ grad, 
     const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32, tap0 = blockIdx.z * TPB;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long total = static_cast<long>(taps) * Cin * Cout;
-    // phase 1: lane = co, (ci, tap) pairs over the warps
-    for (int r = warp; r < 32 * TPB; r += 8) {
-        const int t = r / 32, cl = r - t * 32;
-        const long row = static_cast<long>(tap0 + t) * Cin + ci0 + cl;
-        const float* src = ws + row * Cout + co0 + lane;
-        float acc = 0.f;
-        for (int s = 0; s < splits; ++s) acc += __ldg(src + static_cast<long>(s) * total);
-        tile[lane * kStride + cl * TPB + t] = acc;
+    // phase 1: lane = co; warp w owns the (ci, tap) rows r = w + 8 i.  All R row loads of one split are independent and
+    // in flight together (one load at a time per warp left this kernel latency-bound: 46 us for a 512 x 512 x 9 weight)
+    constexpr int R = 32 * TPB / 8;
+    float acc[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) acc[i] = 0.f;
+    const float* src = ws + (static_cast<long>(tap0) * Cin + ci0 + warp) * Cout + co0 + lane;
+    for (int s = 0; s < splits; ++s) {
+#pragma unroll
+        for (int i = 0; i < R; ++i)   // r = warp + 8 i  ->  tap t = i / 4, channel cl = 8 (i % 4) + warp
+            acc[i] += __ldg(src + (static_cast<long>(i / 4) * Cin + 8 * (i % 4)) * Cout);
+        src += total;
     }
+#pragma unroll
+    for (int i = 0; i < R; ++i) tile[lane * kStride + (8 * (i % 4) + warp) * TPB + i / 4] = acc[i];
     __syncthreads();
     // phase 2: one output channel per warp pass, lanes along the (ci, tap) axis
     const float sc = inv_sigma ? __ldg(inv_sigma) : 1.f;
     float dot = 0.f;
-    for (int col = warp; col < 32; col += 8) {
-        const long base = (static_cast<long>(co0 + col) * Cin + ci0) * taps + tap0;
-        for (int j = lane; j < 32 * TPB; j += 32) {
-            const int cl = j / TPB, t = j - cl * TPB;
-            const long idx = base + static_cast<long>(cl) * taps + t;
-            const float g = tile[col * kStride + j];
-            if (w) dot += g * __ldg(w + idx);
-            grad[idx] = accumulate ? grad[idx] + sc * g : sc * g;
+    // all 4 x TPB loads of grad / w are issued before the first dependent store (a load -> store chain per element
+    // serialised this phase on the memory latency)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        int idx[2][TPB];                      // element offsets fit 32 bits (a weight has < 2^31 elements)
+        float gold[2][TPB], wv[2][TPB];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int col = warp + 8 * (2 * half + q);
+            const int base = ((co0 + col) * Cin + ci0) * taps + tap0;
+#pragma unroll
+            for (int k = 0; k < TPB; ++k) {
+                const int j = lane + 32 * k;
+                const int cl = j / TPB, t = j - cl * TPB;
+                idx[q][k] = base + cl * taps + t;
+                gold[q][k] = accumulate ? grad[idx[q][k]] : 0.f;
+                wv[q][k] = w ? __ldg(w + idx[q][k]) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int col = warp + 8 * (2 * half + q);
+#pragma unroll
+            for (int k = 0; k < TPB; ++k) {
+                const float g = tile[col * kStride + lane + 32 * k];
+                dot += g * wv[q][k];
+                grad[idx[q][k]] = gold[q][k] + sc * g;
+            }
         }
     }
     if (dot_part) {

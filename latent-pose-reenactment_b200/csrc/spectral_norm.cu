@@ -5,7 +5,8 @@
 //   call sites: generators/common/blocks.py:78-100, generators/vector_pose_..._noBottleneck.py:84-86,
 //               discriminators/no_landmarks.py:54-66 — executed on EVERY forward call (3x per step for D).
 //
-//   kernel A  (sn_wt_u)   : t = W^T u                       (blocks over column chunks of every weight)
+//   kernel A  (sn_wt_u)   : partial t = W^T u per slab of 128 rows (blocks over column chunks x row slabs)
+//   kernel A2 (sn_t_sum)  : t = sum of the slab partials (fixed order), |t|^2 partials per column chunk
 //   kernel B  (sn_w_v)    : s = W v_hat, v_hat = t/|t|      (blocks over row chunks of every weight)
 //   kernel C  (sn_final)  : u_new = s/|s|, sigma = |s| (= u_new^T W v_hat), writes u, v, 1/sigma, and a snapshot
 //                           copy of (u, v) for the backward pass (the buffers are overwritten by the next pass)
@@ -20,10 +21,11 @@
 
 namespace b200lp {
 
-constexpr int kSnMaxTensors = 32;   // 32 x 96-byte items = 3 KB of kernel parameters
+constexpr int kSnMaxTensors = 32;   // 32 x 112-byte items = 3.5 KB of kernel parameters (limit 4 KB)
 constexpr int kSnThreads = 256;
 constexpr int kSnColsPerBlock = 32;   // kernel A: 32 columns x 8 row groups
 constexpr int kSnRowsPerBlock = 8;    // kernel B: one warp per row
+constexpr int kSnSlabRows = 128;      // kernel A: rows per block (tall matrices - the 13056 x 768 projector - get many slabs)
 
 struct SnItem {
     const float* w;     // [rows][cols]
@@ -32,11 +34,14 @@ struct SnItem {
     float* snap_u;      // [rows]  copy of the vectors used for this pass's sigma (for backward), may be NULL
     float* snap_v;      // [cols]
     float* t;           // [cols]  scratch: W^T u
+    float* tpart;       // [slabs][cols] scratch: per-slab partial W^T u
     float* s;           // [rows]  scratch: W v
     float* part;        // scratch: partial sums, >= max(blocksA, blocksB) floats
     float* inv_sigma;   // [1]
     int rows, cols;
     int blkA0, blkB0;   // first block index of this tensor in kernels A / B
+    int blkA20;         // ... in kernel A2
+    int slabs;          // ceil(rows / kSnSlabRows)
     float eps;
     int pad;
 };
@@ -46,53 +51,83 @@ struct SnBatch {
     int count;
     int training;
 };
+static_assert(sizeof(SnBatch) <= 4096, "SnBatch travels as a by-value kernel parameter");
 
-__device__ __forceinline__ int find_tensor(const SnBatch& b, int blk, bool kernelA) {
+__device__ __forceinline__ int find_tensor(const SnBatch& b, int blk, int kernel) {
     int t = 0;
     for (int i = 1; i < b.count; ++i) {
-        const int first = kernelA ? b.it[i].blkA0 : b.it[i].blkB0;
+        const int first = kernel == 0 ? b.it[i].blkA0 : (kernel == 1 ? b.it[i].blkB0 : b.it[i].blkA20);
         if (blk >= first) t = i;
     }
     return t;
 }
 
-// t[j] = sum_i W[i][j] u[i];  part[block] = sum_j t[j]^2 over this block's columns
+// tpart[slab][j] = sum over the slab's rows i of W[i][j] u[i]
 __global__ void __launch_bounds__(kSnThreads)
 sn_wt_u_kernel(const __grid_constant__ SnBatch b) {
-    const int ti = find_tensor(b, blockIdx.x, true);
+    const int ti = find_tensor(b, blockIdx.x, 0);
     const SnItem& it = b.it[ti];
-    const int cb = blockIdx.x - it.blkA0;
+    const int local = blockIdx.x - it.blkA0;
+    const int nA = (it.cols + kSnColsPerBlock - 1) / kSnColsPerBlock;
+    const int slab = local / nA, cb = local - slab * nA;
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;     // 32 columns x 8 row groups
     const int col = cb * kSnColsPerBlock + cx;
+    const int r0 = slab * kSnSlabRows;
+    const int r1 = r0 + kSnSlabRows < it.rows ? r0 + kSnSlabRows : it.rows;
     float acc = 0.f;
-    if (col < it.cols)
-        for (int i = ry; i < it.rows; i += 8) acc += __ldg(it.w + static_cast<size_t>(i) * it.cols + col) * __ldg(it.u + i);
+    if (col < it.cols) {
+        const float* wc = it.w + col;
+#pragma unroll 4
+        for (int i = r0 + ry; i < r1; i += 8) acc += __ldg(wc + static_cast<size_t>(i) * it.cols) * __ldg(it.u + i);
+    }
     __shared__ float red[8][33];
     red[ry][cx] = acc;
     __syncthreads();
-    if (ry == 0) {
+    if (ry == 0 && col < it.cols) {
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += red[k][cx];
-        if (col < it.cols) it.t[col] = t;
-        float sq = col < it.cols ? t * t : 0.f;
+        it.tpart[static_cast<size_t>(slab) * it.cols + col] = t;
+    }
+}
+
+// t[j] = sum_slab tpart[slab][j] (fixed order);  part[block] = sum_j t[j]^2 over this block's 256 columns
+__global__ void __launch_bounds__(kSnThreads)
+sn_t_sum_kernel(const __grid_constant__ SnBatch b) {
+    const int ti = find_tensor(b, blockIdx.x, 2);
+    const SnItem& it = b.it[ti];
+    const int cb = blockIdx.x - it.blkA20;
+    const int col = cb * kSnThreads + threadIdx.x;
+    float t = 0.f;
+    if (col < it.cols) {
+        for (int k = 0; k < it.slabs; ++k) t += it.tpart[static_cast<size_t>(k) * it.cols + col];
+        it.t[col] = t;
+    }
+    float sq = t * t;
+    __shared__ float sh[kSnThreads / 32];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        if (cx == 0) it.part[cb] = sq;
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < kSnThreads / 32; ++k) tot += sh[k];
+        it.part[cb] = tot;
     }
 }
 
 // s[i] = sum_j W[i][j] vhat[j];  training: vhat = t / max(|t|, eps) (|t| from kernel A's partials), eval: vhat = v
 __global__ void __launch_bounds__(kSnThreads)
 sn_w_v_kernel(const __grid_constant__ SnBatch b) {
-    const int ti = find_tensor(b, blockIdx.x, false);
+    const int ti = find_tensor(b, blockIdx.x, 1);
     const SnItem& it = b.it[ti];
     const int rb = blockIdx.x - it.blkB0;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     float inv = 1.f;
     const float* vec = it.v;
     if (b.training) {
-        const int nA = (it.cols + kSnColsPerBlock - 1) / kSnColsPerBlock;
+        const int nA = (it.cols + kSnThreads - 1) / kSnThreads;      // |t|^2 partials of sn_t_sum_kernel
         float sq = 0.f;
         for (int k = 0; k < nA; ++k) sq += it.part[k];          // same order in every block: deterministic
         inv = 1.f / fmaxf(sqrtf(sq), it.eps);
@@ -118,7 +153,7 @@ sn_final_kernel(const __grid_constant__ SnBatch b) {
     // |t| again (for v_hat) and |s|^2 or u.s
     float a = 0.f;
     if (b.training) {
-        const int nA = (it.cols + kSnColsPerBlock - 1) / kSnColsPerBlock;
+        const int nA = (it.cols + kSnThreads - 1) / kSnThreads;
         if (threadIdx.x == 0) {
             float sq = 0.f;
             for (int k = 0; k < nA; ++k) sq += it.part[k];
@@ -205,9 +240,9 @@ using namespace b200lp;
 extern "C" int32_t b200lp_sn_max_tensors(void) { return kSnMaxTensors; }
 
 extern "C" int64_t b200lp_sn_scratch_floats(int32_t rows, int32_t cols) {
-    const int nA = (cols + kSnColsPerBlock - 1) / kSnColsPerBlock;
-    const int nB = (rows + kSnRowsPerBlock - 1) / kSnRowsPerBlock;
-    return static_cast<int64_t>(cols) + rows + (nA > nB ? nA : nB);   // t, s, partials
+    const int nA2 = (cols + kSnThreads - 1) / kSnThreads;
+    const int slabs = (rows + kSnSlabRows - 1) / kSnSlabRows;
+    return static_cast<int64_t>(cols) + rows + nA2 + static_cast<int64_t>(slabs) * cols;   // t, s, |t|^2 partials, slab partials
 }
 
 extern "C" int32_t b200lp_sn_sigma_multi(const b200lp_sn_item* items, int32_t count, int32_t training, void* stream) {
@@ -216,23 +251,30 @@ extern "C" int32_t b200lp_sn_sigma_multi(const b200lp_sn_item* items, int32_t co
     SnBatch b;
     b.count = count;
     b.training = training;
-    int blkA = 0, blkB = 0;
+    int blkA = 0, blkB = 0, blkA2 = 0;
     for (int i = 0; i < count; ++i) {
         const b200lp_sn_item& s = items[i];
         B200LP_REQUIRE(s.w && s.u && s.v && s.scratch && s.inv_sigma && s.rows > 0 && s.cols > 0,
                        "sn_sigma_multi: bad item %d", i);
         SnItem& d = b.it[i];
         d.w = s.w; d.u = s.u; d.v = s.v; d.snap_u = s.snap_u; d.snap_v = s.snap_v;
+        const int nA2 = (s.cols + kSnThreads - 1) / kSnThreads;
         d.t = s.scratch; d.s = s.scratch + s.cols; d.part = s.scratch + s.cols + s.rows;
+        d.tpart = d.part + nA2;
         d.inv_sigma = s.inv_sigma;
         d.rows = s.rows; d.cols = s.cols; d.eps = s.eps; d.pad = 0;
-        d.blkA0 = blkA; d.blkB0 = blkB;
-        blkA += (s.cols + kSnColsPerBlock - 1) / kSnColsPerBlock;
+        d.slabs = (s.rows + kSnSlabRows - 1) / kSnSlabRows;
+        d.blkA0 = blkA; d.blkB0 = blkB; d.blkA20 = blkA2;
+        blkA += ((s.cols + kSnColsPerBlock - 1) / kSnColsPerBlock) * d.slabs;
         blkB += (s.rows + kSnRowsPerBlock - 1) / kSnRowsPerBlock;
+        blkA2 += nA2;
     }
     cudaStream_t st = as_stream(stream);
     if (training) {
         sn_wt_u_kernel<<<blkA, kSnThreads, 0, st>>>(b);
+        B200LP_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+        sn_t_sum_kernel<<<blkA2, kSnThreads, 0, st>>>(b);
         B200LP_CHECK_CUDA(cudaGetLastError());
         count_launch();
     }

@@ -234,8 +234,7 @@ class PlainResBlock(nn.Module):
     def forward(self, r, detach_params=False):
         """r = tf32(relu(block input)).  Returns the block output (pre-ReLU)."""
         w0, s0, b0, e0 = self.block.slot(2).operands(detach_params)
-        # h has exactly one consumer (the second conv): its ReLU backward runs in that conv's data-gradient epilogue
-        h = ops.conv2d(r, w0, s0, bias=b0, ksize=3, relu=True, round_out=True, relu_bwd=False, **e0)
+        h = ops.conv2d(r, w0, s0, bias=b0, ksize=3, relu=True, round_out=True, **e0)
         w1, s1, b1, e1 = self.block.slot(5).operands(detach_params)
         if self.skip is not None:
             ws, ss, bs, es = self.skip.slot(0).operands(detach_params)
@@ -244,9 +243,9 @@ class PlainResBlock(nn.Module):
         else:
             s = r
         if self.downsample:
-            h2 = ops.conv2d(h, w1, s1, bias=b1, ksize=3, mask_dx=True, **e1)
+            h2 = ops.conv2d(h, w1, s1, bias=b1, ksize=3, **e1)
             return ops.avgpool2(h2, s)
-        return ops.conv2d(h, w1, s1, bias=b1, residual=s, residual_mode=1, ksize=3, mask_dx=True, **e1)
+        return ops.conv2d(h, w1, s1, bias=b1, residual=s, residual_mode=1, ksize=3, **e1)
 
     def tensor_core_convs(self):
         return [m for m in (self.block.slot(2), self.block.slot(5), self.skip.slot(0) if self.skip is not None else None)

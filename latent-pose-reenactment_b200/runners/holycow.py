@@ -15,6 +15,7 @@ Differences that do not change results:
 import copy
 import itertools
 import logging
+import os
 import time
 
 import torch
@@ -93,7 +94,7 @@ class GradBucket:
 
     def sinks(self):
         """{parameter storage pointer: its gradient view} for b200lp.ops.direct_grads (CUDA buckets only)."""
-        if not self.flat.is_cuda:
+        if not self.flat.is_cuda or os.environ.get('B200LP_NO_GRAD_SINKS'):   # env switch: A/B measurements only
             return {}
         self.attach()
         return {p.data_ptr(): p.grad for p in self.params}

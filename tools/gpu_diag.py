@@ -57,9 +57,6 @@ def _conv_case(N, H, W, Cin, Cout, k, block_n=0, bias=False, residual_mode=0, re
     elif residual_mode == 2:
         res = torch.randn(N, H // 2, W // 2, Cout, device=dev)
         ref = ref + F.interpolate(res.permute(0, 3, 1, 2).double(), scale_factor=2, mode="nearest")
-    elif residual_mode == 3:      # ReLU-backward mask
-        res = torch.randn(N, H, W, Cout, device=dev)
-        ref = ref * (res.permute(0, 3, 1, 2) > 0)
     if relu:
         ref = ref.relu()
     xh = x.permute(0, 2, 3, 1).contiguous()
@@ -92,9 +89,7 @@ def conv_small_planes():
 @check
 def conv_epilogue():
     return [_conv_case(2, 16, 16, 64, 64, 3, bias=True), _conv_case(2, 16, 16, 64, 64, 3, residual_mode=1),
-            _conv_case(2, 16, 16, 64, 64, 3, residual_mode=2, bias=True), _conv_case(2, 16, 16, 64, 64, 3, relu=True),
-            _conv_case(2, 16, 16, 64, 64, 3, residual_mode=3), _conv_case(8, 64, 64, 128, 128, 3, residual_mode=3),
-            _conv_case(8, 4, 4, 512, 512, 3, residual_mode=3), _conv_case(8, 128, 128, 64, 64, 3, residual_mode=3)]
+            _conv_case(2, 16, 16, 64, 64, 3, residual_mode=2, bias=True), _conv_case(2, 16, 16, 64, 64, 3, relu=True)]
 
 
 @check
