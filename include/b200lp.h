@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 14
+#define B200LP_ABI_VERSION 15
 
 #define B200LP_OK 0
 #define B200LP_EINVAL (-1)   /* bad shape / unsupported configuration */
@@ -294,6 +294,42 @@ int32_t b200lp_bias_grad_acc(const float* dy, float* db, int64_t pixels, int32_t
  * int64 nbytes}.  Replaces the per-buffer copies of TrainingModule.update_running_average (runners/holycow.py:106-109:
  * BatchNorm statistics and spectral-norm vectors of E and G, ~370 tensors per step). */
 int32_t b200lp_copy_multi(const void* table_dev, int32_t count, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Pose encoder (torchvision MobileNetV2) forward — FP32 CUDA-core kernels (csrc/mobilenet.cu).
+ * Replaces Embedder.get_pose_embedding (embedders/unsupervised_pose_separate_embResNeXt_segmentation.py:56-58):
+ * Conv2d(1x1 | depthwise 3x3 | 3x3 stride-2 stem) + BatchNorm2d(eps 1e-5, momentum 0.1, train-mode batch statistics or
+ * eval-mode running statistics) + ReLU6, inverted-residual skips, adaptive average pool, Linear.
+ * Activations NHWC fp32.  A conv kernel applies the PRODUCER layer's BatchNorm (+ReLU6) on load through per-channel
+ * (scale, shift), writes its own raw output, and (if `part` != NULL) per-channel [part][2][C] sum / sum-of-squares
+ * partials of that output for b200lp_bn_finalize.  All channel counts must be multiples of 4.
+ */
+/* 1x1 conv / linear: y[M][Cout] = f(x)[M][Cin] . w[Cout][Cin]^T (+ bias);  f(v) = v (in_scale NULL), v*scale+shift,
+ * or relu6(v*scale+shift) (in_relu6).  `part`: b200lp_pw_conv_parts(M, Cout) x 2 x Cout floats, or NULL. */
+int32_t b200lp_pw_conv_parts(int64_t M, int32_t Cout);
+int32_t b200lp_pw_conv(const float* x, const float* in_scale, const float* in_shift, int32_t in_relu6, const float* w,
+                       const float* bias, float* y, float* part, int64_t M, int32_t Cin, int32_t Cout, void* stream);
+/* depthwise 3x3, padding 1, stride 1 or 2, on relu6(x*scale+shift); w [C][1][3][3]; y [N,Ho,Wo,C] raw;
+ * `part`: b200lp_dw_conv3x3_parts(N,H,W,stride) x 2 x C floats, or NULL. */
+int32_t b200lp_dw_conv3x3_parts(int32_t N, int32_t H, int32_t W, int32_t stride);
+int32_t b200lp_dw_conv3x3(const float* x, const float* in_scale, const float* in_shift, const float* w, float* y,
+                          float* part, int32_t N, int32_t H, int32_t W, int32_t C, int32_t stride, void* stream);
+/* stem: 3x3 stride-2 conv 3 -> 32 on the NCHW image; y [N,H/2,W/2,32] raw; part: b200lp_mbv2_stem_parts x 2 x 32 */
+int32_t b200lp_mbv2_stem_parts(int32_t N, int32_t H, int32_t W);
+int32_t b200lp_mbv2_stem(const float* x_nchw, const float* w, float* y_nhwc, float* part, int32_t N, int32_t H,
+                         int32_t W, void* stream);
+/* training != 0: batch mean / biased variance over `count` samples from the partials (fp64 merge, fixed order) ->
+ * scale = gamma*rstd, shift = beta - mean*scale; running_mean / running_var (unbiased) / num_batches_tracked updated
+ * like nn.BatchNorm2d (any of the three may be NULL).  training == 0: scale / shift from the running statistics. */
+int32_t b200lp_bn_finalize(const float* part, int32_t nparts, int64_t count, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                           float eps, float* scale, float* shift, int32_t C, int32_t training, void* stream);
+/* y = x*scale[c] + shift[c] (+ residual) (relu6): materialises an inverted-residual block output */
+int32_t b200lp_bn_apply(const float* x, const float* scale, const float* shift, const float* residual, float* y,
+                        int64_t M, int32_t C, int32_t relu6, void* stream);
+/* y[n][c] = mean_p relu6(x[n,p,c]*scale[c] + shift[c])   (features.18 BN + ReLU6 + adaptive_avg_pool2d(1)) */
+int32_t b200lp_bn_relu6_avgpool(const float* x, const float* scale, const float* shift, float* y, int32_t N, int32_t HW,
+                                int32_t C, void* stream);
 
 #ifdef __cplusplus
 }

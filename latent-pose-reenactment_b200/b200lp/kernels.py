@@ -508,3 +508,94 @@ def sn_wgrad_fix(g, w, inv_sigma, u, v):
         L.check(lib.b200lp_sn_wgrad_fix(L.ptr(g), L.ptr(w.detach().contiguous()), L.ptr(inv_sigma), L.ptr(u), L.ptr(v),
                                         L.ptr(dw), L.ptr(ws), rows, cols, L.stream_ptr()), "sn_wgrad_fix")
     return dw
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Pose encoder (MobileNetV2) forward kernels — csrc/mobilenet.cu
+# ---------------------------------------------------------------------------------------------------------------------
+def pw_conv(x2d, weight, in_scale=None, in_shift=None, in_relu6=False, bias=None, want_stats=False):
+    """y (M, Cout) = f(x2d (M, Cin)) @ weight (Cout, Cin)^T (+ bias); f = producer BatchNorm (+ReLU6) applied on load.
+    Returns y or (y, part) with part (parts, 2, Cout) per-channel sum / sum-of-squares partials of y."""
+    lib = L.load()
+    m, cin = x2d.shape
+    cout = weight.shape[0]
+    assert weight.numel() == cout * cin
+    y = torch.empty((m, cout), dtype=torch.float32, device=x2d.device)
+    part = None
+    if want_stats:
+        part = torch.empty((lib.b200lp_pw_conv_parts(m, cout), 2, cout), dtype=torch.float32, device=x2d.device)
+    with _timed("pose_encoder", flops=2.0 * m * cin * cout):
+        L.check(lib.b200lp_pw_conv(L.ptr(x2d), L.ptr(in_scale), L.ptr(in_shift), int(in_relu6), L.ptr(weight), L.ptr(bias),
+                                   L.ptr(y), L.ptr(part), m, cin, cout, L.stream_ptr()), "pw_conv")
+    return (y, part) if want_stats else y
+
+
+def dw_conv3x3(x, weight, in_scale, in_shift, stride, want_stats=False):
+    """Depthwise 3x3 (padding 1) on relu6(x*scale+shift); x (N,H,W,C) raw producer output -> y (N,Ho,Wo,C) raw."""
+    lib = L.load()
+    n, h, w, c = x.shape
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    y = torch.empty((n, ho, wo, c), dtype=torch.float32, device=x.device)
+    part = None
+    if want_stats:
+        part = torch.empty((lib.b200lp_dw_conv3x3_parts(n, h, w, stride), 2, c), dtype=torch.float32, device=x.device)
+    with _timed("pose_encoder", nbytes=4.0 * (x.numel() + y.numel())):
+        L.check(lib.b200lp_dw_conv3x3(L.ptr(x), L.ptr(in_scale), L.ptr(in_shift), L.ptr(weight), L.ptr(y), L.ptr(part),
+                                      n, h, w, c, stride, L.stream_ptr()), "dw_conv3x3")
+    return (y, part) if want_stats else y
+
+
+def mbv2_stem(x_nchw, weight, want_stats=False):
+    """3x3 stride-2 conv 3 -> 32 on the NCHW image -> (N, H/2, W/2, 32) NHWC raw."""
+    lib = L.load()
+    n, c, h, w = x_nchw.shape
+    assert c == 3 and tuple(weight.shape) == (32, 3, 3, 3)
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = torch.empty((n, ho, wo, 32), dtype=torch.float32, device=x_nchw.device)
+    part = None
+    if want_stats:
+        part = torch.empty((lib.b200lp_mbv2_stem_parts(n, h, w), 2, 32), dtype=torch.float32, device=x_nchw.device)
+    with _timed("pose_encoder", nbytes=4.0 * (x_nchw.numel() + y.numel())):
+        L.check(lib.b200lp_mbv2_stem(L.ptr(x_nchw), L.ptr(weight), L.ptr(y), L.ptr(part), n, h, w, L.stream_ptr()),
+                "mbv2_stem")
+    return (y, part) if want_stats else y
+
+
+def bn_finalize(bn, part, count, training):
+    """(scale, shift) of a torch BatchNorm2d module `bn` for the kernels' on-load normalisation.  training: batch
+    statistics from `part` (+ running-statistics update in place, like the module's forward); else running stats."""
+    lib = L.load()
+    c = bn.num_features
+    dev = bn.weight.device
+    scale = torch.empty(c, dtype=torch.float32, device=dev)
+    shift = torch.empty(c, dtype=torch.float32, device=dev)
+    track = bn.track_running_stats and bn.running_mean is not None
+    nbt = bn.num_batches_tracked if (training and track and bn.num_batches_tracked is not None) else None
+    L.check(lib.b200lp_bn_finalize(L.ptr(part), part.shape[0] if part is not None else 0, int(count),
+                                   L.ptr(bn.weight.detach()), L.ptr(bn.bias.detach()),
+                                   L.ptr(bn.running_mean) if track else None, L.ptr(bn.running_var) if track else None,
+                                   L.ptr(nbt, torch.int64), c_float(bn.momentum if bn.momentum is not None else 0.1),
+                                   c_float(bn.eps), L.ptr(scale), L.ptr(shift), c, int(training), L.stream_ptr()),
+            "bn_finalize")
+    return scale, shift
+
+
+def bn_apply(x, scale, shift, residual=None, relu6=False):
+    lib = L.load()
+    c = x.shape[-1]
+    y = torch.empty_like(x)
+    with _timed("pose_encoder", nbytes=4.0 * x.numel() * (3 if residual is not None else 2)):
+        L.check(lib.b200lp_bn_apply(L.ptr(x), L.ptr(scale), L.ptr(shift), L.ptr(residual), L.ptr(y), x.numel() // c, c,
+                                    int(relu6), L.stream_ptr()), "bn_apply")
+    return y
+
+
+def bn_relu6_avgpool(x, scale, shift):
+    """x (N,H,W,C) raw -> (N, C): spatial mean of relu6(x*scale+shift)."""
+    lib = L.load()
+    n, h, w, c = x.shape
+    y = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    with _timed("pose_encoder", nbytes=4.0 * x.numel()):
+        L.check(lib.b200lp_bn_relu6_avgpool(L.ptr(x), L.ptr(scale), L.ptr(shift), L.ptr(y), n, h * w, c, L.stream_ptr()),
+                "bn_relu6_avgpool")
+    return y

@@ -13,7 +13,7 @@ import torch
 
 _PKG = Path(__file__).resolve().parent.parent
 LIB_PATH = _PKG / "lib" / "libb200lp.so"
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 
 class B200lpError(RuntimeError):
@@ -101,6 +101,15 @@ SIGNATURES = {
     "b200lp_bias_grad": (_I, [_P, _P, _L, _I, _P]),
     "b200lp_bias_grad_acc": (_I, [_P, _P, _L, _I, _P]),
     "b200lp_copy_multi": (_I, [_P, _I, _P]),
+    "b200lp_pw_conv_parts": (_I, [_L, _I]),
+    "b200lp_pw_conv": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _L, _I, _I, _P]),
+    "b200lp_dw_conv3x3_parts": (_I, [_I, _I, _I, _I]),
+    "b200lp_dw_conv3x3": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200lp_mbv2_stem_parts": (_I, [_I, _I, _I]),
+    "b200lp_mbv2_stem": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "b200lp_bn_finalize": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _P]),
+    "b200lp_bn_apply": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P]),
+    "b200lp_bn_relu6_avgpool": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "b200lp_adam_ema_multi": (_I, [_P, _P, _P, _I, _L, _P, _F, _F, _F, _F, _F, _I, _I, _P]),
     "b200lp_ema_multi": (_I, [_P, _P, _P, _I, _L, _F, _P]),
 }

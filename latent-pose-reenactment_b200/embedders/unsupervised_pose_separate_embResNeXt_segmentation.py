@@ -7,6 +7,8 @@ These two encoders are stock torchvision networks in the reference as well (grou
 train-mode BatchNorm); they stay on torch/cuDNN in this round — SURVEY.md §8(f) next-3 — so the state_dict (634
 torchvision keys under `identity_encoder.` / `pose_encoder.`) and numerics are identical by construction.
 """
+import os
+
 import torch
 from torch import nn
 
@@ -47,7 +49,25 @@ class Embedder(nn.Module):
         data_dict['embeds_elemwise'] = per_frame
 
     def get_pose_embedding(self, data_dict):
-        data_dict['pose_embedding'] = self.pose_encoder(data_dict['pose_input_rgbs'][:, 0])
+        x = data_dict['pose_input_rgbs'][:, 0]
+        if self._native_pose_path(x):
+            # libb200lp schedule of the same MobileNetV2 (csrc/mobilenet.cu): ~125 launches instead of ~300
+            from embedders import mobilenet_native
+            data_dict['pose_embedding'] = mobilenet_native.forward(self.pose_encoder, x)
+        else:
+            data_dict['pose_embedding'] = self.pose_encoder(x)
+
+    def _native_pose_path(self, x):
+        """The kernel schedule has no backward: it serves every call that needs no gradient through the encoder
+        (drive.py, fine-tuning with the encoder frozen, running-average forward passes)."""
+        if not x.is_cuda or x.dtype != torch.float32 or os.environ.get('B200LP_TORCH_POSE_ENCODER'):
+            return False
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.pose_encoder.parameters())):
+            return False
+        from embedders import mobilenet_native
+        if self.__dict__.get('_native_ok') is None:
+            self.__dict__['_native_ok'] = mobilenet_native.supported(self.pose_encoder)
+        return self.__dict__['_native_ok']
 
     def forward(self, data_dict):
         if not self.finetuning:

@@ -522,6 +522,122 @@ def wgrad_sn_acc():
 
 
 @check
+def pose_encoder():
+    """Native MobileNetV2 forward (csrc/mobilenet.cu schedule) vs the torchvision module in float64: train mode (batch
+    statistics, running-stat updates, num_batches_tracked) and eval mode; single kernels vs torch ops."""
+    import copy
+    import torch
+    import torch.nn.functional as F
+    import torchvision
+    from b200lp import kernels as K
+    from embedders import mobilenet_native
+    torch.manual_seed(3)
+    out = []
+
+    def add(name, a, b, tol=2e-5):
+        e = _err(a, b); e["case"] = name; e["ok"] = (not e["nan"]) and e["rel"] < tol; out.append(e)
+
+    # --- single kernels
+    x = torch.randn(300, 24, device="cuda"); w = torch.randn(144, 24, device="cuda") * 0.2
+    sc = torch.rand(24, device="cuda") + 0.5; sh = torch.randn(24, device="cuda")
+    y, part = K.pw_conv(x, w, sc, sh, True, want_stats=True)
+    ref = torch.clamp(x.double() * sc.double() + sh.double(), 0, 6) @ w.double().t()
+    add("pw_conv relu6(bn) M300 K24 N144", y, ref)
+    add("pw_conv stats sum", part[:, 0].sum(0), ref.sum(0), 1e-4)
+    add("pw_conv stats sumsq", part[:, 1].sum(0), (ref * ref).sum(0), 1e-4)
+    b = torch.randn(256, device="cuda"); x2 = torch.randn(8, 1280, device="cuda"); w2 = torch.randn(256, 1280, device="cuda") * 0.05
+    add("pw_conv linear+bias M8", K.pw_conv(x2, w2, bias=b), x2.double() @ w2.double().t() + b.double())
+    for (N, H, C, stride) in [(2, 16, 96, 2), (3, 8, 960, 1), (2, 32, 32, 1), (1, 7, 144, 2)]:
+        xd = torch.randn(N, H, H, C, device="cuda"); wd = torch.randn(C, 1, 3, 3, device="cuda")
+        sc = torch.rand(C, device="cuda") + 0.5; sh = torch.randn(C, device="cuda")
+        yd, part = K.dw_conv3x3(xd, wd, sc, sh, stride, want_stats=True)
+        a = torch.clamp(xd.double() * sc.double() + sh.double(), 0, 6).permute(0, 3, 1, 2)
+        ref = F.conv2d(a, wd.double(), stride=stride, padding=1, groups=C).permute(0, 2, 3, 1)
+        add(f"dw_conv3x3 N{N} H{H} C{C} s{stride}", yd, ref)
+        add(f"dw_conv3x3 stats N{N} H{H} C{C} s{stride}", part[:, 0].sum(0), ref.sum((0, 1, 2)), 1e-4)
+    xi = torch.rand(2, 3, 64, 64, device="cuda"); ws = torch.randn(32, 3, 3, 3, device="cuda")
+    ys, part = K.mbv2_stem(xi, ws, want_stats=True)
+    ref = F.conv2d(xi.double(), ws.double(), stride=2, padding=1).permute(0, 2, 3, 1)
+    add("mbv2_stem", ys, ref)
+    add("mbv2_stem stats sumsq", part[:, 1].sum(0), (ref * ref).sum((0, 1, 2)), 1e-4)
+
+    # --- whole network
+    net = torchvision.models.mobilenet_v2(num_classes=256).cuda()
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.2)
+                m.running_mean.normal_(0, 0.3); m.running_var.uniform_(0.5, 2.0)
+    net.classifier[0].p = 0.0
+    assert mobilenet_native.supported(net)
+    for (N, S) in [(8, 256), (3, 128)]:
+        xin = torch.rand(N, 3, S, S, device="cuda")
+        for mode in ("train", "eval"):
+            a, b64 = copy.deepcopy(net), copy.deepcopy(net).double()
+            a.train(mode == "train"); b64.train(mode == "train")
+            with torch.no_grad():
+                ya = mobilenet_native.forward(a, xin)
+                yb = b64(xin.double())
+            torch.cuda.synchronize()
+            add(f"mobilenet_v2 {mode} N{N} S{S} output", ya, yb, 2e-4)
+            if mode == "train":
+                bns_a = [m for m in a.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+                bns_b = [m for m in b64.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+                em = max(_err(p.running_mean, q.running_mean)["rel"] for p, q in zip(bns_a, bns_b))
+                ev = max(_err(p.running_var, q.running_var)["rel"] for p, q in zip(bns_a, bns_b))
+                nb = all(int(p.num_batches_tracked) == int(q.num_batches_tracked) == 1 for p, q in zip(bns_a, bns_b))
+                out.append({"case": f"mobilenet_v2 train N{N} S{S} running stats", "rel_mean": em, "rel_var": ev,
+                            "num_batches_tracked": nb, "ok": em < 1e-4 and ev < 1e-4 and nb})
+    # timing: native vs torch module, train mode bs 8 (the fine-tuning step's call) and eval bs 64 (drive.py)
+    for (N, mode) in [(8, "train"), (64, "eval")]:
+        xin = torch.rand(N, 3, 256, 256, device="cuda")
+        a = copy.deepcopy(net); a.train(mode == "train")
+        with torch.no_grad():
+            t_native = _time_us(lambda: mobilenet_native.forward(a, xin))
+            t_torch = _time_us(lambda: a(xin))
+        out.append({"case": f"timing {mode} N{N}", "native_us": round(t_native, 1), "torch_us": round(t_torch, 1), "ok": True})
+    return out
+
+
+@check
+def pose_timing():
+    """Per-layer time of the pose-encoder kernels at drive.py's batch (64) and a training step's (8): TFLOP/s for the
+    1x1 convs, GB/s (input + output bytes) for the depthwise ones."""
+    import torch
+    from b200lp import kernels as K
+    out = []
+    pw_shapes = [(16384, 32, 16), (16384, 16, 96), (4096, 96, 24), (4096, 24, 144), (4096, 144, 24), (1024, 144, 32),
+                 (1024, 32, 192), (1024, 192, 32), (256, 192, 64), (256, 64, 384), (256, 384, 64), (256, 384, 96),
+                 (256, 96, 576), (256, 576, 96), (64, 576, 160), (64, 160, 960), (64, 960, 160), (64, 960, 320),
+                 (64, 320, 1280)]
+    dw_shapes = [(128, 32, 1), (128, 96, 2), (64, 144, 1), (64, 144, 2), (32, 192, 1), (32, 192, 2), (16, 384, 1),
+                 (16, 576, 1), (16, 576, 2), (8, 960, 1)]
+    for batch in (64, 8):
+        tot = 0.0
+        for (hw, cin, cout) in pw_shapes:
+            m = batch * hw
+            x = torch.randn(m, cin, device="cuda"); w = torch.randn(cout, cin, device="cuda")
+            sc = torch.rand(cin, device="cuda"); sh = torch.randn(cin, device="cuda")
+            t = _time_us(lambda: K.pw_conv(x, w, sc, sh, True, want_stats=True), reps=5)
+            tot += t
+            out.append({"case": f"pw b{batch} M{m} {cin}->{cout}", "us": round(t, 1),
+                        "tflops": round(2.0 * m * cin * cout / t * 1e-6, 2),
+                        "gbs": round(4.0 * m * (cin + cout) / t * 1e-3, 0), "ok": True})
+        out.append({"case": f"pw b{batch} total (each distinct shape once)", "us": round(tot, 1), "ok": True})
+        tot = 0.0
+        for (h, c, stride) in dw_shapes:
+            x = torch.randn(batch, h, h, c, device="cuda"); w = torch.randn(c, 1, 3, 3, device="cuda")
+            sc = torch.rand(c, device="cuda"); sh = torch.randn(c, device="cuda")
+            t = _time_us(lambda: K.dw_conv3x3(x, w, sc, sh, stride, want_stats=True), reps=5)
+            tot += t
+            ho = (h - 1) // stride + 1
+            out.append({"case": f"dw b{batch} {h}x{h} C{c} s{stride}", "us": round(t, 1),
+                        "gbs": round(4.0 * batch * c * (h * h + ho * ho) / t * 1e-3, 0), "ok": True})
+        out.append({"case": f"dw b{batch} total (each distinct shape once)", "us": round(tot, 1), "ok": True})
+    return out
+
+
+@check
 def fused_optim():
     """Fused Adam / RAdam + EMA kernel vs torch.optim.Adam and a per-tensor RAdam port, 8 steps."""
     import torch
