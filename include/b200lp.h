@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 15
+#define B200LP_ABI_VERSION 16
 
 #define B200LP_OK 0
 #define B200LP_EINVAL (-1)   /* bad shape / unsupported configuration */
@@ -254,10 +254,15 @@ int32_t b200lp_col2im3x3_c3(const float* dcol_nhwc32, const float* pre_scale, fl
 int32_t b200lp_gen_tail_fwd(const float* x_nhwc, const float* w_oihw, const float* wscale, const float* bias,
                             float* fake_rgbs_nchw, float* fake_segm_nchw, float* t_out, int32_t N, int32_t H,
                             int32_t W, int32_t Cin, void* stream);
+/* Tensor-core form of the same tail: the 3x3 conv runs as b200lp_conv_fwd (bf16x3) on a weight zero-padded to 32 output
+ * channels; this entry point is the remaining composition  t = tanh(a[..., 0:4] + bias) -> fake_rgbs, fake_segm, t_out.
+ * `a_nhwc` has `a_stride` floats per pixel (32). */
+int32_t b200lp_gen_tail_compose(const float* a_nhwc, const float* bias, float* fake_rgbs_nchw, float* fake_segm_nchw,
+                                float* t_out, int32_t N, int32_t H, int32_t W, int32_t a_stride, void* stream);
 /* backward: from d(fake_rgbs) [N,3,H,W], d(fake_segm) [N,1,H,W] (either may be NULL) and saved t:
  * da [N,H,W,4] (pre-tanh gradient), then dx = conv-transpose, dw, dbias */
 /* da has `da_stride` (4 or 32) floats per pixel; with 32 the 28 extra channels are written as zeros so that `da` is a
- * 32-channel NHWC tensor the tensor-core weight-gradient kernel (b200lp_conv_wgrad) accepts. */
+ * 32-channel NHWC tensor the tensor-core weight- / data-gradient kernels accept (values rounded to tf32 in that form). */
 int32_t b200lp_gen_tail_bwd_act(const float* t, const float* d_rgbs, const float* d_segm, float* da, int32_t N,
                                 int32_t H, int32_t W, int32_t da_stride, void* stream);
 int32_t b200lp_gen_tail_bwd_data(const float* da, const float* w_oihw, const float* wscale, float* dx_nhwc,

@@ -382,6 +382,31 @@ def gen_tail_fwd(x, w, wscale, bias):
     return rgbs, segm, t
 
 
+def gen_tail_compose(a32, bias):
+    """a32 (N,H,W,32): tensor-core conv output whose first 4 channels are the tail's pre-tanh values (bias not yet added)
+    -> fake_rgbs (N,3,H,W), fake_segm (N,1,H,W), t (N,H,W,4)."""
+    lib = L.load()
+    n, h, wd, stride = a32.shape
+    rgbs = torch.empty((n, 3, h, wd), dtype=torch.float32, device=a32.device)
+    segm = torch.empty((n, 1, h, wd), dtype=torch.float32, device=a32.device)
+    t = torch.empty((n, h, wd, 4), dtype=torch.float32, device=a32.device)
+    with _timed("gen_tail_fwd", nbytes=4.0 * (a32.numel() // 8 * 2 + rgbs.numel() + segm.numel() + t.numel())):
+        L.check(lib.b200lp_gen_tail_compose(L.ptr(a32), L.ptr(bias), L.ptr(rgbs), L.ptr(segm), L.ptr(t), n, h, wd, stride,
+                                            L.stream_ptr()), "gen_tail_compose")
+    return rgbs, segm, t
+
+
+def gen_tail_bwd_act(t, d_rgbs, d_segm, stride=32):
+    """Pre-tanh gradient (N,H,W,stride): 4 real channels, zero padded (and tf32-rounded) when stride is 32."""
+    lib = L.load()
+    n, h, wd, _ = t.shape
+    da = torch.empty((n, h, wd, stride), dtype=torch.float32, device=t.device)
+    with _timed("gen_tail_bwd_act", nbytes=4.0 * (da.numel() + 2 * t.numel())):
+        L.check(lib.b200lp_gen_tail_bwd_act(L.ptr(t), L.ptr(d_rgbs), L.ptr(d_segm), L.ptr(da), n, h, wd, stride,
+                                            L.stream_ptr()), "gen_tail_bwd_act")
+    return da
+
+
 def gen_tail_bwd(x, t, w, wscale, d_rgbs, d_segm, need_dx=True, need_dw=True):
     """Backward of the generator tail.  Returns (dx, g, db): g = gradient w.r.t. the scaled weight (w*wscale), OIHW.
     The weight gradient runs on the tensor cores: the 4-channel pre-tanh gradient is written as a zero-padded

@@ -13,7 +13,7 @@ import torch
 
 _PKG = Path(__file__).resolve().parent.parent
 LIB_PATH = _PKG / "lib" / "libb200lp.so"
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 
 class B200lpError(RuntimeError):
@@ -93,6 +93,7 @@ SIGNATURES = {
     "b200lp_conv3x3_c3_dgrad": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200lp_conv3x3_c3_wgrad": (_I, [_P, _P, _P, _F, _I, _I, _I, _I, _P]),
     "b200lp_gen_tail_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_gen_tail_compose": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200lp_gen_tail_bwd_act": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200lp_gen_tail_bwd_data": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200lp_im2col3x3_c3": (_I, [_P, _P, _I, _I, _I, _P]),

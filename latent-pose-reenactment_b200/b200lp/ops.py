@@ -371,6 +371,67 @@ def gen_tail(x, weight_orig, inv_sigma, bias):
     return GenTailFn.apply(x, weight_orig, inv_sigma, bias)
 
 
+def tail_tensor_core_ok(x, weight_orig):
+    """The generator tail runs on the tensor cores when the halo kernel takes the shape (Cin % 64 == 0, power-of-two
+    plane >= 32 x 16, 4 output channels); otherwise the CUDA-core kernels of GenTailFn are used."""
+    n, h, w, c = x.shape
+    pow2 = (h & (h - 1)) == 0 and (w & (w - 1)) == 0
+    return c % 64 == 0 and pow2 and h >= 32 and w >= 16 and tuple(weight_orig.shape[2:]) == (3, 3) and weight_orig.shape[0] == 4
+
+
+class AdaINTailFn(torch.autograd.Function):
+    """Final AdaIN + ReLU + tail conv3x3(Cin -> 4) + bias + tanh + rgb*segm composition as ONE autograd node
+    (generators/vector_pose_unsupervised_segmentation_noBottleneck.py:80-88,165-181), the conv on the tensor cores:
+        forward : in_stats -> adain_relu (bf16 (hi, lo) operand planes) -> tcgen05 bf16x3 conv on the weight zero-padded to
+                  32 output channels -> gen_tail_compose (bias, tanh, composition, NCHW images)
+        backward: gen_tail_bwd_act (32-channel padded, tf32) -> TF32 data-gradient conv 32 -> Cin, TF32 weight gradient
+                  -> AdaIN backward kernels.
+    The CUDA-core tail (GenTailFn) needed 349 us forward / 183 us data-gradient at bs 8, 256^2: N = 4 is HBM-bound on
+    paper, but 2304 FMAs per pixel from shared-memory weights are LDS-bound in practice."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, weight_orig, inv_sigma, bias, eps):
+        mean, rstd = K.in_stats(x, eps)
+        need_bwd = any(ctx.needs_input_grad)
+        if need_bwd:
+            a_f32, a_split = K.adain_relu(x, mean, rstd, gamma, beta, round_tf32=True, want_f32=True, want_split=True)
+        else:
+            a_f32, a_split = None, K.adain_relu(x, mean, rstd, gamma, beta, want_f32=False, want_split=True)
+        w32 = torch.zeros((32,) + tuple(weight_orig.shape[1:]), dtype=torch.float32, device=x.device)
+        w32[:4].copy_(weight_orig.detach())
+        wp = K.pack_conv_weight(w32, precision=K.BF16X3)
+        a32 = K.conv_fwd(a_split, wp, 3, scale=inv_sigma)
+        rgbs, segm, t = K.gen_tail_compose(a32, bias.detach())
+        ctx.save_for_backward(x, mean, rstd, gamma, beta, weight_orig, inv_sigma, a_f32, t, w32)
+        return rgbs, segm
+
+    @staticmethod
+    def backward(ctx, d_rgbs, d_segm):
+        x, mean, rstd, gamma, beta, weight_orig, inv_sigma, a_f32, t, w32 = ctx.saved_tensors
+        d_rgbs = d_rgbs.contiguous() if d_rgbs is not None else None
+        d_segm = d_segm.contiguous() if d_segm is not None else None
+        need_x, need_g, need_bt, need_w, need_s, need_b = ctx.needs_input_grad[:6]
+        da = K.gen_tail_bwd_act(t, d_rgbs, d_segm, stride=32)
+        dx = dgm = dbt = dw = ds = db = None
+        if need_x or need_g or need_bt:
+            wpt = K.pack_conv_weight(w32, transpose=True)             # (Cin, 9, 32): data-gradient layout, tf32
+            d_a = K.conv_fwd(da, wpt, 3, scale=inv_sigma)
+            dx, dgm, dbt = K.adain_relu_bwd(x, mean, rstd, gamma, beta, d_a)
+        if need_w or need_s:
+            g = K.conv_wgrad(a_f32, da, 3)[:4].contiguous()
+            if need_s:
+                ds = _dot(g, weight_orig).reshape(inv_sigma.shape)
+            if need_w:
+                dw = g * inv_sigma
+        if need_b:
+            db = K.bias_grad(da)[:4].contiguous()
+        return dx, dgm, dbt, dw, ds, db, None
+
+
+def adain_tail(x, gamma, beta, weight_orig, inv_sigma, bias, eps=1e-4):
+    return AdaINTailFn.apply(x, gamma, beta, weight_orig, inv_sigma, bias, eps)
+
+
 class ReluRoundFn(torch.autograd.Function):
     """tf32(relu(x)) — the discriminator blocks' leading ReLU(inplace) (blocks.py:73 with norm_layer='none')."""
 

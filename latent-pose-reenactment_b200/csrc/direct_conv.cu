@@ -274,6 +274,26 @@ gen_tail_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     segm[n * HW + hw] = sg;
 }
 
+// Composition stage of the tensor-core tail: a32[n,h,w,0:4] (+ bias) is the 4-channel conv output computed by the
+// tcgen05 bf16x3 kernel on a weight zero-padded to 32 output channels; t = tanh(a), then the same rgb*segm composition
+// as gen_tail_fwd_kernel.  Thread per pixel.
+__global__ void __launch_bounds__(256)
+gen_tail_compose_kernel(const float* __restrict__ a32, const float* __restrict__ bias, float* __restrict__ rgbs,
+                        float* __restrict__ segm, float* __restrict__ t_out, long NP, long HW, int stride) {
+    const long P = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (P >= NP) return;
+    const float4 a = ldg4(a32 + P * stride);
+    const float t0 = tanhf(a.x + __ldg(bias + 0)), t1 = tanhf(a.y + __ldg(bias + 1)), t2 = tanhf(a.z + __ldg(bias + 2)),
+                t3 = tanhf(a.w + __ldg(bias + 3));
+    *reinterpret_cast<float4*>(t_out + P * 4) = make_float4(t0, t1, t2, t3);
+    const float sg = t3 * 0.5f + 0.5f;
+    const long n = P / HW, hw = P - n * HW;
+    rgbs[(n * 3 + 0) * HW + hw] = (t0 * 0.75f + 0.5f) * sg;
+    rgbs[(n * 3 + 1) * HW + hw] = (t1 * 0.75f + 0.5f) * sg;
+    rgbs[(n * 3 + 2) * HW + hw] = (t2 * 0.75f + 0.5f) * sg;
+    segm[n * HW + hw] = sg;
+}
+
 // da = d(loss)/d(pre-tanh) from d(fake_rgbs), d(fake_segm)
 __global__ void gen_tail_bwd_act_kernel(const float* __restrict__ t, const float* __restrict__ d_rgbs,
                                         const float* __restrict__ d_segm, float* __restrict__ da, long NP, long HW,
@@ -299,6 +319,9 @@ __global__ void gen_tail_bwd_act_kernel(const float* __restrict__ t, const float
     o.z = (1.f - tv.z * tv.z) * dt2;
     o.w = (1.f - tv.w * tv.w) * dt3;
     float* dst = da + P * da_stride;
+    if (da_stride == 32) {   // the padded form feeds the tensor cores (weight / data gradient): round, do not truncate
+        o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+    }
     *reinterpret_cast<float4*>(dst) = o;
     // da_stride 32: zero-padded to a 32-channel NHWC tensor so that the tensor-core weight-gradient kernel can take it
     for (int j = 4; j < da_stride; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -571,6 +594,21 @@ extern "C" int32_t b200lp_gen_tail_fwd(const float* x_nhwc, const float* w_oihw,
     const int blocks = static_cast<int>((total + 127) / 128);
     gen_tail_fwd_kernel<<<blocks, 128, 9 * Cin * 16, as_stream(stream)>>>(x_nhwc, w_oihw, wscale, bias, fake_rgbs_nchw,
                                                                           fake_segm_nchw, t_out, N, H, W, Cin);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_gen_tail_compose(const float* a_nhwc, const float* bias, float* fake_rgbs_nchw,
+                                           float* fake_segm_nchw, float* t_out, int32_t N, int32_t H, int32_t W,
+                                           int32_t a_stride, void* stream) {
+    B200LP_REQUIRE(a_nhwc && bias && fake_rgbs_nchw && fake_segm_nchw && t_out && N > 0 && H > 0 && W > 0 &&
+                       a_stride >= 4 && a_stride % 4 == 0,
+                   "gen_tail_compose: bad args");
+    const long HW = static_cast<long>(H) * W;
+    const long NP = N * HW;
+    gen_tail_compose_kernel<<<static_cast<int>((NP + 255) / 256), 256, 0, as_stream(stream)>>>(
+        a_nhwc, bias, fake_rgbs_nchw, fake_segm_nchw, t_out, NP, HW, a_stride);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

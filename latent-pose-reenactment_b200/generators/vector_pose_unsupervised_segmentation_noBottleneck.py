@@ -97,6 +97,9 @@ class Generator(nn.Module):
         # (hi, lo) operand planes, ~fp32 accuracy, generator RGB within 1e-3 of the fp32 reference) or 'tf32' (one MMA
         # per K step, 1.5x less tensor time, ~3e-3 max-abs on nets with O(1) AdaIN gains).  Not part of the state_dict.
         self.precision = 'bf16x3'
+        # final AdaIN + conv3x3(C -> 4) + tanh tail: tcgen05 bf16x3 conv on a weight padded to 32 outputs (True) or the
+        # fp32 CUDA-core kernel (False; also taken for shapes the tensor-core kernel does not cover)
+        self.tail_on_tensor_cores = True
 
     def get_num_affine_params(self):
         return sum(2 * c for c in self.adain_sizes)
@@ -157,7 +160,10 @@ class Generator(nn.Module):
             feeds_skip_conv = nxt is not None and nxt.skip is not None
             x, x_split = blk(x, g0, b0, g1, b1, feeds_skip_conv, x_split=x_split, precision=self.precision)
         g, bt = take(self.adain_sizes[-1])
-        a = ops.adain_relu(x, g, bt, round_out=False)
-        fake_rgbs, fake_segm = ops.gen_tail(a, tail.weight_orig, tail.scale(), tail.bias)
+        if getattr(self, 'tail_on_tensor_cores', True) and ops.tail_tensor_core_ok(x, tail.weight_orig):
+            fake_rgbs, fake_segm = ops.adain_tail(x, g, bt, tail.weight_orig, tail.scale(), tail.bias)
+        else:
+            a = ops.adain_relu(x, g, bt, round_out=False)
+            fake_rgbs, fake_segm = ops.gen_tail(a, tail.weight_orig, tail.scale(), tail.bias)
         data_dict['fake_rgbs'] = fake_rgbs
         data_dict['fake_segm'] = fake_segm

@@ -638,6 +638,48 @@ def pose_timing():
 
 
 @check
+def tail_tensor_core():
+    """Fused AdaIN + tail on the tensor cores (ops.adain_tail) vs float64 torch ops: outputs and every gradient; timing
+    against the CUDA-core tail at the step's shape."""
+    import torch
+    import torch.nn.functional as F
+    from b200lp import ops
+    torch.manual_seed(9)
+    out = []
+    for (N, H, C) in [(2, 64, 64), (1, 32, 128)]:
+        x = torch.randn(N, H, H, C, device="cuda", requires_grad=True)
+        aff0 = torch.randn(N, 2 * C, device="cuda"); aff0[:, C:] += 1.0
+        aff = aff0.requires_grad_(True)
+        w = (torch.randn(4, C, 3, 3, device="cuda") * 0.05).requires_grad_(True)
+        s = torch.tensor([0.7], device="cuda", requires_grad=True)
+        b = torch.randn(4, device="cuda", requires_grad=True)
+        g_r = torch.randn(N, 3, H, H, device="cuda"); g_s = torch.randn(N, 1, H, H, device="cuda")
+        rgbs, segm = ops.adain_tail(x, aff[:, C:], aff[:, :C], w, s, b)
+        grads = torch.autograd.grad([rgbs, segm], [x, aff, w, s, b], [g_r, g_s])
+        xd, ad, wd, sd, bd = [t.detach().double().requires_grad_(True) for t in (x, aff, w, s, b)]
+        xn = xd.permute(0, 3, 1, 2)
+        a = F.relu(F.instance_norm(xn, eps=1e-4) * ad[:, C:][:, :, None, None] + ad[:, :C][:, :, None, None])
+        t = torch.tanh(F.conv2d(a, wd * sd, bd, padding=1))
+        seg = t[:, 3:] * 0.5 + 0.5
+        ref_r, ref_s = (t[:, :3] * 0.75 + 0.5) * seg, seg
+        ref_g = torch.autograd.grad([ref_r, ref_s], [xd, ad, wd, sd, bd], [g_r.double(), g_s.double()])
+        e = _err(rgbs, ref_r); e["case"] = f"adain_tail rgbs N{N} H{H} C{C}"; e["ok"] = e["max_abs"] < 1e-4; out.append(e)
+        e = _err(segm, ref_s); e["case"] = f"adain_tail segm N{N} H{H} C{C}"; e["ok"] = e["max_abs"] < 1e-4; out.append(e)
+        for name, ga, gb in zip(["dx", "daffine", "dw", "ds", "db"], grads, ref_g):
+            if name == "dx":
+                gb = gb  # xd is NHWC already
+            e = _err(ga, gb); e["case"] = f"adain_tail {name} N{N} H{H} C{C}"; e["ok"] = (not e["nan"]) and e["rel"] < 5e-3
+            out.append(e)
+    x = torch.randn(8, 256, 256, 64, device="cuda"); aff = torch.randn(8, 128, device="cuda")
+    w = torch.randn(4, 64, 3, 3, device="cuda") * 0.05; s = torch.tensor([0.7], device="cuda"); b = torch.randn(4, device="cuda")
+    with torch.no_grad():
+        t_tc = _time_us(lambda: ops.adain_tail(x, aff[:, 64:], aff[:, :64], w, s, b))
+        t_cc = _time_us(lambda: ops.gen_tail(ops.adain_relu(x, aff[:, 64:], aff[:, :64], round_out=False), w, s, b))
+    out.append({"case": "timing AdaIN + tail forward bs8 256^2", "tensor_core_us": round(t_tc, 1), "cuda_core_us": round(t_cc, 1), "ok": True})
+    return out
+
+
+@check
 def fused_optim():
     """Fused Adam / RAdam + EMA kernel vs torch.optim.Adam and a per-tensor RAdam port, 8 steps."""
     import torch
