@@ -419,7 +419,11 @@ def main():
     if sampler:
         sampler.start()
     l0 = lib.load().b200lp_launch_count()
+    if args.timed_only:          # `ncu --profile-from-start off`: only the timed steps are profiled
+        torch.cuda.profiler.start()
     ms = timed(step_resident, args.steps, dist_on)
+    if args.timed_only:
+        torch.cuda.profiler.stop()
     launches = lib.load().b200lp_launch_count() - l0
     if graphed is not None:      # replays do not pass through the library's host-side counter
         launches = graphed.kernels_per_replay * args.steps

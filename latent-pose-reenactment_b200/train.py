@@ -196,6 +196,10 @@ def main():
         training_module.generator.enable_finetuning(data_dict)
         training_module.discriminator.enable_finetuning(data_dict)
         training_module.embedder.enable_finetuning()
+        # The embedder is not in optimizer_G while fine-tuning (runners/holycow.py:35-37): the reference still back-propagates
+        # into it and never reads those gradients.  Freezing it leaves every loss and every G / D update unchanged and lets
+        # the pose encoder run its forward-only kernel schedule (embedders/mobilenet_native.py).
+        training_module.embedder.requires_grad_(False)
         if args.weights_running_average:
             for name in ('generator', 'embedder'):
                 if name in training_module.running_averages:

@@ -176,3 +176,53 @@ def test_grad_bucket_views():
     lin.weight.grad = None                       # e.g. optimizer.zero_grad(set_to_none=True)
     bucket.zero()
     assert lin.weight.grad is not None and float(bucket.flat.abs().sum()) == 0.0
+
+
+def test_inv_sigma_edge_matches_autograd_of_torch_formula():
+    """ops.InvSigmaFn (the autograd edge given to a batched-kernel 1/sigma) against autograd through torch's
+    spectral-norm formula sigma = u^T W v with u, v constants (torch/nn/utils/spectral_norm.py compute_weight)."""
+    from b200lp import ops
+    torch.manual_seed(1)
+    w = torch.randn(6, 4, 3, 3, dtype=torch.float64, requires_grad=True)
+    u = torch.nn.functional.normalize(torch.randn(6, dtype=torch.float64), dim=0)
+    v = torch.nn.functional.normalize(torch.randn(36, dtype=torch.float64), dim=0)
+    c = torch.randn(1, dtype=torch.float64)
+    sigma = torch.dot(u, torch.mv(w.reshape(6, -1), v))
+    ((1.0 / sigma).reshape(1) * c).sum().backward()
+    ref = w.grad.clone()
+    w.grad = None
+    s_const = (1.0 / sigma.detach()).reshape(1)
+    (ops.inv_sigma_edge(w, s_const, u, v) * c).sum().backward()
+    torch.testing.assert_close(w.grad, ref, rtol=1e-12, atol=1e-14)
+
+
+def test_direct_grads_context_and_cpu_buckets():
+    """Gradient sinks are active only inside the context manager, nest, and are never offered for CPU buckets (the
+    in-place accumulating kernels are CUDA-only; CPU runs keep plain autograd accumulation)."""
+    from b200lp import ops
+    from runners.holycow import GradBucket
+    p = torch.nn.Parameter(torch.randn(4, 3))
+    bucket = GradBucket([p])
+    assert bucket.sinks() == {}
+    fake_sink = {p.data_ptr(): p.grad}
+    assert ops._sink(p) is None
+    with ops.direct_grads(fake_sink):
+        assert ops._sink(p) is p.grad
+        assert ops._sink(p.detach()) is p.grad            # aliases of the parameter share its storage pointer
+        assert ops._sink(torch.randn(2, 2)) is None
+        with ops.direct_grads({}):
+            assert ops._sink(p) is p.grad
+    assert ops._sink(p) is None
+
+
+def test_native_pose_schedule_recognises_mobilenet_v2_only():
+    import torchvision
+    from embedders import mobilenet_native
+    assert mobilenet_native.supported(torchvision.models.mobilenet_v2(num_classes=16))
+    assert not mobilenet_native.supported(torchvision.models.resnet18(num_classes=16))
+    # on CPU (or when a gradient is needed) the embedder keeps the torch module: no silent native path without CUDA
+    from embedders.unsupervised_pose_separate_embResNeXt_segmentation import Embedder
+    e = Embedder.__new__(Embedder)
+    torch.nn.Module.__init__(e)
+    e.pose_encoder = torchvision.models.mobilenet_v2(num_classes=16)
+    assert e._native_pose_path(torch.zeros(1, 3, 32, 32)) is False

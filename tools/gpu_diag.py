@@ -381,13 +381,15 @@ def direct_convs():
     add("tail_rgbs", rgbs, fake); add("tail_segm", segm, sg)
     gx1 = xtd.grad.clone(); gw1 = wtd.grad.clone(); gb1 = btd.grad.clone()
     dx, dw, db = K.gen_tail_bwd(xt, tt, wt, sc, g1.float().contiguous(), None)
-    add("tail_dx(rgb)", dx.permute(0, 3, 1, 2), gx1, 1e-4)
-    add("tail_dw(rgb)", dw * 0.7, gw1, 2e-3)   # kernel returns d/d(w*scale); TF32 tensor-core weight gradient
-    add("tail_db(rgb)", db, gb1, 1e-4)
+    # with a weight gradient requested the pre-tanh gradient is produced in its 32-channel tf32-rounded form (operand of
+    # the tensor-core gradient kernels): 2e-3; the kernel returns d/d(w*scale)
+    add("tail_dx(rgb)", dx.permute(0, 3, 1, 2), gx1, 2e-3)
+    add("tail_dw(rgb)", dw * 0.7, gw1, 2e-3)
+    add("tail_db(rgb)", db, gb1, 2e-3)
     xtd.grad = None; wtd.grad = None; btd.grad = None
     ((fake * g1).sum() + (sg * g2).sum()).backward()
     dx, dw, db = K.gen_tail_bwd(xt, tt, wt, sc, g1.float().contiguous(), g2.float().contiguous())
-    add("tail_dx(rgb+segm)", dx.permute(0, 3, 1, 2), xtd.grad, 1e-4)
+    add("tail_dx(rgb+segm)", dx.permute(0, 3, 1, 2), xtd.grad, 2e-3)
     add("tail_dw(rgb+segm)", dw * 0.7, wtd.grad, 2e-3)
     return out
 

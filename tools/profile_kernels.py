@@ -25,27 +25,60 @@ def main():
         x = torch.randn(8, H, H, Cin, device=dev)
         wp = K.pack_conv_weight(torch.randn(Cout, Cin, 3, 3, device=dev))
         y = torch.empty(8, H, H, Cout, device=dev)
-        for _ in range(3):
+        for _ in range(2):
             K.conv_fwd(x, wp, 3, out=y)
     x = torch.randn(8, 128, 128, 128, device=dev)
     xs = split_bf16(x)
     wps = K.pack_conv_weight(torch.randn(128, 128, 3, 3, device=dev), precision=K.BF16X3)
-    for _ in range(3):
+    for _ in range(2):
         K.conv_fwd(xs, wps, 3)
     for (H, C) in [(256, 64), (128, 128)]:
         x = torch.randn(8, H, H, C, device=dev)
         dy = torch.randn(8, H, H, C, device=dev)
-        for _ in range(3):
+        for _ in range(2):
             K.conv_wgrad(x, dy, 3)
     aff = torch.randn(8, 256, device=dev)
     x = torch.randn(8, 256, 256, 64, device=dev)
-    for _ in range(3):
+    for _ in range(2):
         mean, rstd = K.in_stats(x, 1e-4)
         K.adain_relu(x, mean, rstd, aff[:, 64:128], aff[:, :64])
     x = torch.randn(8, 128, 128, 128, device=dev)
     mean, rstd = K.in_stats(x, 1e-4)
-    for _ in range(3):
+    for _ in range(2):
         K.adain_relu(x, mean, rstd, aff[:, 128:256], aff[:, :128], upsample2=True)
+    # round-1 additions: fused weight-gradient path (tensor-core kernel -> tiled reduce + accumulate + <G,W> partials ->
+    # rank-1 term), the generator tail on the tensor cores, the pose-encoder kernels
+    import torch.nn.functional as F
+    for (H, Cin, Cout) in [(32, 512, 512), (128, 128, 128)]:
+        x = torch.randn(8, H, H, Cin, device=dev)
+        dy = torch.randn(8, H, H, Cout, device=dev)
+        w = torch.randn(Cout, Cin, 3, 3, device=dev) * 0.02
+        grad = torch.zeros_like(w)
+        u = F.normalize(torch.randn(Cout, device=dev), dim=0)
+        v = F.normalize(torch.randn(Cin * 9, device=dev), dim=0)
+        s_ = torch.ones(1, device=dev)
+        for _ in range(2):
+            K.conv_wgrad_sn_acc(x, dy, 3, grad, w, s_, u, v)
+    from b200lp import ops
+    x = torch.randn(8, 256, 256, 64, device=dev)
+    w4 = torch.randn(4, 64, 3, 3, device=dev) * 0.05
+    with torch.no_grad():
+        for _ in range(2):
+            ops.adain_tail(x, aff[:, 64:128], aff[:, :64], w4, torch.ones(1, device=dev), torch.zeros(4, device=dev))
+    for (m, cin, cout) in [(131072, 16, 96), (2048, 576, 96), (512, 960, 320)]:
+        xm = torch.randn(m, cin, device=dev)
+        wm = torch.randn(cout, cin, device=dev)
+        sc = torch.rand(cin, device=dev)
+        sh = torch.randn(cin, device=dev)
+        for _ in range(2):
+            K.pw_conv(xm, wm, sc, sh, True, want_stats=True)
+    for (h, c, stride) in [(128, 96, 2), (64, 144, 1)]:
+        xd = torch.randn(8, h, h, c, device=dev)
+        wd = torch.randn(c, 1, 3, 3, device=dev)
+        sc = torch.rand(c, device=dev)
+        sh = torch.randn(c, device=dev)
+        for _ in range(2):
+            K.dw_conv3x3(xd, wd, sc, sh, stride, want_stats=True)
     torch.cuda.synchronize()
 
 
