@@ -318,6 +318,42 @@ def adain_conv(x, gamma, beta, weight_orig, inv_sigma, residual=None, residual_m
                              emit_split, cache, sn)
 
 
+class SplitAffineFn(torch.autograd.Function):
+    """The projector output (B, sum 2C) cut into the per-AdaIN (beta, gamma) column blocks as ONE autograd node
+    (generators/vector_pose_unsupervised_segmentation_noBottleneck.py:108-125, `assign_affine_params`).  With plain
+    slicing every one of the 34 slices gets its own backward: a zero-filled (B, 13056) tensor, a slice copy and an
+    accumulation — ~100 tiny launches per generator backward; here the 34 incoming gradients are concatenated once.
+    Outputs are column views (row stride = sum 2C) of one private copy: the kernels read them through
+    (pointer, affine_stride)."""
+
+    @staticmethod
+    def forward(ctx, affine, sizes):
+        base = affine.detach().clone(memory_format=torch.contiguous_format)
+        ctx.sizes = tuple(sizes)
+        outs, off = [], 0
+        for c in ctx.sizes:
+            outs.append(base[:, off:off + c])              # beta  (bias of the AdaIN)
+            outs.append(base[:, off + c:off + 2 * c])      # gamma (weight)
+            off += 2 * c
+        assert off == affine.shape[1], (off, affine.shape)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        ref = next(g for g in grads if g is not None)
+        parts = []
+        for i, g in enumerate(grads):
+            c = ctx.sizes[i // 2]
+            parts.append(g if g is not None else ref.new_zeros((ref.shape[0], c)))
+        return torch.cat(parts, dim=1), None
+
+
+def split_affine(affine, sizes):
+    """-> [(gamma_i, beta_i)] for the AdaIN layers in `sizes` order."""
+    outs = SplitAffineFn.apply(affine, tuple(sizes))
+    return [(outs[2 * i + 1], outs[2 * i]) for i in range(len(sizes))]
+
+
 class AdaINReLUFn(torch.autograd.Function):
     """relu(instance_norm(x) * gamma + beta) [nearest 2x] [tf32].  Replaces AdaptiveNorm2d.forward + ReLU + Upsample
     (generators/common/blocks.py:18-26,73,75) and their backward."""

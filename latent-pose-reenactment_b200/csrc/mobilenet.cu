@@ -299,20 +299,20 @@ mbv2_stem_kernel(const float* __restrict__ x, const float* __restrict__ w, float
 
 // ------------------------------------------------------------------------------------------------ BatchNorm pieces
 // training: mean / biased var of `count` samples from [nparts][2][C] partials; eval: running statistics.
-// grid = ceil(C / 32); block = 32 channels x 8 partial lanes.
-__global__ void __launch_bounds__(256)
+// grid = ceil(C / 32); block = 32 channels x 32 partial lanes (the stem and the 128 x 128 layers have 2048 partials).
+__global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ part, int nparts, double count, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
                    long long* __restrict__ num_batches_tracked, float momentum, float eps, float* __restrict__ scale,
                    float* __restrict__ shift, int C, int training) {
-    __shared__ double red[2][8][32];
+    __shared__ double red[2][32][33];
     const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
     if (training) {
         double s1 = 0.0, s2 = 0.0;
         if (c < C)
 #pragma unroll 8
-            for (int i = pl; i < nparts; i += 8) {
+            for (int i = pl; i < nparts; i += 32) {
                 s1 += static_cast<double>(part[(static_cast<size_t>(i) * 2 + 0) * C + c]);
                 s2 += static_cast<double>(part[(static_cast<size_t>(i) * 2 + 1) * C + c]);
             }
@@ -322,7 +322,7 @@ bn_finalize_kernel(const float* __restrict__ part, int nparts, double count, con
         if (pl == 0 && c < C) {
             double a = 0.0, b = 0.0;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) { a += red[0][r][cl]; b += red[1][r][cl]; }
+            for (int r = 0; r < 32; ++r) { a += red[0][r][cl]; b += red[1][r][cl]; }
             const double mean = a / count;
             double var = b / count - mean * mean;
             if (var < 0.0) var = 0.0;
@@ -485,7 +485,7 @@ extern "C" int32_t b200lp_bn_finalize(const float* part, int32_t nparts, int64_t
     B200LP_REQUIRE(gamma && beta && scale && shift && C > 0, "bn_finalize: bad args");
     B200LP_REQUIRE(training ? (part && nparts > 0 && count > 0) : (running_mean && running_var),
                    "bn_finalize: training needs partials, eval needs running statistics");
-    bn_finalize_kernel<<<(C + 31) / 32, 256, 0, as_stream(stream)>>>(
+    bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, as_stream(stream)>>>(
         part, nparts, static_cast<double>(count), gamma, beta, running_mean, running_var,
         reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, scale, shift, C, training);
     B200LP_CHECK_CUDA(cudaGetLastError());

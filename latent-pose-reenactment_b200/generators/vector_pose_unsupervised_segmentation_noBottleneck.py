@@ -137,15 +137,14 @@ class Generator(nn.Module):
             convs += self.decoder_blocks.slot(i).tensor_core_convs()
         tail = self.decoder_blocks.slot(self.num_blocks + 2)
         blocks.spectral_sigmas(convs + [tail, self.affine_params_projector.slot(0), self.affine_params_projector.slot(2)])
-        affine = self.compute_affine_params(data_dict).contiguous()      # (B, sum 2C): per AdaIN [beta | gamma]
+        affine = self.compute_affine_params(data_dict)        # (B, sum 2C): per AdaIN [beta | gamma]
         batch = affine.shape[0]
-
-        off = 0
+        # all 17 (gamma, beta) pairs from one autograd node (one concatenation in backward instead of 34 slice backwards)
+        pairs = iter(ops.split_affine(affine, self.adain_sizes))
 
         def take(c):
-            nonlocal off
-            beta, gamma = affine[:, off:off + c], affine[:, off + c:off + 2 * c]
-            off += 2 * c
+            gamma, beta = next(pairs)
+            assert gamma.shape[1] == c
             return gamma, beta
 
         # constant (1,C,s,s) NCHW parameter -> (B,s,s,C) NHWC

@@ -226,3 +226,30 @@ def test_native_pose_schedule_recognises_mobilenet_v2_only():
     torch.nn.Module.__init__(e)
     e.pose_encoder = torchvision.models.mobilenet_v2(num_classes=16)
     assert e._native_pose_path(torch.zeros(1, 3, 32, 32)) is False
+
+
+def test_split_affine_matches_plain_slicing():
+    """ops.SplitAffineFn (all AdaIN (gamma, beta) blocks from one autograd node) against plain column slicing of the
+    projector output (reference assign_affine_params, generator :108-125): same views, same gradient."""
+    from b200lp import ops
+    torch.manual_seed(2)
+    sizes = [8, 8, 4, 2]
+    a = torch.randn(3, 2 * sum(sizes), dtype=torch.float64, requires_grad=True)
+    b = a.detach().clone().requires_grad_(True)
+    coefs = [torch.randn(3, c, dtype=torch.float64) for c in sizes for _ in range(2)]
+    pairs = ops.split_affine(a, sizes)
+    loss, off, k = 0.0, 0, 0
+    ref = 0.0
+    for i, c in enumerate(sizes):
+        gamma, beta = pairs[i]
+        assert gamma.stride(1) == 1 and gamma.stride(0) == beta.stride(0) == a.shape[1]
+        torch.testing.assert_close(beta, b[:, off:off + c].detach())
+        torch.testing.assert_close(gamma, b[:, off + c:off + 2 * c].detach())
+        if i != 2:                                   # one pair left unused: its gradient must come back as zeros
+            loss = loss + (gamma * coefs[k]).sum() + (beta.sin() * coefs[k + 1]).sum()
+            ref = ref + (b[:, off + c:off + 2 * c] * coefs[k]).sum() + (b[:, off:off + c].sin() * coefs[k + 1]).sum()
+        off += 2 * c
+        k += 2
+    loss.backward()
+    ref.backward()
+    torch.testing.assert_close(a.grad, b.grad)
