@@ -27,6 +27,9 @@ def supported(net):
         for blk in list(f)[1:-1]:
             layers = list(blk.conv)
             ok = ok and len(layers) in (3, 4) and hasattr(blk, 'use_res_connect')
+        for m in net.modules():      # the finalize kernel implements the exponential running average only
+            if isinstance(m, torch.nn.BatchNorm2d):
+                ok = ok and m.momentum is not None and m.affine
         return bool(ok)
     except Exception:
         return False

@@ -1,0 +1,100 @@
+"""The pose-encoder kernel SCHEDULE (embedders/mobilenet_native.py) on the CPU: every libb200lp entry point it calls is
+replaced here by a plain-torch emulation of that kernel's contract (include/b200lp.h), so the test checks the host
+logic — which layer's BatchNorm is applied by which consumer, where ReLU6 sits, skip connections, statistics counts,
+running-statistics updates — against the torchvision module itself.  (The kernels are checked against torch on the GPU:
+tools/gpu_diag.py `pose_encoder`.)"""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+
+def _act(x, scale, shift, relu6):
+    if scale is None:
+        return x
+    y = x * scale + shift
+    return y.clamp(0, 6) if relu6 else y
+
+
+def _stats(y2d):
+    return torch.stack([y2d.sum(0), (y2d * y2d).sum(0)])[None]          # (1 part, 2, C)
+
+
+class _Emu:
+    """torch emulations of b200lp.kernels' pose-encoder wrappers (same signatures, same return conventions)."""
+
+    @staticmethod
+    def mbv2_stem(x_nchw, weight, want_stats=False):
+        y = F.conv2d(x_nchw, weight, stride=2, padding=1).permute(0, 2, 3, 1).contiguous()
+        return (y, _stats(y.reshape(-1, 32))) if want_stats else y
+
+    @staticmethod
+    def pw_conv(x2d, weight, in_scale=None, in_shift=None, in_relu6=False, bias=None, want_stats=False):
+        y = _act(x2d, in_scale, in_shift, in_relu6) @ weight.t()
+        part = _stats(y) if want_stats else None
+        if bias is not None:
+            y = y + bias
+        return (y, part) if want_stats else y
+
+    @staticmethod
+    def dw_conv3x3(x, weight, in_scale, in_shift, stride, want_stats=False):
+        a = _act(x, in_scale, in_shift, True).permute(0, 3, 1, 2)
+        y = F.conv2d(a, weight, stride=stride, padding=1, groups=x.shape[-1]).permute(0, 2, 3, 1).contiguous()
+        return (y, _stats(y.reshape(-1, y.shape[-1]))) if want_stats else y
+
+    @staticmethod
+    def bn_finalize(bn, part, count, training):
+        if training:
+            s1, s2 = part[:, 0].sum(0), part[:, 1].sum(0)
+            mean = s1 / count
+            var = (s2 / count - mean * mean).clamp_min(0)
+            if bn.track_running_stats and bn.running_mean is not None:
+                with torch.no_grad():
+                    bn.running_mean.mul_(1 - bn.momentum).add_(bn.momentum * mean)
+                    bn.running_var.mul_(1 - bn.momentum).add_(bn.momentum * var * count / max(count - 1, 1))
+                    bn.num_batches_tracked += 1
+        else:
+            mean, var = bn.running_mean, bn.running_var
+        scale = bn.weight.detach() / torch.sqrt(var + bn.eps)
+        return scale, bn.bias.detach() - mean * scale
+
+    @staticmethod
+    def bn_apply(x, scale, shift, residual=None, relu6=False):
+        y = _act(x, scale, shift, relu6)
+        return y + residual if residual is not None else y
+
+    @staticmethod
+    def bn_relu6_avgpool(x, scale, shift):
+        return _act(x, scale, shift, True).mean((1, 2))
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_native_schedule_matches_torchvision(monkeypatch, mode):
+    import torchvision
+    from b200lp import kernels as K
+    from embedders import mobilenet_native
+    for name in ("mbv2_stem", "pw_conv", "dw_conv3x3", "bn_finalize", "bn_apply", "bn_relu6_avgpool"):
+        monkeypatch.setattr(K, name, getattr(_Emu, name))
+    torch.manual_seed(0)
+    net = torchvision.models.mobilenet_v2(num_classes=24).double()
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.2)
+                m.running_mean.normal_(0, 0.3); m.running_var.uniform_(0.5, 2.0)
+    net.classifier[0].p = 0.0                      # dropout is RNG-dependent (it stays a torch op in the schedule)
+    assert mobilenet_native.supported(net)
+    a, b = copy.deepcopy(net), copy.deepcopy(net)
+    a.train(mode == "train"); b.train(mode == "train")
+    x = torch.rand(3, 3, 64, 64, dtype=torch.float64)
+    monkeypatch.setattr(torch.Tensor, "float", lambda self: self)     # keep float64 through the schedule's `.float()`
+    with torch.no_grad():
+        ya = mobilenet_native.forward(a, x)
+        yb = b(x)
+    torch.testing.assert_close(ya, yb, rtol=1e-9, atol=1e-10)
+    for p, q in zip(a.modules(), b.modules()):
+        if isinstance(p, torch.nn.BatchNorm2d):
+            torch.testing.assert_close(p.running_mean, q.running_mean, rtol=1e-9, atol=1e-11)
+            torch.testing.assert_close(p.running_var, q.running_var, rtol=1e-9, atol=1e-11)
+            assert int(p.num_batches_tracked) == int(q.num_batches_tracked) == (1 if mode == "train" else 0)
