@@ -375,7 +375,9 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int ksize, WgPlan*
     // extra wave), with at least 4 K steps per CTA
     int splits = splits_req ? splits_req : (2 * 148) / base;
     if (!splits_req && splits > pl->total_steps / 4) splits = pl->total_steps / 4;
-    if (splits > 64) splits = 64;
+    // at most 64 splits, except for single-tile grids (the Cin = 3 stems' 27(+5)-column patch GEMM at 256 x 256: 64 CTAs
+    // ran 49 us): those may take one CTA per SM
+    if (splits > (base == 1 ? 148 : 64)) splits = base == 1 ? 148 : 64;
     if (splits > pl->total_steps) splits = pl->total_steps;
     if (splits < 1) splits = 1;
     pl->steps_per_split = (pl->total_steps + splits - 1) / splits;
@@ -494,9 +496,10 @@ extern "C" int32_t b200lp_conv_wgrad(const b200lp_wgrad_args* a, void* stream) {
 static int wgrad_acc_parts(int Cin, int Cout, int ksize, bool* all_taps) {
     const int tiles = (Cin / 32) * (Cout / 32);
     const int taps = ksize * ksize;
-    // few tiles (64- / 128-channel layers): one block per tap keeps >= 36 blocks busy; the strided OIHW accesses of
-    // that form touch at most a few hundred KB
-    *all_taps = taps == 1 || tiles >= 64;
+    // fewer than 256 tiles (up to 256 x 512 channels): one block per tap — 9x the blocks; measured with one block per
+    // tile: 64 blocks 50 us, 128 blocks 28 us, 256 blocks 16.5 us (profiles/r01_ncu_launch_list_graph_step.csv).  The
+    // strided OIHW accesses of the per-tap form stay in L2 (a weight is <= 4.7 MB there)
+    *all_taps = taps == 1 || tiles >= 256;
     return *all_taps ? tiles : tiles * taps;
 }
 

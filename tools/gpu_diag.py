@@ -256,7 +256,8 @@ def wgrad_3x3():
 
 @check
 def wgrad_big():
-    return [_wgrad_case(8, 256, 256, 64, 64, 3), _wgrad_case(8, 32, 32, 512, 512, 3), _wgrad_case(8, 128, 128, 128, 64, 3)]
+    return [_wgrad_case(8, 256, 256, 64, 64, 3), _wgrad_case(8, 32, 32, 512, 512, 3), _wgrad_case(8, 128, 128, 128, 64, 3),
+            _wgrad_case(8, 256, 256, 32, 64, 1)]     # single-tile grid: one split per SM
 
 
 @check
