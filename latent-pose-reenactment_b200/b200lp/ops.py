@@ -433,7 +433,7 @@ class AdaINTailFn(torch.autograd.Function):
             a_f32, a_split = K.adain_relu(x, mean, rstd, gamma, beta, round_tf32=True, want_f32=True, want_split=True)
         else:
             a_f32, a_split = None, K.adain_relu(x, mean, rstd, gamma, beta, want_f32=False, want_split=True)
-        w32 = torch.zeros((32,) + tuple(weight_orig.shape[1:]), dtype=torch.float32, device=x.device)
+        w32 = torch.zeros((32,) + tuple(weight_orig.shape[1:]), dtype=weight_orig.dtype, device=x.device)
         w32[:4].copy_(weight_orig.detach())
         wp = K.pack_conv_weight(w32, precision=K.BF16X3)
         a32 = K.conv_fwd(a_split, wp, 3, scale=inv_sigma)

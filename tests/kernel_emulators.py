@@ -1,0 +1,302 @@
+"""Plain-torch emulations of the tensor-level kernel wrappers in b200lp/kernels.py — TEST INFRASTRUCTURE ONLY.
+
+Each function restates the *contract* of one C-ABI entry point (include/b200lp.h) with torch CPU operators, in whatever
+dtype its inputs have (the schedule tests run them in float64).  Monkeypatched over `b200lp.kernels` they let the
+"not gpu" suite execute the plugins' host logic — which kernel is called on which tensor, layouts, residual modes,
+spectral-norm bookkeeping, gradient sinks — and compare it with the oracle / the reference's golden vectors without a
+GPU.  Nothing under latent-pose-reenactment_b200/ imports this file; the kernels themselves are checked against torch
+on the GPU (tools/gpu_diag.py).
+"""
+import torch
+import torch.nn.functional as F
+
+TF32, BF16X3 = 0, 1
+
+
+# ------------------------------------------------------------------------------------------------ weights, convs
+def pack_conv_weight(w_oihw, scale=None, transpose=False, precision=TF32, out=None):
+    co, ci, kh, kw = w_oihw.shape
+    w = w_oihw.detach() * (scale if scale is not None else 1.0)
+    if transpose:       # wp[ci][T-1-tap][co]
+        p = w.reshape(co, ci, kh * kw).flip(2).permute(1, 2, 0).contiguous()
+    else:               # wp[co][tap][ci]
+        p = w.reshape(co, ci, kh * kw).permute(0, 2, 1).contiguous()
+    if precision != TF32:
+        p = torch.stack([p, torch.zeros_like(p)])          # (hi, lo) planes: no rounding in the emulation
+    if out is not None:
+        out.copy_(p)
+        return out
+    return p
+
+
+def _unpack(wp, ksize):
+    if wp.dim() == 4:
+        wp = wp[0] + wp[1]
+    rows, taps, cols = wp.shape
+    assert taps == ksize * ksize
+    return wp.reshape(rows, ksize, ksize, cols).permute(0, 3, 1, 2)       # -> (rows, cols, k, k) = conv2d weight
+
+
+def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False, round_tf32=False, block_n=0,
+             out=None, emit_split=False, stages=0, scale=None, ctas_per_sm=0, splits=0, variant=0, a_stages=0):
+    if x.dim() == 5:
+        x = x[0] + x[1]
+    w = _unpack(wp, ksize).to(x.dtype)
+    y = F.conv2d(x.permute(0, 3, 1, 2), w, padding=ksize // 2)
+    if scale is not None:
+        y = y * scale.to(y.dtype)
+    if bias is not None:
+        y = y + bias.to(y.dtype)[None, :, None, None]
+    if residual is not None and residual_mode == 1:
+        y = y + residual.permute(0, 3, 1, 2)
+    elif residual is not None and residual_mode == 2:
+        y = y + F.interpolate(residual.permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    if relu:
+        y = y.relu()
+    y = y.permute(0, 2, 3, 1).contiguous()
+    if out is not None:
+        out.copy_(y)
+        y = out
+    return (y, torch.stack([y, torch.zeros_like(y)])) if emit_split else y
+
+
+def conv_wgrad(x, dy, ksize, scale=1.0, kstep=0, stages=0, splits=0):
+    cin, cout = x.shape[3], dy.shape[3]
+    g = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2), (cout, cin, ksize, ksize), dy.permute(0, 3, 1, 2),
+                                    padding=ksize // 2)
+    return (g * scale).contiguous()
+
+
+def conv_wgrad_sn_acc(x, dy, ksize, grad, weight=None, inv_sigma=None, u=None, v=None, accumulate=True):
+    g = conv_wgrad(x, dy, ksize)
+    if inv_sigma is not None:
+        s = inv_sigma.reshape(())
+        dot = (g * weight.detach()).sum()
+        g = s * g - s * s * dot * torch.outer(u, v).reshape(g.shape)
+    if accumulate:
+        grad.add_(g)
+    else:
+        grad.copy_(g)
+    return grad
+
+
+def bias_grad(dy, acc_into=None):
+    db = dy.reshape(-1, dy.shape[-1]).sum(0)
+    if acc_into is not None:
+        acc_into.add_(db)
+        return acc_into
+    return db
+
+
+# ------------------------------------------------------------------------------------------------ spectral norm
+def sn_scratch(w):
+    return torch.empty(1, dtype=w.dtype, device=w.device)
+
+
+def sn_sigma_multi(layers, training):
+    inv, snaps = [], []
+    for (w, u, v, eps, _scratch) in layers:
+        wm = w.reshape(w.shape[0], -1)
+        if training:
+            vn = torch.mv(wm.t(), u)
+            vn = vn / vn.norm().clamp_min(eps)
+            un = torch.mv(wm, vn)
+            un = un / un.norm().clamp_min(eps)
+            v.copy_(vn)
+            u.copy_(un)
+        inv.append(1.0 / torch.dot(u, torch.mv(wm, v)))
+        snaps.append((u.clone(), v.clone()))
+    return torch.stack(inv), snaps
+
+
+def sn_wgrad_fix(g, w, inv_sigma, u, v):
+    s = inv_sigma.reshape(())
+    return s * g - s * s * (g * w.detach()).sum() * torch.outer(u, v).reshape(g.shape)
+
+
+# ------------------------------------------------------------------------------------------------ AdaIN
+def in_stats(x, eps):
+    mean = x.mean((1, 2))
+    var = x.var((1, 2), unbiased=False)
+    return mean, (var + eps).rsqrt()
+
+
+def _adain(x, mean, rstd, gamma, beta, upsample2):
+    y = ((x - mean[:, None, None, :]) * rstd[:, None, None, :] * gamma[:, None, None, :] + beta[:, None, None, :]).relu()
+    if upsample2:
+        y = y.repeat_interleave(2, 1).repeat_interleave(2, 2)
+    return y
+
+
+def adain_relu(x, mean, rstd, gamma, beta, upsample2=False, round_tf32=True, want_f32=True, want_split=False):
+    y = _adain(x, mean, rstd, gamma, beta, upsample2).contiguous()
+    ys = torch.stack([y, torch.zeros_like(y)]) if want_split else None
+    if want_f32 and want_split:
+        return y, ys
+    return y if want_f32 else ys
+
+
+def adain_relu_bwd(x, mean, rstd, gamma, beta, dy, upsample2=False):
+    """Autograd through the emulated forward INCLUDING the statistics' dependence on x."""
+    with torch.enable_grad():
+        xr = x.detach().requires_grad_(True)
+        gr = gamma.detach().clone().requires_grad_(True)
+        br = beta.detach().clone().requires_grad_(True)
+        m = xr.mean((1, 2))
+        eps = (1.0 / rstd.detach() ** 2 - x.detach().var((1, 2), unbiased=False))      # recover the layer's eps
+        r = (xr.var((1, 2), unbiased=False) + eps).rsqrt()
+        y = _adain(xr, m, r, gr, br, upsample2)
+        dx, dg, db = torch.autograd.grad(y, [xr, gr, br], dy)
+    return dx, dg, db
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def nchw_to_nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nhwc_to_nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def relu_round(x):
+    return x.relu()
+
+
+def relu_bwd(y, dy):
+    return dy * (y > 0)
+
+
+def avgpool2(x, addend=None, round_tf32=False):
+    y = F.avg_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).contiguous()
+    return y + addend if addend is not None else y
+
+
+def avgpool2_bwd(dy):
+    return (dy * 0.25).repeat_interleave(2, 1).repeat_interleave(2, 2).contiguous()
+
+
+def upsample2_bwd(dy):
+    n, h2, w2, c = dy.shape
+    return dy.reshape(n, h2 // 2, 2, w2 // 2, 2, c).sum((2, 4))
+
+
+def l1_sum(a, b, out, scale):
+    out += scale * (a - b).abs().sum()
+
+
+def l1_bwd(a, b, gscale, scale2, da=None):
+    g = torch.sign(a - b) * (gscale.reshape(()) * scale2)
+    if da is not None:
+        da.add_(g)
+        return da
+    return g
+
+
+def l1_relu_bwd(a, b, gscale, scale2, d_in=None):
+    g = torch.sign(a - b) * (gscale.reshape(()) * scale2)
+    if d_in is not None:
+        g = g + d_in
+    return g * (a > 0)
+
+
+# ------------------------------------------------------------------------------------------------ Cin = 3 stems
+def conv3x3_c3_fwd(x_nchw, w, wscale=None, bias=None, pre_scale=None, pre_shift=None, relu=False, round_tf32=False):
+    x = x_nchw
+    if pre_scale is not None:
+        x = x * pre_scale[None, :, None, None] + pre_shift[None, :, None, None]
+    y = F.conv2d(x, w.detach() * (wscale.reshape(()) if wscale is not None else 1.0), bias, padding=1)
+    if relu:
+        y = y.relu()
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def im2col3x3_c3(x_nchw):
+    n, c, h, w = x_nchw.shape
+    col = F.unfold(x_nchw, 3, padding=1).reshape(n, 27, h, w).permute(0, 2, 3, 1)      # column index = c*9 + kh*3 + kw
+    return torch.cat([col, col.new_zeros(n, h, w, 5)], dim=3).contiguous()
+
+
+def col2im3x3_c3(dcol, pre_scale=None):
+    n, h, w, _ = dcol.shape
+    dx = F.fold(dcol[..., :27].permute(0, 3, 1, 2).reshape(n, 27, h * w), (h, w), 3, padding=1)
+    if pre_scale is not None:
+        dx = dx * pre_scale[None, :, None, None]
+    return dx.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ generator tail
+def _compose(t):
+    segm = t[..., 3:] * 0.5 + 0.5
+    rgb = (t[..., :3] * 0.75 + 0.5) * segm
+    return rgb.permute(0, 3, 1, 2).contiguous(), segm.permute(0, 3, 1, 2).contiguous()
+
+
+def gen_tail_fwd(x, w, wscale, bias):
+    a = F.conv2d(x.permute(0, 3, 1, 2), w.detach() * wscale.reshape(()), bias, padding=1).permute(0, 2, 3, 1)
+    t = torch.tanh(a).contiguous()
+    rgbs, segm = _compose(t)
+    return rgbs, segm, t
+
+
+def gen_tail_compose(a32, bias):
+    t = torch.tanh(a32[..., :4] + bias).contiguous()
+    rgbs, segm = _compose(t)
+    return rgbs, segm, t
+
+
+def gen_tail_bwd_act(t, d_rgbs, d_segm, stride=32):
+    with torch.enable_grad():
+        a = torch.atanh(t.detach().clamp(-1 + 1e-15, 1 - 1e-15)).requires_grad_(True)
+        rgbs, segm = _compose(torch.tanh(a))
+        outs, gs = [], []
+        if d_rgbs is not None:
+            outs.append(rgbs); gs.append(d_rgbs)
+        if d_segm is not None:
+            outs.append(segm); gs.append(d_segm)
+        (da,) = torch.autograd.grad(outs, [a], gs)
+    if stride > 4:
+        da = torch.cat([da, da.new_zeros(da.shape[:3] + (stride - 4,))], dim=3)
+    return da.contiguous()
+
+
+def gen_tail_bwd(x, t, w, wscale, d_rgbs, d_segm, need_dx=True, need_dw=True):
+    da = gen_tail_bwd_act(t, d_rgbs, d_segm, stride=4)
+    dx = dw = db = None
+    if need_dx:
+        dx = F.conv_transpose2d(da.permute(0, 3, 1, 2), w.detach() * wscale.reshape(()), padding=1).permute(0, 2, 3, 1)
+        dx = dx.contiguous()
+    if need_dw:
+        dw = conv_wgrad(x, da, 3)
+        db = bias_grad(da)
+    return dx, dw, db
+
+
+# ------------------------------------------------------------------------------------------------ buffer copies
+def copy_plan(pairs):
+    return dict(pairs=list(pairs), sig=None, count=len(pairs))
+
+
+def copy_multi(plan):
+    for d, s in plan["pairs"]:
+        d.copy_(s)
+
+
+EMULATED = [
+    "pack_conv_weight", "conv_fwd", "conv_wgrad", "conv_wgrad_sn_acc", "bias_grad", "sn_scratch", "sn_sigma_multi",
+    "sn_wgrad_fix", "in_stats", "adain_relu", "adain_relu_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "relu_round", "relu_bwd",
+    "avgpool2", "avgpool2_bwd", "upsample2_bwd", "l1_sum", "l1_bwd", "l1_relu_bwd", "conv3x3_c3_fwd", "im2col3x3_c3",
+    "col2im3x3_c3", "gen_tail_fwd", "gen_tail_compose", "gen_tail_bwd_act", "gen_tail_bwd", "copy_plan", "copy_multi",
+]
+
+
+def install(monkeypatch):
+    """Replace the wrappers of b200lp.kernels with the emulations above and let the plugins run on the CPU."""
+    import sys
+    from b200lp import kernels as K
+    from b200lp import lib as L
+    this = sys.modules[__name__]
+    for name in EMULATED:
+        assert hasattr(K, name), name
+        monkeypatch.setattr(K, name, getattr(this, name))
+    monkeypatch.setattr(L, "require_device", lambda: 100)
