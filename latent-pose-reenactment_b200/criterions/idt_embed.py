@@ -71,7 +71,7 @@ def sampling_grid(bboxes, image_shape, target_size=None):
 
 
 def sample(images, grid):
-    return torch.nn.functional.grid_sample(images, grid, mode='bilinear', padding_mode='reflection',
+    return torch.nn.functional.grid_sample(images, grid.to(images.dtype), mode='bilinear', padding_mode='reflection',
                                            align_corners=False)
 
 

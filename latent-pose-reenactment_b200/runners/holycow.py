@@ -71,7 +71,8 @@ class GradBucket:
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         device = self.params[0].device if self.params else 'cpu'
-        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        dtype = self.params[0].dtype if self.params else torch.float32      # fp32 in production; fp64 in CPU tests
+        self.flat = torch.zeros(total, dtype=dtype, device=device)
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
