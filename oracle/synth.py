@@ -156,3 +156,38 @@ def make_inputs(cfg, batch, seed=4, n_identity_frames=1):
         embeds_elemwise=torch.randn(batch, n_identity_frames, cfg["embed_channels"], generator=g),
     )
     return data, target, emb
+
+
+def pose_encoder_state_dict(num_classes=32, seed=7):
+    """Deterministic weights for the pose encoder (torchvision MobileNetV2, the reference's
+    embedders/unsupervised_pose_separate_embResNeXt_segmentation.py:28): torchvision's own key / shape layout, values
+    from a seeded generator (He-scaled convs, non-trivial BatchNorm affine parameters AND running statistics, so that
+    eval mode and the running-statistics update are both exercised)."""
+    import torchvision
+    g = _gen(seed)
+    layout = torchvision.models.mobilenet_v2(num_classes=num_classes).state_dict()
+    sd = {}
+    for k, v in layout.items():
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros((), dtype=torch.int64)
+        elif k.endswith("running_mean"):
+            sd[k] = _randn(g, *v.shape, std=0.3)
+        elif k.endswith("running_var"):
+            sd[k] = torch.rand(v.shape, generator=g) * 1.5 + 0.5
+        elif v.dim() == 4:                                  # conv: He scaling on the fan-in
+            fan_in = v.shape[1] * v.shape[2] * v.shape[3]
+            sd[k] = _randn(g, *v.shape, std=(2.0 / fan_in) ** 0.5)
+        elif v.dim() == 2:                                  # classifier
+            sd[k] = _randn(g, *v.shape, std=(1.0 / v.shape[1]) ** 0.5)
+        elif k.endswith("bias") and "classifier" in k:
+            sd[k] = _randn(g, *v.shape, std=0.1)
+        elif k.endswith("weight"):                          # BatchNorm gamma
+            sd[k] = torch.rand(v.shape, generator=g) + 0.5
+        else:                                               # BatchNorm beta
+            sd[k] = _randn(g, *v.shape, std=0.2)
+    return sd
+
+
+def pose_inputs(batch=3, image_size=64, seed=8):
+    g = _gen(seed)
+    return torch.rand((batch, 1, 3, image_size, image_size), generator=g)

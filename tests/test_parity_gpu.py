@@ -295,3 +295,32 @@ def test_full_size_batch_properties():
     assert torch.isfinite(out8).all()
     assert float(out8.min()) >= -0.25 - 1e-6 and float(out8.max()) <= 1.25 + 1e-6
     assert float(dd["fake_segm"].min()) >= 0 and float(dd["fake_segm"].max()) <= 1
+
+
+def test_pose_encoder_native_vs_reference_golden():
+    """Embedder.get_pose_embedding through the native MobileNetV2 kernel schedule (csrc/mobilenet.cu) against the outputs
+    of the UNMODIFIED reference embedder on the same deterministic weights (tests/golden/pose.pt, made by
+    oracle/make_golden_pose.py): eval mode, train mode (batch statistics; dropout probability 0 on both sides) and the
+    BatchNorm running statistics after the train-mode call.  fp32 kernels vs fp32 torch CPU: 1e-4 / 3e-4 relative."""
+    from conftest import GOLDEN
+    from embedders.unsupervised_pose_separate_embResNeXt_segmentation import Embedder
+    gold = torch.load(GOLDEN / "pose.pt", map_location="cpu", weights_only=False)
+    emb = Embedder(16, gold["num_classes"], "sum")
+    emb.pose_encoder.load_state_dict(synth.pose_encoder_state_dict(gold["num_classes"], seed=7), strict=True)
+    emb = emb.to(DEV)
+    x = synth.pose_inputs(batch=3, image_size=128, seed=8).to(DEV)
+    with torch.no_grad():
+        emb.eval()
+        assert emb._native_pose_path(x[:, 0])                 # the kernel schedule, not the torch modules
+        d = {"pose_input_rgbs": x}
+        emb.get_pose_embedding(d)
+        assert rel_err(d["pose_embedding"], gold["eval.pose_embedding"]) < 1e-4
+        emb.train()
+        emb.pose_encoder.classifier[0].p = 0.0
+        d = {"pose_input_rgbs": x}
+        emb.get_pose_embedding(d)
+        assert rel_err(d["pose_embedding"], gold["train.pose_embedding"]) < 3e-4
+    bns = [m for m in emb.pose_encoder.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    assert rel_err(torch.cat([m.running_mean for m in bns]), gold["train.running_mean"]) < 1e-4
+    assert rel_err(torch.cat([m.running_var for m in bns]), gold["train.running_var"]) < 1e-4
+    assert int(bns[0].num_batches_tracked) == gold["train.num_batches_tracked"] == 1

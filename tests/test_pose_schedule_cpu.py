@@ -98,3 +98,52 @@ def test_native_schedule_matches_torchvision(monkeypatch, mode):
             torch.testing.assert_close(p.running_mean, q.running_mean, rtol=1e-9, atol=1e-11)
             torch.testing.assert_close(p.running_var, q.running_var, rtol=1e-9, atol=1e-11)
             assert int(p.num_batches_tracked) == int(q.num_batches_tracked) == (1 if mode == "train" else 0)
+
+
+def _reference_pose_golden():
+    from conftest import GOLDEN
+    return torch.load(GOLDEN / "pose.pt", map_location="cpu", weights_only=False)
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_native_schedule_matches_reference_golden(monkeypatch, mode):
+    """The schedule (over the kernel emulations, float64) against the UNMODIFIED reference embedder's pose path on the
+    deterministic weights of oracle/synth.py (tests/golden/pose.pt, oracle/make_golden_pose.py)."""
+    from b200lp import kernels as K
+    from embedders import mobilenet_native
+    from embedders.unsupervised_pose_separate_embResNeXt_segmentation import Embedder
+    from oracle import synth
+    gold = _reference_pose_golden()
+    for name in ("mbv2_stem", "pw_conv", "dw_conv3x3", "bn_finalize", "bn_apply", "bn_relu6_avgpool"):
+        monkeypatch.setattr(K, name, getattr(_Emu, name))
+    emb = Embedder(16, gold["num_classes"], "sum")
+    emb.pose_encoder.load_state_dict(synth.pose_encoder_state_dict(gold["num_classes"], seed=7), strict=True)
+    net = emb.pose_encoder.double()
+    net.train(mode == "train")
+    net.classifier[0].p = 0.0
+    x = synth.pose_inputs(batch=3, image_size=128, seed=8)[:, 0].double()
+    monkeypatch.setattr(torch.Tensor, "float", lambda self: self)
+    with torch.no_grad():
+        y = mobilenet_native.forward(net, x)
+    ref = gold[f"{mode}.pose_embedding"].double()
+    assert float((y - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    if mode == "train":
+        bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+        rm, rv = torch.cat([m.running_mean for m in bns]), torch.cat([m.running_var for m in bns])
+        assert float((rm - gold["train.running_mean"]).abs().max()) <= 1e-5 * float(gold["train.running_mean"].abs().max())
+        assert float((rv - gold["train.running_var"]).abs().max()) <= 1e-5 * float(gold["train.running_var"].abs().max())
+        assert int(bns[0].num_batches_tracked) == gold["train.num_batches_tracked"] == 1
+
+
+def test_embedder_plugin_torch_path_matches_reference_golden():
+    """The plugin's differentiable path (torch modules, used when a gradient flows through the encoder) is the same
+    torchvision network as the reference's: identical outputs on identical weights."""
+    from embedders.unsupervised_pose_separate_embResNeXt_segmentation import Embedder
+    from oracle import synth
+    gold = _reference_pose_golden()
+    emb = Embedder(16, gold["num_classes"], "sum").eval()
+    emb.pose_encoder.load_state_dict(synth.pose_encoder_state_dict(gold["num_classes"], seed=7), strict=True)
+    d = {"pose_input_rgbs": synth.pose_inputs(batch=3, image_size=128, seed=8)}
+    with torch.no_grad():
+        emb.get_pose_embedding(d)
+    torch.testing.assert_close(d["pose_embedding"], gold["eval.pose_embedding"], rtol=1e-5, atol=1e-6)
