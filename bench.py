@@ -303,6 +303,75 @@ def roofline_pass(step_fn, peaks):
     return out
 
 
+def is_own_kernel(name):
+    """Every kernel of libb200lp.so lives in namespace b200lp (csrc/*.cu); anything else is torch / cuDNN / cuBLAS / NCCL."""
+    return "b200lp::" in name
+
+
+def kernel_family(name):
+    """Kernel name (CUPTI, demangled) -> family key used by the roofline table."""
+    import re
+    if not is_own_kernel(name):
+        if "nccl" in name.lower():
+            return "nccl"
+        if name.startswith("Memcpy") or name.startswith("Memset"):
+            return "memcpy/memset"
+        return "torch/cudnn/cublas"
+    base = name.split("b200lp::", 1)[1].split("(", 1)[0]
+    m = re.match(r"(conv_igemm_kernel|conv_halo_kernel|conv_halo2_kernel)<(.*)>", base)
+    if m:
+        mode = m.group(2).split(",")[-1].strip().rstrip(">")
+        return "conv_igemm_bf16x3" if mode.startswith("1") else "conv_igemm_tf32"
+    base = base.split("<", 1)[0]
+    table = (("splitk_epilogue", "conv_splitk_epilogue"), ("conv_wgrad_tf32", "conv_wgrad_tf32"), ("wgrad_", "wgrad_reduce"),
+             ("sn_rank1", "wgrad_reduce"), ("sn_", "spectral_norm"), ("in_stats", "in_stats"), ("adain_bwd", "adain_relu_bwd"),
+             ("adain_relu", "adain_relu"), ("l1_", "l1"), ("pack_conv_weight", "pack_conv_weight"),
+             ("adam_ema", "optimizer"), ("ema_multi", "optimizer"), ("opt_tick", "optimizer"),
+             ("gen_tail", "gen_tail"), ("conv3x3_c3", "c3_stem"), ("im2col3x3", "c3_stem"), ("col2im3x3", "c3_stem"),
+             ("gconv", "resnext_grouped"), ("rx_", "resnext"), ("bn_", "batchnorm"), ("pw_", "pose_encoder"),
+             ("dw_", "pose_encoder"), ("mbv2", "pose_encoder"))
+    for prefix, fam in table:
+        if base.startswith(prefix):
+            return fam
+    return "elementwise"
+
+
+def replay_kernel_times(fn):
+    """{kernel name: (ms, launches)} of the device work fn() enqueues (one CUDA-graph replay of the step), measured by
+    CUPTI through torch.profiler: per-kernel durations of the kernels as they run back to back inside the replay, not
+    event pairs around eager launches.  Outside every timed region."""
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        fn()
+        torch.cuda.synchronize()
+    rows = {}
+    for e in prof.events():
+        if e.device_type != torch.autograd.DeviceType.CUDA:
+            continue
+        ms, c = rows.get(e.name, (0.0, 0))
+        rows[e.name] = (ms + e.device_time / 1e3, c + 1)
+    return rows, sum(ms for ms, _ in rows.values())
+
+
+def family_table(rows, work=None):
+    """Aggregate replay_kernel_times rows into families; `work` = {family: {flops, bytes}} algorithmic work of one step
+    (b200lp.kernels.WORK, accumulated on the host while the step was captured)."""
+    fam = {}
+    for name, (ms, c) in rows.items():
+        d = fam.setdefault(kernel_family(name), {"ms": 0.0, "launches": 0})
+        d["ms"] += ms
+        d["launches"] += c
+    total = sum(d["ms"] for d in fam.values()) or 1.0
+    out = {}
+    for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+        w = (work or {}).get(k, {})
+        out[k] = {"ms": round(v["ms"], 3), "share": round(v["ms"] / total, 3), "launches": v["launches"],
+                  "tflops": round(w["flops"] / v["ms"] / 1e9, 1) if w.get("flops") else None,
+                  "gbs": round(w["bytes"] / v["ms"] / 1e6, 1) if w.get("bytes") else None}
+    return out
+
+
 def drive_benchmark(device, batch=64, n_batches=6):
     """BASELINE configs[3]: drive.py inner loop (drive.py:84-98) batched — pinned host frames -> pose embedder ->
     generator forward (eval, fine-tuned) -> clamp/uint8 -> asynchronous D2H.  Returns frames/s (end to end)."""

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 16
+#define B200LP_ABI_VERSION 17
 
 #define B200LP_OK 0
 #define B200LP_EINVAL (-1)   /* bad shape / unsupported configuration */
@@ -278,13 +278,14 @@ int32_t b200lp_gen_tail_bwd_weight(const float* x_nhwc, const float* da, float* 
  *   table_dev        : device array of {float* p; const float* g; float* m; float* v; float* ema (or NULL); int64 n}
  *   chunk_tensor_dev / chunk_off_dev : work list, chunk i covers table[chunk_tensor[i]] elements
  *                      [chunk_off[i], chunk_off[i] + chunk_elems)
- *   state_dev        : 4 floats {step, step_size, rectified flag, 1/sqrt(bias_correction2)}; step advances by 1 per call
+ *   state_dev        : 8 floats {step, step_size, rectified flag, 1/sqrt(bias_correction2), lr, ema_alpha, -, -};
+ *                      step advances by 1 per call; lr and ema_alpha are READ from the device vector (the caller
+ *                      rewrites them between CUDA-graph replays when a schedule changes them)
  *   mode 0 = torch.optim.Adam semantics, 1 = RAdam (utils/radam.py) semantics;  ema = ema*ema_alpha + p*(1-ema_alpha)
  */
 int32_t b200lp_adam_ema_multi(const void* table_dev, const int32_t* chunk_tensor_dev, const int64_t* chunk_off_dev,
-                              int32_t n_chunks, int64_t chunk_elems, float* state_dev, float lr, float beta1,
-                              float beta2, float eps, float ema_alpha, int32_t mode, int32_t degenerated_to_sgd,
-                              void* stream);
+                              int32_t n_chunks, int64_t chunk_elems, float* state_dev, float beta1, float beta2,
+                              float eps, int32_t mode, int32_t degenerated_to_sgd, void* stream);
 /* ema = ema*ema_alpha + p*(1-ema_alpha) over the same kind of table (entries with ema == NULL are skipped) */
 int32_t b200lp_ema_multi(const void* table_dev, const int32_t* chunk_tensor_dev, const int64_t* chunk_off_dev,
                          int32_t n_chunks, int64_t chunk_elems, float ema_alpha, void* stream);

@@ -13,7 +13,7 @@ import torch
 
 _PKG = Path(__file__).resolve().parent.parent
 LIB_PATH = _PKG / "lib" / "libb200lp.so"
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 
 class B200lpError(RuntimeError):
@@ -111,7 +111,7 @@ SIGNATURES = {
     "b200lp_bn_finalize": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _P]),
     "b200lp_bn_apply": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P]),
     "b200lp_bn_relu6_avgpool": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
-    "b200lp_adam_ema_multi": (_I, [_P, _P, _P, _I, _L, _P, _F, _F, _F, _F, _F, _I, _I, _P]),
+    "b200lp_adam_ema_multi": (_I, [_P, _P, _P, _I, _L, _P, _F, _F, _F, _I, _I, _P]),
     "b200lp_ema_multi": (_I, [_P, _P, _P, _I, _L, _F, _P]),
 }
 

@@ -22,10 +22,12 @@ struct OptTensor {
     long long n;
 };
 
-// state[0] = step (as float), [1] = step_size (lr folded in), [2] = rectified flag / 1, [3] = 1/sqrt(bias_correction2)
-__global__ void opt_tick_kernel(float* __restrict__ state, float lr, float beta1, float beta2, int mode,
-                                int degenerated_to_sgd) {
+// state[0] = step (as float), [1] = step_size (lr folded in), [2] = rectified flag / 1, [3] = 1/sqrt(bias_correction2),
+// [4] = learning rate, [5] = running-average alpha.  lr and alpha are read from the DEVICE vector, so a captured CUDA
+// graph of the step follows a learning-rate schedule: the host only rewrites state[4..5] between replays.
+__global__ void opt_tick_kernel(float* __restrict__ state, float beta1, float beta2, int mode, int degenerated_to_sgd) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double lr = static_cast<double>(state[4]);
     const double t = static_cast<double>(state[0]) + 1.0;
     state[0] = static_cast<float>(t);
     const double b1t = pow(static_cast<double>(beta1), t), b2t = pow(static_cast<double>(beta2), t);
@@ -51,8 +53,9 @@ __global__ void opt_tick_kernel(float* __restrict__ state, float lr, float beta1
 __global__ void __launch_bounds__(256)
 adam_ema_multi_kernel(const OptTensor* __restrict__ table, const int* __restrict__ chunk_tensor,
                       const long long* __restrict__ chunk_off, long long chunk_elems, const float* __restrict__ state,
-                      float beta1, float beta2, float eps, float ema_alpha, int mode) {
+                      float beta1, float beta2, float eps, int mode) {
     const OptTensor t = table[chunk_tensor[blockIdx.x]];
+    const float ema_alpha = state[5];
     const long long off = chunk_off[blockIdx.x];
     long long end = off + chunk_elems;
     if (end > t.n) end = t.n;
@@ -135,18 +138,18 @@ using namespace b200lp;
 
 extern "C" int32_t b200lp_adam_ema_multi(const void* table_dev, const int32_t* chunk_tensor_dev,
                                          const int64_t* chunk_off_dev, int32_t n_chunks, int64_t chunk_elems,
-                                         float* state_dev, float lr, float beta1, float beta2, float eps,
-                                         float ema_alpha, int32_t mode, int32_t degenerated_to_sgd, void* stream) {
+                                         float* state_dev, float beta1, float beta2, float eps, int32_t mode,
+                                         int32_t degenerated_to_sgd, void* stream) {
     B200LP_REQUIRE(table_dev && chunk_tensor_dev && chunk_off_dev && state_dev && n_chunks > 0 && chunk_elems > 0 &&
                        (mode == 0 || mode == 1),
                    "adam_ema_multi: bad args");
     cudaStream_t st = as_stream(stream);
-    opt_tick_kernel<<<1, 32, 0, st>>>(state_dev, lr, beta1, beta2, mode, degenerated_to_sgd);
+    opt_tick_kernel<<<1, 32, 0, st>>>(state_dev, beta1, beta2, mode, degenerated_to_sgd);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     adam_ema_multi_kernel<<<n_chunks, 256, 0, st>>>(static_cast<const OptTensor*>(table_dev), chunk_tensor_dev,
                                                     reinterpret_cast<const long long*>(chunk_off_dev), chunk_elems,
-                                                    state_dev, beta1, beta2, eps, ema_alpha, mode);
+                                                    state_dev, beta1, beta2, eps, mode);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

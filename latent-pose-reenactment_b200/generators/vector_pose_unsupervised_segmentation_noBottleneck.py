@@ -90,8 +90,9 @@ class Generator(nn.Module):
         joint = identity_embedding_size + pose_embedding_size
         hidden = max(joint, 512)
         self.affine_params_projector = blocks.Slots(**{
-            "0": blocks.SNLinear(joint, hidden),
-            "2": blocks.SNLinear(hidden, self.get_num_affine_params())})
+            # torch's default spectral_norm eps here (reference :97-101 passes none); 1e-4 is only used for the convs
+            "0": blocks.SNLinear(joint, hidden, eps=1e-12),
+            "2": blocks.SNLinear(hidden, self.get_num_affine_params(), eps=1e-12)})
         self.finetuning = False
         # tensor-core operand precision of the decoder convolutions: 'bf16x3' (default; three bf16 MMAs per K step on
         # (hi, lo) operand planes, ~fp32 accuracy, generator RGB within 1e-3 of the fp32 reference) or 'tf32' (one MMA

@@ -321,7 +321,14 @@ class GraphedTrainStep:
     def __init__(self, training_module, optimizer_G, optimizer_D, finetune, data_dict, target_dict, warmup=3):
         self.static_data = {k: v.clone() for k, v in data_dict.items() if torch.is_tensor(v)}
         self.static_target = {k: v.clone() for k, v in target_dict.items() if torch.is_tensor(v)}
+        self.optimizers = [o for o in (optimizer_G, optimizer_D) if o is not None]
         args = (training_module, self.static_data, self.static_target, optimizer_G, optimizer_D, finetune)
+        # The warm-up steps exist only for lazy initialisation (gradient buckets, optimizer tables, packed weights, the
+        # allocator's pools); they must not train: one batch = one update, like the reference (run_epoch :230-257).
+        # Everything a step mutates is snapshotted here and put back after the capture — parameters and buffers of
+        # E / G / D (BatchNorm statistics, spectral-norm vectors), the running averages, both optimizers' moments and
+        # step counters, and the RNG streams (Dropout in the pose encoder).
+        saved = self._snapshot(training_module)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -338,9 +345,64 @@ class GraphedTrainStep:
                                       optimizer_D, finetune)
         # libb200lp kernels recorded in the graph = launched by every replay
         self.kernels_per_replay = int(b200lp_lib.load().b200lp_launch_count() - launched)
+        self._restore(training_module, saved)
+
+    def _snapshot(self, tm):
+        mods = [tm] + list(tm.running_averages.values())
+        tensors = []
+        for m in mods:
+            tensors += [t for t in itertools.chain(m.parameters(), m.buffers())]
+        seen, uniq = set(), []
+        for t in tensors:
+            if t.data_ptr() not in seen and t.numel():
+                seen.add(t.data_ptr())
+                uniq.append(t)
+        opt = []
+        for o in self.optimizers:
+            if hasattr(o, 'snapshot'):
+                opt.append((o.snapshot(), 0.0, None))
+            else:
+                opt.append((None, 0.0, copy.deepcopy(o.state_dict())))
+        rng = (torch.get_rng_state(), torch.cuda.get_rng_state())
+        return [(t, t.detach().clone()) for t in uniq], opt, rng
+
+    def _restore(self, tm, saved):
+        from b200lp import ops
+        tensors, opt, rng = saved
+        with torch.no_grad():
+            for t, v in tensors:
+                t.copy_(v)
+            for o, (snap, step0, sd) in zip(self.optimizers, opt):
+                if hasattr(o, 'restore'):
+                    o.restore(snap, fresh_state=step0)
+                elif sd is not None:
+                    o.load_state_dict(sd)
+        torch.set_rng_state(rng[0])
+        torch.cuda.set_rng_state(rng[1])
+        ops.bump_generation()                 # weights went back to their pre-warm-up values: packed copies are stale
+        for o in self.optimizers:             # refresh the packed copies whose addresses the graph holds
+            t = getattr(o, '_tables', None)
+            if t is not None:
+                ops.repack_weights(t['params'], owner=id(o))
+        torch.cuda.synchronize()
+
+    def matches(self, data_dict, target_dict):
+        """True when the batch has the captured shapes (a short last batch, a missing key ... -> eager step)."""
+        for static, given in ((self.static_data, data_dict), (self.static_target, target_dict)):
+            for k, v in static.items():
+                g = given.get(k)
+                if not torch.is_tensor(g) or g.shape != v.shape or g.dtype != v.dtype:
+                    return False
+        return True
 
     def __call__(self, data_dict, target_dict):
         from b200lp import ops
+        if not self.matches(data_dict, target_dict):
+            raise ValueError("GraphedTrainStep: batch does not have the captured shapes / keys "
+                             f"({ {k: tuple(v.shape) for k, v in self.static_data.items()} })")
+        for o in self.optimizers:            # lr / ema_alpha live in a device vector the captured kernels read
+            if hasattr(o, 'sync_hyper'):
+                o.sync_hyper()
         for k, v in self.static_data.items():
             v.copy_(data_dict[k], non_blocking=True)
         for k, v in self.static_target.items():
@@ -366,7 +428,11 @@ def run_epoch(dataloader, training_module, optimizer_G, optimizer_D, epoch, args
                 graphed = (key, GraphedTrainStep(training_module, optimizer_G, optimizer_D, args.finetune, data_dict,
                                                  target_dict))
                 training_module._graphed_step = graphed
-            all_data_dict, losses_G_dict, losses_D_dict = graphed[1](data_dict, target_dict)
+            if graphed[1].matches(data_dict, target_dict):
+                all_data_dict, losses_G_dict, losses_D_dict = graphed[1](data_dict, target_dict)
+            else:       # e.g. a dataset plugin's own loader without drop_last: run this batch eagerly
+                all_data_dict, losses_G_dict, losses_D_dict = train_step(
+                    training_module, data_dict, target_dict, optimizer_G, optimizer_D, finetune=args.finetune)
         elif phase == 'train':
             all_data_dict, losses_G_dict, losses_D_dict = train_step(
                 training_module, data_dict, target_dict, optimizer_G, optimizer_D, finetune=args.finetune)

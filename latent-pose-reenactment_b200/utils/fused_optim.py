@@ -28,6 +28,33 @@ class FusedAdamEMA(Optimizer):
         self._ema_of = {}
         self.ema_alpha = 1.0
 
+    def _hyper(self):
+        """The one set of hyper-parameters the kernel runs with.  Several param groups are fine as long as they agree
+        (the reference builds a single group, runners/holycow.py:34-41); disagreeing groups are refused instead of
+        being silently treated as group 0."""
+        g0 = self.param_groups[0]
+        for g in self.param_groups[1:]:
+            for k in ('lr', 'betas', 'eps', 'weight_decay'):
+                if g[k] != g0[k]:
+                    raise NotImplementedError(f"fused optimizer: param groups disagree on {k} ({g[k]} vs {g0[k]})")
+        if g0['weight_decay'] != 0:
+            raise NotImplementedError("the fused optimizer implements weight_decay=0 (the value the reference uses)")
+        return float(g0['lr']), float(g0['betas'][0]), float(g0['betas'][1]), float(g0['eps'])
+
+    def sync_hyper(self):
+        """Upload lr / ema_alpha to the device state vector when they changed (an LR schedule, the runner switching the
+        running-average alpha).  The kernels read them from there, so a captured CUDA graph of the step follows the
+        change; call between replays (never while capturing)."""
+        t = self._tables
+        if t is None:
+            return
+        want = (self._hyper()[0], float(self.ema_alpha))
+        if t.get('hyper') != want:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("fused optimizer: lr / ema_alpha changed while a CUDA graph is being captured")
+            t['state'][4:6].copy_(torch.tensor(want, dtype=torch.float32))
+            t['hyper'] = want
+
     # ------------------------------------------------------------------ wiring
     def attach_ema(self, pairs, alpha):
         """pairs: iterable of (parameter, running-average tensor) — updated inside the same kernel."""
@@ -67,10 +94,10 @@ class FusedAdamEMA(Optimizer):
                 chunk_t.append(i)
                 chunk_o.append(o)
             off += n
-        state_dev = torch.tensor([old_step, 0.0, 0.0, 1.0], dtype=torch.float32, device=dev)
-        for p, r in zip(params, rows):
-            n = p.numel()
-            self.state[p]['step'] = state_dev[0]
+        hyper = (self._hyper()[0], float(self.ema_alpha))
+        state_dev = torch.tensor([old_step, 0.0, 0.0, 1.0, hyper[0], hyper[1], 0.0, 0.0], dtype=torch.float32, device=dev)
+        for p in params:
+            self.state[p]['step'] = state_dev[0]     # in-memory alias of the ONE device counter; see state_dict()
         off = 0
         for p in params:
             n = p.numel()
@@ -81,11 +108,49 @@ class FusedAdamEMA(Optimizer):
             params=params, grad_ptrs=[p.grad.data_ptr() for p in params], m=m_flat, v=v_flat, state=state_dev,
             table=torch.tensor(rows, dtype=torch.int64, device=dev),
             chunk_t=torch.tensor(chunk_t, dtype=torch.int32, device=dev),
-            chunk_o=torch.tensor(chunk_o, dtype=torch.int64, device=dev), n_chunks=len(chunk_t))
+            chunk_o=torch.tensor(chunk_o, dtype=torch.int64, device=dev), n_chunks=len(chunk_t), hyper=hyper)
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         self._tables = None              # moments are re-packed into the flat buffers at the next step
+
+    def state_dict(self):
+        """Same layout as torch.optim.Adam / the reference's RAdam — and NOT aliased: in memory every parameter's `step`
+        is a view of one device counter and the moments are views into two flat buffers; a checkpoint written that way
+        and loaded into an optimizer that does `state['step'] += 1` per parameter would advance the shared counter
+        len(params) times per step.  Here every parameter gets its own Python-number `step` and cloned moments."""
+        sd = super().state_dict()
+        step = None
+        out_state = {}
+        for idx, st in sd['state'].items():
+            new = dict(st)
+            if torch.is_tensor(new.get('step')):
+                if step is None:
+                    step = int(round(float(new['step'])))
+                new['step'] = step
+            for k in ('exp_avg', 'exp_avg_sq'):
+                if torch.is_tensor(new.get(k)):
+                    new[k] = new[k].detach().clone()
+            out_state[idx] = new
+        return {'state': out_state, 'param_groups': sd['param_groups']}
+
+    def snapshot(self):
+        """(step, exp_avg, exp_avg_sq flat copies) of the live tables — GraphedTrainStep restores this after its
+        side-effect-free warm-up."""
+        if self._tables is None:
+            self._build()            # also carries over moments / step restored from a checkpoint
+        t = self._tables
+        return t['state'][:4].clone(), t['m'].clone(), t['v'].clone()
+
+    def restore(self, snap, fresh_state=None):
+        """Inverse of snapshot(): the tables may have been rebuilt since (new gradient buffers), the parameter order —
+        and with it the flat layout of the moments — is the same."""
+        t = self._tables
+        if t is None or snap is None:
+            return
+        t['state'][:4].copy_(snap[0])
+        t['m'].copy_(snap[1])
+        t['v'].copy_(snap[2])
 
     # ------------------------------------------------------------------ step
     @torch.no_grad()
@@ -100,13 +165,13 @@ class FusedAdamEMA(Optimizer):
             t = self._tables
         from b200lp import lib as L
         from b200lp import ops
-        g = self.param_groups[0]
+        _, beta1, beta2, eps = self._hyper()
+        self.sync_hyper()
         lib = L.load()
         L.check(lib.b200lp_adam_ema_multi(
             L.c_void_p(t['table'].data_ptr()), L.c_void_p(t['chunk_t'].data_ptr()), L.c_void_p(t['chunk_o'].data_ptr()),
-            t['n_chunks'], CHUNK, L.ptr(t['state']), float(g['lr']), float(g['betas'][0]), float(g['betas'][1]),
-            float(g['eps']), float(self.ema_alpha), self.MODE, int(self.degenerated_to_sgd), L.stream_ptr()),
-            "adam_ema_multi")
+            t['n_chunks'], CHUNK, L.ptr(t['state']), beta1, beta2, eps, self.MODE, int(self.degenerated_to_sgd),
+            L.stream_ptr()), "adam_ema_multi")
         ops.bump_generation(t['params'])  # parameters changed behind torch's back: their packed copies are stale
         ops.repack_weights(t['params'], owner=id(self))   # ... and refreshed here by one multi-tensor launch
         return loss

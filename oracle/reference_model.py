@@ -75,9 +75,9 @@ def generator_forward(sd, identity_embedding, pose_embedding, layout, training, 
     `identity_embedding` parameter in fine-tuning mode, :128-129).  Returns fake_rgbs, fake_segm, affine_params."""
     blocks, c_last = layout
     joint = torch.cat((identity_embedding, pose_embedding), dim=1)                       # :133
-    w0, _ = spectral_norm_weight(sd, "affine_params_projector.0", training, update=update_sn)
+    w0, _ = spectral_norm_weight(sd, "affine_params_projector.0", training, eps=1e-12, update=update_sn)   # torch default eps
     h = F.relu(F.linear(joint, w0, sd["affine_params_projector.0.bias"]))                # :98-99
-    w2, _ = spectral_norm_weight(sd, "affine_params_projector.2", training, update=update_sn)
+    w2, _ = spectral_norm_weight(sd, "affine_params_projector.2", training, eps=1e-12, update=update_sn)
     affine = F.linear(h, w2, sd["affine_params_projector.2.bias"])                       # :100
 
     off = 0

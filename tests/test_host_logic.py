@@ -253,3 +253,46 @@ def test_split_affine_matches_plain_slicing():
     loss.backward()
     ref.backward()
     torch.testing.assert_close(a.grad, b.grad)
+
+
+def test_fused_optimizer_state_dict_is_not_aliased():
+    """In memory every parameter's `step` of the fused optimizer is a view of one device counter and the moments are
+    views into two flat buffers; state_dict() must hand out independent values, so that a checkpoint loaded into
+    torch.optim.Adam / the vendored RAdam (which do `state['step'] += 1` per parameter) advances by ONE per step."""
+    from utils.fused_optim import FusedAdamEMA
+    from utils.radam import RAdam
+    ps = [torch.nn.Parameter(torch.randn(n)) for n in (5, 7, 3, 11, 2)]
+    opt = FusedAdamEMA(ps, lr=1e-3, betas=(0.0, 0.999), eps=1e-5)
+    counter = torch.tensor([7.0, 0.0, 0.0, 1.0])
+    m_flat, v_flat = torch.randn(28), torch.rand(28)
+    off = 0
+    for p in ps:       # what FusedAdamEMA._build leaves in self.state (here on the CPU: no kernel is involved)
+        opt.state[p] = {"step": counter[0], "exp_avg": m_flat[off:off + p.numel()].view_as(p),
+                        "exp_avg_sq": v_flat[off:off + p.numel()].view_as(p)}
+        off += p.numel()
+    sd = opt.state_dict()
+    steps = [st["step"] for st in sd["state"].values()]
+    assert steps == [7] * 5 and all(isinstance(s, int) for s in steps)
+    ptrs = {st["exp_avg"].untyped_storage().data_ptr() for st in sd["state"].values()}
+    assert len(ptrs) == 5 and m_flat.untyped_storage().data_ptr() not in ptrs
+    for cls in (torch.optim.Adam, RAdam):
+        other = cls(ps, lr=1e-3, betas=(0.0, 0.999), eps=1e-5)
+        other.load_state_dict(sd)
+        for p in ps:
+            p.grad = torch.randn_like(p)
+        other.step()
+        assert all(float(other.state[p]["step"]) == 8.0 for p in ps), [float(other.state[p]["step"]) for p in ps]
+    assert float(counter[0]) == 7.0
+    back = FusedAdamEMA(ps, lr=1e-3, betas=(0.0, 0.999), eps=1e-5)
+    back.load_state_dict(other.state_dict())          # and back: plain per-parameter state is accepted
+    assert float(back.state[ps[0]]["step"]) == 8.0
+
+
+def test_fused_optimizer_refuses_disagreeing_param_groups():
+    from utils.fused_optim import FusedAdamEMA
+    a, b = torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(3))
+    opt = FusedAdamEMA([{"params": [a]}, {"params": [b], "lr": 1e-2}], lr=1e-3)
+    with pytest.raises(NotImplementedError, match="param groups disagree"):
+        opt._hyper()
+    same = FusedAdamEMA([{"params": [a]}, {"params": [b]}], lr=1e-3)
+    assert same._hyper()[0] == 1e-3

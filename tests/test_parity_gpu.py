@@ -239,22 +239,22 @@ def test_graphed_step_equals_eager_step(small):
         losses = []
         if use_graph:
             step = runner.GraphedTrainStep(tm, opt_G, opt_D, False, data, target, warmup=2)
-            n_before = 3            # 2 warm-up + 1 capture pass executed eagerly... capture does not execute
-            for _ in range(3):
+            for _ in range(3):      # the warm-up is side-effect free: replay k IS update k
                 _, lg, ld = step(data, target)
                 losses.append({k: float(v) for k, v in {**lg, **ld}.items()})
         else:
-            for _ in range(5):
+            for _ in range(3):
                 _, lg, ld = runner.train_step(tm, dict(data), dict(target), opt_G, opt_D, finetune=False)
                 losses.append({k: float(v) for k, v in {**lg, **ld}.items()})
         results.append((losses, {k: v.detach().clone() for k, v in G.state_dict().items()},
                         tm.running_averages["generator"].state_dict()["decoder_blocks.0.block.3.weight_orig"].clone()))
     eager_losses, eager_sd, eager_ema = results[0]
     graph_losses, graph_sd, graph_ema = results[1]
-    # graph path: 2 eager warm-up steps + 3 replays = 5 updates; its replay k corresponds to eager step 2 + k
+    # graph path: the warm-up steps are rolled back after capture (weights, buffers, optimizer state, RNG), so the
+    # graph's replay k is the k-th update — one update per batch like the reference's run_epoch
     for k in range(3):
         for name, v in graph_losses[k].items():
-            ref = eager_losses[2 + k][name]
+            ref = eager_losses[k][name]
             assert abs(v - ref) <= 2e-3 * abs(ref) + 1e-5, (k, name, v, ref)
     w = "decoder_blocks.3.block.4.weight_orig"
     assert max_abs(graph_sd[w], eager_sd[w]) < 5e-4 * float(eager_sd[w].abs().max()) + 1e-6

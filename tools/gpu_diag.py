@@ -724,6 +724,28 @@ def fused_optim():
         e = {"case": f"{kind} state keys/step", "ok": set(st.keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(st["step"]) == 8.0,
              "max_abs": 0.0, "rel": 0.0, "nan": False, "ref_max": 8.0}
         out.append(e)
+        # a learning-rate change reaches the kernel through the device state vector (what a CUDA-graph replay reads),
+        # and the checkpoint round trip fused -> plain optimizer -> fused keeps one step per update
+        for grp in opt.param_groups:
+            grp["lr"] = 1e-3
+        for grp in oref.param_groups:
+            grp["lr"] = 1e-3
+        sd = opt.state_dict()
+        opt2 = cls(ps, lr=1e-3, betas=(0.0, 0.999) if kind == "RAdam" else (0.5, 0.999), eps=1e-5)
+        opt2.load_state_dict(sd)
+        opt2.attach_ema(zip(ps, ema), 0.9)
+        for p, r in zip(ps, ref):
+            g = torch.randn_like(p)
+            p.grad.copy_(g)
+            r.grad = g.double()
+        opt2.step(); oref.step()
+        torch.cuda.synchronize()
+        for i, (p, r) in enumerate(zip(ps, ref)):
+            e = _err(p.detach(), r.detach()); e["case"] = f"{kind} param after lr change + state_dict round trip {shapes[i]}"
+            e["ok"] = (not e["nan"]) and e["rel"] < 1e-5; out.append(e)
+        steps = {int(v["step"]) for v in opt2.state_dict()["state"].values()}
+        out.append({"case": f"{kind} step after round trip", "ok": steps == {9}, "max_abs": 0.0, "rel": 0.0, "nan": False,
+                    "ref_max": 9.0})
     return out
 
 
