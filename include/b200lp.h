@@ -326,16 +326,83 @@ int32_t b200lp_mbv2_stem(const float* x_nchw, const float* w, float* y_nhwc, flo
                          int32_t W, void* stream);
 /* training != 0: batch mean / biased variance over `count` samples from the partials (fp64 merge, fixed order) ->
  * scale = gamma*rstd, shift = beta - mean*scale; running_mean / running_var (unbiased) / num_batches_tracked updated
- * like nn.BatchNorm2d (any of the three may be NULL).  training == 0: scale / shift from the running statistics. */
+ * like nn.BatchNorm2d (any of the three may be NULL).  training == 0: scale / shift from the running statistics.
+ * mean_out / rstd_out (both or neither, may be NULL): the statistics the layer normalised with (for b200lp_bn_bwd). */
 int32_t b200lp_bn_finalize(const float* part, int32_t nparts, int64_t count, const float* gamma, const float* beta,
                            float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
-                           float eps, float* scale, float* shift, int32_t C, int32_t training, void* stream);
+                           float eps, float* scale, float* shift, float* mean_out, float* rstd_out, int32_t C,
+                           int32_t training, void* stream);
 /* y = x*scale[c] + shift[c] (+ residual) (relu6): materialises an inverted-residual block output */
 int32_t b200lp_bn_apply(const float* x, const float* scale, const float* shift, const float* residual, float* y,
                         int64_t M, int32_t C, int32_t relu6, void* stream);
 /* y[n][c] = mean_p relu6(x[n,p,c]*scale[c] + shift[c])   (features.18 BN + ReLU6 + adaptive_avg_pool2d(1)) */
 int32_t b200lp_bn_relu6_avgpool(const float* x, const float* scale, const float* shift, float* y, int32_t N, int32_t HW,
                                 int32_t C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Identity encoder (torchvision ResNeXt50-32x4d, train-mode BatchNorm) forward + backward, and the shared BatchNorm
+ * backward of both encoders — csrc/encoder.cu.  Replaces Embedder.get_identity_embedding
+ * (embedders/unsupervised_pose_separate_embResNeXt_segmentation.py:26-27,37-54) and its autograd backward: cuDNN
+ * BatchNorm forward / backward, grouped 3x3 convolutions (groups = 32), max-pool, ReLU / residual adds.  The 1x1
+ * convolutions and the 7x7 stem (through b200lp_im2col7x7_s2) run on b200lp_conv_fwd / b200lp_conv_wgrad.
+ * Activations NHWC fp32, a layer is an [M][C] matrix, C % 4 == 0.
+ */
+/* per-channel sum / sum-of-squares partials of x [M][C] -> part [b200lp_col_stats_parts(M)][2][C] (for bn_finalize) */
+int32_t b200lp_col_stats_parts(int64_t M);
+int32_t b200lp_col_stats(const float* x, float* part, int64_t M, int32_t C, void* stream);
+/* y = act(x*scale + shift (+ res [*res_scale + res_shift]));  act 0 none / 1 relu / 2 relu6.  scale/shift may be NULL
+ * (identity).  Outputs (either or both): y fp32 (tf32-rounded when round_tf32) and y_split = (hi, lo) bf16 planes
+ * [2][M][C] of the unrounded value (operand of the bf16x3 tensor-core GEMM). */
+int32_t b200lp_bn_act(const float* x, const float* scale, const float* shift, const float* res, const float* res_scale,
+                      const float* res_shift, float* y, void* y_split, int64_t M, int32_t C, int32_t act,
+                      int32_t round_tf32, void* stream);
+/* BatchNorm (+ activation) backward over [M][C].  dz = dy * mask, mask_mode 0: none; 1: mask_src > 0 (a materialised
+ * activation output); 2: relu(x_raw*scale+shift) > 0; 3: 0 < x_raw*scale+shift < 6 (ReLU6).
+ *   dgamma (+)= sum dz*xhat, dbeta (+)= sum dz   (accumulate != 0: added to the buffers; either may be NULL)
+ *   dx = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat))  [batch_stats != 0]   or   gamma*rstd*dz  [running statistics]
+ *   dz_out (optional) = dz.   xhat = (x_raw - mean)*rstd.   dx tf32-rounded when round_tf32 (it feeds a TF32 GEMM).
+ * Three launches (partial sums, fp64 fixed-order merge, apply); workspace >= b200lp_bn_bwd_workspace(M, C) bytes. */
+int64_t b200lp_bn_bwd_workspace(int64_t M, int32_t C);
+int32_t b200lp_bn_bwd(const float* dy, const float* mask_src, const float* x_raw, const float* mean, const float* rstd,
+                      const float* scale, const float* shift, const float* gamma, float* dgamma, float* dbeta,
+                      int32_t accumulate, float* dx, float* dz_out, float* workspace, int64_t workspace_bytes, int64_t M,
+                      int32_t C, int32_t mask_mode, int32_t batch_stats, int32_t round_tf32, void* stream);
+/* grouped 3x3 convolution, padding 1, groups = C / cpg (cpg in {4,8,16,32}, C a multiple of 8*cpg), w [C][cpg][3][3],
+ * FP32 on the CUDA cores.  Input = relu(x*in_scale+in_shift) (producer BatchNorm + ReLU on load; NULL: x itself).
+ * transposed != 0 (stride 1 only): y = data gradient of the stride-1 convolution for output gradient x.
+ * part (optional): [b200lp_gconv3x3_parts(...)][2][C] statistics partials of y. */
+int32_t b200lp_gconv3x3_parts(int32_t N, int32_t H, int32_t W, int32_t C, int32_t cpg, int32_t stride);
+int32_t b200lp_gconv3x3_fwd(const float* x, const float* in_scale, const float* in_shift, const float* w, float* y,
+                            float* part, int32_t N, int32_t H, int32_t W, int32_t C, int32_t cpg, int32_t stride,
+                            int32_t transposed, void* stream);
+/* data gradient: dy [N,Ho,Wo,C] -> dx [N,H,W,C] (stride 1 or 2) */
+int32_t b200lp_gconv3x3_dgrad(const float* dy, const float* w, float* dx, int32_t N, int32_t H, int32_t W, int32_t C,
+                              int32_t cpg, int32_t stride, void* stream);
+/* weight gradient: dw [C][cpg][3][3] (+)= sum_pixels dy (x) relu(x*in_scale+in_shift); deterministic two-stage sum */
+int64_t b200lp_gconv3x3_wgrad_workspace(int32_t N, int32_t H, int32_t W, int32_t C, int32_t cpg, int32_t stride);
+int32_t b200lp_gconv3x3_wgrad(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dw,
+                              int32_t accumulate, float* workspace, int64_t workspace_bytes, int32_t N, int32_t H,
+                              int32_t W, int32_t C, int32_t cpg, int32_t stride, void* stream);
+/* 7x7 stride-2 padding-3 patch matrix of an NCHW image: col [N*Ho*Wo][KP], column c*49+kh*7+kw (147 real, zero padded to
+ * KP); col fp32 tf32-rounded and / or col_split (hi, lo) bf16 planes */
+int32_t b200lp_im2col7x7_s2(const float* x_nchw, float* col, void* col_split, int32_t N, int32_t H, int32_t W, int32_t KP,
+                            void* stream);
+/* y = maxpool3x3/s2/p1(relu(x*scale+shift)); idx [N,Ho,Wo,C] uint8 = tap of the maximum (for the backward gather) */
+int32_t b200lp_maxpool3x3s2_fwd(const float* x, const float* scale, const float* shift, float* y, void* y_split,
+                                uint8_t* idx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t round_tf32, void* stream);
+int32_t b200lp_maxpool3x3s2_bwd(const float* dy, const uint8_t* idx, float* dx, int32_t N, int32_t H, int32_t W, int32_t C,
+                                void* stream);
+/* y[n,h,w,:] = x[n,2h,2w,:] (fp32 and / or (hi, lo) planes): operand of a stride-2 1x1 convolution; and its adjoint
+ * dx[n,2h,2w,:] += dsub[n,h,w,:] */
+int32_t b200lp_subsample2(const float* x, const void* x_split, float* y, void* y_split, int32_t N, int32_t Ho, int32_t Wo,
+                          int32_t C, void* stream);
+int32_t b200lp_scatter_add2(const float* dsub, float* dx, int32_t N, int32_t Ho, int32_t Wo, int32_t C, void* stream);
+/* global average pool over the HW pixels of [N][HW][C] and its backward */
+int32_t b200lp_avgpool_fwd(const float* x, float* y, int32_t N, int32_t HW, int32_t C, void* stream);
+int32_t b200lp_avgpool_bwd(const float* dy, float* dx, int32_t N, int32_t HW, int32_t C, void* stream);
+/* C[M][N] (+)= sum_k A[i*sai + k*sak] * B[k*sbk + j*sbj]  (fp32; the classifier layers and their gradients) */
+int32_t b200lp_sgemm_strided(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj, float* C,
+                             int32_t M, int32_t N, int32_t K, int32_t accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -586,23 +586,27 @@ def mbv2_stem(x_nchw, weight, want_stats=False):
     return (y, part) if want_stats else y
 
 
-def bn_finalize(bn, part, count, training):
+def bn_finalize(bn, part, count, training, want_stats=False):
     """(scale, shift) of a torch BatchNorm2d module `bn` for the kernels' on-load normalisation.  training: batch
-    statistics from `part` (+ running-statistics update in place, like the module's forward); else running stats."""
+    statistics from `part` (+ running-statistics update in place, like the module's forward); else running stats.
+    want_stats: also return (mean, rstd) the layer normalised with (inputs of bn_bwd)."""
     lib = L.load()
     c = bn.num_features
     dev = bn.weight.device
     scale = torch.empty(c, dtype=torch.float32, device=dev)
     shift = torch.empty(c, dtype=torch.float32, device=dev)
+    mean = torch.empty(c, dtype=torch.float32, device=dev) if want_stats else None
+    rstd = torch.empty(c, dtype=torch.float32, device=dev) if want_stats else None
     track = bn.track_running_stats and bn.running_mean is not None
     nbt = bn.num_batches_tracked if (training and track and bn.num_batches_tracked is not None) else None
     L.check(lib.b200lp_bn_finalize(L.ptr(part), part.shape[0] if part is not None else 0, int(count),
                                    L.ptr(bn.weight.detach()), L.ptr(bn.bias.detach()),
                                    L.ptr(bn.running_mean) if track else None, L.ptr(bn.running_var) if track else None,
                                    L.ptr(nbt, torch.int64), c_float(bn.momentum if bn.momentum is not None else 0.1),
-                                   c_float(bn.eps), L.ptr(scale), L.ptr(shift), c, int(training), L.stream_ptr()),
+                                   c_float(bn.eps), L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(rstd), c,
+                                   int(training), L.stream_ptr()),
             "bn_finalize")
-    return scale, shift
+    return (scale, shift, mean, rstd) if want_stats else (scale, shift)
 
 
 def bn_apply(x, scale, shift, residual=None, relu6=False):
@@ -624,3 +628,209 @@ def bn_relu6_avgpool(x, scale, shift):
         L.check(lib.b200lp_bn_relu6_avgpool(L.ptr(x), L.ptr(scale), L.ptr(shift), L.ptr(y), n, h * w, c, L.stream_ptr()),
                 "bn_relu6_avgpool")
     return y
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Identity encoder (ResNeXt50-32x4d) + shared BatchNorm backward — csrc/encoder.cu
+# ---------------------------------------------------------------------------------------------------------------------
+def col_stats(x2d):
+    """x (M, C) -> part (parts, 2, C): per-channel sum / sum-of-squares partials for bn_finalize."""
+    lib = L.load()
+    m, c = x2d.shape
+    part = torch.empty((lib.b200lp_col_stats_parts(m), 2, c), dtype=torch.float32, device=x2d.device)
+    with _timed("batchnorm", nbytes=4.0 * x2d.numel()):
+        L.check(lib.b200lp_col_stats(L.ptr(x2d), L.ptr(part), m, c, L.stream_ptr()), "col_stats")
+    return part
+
+
+def bn_act(x, scale=None, shift=None, res=None, res_scale=None, res_shift=None, act=1, round_tf32=True, want_f32=True,
+           want_split=False):
+    """act(x*scale+shift (+ res[*res_scale+res_shift])) over an (..., C) tensor; act 0 none / 1 relu / 2 relu6.
+    Returns y (fp32), (y, y_split) or y_split with y_split (2, ...) bfloat16 (hi, lo) planes of the unrounded value."""
+    lib = L.load()
+    c = x.shape[-1]
+    m = x.numel() // c
+    y = torch.empty_like(x) if want_f32 else None
+    ys = torch.empty((2,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device) if want_split else None
+    n_in = 1 + int(res is not None)
+    with _timed("batchnorm", nbytes=4.0 * x.numel() * (n_in + int(want_f32) + int(want_split))):
+        L.check(lib.b200lp_bn_act(L.ptr(x), L.ptr(scale), L.ptr(shift), L.ptr(res), L.ptr(res_scale), L.ptr(res_shift),
+                                  L.ptr(y), L.ptr(ys, torch.bfloat16), m, c, int(act), int(round_tf32), L.stream_ptr()),
+                "bn_act")
+    if want_f32 and want_split:
+        return y, ys
+    return y if want_f32 else ys
+
+
+def bn_bwd(dy, x_raw, mean, rstd, gamma, scale=None, shift=None, mask_src=None, mask_mode=0, dgamma=None, dbeta=None,
+           accumulate=False, batch_stats=True, round_tf32=False, want_dz=False):
+    """BatchNorm(+activation) backward over (..., C) tensors; see include/b200lp.h.  Returns (dx, dgamma, dbeta, dz);
+    dgamma / dbeta are the given buffers (added into when accumulate) or fresh tensors; dz only when want_dz."""
+    lib = L.load()
+    c = dy.shape[-1]
+    m = dy.numel() // c
+    ws = _ws(lib.b200lp_bn_bwd_workspace(m, c), dy.device)
+    if dgamma is None:
+        dgamma, dbeta, accumulate = (torch.empty(c, dtype=torch.float32, device=dy.device),
+                                     torch.empty(c, dtype=torch.float32, device=dy.device), False)
+    dx = torch.empty_like(dy)
+    dz = torch.empty_like(dy) if want_dz else None
+    n_streams = 3 + int(mask_mode == 1)
+    with _timed("batchnorm", nbytes=4.0 * dy.numel() * (n_streams + int(want_dz))):   # ideal: dy, x read once, dx written
+        L.check(lib.b200lp_bn_bwd(L.ptr(dy), L.ptr(mask_src), L.ptr(x_raw), L.ptr(mean), L.ptr(rstd), L.ptr(scale),
+                                  L.ptr(shift), L.ptr(gamma), L.ptr(dgamma), L.ptr(dbeta), int(accumulate), L.ptr(dx),
+                                  L.ptr(dz), L.ptr(ws), ws.numel() * 4, m, c, int(mask_mode), int(batch_stats),
+                                  int(round_tf32), L.stream_ptr()), "bn_bwd")
+    return dx, dgamma, dbeta, dz
+
+
+def gconv3x3_fwd(x, w, in_scale=None, in_shift=None, stride=1, want_stats=False):
+    """Grouped 3x3 conv (padding 1) on relu(x*in_scale+in_shift) (or x); x (N,H,W,C) raw, w (C, cpg, 3, 3)."""
+    lib = L.load()
+    n, h, wd, c = x.shape
+    cpg = w.shape[1]
+    ho, wo = (h - 1) // stride + 1, (wd - 1) // stride + 1
+    y = torch.empty((n, ho, wo, c), dtype=torch.float32, device=x.device)
+    part = None
+    if want_stats:
+        nparts = lib.b200lp_gconv3x3_parts(n, h, wd, c, cpg, stride)
+        if nparts <= 0:
+            raise L.B200lpError(f"gconv3x3: unsupported shape {tuple(x.shape)} cpg={cpg} stride={stride}")
+        part = torch.empty((nparts, 2, c), dtype=torch.float32, device=x.device)
+    with _timed("resnext_grouped", flops=2.0 * n * ho * wo * c * cpg * 9):
+        L.check(lib.b200lp_gconv3x3_fwd(L.ptr(x), L.ptr(in_scale), L.ptr(in_shift), L.ptr(w), L.ptr(y), L.ptr(part), n, h,
+                                        wd, c, cpg, stride, 0, L.stream_ptr()), "gconv3x3_fwd")
+    return (y, part) if want_stats else y
+
+
+def gconv3x3_dgrad(dy, w, in_hw, stride=1):
+    """dy (N,Ho,Wo,C) -> dx (N,H,W,C) with (H, W) = in_hw."""
+    lib = L.load()
+    n, ho, wo, c = dy.shape
+    h, wd = in_hw
+    cpg = w.shape[1]
+    dx = torch.empty((n, h, wd, c), dtype=torch.float32, device=dy.device)
+    with _timed("resnext_grouped", flops=2.0 * n * ho * wo * c * cpg * 9):
+        L.check(lib.b200lp_gconv3x3_dgrad(L.ptr(dy), L.ptr(w), L.ptr(dx), n, h, wd, c, cpg, stride, L.stream_ptr()),
+                "gconv3x3_dgrad")
+    return dx
+
+
+def gconv3x3_wgrad(x, dy, cpg, in_scale=None, in_shift=None, stride=1, acc_into=None):
+    """dw (C, cpg, 3, 3) = sum_pixels dy (x) relu(x*in_scale+in_shift); added into `acc_into` when given."""
+    lib = L.load()
+    n, h, wd, c = x.shape
+    nbytes = lib.b200lp_gconv3x3_wgrad_workspace(n, h, wd, c, cpg, stride)
+    if nbytes <= 0:
+        raise L.B200lpError(f"gconv3x3_wgrad: unsupported shape {tuple(x.shape)} cpg={cpg} stride={stride}")
+    ws = _ws(nbytes, x.device)
+    dw = acc_into if acc_into is not None else torch.empty((c, cpg, 3, 3), dtype=torch.float32, device=x.device)
+    assert tuple(dw.shape) == (c, cpg, 3, 3)
+    with _timed("resnext_grouped", flops=2.0 * dy.numel() * cpg * 9):
+        L.check(lib.b200lp_gconv3x3_wgrad(L.ptr(x), L.ptr(in_scale), L.ptr(in_shift), L.ptr(dy), L.ptr(dw),
+                                          int(acc_into is not None), L.ptr(ws), ws.numel() * 4, n, h, wd, c, cpg, stride,
+                                          L.stream_ptr()), "gconv3x3_wgrad")
+    return dw
+
+
+STEM_KP = 192      # 147 patch columns of the 7x7x3 stem, zero padded to a multiple of 64 (bf16x3 K rows)
+
+
+def im2col7x7_s2(x_nchw, want_f32=True, want_split=True):
+    """(N,3,H,W) -> patch matrix (N,Ho,Wo,STEM_KP): fp32 tf32-rounded and / or (2, ...) bf16 (hi, lo) planes."""
+    lib = L.load()
+    n, c, h, w = x_nchw.shape
+    assert c == 3
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    col = torch.empty((n, ho, wo, STEM_KP), dtype=torch.float32, device=x_nchw.device) if want_f32 else None
+    cols = torch.empty((2, n, ho, wo, STEM_KP), dtype=torch.bfloat16, device=x_nchw.device) if want_split else None
+    with _timed("resnext", nbytes=4.0 * n * ho * wo * STEM_KP * (int(want_f32) + int(want_split))):
+        L.check(lib.b200lp_im2col7x7_s2(L.ptr(x_nchw), L.ptr(col), L.ptr(cols, torch.bfloat16), n, h, w, STEM_KP,
+                                        L.stream_ptr()), "im2col7x7_s2")
+    if want_f32 and want_split:
+        return col, cols
+    return col if want_f32 else cols
+
+
+def maxpool3x3s2_fwd(x, scale, shift, want_f32=True, want_split=False, want_idx=True, round_tf32=True):
+    """maxpool3x3/s2/p1(relu(x*scale+shift)) -> (y | None, y_split | None, idx | None)."""
+    lib = L.load()
+    n, h, w, c = x.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = torch.empty((n, ho, wo, c), dtype=torch.float32, device=x.device) if want_f32 else None
+    ys = torch.empty((2, n, ho, wo, c), dtype=torch.bfloat16, device=x.device) if want_split else None
+    idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device) if want_idx else None
+    with _timed("resnext", nbytes=4.0 * (x.numel() + n * ho * wo * c * (int(want_f32) + int(want_split)))):
+        L.check(lib.b200lp_maxpool3x3s2_fwd(L.ptr(x), L.ptr(scale), L.ptr(shift), L.ptr(y), L.ptr(ys, torch.bfloat16),
+                                            L.ptr(idx, torch.uint8), n, h, w, c, int(round_tf32), L.stream_ptr()),
+                "maxpool3x3s2_fwd")
+    return y, ys, idx
+
+
+def maxpool3x3s2_bwd(dy, idx, in_hw):
+    lib = L.load()
+    n, ho, wo, c = dy.shape
+    h, w = in_hw
+    dx = torch.empty((n, h, w, c), dtype=torch.float32, device=dy.device)
+    with _timed("resnext", nbytes=4.0 * (dx.numel() + dy.numel())):
+        L.check(lib.b200lp_maxpool3x3s2_bwd(L.ptr(dy), L.ptr(idx, torch.uint8), L.ptr(dx), n, h, w, c, L.stream_ptr()),
+                "maxpool3x3s2_bwd")
+    return dx
+
+
+def subsample2(x=None, x_split=None):
+    """x (N,H,W,C) fp32 and / or x_split (2,N,H,W,C) bf16 -> the even pixels (N,H/2,W/2,C)."""
+    lib = L.load()
+    ref = x if x is not None else x_split[0]
+    n, h, w, c = ref.shape
+    y = torch.empty((n, h // 2, w // 2, c), dtype=torch.float32, device=ref.device) if x is not None else None
+    ys = torch.empty((2, n, h // 2, w // 2, c), dtype=torch.bfloat16, device=ref.device) if x_split is not None else None
+    with _timed("resnext", nbytes=2.0 * n * (h // 2) * (w // 2) * c * (4 * int(x is not None) + 4 * int(x_split is not None))):
+        L.check(lib.b200lp_subsample2(L.ptr(x), L.ptr(x_split, torch.bfloat16), L.ptr(y), L.ptr(ys, torch.bfloat16), n,
+                                      h // 2, w // 2, c, L.stream_ptr()), "subsample2")
+    return y, ys
+
+
+def scatter_add2(dsub, dx):
+    """dx[:, ::2, ::2] += dsub (in place)."""
+    lib = L.load()
+    n, ho, wo, c = dsub.shape
+    assert tuple(dx.shape) == (n, 2 * ho, 2 * wo, c)
+    with _timed("resnext", nbytes=12.0 * dsub.numel()):
+        L.check(lib.b200lp_scatter_add2(L.ptr(dsub), L.ptr(dx), n, ho, wo, c, L.stream_ptr()), "scatter_add2")
+    return dx
+
+
+def avgpool_fwd(x):
+    lib = L.load()
+    n, h, w, c = x.shape
+    y = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    with _timed("resnext", nbytes=4.0 * x.numel()):
+        L.check(lib.b200lp_avgpool_fwd(L.ptr(x), L.ptr(y), n, h * w, c, L.stream_ptr()), "avgpool_fwd")
+    return y
+
+
+def avgpool_bwd(dy, hw):
+    lib = L.load()
+    n, c = dy.shape
+    h, w = hw
+    dx = torch.empty((n, h, w, c), dtype=torch.float32, device=dy.device)
+    with _timed("resnext", nbytes=4.0 * dx.numel()):
+        L.check(lib.b200lp_avgpool_bwd(L.ptr(dy), L.ptr(dx), n, h * w, c, L.stream_ptr()), "avgpool_bwd")
+    return dx
+
+
+def sgemm(a, b, trans_a=False, trans_b=False, acc_into=None):
+    """(a^T if trans_a else a) @ (b^T if trans_b else b) for small contiguous fp32 matrices (classifier layers)."""
+    lib = L.load()
+    m, k = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    kb, n = (b.shape[1], b.shape[0]) if trans_b else b.shape
+    assert k == kb, (a.shape, b.shape, trans_a, trans_b)
+    sai, sak = (1, a.shape[1]) if trans_a else (a.shape[1], 1)
+    sbk, sbj = (1, b.shape[1]) if trans_b else (b.shape[1], 1)
+    out = acc_into if acc_into is not None else torch.empty((m, n), dtype=torch.float32, device=a.device)
+    assert out.numel() == m * n
+    with _timed("resnext", flops=2.0 * m * n * k):
+        L.check(lib.b200lp_sgemm_strided(L.ptr(a), sai, sak, L.ptr(b), sbk, sbj, L.ptr(out), m, n, k,
+                                         int(acc_into is not None), L.stream_ptr()), "sgemm_strided")
+    return out

@@ -108,11 +108,29 @@ SIGNATURES = {
     "b200lp_dw_conv3x3": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200lp_mbv2_stem_parts": (_I, [_I, _I, _I]),
     "b200lp_mbv2_stem": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
-    "b200lp_bn_finalize": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _P]),
+    "b200lp_bn_finalize": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _I, _I, _P]),
     "b200lp_bn_apply": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P]),
     "b200lp_bn_relu6_avgpool": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "b200lp_adam_ema_multi": (_I, [_P, _P, _P, _I, _L, _P, _F, _F, _F, _I, _I, _P]),
     "b200lp_ema_multi": (_I, [_P, _P, _P, _I, _L, _F, _P]),
+    "b200lp_col_stats_parts": (_I, [_L]),
+    "b200lp_col_stats": (_I, [_P, _P, _L, _I, _P]),
+    "b200lp_bn_act": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P]),
+    "b200lp_bn_bwd_workspace": (_L, [_L, _I]),
+    "b200lp_bn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _L, _L, _I, _I, _I, _I, _P]),
+    "b200lp_gconv3x3_parts": (_I, [_I, _I, _I, _I, _I, _I]),
+    "b200lp_gconv3x3_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "b200lp_gconv3x3_dgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "b200lp_gconv3x3_wgrad_workspace": (_L, [_I, _I, _I, _I, _I, _I]),
+    "b200lp_gconv3x3_wgrad": (_I, [_P, _P, _P, _P, _P, _I, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
+    "b200lp_im2col7x7_s2": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_maxpool3x3s2_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200lp_maxpool3x3s2_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_subsample2": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_scatter_add2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_avgpool_fwd": (_I, [_P, _P, _I, _I, _I, _P]),
+    "b200lp_avgpool_bwd": (_I, [_P, _P, _I, _I, _I, _P]),
+    "b200lp_sgemm_strided": (_I, [_P, _L, _L, _P, _L, _L, _P, _I, _I, _I, _I, _P]),
 }
 
 _lib = None

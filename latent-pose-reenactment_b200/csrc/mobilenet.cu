@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ part, int nparts, double count, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
                    long long* __restrict__ num_batches_tracked, float momentum, float eps, float* __restrict__ scale,
-                   float* __restrict__ shift, int C, int training) {
+                   float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ rstd_out, int C,
+                   int training) {
     __shared__ double red[2][32][33];
     const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
@@ -330,6 +331,7 @@ bn_finalize_kernel(const float* __restrict__ part, int nparts, double count, con
             const float sc = __ldg(gamma + c) * rstd;
             scale[c] = sc;
             shift[c] = __ldg(beta + c) - static_cast<float>(mean) * sc;
+            if (mean_out) { mean_out[c] = static_cast<float>(mean); rstd_out[c] = rstd; }
             if (running_mean) {
                 const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
                 running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
@@ -343,6 +345,7 @@ bn_finalize_kernel(const float* __restrict__ part, int nparts, double count, con
         const float sc = __ldg(gamma + c) * rs;
         scale[c] = sc;
         shift[c] = __ldg(beta + c) - running_mean[c] * sc;
+        if (mean_out) { mean_out[c] = running_mean[c]; rstd_out[c] = rs; }
     }
 }
 
@@ -481,13 +484,15 @@ extern "C" int32_t b200lp_mbv2_stem(const float* x_nchw, const float* w, float* 
 extern "C" int32_t b200lp_bn_finalize(const float* part, int32_t nparts, int64_t count, const float* gamma,
                                       const float* beta, float* running_mean, float* running_var,
                                       int64_t* num_batches_tracked, float momentum, float eps, float* scale,
-                                      float* shift, int32_t C, int32_t training, void* stream) {
+                                      float* shift, float* mean_out, float* rstd_out, int32_t C, int32_t training,
+                                      void* stream) {
     B200LP_REQUIRE(gamma && beta && scale && shift && C > 0, "bn_finalize: bad args");
+    B200LP_REQUIRE((mean_out == nullptr) == (rstd_out == nullptr), "bn_finalize: mean_out and rstd_out go together");
     B200LP_REQUIRE(training ? (part && nparts > 0 && count > 0) : (running_mean && running_var),
                    "bn_finalize: training needs partials, eval needs running statistics");
     bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, as_stream(stream)>>>(
         part, nparts, static_cast<double>(count), gamma, beta, running_mean, running_var,
-        reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, scale, shift, C, training);
+        reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, scale, shift, mean_out, rstd_out, C, training);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

@@ -3,9 +3,10 @@
 
 identity = torchvision ResNeXt50-32x4d -> `embed_channels`, averaged over the K identity frames;
 pose     = torchvision MobileNetV2     -> `pose_embedding_size`.
-These two encoders are stock torchvision networks in the reference as well (grouped / depthwise convs with
-train-mode BatchNorm); they stay on torch/cuDNN in this round — SURVEY.md §8(f) next-3 — so the state_dict (634
-torchvision keys under `identity_encoder.` / `pose_encoder.`) and numerics are identical by construction.
+The two torchvision modules are kept as the OWNERS of parameters and buffers, so the state_dict (634 torchvision keys
+under `identity_encoder.` / `pose_encoder.`) is the reference's; on a B200 their arithmetic — forward and backward —
+runs as libb200lp kernel schedules over those parameters (embedders/resnext_native.py: tcgen05 1x1 / stem GEMMs, FP32
+grouped convolutions, fused BatchNorm kernels; embedders/mobilenet_native.py).
 """
 import os
 
@@ -43,7 +44,12 @@ class Embedder(nn.Module):
     def get_identity_embedding(self, data_dict):
         inputs = data_dict['enc_rgbs']
         batch_size, num_faces, c, h, w = inputs.shape
-        per_frame = self.identity_encoder(inputs.reshape(-1, c, h, w)).view(batch_size, num_faces, -1)
+        frames = inputs.reshape(-1, c, h, w)
+        if self._native_identity_path(frames):
+            from embedders import resnext_native
+            per_frame = resnext_native.apply(self.identity_encoder, frames).view(batch_size, num_faces, -1)
+        else:
+            per_frame = self.identity_encoder(frames).view(batch_size, num_faces, -1)
         assert per_frame.shape[2] == self.identity_embedding_size
         data_dict['embeds'] = per_frame.mean(1) if self.average_function == 'sum' else per_frame.max(1)[0]
         data_dict['embeds_elemwise'] = per_frame
@@ -56,6 +62,19 @@ class Embedder(nn.Module):
             data_dict['pose_embedding'] = mobilenet_native.forward(self.pose_encoder, x)
         else:
             data_dict['pose_embedding'] = self.pose_encoder(x)
+
+    def _native_identity_path(self, x):
+        """Kernel schedule of the identity encoder (forward + backward) for float32 CUDA frames whose planes the
+        tensor-core kernels tile (powers of two, >= 64 x 64, an even number of frames)."""
+        if not x.is_cuda or x.dtype != torch.float32 or os.environ.get('B200LP_TORCH_IDENTITY_ENCODER'):
+            return False
+        n, _, h, w = x.shape
+        if h < 64 or w < 64 or (h & (h - 1)) or (w & (w - 1)) or n % 8:
+            return False
+        from embedders import resnext_native
+        if self.__dict__.get('_native_id_ok') is None:
+            self.__dict__['_native_id_ok'] = resnext_native.supported(self.identity_encoder)
+        return self.__dict__['_native_id_ok']
 
     def _native_pose_path(self, x):
         """The kernel schedule has no backward: it serves every call that needs no gradient through the encoder

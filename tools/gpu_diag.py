@@ -1017,6 +1017,277 @@ def wgrad_tune():
     return out
 
 
+def _emu():
+    sys.path.insert(0, str(ROOT / "tests"))
+    import encoder_emulators
+    return encoder_emulators
+
+
+def _cmp(name, got, ref, tol=2e-5, **extra):
+    e = _err(got, ref)
+    e["case"] = name
+    e["ok"] = (not e["nan"]) and e["rel"] < tol
+    e.update(extra)
+    return e
+
+
+@check
+def encoder_bn():
+    """col_stats / bn_finalize(+mean, rstd) / bn_act / bn_bwd (all mask modes, batch and running statistics) vs the
+    float64 emulations of tests/encoder_emulators.py."""
+    import torch
+    from b200lp import kernels as K
+    E = _emu()
+    out = []
+    torch.manual_seed(3)
+    dev = "cuda"
+    for (m, c) in [(4096, 64), (1000, 128), (333, 1028), (64 * 64 * 16, 256), (70, 2048)]:
+        x = torch.randn(m, c, device=dev) * 2 + 0.5
+        out.append(_cmp(f"col_stats M{m} C{c}", K.col_stats(x).double().sum(0), E.col_stats(x.double())[0], 1e-5))
+        for training in (True, False):
+            bn = torch.nn.BatchNorm2d(c).to(dev)
+            with torch.no_grad():
+                bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.3)
+                bn.running_mean.normal_(0, 0.3); bn.running_var.uniform_(0.5, 2.0)
+            bn64 = torch.nn.BatchNorm2d(c).to(dev).double()
+            bn64.load_state_dict({k: (v.double() if v.is_floating_point() else v.clone()) for k, v in bn.state_dict().items()})
+            got = K.bn_finalize(bn, K.col_stats(x) if training else None, m, training, want_stats=True)
+            ref = E.bn_finalize(bn64, E.col_stats(x.double()) if training else None, m, training, want_stats=True)
+            for nm, g, r in zip(("scale", "shift", "mean", "rstd"), got, ref):
+                out.append(_cmp(f"bn_finalize {nm} M{m} C{c} train{int(training)}", g, r, 2e-5))
+            out.append(_cmp(f"bn_finalize running_var M{m} C{c} train{int(training)}", bn.running_var, bn64.running_var, 2e-5))
+            sc, sh, mean, rstd = got
+            res = torch.randn(m, c, device=dev)
+            for act in (0, 1, 2):
+                y, ys = K.bn_act(x, sc, sh, res=res, res_scale=sc, res_shift=sh, act=act, round_tf32=False, want_f32=True,
+                                 want_split=True)
+                r = E.bn_act(x.double(), sc.double(), sh.double(), res=res.double(), res_scale=sc.double(),
+                             res_shift=sh.double(), act=act)
+                out.append(_cmp(f"bn_act res+affine act{act} M{m} C{c}", y, r, 1e-5))
+                out.append(_cmp(f"bn_act split planes act{act} M{m} C{c}", ys[0].double() + ys[1].double(), r, 2e-5))
+            y = K.bn_act(x, sc, sh, res=res, act=1, round_tf32=True)
+            out.append(_cmp(f"bn_act res act1 tf32 M{m} C{c}", y, tf32_round(E.bn_act(x.double(), sc.double(), sh.double(),
+                                                                                   res=res.double(), act=1).float()), 1e-5))
+            dy = torch.randn(m, c, device=dev)
+            outp = E.bn_act(x.double(), sc.double(), sh.double(), res=res.double(), act=1)
+            for mode in (0, 1, 2, 3):
+                dg0 = torch.randn(c, device=dev); db0 = torch.randn(c, device=dev)
+                dg, db = dg0.clone(), db0.clone()
+                dx, _, _, dz = K.bn_bwd(dy, x, mean, rstd, bn.weight.detach(), sc, sh, mask_src=outp.float(), mask_mode=mode,
+                                        dgamma=dg, dbeta=db, accumulate=True, batch_stats=training, want_dz=True)
+                rdx, rdg, rdb, rdz = E.bn_bwd(dy.double(), x.double(), mean.double(), rstd.double(), bn.weight.detach().double(),
+                                              sc.double(), sh.double(), mask_src=outp, mask_mode=mode, batch_stats=training,
+                                              want_dz=True)
+                out.append(_cmp(f"bn_bwd dx mode{mode} M{m} C{c} train{int(training)}", dx, rdx, 3e-5))
+                out.append(_cmp(f"bn_bwd dz mode{mode} M{m} C{c}", dz, rdz, 1e-6))
+                out.append(_cmp(f"bn_bwd dgamma(acc) mode{mode} M{m} C{c}", dg - dg0, rdg, 3e-5))
+                out.append(_cmp(f"bn_bwd dbeta(acc) mode{mode} M{m} C{c}", db - db0, rdb, 3e-5))
+    return out
+
+
+@check
+def encoder_gconv():
+    """Grouped 3x3 convolution (32 groups of 4 / 8 / 16 / 32 channels): forward with BatchNorm + ReLU on load and output
+    statistics, stride 1 / 2, data gradient (stride 1 = transposed forward kernel, stride 2 = gather kernel), weight
+    gradient (+ accumulation) vs float64 torch; then GFLOP/s at the identity encoder's shapes."""
+    import torch
+    from b200lp import kernels as K
+    E = _emu()
+    out = []
+    torch.manual_seed(5)
+    dev = "cuda"
+    for (n, h, w, cpg, stride) in [(2, 16, 16, 4, 1), (3, 16, 8, 4, 2), (2, 8, 8, 8, 1), (2, 8, 8, 8, 2), (1, 10, 6, 8, 1),
+                                   (2, 8, 8, 16, 1), (2, 8, 8, 16, 2), (2, 4, 4, 32, 1), (3, 4, 4, 32, 2), (1, 2, 2, 32, 1),
+                                   (1, 2, 2, 32, 2), (8, 64, 64, 4, 1)]:
+        c = 32 * cpg
+        x = torch.randn(n, h, w, c, device=dev)
+        wt = torch.randn(c, cpg, 3, 3, device=dev) * 0.2
+        sc = torch.rand(c, device=dev) + 0.5
+        sh = torch.randn(c, device=dev) * 0.3
+        tag = f"N{n} H{h} W{w} cpg{cpg} s{stride}"
+        y, part = K.gconv3x3_fwd(x, wt, sc, sh, stride=stride, want_stats=True)
+        ry, rpart = E.gconv3x3_fwd(x.double(), wt.double(), sc.double(), sh.double(), stride=stride, want_stats=True)
+        out.append(_cmp(f"gconv fwd {tag}", y, ry, 1e-5))
+        out.append(_cmp(f"gconv fwd stats {tag}", part.double().sum(0), rpart[0], 1e-5))
+        y2 = K.gconv3x3_fwd(x, wt, stride=stride)
+        out.append(_cmp(f"gconv fwd plain {tag}", y2, E.gconv3x3_fwd(x.double(), wt.double(), stride=stride), 1e-5))
+        dy = torch.randn_like(y)
+        dx = K.gconv3x3_dgrad(dy, wt, (h, w), stride=stride)
+        out.append(_cmp(f"gconv dgrad {tag}", dx, E.gconv3x3_dgrad(dy.double(), wt.double(), (h, w), stride=stride), 1e-5))
+        base = torch.randn_like(wt)
+        acc = base.clone()
+        K.gconv3x3_wgrad(x, dy, cpg, sc, sh, stride=stride, acc_into=acc)
+        rg = E.gconv3x3_wgrad(x.double(), dy.double(), cpg, sc.double(), sh.double(), stride=stride)
+        out.append(_cmp(f"gconv wgrad(acc) {tag}", acc - base, rg, 3e-5))
+        g = K.gconv3x3_wgrad(x, dy, cpg, sc, sh, stride=stride)
+        out.append(_cmp(f"gconv wgrad {tag}", g, rg, 3e-5))
+    for (n, h, cpg, stride) in [(64, 64, 4, 1), (64, 64, 8, 2), (64, 32, 8, 1), (64, 32, 16, 2), (64, 16, 16, 1),
+                                (64, 16, 32, 2), (64, 8, 32, 1)]:
+        c = 32 * cpg
+        x = torch.randn(n, h, h, c, device=dev)
+        wt = torch.randn(c, cpg, 3, 3, device=dev) * 0.1
+        sc = torch.rand(c, device=dev) + 0.5
+        sh = torch.randn(c, device=dev) * 0.3
+        ho = h // stride
+        dy = torch.randn(n, ho, ho, c, device=dev)
+        flops = 2.0 * n * ho * ho * c * cpg * 9
+        rec = {"case": f"timing gconv N{n} H{h} cpg{cpg} s{stride}", "ok": True, "max_abs": 0.0, "rel": 0.0, "nan": False,
+               "ref_max": 0.0}
+        rec["fwd_us"] = round(_time_us(lambda: K.gconv3x3_fwd(x, wt, sc, sh, stride=stride, want_stats=True)), 1)
+        rec["dgrad_us"] = round(_time_us(lambda: K.gconv3x3_dgrad(dy, wt, (h, h), stride=stride)), 1)
+        rec["wgrad_us"] = round(_time_us(lambda: K.gconv3x3_wgrad(x, dy, cpg, sc, sh, stride=stride)), 1)
+        rec["fwd_tflops"] = round(flops / rec["fwd_us"] / 1e6, 1)
+        rec["dgrad_tflops"] = round(flops / rec["dgrad_us"] / 1e6, 1)
+        rec["wgrad_tflops"] = round(flops / rec["wgrad_us"] / 1e6, 1)
+        out.append(rec)
+    return out
+
+
+@check
+def encoder_misc():
+    """im2col7x7_s2, maxpool3x3s2 fwd / bwd, subsample2 / scatter_add2, avgpool fwd / bwd, strided sgemm."""
+    import torch
+    from b200lp import kernels as K
+    E = _emu()
+    out = []
+    torch.manual_seed(7)
+    dev = "cuda"
+    for (n, h, w) in [(2, 64, 64), (3, 32, 48), (1, 18, 14)]:
+        x = torch.rand(n, 3, h, w, device=dev)
+        col, cols = K.im2col7x7_s2(x)
+        ref = E.im2col7x7_s2(x.double(), True, False)
+        out.append(_cmp(f"im2col7x7 f32 N{n} H{h} W{w}", col, tf32_round(ref.float()), 1e-6))
+        out.append(_cmp(f"im2col7x7 split N{n} H{h} W{w}", cols[0].double() + cols[1].double(), ref, 2e-5))
+    for (n, h, w, c) in [(2, 32, 32, 64), (3, 16, 20, 8), (1, 7, 9, 4)]:
+        x = torch.randn(n, h, w, c, device=dev)
+        sc = torch.rand(c, device=dev) + 0.5
+        sh = torch.randn(c, device=dev) * 0.3
+        y, ys, idx = K.maxpool3x3s2_fwd(x, sc, sh, want_f32=True, want_split=True, want_idx=True, round_tf32=False)
+        ry, _, ridx = E.maxpool3x3s2_fwd(x.double(), sc.double(), sh.double())
+        out.append(_cmp(f"maxpool fwd N{n} H{h} W{w} C{c}", y, ry, 1e-6))
+        out.append(_cmp(f"maxpool split N{n} H{h} W{w} C{c}", ys[0].double() + ys[1].double(), ry, 2e-5))
+        dy = torch.randn_like(y)
+        dx = K.maxpool3x3s2_bwd(dy, idx, (h, w))
+        # route through the kernel's own argmax (ties among zeros are resolved arbitrarily but consistently)
+        out.append(_cmp(f"maxpool bwd N{n} H{h} W{w} C{c}", dx, E.maxpool3x3s2_bwd(dy.double(), idx, (h, w)), 1e-6))
+        agree = float((idx == ridx.to(idx.device)).float().mean())
+        # where the maximum is positive (no tie among clamped zeros) the argmax must agree
+        pos = ry > 0
+        agree_pos = float((idx[pos] == ridx.to(idx.device)[pos]).float().mean())
+        out.append({"case": f"maxpool argmax agreement N{n} H{h} W{w} C{c}", "ok": agree_pos == 1.0, "max_abs": 1 - agree_pos,
+                    "rel": 1 - agree, "nan": False, "ref_max": 1.0})
+    for (n, h, w, c) in [(2, 16, 16, 64), (3, 8, 4, 256)]:
+        x = torch.randn(n, h, w, c, device=dev)
+        xs = split_bf16(x)
+        y, ys = K.subsample2(x, xs)
+        out.append(_cmp(f"subsample2 f32 N{n} H{h} C{c}", y, x[:, ::2, ::2].double(), 1e-7))
+        out.append(_cmp(f"subsample2 split N{n} H{h} C{c}", ys.float(), xs[:, :, ::2, ::2].float().double(), 1e-7))
+        ys_only = K.subsample2(None, xs)[1]
+        out.append(_cmp(f"subsample2 split-only N{n} H{h} C{c}", ys_only.float(), xs[:, :, ::2, ::2].float().double(), 1e-7))
+        d = torch.randn(n, h // 2, w // 2, c, device=dev)
+        tgt = torch.randn(n, h, w, c, device=dev)
+        ref = tgt.double().clone(); ref[:, ::2, ::2] += d.double()
+        out.append(_cmp(f"scatter_add2 N{n} H{h} C{c}", K.scatter_add2(d, tgt), ref, 1e-6))
+    for (n, h, w, c) in [(4, 8, 8, 2048), (3, 2, 2, 64), (2, 5, 3, 36)]:
+        x = torch.randn(n, h, w, c, device=dev)
+        out.append(_cmp(f"avgpool fwd N{n} HW{h * w} C{c}", K.avgpool_fwd(x), x.double().mean((1, 2)), 1e-5))
+        dy = torch.randn(n, c, device=dev)
+        out.append(_cmp(f"avgpool bwd N{n} HW{h * w} C{c}", K.avgpool_bwd(dy, (h, w)), E.avgpool_bwd(dy.double(), (h, w)), 1e-6))
+    for (m, k, nn_) in [(64, 512, 2048), (8, 256, 1280), (70, 33, 130)]:
+        a = torch.randn(m, k, device=dev); b = torch.randn(k, nn_, device=dev)
+        out.append(_cmp(f"sgemm NN {m}x{k}x{nn_}", K.sgemm(a, b), a.double() @ b.double(), 1e-5))
+        bt = b.t().contiguous()
+        out.append(_cmp(f"sgemm NT {m}x{k}x{nn_}", K.sgemm(a, bt, trans_b=True), a.double() @ b.double(), 1e-5))
+        at = a.t().contiguous()
+        base = torch.randn(m, nn_, device=dev)
+        acc = base.clone()
+        K.sgemm(at, b, trans_a=True, acc_into=acc)
+        out.append(_cmp(f"sgemm TN(acc) {m}x{k}x{nn_}", acc - base, a.double() @ b.double(), 1e-5))
+    return out
+
+
+@check
+def identity_encoder():
+    """The whole identity-encoder schedule (embedders/resnext_native.py) on the GPU vs the torchvision module in
+    float64 with torch autograd: embeddings, every parameter gradient (relative to the gradient's max), running
+    statistics; train and eval mode; then device time of forward + backward at the meta-training shape (64 x 256^2)."""
+    import copy
+    import torch
+    import torchvision
+    from b200lp import ops
+    from embedders import resnext_native
+    out = []
+    dev = "cuda"
+    torch.manual_seed(11)
+    net = torchvision.models.resnext50_32x4d(num_classes=512)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.2)
+                m.running_mean.normal_(0, 0.3); m.running_var.uniform_(0.5, 2.0)
+    for mode, (n, s) in (("train", (8, 128)), ("eval", (8, 64)), ("train", (16, 64))):
+        a = copy.deepcopy(net).to(dev).train(mode == "train")
+        b = copy.deepcopy(net).double().to(dev).train(mode == "train")
+        x = torch.rand(n, 3, s, s, device=dev)
+        wgt = torch.randn(n, 512, device=dev)
+        ya = resnext_native.apply(a, x)
+        (ya * wgt).sum().backward()
+        yb = b(x.double())
+        (yb * wgt.double()).sum().backward()
+        torch.cuda.synchronize()
+        tag = f"{mode} N{n} {s}x{s}"
+        out.append(_cmp(f"identity embeddings {tag}", ya, yb, 2e-3))
+        worst, worst_name, rels = 0.0, "", []
+        for (nm, p), q in zip(a.named_parameters(), b.parameters()):
+            r = float((p.grad.double() - q.grad).abs().max() / (q.grad.abs().max() + 1e-30))
+            rels.append(r)
+            if r > worst:
+                worst, worst_name = r, nm
+        rels.sort()
+        out.append({"case": f"identity parameter gradients {tag}", "ok": worst < 3e-2, "max_abs": worst, "rel": worst,
+                    "nan": worst != worst, "ref_max": 1.0, "worst": worst_name, "median_rel": rels[len(rels) // 2],
+                    "p90_rel": rels[int(len(rels) * 0.9)]})
+        if mode == "train":
+            rm = torch.cat([m.running_mean for m in a.modules() if isinstance(m, torch.nn.BatchNorm2d)])
+            rmb = torch.cat([m.running_mean for m in b.modules() if isinstance(m, torch.nn.BatchNorm2d)])
+            rv = torch.cat([m.running_var for m in a.modules() if isinstance(m, torch.nn.BatchNorm2d)])
+            rvb = torch.cat([m.running_var for m in b.modules() if isinstance(m, torch.nn.BatchNorm2d)])
+            out.append(_cmp(f"identity running_mean {tag}", rm, rmb, 1e-3))
+            out.append(_cmp(f"identity running_var {tag}", rv, rvb, 1e-3))
+        # gradient sinks: same gradients accumulated in place
+        a2 = copy.deepcopy(net).to(dev).train(mode == "train")
+        bufs = {nm: torch.zeros_like(p) for nm, p in a2.named_parameters()}
+        with ops.direct_grads({p.data_ptr(): bufs[nm] for nm, p in a2.named_parameters()}):
+            y2 = resnext_native.apply(a2, x)
+            (y2 * wgt).sum().backward()
+        torch.cuda.synchronize()
+        worst = max(float((bufs[nm] - p.grad).abs().max() / (p.grad.abs().max() + 1e-30)) for nm, p in a.named_parameters())
+        out.append({"case": f"identity gradient sinks == autograd path {tag}", "ok": worst < 1e-5, "max_abs": worst, "rel": worst,
+                    "nan": worst != worst, "ref_max": 1.0})
+        del a, b, a2
+    # timing at the meta-training shape
+    a = copy.deepcopy(net).to(dev).train()
+    x = torch.rand(64, 3, 256, 256, device=dev)
+    wgt = torch.randn(64, 512, device=dev)
+
+    def step_native():
+        y = resnext_native.apply(a, x)
+        (y * wgt).sum().backward()
+
+    def step_torch():
+        y = a(x)
+        (y * wgt).sum().backward()
+
+    rec = {"case": "timing identity encoder fwd+bwd 64 x 256x256 (us)", "ok": True, "max_abs": 0.0, "rel": 0.0, "nan": False,
+           "ref_max": 0.0}
+    rec["native_us"] = round(_time_us(step_native, reps=3, warm=2), 0)
+    rec["torch_cudnn_us"] = round(_time_us(step_torch, reps=3, warm=2), 0)
+    with torch.no_grad():
+        rec["native_fwd_only_us"] = round(_time_us(lambda: resnext_native.apply(a, x), reps=3, warm=1), 0)
+    out.append(rec)
+    return out
+
+
 def _run_child(name):
     res = CHECKS[name]()
     print("@@RESULT@@" + json.dumps(res))
