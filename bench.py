@@ -6,11 +6,14 @@ One "step" = one full optimisation step of the reference's runner (runners/holyc
 synthetic 256x256 samples per GPU: embedder -> generator -> discriminator x3 -> criteria -> loss_G.backward ->
 optimizer_G -> loss_D.backward -> optimizer_D -> EMA.  Default workload = BASELINE.json configs[1]
 (`finetuning-base`: criteria adversarial+featmat+idt_embed+perceptual+dice, RAdam, EMA 0.972, identity encoder off),
-per-GPU batch fixed as N grows (weak scaling, one NCCL all-reduce per backward).
+per-GPU batch fixed as N grows (weak scaling, one NCCL all-reduce per backward).  Under torchrun (N > 1) the workload
+is BASELINE.json configs[2] (meta-training, the only configuration the reference runs data-parallel); the N = 1 line
+reports that workload too (`e2e.metatrain`).
 
 Prints ONE JSON line (rank 0).  `value` = frames/s with the batches already resident in HBM; `e2e` = the same metric
 through the public plugin API with pinned HOST batches (H2D inside the timed region, loss values read back).
-`--impl reference` times the CPU port of the reference step (oracle/cpu_step.py) on the host cores.
+`--impl reference` times the UNMODIFIED reference's step (its own modules, imported from baseline/_ref by
+oracle/ref_bench.py in a separate process) on the host cores, same workload and batch.
 """
 import argparse
 import json
@@ -53,7 +56,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="finetune", choices=list(WORKLOADS) + ["drive"])
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS) + ["drive"],
+                    help="default: finetune (BASELINE configs[1]) on one GPU, metatrain (configs[2]) under torchrun")
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the step kernel by kernel instead of replaying a CUDA graph")
@@ -169,13 +173,33 @@ def timed(fn, steps, dist_on):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(workload, sample_batch, steps, warmup, budget_s=25.0):
-    """frames/s of the CPU port of the reference step (oracle/cpu_step.py) with all host threads."""
+def reference_cpu_run(workload, batch, steps, warmup, budget_s):
+    """The UNMODIFIED reference's step on the host cores (oracle/ref_bench.py in its own process: the reference's package
+    names collide with this repo's plugin tree).  Returns its JSON dict, or None when no reference tree travels with the
+    repo (baseline/_ref, staged by __graft_entry__.build(), or /root/reference)."""
+    # torch CPU convolutions stop scaling (and then thrash) well below the 128 hardware threads some hosts expose:
+    # 132.8 s/step with 128 threads (profiles/r01_bench_first_run.json) — use at most 32 and say so
+    cores = min(os.cpu_count() or 1, 32)
+    cmd = [sys.executable, str(ROOT / "oracle" / "ref_bench.py"), "--workload", workload, "--batch", str(batch), "--steps",
+           str(steps), "--warmup", str(warmup), "--budget-s", str(budget_s), "--threads", str(cores)]
+    env = dict(os.environ)
+    env.pop("OMP_NUM_THREADS", None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=budget_s * 3 + 600, env=env).stdout
+    except Exception:
+        return None
+    for line in reversed(out.strip().splitlines()):
+        if line.startswith("{"):
+            d = json.loads(line)
+            return None if "unavailable" in d else d
+    return None
+
+
+def cpu_port_rate(workload, sample_batch, steps, warmup, budget_s=25.0):
+    """Fallback when the reference tree is absent: frames/s of the CPU port of the step (oracle/cpu_step.py)."""
     from oracle.cpu_step import OracleTrainer
     from oracle import synth
     wl = WORKLOADS[workload]
-    # torch CPU convolutions stop scaling (and then thrash) well below the 128 hardware threads of the GPU box's host:
-    # 132.8 s/step with 128 threads (profiles/r01_bench_first_run.json) — use at most 32 and say so
     cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     cfg = dict(synth.FULL_CFG)
@@ -194,25 +218,43 @@ def cpu_reference_rate(workload, sample_batch, steps, warmup, budget_s=25.0):
         if time.perf_counter() - t0 > budget_s:      # bounded sample: stop after ~budget_s seconds of CPU work
             break
     dt = (time.perf_counter() - t0) / done
-    return sample_batch / dt, dt, cores
+    return {"frames_per_s": sample_batch / dt, "s_per_step": dt, "steps": done, "warmup": warmup, "batch": sample_batch,
+            "cores": cores, "kind": "port", "spread": 0.0}
+
+
+def cpu_step_rate(workload, batch, steps, warmup, budget_s):
+    r = reference_cpu_run(workload, batch, steps, warmup, budget_s)
+    if r is None:
+        r = cpu_port_rate(workload, batch, steps, warmup, budget_s)
+        r["note"] = "reference tree absent (no baseline/_ref): CPU port of the step (oracle/cpu_step.py)"
+    return r
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the step, SAME workload and per-GPU batch as this
+    repo's arm, 1 warm-up + as many of the requested steps as fit the time budget (>= 3 when possible); rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl_name = "finetune" if args.workload == "drive" else args.workload
-    sample_b = 1
-    steps, warmup = max(1, min(args.steps, 6)), 0
-    rate, dt, cores = cpu_reference_rate(wl_name, sample_b, steps, warmup, budget_s=60.0)
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    wl_name = args.workload or ("finetune" if world == 1 else "metatrain")
+    if wl_name == "drive":
+        wl_name = "finetune"
+    warmup = 1 if args.warmup > 0 else 0
+    r = cpu_step_rate(wl_name, args.batch, max(args.steps, 3), warmup, budget_s=200.0)
+    rate, dt = r["frames_per_s"], r["s_per_step"]
+    sample = (f"{r['steps']} step(s) after {r['warmup']} warm-up at batch {r['batch']} = the per-GPU batch of the product arm, "
+              f"fp32, {r['cores']} torch threads (reference pins 1, utils/utils.py:19: overridden), "
+              f"run-to-run spread {100 * r.get('spread', 0.0):.1f} %")
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+            "warmup": r["warmup"], "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS[wl_name]["desc"], "global_batch": sample_b,
-                       "note": "reference's CPU implementation of the step (torch CPU operators, oracle port), "
-                               "each step a bounded sample: batch 1 of the same workload"},
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{steps} step(s) at batch {sample_b}, fp32, {cores} torch threads"},
+            "config": {"workload": WORKLOADS[wl_name]["desc"], "global_batch": args.batch, "per_gpu_batch": args.batch,
+                       "image_size": 256,
+                       "note": ("the UNMODIFIED reference modules (runners.holycow step over the reference's plugins) on the "
+                                "host CPU" if r["kind"] == "reference" else r.get("note", "CPU port")) +
+                               f"; requested steps {args.steps} / warm-up {args.warmup} bounded to a ~200 s CPU budget"},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -257,49 +299,50 @@ def build_training(wl, device, batch):
     return runner, tm, opt_G, opt_D, ns
 
 
-def roofline_pass(step_fn, peaks):
-    """One instrumented step: CUDA events around every libb200lp call on the launching stream -> per-family time,
-    algorithmic FLOPs / bytes -> achieved throughput of the dominant kernel family."""
-    from b200lp import kernels as K
-    rec = []
-    torch.cuda.synchronize()
-    # Park the GPU on a ~150 ms spin kernel while the host enqueues the whole step (kernels + bracketing events): the
-    # kernels then run back to back and the event pairs measure kernel time, not the host's launch latency.
-    torch.cuda._sleep(int(0.15 * 1.9e9))
-    K.PROFILE = rec
-    step_fn(0)
-    K.PROFILE = None
-    torch.cuda.synchronize()
-    fam = {}
-    for name, work, e0, e1 in rec:
-        d = fam.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
-        d["ms"] += e0.elapsed_time(e1)
-        d["flops"] += work.get("flops", 0.0)
-        d["bytes"] += work.get("bytes", 0.0)
-        d["launches"] += 1
-    total_ms = sum(d["ms"] for d in fam.values()) or 1.0
-    table = {k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / total_ms, 3), "launches": v["launches"],
-                 "tflops": round(v["flops"] / v["ms"] / 1e9, 1) if v["flops"] else None,
-                 "gbs": round(v["bytes"] / v["ms"] / 1e6, 1) if v["bytes"] else None}
-             for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
-    out = {"families": table}
-    conv = fam.get("conv_igemm_tf32")
-    if conv:
+def roofline_from_replay(replay_fn, work, peaks):
+    """Per-family device time of ONE replay of the captured step (CUPTI kernel durations through torch.profiler: the
+    kernels as they run back to back inside the graph, not event pairs around eager launches) against the algorithmic
+    FLOPs / bytes the host booked while the step was captured (b200lp.kernels.WORK) -> the dominant
+    family's achieved throughput.  Runs outside every timed region."""
+    rows, total_ms = replay_kernel_times(replay_fn)
+    table = family_table(rows, work)
+    own_ms = sum(ms for n, (ms, c) in rows.items() if is_own_kernel(n))
+    out = {"families": table, "replay": {"kernel_ms": round(total_ms, 3), "launches": sum(c for _, c in rows.values()),
+                                         "libb200lp_share": round(own_ms / (total_ms or 1.0), 3)}}
+    traffic = {}
+    tj = ROOT / "profiles" / "r02_dram_traffic.json"      # ncu dram__bytes_{read,write}.sum per launch, same command
+    if tj.exists():
+        traffic = json.loads(tj.read_text())
+    conv = table.get("conv_igemm_tf32")
+    if conv and conv["tflops"]:
         tf32_peak = peaks.get("bf16_tflops_sustained", 1437.4) / 2.0
-        ach = conv["flops"] / conv["ms"] / 1e9
-        out["roofline"] = {"kernel": "conv_igemm_tf32 (tcgen05 fwd + dgrad)", "bound": "tensor", "achieved": round(ach, 1),
-                           "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": round(ach / tf32_peak, 3),
-                           "traffic": None,
+        ach = conv["tflops"]
+        t = traffic.get("conv_igemm_tf32", {})
+        out["roofline"] = {"kernel": "conv_igemm_tf32 family: conv_halo2 / conv_halo / conv_igemm <.., tf32> (tcgen05 fwd + dgrad)",
+                           "bound": "tensor", "achieved": ach, "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
+                           "frac": round(ach / tf32_peak, 3), "traffic": t.get("dram_bytes_per_launch"),
+                           "traffic_note": t.get("note"),
                            "peak_note": "TF32 dense = measured sustained bf16 cuBLAS TF/s / 2 (MEASURED_PEAKS.json); "
                                         "frac of the bf16 figure itself = %.3f" % (ach / (2 * tf32_peak)),
-                           "avg_launch_ms": round(conv["ms"] / conv["launches"], 4), "launches_per_step": conv["launches"]}
-    hbm = fam.get("adain_relu")
-    if hbm:
-        ach = hbm["bytes"] / hbm["ms"] / 1e6
-        peak = peaks.get("hbm_gbs", 6580.3)
-        out["roofline_hbm"] = {"kernel": "adain_relu (IN apply + AdaIN + ReLU [+2x])", "bound": "hbm",
-                               "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 3),
-                               "traffic": None}
+                           "timing": "CUPTI kernel durations of one graph replay", "avg_launch_ms":
+                               round(conv["ms"] / conv["launches"], 4), "launches_per_step": conv["launches"],
+                           "algorithmic_tflop_per_step": round(work.get("conv_igemm_tf32", {}).get("flops", 0.0) / 1e12, 3)}
+        wg = table.get("conv_wgrad_tf32")
+        if wg and wg["tflops"]:
+            red = table.get("wgrad_reduce", {"ms": 0.0})
+            out["roofline"]["wgrad"] = {"kernel": "conv_wgrad_tf32_kernel", "achieved": wg["tflops"],
+                                        "frac": round(wg["tflops"] / tf32_peak, 3),
+                                        "achieved_with_reduce": round(wg["tflops"] * wg["ms"] / (wg["ms"] + red["ms"]), 1),
+                                        "unit": "TFLOP/s"}
+        peak_h = peaks.get("hbm_gbs", 6580.3)
+        hb = {}
+        for fam in ("adain_relu", "in_stats", "adain_relu_bwd", "batchnorm", "l1", "elementwise"):
+            f = table.get(fam)
+            if f and f["gbs"]:
+                hb[fam] = {"achieved": f["gbs"], "frac": round(f["gbs"] / peak_h, 3), "ms": f["ms"]}
+        if hb:
+            out["roofline"]["hbm"] = {"peak": peak_h, "unit": "GB/s", "bound": "hbm", "families": hb,
+                                      "note": "algorithmic bytes (DESIGN.md §3) / CUPTI time of the family in one replay"}
     return out
 
 
@@ -328,8 +371,10 @@ def kernel_family(name):
              ("adain_relu", "adain_relu"), ("l1_", "l1"), ("pack_conv_weight", "pack_conv_weight"),
              ("adam_ema", "optimizer"), ("ema_multi", "optimizer"), ("opt_tick", "optimizer"),
              ("gen_tail", "gen_tail"), ("conv3x3_c3", "c3_stem"), ("im2col3x3", "c3_stem"), ("col2im3x3", "c3_stem"),
-             ("gconv", "resnext_grouped"), ("rx_", "resnext"), ("bn_", "batchnorm"), ("pw_", "pose_encoder"),
-             ("dw_", "pose_encoder"), ("mbv2", "pose_encoder"))
+             ("gconv", "resnext_grouped"), ("im2col7x7", "resnext"), ("maxpool3x3s2", "resnext"), ("subsample2", "resnext"),
+             ("scatter_add2", "resnext"), ("avgpool_", "resnext"), ("sgemm_", "resnext"), ("col_stats", "batchnorm"),
+             ("bn_apply", "pose_encoder"), ("bn_relu6_avgpool", "pose_encoder"), ("bn_", "batchnorm"),
+             ("pw_", "pose_encoder"), ("dw_", "pose_encoder"), ("mbv2", "pose_encoder"))
     for prefix, fam in table:
         if base.startswith(prefix):
             return fam
@@ -354,9 +399,20 @@ def replay_kernel_times(fn):
     return rows, sum(ms for ms, _ in rows.values())
 
 
+WRAPPER_FAMILY = {"conv3x3_c3_fwd": "c3_stem", "c3_im2col": "c3_stem", "c3_col2im": "c3_stem", "conv3x3_c3_dgrad": "c3_stem",
+                  "conv3x3_c3_wgrad": "c3_stem", "gen_tail_fwd": "gen_tail", "gen_tail_bwd_act": "gen_tail",
+                  "gen_tail_bwd_data": "gen_tail"}
+
+
 def family_table(rows, work=None):
     """Aggregate replay_kernel_times rows into families; `work` = {family: {flops, bytes}} algorithmic work of one step
     (b200lp.kernels.WORK, accumulated on the host while the step was captured)."""
+    merged = {}
+    for k, v in (work or {}).items():
+        d = merged.setdefault(WRAPPER_FAMILY.get(k, k), {"flops": 0.0, "bytes": 0.0})
+        d["flops"] += v.get("flops", 0.0)
+        d["bytes"] += v.get("bytes", 0.0)
+    work = merged
     fam = {}
     for name, (ms, c) in rows.items():
         d = fam.setdefault(kernel_family(name), {"ms": 0.0, "launches": 0})
@@ -405,17 +461,91 @@ def drive_benchmark(device, batch=64, n_batches=6):
                     "(bf16x3), clamp+uint8, async D2H of the frames"}
 
 
-def shutdown_distributed():
-    """Leave a multi-rank run without touching NCCL again: the step's CUDA graph holds the communicator's captured
-    all-reduces, and tearing the process group down under it was observed to hang (2-GPU run, profiles/README.md).
-    Everything has been printed and synchronised by now, so the ranks just meet once more and exit."""
-    import sys
+def shutdown_distributed(graphed_steps):
+    """Leave a multi-rank run cleanly: the step's CUDA graph holds the communicator's captured all-reduces, and tearing
+    the process group down UNDER a live graph hangs — so the graphs (and everything they keep alive) are destroyed first,
+    the device is drained, and only then the process group is destroyed.  A watchdog thread ends the process if NCCL's
+    teardown still does not return (everything has been printed by then)."""
+    import gc
     torch.cuda.synchronize()
     torch.distributed.barrier()
+    for g in graphed_steps:
+        if g is not None:
+            g.release()
+    gc.collect()
     torch.cuda.synchronize()
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
+    timer = threading.Timer(30.0, lambda: os._exit(0))
+    timer.daemon = True
+    timer.start()
+    torch.distributed.destroy_process_group()
+    timer.cancel()
+
+
+class StepBench:
+    """One workload set up for measurement: networks, optimizers, the captured step, host and device batches."""
+
+    def __init__(self, name, device, batch, rank, use_graph=True):
+        from utils import utils as U
+        self.U, self.name, self.wl, self.B, self.device = U, name, WORKLOADS[name], batch, device
+        wl = self.wl
+        self.runner, self.tm, self.opt_G, self.opt_D, self.ns = build_training(wl, device, batch)
+        self.tm.broadcast_parameters()
+        self.n_batches = 4
+        self.host = make_host_batches(self.n_batches, batch, wl["k_frames"], wl["num_labels"], rank=rank)
+        self.dev = [({k: v.to(device) for k, v in d.items()}, {k: v.to(device) for k, v in t.items()}) for d, t in self.host]
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host[0][0].values()) + \
+            sum(v.numel() * v.element_size() for v in self.host[0][1].values())
+        self.graphed, self.graph_note = None, "off (--no-graph)"
+        if use_graph:
+            try:
+                self.graphed = self.runner.GraphedTrainStep(self.tm, self.opt_G, self.opt_D, wl["finetune"], self.dev[0][0],
+                                                            self.dev[0][1])
+                self.graph_note = "whole step captured once, replayed per batch"
+            except Exception as err:      # keep measuring (eagerly) and say why
+                self.graph_note = f"capture failed, eager launches: {type(err).__name__}: {str(err)[:160]}"
+                torch.cuda.synchronize()
+        self.n_losses = 0
+
+    def step_eager(self, i):
+        d, t = self.dev[i % self.n_batches]
+        self.runner.train_step(self.tm, dict(d), dict(t), self.opt_G, self.opt_D, finetune=self.wl["finetune"])
+
+    def step_resident(self, i):
+        d, t = self.dev[i % self.n_batches]
+        if self.graphed is not None:
+            self.graphed(d, t)           # device->device copy into the graph's static inputs + replay
+        else:
+            self.runner.train_step(self.tm, dict(d), dict(t), self.opt_G, self.opt_D, finetune=self.wl["finetune"])
+
+    def step_e2e(self, i):
+        """The public API with HOST batches: pinned host -> device inside the timed region (the NEXT batch's upload is
+        prefetched on the copy stream while this step's graph runs, like a prefetching data loader), replay, loss
+        values read back to the host."""
+        d, t = self.host[i % self.n_batches]
+        if self.graphed is not None:
+            nxt = self.host[(i + 1) % self.n_batches]
+            _, lg, ld = self.graphed(d, t, prefetch_next=nxt)
+        else:
+            d, t = dict(d), dict(t)
+            self.U.dict_to_device(d, self.device)
+            self.U.dict_to_device(t, self.device)
+            _, lg, ld = self.runner.train_step(self.tm, d, t, self.opt_G, self.opt_D, finetune=self.wl["finetune"])
+        vals = torch.stack([v.detach().float().reshape(()) for v in list(lg.values()) + list(ld.values())])
+        self.n_losses = vals.numel()
+        return vals.cpu()           # device -> host read of the step's result (the runner's Meter does the same)
+
+    def measure(self, steps, warmup, dist_on, with_e2e=True):
+        for i in range(max(warmup, 3)):
+            self.step_resident(i)
+        ms = timed(self.step_resident, steps, dist_on)
+        ms_e2e = None
+        if with_e2e:
+            for i in range(2):
+                self.step_e2e(i)
+            ms_e2e = timed(self.step_e2e, steps, dist_on)
+        return ms, ms_e2e
 
 
 def main():
@@ -434,68 +564,29 @@ def main():
     if dist_on:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group(backend="nccl", init_method="env://", rank=rank, world_size=world)
-    wl = WORKLOADS[args.workload]
+    # N = 1: BASELINE configs[1] (the fine-tune step, the configuration the reference pins to ONE GPU, train.py:120-126);
+    # N > 1: BASELINE configs[2] (meta-training: the only configuration the reference runs data-parallel,
+    # train.py:98-109) — the N = 1 line carries the meta-training number too (`e2e.metatrain`) as the weak-scaling base.
+    wl_name = args.workload or ("finetune" if world == 1 else "metatrain")
+    wl = WORKLOADS[wl_name]
     B = args.batch
-    runner, tm, opt_G, opt_D, ns = build_training(wl, device, B)
-    tm.broadcast_parameters()
-
     from b200lp import lib
-    from utils import utils as U
-    n_batches = 4
-    host = make_host_batches(n_batches, B, wl["k_frames"], wl["num_labels"], rank=rank)
-    dev_batches = [({k: v.to(device) for k, v in d.items()}, {k: v.to(device) for k, v in t.items()}) for d, t in host]
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0][0].values()) + \
-        sum(v.numel() * v.element_size() for v in host[0][1].values())
+    sb = StepBench(wl_name, device, B, rank, use_graph=not args.no_graph)
 
-    def step_eager(i):
-        d, t = dev_batches[i % n_batches]
-        runner.train_step(tm, dict(d), dict(t), opt_G, opt_D, finetune=wl["finetune"])
-
-    graphed, graph_note = None, "off (--no-graph)"
-    if not args.no_graph:
-        try:
-            graphed = runner.GraphedTrainStep(tm, opt_G, opt_D, wl["finetune"], dev_batches[0][0], dev_batches[0][1])
-            graph_note = "whole step captured once, replayed per batch"
-        except Exception as err:      # keep measuring (eagerly) and say why
-            graph_note = f"capture failed, eager launches: {type(err).__name__}: {str(err)[:160]}"
-            torch.cuda.synchronize()
-
-    def step_resident(i):
-        d, t = dev_batches[i % n_batches]
-        if graphed is not None:
-            graphed(d, t)           # device->device copy into the graph's static inputs + replay
-        else:
-            runner.train_step(tm, dict(d), dict(t), opt_G, opt_D, finetune=wl["finetune"])
-
-    n_losses = [0]
-
-    def step_e2e(i):
-        d, t = host[i % n_batches]
-        if graphed is not None:
-            _, lg, ld = graphed(d, t)          # pinned host -> static device inputs (H2D) + replay
-        else:
-            d, t = dict(d), dict(t)
-            U.dict_to_device(d, device)
-            U.dict_to_device(t, device)
-            _, lg, ld = runner.train_step(tm, d, t, opt_G, opt_D, finetune=wl["finetune"])
-        vals = torch.stack([v.detach().float().reshape(()) for v in list(lg.values()) + list(ld.values())])
-        n_losses[0] = vals.numel()
-        return vals.cpu()           # device -> host read of the step's result (the runner's Meter does the same)
-
-    for i in range(max(args.warmup, 3)):
-        step_resident(i)
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    for i in range(max(args.warmup, 3)):
+        sb.step_resident(i)
     if sampler:
         sampler.start()
     l0 = lib.load().b200lp_launch_count()
     if args.timed_only:          # `ncu --profile-from-start off`: only the timed steps are profiled
         torch.cuda.profiler.start()
-    ms = timed(step_resident, args.steps, dist_on)
+    ms = timed(sb.step_resident, args.steps, dist_on)
     if args.timed_only:
         torch.cuda.profiler.stop()
     launches = lib.load().b200lp_launch_count() - l0
-    if graphed is not None:      # replays do not pass through the library's host-side counter
-        launches = graphed.kernels_per_replay * args.steps
+    if sb.graphed is not None:      # replays do not pass through the library's host-side counter
+        launches = sb.graphed.kernels_per_replay * args.steps
     clocks = sampler.stop() if sampler else None
     if args.timed_only:
         if rank == 0:
@@ -503,41 +594,61 @@ def main():
                               "ms_per_step": round(ms / args.steps, 3), "gpu_launches": int(launches),
                               "note": "timed-only run (profiling aid, not a bench line)"}))
         if dist_on:
-            shutdown_distributed()
+            shutdown_distributed([sb.graphed])
         return
     for i in range(2):
-        step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps, dist_on)
+        sb.step_e2e(i)
+    ms_e2e = timed(sb.step_e2e, args.steps, dist_on)
 
     frames = B * world * args.steps
     value = frames / (ms / 1e3)
     e2e_value = frames / (ms_e2e / 1e3)
 
     extra = {}
-    if not args.no_roofline:
-        # every rank runs the instrumented step (it contains the gradient all-reduces); rank 0 reports
+    if not args.no_roofline and sb.graphed is not None:
+        # every rank replays (the step contains the gradient all-reduces); rank 0 reports
         peaks = {}
         pk = ROOT / "MEASURED_PEAKS.json"
         if pk.exists():
             peaks = json.loads(pk.read_text())
-        prof = roofline_pass(step_eager, peaks)
+        prof = roofline_from_replay(lambda: sb.graphed(*sb.dev[0]), sb.graphed.work, peaks)
         if rank == 0:
             extra.update(prof)
             extra["peaks_source"] = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    also = {}
     if rank == 0 and world == 1:
         try:
             with torch.no_grad():
-                extra["drive"] = drive_benchmark(device)
+                also["drive"] = drive_benchmark(device)
         except Exception as err:
-            extra["drive"] = {"error": str(err)[:200]}
+            also["drive"] = {"error": str(err)[:200]}
+    if world == 1 and wl_name == "finetune" and args.workload is None:
+        # the weak-scaling base of the N > 1 runs: the meta-training step on one GPU
+        try:
+            sb.graphed and sb.graphed.release()
+            sb2 = StepBench("metatrain", device, B, rank, use_graph=not args.no_graph)
+            k2 = max(5, args.steps // 2)
+            ms2, ms2e = sb2.measure(k2, 3, False)
+            also["metatrain"] = {"workload": WORKLOADS["metatrain"]["desc"], "value": round(B * k2 / (ms2 / 1e3), 2),
+                                 "unit": UNIT, "ms_per_step": round(ms2 / k2, 3), "e2e_value": round(B * k2 / (ms2e / 1e3), 2),
+                                 "e2e_ms_per_step": round(ms2e / k2, 3), "steps": k2, "h2d_bytes_per_step": sb2.h2d_bytes,
+                                 "what": "BASELINE configs[2] at N = 1: the base of the N > 1 weak-scaling runs"}
+            if not args.no_roofline and sb2.graphed is not None:
+                rows, tot = replay_kernel_times(lambda: sb2.graphed(*sb2.dev[0]))
+                own = sum(m for n_, (m, c) in rows.items() if is_own_kernel(n_))
+                also["metatrain"]["libb200lp_share_of_kernel_time"] = round(own / (tot or 1.0), 3)
+            sb2.graphed and sb2.graphed.release()
+        except Exception as err:
+            also["metatrain"] = {"error": f"{type(err).__name__}: {str(err)[:200]}"}
     if dist_on:
         torch.distributed.barrier()
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            rate, dt, cores = cpu_reference_rate(args.workload, 1, 2, 0, budget_s=20.0)
-            cpu_baseline = {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": f"<=2 steps at batch 1 of the same workload ({dt:.1f} s/step), fp32, {cores} torch threads"}
+            r = cpu_step_rate(wl_name, 2, 1, 0, budget_s=20.0)
+            cpu_baseline = {"value": round(r["frames_per_s"], 4), "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                            "sample": f"{r['steps']} step at batch {r['batch']} of the same workload ({r['s_per_step']:.1f} s/step, no "
+                                      f"warm-up), fp32, {r['cores']} torch threads; `--impl reference` runs the full batch"}
         except Exception as err:   # the checker must never take the product number down with it
             cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {err}"}
 
@@ -549,16 +660,21 @@ def main():
                 "config": {"workload": wl["desc"], "global_batch": B * world, "per_gpu_batch": B, "image_size": 256,
                            "parallelism": f"dp{world}", "weights": "random init, spectral norm converged",
                            "l2": "per-step working set (activations, ~GBs) >> 126 MB L2; 4 distinct input batches cycled",
-                           "cuda_graph": graph_note},
-                "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                        "d2h_bytes_per_step": 4 * n_losses[0], "ms_per_step": round(ms_e2e / args.steps, 3)},
+                           "cuda_graph": sb.graph_note,
+                           "workload_by_n": "N = 1: configs[1] (reference pins fine-tuning to one GPU, train.py:120-126); "
+                                            "N > 1: configs[2] meta-training (train.py:98-109); its N = 1 base is e2e.metatrain "
+                                            "of the N = 1 line"},
+                "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": sb.h2d_bytes,
+                        "d2h_bytes_per_step": 4 * sb.n_losses, "ms_per_step": round(ms_e2e / args.steps, 3),
+                        "h2d": "pinned host batch -> device on a copy stream, prefetched one step ahead"},
                 "gpu_launches": int(launches), "clocks": clocks}
+        line["e2e"].update(also)
         line.update(extra)
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
     if dist_on:
-        shutdown_distributed()
+        shutdown_distributed([sb.graphed])
 
 
 if __name__ == "__main__":

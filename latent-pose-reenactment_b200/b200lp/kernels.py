@@ -12,6 +12,10 @@ from . import lib as L
 # bench.py's roofline pass: when PROFILE is a list, every C-ABI call is bracketed by CUDA events on the launching
 # stream and recorded as (kernel family, algorithmic work {flops|bytes}, start event, end event).
 PROFILE = None
+# when WORK is a dict, every C-ABI call adds its algorithmic work to WORK[family] = {"flops", "bytes", "calls"} (host-side
+# bookkeeping only; runners.holycow.GraphedTrainStep sets it while it captures the step, bench.py divides the replay's
+# CUPTI kernel times by it)
+WORK = None
 
 
 class _timed:
@@ -19,6 +23,11 @@ class _timed:
         self.family, self.work = family, {"flops": float(flops), "bytes": float(nbytes)}
 
     def __enter__(self):
+        if WORK is not None:
+            d = WORK.setdefault(self.family, {"flops": 0.0, "bytes": 0.0, "calls": 0})
+            d["flops"] += self.work["flops"]
+            d["bytes"] += self.work["bytes"]
+            d["calls"] += 1
         if PROFILE is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e0.record()

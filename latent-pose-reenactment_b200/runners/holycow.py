@@ -339,10 +339,15 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         from b200lp import lib as b200lp_lib
         launched = b200lp_lib.load().b200lp_launch_count()
+        from b200lp import kernels as b200lp_kernels
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.outputs = train_step(training_module, dict(self.static_data), dict(self.static_target), optimizer_G,
-                                      optimizer_D, finetune)
+        b200lp_kernels.WORK = {}            # algorithmic FLOPs / bytes per kernel family of ONE step (host bookkeeping)
+        try:
+            with torch.cuda.graph(self.graph):
+                self.outputs = train_step(training_module, dict(self.static_data), dict(self.static_target),
+                                          optimizer_G, optimizer_D, finetune)
+        finally:
+            self.work, b200lp_kernels.WORK = b200lp_kernels.WORK, None
         # libb200lp kernels recorded in the graph = launched by every replay
         self.kernels_per_replay = int(b200lp_lib.load().b200lp_launch_count() - launched)
         self._restore(training_module, saved)
@@ -395,48 +400,135 @@ class GraphedTrainStep:
                     return False
         return True
 
-    def __call__(self, data_dict, target_dict):
+    # ---------------------------------------------------------------- host -> device input staging
+    def _stage(self, which):
+        """Staging buffers (two sets, used alternately) for batches that arrive in HOST memory: the upload of batch i+1
+        runs on a copy stream while the graph of batch i executes; at the start of step i+1 the graph's static inputs
+        are refreshed from the staging set by a device-to-device copy (tens of microseconds)."""
+        if getattr(self, '_staging', None) is None:
+            self._staging = [None, None]
+            self._consumed = [None, None]      # event: the compute stream finished reading that staging set
+            self._copy_stream = torch.cuda.Stream()
+            self._pending = None
+        if self._staging[which] is None:
+            self._staging[which] = ({k: torch.empty_like(v) for k, v in self.static_data.items()},
+                                    {k: torch.empty_like(v) for k, v in self.static_target.items()})
+        return self._staging[which]
+
+    def prefetch(self, data_dict, target_dict):
+        """Start the host -> device upload of a FUTURE batch on the copy stream (pinned host tensors make it
+        asynchronous).  The next __call__ with these very dicts consumes it."""
+        if not self.matches(data_dict, target_dict) or any(v.is_cuda for v in data_dict.values() if torch.is_tensor(v)):
+            return
+        which = 1 - getattr(self, '_last_stage', 1)
+        sd, st = self._stage(which)
+        with torch.cuda.stream(self._copy_stream):
+            # the set being overwritten was last read by the device-to-device refresh of two steps ago: wait for THAT
+            # copy only (not for the compute stream's current position — the replay in flight must keep overlapping)
+            if self._consumed[which] is not None:
+                self._copy_stream.wait_event(self._consumed[which])
+            for k, v in sd.items():
+                v.copy_(data_dict[k], non_blocking=True)
+            for k, v in st.items():
+                v.copy_(target_dict[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._pending = (id(data_dict), id(target_dict), which, ev)
+        self._last_stage = which
+
+    def release(self):
+        """Destroy the captured graph and everything it keeps alive (its private memory pool, the captured NCCL
+        all-reduces).  Must happen before torch.distributed.destroy_process_group()."""
+        self.graph = None
+        self.outputs = None
+        self._staging = None
+        self._consumed = [None, None]
+        self._pending = None
+        torch.cuda.synchronize()
+
+    def __call__(self, data_dict, target_dict, prefetch_next=None):
+        """Replay the step on a batch.  Device-resident batches are copied into the static inputs directly; host batches
+        go through the prefetched staging set when `prefetch` was called for them (else an in-line upload).
+        `prefetch_next` = (data_dict, target_dict) of the batch after this one: its upload overlaps this replay."""
         from b200lp import ops
+        if self.graph is None:
+            raise RuntimeError("GraphedTrainStep was released")
         if not self.matches(data_dict, target_dict):
             raise ValueError("GraphedTrainStep: batch does not have the captured shapes / keys "
                              f"({ {k: tuple(v.shape) for k, v in self.static_data.items()} })")
         for o in self.optimizers:            # lr / ema_alpha live in a device vector the captured kernels read
             if hasattr(o, 'sync_hyper'):
                 o.sync_hyper()
-        for k, v in self.static_data.items():
-            v.copy_(data_dict[k], non_blocking=True)
-        for k, v in self.static_target.items():
-            v.copy_(target_dict[k], non_blocking=True)
+        pend = getattr(self, '_pending', None)
+        if pend is not None and pend[0] == id(data_dict) and pend[1] == id(target_dict):
+            sd, st = self._staging[pend[2]]
+            torch.cuda.current_stream().wait_event(pend[3])
+            for k, v in self.static_data.items():
+                v.copy_(sd[k], non_blocking=True)
+            for k, v in self.static_target.items():
+                v.copy_(st[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._consumed[pend[2]] = ev
+            self._pending = None
+        else:
+            for k, v in self.static_data.items():
+                v.copy_(data_dict[k], non_blocking=True)
+            for k, v in self.static_target.items():
+                v.copy_(target_dict[k], non_blocking=True)
         self.graph.replay()
+        if prefetch_next is not None:
+            self.prefetch(*prefetch_next)
         ops.bump_generation()        # weights were rewritten by the replayed optimizer kernels
         return self.outputs
+
+
+def _with_lookahead(iterable):
+    """(item, next item or None) pairs: lets the epoch loop start the next batch's upload while this one computes."""
+    it = iter(iterable)
+    try:
+        cur = next(it)
+    except StopIteration:
+        return
+    for nxt in it:
+        yield cur, nxt
+        cur = nxt
+    yield cur, None
 
 
 def run_epoch(dataloader, training_module, optimizer_G, optimizer_D, epoch, args, phase, writer=None, saver=None):
     meter = Meter()
     end = time.time()
     use_graph = phase == 'train' and getattr(args, 'cuda_graph', False) and str(args.device).startswith('cuda')
-    for it, (data_dict, target_dict) in enumerate(dataloader):
+    for it, ((data_dict, target_dict), upcoming) in enumerate(_with_lookahead(dataloader)):
         meter.add('Data_time', time.time() - end)
-        utils.dict_to_device(data_dict, args.device)
-        utils.dict_to_device(target_dict, args.device)
 
         if use_graph:
             key = (id(optimizer_G), id(optimizer_D))
             graphed = getattr(training_module, '_graphed_step', None)
             if graphed is None or graphed[0] != key:
-                graphed = (key, GraphedTrainStep(training_module, optimizer_G, optimizer_D, args.finetune, data_dict,
-                                                 target_dict))
+                dev_data, dev_target = dict(data_dict), dict(target_dict)
+                utils.dict_to_device(dev_data, args.device)
+                utils.dict_to_device(dev_target, args.device)
+                graphed = (key, GraphedTrainStep(training_module, optimizer_G, optimizer_D, args.finetune, dev_data,
+                                                 dev_target))
                 training_module._graphed_step = graphed
             if graphed[1].matches(data_dict, target_dict):
-                all_data_dict, losses_G_dict, losses_D_dict = graphed[1](data_dict, target_dict)
+                # host batches: this batch's upload was prefetched during the previous step; start the next one's now
+                all_data_dict, losses_G_dict, losses_D_dict = graphed[1](data_dict, target_dict, prefetch_next=upcoming)
             else:       # e.g. a dataset plugin's own loader without drop_last: run this batch eagerly
+                utils.dict_to_device(data_dict, args.device)
+                utils.dict_to_device(target_dict, args.device)
                 all_data_dict, losses_G_dict, losses_D_dict = train_step(
                     training_module, data_dict, target_dict, optimizer_G, optimizer_D, finetune=args.finetune)
         elif phase == 'train':
+            utils.dict_to_device(data_dict, args.device)
+            utils.dict_to_device(target_dict, args.device)
             all_data_dict, losses_G_dict, losses_D_dict = train_step(
                 training_module, data_dict, target_dict, optimizer_G, optimizer_D, finetune=args.finetune)
         else:
+            utils.dict_to_device(data_dict, args.device)
+            utils.dict_to_device(target_dict, args.device)
             all_data_dict, losses_G_dict, losses_D_dict = training_module(data_dict, target_dict)
             if saver is not None:
                 saver.save(epoch=epoch, data=all_data_dict)
