@@ -483,52 +483,74 @@ gconv3x3_dgrad_s2_kernel(const float* __restrict__ dy, const float* __restrict__
 }
 
 // weight gradient: dW[g*CPG+co][ci][tap] = sum_{n,ho,wo} dy[n,ho,wo,g*CPG+co] * f(x[n, ho*s+kh-1, wo*s+kw-1, g*CPG+ci]).
-// A thread owns (group, 2 output channels, 4 input channels) x 9 taps = 72 accumulators and walks the pixels of its
-// chunk; partial sums go to ws[chunk][tap][co_abs][ci] (16-byte stores), merged in a fixed order by the reduce kernel.
-// block 256 = TS owner threads x (256 / TS) pixel lanes;  TS = min(256, C*CPG/8);  grid = (chunks, C*CPG/8 / TS)
+// A thread owns (group, 2 output channels, 4 input channels, ONE filter row kh) = 24 accumulators and walks the pixels of
+// its chunk two at a time with all eight loads (2 x (dy pair + three taps of x)) issued before the first use — the first
+// version (72 accumulators, a branch per tap) serialised on the L2 latency at 8 warps per SM: 1.2 ms per layer.  Partial
+// sums go to ws[chunk][tap][co_abs][ci] (16-byte stores), merged in a fixed order by the reduce kernel.
+// block = TS owner threads x (256 / TS) pixel lanes;  TS = min(256, 3*C*CPG/8) (a multiple of 3*CPG/4... of 32 here);
+// grid = (chunks, 3*C*CPG/8 / TS)
 template <int CPG>
 __global__ void __launch_bounds__(256)
 gconv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, const float* __restrict__ in_shift,
                       const float* __restrict__ dy, float* __restrict__ ws, int N, int H, int W, int C, int stride, int Ho,
                       int Wo, int pix_per_chunk, int TS) {
-    extern __shared__ float4 red4[];                  // [lanes-1][TS][18] float4 for the cross-lane merge
-    const int t = threadIdx.x % TS, lanes = 256 / TS, ln = threadIdx.x / TS;
-    const int owner = blockIdx.y * TS + t;            // (g, co2, ci4): ci4 fastest
-    const int ci4 = owner % (CPG / 4);
-    const int co2 = (owner / (CPG / 4)) % (CPG / 2);
-    const int g = owner / ((CPG / 4) * (CPG / 2));
+    extern __shared__ float4 red4[];                  // [lanes-1][TS][6] float4 for the cross-lane merge
+    const int t = threadIdx.x % TS, lanes = blockDim.x / TS, ln = threadIdx.x / TS;
+    const int owner = blockIdx.y * TS + t;            // (g, co2, ci4, kh): kh fastest, then ci4
+    const int kh = owner % 3;
+    const int ci4 = (owner / 3) % (CPG / 4);
+    const int co2 = (owner / (3 * (CPG / 4))) % (CPG / 2);
+    const int g = owner / (3 * (CPG / 4) * (CPG / 2));
     const int cin = g * CPG + ci4 * 4, cout = g * CPG + co2 * 2;
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
     if (in_scale) { sc = ldg4(in_scale + cin); sh = ldg4(in_shift + cin); }
-    float4 acc[2][9];
+    float4 acc[2][3];
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int k = 0; k < 9; ++k) acc[c][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 3; ++k) acc[c][k] = make_float4(0.f, 0.f, 0.f, 0.f);
     const long P = static_cast<long>(N) * Ho * Wo;
     const long p0 = static_cast<long>(blockIdx.x) * pix_per_chunk;
     const long p1 = min(p0 + static_cast<long>(pix_per_chunk), P);
-    for (long p = p0 + ln; p < p1; p += lanes) {
-        const int wo = static_cast<int>(p % Wo);
-        const int ho = static_cast<int>((p / Wo) % Ho);
-        const int n = static_cast<int>(p / (static_cast<long>(Wo) * Ho));
-        const float2 d = __ldg(reinterpret_cast<const float2*>(dy + static_cast<size_t>(p) * C + cout));
+    const bool act = in_scale != nullptr;
+    for (long pb = p0 + ln; pb < p1; pb += 2L * lanes) {
+        float2 d[2];
+        float4 v[2][3];
+        bool ok[2][3];
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
+        for (int u = 0; u < 2; ++u) {
+            const long p = pb + static_cast<long>(u) * lanes;
+            const bool pv = p < p1;
+            const long pp = pv ? p : p0;
+            const int wo = static_cast<int>(pp % Wo);
+            const int ho = static_cast<int>((pp / Wo) % Ho);
+            const int n = static_cast<int>(pp / (static_cast<long>(Wo) * Ho));
             const int hi = ho * stride + kh - 1;
+            const bool hok = pv && hi >= 0 && hi < H;
+            d[u] = __ldg(reinterpret_cast<const float2*>(dy + static_cast<size_t>(pp) * C + cout));
+            const size_t rowbase = static_cast<size_t>(n * H + (hok ? hi : 0)) * W;
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
                 const int wi = wo * stride + kw - 1;
-                if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
-                float4 v = ldg4(x + (static_cast<size_t>(n * H + hi) * W + wi) * C + cin);
-                if (in_scale) {
-                    v.x = fmaxf(v.x * sc.x + sh.x, 0.f); v.y = fmaxf(v.y * sc.y + sh.y, 0.f);
-                    v.z = fmaxf(v.z * sc.z + sh.z, 0.f); v.w = fmaxf(v.w * sc.w + sh.w, 0.f);
+                const bool in = hok && wi >= 0 && wi < W;
+                ok[u][kw] = in;
+                v[u][kw] = ldg4(x + (rowbase + (in ? wi : 0)) * C + cin);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                if (!ok[u][kw]) continue;                 // zero padding applies to the activation, not to the raw input
+                float4 a = v[u][kw];
+                if (act) {
+                    a.x = fmaxf(a.x * sc.x + sh.x, 0.f); a.y = fmaxf(a.y * sc.y + sh.y, 0.f);
+                    a.z = fmaxf(a.z * sc.z + sh.z, 0.f); a.w = fmaxf(a.w * sc.w + sh.w, 0.f);
                 }
-                float4& a0 = acc[0][kh * 3 + kw];
-                float4& a1 = acc[1][kh * 3 + kw];
-                a0.x = fmaf(d.x, v.x, a0.x); a0.y = fmaf(d.x, v.y, a0.y); a0.z = fmaf(d.x, v.z, a0.z); a0.w = fmaf(d.x, v.w, a0.w);
-                a1.x = fmaf(d.y, v.x, a1.x); a1.y = fmaf(d.y, v.y, a1.y); a1.z = fmaf(d.y, v.z, a1.z); a1.w = fmaf(d.y, v.w, a1.w);
+                float4& a0 = acc[0][kw];
+                float4& a1 = acc[1][kw];
+                a0.x = fmaf(d[u].x, a.x, a0.x); a0.y = fmaf(d[u].x, a.y, a0.y); a0.z = fmaf(d[u].x, a.z, a0.z); a0.w = fmaf(d[u].x, a.w, a0.w);
+                a1.x = fmaf(d[u].y, a.x, a1.x); a1.y = fmaf(d[u].y, a.y, a1.y); a1.z = fmaf(d[u].y, a.z, a1.z); a1.w = fmaf(d[u].y, a.w, a1.w);
             }
         }
     }
@@ -538,7 +560,7 @@ gconv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ in_
 #pragma unroll
             for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int k = 0; k < 9; ++k) red4[(static_cast<size_t>(ln - 1) * TS + t) * 18 + c * 9 + k] = acc[c][k];
+                for (int k = 0; k < 3; ++k) red4[(static_cast<size_t>(ln - 1) * TS + t) * 6 + c * 3 + k] = acc[c][k];
         }
         __syncthreads();
         if (ln == 0) {
@@ -546,8 +568,8 @@ gconv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ in_
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) {
-                        const float4 o = red4[(static_cast<size_t>(l - 1) * TS + t) * 18 + c * 9 + k];
+                    for (int k = 0; k < 3; ++k) {
+                        const float4 o = red4[(static_cast<size_t>(l - 1) * TS + t) * 6 + c * 3 + k];
                         acc[c][k].x += o.x; acc[c][k].y += o.y; acc[c][k].z += o.z; acc[c][k].w += o.w;
                     }
         }
@@ -557,8 +579,8 @@ gconv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ in_
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
-            for (int k = 0; k < 9; ++k)
-                *reinterpret_cast<float4*>(base + (static_cast<size_t>(k) * C + cout + c) * CPG + ci4 * 4) = acc[c][k];
+            for (int k = 0; k < 3; ++k)
+                *reinterpret_cast<float4*>(base + (static_cast<size_t>(kh * 3 + k) * C + cout + c) * CPG + ci4 * 4) = acc[c][k];
     }
 }
 
@@ -828,12 +850,14 @@ static int ew_blocks(long total4) {
     return static_cast<int>(blocks);
 }
 
-// pixel chunks of the grouped weight gradient: about 148 x 8 blocks in total, >= 32 pixels per chunk
+// pixel chunks of the grouped weight gradient: about 148 x 16 blocks in total, >= 32 pixels per chunk
 static int gconv_wgrad_plan(long P, int C, int cpg, int* pix_per_chunk, int* TS, int* slices) {
-    const int owners = C * cpg / 8;
-    *TS = owners < 256 ? owners : 256;
-    *slices = owners / *TS;
-    long chunks = (148L * 8) / *slices;
+    const int owners = 3 * (C * cpg / 8);           // (group, output-channel pair, input-channel quad, filter row)
+    int ts = owners < 256 ? owners : 256;           // 3 * 32 * cpg^2 / 8 owners for 32 groups: 192 for cpg = 4, k * 256 above
+    while (owners % ts) --ts;                       // other group counts: the largest divisor <= 256
+    *TS = ts;
+    *slices = owners / ts;
+    long chunks = (148L * 16) / *slices;
     if (chunks < 1) chunks = 1;
     long ppc = (P + chunks - 1) / chunks;
     if (ppc < 32) ppc = 32;
@@ -1024,14 +1048,14 @@ static int launch_gconv_wgrad(const float* x, const float* sc, const float* sh, 
                               int W, int C, int stride, int Ho, int Wo, int chunks, int ppc, int ts, int slices,
                               cudaStream_t st) {
     const int lanes = 256 / ts;
-    const int bytes = (lanes > 1 ? (lanes - 1) * ts * 18 * 16 : 16);
+    const int bytes = (lanes > 1 ? (lanes - 1) * ts * 6 * 16 : 16);
     static bool attr_set = false;
     if (!attr_set) {
         B200LP_CHECK_CUDA(cudaFuncSetAttribute(gconv3x3_wgrad_kernel<CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
         attr_set = true;
     }
     dim3 grid(chunks, slices);
-    gconv3x3_wgrad_kernel<CPG><<<grid, 256, bytes, st>>>(x, sc, sh, dy, ws, N, H, W, C, stride, Ho, Wo, ppc, ts);
+    gconv3x3_wgrad_kernel<CPG><<<grid, lanes * ts, bytes, st>>>(x, sc, sh, dy, ws, N, H, W, C, stride, Ho, Wo, ppc, ts);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

@@ -217,6 +217,9 @@ def _bn_backward(grads, st, dy, x_raw, mask_mode, mask_src=None, round_tf32=Fals
     return dx, dz
 
 
+TRACE = None     # tests: a list that receives (block record, incoming gradient, outgoing gradient) per block
+
+
 def backward(net, saved, d_emb, params):
     """d_emb (N, num_classes) -> list of parameter gradients aligned with `params` (None where a sink took it)."""
     grads = _Grads(params)
@@ -242,6 +245,7 @@ def backward(net, saved, d_emb, params):
         blk, s = rec["blk"], rec["stride"]
         h, w = rec["hw"]
         # final ReLU + bn3 (dz3 = masked gradient, also the identity branch's gradient)
+        d_block_out = d_out if TRACE is not None else None
         dr3, dz3 = _bn_backward(grads, rec["bn3"], d_out, rec["r3"], 1, mask_src=rec["out"], round_tf32=True, want_dz=True)
         del d_out
         d_a2 = K.conv_fwd(dr3, _packed(blk.conv3, True, K.TF32), 1)
@@ -273,6 +277,8 @@ def backward(net, saved, d_emb, params):
                 d_out = K.conv_fwd(dr1, wt1, 1, residual=d_sub, residual_mode=1)
         else:
             d_out = K.conv_fwd(dr1, wt1, 1, residual=dz3, residual_mode=1)
+        if TRACE is not None:
+            TRACE.append((rec, d_block_out, d_out))
 
     # stem: max-pool gather, bn1 + ReLU backward, weight gradient through the patch matrix
     d_act0 = K.maxpool3x3s2_bwd(d_out, saved["idx"], saved["stem_hw"])

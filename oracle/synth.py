@@ -191,3 +191,37 @@ def pose_encoder_state_dict(num_classes=32, seed=7):
 def pose_inputs(batch=3, image_size=64, seed=8):
     g = _gen(seed)
     return torch.rand((batch, 1, 3, image_size, image_size), generator=g)
+
+
+def identity_encoder_state_dict(num_classes=512, seed=9):
+    """Deterministic weights for the identity encoder (torchvision ResNeXt50-32x4d, the reference's
+    embedders/unsupervised_pose_separate_embResNeXt_segmentation.py:27): torchvision's key / shape layout, values from
+    a seeded generator (He-scaled convs, non-trivial BatchNorm affine parameters and running statistics)."""
+    import torchvision
+    g = _gen(seed)
+    layout = torchvision.models.resnext50_32x4d(num_classes=num_classes).state_dict()
+    sd = {}
+    for k, v in layout.items():
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros((), dtype=torch.int64)
+        elif k.endswith("running_mean"):
+            sd[k] = _randn(g, *v.shape, std=0.3)
+        elif k.endswith("running_var"):
+            sd[k] = torch.rand(v.shape, generator=g) * 1.5 + 0.5
+        elif v.dim() == 4:
+            fan_in = v.shape[1] * v.shape[2] * v.shape[3]
+            sd[k] = _randn(g, *v.shape, std=(2.0 / fan_in) ** 0.5)
+        elif v.dim() == 2:
+            sd[k] = _randn(g, *v.shape, std=(1.0 / v.shape[1]) ** 0.5)
+        elif k.startswith("fc.") and k.endswith("bias"):
+            sd[k] = _randn(g, *v.shape, std=0.1)
+        elif k.endswith("weight"):                          # BatchNorm gamma (block-final ones included: O(1))
+            sd[k] = torch.rand(v.shape, generator=g) * 0.5 + 0.5
+        else:
+            sd[k] = _randn(g, *v.shape, std=0.2)
+    return sd
+
+
+def identity_inputs(batch=2, frames=4, image_size=128, seed=10):
+    g = _gen(seed)
+    return torch.rand((batch, frames, 3, image_size, image_size), generator=g)

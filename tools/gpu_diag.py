@@ -728,8 +728,11 @@ def fused_optim():
         # and the checkpoint round trip fused -> plain optimizer -> fused keeps one step per update
         for grp in opt.param_groups:
             grp["lr"] = 1e-3
-        for grp in oref.param_groups:
-            grp["lr"] = 1e-3
+        if hasattr(oref, "param_groups"):
+            for grp in oref.param_groups:
+                grp["lr"] = 1e-3
+        else:
+            oref.lr = 1e-3
         sd = opt.state_dict()
         opt2 = cls(ps, lr=1e-3, betas=(0.0, 0.999) if kind == "RAdam" else (0.5, 0.999), eps=1e-5)
         opt2.load_state_dict(sd)
@@ -1066,8 +1069,12 @@ def encoder_bn():
                 out.append(_cmp(f"bn_act res+affine act{act} M{m} C{c}", y, r, 1e-5))
                 out.append(_cmp(f"bn_act split planes act{act} M{m} C{c}", ys[0].double() + ys[1].double(), r, 2e-5))
             y = K.bn_act(x, sc, sh, res=res, act=1, round_tf32=True)
+            # one tf32 ulp (2^-10 relative): the fp32 value may sit on the other side of a rounding boundary
             out.append(_cmp(f"bn_act res act1 tf32 M{m} C{c}", y, tf32_round(E.bn_act(x.double(), sc.double(), sh.double(),
-                                                                                   res=res.double(), act=1).float()), 1e-5))
+                                                                                   res=res.double(), act=1).float()), 1.1e-3))
+            lowbits = int((y.view(torch.int32) & 0x1FFF).abs().max())
+            out.append({"case": f"bn_act tf32 output has no low mantissa bits M{m} C{c}", "ok": lowbits == 0, "max_abs": lowbits,
+                        "rel": 0.0, "nan": False, "ref_max": 0.0})
             dy = torch.randn(m, c, device=dev)
             outp = E.bn_act(x.double(), sc.double(), sh.double(), res=res.double(), act=1)
             for mode in (0, 1, 2, 3):
@@ -1099,12 +1106,12 @@ def encoder_gconv():
     for (n, h, w, cpg, stride) in [(2, 16, 16, 4, 1), (3, 16, 8, 4, 2), (2, 8, 8, 8, 1), (2, 8, 8, 8, 2), (1, 10, 6, 8, 1),
                                    (2, 8, 8, 16, 1), (2, 8, 8, 16, 2), (2, 4, 4, 32, 1), (3, 4, 4, 32, 2), (1, 2, 2, 32, 1),
                                    (1, 2, 2, 32, 2), (8, 64, 64, 4, 1)]:
-        c = 32 * cpg
+        c = (16 if (n, h, w) == (1, 10, 6) else 32) * cpg        # one case with 16 groups
         x = torch.randn(n, h, w, c, device=dev)
         wt = torch.randn(c, cpg, 3, 3, device=dev) * 0.2
         sc = torch.rand(c, device=dev) + 0.5
         sh = torch.randn(c, device=dev) * 0.3
-        tag = f"N{n} H{h} W{w} cpg{cpg} s{stride}"
+        tag = f"N{n} H{h} W{w} C{c} cpg{cpg} s{stride}"
         y, part = K.gconv3x3_fwd(x, wt, sc, sh, stride=stride, want_stats=True)
         ry, rpart = E.gconv3x3_fwd(x.double(), wt.double(), sc.double(), sh.double(), stride=stride, want_stats=True)
         out.append(_cmp(f"gconv fwd {tag}", y, ry, 1e-5))
@@ -1244,9 +1251,14 @@ def identity_encoder():
             if r > worst:
                 worst, worst_name = r, nm
         rels.sort()
-        out.append({"case": f"identity parameter gradients {tag}", "ok": worst < 3e-2, "max_abs": worst, "rel": worst,
+        ga = torch.cat([p.grad.double().flatten() for p in a.parameters()])
+        gb = torch.cat([q.grad.flatten() for q in b.parameters()])
+        cos = float((ga * gb).sum() / (ga.norm() * gb.norm()))
+        # eval mode (fixed statistics) is well conditioned: TF32-level agreement; train mode: see the block-local check
+        ok = (worst < 3e-2) if mode == "eval" else (cos > 0.9 and rels[len(rels) // 2] < 0.2)
+        out.append({"case": f"identity parameter gradients {tag}", "ok": ok, "max_abs": worst, "rel": worst,
                     "nan": worst != worst, "ref_max": 1.0, "worst": worst_name, "median_rel": rels[len(rels) // 2],
-                    "p90_rel": rels[int(len(rels) * 0.9)]})
+                    "p90_rel": rels[int(len(rels) * 0.9)], "cosine_all_parameters": cos})
         if mode == "train":
             rm = torch.cat([m.running_mean for m in a.modules() if isinstance(m, torch.nn.BatchNorm2d)])
             rmb = torch.cat([m.running_mean for m in b.modules() if isinstance(m, torch.nn.BatchNorm2d)])
@@ -1265,6 +1277,44 @@ def identity_encoder():
         out.append({"case": f"identity gradient sinks == autograd path {tag}", "ok": worst < 1e-5, "max_abs": worst, "rel": worst,
                     "nan": worst != worst, "ref_max": 1.0})
         del a, b, a2
+    # Block-local backward parity at the meta-training plane sizes.  A deep train-mode BatchNorm net at random
+    # initialisation is chaotic in its gradients: rounding the forward GEMM operands to 16 mantissa bits alone moves
+    # the end-to-end gradients by ~9 % (median) in a float64 emulation (tests/test_identity_schedule_cpu.py), so the
+    # end-to-end numbers above only bound gross errors.  Here every bottleneck's hand-written backward is compared with
+    # torch autograd (float64) through the SAME block on the SAME block input and the SAME incoming gradient.
+    a = copy.deepcopy(net).to(dev).train()
+    b = copy.deepcopy(net).double().to(dev).train()
+    x = torch.rand(16, 3, 256, 256, device=dev)
+    wgt = torch.randn(16, 512, device=dev)
+    resnext_native.TRACE = []
+    ya = resnext_native.apply(a, x)
+    (ya * wgt).sum().backward()
+    trace, resnext_native.TRACE = resnext_native.TRACE, None
+    torch.cuda.synchronize()
+    blocks_a, blocks_b = resnext_native.blocks_of(a), resnext_native.blocks_of(b)
+    worst_p, worst_in, worst_name = 0.0, 0.0, ""
+    for rec, d_blk_out, d_blk_in in trace:
+        bi = blocks_a.index(rec["blk"])
+        blk_b = blocks_b[bi]
+        for p_ in blk_b.parameters():
+            p_.grad = None
+        xin = rec["a_f32"].permute(0, 3, 1, 2).double().requires_grad_(True)
+        yout = blk_b(xin)
+        yout.backward(d_blk_out.permute(0, 3, 1, 2).double())
+        e_in = float((d_blk_in.permute(0, 3, 1, 2).double() - xin.grad).abs().max() / (xin.grad.abs().max() + 1e-30))
+        worst_in = max(worst_in, e_in)
+        for (nm, pa), pb in zip(rec["blk"].named_parameters(), blk_b.parameters()):
+            e = float((pa.grad.double() - pb.grad).abs().max() / (pb.grad.abs().max() + 1e-30))
+            if e > worst_p:
+                worst_p, worst_name = e, f"block {bi} {nm}"
+    out.append({"case": "identity block-local backward (16 x 256x256, train): parameter gradients vs fp64 autograd on the same "
+                        "block input", "ok": worst_p < 1e-2, "max_abs": worst_p, "rel": worst_p, "nan": worst_p != worst_p,
+                "ref_max": 1.0, "worst": worst_name})
+    out.append({"case": "identity block-local backward: input gradients", "ok": worst_in < 1e-2, "max_abs": worst_in,
+                "rel": worst_in, "nan": worst_in != worst_in, "ref_max": 1.0})
+    del a, b, trace
+    torch.cuda.empty_cache()
+
     # timing at the meta-training shape
     a = copy.deepcopy(net).to(dev).train()
     x = torch.rand(64, 3, 256, 256, device=dev)
