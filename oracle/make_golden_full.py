@@ -30,10 +30,11 @@ from oracle.make_golden import StubEmbedder, fabricate_vgg_files, make_args, set
 
 def sub(t):
     """Strided sub-sample used for every stored activation / gradient tensor: <= ~16 K values."""
-    if t.dim() == 4:        # (N, C, H, W)
+    if t.dim() == 4:        # activations (N, C, H, W) and conv weights (O, I, k, k)
+        s0 = max(1, t.shape[0] // 16)
         cs = max(1, t.shape[1] // 16)
         ss = max(1, t.shape[2] // 16)
-        return t[:, ::cs, ::ss, ::ss].clone()
+        return t[::s0, ::cs, ::ss, ::ss].clone()
     if t.dim() == 2:
         return t[::max(1, t.shape[0] // 64), ::max(1, t.shape[1] // 64)].clone()
     return t.clone()

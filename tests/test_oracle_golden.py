@@ -144,3 +144,47 @@ def test_full_size_generator(golden_full):
     assert (rgb[:, :, ::4, ::4].double() - golden_full["g_eval.fake_rgbs.sub4.fp64"]).abs().max() < 5e-5
     assert (segm[:, :, ::4, ::4] - golden_full["g_eval.fake_segm.sub4"]).abs().max() < 5e-5
     assert float(golden_full["g_eval.fp32_vs_fp64_maxabs"]) < 1e-4
+
+
+def test_full_size_step_losses_and_gradients():
+    """The restatement at the REAL size (256x256, 64..512 channels, batch 2, train mode) against the full runner step of
+    the unmodified reference (tests/golden/full_step.pt, oracle/make_golden_full.py): every loss, every generator /
+    discriminator gradient norm, the sub-sampled gradient tensors."""
+    from conftest import GOLDEN
+    gold = torch.load(GOLDEN / "full_step.pt", map_location="cpu", weights_only=False)
+    cfg = gold["cfg"]
+    g_sd0, d_sd0 = synth.generator_state_dict(cfg, seed=21), synth.discriminator_state_dict(cfg, seed=22)
+    g_sd = {k: (v.clone().requires_grad_(True) if "weight_orig" in k or k.endswith("bias") or k == "constant.constant"
+                else v.clone()) for k, v in g_sd0.items()}
+    d_sd = {k: (v.clone().requires_grad_(True) if "weight_orig" in k or k.endswith("bias") else v.clone())
+            for k, v in d_sd0.items()}
+    data, target, emb = synth.make_inputs(cfg, batch=2, seed=24)
+    out, lg, ld = R.forward_losses(g_sd, d_sd, synth.vgg_state_dict("vgg19", seed=3), synth.vgg_state_dict("vgg16", seed=5),
+                                   cfg, emb["embeds"], emb["pose_embedding"], data["target_rgbs"][:, 0],
+                                   target["real_segm"][:, 0], target["label"], training=True,
+                                   embeds_elemwise=emb["embeds_elemwise"],
+                                   criteria=("idt_embed", "perceptual", "adversarial", "featmat", "dis_embed", "dice"))
+    for k, v in {**lg, **ld}.items():
+        torch.testing.assert_close(v.detach(), gold["step.loss." + k], rtol=3e-4, atol=1e-6)
+
+    def sub(t):
+        if t.dim() == 4:
+            return t[::max(1, t.shape[0] // 16), ::max(1, t.shape[1] // 16), ::max(1, t.shape[2] // 16), ::max(1, t.shape[2] // 16)]
+        if t.dim() == 2:
+            return t[::max(1, t.shape[0] // 64), ::max(1, t.shape[1] // 64)]
+        return t
+    g_params = {k: v for k, v in g_sd.items() if v.requires_grad}
+    grads = torch.autograd.grad(sum(lg.values()), list(g_params.values()), retain_graph=True, allow_unused=True)
+    g_max = max(gold["step.gradG.norms"].values())
+    for (k, _), g in zip(g_params.items(), grads):
+        ref_norm = gold["step.gradG.norms"][k]
+        assert abs(float(g.norm()) - ref_norm) <= 3e-3 * ref_norm + 1e-5 * g_max, k
+        ref = gold["step.gradG.sub." + k]
+        assert float((sub(g) - ref).abs().max()) <= 3e-3 * float(ref.abs().max()) + 1e-5 * g_max, k
+    d_params = {k: v for k, v in d_sd.items() if v.requires_grad}
+    grads = torch.autograd.grad(sum(ld.values()), list(d_params.values()), allow_unused=True)
+    d_max = max(gold["step.gradD.norms"].values())
+    for (k, _), g in zip(d_params.items(), grads):
+        ref_norm = gold["step.gradD.norms"][k]
+        gn = 0.0 if g is None else float(g.norm())
+        assert abs(gn - ref_norm) <= 3e-3 * ref_norm + 1e-5 * d_max, k
