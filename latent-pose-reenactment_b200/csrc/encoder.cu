@@ -128,8 +128,8 @@ bn_act_kernel(const float4* __restrict__ x, const float* __restrict__ scale, con
               const float4* __restrict__ res, const float* __restrict__ res_scale, const float* __restrict__ res_shift,
               float4* __restrict__ y, __nv_bfloat16* __restrict__ ys, long long split_stride, long total4, int C4, int act,
               int round_out) {
-    for (long i = blockIdx.x * 256L + threadIdx.x; i < total4; i += gridDim.x * 256L) {
-        const int c = static_cast<int>(i % C4) * 4;
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < static_cast<unsigned>(total4); i += gridDim.x * 256u) {   // 32-bit index math
+        const int c = static_cast<int>(i % static_cast<unsigned>(C4)) * 4;
         float4 v = __ldg(x + i);
         if (scale) {
             const float4 sc = ldg4(scale + c), sh = ldg4(shift + c);
@@ -236,8 +236,8 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ mask
                     const float* __restrict__ shift, const float* __restrict__ gamma, const float* __restrict__ coef,
                     float* __restrict__ dx, float* __restrict__ dz_out, long total4, int C, int mask_mode, int round_out) {
     const int C4 = C >> 2;
-    for (long i = blockIdx.x * 256L + threadIdx.x; i < total4; i += gridDim.x * 256L) {
-        const int c = static_cast<int>(i % C4) * 4;
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < static_cast<unsigned>(total4); i += gridDim.x * 256u) {   // 32-bit index math
+        const int c = static_cast<int>(i % static_cast<unsigned>(C4)) * 4;
         const size_t off = static_cast<size_t>(i) * 4;
         const float4 g = ldg4(dy + off), xr = ldg4(x_raw + off);
         float4 m = xr;
@@ -268,143 +268,137 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ mask
 // per (tap, co, 4 input channels) serves 4*PPT FMAs.  TRANSPOSED: the same kernel computes the stride-1 data gradient
 // (w^T with flipped taps, gathered while staging the weights).
 template <int CPG> struct GconvCfg;
-template <> struct GconvCfg<4>  { static constexpr int PPT = 4, CI4C = 1; };
-template <> struct GconvCfg<8>  { static constexpr int PPT = 4, CI4C = 2; };
-template <> struct GconvCfg<16> { static constexpr int PPT = 2, CI4C = 2; };
-template <> struct GconvCfg<32> { static constexpr int PPT = 2, CI4C = 1; };
+// PPT = output pixels per lane; GL = groups per block (their weights for ALL input channels stay in shared memory for the
+// whole kernel: 4.6 / 18 / 74 / 147 KB); CI4C = chunk of input-channel quads of the stride-2 data-gradient kernel
+template <> struct GconvCfg<4>  { static constexpr int PPT = 4, GL = 8, CI4C = 1; };
+template <> struct GconvCfg<8>  { static constexpr int PPT = 4, GL = 8, CI4C = 2; };
+template <> struct GconvCfg<16> { static constexpr int PPT = 2, GL = 8, CI4C = 2; };
+template <> struct GconvCfg<32> { static constexpr int PPT = 2, GL = 4, CI4C = 1; };
 
 template <int CPG, int STRIDE, bool TRANSPOSED>
 __global__ void __launch_bounds__(256)
 gconv3x3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, const float* __restrict__ in_shift,
                     const float* __restrict__ w, float* __restrict__ y, float* __restrict__ part, int N, int H, int W,
                     int C, int Ho, int Wo) {
-    constexpr int PPT = GconvCfg<CPG>::PPT, CI4C = GconvCfg<CPG>::CI4C;
+    constexpr int PPT = GconvCfg<CPG>::PPT, GL = GconvCfg<CPG>::GL, PL = 32 / GL, CI4 = CPG / 4;
     constexpr int NCOL = (PPT - 1) * STRIDE + 3;
-    extern __shared__ float4 sw[];                    // [tap 9][ci4l CI4C][co CPG][gl 8]  (+ stats scratch behind)
+    constexpr int SPT = 8 * PL;                       // pixel strips per tile (8 warps x PL lanes)
+    extern __shared__ float4 sw[];                    // [tap 9][ci4 CI4][co CPG][gl GL]  (+ stats scratch reuses it)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gl = lane & 7, pl = lane >> 3;
-    const int g = blockIdx.y * 8 + gl;                // absolute group
+    const int gl = lane % GL, pl = lane / GL;
+    const int g = blockIdx.y * GL + gl;               // absolute group
     const int cbase = g * CPG;
-    const int strips_w = (Wo + PPT - 1) / PPT;
-    const long total_strips = static_cast<long>(N) * Ho * strips_w;
+    // the weights of this block's GL groups, staged once: sw[((tap*CI4 + ci4)*CPG + co)*GL + gl] = 4 input channels
+    for (int i = threadIdx.x; i < 9 * CI4 * CPG * GL; i += 256) {
+        const int sgl = i % GL;
+        const int co = (i / GL) % CPG;
+        const int ci4 = (i / (GL * CPG)) % CI4;
+        const int tap = i / (GL * CPG * CI4);
+        const int sg = blockIdx.y * GL + sgl;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // forward: w[sg*CPG + co][ci4*4 + j][tap];  transposed: output channel `co` is an INPUT channel of the forward
+            // conv, the reduction runs over its output channels, taps flipped: w[sg*CPG + ci4*4 + j][co][8 - tap]
+            const size_t idx = TRANSPOSED ? (static_cast<size_t>(sg * CPG + ci4 * 4 + j) * CPG + co) * 9 + (8 - tap)
+                                          : (static_cast<size_t>(sg * CPG + co) * CPG + ci4 * 4 + j) * 9 + tap;
+            v[j] = __ldg(w + idx);
+        }
+        sw[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
+    const unsigned strips_w = (Wo + PPT - 1) / PPT;
+    const unsigned total_strips = static_cast<unsigned>(N) * Ho * strips_w;     // < 2^31 (host check)
     float st1[CPG], st2[CPG];
 #pragma unroll
     for (int j = 0; j < CPG; ++j) { st1[j] = 0.f; st2[j] = 0.f; }
 
-    for (long tile = blockIdx.x; tile * 32 < total_strips; tile += gridDim.x) {
-        const long strip = tile * 32 + warp * 4 + pl;
-        const bool svalid = strip < total_strips;
-        const long sclamped = svalid ? strip : 0;
-        const int sw_i = static_cast<int>(sclamped % strips_w);
-        const int ho = static_cast<int>((sclamped / strips_w) % Ho);
-        const int n = static_cast<int>(sclamped / (static_cast<long>(strips_w) * Ho));
-        const int wo0 = sw_i * PPT;
+    for (unsigned tile = blockIdx.x; tile * SPT < total_strips; tile += gridDim.x) {
+        const unsigned strip = tile * SPT + warp * PL + pl;
+        if (strip >= total_strips) continue;
+        const unsigned sw_i = strip % strips_w;
+        const unsigned t2 = strip / strips_w;
+        const int ho = static_cast<int>(t2 % Ho);
+        const int n = static_cast<int>(t2 / Ho);
+        const int wo0 = static_cast<int>(sw_i) * PPT;
         float acc[PPT][CPG];
 #pragma unroll
         for (int u = 0; u < PPT; ++u)
 #pragma unroll
             for (int j = 0; j < CPG; ++j) acc[u][j] = 0.f;
-
-        for (int cc = 0; cc < CPG / 4; cc += CI4C) {   // chunks of input channels (4 * CI4C each)
-            __syncthreads();
-            // stage the weights of this block's 8 groups for the chunk: sw[((tap*CI4C + ci4l)*CPG + co)*8 + gl] = 4 ci values
-            for (int i = threadIdx.x; i < 9 * CI4C * CPG * 8; i += 256) {
-                const int sgl = i & 7;
-                const int co = (i >> 3) % CPG;
-                const int ci4l = ((i >> 3) / CPG) % CI4C;
-                const int tap = (i >> 3) / (CPG * CI4C);
-                const int sg = blockIdx.y * 8 + sgl;
-                const int ci0 = (cc + ci4l) * 4;
-                float v[4];
+#pragma unroll 1
+        for (int ci4 = 0; ci4 < CI4; ++ci4) {
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in_scale) { sc = ldg4(in_scale + cbase + ci4 * 4); sh = ldg4(in_shift + cbase + ci4 * 4); }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    // forward: w[sg*CPG + co][ci0 + j][tap];  transposed: output channel `co` is an INPUT channel of the
-                    // forward conv, the reduction runs over its output channels, taps flipped: w[sg*CPG + ci0 + j][co][8 - tap]
-                    const size_t idx = TRANSPOSED ? (static_cast<size_t>(sg * CPG + ci0 + j) * CPG + co) * 9 + (8 - tap)
-                                                  : (static_cast<size_t>(sg * CPG + co) * CPG + ci0 + j) * 9 + tap;
-                    v[j] = __ldg(w + idx);
+            for (int kh = 0; kh < 3; ++kh) {
+                const int hi = ho * STRIDE + kh - 1;
+                const bool hok = hi >= 0 && hi < H;
+                const float* rowp = x + (static_cast<size_t>(n * H + (hok ? hi : 0)) * W) * C + cbase + ci4 * 4;
+                float4 xin[NCOL];
+#pragma unroll
+                for (int col = 0; col < NCOL; ++col) {
+                    const int wi = wo0 * STRIDE + col - 1;
+                    const bool ok = hok && wi >= 0 && wi < W;
+                    float4 v = ldg4(rowp + static_cast<size_t>(ok ? wi : 0) * C);
+                    if (in_scale) {
+                        v.x = fmaxf(v.x * sc.x + sh.x, 0.f); v.y = fmaxf(v.y * sc.y + sh.y, 0.f);
+                        v.z = fmaxf(v.z * sc.z + sh.z, 0.f); v.w = fmaxf(v.w * sc.w + sh.w, 0.f);
+                    }
+                    xin[col] = ok ? v : make_float4(0.f, 0.f, 0.f, 0.f);    // zero padding AFTER the activation
                 }
-                sw[i] = make_float4(v[0], v[1], v[2], v[3]);
-            }
-            __syncthreads();
-            if (svalid) {
 #pragma unroll
-                for (int ci4l = 0; ci4l < CI4C; ++ci4l) {
-                    const int ci0 = (cc + ci4l) * 4;
-                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (in_scale) { sc = ldg4(in_scale + cbase + ci0); sh = ldg4(in_shift + cbase + ci0); }
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float4* wrow = sw + ((kh * 3 + kw) * CI4 + ci4) * CPG * GL + gl;
 #pragma unroll
-                    for (int kh = 0; kh < 3; ++kh) {
-                        const int hi = ho * STRIDE + kh - 1;
-                        const bool hok = hi >= 0 && hi < H;
-                        float4 xin[NCOL];
+                    for (int co = 0; co < CPG; ++co) {
+                        const float4 wv = wrow[co * GL];
 #pragma unroll
-                        for (int col = 0; col < NCOL; ++col) {
-                            const int wi = wo0 * STRIDE + col - 1;
-                            const bool ok = hok && wi >= 0 && wi < W;
-                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (ok) {
-                                v = ldg4(x + (static_cast<size_t>(n * H + hi) * W + wi) * C + cbase + ci0);
-                                if (in_scale) {
-                                    v.x = fmaxf(v.x * sc.x + sh.x, 0.f); v.y = fmaxf(v.y * sc.y + sh.y, 0.f);
-                                    v.z = fmaxf(v.z * sc.z + sh.z, 0.f); v.w = fmaxf(v.w * sc.w + sh.w, 0.f);
-                                }
-                            }
-                            xin[col] = v;
-                        }
-#pragma unroll
-                        for (int kw = 0; kw < 3; ++kw) {
-                            const float4* wrow = sw + ((kh * 3 + kw) * CI4C + ci4l) * CPG * 8 + gl;
-#pragma unroll
-                            for (int co = 0; co < CPG; ++co) {
-                                const float4 wv = wrow[co * 8];
-#pragma unroll
-                                for (int u = 0; u < PPT; ++u) {
-                                    const float4 xv = xin[u * STRIDE + kw];
-                                    acc[u][co] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[u][co]))));
-                                }
-                            }
+                        for (int u = 0; u < PPT; ++u) {
+                            const float4 xv = xin[u * STRIDE + kw];
+                            acc[u][co] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[u][co]))));
                         }
                     }
                 }
             }
         }
-        if (svalid) {
 #pragma unroll
-            for (int u = 0; u < PPT; ++u) {
-                const int wo = wo0 + u;
-                if (wo < Wo) {
-                    float* o = y + (static_cast<size_t>(n * Ho + ho) * Wo + wo) * C + cbase;
+        for (int u = 0; u < PPT; ++u) {
+            const int wo = wo0 + u;
+            if (wo < Wo) {
+                float* o = y + (static_cast<size_t>(n * Ho + ho) * Wo + wo) * C + cbase;
 #pragma unroll
-                    for (int j = 0; j < CPG; j += 4)
-                        *reinterpret_cast<float4*>(o + j) = make_float4(acc[u][j], acc[u][j + 1], acc[u][j + 2], acc[u][j + 3]);
+                for (int j = 0; j < CPG; j += 4)
+                    *reinterpret_cast<float4*>(o + j) = make_float4(acc[u][j], acc[u][j + 1], acc[u][j + 2], acc[u][j + 3]);
 #pragma unroll
-                    for (int j = 0; j < CPG; ++j) { st1[j] += acc[u][j]; st2[j] += acc[u][j] * acc[u][j]; }
-                }
+                for (int j = 0; j < CPG; ++j) { st1[j] += acc[u][j]; st2[j] += acc[u][j] * acc[u][j]; }
             }
         }
     }
     if (part) {
-        // per-channel sums of this block: lanes pl = 0..3 of a warp (shuffle), then the 8 warps (shared memory, fixed order)
+        // per-channel sums of this block: the PL pixel lanes of a warp (shuffle), then the 8 warps (shared memory, fixed order)
         __syncthreads();
-        float* red = reinterpret_cast<float*>(sw);           // [2][8 warps][8 gl][CPG]
+        float* red = reinterpret_cast<float*>(sw);           // [2][8 warps][GL][CPG]
 #pragma unroll
         for (int j = 0; j < CPG; ++j) {
             float a = st1[j], b = st2[j];
-            a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
-            a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
+#pragma unroll
+            for (int m = GL; m < 32; m <<= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, m);
+                b += __shfl_xor_sync(0xffffffffu, b, m);
+            }
             if (pl == 0) {
-                red[((0 * 8 + warp) * 8 + gl) * CPG + j] = a;
-                red[((1 * 8 + warp) * 8 + gl) * CPG + j] = b;
+                red[((0 * 8 + warp) * GL + gl) * CPG + j] = a;
+                red[((1 * 8 + warp) * GL + gl) * CPG + j] = b;
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < 2 * 8 * CPG; i += 256) {
-            const int wh = i / (8 * CPG), r = i % (8 * CPG);          // r = gl*CPG + j: channel within the group octet
-            float s = 0.f;
+        for (int i = threadIdx.x; i < 2 * GL * CPG; i += 256) {
+            const int wh = i / (GL * CPG), r = i % (GL * CPG);        // r = gl*CPG + j: channel within the block's groups
+            float s_ = 0.f;
 #pragma unroll
-            for (int wq = 0; wq < 8; ++wq) s += red[((wh * 8 + wq) * 8) * CPG + r];
-            part[(static_cast<size_t>(blockIdx.x) * 2 + wh) * C + blockIdx.y * 8 * CPG + r] = s;
+            for (int wq = 0; wq < 8; ++wq) s_ += red[((wh * 8 + wq) * GL) * CPG + r];
+            part[(static_cast<size_t>(blockIdx.x) * 2 + wh) * C + blockIdx.y * GL * CPG + r] = s_;
         }
     }
 }
@@ -423,7 +417,7 @@ gconv3x3_dgrad_s2_kernel(const float* __restrict__ dy, const float* __restrict__
     const int gl = lane & 7, pl = lane >> 3;
     const int g = blockIdx.y * 8 + gl;
     const int cbase = g * CPG;
-    const long total = static_cast<long>(N) * H * W;
+    const unsigned total = static_cast<unsigned>(N) * H * W;          // < 2^31 (host check)
     for (int cc = 0; cc < CPG / 4; cc += CO4C) {
         __syncthreads();
         for (int i = threadIdx.x; i < 9 * CO4C * CPG * 8; i += 256) {
@@ -439,10 +433,11 @@ gconv3x3_dgrad_s2_kernel(const float* __restrict__ dy, const float* __restrict__
             sw[i] = make_float4(v[0], v[1], v[2], v[3]);
         }
         __syncthreads();
-        for (long p = static_cast<long>(blockIdx.x) * 32 + warp * 4 + pl; p < total; p += static_cast<long>(gridDim.x) * 32) {
-            const int wi = static_cast<int>(p % W);
-            const int hi = static_cast<int>((p / W) % H);
-            const int n = static_cast<int>(p / (static_cast<long>(W) * H));
+        for (unsigned p = blockIdx.x * 32u + warp * 4 + pl; p < total; p += gridDim.x * 32u) {
+            const int wi = static_cast<int>(p % static_cast<unsigned>(W));
+            const unsigned t2 = p / static_cast<unsigned>(W);
+            const int hi = static_cast<int>(t2 % static_cast<unsigned>(H));
+            const int n = static_cast<int>(t2 / static_cast<unsigned>(H));
             float* o = dx + static_cast<size_t>(p) * C + cbase;
             float acc[CPG];
             if (cc == 0) {
@@ -509,22 +504,23 @@ gconv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ in_
     for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int k = 0; k < 3; ++k) acc[c][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const long P = static_cast<long>(N) * Ho * Wo;
-    const long p0 = static_cast<long>(blockIdx.x) * pix_per_chunk;
-    const long p1 = min(p0 + static_cast<long>(pix_per_chunk), P);
+    const unsigned P = static_cast<unsigned>(N) * Ho * Wo;             // < 2^31 (host check): 32-bit index math —
+    const unsigned p0 = blockIdx.x * static_cast<unsigned>(pix_per_chunk);   // 64-bit divisions cost ~100 instructions each
+    const unsigned p1 = min(p0 + static_cast<unsigned>(pix_per_chunk), P);
     const bool act = in_scale != nullptr;
-    for (long pb = p0 + ln; pb < p1; pb += 2L * lanes) {
+    for (unsigned pb = p0 + ln; pb < p1; pb += 2u * lanes) {
         float2 d[2];
         float4 v[2][3];
         bool ok[2][3];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            const long p = pb + static_cast<long>(u) * lanes;
+            const unsigned p = pb + static_cast<unsigned>(u) * lanes;
             const bool pv = p < p1;
-            const long pp = pv ? p : p0;
-            const int wo = static_cast<int>(pp % Wo);
-            const int ho = static_cast<int>((pp / Wo) % Ho);
-            const int n = static_cast<int>(pp / (static_cast<long>(Wo) * Ho));
+            const unsigned pp = pv ? p : p0;
+            const int wo = static_cast<int>(pp % static_cast<unsigned>(Wo));
+            const unsigned t2 = pp / static_cast<unsigned>(Wo);
+            const int ho = static_cast<int>(t2 % static_cast<unsigned>(Ho));
+            const int n = static_cast<int>(t2 / static_cast<unsigned>(Ho));
             const int hi = ho * stride + kh - 1;
             const bool hok = pv && hi >= 0 && hi < H;
             d[u] = __ldg(reinterpret_cast<const float2*>(dy + static_cast<size_t>(pp) * C + cout));
@@ -584,17 +580,36 @@ gconv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ in_
     }
 }
 
-// dW[co][ci][tap] (+)= sum over chunks of ws[chunk][tap][co][ci]
+// dW[co][ci][tap] (+)= sum over chunks of ws[chunk][tap][co][ci], in two stages with a fixed order: stage 1 — block
+// (x, j) sums chunks j, j + CG, ... of 256 consecutive (tap, co, ci) elements (coalesced) into ws2[j][...]; stage 2 — sums
+// the <= 32 stage-1 rows and transposes to [co][ci][tap].  (One thread per output walking ALL chunks serialised 2368
+// dependent L2 round trips: 0.42 ms per layer.)
 __global__ void __launch_bounds__(256)
-gconv3x3_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int chunks, int C, int cpg,
-                             int accumulate) {
-    const long total = static_cast<long>(C) * cpg * 9;
-    for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += gridDim.x * 256L) {
-        const int tap = static_cast<int>(i % 9);
-        const long cc = i / 9;                                    // co*cpg + ci
-        const float* src = ws + static_cast<size_t>(tap) * C * cpg + cc;
+gconv3x3_wgrad_reduce1_kernel(const float* __restrict__ ws, float* __restrict__ ws2, int chunks, int CG, unsigned total) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= total) return;
+    const float* src = ws + i;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = blockIdx.y;
+    for (; k + 3 * CG < chunks; k += 4 * CG) {
+        s0 += __ldg(src + static_cast<size_t>(k) * total);
+        s1 += __ldg(src + static_cast<size_t>(k + CG) * total);
+        s2 += __ldg(src + static_cast<size_t>(k + 2 * CG) * total);
+        s3 += __ldg(src + static_cast<size_t>(k + 3 * CG) * total);
+    }
+    for (; k < chunks; k += CG) s0 += __ldg(src + static_cast<size_t>(k) * total);
+    ws2[static_cast<size_t>(blockIdx.y) * total + i] = (s0 + s1) + (s2 + s3);
+}
+
+__global__ void __launch_bounds__(256)
+gconv3x3_wgrad_reduce2_kernel(const float* __restrict__ ws2, float* __restrict__ dw, int CG, int C, int cpg, int accumulate) {
+    const unsigned total = static_cast<unsigned>(C) * cpg * 9;
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+        const unsigned tap = i % 9u;
+        const unsigned cc = i / 9u;                               // co*cpg + ci
+        const float* src = ws2 + static_cast<size_t>(tap) * C * cpg + cc;
         float s = 0.f;
-        for (int k = 0; k < chunks; ++k) s += __ldg(src + static_cast<size_t>(k) * 9 * C * cpg);
+        for (int k = 0; k < CG; ++k) s += __ldg(src + static_cast<size_t>(k) * total);
         dw[i] = (accumulate ? dw[i] : 0.f) + s;
     }
 }
@@ -608,12 +623,12 @@ im2col7x7_s2_kernel(const float* __restrict__ x, float* __restrict__ col, __nv_b
                     long long split_stride, int N, int H, int W, int Ho, int Wo, int KP) {
     const int K4 = KP >> 2;
     const long total4 = static_cast<long>(N) * Ho * Wo * K4;
-    for (long i = blockIdx.x * 256L + threadIdx.x; i < total4; i += gridDim.x * 256L) {
-        const int k0 = static_cast<int>(i % K4) * 4;
-        const long p = i / K4;
-        const int wo = static_cast<int>(p % Wo);
-        const int ho = static_cast<int>((p / Wo) % Ho);
-        const long n = p / (static_cast<long>(Wo) * Ho);
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < static_cast<unsigned>(total4); i += gridDim.x * 256u) {   // 32-bit index math
+        const int k0 = static_cast<int>(i % static_cast<unsigned>(K4)) * 4;
+        const unsigned p = i / static_cast<unsigned>(K4);
+        const int wo = static_cast<int>(p % static_cast<unsigned>(Wo));
+        const int ho = static_cast<int>((p / static_cast<unsigned>(Wo)) % static_cast<unsigned>(Ho));
+        const long n = p / (static_cast<unsigned>(Wo) * static_cast<unsigned>(Ho));
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -641,12 +656,12 @@ maxpool3x3s2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ s
                         unsigned char* __restrict__ idx, int N, int H, int W, int C, int Ho, int Wo, int round_out) {
     const int C4 = C >> 2;
     const long total4 = static_cast<long>(N) * Ho * Wo * C4;
-    for (long i = blockIdx.x * 256L + threadIdx.x; i < total4; i += gridDim.x * 256L) {
-        const int c = static_cast<int>(i % C4) * 4;
-        const long p = i / C4;
-        const int wo = static_cast<int>(p % Wo);
-        const int ho = static_cast<int>((p / Wo) % Ho);
-        const long n = p / (static_cast<long>(Wo) * Ho);
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < static_cast<unsigned>(total4); i += gridDim.x * 256u) {   // 32-bit index math
+        const int c = static_cast<int>(i % static_cast<unsigned>(C4)) * 4;
+        const unsigned p = i / static_cast<unsigned>(C4);
+        const int wo = static_cast<int>(p % static_cast<unsigned>(Wo));
+        const int ho = static_cast<int>((p / static_cast<unsigned>(Wo)) % static_cast<unsigned>(Ho));
+        const long n = p / (static_cast<unsigned>(Wo) * static_cast<unsigned>(Ho));
         const float4 sc = ldg4(scale + c), sh = ldg4(shift + c);
         float best[4] = {-1.f, -1.f, -1.f, -1.f};          // activations are >= 0: any in-image tap beats -1
         int bi[4] = {0, 0, 0, 0};
@@ -679,12 +694,12 @@ maxpool3x3s2_bwd_kernel(const float* __restrict__ dy, const unsigned char* __res
                         int H, int W, int C, int Ho, int Wo) {
     const int C4 = C >> 2;
     const long total4 = static_cast<long>(N) * H * W * C4;
-    for (long i = blockIdx.x * 256L + threadIdx.x; i < total4; i += gridDim.x * 256L) {
-        const int c = static_cast<int>(i % C4) * 4;
-        const long p = i / C4;
-        const int wi = static_cast<int>(p % W);
-        const int hi = static_cast<int>((p / W) % H);
-        const long n = p / (static_cast<long>(W) * H);
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < static_cast<unsigned>(total4); i += gridDim.x * 256u) {   // 32-bit index math
+        const int c = static_cast<int>(i % static_cast<unsigned>(C4)) * 4;
+        const unsigned p = i / static_cast<unsigned>(C4);
+        const int wi = static_cast<int>(p % static_cast<unsigned>(W));
+        const int hi = static_cast<int>((p / static_cast<unsigned>(W)) % static_cast<unsigned>(H));
+        const long n = p / (static_cast<unsigned>(W) * static_cast<unsigned>(H));
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
@@ -716,12 +731,12 @@ subsample2_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__
                   int C) {
     const int C4 = C >> 2;
     const long total4 = static_cast<long>(N) * Ho * Wo * C4;
-    for (long i = blockIdx.x * 256L + threadIdx.x; i < total4; i += gridDim.x * 256L) {
-        const int c = static_cast<int>(i % C4) * 4;
-        const long p = i / C4;
-        const int wo = static_cast<int>(p % Wo);
-        const int ho = static_cast<int>((p / Wo) % Ho);
-        const long n = p / (static_cast<long>(Wo) * Ho);
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < static_cast<unsigned>(total4); i += gridDim.x * 256u) {   // 32-bit index math
+        const int c = static_cast<int>(i % static_cast<unsigned>(C4)) * 4;
+        const unsigned p = i / static_cast<unsigned>(C4);
+        const int wo = static_cast<int>(p % static_cast<unsigned>(Wo));
+        const int ho = static_cast<int>((p / static_cast<unsigned>(Wo)) % static_cast<unsigned>(Ho));
+        const long n = p / (static_cast<unsigned>(Wo) * static_cast<unsigned>(Ho));
         const size_t src = ((n * 2 * Ho + 2 * ho) * (2 * Wo) + 2 * wo) * C + c;
         if (y) *reinterpret_cast<float4*>(y + static_cast<size_t>(i) * 4) = ldg4(x + src);
         if (ys) {
@@ -737,12 +752,12 @@ __global__ void __launch_bounds__(256)
 scatter_add2_kernel(const float* __restrict__ dsub, float* __restrict__ dx, int N, int Ho, int Wo, int C) {
     const int C4 = C >> 2;
     const long total4 = static_cast<long>(N) * Ho * Wo * C4;
-    for (long i = blockIdx.x * 256L + threadIdx.x; i < total4; i += gridDim.x * 256L) {
-        const int c = static_cast<int>(i % C4) * 4;
-        const long p = i / C4;
-        const int wo = static_cast<int>(p % Wo);
-        const int ho = static_cast<int>((p / Wo) % Ho);
-        const long n = p / (static_cast<long>(Wo) * Ho);
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < static_cast<unsigned>(total4); i += gridDim.x * 256u) {   // 32-bit index math
+        const int c = static_cast<int>(i % static_cast<unsigned>(C4)) * 4;
+        const unsigned p = i / static_cast<unsigned>(C4);
+        const int wo = static_cast<int>(p % static_cast<unsigned>(Wo));
+        const int ho = static_cast<int>((p / static_cast<unsigned>(Wo)) % static_cast<unsigned>(Ho));
+        const long n = p / (static_cast<unsigned>(Wo) * static_cast<unsigned>(Ho));
         float4* d = reinterpret_cast<float4*>(dx + ((n * 2 * Ho + 2 * ho) * (2 * Wo) + 2 * wo) * C + c);
         const float4 g = ldg4(dsub + static_cast<size_t>(i) * 4);
         float4 v = *d;
@@ -780,9 +795,9 @@ avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int HW, i
 __global__ void __launch_bounds__(256)
 avgpool_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, long total4, int HW, int C4) {
     const float inv = 1.f / static_cast<float>(HW);
-    for (long i = blockIdx.x * 256L + threadIdx.x; i < total4; i += gridDim.x * 256L) {
-        const int c4 = static_cast<int>(i % C4);
-        const long n = i / (static_cast<long>(C4) * HW);
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < static_cast<unsigned>(total4); i += gridDim.x * 256u) {   // 32-bit index math
+        const int c4 = static_cast<int>(i % static_cast<unsigned>(C4));
+        const long n = i / (static_cast<unsigned>(C4) * static_cast<unsigned>(HW));
         const float4 g = ldg4(dy + (n * C4 + c4) * 4);
         *reinterpret_cast<float4*>(dx + static_cast<size_t>(i) * 4) = make_float4(g.x * inv, g.y * inv, g.z * inv, g.w * inv);
     }
@@ -843,7 +858,7 @@ sgemm_strided_kernel(const float* __restrict__ A, long sai, long sak, const floa
     }
 }
 
-static int ew_blocks(long total4) {
+static int ew_blocks(long total4) {      // callers keep total4 < 2^31 (the kernels index with 32-bit integers)
     long blocks = (total4 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
@@ -868,8 +883,9 @@ static int gconv_wgrad_plan(long P, int C, int cpg, int* pix_per_chunk, int* TS,
 template <int CPG, int STRIDE, bool TR>
 static int launch_gconv(const float* x, const float* sc, const float* sh, const float* w, float* y, float* part, int N,
                         int H, int W, int C, int Ho, int Wo, int blocks_x, cudaStream_t st) {
-    constexpr int kSmem = 9 * GconvCfg<CPG>::CI4C * CPG * 8 * 16;
-    constexpr int kRed = 2 * 8 * 8 * CPG * 4;
+    constexpr int GL = GconvCfg<CPG>::GL;
+    constexpr int kSmem = 9 * (CPG / 4) * CPG * GL * 16;
+    constexpr int kRed = 2 * 8 * GL * CPG * 4;
     constexpr int kBytes = kSmem > kRed ? kSmem : kRed;
     static bool attr_set = false;
     if (!attr_set) {
@@ -877,18 +893,24 @@ static int launch_gconv(const float* x, const float* sc, const float* sh, const 
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
         attr_set = true;
     }
-    dim3 grid(blocks_x, C / (8 * CPG));
+    dim3 grid(blocks_x, C / (GL * CPG));
     gconv3x3_fwd_kernel<CPG, STRIDE, TR><<<grid, 256, kBytes, st>>>(x, sc, sh, w, y, part, N, H, W, C, Ho, Wo);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;
 }
 
+// persistent blocks: each stages its groups' weights once, then walks pixel tiles; about 4 / 4 / 2 / 1 resident blocks
+// per SM (the weight tile is 4.6 / 18 / 74 / 147 KB of shared memory)
 static int gconv_blocks_x(int N, int Ho, int Wo, int cpg, int C) {
     const int ppt = (cpg <= 8) ? 4 : 2;
+    const int gl = cpg == 32 ? 4 : 8;
+    const int spt = 8 * (32 / gl);
     const long strips = static_cast<long>(N) * Ho * ((Wo + ppt - 1) / ppt);
-    long tiles = (strips + 31) / 32;
-    const long cap = (148L * 8) / (C / (8 * cpg));     // ~8 resident blocks per SM over all group octets
+    long tiles = (strips + spt - 1) / spt;
+    const int per_sm = cpg <= 8 ? 4 : (cpg == 16 ? 2 : 1);
+    long cap = (148L * per_sm) / (C / (gl * cpg));
+    if (cap < 1) cap = 1;
     if (tiles > cap) tiles = cap;
     return static_cast<int>(tiles < 1 ? 1 : tiles);
 }
@@ -1023,6 +1045,7 @@ extern "C" int32_t b200lp_gconv3x3_dgrad(const float* dy, const float* w, float*
     // (N, H, W) = shape of dx (the forward INPUT); dy is (N, Ho, Wo, C)
     if (stride == 1) return b200lp_gconv3x3_fwd(dy, nullptr, nullptr, w, dx, nullptr, N, H, W, C, cpg, 1, 1, stream);
     B200LP_REQUIRE(dy && w && dx && N > 0 && H > 0 && W > 0 && stride == 2, "gconv3x3_dgrad: bad args");
+    B200LP_REQUIRE(static_cast<long>(N) * H * W < (1L << 31), "gconv3x3_dgrad: more than 2^31 pixels");
     B200LP_REQUIRE((cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32) && C % (8 * cpg) == 0, "gconv3x3_dgrad: bad cpg %d / C %d", cpg, C);
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     cudaStream_t st = as_stream(stream);
@@ -1040,7 +1063,8 @@ extern "C" int64_t b200lp_gconv3x3_wgrad_workspace(int32_t N, int32_t H, int32_t
     const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
     int ppc, ts, slices;
     const int chunks = gconv_wgrad_plan(static_cast<long>(N) * Ho * Wo, C, cpg, &ppc, &ts, &slices);
-    return static_cast<int64_t>(chunks) * 9 * C * cpg * 4;
+    const int cg = chunks < 32 ? chunks : 32;
+    return static_cast<int64_t>(chunks + cg) * 9 * C * cpg * 4;       // chunk partials + the stage-1 rows of the reduction
 }
 
 template <int CPG>
@@ -1070,6 +1094,7 @@ extern "C" int32_t b200lp_gconv3x3_wgrad(const float* x, const float* in_scale, 
     B200LP_REQUIRE(need > 0, "gconv3x3_wgrad: unsupported shape N=%d H=%d W=%d C=%d cpg=%d stride=%d", N, H, W, C, cpg, stride);
     B200LP_REQUIRE(workspace_bytes >= need, "gconv3x3_wgrad: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
     B200LP_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "gconv3x3_wgrad: in_scale and in_shift go together");
+    B200LP_REQUIRE(static_cast<long>(N) * H * W < (1L << 31), "gconv3x3_wgrad: more than 2^31 pixels");
     const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
     int ppc, ts, slices;
     const int chunks = gconv_wgrad_plan(static_cast<long>(N) * Ho * Wo, C, cpg, &ppc, &ts, &slices);
@@ -1080,8 +1105,14 @@ extern "C" int32_t b200lp_gconv3x3_wgrad(const float* x, const float* in_scale, 
     else if (cpg == 16) r = launch_gconv_wgrad<16>(x, in_scale, in_shift, dy, workspace, N, H, W, C, stride, Ho, Wo, chunks, ppc, ts, slices, st);
     else r = launch_gconv_wgrad<32>(x, in_scale, in_shift, dy, workspace, N, H, W, C, stride, Ho, Wo, chunks, ppc, ts, slices, st);
     if (r) return r;
-    const long total = static_cast<long>(C) * cpg * 9;
-    gconv3x3_wgrad_reduce_kernel<<<ew_blocks((total + 3) / 4), 256, 0, st>>>(workspace, dw, chunks, C, cpg, accumulate);
+    const unsigned total = static_cast<unsigned>(C) * cpg * 9;
+    const int cg = chunks < 32 ? chunks : 32;
+    float* ws2 = workspace + static_cast<size_t>(chunks) * total;
+    dim3 g1((total + 255) / 256, cg);
+    gconv3x3_wgrad_reduce1_kernel<<<g1, 256, 0, st>>>(workspace, ws2, chunks, cg, total);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    gconv3x3_wgrad_reduce2_kernel<<<ew_blocks((total + 3) / 4), 256, 0, st>>>(ws2, dw, cg, C, cpg, accumulate);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;
