@@ -400,9 +400,44 @@ int32_t b200lp_scatter_add2(const float* dsub, float* dx, int32_t N, int32_t Ho,
 /* global average pool over the HW pixels of [N][HW][C] and its backward */
 int32_t b200lp_avgpool_fwd(const float* x, float* y, int32_t N, int32_t HW, int32_t C, void* stream);
 int32_t b200lp_avgpool_bwd(const float* dy, float* dx, int32_t N, int32_t HW, int32_t C, void* stream);
-/* C[M][N] (+)= sum_k A[i*sai + k*sak] * B[k*sbk + j*sbj]  (fp32; the classifier layers and their gradients) */
+/* C[M][N] (+)= alpha * sum_k A[i*sai + k*sak] * B[k*sbk + j*sbj] (+ bias[j]); alpha = *alpha_dev (device scalar) or 1
+ * (fp32; the classifier / projector layers (generators/...noBottleneck.py:97-101) and their gradients) */
 int32_t b200lp_sgemm_strided(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj, float* C,
-                             int32_t M, int32_t N, int32_t K, int32_t accumulate, void* stream);
+                             const float* alpha_dev, const float* bias, int32_t M, int32_t N, int32_t K,
+                             int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Scalar losses and the small dense pieces around them — csrc/losses.cu (two-stage fixed-order reductions, gather-form
+ * backward kernels: bit-reproducible).
+ */
+/* dice (criterions/dice.py:30-34): fake (B, HW), real (B, CR, HW) -> sums[3] = (sum f*r, sum f^2, sum r^2) with f
+ * broadcast over real's CR channels, loss[0] = -log(2 sums0 / (sums1 + sums2)) * weight; backward: d_fake (B, HW) */
+int64_t b200lp_dice_workspace(int32_t B, int32_t HW);
+int32_t b200lp_dice_fwd(const float* fake, const float* real, float weight, float* sums, float* loss, float* workspace,
+                        int64_t workspace_bytes, int32_t B, int32_t CR, int32_t HW, void* stream);
+int32_t b200lp_dice_bwd(const float* fake, const float* real, const float* sums, const float* grad, float weight,
+                        float* d_fake, int32_t B, int32_t CR, int32_t HW, void* stream);
+/* adversarial losses (criterions/adversarial.py:20-47) on (B,) score vectors: out2 = (loss_G, loss_D);
+ * relativistic 0 = gan (hinge D, -mean G), 1 = rgan, 2 = ragan.  Backward for gan: any output / gradient pointer may be NULL */
+int32_t b200lp_adversarial_fwd(const float* fake_g, const float* fake_d, const float* real, float* out2, int32_t B,
+                               int32_t relativistic, void* stream);
+int32_t b200lp_adversarial_bwd(const float* fake_d, const float* real, const float* grad_g, const float* grad_d,
+                               float* d_fake_g, float* d_fake_d, float* d_real, int32_t B, void* stream);
+/* box crop + resize (criterions/idt_embed.py:62-83): boxes (B, 4) = [t, b, l, r] in pixels (device), x (B, C, H, W) ->
+ * y (B, C, OH, OW) with torch's affine_grid(align_corners=False) + grid_sample(bilinear, reflection) semantics.
+ * Backward (gather form) requires boxes whose sampling positions stay inside the image (no reflection active). */
+int32_t b200lp_crop_bilinear_fwd(const float* x, const float* boxes, float* y, int32_t B, int32_t C, int32_t H, int32_t W,
+                                 int32_t OH, int32_t OW, void* stream);
+int32_t b200lp_crop_bilinear_bwd(const float* dy, const float* boxes, float* dx, int32_t B, int32_t C, int32_t H, int32_t W,
+                                 int32_t OH, int32_t OW, void* stream);
+/* discriminator head (discriminators/no_landmarks.py:101-105): feat (B, P, C) NHWC raw -> o (B, C) = sum_p relu(feat),
+ * score (B,) = inv_sigma * <o, w> + bias + <o, embed> (embed (B, C) or NULL).  Backward: d_feat, d_embed, and the linear
+ * layer's dw (C) (+)= inv_sigma * sum_b g o, ds = sum_b g <o, w> (gradient w.r.t. inv_sigma), dbias (+)= sum_b g. */
+int32_t b200lp_disc_head_fwd(const float* feat, const float* embed, const float* w, const float* inv_sigma,
+                             const float* bias, float* o, float* score, int32_t B, int32_t P, int32_t C, void* stream);
+int32_t b200lp_disc_head_bwd(const float* feat, const float* embed, const float* w, const float* inv_sigma, const float* o,
+                             const float* grad, float* d_feat, float* d_embed, float* dw, float* ds, float* dbias,
+                             int32_t accumulate, int32_t B, int32_t P, int32_t C, void* stream);
 
 #ifdef __cplusplus
 }

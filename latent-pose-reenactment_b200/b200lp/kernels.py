@@ -829,8 +829,9 @@ def avgpool_bwd(dy, hw):
     return dx
 
 
-def sgemm(a, b, trans_a=False, trans_b=False, acc_into=None):
-    """(a^T if trans_a else a) @ (b^T if trans_b else b) for small contiguous fp32 matrices (classifier layers)."""
+def sgemm(a, b, trans_a=False, trans_b=False, acc_into=None, alpha=None, bias=None):
+    """alpha * (a^T if trans_a else a) @ (b^T if trans_b else b) (+ bias per column) for small contiguous fp32 matrices
+    (classifier / projector layers); alpha: 1-element device tensor; added into `acc_into` when given."""
     lib = L.load()
     m, k = (a.shape[1], a.shape[0]) if trans_a else a.shape
     kb, n = (b.shape[1], b.shape[0]) if trans_b else b.shape
@@ -839,7 +840,112 @@ def sgemm(a, b, trans_a=False, trans_b=False, acc_into=None):
     sbk, sbj = (1, b.shape[1]) if trans_b else (b.shape[1], 1)
     out = acc_into if acc_into is not None else torch.empty((m, n), dtype=torch.float32, device=a.device)
     assert out.numel() == m * n
-    with _timed("resnext", flops=2.0 * m * n * k):
-        L.check(lib.b200lp_sgemm_strided(L.ptr(a), sai, sak, L.ptr(b), sbk, sbj, L.ptr(out), m, n, k,
-                                         int(acc_into is not None), L.stream_ptr()), "sgemm_strided")
+    with _timed("dense_small", flops=2.0 * m * n * k):
+        L.check(lib.b200lp_sgemm_strided(L.ptr(a), sai, sak, L.ptr(b), sbk, sbj, L.ptr(out), L.ptr(alpha), L.ptr(bias), m, n,
+                                         k, int(acc_into is not None), L.stream_ptr()), "sgemm_strided")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Scalar losses and the small dense pieces around them — csrc/losses.cu
+# ---------------------------------------------------------------------------------------------------------------------
+def dice_fwd(fake, real, weight):
+    """fake (B, 1, H, W), real (B, CR, H, W) -> (loss (1,), sums (3,)) of criterions/dice.py:30-34."""
+    lib = L.load()
+    b, cr = real.shape[0], real.shape[1]
+    hw = real.shape[2] * real.shape[3]
+    assert fake.numel() == b * hw
+    ws = _ws(lib.b200lp_dice_workspace(b, hw), fake.device)
+    sums = torch.empty(3, dtype=torch.float32, device=fake.device)
+    loss = torch.empty(1, dtype=torch.float32, device=fake.device)
+    with _timed("losses", nbytes=4.0 * (fake.numel() + real.numel())):
+        L.check(lib.b200lp_dice_fwd(L.ptr(fake), L.ptr(real), c_float(weight), L.ptr(sums), L.ptr(loss), L.ptr(ws),
+                                    ws.numel() * 4, b, cr, hw, L.stream_ptr()), "dice_fwd")
+    return loss, sums
+
+
+def dice_bwd(fake, real, sums, grad, weight):
+    lib = L.load()
+    b, cr = real.shape[0], real.shape[1]
+    hw = real.shape[2] * real.shape[3]
+    d_fake = torch.empty_like(fake)
+    with _timed("losses", nbytes=4.0 * (2 * fake.numel() + real.numel())):
+        L.check(lib.b200lp_dice_bwd(L.ptr(fake), L.ptr(real), L.ptr(sums), L.ptr(grad), c_float(weight), L.ptr(d_fake), b, cr,
+                                    hw, L.stream_ptr()), "dice_bwd")
+    return d_fake
+
+
+def adversarial_fwd(fake_g, fake_d, real, relativistic=0):
+    """(B,) score vectors -> out (2,) = (loss_G, loss_D)."""
+    lib = L.load()
+    out = torch.empty(2, dtype=torch.float32, device=real.device)
+    L.check(lib.b200lp_adversarial_fwd(L.ptr(fake_g), L.ptr(fake_d), L.ptr(real), L.ptr(out), real.numel(), relativistic,
+                                       L.stream_ptr()), "adversarial_fwd")
+    return out
+
+
+def adversarial_bwd(fake_d, real, grad_g, grad_d, need_g=True, need_d=True):
+    """-> (d_fake_g, d_fake_d, d_real) for the `gan` type; grad_g / grad_d: 1-element device tensors or None."""
+    lib = L.load()
+    b = real.numel()
+    dg = torch.empty_like(real) if need_g and grad_g is not None else None
+    dd = torch.empty_like(real) if need_d and grad_d is not None else None
+    dr = torch.empty_like(real) if need_d and grad_d is not None else None
+    L.check(lib.b200lp_adversarial_bwd(L.ptr(fake_d), L.ptr(real), L.ptr(grad_g), L.ptr(grad_d), L.ptr(dg), L.ptr(dd),
+                                       L.ptr(dr), b, L.stream_ptr()), "adversarial_bwd")
+    return dg, dd, dr
+
+
+def crop_bilinear_fwd(x, boxes, out_hw=None):
+    """x (B, C, H, W), boxes (B, 4) [t, b, l, r] pixels (device) -> (B, C, OH, OW): affine_grid + grid_sample(bilinear,
+    reflection, align_corners=False)."""
+    lib = L.load()
+    b, c, h, w = x.shape
+    oh, ow = out_hw or (h, w)
+    y = torch.empty((b, c, oh, ow), dtype=torch.float32, device=x.device)
+    with _timed("losses", nbytes=4.0 * (x.numel() + y.numel())):
+        L.check(lib.b200lp_crop_bilinear_fwd(L.ptr(x), L.ptr(boxes), L.ptr(y), b, c, h, w, oh, ow, L.stream_ptr()),
+                "crop_bilinear_fwd")
+    return y
+
+
+def crop_bilinear_bwd(dy, boxes, in_hw):
+    lib = L.load()
+    b, c, oh, ow = dy.shape
+    h, w = in_hw
+    dx = torch.empty((b, c, h, w), dtype=torch.float32, device=dy.device)
+    with _timed("losses", nbytes=4.0 * (dx.numel() + dy.numel())):
+        L.check(lib.b200lp_crop_bilinear_bwd(L.ptr(dy), L.ptr(boxes), L.ptr(dx), b, c, h, w, oh, ow, L.stream_ptr()),
+                "crop_bilinear_bwd")
+    return dx
+
+
+def disc_head_fwd(feat, embed, w, inv_sigma, bias):
+    """feat (B, H, W, C) NHWC raw -> (score (B,), o (B, C))."""
+    lib = L.load()
+    b, h, wd, c = feat.shape
+    o = torch.empty((b, c), dtype=torch.float32, device=feat.device)
+    score = torch.empty(b, dtype=torch.float32, device=feat.device)
+    L.check(lib.b200lp_disc_head_fwd(L.ptr(feat), L.ptr(embed), L.ptr(w), L.ptr(inv_sigma), L.ptr(bias), L.ptr(o),
+                                     L.ptr(score), b, h * wd, c, L.stream_ptr()), "disc_head_fwd")
+    return score, o
+
+
+def disc_head_bwd(feat, embed, w, inv_sigma, o, grad, need_feat=True, need_embed=True, need_params=True, dw_acc=None,
+                  db_acc=None):
+    """-> (d_feat, d_embed, dw, ds, dbias); dw / dbias are added into dw_acc / db_acc when given."""
+    lib = L.load()
+    b, h, wd, c = feat.shape
+    d_feat = torch.empty_like(feat) if need_feat else None
+    d_embed = torch.empty((b, c), dtype=torch.float32, device=feat.device) if (need_embed and embed is not None and need_feat) else None
+    dw = ds = db = None
+    acc = 0
+    if need_params:
+        acc = int(dw_acc is not None)
+        dw = dw_acc if dw_acc is not None else torch.empty(c, dtype=torch.float32, device=feat.device)
+        db = db_acc if db_acc is not None else torch.empty(1, dtype=torch.float32, device=feat.device)
+        ds = torch.empty(1, dtype=torch.float32, device=feat.device)
+    L.check(lib.b200lp_disc_head_bwd(L.ptr(feat), L.ptr(embed), L.ptr(w), L.ptr(inv_sigma), L.ptr(o), L.ptr(grad),
+                                     L.ptr(d_feat), L.ptr(d_embed), L.ptr(dw), L.ptr(ds), L.ptr(db), acc, b, h * wd, c,
+                                     L.stream_ptr()), "disc_head_bwd")
+    return d_feat, d_embed, dw, ds, db

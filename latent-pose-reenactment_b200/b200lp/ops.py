@@ -662,3 +662,186 @@ class VggPerceptualFn(torch.autograd.Function):
 
 def vgg_perceptual(fake_nchw, real_nchw, packed, weight):
     return VggPerceptualFn.apply(fake_nchw, real_nchw.detach(), packed, float(weight))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Small dense layers and scalar losses (csrc/losses.cu, sgemm of csrc/encoder.cu): the last torch arithmetic of the step
+# ----------------------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = inv_sigma * (x W^T) + b — nn.Linear under spectral_norm without materialising W / sigma
+    (generators/vector_pose_unsupervised_segmentation_noBottleneck.py:97-101: the 768 -> 768 -> 13056 projector)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, inv_sigma, bias):
+        x = x.contiguous()
+        y = K.sgemm(x, weight.detach(), trans_b=True, alpha=inv_sigma, bias=bias.detach() if bias is not None else None)
+        ctx.save_for_backward(x, weight, inv_sigma)
+        ctx.bias_ref = bias.detach() if bias is not None else None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, inv_sigma = ctx.saved_tensors
+        dy = dy.contiguous()
+        need_x, need_w, need_s, need_b = ctx.needs_input_grad
+        dx = dw = ds = db = None
+        if need_x:
+            dx = K.sgemm(dy, weight.detach(), alpha=inv_sigma)
+        if need_w or need_s:
+            sink = _sink(weight) if need_w else None
+            if sink is not None and not need_s:
+                K.sgemm(dy, x, trans_a=True, acc_into=sink, alpha=inv_sigma)
+            else:
+                g = K.sgemm(dy, x, trans_a=True)                    # dL/d(W / sigma) before the scale
+                if need_s:
+                    ds = _dot(g, weight.detach()).reshape(inv_sigma.shape)
+                if need_w:
+                    if sink is not None:
+                        sink.add_(g * inv_sigma)
+                    else:
+                        dw = g * inv_sigma
+        if need_b and ctx.bias_ref is not None:
+            bsink = _sink(ctx.bias_ref)
+            if bsink is not None:
+                K.bias_grad(dy, acc_into=bsink)
+            else:
+                db = K.bias_grad(dy)
+        return dx, dw, ds, db
+
+
+def linear(x, weight, inv_sigma, bias):
+    return LinearFn.apply(x, weight, inv_sigma, bias)
+
+
+class DiscHeadFn(torch.autograd.Function):
+    """score = inv_sigma * <o, w> + b + <o, embed>, o = spatial sum of relu(feat) — the discriminator's projection head
+    (discriminators/no_landmarks.py:101-105) as one kernel forward, two backward."""
+
+    @staticmethod
+    def forward(ctx, feat, embed, weight, inv_sigma, bias):
+        feat = feat.contiguous()
+        emb = embed.contiguous() if embed is not None else None
+        score, o = K.disc_head_fwd(feat, emb, weight.detach().reshape(-1), inv_sigma, bias.detach())
+        ctx.save_for_backward(feat, emb, weight, inv_sigma, o)
+        ctx.bias_ref = bias.detach()
+        return score
+
+    @staticmethod
+    def backward(ctx, g):
+        feat, emb, weight, inv_sigma, o = ctx.saved_tensors
+        need_f, need_e, need_w, need_s, need_b = ctx.needs_input_grad
+        wsink = _sink(weight) if need_w else None
+        bsink = _sink(ctx.bias_ref) if need_b else None
+        in_place = wsink is not None and bsink is not None
+        d_feat, d_emb, dw, ds, db = K.disc_head_bwd(
+            feat, emb, weight.detach().reshape(-1), inv_sigma, o, g.contiguous(), need_feat=need_f or need_e,
+            need_embed=need_e, need_params=need_w or need_s or need_b,
+            dw_acc=wsink.reshape(-1) if in_place else None, db_acc=bsink if in_place else None)
+        if in_place:
+            dw = db = None
+        else:
+            if dw is not None and wsink is not None:
+                wsink.add_(dw.view_as(wsink)); dw = None
+            if db is not None and bsink is not None:
+                bsink.add_(db.view_as(bsink)); db = None
+        return (d_feat if need_f else None, d_emb if need_e else None,
+                dw.view_as(weight) if (dw is not None and need_w) else None,
+                ds.reshape(inv_sigma.shape) if (ds is not None and need_s) else None,
+                db if need_b else None)
+
+
+def disc_head(feat, embed, weight, inv_sigma, bias):
+    return DiscHeadFn.apply(feat, embed, weight, inv_sigma, bias)
+
+
+class DiceFn(torch.autograd.Function):
+    """-log(2 sum(f*r) / (sum f^2 + sum r^2)) * w with f (B,1,H,W) broadcast over r's channels (criterions/dice.py:30-34)."""
+
+    @staticmethod
+    def forward(ctx, fake_segm, real_segm, weight):
+        f, r = fake_segm.contiguous(), real_segm.contiguous()
+        loss, sums = K.dice_fwd(f, r, weight)
+        ctx.save_for_backward(f, r, sums)
+        ctx.weight = weight
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        f, r, sums = ctx.saved_tensors
+        return K.dice_bwd(f, r, sums, g.reshape(1).contiguous().float(), ctx.weight), None, None
+
+
+def dice_loss(fake_segm, real_segm, weight):
+    return DiceFn.apply(fake_segm, real_segm.detach(), float(weight))
+
+
+class AdversarialGFn(torch.autograd.Function):
+    """loss_G = -mean(fake_score_G) (criterions/adversarial.py:44-45, `gan`).  Separate nodes for the two losses:
+    loss_D.backward() must not reach the generator's graph through a shared node."""
+
+    @staticmethod
+    def forward(ctx, fake_g):
+        fg = fake_g.contiguous()
+        ctx.n = fg.numel()
+        ctx.save_for_backward(fg)
+        return K.adversarial_fwd(fg, fg, fg, 0)[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (fg,) = ctx.saved_tensors
+        dg, _, _ = K.adversarial_bwd(fg, fg, g.reshape(1).contiguous().float(), None, need_g=True, need_d=False)
+        return dg
+
+
+class AdversarialDFn(torch.autograd.Function):
+    """loss_D = mean(relu(1 - real)) + mean(relu(1 + fake_D)) (criterions/adversarial.py:42, hinge)."""
+
+    @staticmethod
+    def forward(ctx, fake_d, real):
+        fd, rl = fake_d.contiguous(), real.contiguous()
+        ctx.save_for_backward(fd, rl)
+        return K.adversarial_fwd(fd, fd, rl, 0)[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        fd, rl = ctx.saved_tensors
+        _, dd, dr = K.adversarial_bwd(fd, rl, None, g.reshape(1).contiguous().float(), need_g=False, need_d=True)
+        return dd, dr
+
+
+def adversarial_losses(fake_g, fake_d, real):
+    return AdversarialGFn.apply(fake_g), AdversarialDFn.apply(fake_d, real)
+
+
+class CropFn(torch.autograd.Function):
+    """Box crop + bilinear resize (criterions/idt_embed.py:62-83, torch affine_grid + grid_sample(bilinear, reflection))."""
+
+    @staticmethod
+    def forward(ctx, images, boxes):
+        x = images.contiguous()
+        ctx.save_for_backward(boxes)
+        ctx.hw = tuple(x.shape[2:])
+        return K.crop_bilinear_fwd(x, boxes)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (boxes,) = ctx.saved_tensors
+        return K.crop_bilinear_bwd(dy.contiguous(), boxes, ctx.hw), None
+
+
+def crop_boxes_inside(boxes_host, h, w, oh, ow):
+    """True when every sampling position of the boxes (host list of [t, b, l, r]) lies inside the image, i.e. the
+    reflection padding never acts and CropFn's gather-form backward is exact."""
+    for t, b, l, r in boxes_host:
+        ay, ax = (b - t) / oh, (r - l) / ow
+        if ay <= 0 or ax <= 0:
+            return False
+        y0, y1 = t + 0.5 * ay - 0.5, t + 0.5 * ay - 0.5 + ay * (oh - 1)
+        x0, x1 = l + 0.5 * ax - 0.5, l + 0.5 * ax - 0.5 + ax * (ow - 1)
+        if y0 < 0 or x0 < 0 or y1 > h - 1 or x1 > w - 1:
+            return False
+    return True
+
+
+def crop_bilinear(images, boxes):
+    return CropFn.apply(images, boxes)

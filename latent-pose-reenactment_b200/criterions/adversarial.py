@@ -33,6 +33,11 @@ class Criterion(nn.Module):
         fake_score_G = data_dict['fake_score_G']
         fake_score_D = data_dict['fake_score_D']
         real_score = data_dict['real_score']
+        if self.gan_type == 'gan':
+            # one kernel for both losses (hinge / -mean over the (B,) score vectors), one for their gradients
+            from b200lp import ops
+            loss_G, loss_D = ops.adversarial_losses(fake_score_G, fake_score_D, real_score)
+            return {'adversarial_G': loss_G}, {'adversarial_D': loss_D}
 
         real_pred, fake_pred_D = self.get_dis_preds(real_score, fake_score_D)
         _, fake_pred_G = self.get_dis_preds(real_score, fake_score_G)

@@ -50,10 +50,18 @@ class Criterion(torch.nn.Module):
                 t = h * (1 - crop_factor) / 2
                 l = w * (1 - crop_factor) / 2
                 bboxes = torch.tensor([[t, h - t, l, w - l]], dtype=torch.float32, device=real_rgb.device)
-                grid = sampling_grid(bboxes.expand(len(real_rgb), 4), real_rgb.shape)
+                # crop kernel (bilinear gather forward, gather-form backward): the box is strictly inside the image
+                from b200lp import ops
+                assert ops.crop_boxes_inside([[t, h - t, l, w - l]], h, w, h, w)
+                grid = ('boxes', bboxes.expand(len(real_rgb), 4).contiguous())
                 self._center_grid[key] = grid
-            fake_cropped = sample(fake_rgb, grid)
-            real_cropped = sample(real_rgb, grid)
+            if isinstance(grid, tuple):
+                from b200lp import ops
+                fake_cropped = ops.crop_bilinear(fake_rgb, grid[1])
+                real_cropped = ops.crop_bilinear(real_rgb.detach(), grid[1])
+            else:
+                fake_cropped = sample(fake_rgb, grid)
+                real_cropped = sample(real_rgb, grid)
         return {'VGGFace': self.idt_embed_crit(fake_cropped, real_cropped)}
 
 

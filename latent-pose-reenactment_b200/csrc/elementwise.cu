@@ -833,6 +833,18 @@ extern "C" int32_t b200lp_copy_multi(const void* table_dev, int32_t count, void*
     return B200LP_OK;
 }
 
+namespace b200lp {
+// wide, short matrices (the 13056-column projector output of a batch of 8): one thread per column walks the rows
+__global__ void __launch_bounds__(256)
+bias_grad_wide_kernel(const float* __restrict__ dy, float* __restrict__ db, int rows, int C, int accumulate) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += __ldg(dy + static_cast<size_t>(r) * C + c);
+    db[c] = (accumulate ? db[c] : 0.f) + s;
+}
+}  // namespace b200lp
+
 static int32_t bias_grad_impl(const float* dy, float* db, int64_t pixels, int32_t C, int32_t accumulate, void* stream);
 
 extern "C" int32_t b200lp_bias_grad(const float* dy, float* db, int64_t pixels, int32_t C, void* stream) {
@@ -844,8 +856,16 @@ extern "C" int32_t b200lp_bias_grad_acc(const float* dy, float* db, int64_t pixe
 }
 
 static int32_t bias_grad_impl(const float* dy, float* db, int64_t pixels, int32_t C, int32_t accumulate, void* stream) {
-    B200LP_REQUIRE(dy && db && pixels > 0 && C > 0 && C % 4 == 0 && C / 4 <= kEwThreads, "bias_grad: bad args");
+    B200LP_REQUIRE(dy && db && pixels > 0 && C > 0, "bias_grad: bad args");
     cudaStream_t s = as_stream(stream);
+    if (C % 4 != 0 || C / 4 > kEwThreads) {
+        B200LP_REQUIRE(pixels <= 4096, "bias_grad: C=%d needs the wide kernel, which is for short matrices (rows=%lld)", C,
+                       (long long)pixels);
+        bias_grad_wide_kernel<<<(C + 255) / 256, 256, 0, s>>>(dy, db, static_cast<int>(pixels), C, accumulate);
+        B200LP_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+        return B200LP_OK;
+    }
     if (!accumulate) B200LP_CHECK_CUDA(cudaMemsetAsync(db, 0, static_cast<size_t>(C) * 4, s));
     const int rows = kEwThreads / (C / 4);
     long blocks = 148 * 4;

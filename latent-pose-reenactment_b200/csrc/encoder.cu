@@ -804,11 +804,15 @@ avgpool_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, long to
 }
 
 // ------------------------------------------------------------------------------------------------ small strided SGEMM
-// C[i][j] (+)= sum_k A(i,k) * B(k,j),  A(i,k) = A[i*sai + k*sak],  B(k,j) = B[k*sbk + j*sbj]  (fp32, 64x64 tile, K step 16).
-// For the classifier layers and their gradients (M <= 64 rows): dgrad = dy @ W, wgrad = dy^T @ x.
+// C[i][j] (+)= alpha * sum_k A(i,k) * B(k,j) (+ bias[j]),  A(i,k) = A[i*sai + k*sak],  B(k,j) = B[k*sbk + j*sbj]
+// (fp32, 64x64 tile, K step 16; alpha = *alpha_dev or 1).  For the classifier / projector layers and their gradients
+// (M <= 64 rows): y = x W^T, dgrad = dy W, wgrad = dy^T x.  The tile loaders run along whichever axis of the operand
+// is contiguous (AK / BK: the k axis), so every operand streams in full 32-byte sectors.
+template <bool AK, bool BK>
 __global__ void __launch_bounds__(256)
 sgemm_strided_kernel(const float* __restrict__ A, long sai, long sak, const float* __restrict__ B, long sbk, long sbj,
-                     float* __restrict__ Cm, int M, int N, int K, int accumulate) {
+                     float* __restrict__ Cm, const float* __restrict__ alpha_dev, const float* __restrict__ bias, int M, int N,
+                     int K, int accumulate) {
     __shared__ float As[16][65], Bs[16][65];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
@@ -819,12 +823,12 @@ sgemm_strided_kernel(const float* __restrict__ A, long sai, long sak, const floa
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     for (int k0 = 0; k0 < K; k0 += 16) {
         for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-            const int kk = e & 15, r = e >> 4;           // A: consecutive threads along k
+            const int kk = AK ? (e & 15) : (e >> 6), r = AK ? (e >> 4) : (e & 63);
             const int m = m0 + r, k = k0 + kk;
             As[kk][r] = (m < M && k < K) ? __ldg(A + m * sai + k * sak) : 0.f;
         }
         for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-            const int r = e & 63, kk = e >> 6;           // B: consecutive threads along j
+            const int kk = BK ? (e & 15) : (e >> 6), r = BK ? (e >> 4) : (e & 63);
             const int n = n0 + r, k = k0 + kk;
             Bs[kk][r] = (n < N && k < K) ? __ldg(B + k * sbk + n * sbj) : 0.f;
         }
@@ -843,6 +847,7 @@ sgemm_strided_kernel(const float* __restrict__ A, long sai, long sak, const floa
         }
         __syncthreads();
     }
+    const float alpha = alpha_dev ? __ldg(alpha_dev) : 1.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int m = m0 + ty * 4 + i;
@@ -852,7 +857,7 @@ sgemm_strided_kernel(const float* __restrict__ A, long sai, long sak, const floa
             const int n = n0 + tx * 4 + j;
             if (n < N) {
                 float* o = Cm + static_cast<size_t>(m) * N + n;
-                *o = (accumulate ? *o : 0.f) + acc[i][j];
+                *o = (accumulate ? *o : 0.f) + alpha * acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
             }
         }
     }
@@ -1200,10 +1205,16 @@ extern "C" int32_t b200lp_avgpool_bwd(const float* dy, float* dx, int32_t N, int
 }
 
 extern "C" int32_t b200lp_sgemm_strided(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj,
-                                        float* C, int32_t M, int32_t N, int32_t K, int32_t accumulate, void* stream) {
+                                        float* C, const float* alpha_dev, const float* bias, int32_t M, int32_t N, int32_t K,
+                                        int32_t accumulate, void* stream) {
     B200LP_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "sgemm_strided: bad args");
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    sgemm_strided_kernel<<<grid, 256, 0, as_stream(stream)>>>(A, sai, sak, B, sbk, sbj, C, M, N, K, accumulate);
+    cudaStream_t st = as_stream(stream);
+    const bool ak = sak == 1, bk = sbk == 1 && sbj != 1;
+    if (ak && bk) sgemm_strided_kernel<true, true><<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, alpha_dev, bias, M, N, K, accumulate);
+    else if (ak) sgemm_strided_kernel<true, false><<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, alpha_dev, bias, M, N, K, accumulate);
+    else if (bk) sgemm_strided_kernel<false, true><<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, alpha_dev, bias, M, N, K, accumulate);
+    else sgemm_strided_kernel<false, false><<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, alpha_dev, bias, M, N, K, accumulate);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

@@ -115,10 +115,9 @@ class Discriminator(nn.Module):
             feats.append(r)
             out = block(r, detach_params)
         feats.append(out)                  # the last feature stays pre-ReLU (reference :100 is out of place)
-        o = torch.relu(out).sum(dim=(1, 2))                       # (B, C): spatial sum of the NHWC map
         wl, sl, bl = self.linear.operands_edge(detach_params)
-        out_linear = (torch.nn.functional.linear(o, wl) * sl + bl)[:, 0]
-        score = (o * embed).sum(1) + out_linear if embed is not None else out_linear
+        # relu -> spatial sum -> SN-linear + projection onto the label embedding as one kernel (+ two backward)
+        score = ops.disc_head(out, embed, wl, sl, bl)
         return score, [f.permute(0, 3, 1, 2) for f in feats]
 
     def _tensor_core_convs(self):

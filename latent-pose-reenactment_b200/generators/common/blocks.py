@@ -148,6 +148,8 @@ class SNLinear(SpectralNormed):
 
     def forward(self, x):
         # (x W^T) / sigma + b  ==  F.linear(x, W / sigma, b) without materialising W / sigma
+        if x.dim() == 2:
+            return ops.linear(x, self.weight_orig, self.scale(), self.bias)       # one SGEMM kernel, scale + bias fused
         return torch.nn.functional.linear(x, self.weight_orig) * self.scale() + self.bias
 
 

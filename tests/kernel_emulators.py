@@ -282,7 +282,102 @@ def copy_multi(plan):
         d.copy_(s)
 
 
+# ------------------------------------------------------------------------------------------------ small dense / losses
+def sgemm(a, b, trans_a=False, trans_b=False, acc_into=None, alpha=None, bias=None):
+    r = (a.t() if trans_a else a) @ (b.t() if trans_b else b)
+    if alpha is not None:
+        r = r * alpha.reshape(()).to(r.dtype)
+    if bias is not None:
+        r = r + bias
+    if acc_into is not None:
+        acc_into.add_(r.view_as(acc_into))
+        return acc_into
+    return r.contiguous()
+
+
+def dice_fwd(fake, real, weight):
+    s0, s1, s2 = (fake * real).sum(), (fake * fake).sum(), (real * real).sum()
+    sums = torch.stack([s0, s1, s2])
+    return (-torch.log(2 * s0 / (s1 + s2)) * weight).reshape(1), sums
+
+
+def dice_bwd(fake, real, sums, grad, weight):
+    rs = real.sum(1, keepdim=True)
+    return -weight * grad.reshape(()) * (rs / sums[0] - 2 * fake / (sums[1] + sums[2]))
+
+
+def adversarial_fwd(fake_g, fake_d, real, relativistic=0):
+    assert relativistic == 0
+    return torch.stack([-fake_g.mean(), torch.relu(1 - real).mean() + torch.relu(1 + fake_d).mean()])
+
+
+def adversarial_bwd(fake_d, real, grad_g, grad_d, need_g=True, need_d=True):
+    b = real.numel()
+    dg = dd = dr = None
+    if need_g and grad_g is not None:
+        dg = torch.full_like(real, -1.0 / b) * grad_g.reshape(())
+    if need_d and grad_d is not None:
+        dd = (1 + fake_d > 0).to(real.dtype) * grad_d.reshape(()) / b
+        dr = -(1 - real > 0).to(real.dtype) * grad_d.reshape(()) / b
+    return dg, dd, dr
+
+
+def _crop_grid(boxes, shape):
+    t, b, l, r = boxes.t()
+    n, c, h, w = shape
+    theta = torch.zeros(n, 2, 3, dtype=boxes.dtype, device=boxes.device)
+    theta[:, 0, 0] = (r - l) / w
+    theta[:, 1, 1] = (b - t) / h
+    theta[:, 0, 2] = (l + r) / w - 1
+    theta[:, 1, 2] = (t + b) / h - 1
+    return F.affine_grid(theta, list(shape), align_corners=False)
+
+
+def crop_bilinear_fwd(x, boxes, out_hw=None):
+    shape = tuple(x.shape[:2]) + tuple(out_hw or x.shape[2:])
+    return F.grid_sample(x, _crop_grid(boxes.to(x.dtype), shape), mode="bilinear", padding_mode="reflection", align_corners=False)
+
+
+def crop_bilinear_bwd(dy, boxes, in_hw):
+    x = torch.zeros(tuple(dy.shape[:2]) + tuple(in_hw), dtype=dy.dtype, device=dy.device, requires_grad=True)
+    with torch.enable_grad():
+        y = F.grid_sample(x, _crop_grid(boxes.to(dy.dtype), tuple(dy.shape)), mode="bilinear", padding_mode="reflection",
+                          align_corners=False)
+        (g,) = torch.autograd.grad(y, x, dy)
+    return g
+
+
+def disc_head_fwd(feat, embed, w, inv_sigma, bias):
+    o = feat.clamp_min(0).sum((1, 2))
+    score = (o @ w) * inv_sigma.reshape(()) + bias.reshape(())
+    if embed is not None:
+        score = score + (o * embed).sum(1)
+    return score, o
+
+
+def disc_head_bwd(feat, embed, w, inv_sigma, o, grad, need_feat=True, need_embed=True, need_params=True, dw_acc=None,
+                  db_acc=None):
+    s = inv_sigma.reshape(())
+    d_feat = d_embed = dw = ds = db = None
+    if need_feat:
+        k = grad[:, None] * (s * w[None, :] + (embed if embed is not None else 0))
+        d_feat = (feat > 0).to(feat.dtype) * k[:, None, None, :]
+        if need_embed and embed is not None:
+            d_embed = grad[:, None] * o
+    if need_params:
+        a = (grad[:, None] * o).sum(0)
+        ds = (a * w).sum().reshape(1)
+        if dw_acc is not None:
+            dw_acc.add_(s * a); dw = dw_acc
+            db_acc.add_(grad.sum()); db = db_acc
+        else:
+            dw, db = s * a, grad.sum().reshape(1)
+    return d_feat, d_embed, dw, ds, db
+
+
 EMULATED = [
+    "sgemm", "dice_fwd", "dice_bwd", "adversarial_fwd", "adversarial_bwd", "crop_bilinear_fwd", "crop_bilinear_bwd",
+    "disc_head_fwd", "disc_head_bwd",
     "pack_conv_weight", "conv_fwd", "conv_wgrad", "conv_wgrad_sn_acc", "bias_grad", "sn_scratch", "sn_sigma_multi",
     "sn_wgrad_fix", "in_stats", "adain_relu", "adain_relu_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "relu_round", "relu_bwd",
     "avgpool2", "avgpool2_bwd", "upsample2_bwd", "l1_sum", "l1_bwd", "l1_relu_bwd", "conv3x3_c3_fwd", "im2col3x3_c3",

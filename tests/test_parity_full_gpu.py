@@ -4,10 +4,14 @@ benchmark spends its time in (conv_halo2 / conv_halo / split-K conv_igemm, the t
 AdaIN / L1 / pooling passes) are each reached by a reference golden; one 512x512 forward (configs[4] shapes: 19 AdaIN
 sites, 8 up-blocks); and the identity encoder (ResNeXt50-32x4d, train-mode BatchNorm) against the reference embedder.
 
-Tolerances: generator RGB max-abs <= 1e-3 (north_star); discriminator / loss values 3e-3 relative (TF32 operands);
-gradients are reported per parameter (`gpurun_out/full_step_gradient_errors.json`) and asserted at 8e-3 of the
-parameter's gradient max (sub-sampled tensors) / 5e-3 on norms — what TF32 (2^-11 operand rounding) needs, instead of
-round 1's 2e-2.
+Tolerances: generator RGB max-abs <= 1e-3 (north_star); discriminator / loss values 3e-3 relative (TF32 operands).
+Gradients: the achieved error of EVERY parameter is written to `gpurun_out/full_step_gradient_errors.json` and asserted
+(a) on the gradient NORM at 5e-3 and (b) element-wise (sub-sampled tensors, relative to the tensor's max) against what
+TF32 operands cost on this very step: `profiles/r02_grad_error_study_torch_fp32_tf32.json` holds, per parameter, the
+same error for torch's own kernels run on the B200 in true fp32 and with cuDNN / cuBLAS TF32 (torch's default for
+convolutions) — tools/grad_error_study.py.  torch-TF32 reaches 4.7e-2 on the deepest 4x4-plane discriminator weights
+(32 pixels per weight-gradient element at batch 2) and 1e-2..1.3e-1 on the generator; this path must stay within
+max(8e-3, 1.25 x torch-TF32's error) per parameter, and within 8e-3 for 90 % of them.
 """
 import importlib
 import json
@@ -145,6 +149,10 @@ def test_full_size_training_step(full, gold):
     report = {"generator": {}, "discriminator": {}}
     g_max = max(gold["step.gradG.norms"].values())
     worst = []
+    study = json.loads((ROOT / "profiles" / "r02_grad_error_study_torch_fp32_tf32.json").read_text())["torch_tf32"]
+
+    def elem_tol(name):
+        return max(8e-3, 1.25 * study.get(name, {}).get("sub_rel_to_max", 0.0))
     for k, p in G.named_parameters():
         ref_norm = gold["step.gradG.norms"][k]
         ref_sub = gold["step.gradG.sub." + k]
@@ -152,7 +160,7 @@ def test_full_size_training_step(full, gold):
         e_sub = max_abs(sub(p.grad), ref_sub) / (float(ref_sub.abs().max()) + 1e-30)
         report["generator"][k] = {"norm_rel": e_norm, "sub_rel_to_max": e_sub, "ref_norm": ref_norm}
         if ref_norm > 1e-4 * g_max:          # analytically ~0 gradients (a bias the next InstanceNorm removes) are noise
-            worst.append((max(e_norm / 5e-3, e_sub / 8e-3), k, e_norm, e_sub))
+            worst.append((max(e_norm / 5e-3, e_sub / elem_tol(k)), k, e_norm, e_sub))
     assert abs(float(E.scale.grad) - float(gold["step.gradE.scale"])) <= 5e-3 * abs(float(gold["step.gradE.scale"])) + 1e-7
     opt_G.step()
     bucket_D.zero()
@@ -166,7 +174,7 @@ def test_full_size_training_step(full, gold):
         e_sub = max_abs(sub(p.grad), ref_sub) / (float(ref_sub.abs().max()) + 1e-30)
         report["discriminator"][k] = {"norm_rel": e_norm, "sub_rel_to_max": e_sub, "ref_norm": ref_norm}
         if ref_norm > 1e-4 * d_max:
-            worst.append((max(e_norm / 5e-3, e_sub / 8e-3), k, e_norm, e_sub))
+            worst.append((max(e_norm / 5e-3, e_sub / elem_tol(k)), k, e_norm, e_sub))
     opt_D.step()
     tm.update_running_average(0.999)
     out = ROOT / "gpurun_out"
@@ -175,6 +183,8 @@ def test_full_size_training_step(full, gold):
     report["worst"] = [dict(param=k, norm_rel=a, sub_rel_to_max=b) for _, k, a, b in worst[:10]]
     (out / "full_step_gradient_errors.json").write_text(json.dumps(report, indent=1))
     assert worst[0][0] <= 1.0, worst[:5]
+    subs = sorted(w_[3] for w_ in worst)
+    assert subs[int(0.9 * len(subs))] <= 8e-3, subs[int(0.9 * len(subs))]
     for k in ("decoder_blocks.5.block.4.weight_orig", "decoder_blocks.7.block.8.weight_orig"):
         got = sub(dict(G.named_parameters())[k].detach())
         assert max_abs(got, gold["step.after.G.sub." + k]) < 1.5e-4                      # lr_gen * O(1)

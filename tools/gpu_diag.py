@@ -1292,7 +1292,11 @@ def identity_encoder():
     trace, resnext_native.TRACE = resnext_native.TRACE, None
     torch.cuda.synchronize()
     blocks_a, blocks_b = resnext_native.blocks_of(a), resnext_native.blocks_of(b)
-    worst_p, worst_in, worst_name = 0.0, 0.0, ""
+    worst_p, worst_in, worst_name, per_block = 0.0, 0.0, "", []
+
+    def l2rel(x_, y_):
+        return float((x_.double() - y_).norm() / (y_.norm() + 1e-30))
+
     for rec, d_blk_out, d_blk_in in trace:
         bi = blocks_a.index(rec["blk"])
         blk_b = blocks_b[bi]
@@ -1301,17 +1305,24 @@ def identity_encoder():
         xin = rec["a_f32"].permute(0, 3, 1, 2).double().requires_grad_(True)
         yout = blk_b(xin)
         yout.backward(d_blk_out.permute(0, 3, 1, 2).double())
-        e_in = float((d_blk_in.permute(0, 3, 1, 2).double() - xin.grad).abs().max() / (xin.grad.abs().max() + 1e-30))
+        # relative L2 errors: a ReLU mask that flips under the forward's 2^-17 operand rounding changes single elements by
+        # O(1) (max-norm metrics see only those), but it is a 1e-5 fraction of the elements
+        e_in = l2rel(d_blk_in.permute(0, 3, 1, 2), xin.grad)
+        e_in_max = float((d_blk_in.permute(0, 3, 1, 2).double() - xin.grad).abs().max() / (xin.grad.abs().max() + 1e-30))
         worst_in = max(worst_in, e_in)
+        row = {"block": bi, "d_in_l2": e_in, "d_in_max": e_in_max,
+               "fwd_l2": l2rel(rec["out"].permute(0, 3, 1, 2), yout.detach())}
         for (nm, pa), pb in zip(rec["blk"].named_parameters(), blk_b.parameters()):
-            e = float((pa.grad.double() - pb.grad).abs().max() / (pb.grad.abs().max() + 1e-30))
+            e = l2rel(pa.grad, pb.grad)
+            row[nm] = e
             if e > worst_p:
                 worst_p, worst_name = e, f"block {bi} {nm}"
+        per_block.append(row)
     out.append({"case": "identity block-local backward (16 x 256x256, train): parameter gradients vs fp64 autograd on the same "
-                        "block input", "ok": worst_p < 1e-2, "max_abs": worst_p, "rel": worst_p, "nan": worst_p != worst_p,
-                "ref_max": 1.0, "worst": worst_name})
-    out.append({"case": "identity block-local backward: input gradients", "ok": worst_in < 1e-2, "max_abs": worst_in,
-                "rel": worst_in, "nan": worst_in != worst_in, "ref_max": 1.0})
+                        "block input (relative L2)", "ok": worst_p < 1e-2, "max_abs": worst_p, "rel": worst_p,
+                "nan": worst_p != worst_p, "ref_max": 1.0, "worst": worst_name, "per_block": per_block})
+    out.append({"case": "identity block-local backward: input gradients (relative L2)", "ok": worst_in < 1e-2,
+                "max_abs": worst_in, "rel": worst_in, "nan": worst_in != worst_in, "ref_max": 1.0})
     del a, b, trace
     torch.cuda.empty_cache()
 
@@ -1335,6 +1346,109 @@ def identity_encoder():
     with torch.no_grad():
         rec["native_fwd_only_us"] = round(_time_us(lambda: resnext_native.apply(a, x), reps=3, warm=1), 0)
     out.append(rec)
+    return out
+
+
+@check
+def losses_kernels():
+    """dice / adversarial / crop (grid_sample semantics) / discriminator head / strided sgemm (+alpha, bias) / wide
+    bias gradient vs torch in float64."""
+    import torch
+    import torch.nn.functional as F
+    from b200lp import kernels as K
+    from b200lp import ops
+    sys.path.insert(0, str(ROOT / "tests"))
+    import kernel_emulators as KE
+    out = []
+    dev = "cuda"
+    torch.manual_seed(21)
+    for (b, cr, h, w) in [(8, 3, 256, 256), (2, 3, 32, 32), (3, 1, 17, 9)]:
+        f = torch.rand(b, 1, h, w, device=dev, requires_grad=True)
+        r = (torch.rand(b, cr, h, w, device=dev) > 0.5).float()
+        loss = ops.dice_loss(f, r, 1.7)
+        (loss * 0.3).backward()
+        f64 = f.detach().double().requires_grad_(True)
+        ref = -torch.log((2 * f64 * r.double()).sum() / ((f64 ** 2).sum() + (r.double() ** 2).sum())) * 1.7
+        (ref * 0.3).backward()
+        out.append(_cmp(f"dice loss B{b} CR{cr} {h}x{w}", loss.detach().reshape(1), ref.detach().reshape(1), 1e-5))
+        out.append(_cmp(f"dice grad B{b} CR{cr} {h}x{w}", f.grad, f64.grad, 1e-5))
+    for b in (8, 2, 33):
+        fg = torch.randn(b, device=dev, requires_grad=True)
+        fd = torch.randn(b, device=dev, requires_grad=True)
+        rl = torch.randn(b, device=dev, requires_grad=True)
+        lg, ld = ops.adversarial_losses(fg, fd, rl)
+        (lg * 0.7 + ld * 1.3).backward()
+        a, c, d = (t.detach().double().requires_grad_(True) for t in (fg, fd, rl))
+        rg = -a.mean()
+        rd = torch.relu(1 - d).mean() + torch.relu(1 + c).mean()
+        (rg * 0.7 + rd * 1.3).backward()
+        out.append(_cmp(f"adversarial losses B{b}", torch.stack([lg, ld]).detach(), torch.stack([rg, rd]).detach(), 1e-6))
+        for nm, t, t64 in (("fake_G", fg, a), ("fake_D", fd, c), ("real", rl, d)):
+            out.append(_cmp(f"adversarial grad {nm} B{b}", t.grad, t64.grad, 1e-6))
+    for (b, c, h, w, box) in [(8, 3, 256, 256, None), (2, 3, 32, 32, None), (2, 2, 20, 12, [3.3, 15.1, 2.2, 9.7])]:
+        if box is None:
+            t_, l_ = h * (1 - 1 / 1.8) / 2, w * (1 - 1 / 1.8) / 2
+            box = [t_, h - t_, l_, w - l_]
+        boxes = torch.tensor([box], dtype=torch.float32, device=dev).expand(b, 4).contiguous()
+        x = torch.rand(b, c, h, w, device=dev, requires_grad=True)
+        y = ops.crop_bilinear(x, boxes)
+        wgt = torch.randn_like(y)
+        (y * wgt).sum().backward()
+        x64 = x.detach().double().requires_grad_(True)
+        y64 = KE.crop_bilinear_fwd(x64, boxes.double())
+        (y64 * wgt.double()).sum().backward()
+        out.append(_cmp(f"crop fwd B{b} C{c} {h}x{w}", y, y64, 2e-5, inside=ops.crop_boxes_inside([box], h, w, h, w)))
+        out.append(_cmp(f"crop bwd B{b} C{c} {h}x{w}", x.grad, x64.grad, 2e-5))
+    # forward-only: a box that leaves the image (reflection padding active)
+    x = torch.rand(2, 3, 24, 24, device=dev)
+    boxes = torch.tensor([[-4.0, 20.0, 3.0, 30.0]], device=dev).expand(2, 4).contiguous()
+    out.append(_cmp("crop fwd with reflection", K.crop_bilinear_fwd(x, boxes), KE.crop_bilinear_fwd(x.double(), boxes.double()), 2e-5))
+    for (b, p, c, with_embed) in [(8, 16, 512, True), (2, 4, 64, True), (3, 16, 96, False)]:
+        feat = torch.randn(b, 4, p // 4, c, device=dev, requires_grad=True)
+        emb = torch.randn(b, c, device=dev, requires_grad=True) if with_embed else None
+        wl = torch.randn(1, c, device=dev, requires_grad=True)
+        sl = (torch.rand(1, device=dev) + 0.5).requires_grad_(True)
+        bl = torch.randn(1, device=dev, requires_grad=True)
+        score = ops.disc_head(feat, emb, wl, sl, bl)
+        g = torch.randn(b, device=dev)
+        (score * g).sum().backward()
+        f64, w64, s64, b64 = (t.detach().double().requires_grad_(True) for t in (feat, wl, sl, bl))
+        e64 = emb.detach().double().requires_grad_(True) if with_embed else None
+        o = torch.relu(f64).sum((1, 2))
+        ref = (F.linear(o, w64) * s64 + b64)[:, 0]
+        if with_embed:
+            ref = ref + (o * e64).sum(1)
+        (ref * g.double()).sum().backward()
+        tag = f"B{b} P{p} C{c} embed{int(with_embed)}"
+        out.append(_cmp(f"disc head score {tag}", score, ref, 1e-5))
+        pairs = [("feat", feat, f64), ("w", wl, w64), ("inv_sigma", sl, s64), ("bias", bl, b64)]
+        if with_embed:
+            pairs.append(("embed", emb, e64))
+        for nm, t, t64 in pairs:
+            out.append(_cmp(f"disc head grad {nm} {tag}", t.grad, t64.grad, 2e-5))
+    for (m, k, n) in [(8, 768, 13056), (8, 768, 768), (5, 33, 70)]:
+        x = torch.randn(m, k, device=dev, requires_grad=True)
+        wt = (torch.randn(n, k, device=dev) * 0.05).requires_grad_(True)
+        s_ = (torch.rand(1, device=dev) + 0.5).requires_grad_(True)
+        bias = torch.randn(n, device=dev, requires_grad=True)
+        y = ops.linear(x, wt, s_, bias)
+        g = torch.randn_like(y)
+        (y * g).sum().backward()
+        x64, w64, s64, b64 = (t.detach().double().requires_grad_(True) for t in (x, wt, s_, bias))
+        ref = F.linear(x64, w64) * s64 + b64
+        (ref * g.double()).sum().backward()
+        out.append(_cmp(f"linear fwd {m}x{k}x{n}", y, ref, 1e-5))
+        for nm, t, t64 in (("x", x, x64), ("w", wt, w64), ("inv_sigma", s_, s64), ("bias", bias, b64)):
+            out.append(_cmp(f"linear grad {nm} {m}x{k}x{n}", t.grad, t64.grad, 2e-5))
+        # gradient sinks: weight and bias gradients accumulated in place
+        wt2 = wt.detach().clone().requires_grad_(True)
+        b2 = bias.detach().clone().requires_grad_(True)
+        sinks = {wt2.data_ptr(): torch.ones_like(wt2), b2.data_ptr(): torch.ones_like(b2)}
+        with ops.direct_grads(sinks):
+            y2 = ops.linear(x.detach(), wt2, s_.detach(), b2)
+            (y2 * g).sum().backward()
+        out.append(_cmp(f"linear sink w {m}x{k}x{n}", sinks[wt2.data_ptr()] - 1, w64.grad, 2e-5))
+        out.append(_cmp(f"linear sink bias {m}x{k}x{n}", sinks[b2.data_ptr()] - 1, b64.grad, 2e-5))
     return out
 
 
