@@ -372,7 +372,7 @@ def kernel_family(name):
              ("adam_ema", "optimizer"), ("ema_multi", "optimizer"), ("opt_tick", "optimizer"),
              ("gen_tail", "gen_tail"), ("conv3x3_c3", "c3_stem"), ("im2col3x3", "c3_stem"), ("col2im3x3", "c3_stem"),
              ("gconv", "resnext_grouped"), ("im2col7x7", "resnext"), ("maxpool3x3s2", "resnext"), ("subsample2", "resnext"),
-             ("scatter_add2", "resnext"), ("avgpool_", "resnext"), ("sgemm_", "resnext"), ("col_stats", "batchnorm"),
+             ("scatter_add2", "resnext"), ("avgpool_", "resnext"), ("sgemm_", "dense_small"), ("col_stats", "batchnorm"),
              ("bn_apply", "pose_encoder"), ("bn_relu6_avgpool", "pose_encoder"), ("bn_", "batchnorm"),
              ("pw_", "pose_encoder"), ("dw_", "pose_encoder"), ("mbv2", "pose_encoder"))
     for prefix, fam in table:

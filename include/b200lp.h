@@ -402,9 +402,10 @@ int32_t b200lp_avgpool_fwd(const float* x, float* y, int32_t N, int32_t HW, int3
 int32_t b200lp_avgpool_bwd(const float* dy, float* dx, int32_t N, int32_t HW, int32_t C, void* stream);
 /* C[M][N] (+)= alpha * sum_k A[i*sai + k*sak] * B[k*sbk + j*sbj] (+ bias[j]); alpha = *alpha_dev (device scalar) or 1
  * (fp32; the classifier / projector layers (generators/...noBottleneck.py:97-101) and their gradients) */
+int64_t b200lp_sgemm_strided_workspace(int32_t M, int32_t N, int32_t K);    /* split-K partial sums (0: none needed) */
 int32_t b200lp_sgemm_strided(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj, float* C,
                              const float* alpha_dev, const float* bias, int32_t M, int32_t N, int32_t K,
-                             int32_t accumulate, void* stream);
+                             int32_t accumulate, float* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Scalar losses and the small dense pieces around them — csrc/losses.cu (two-stage fixed-order reductions, gather-form
@@ -438,6 +439,31 @@ int32_t b200lp_disc_head_fwd(const float* feat, const float* embed, const float*
 int32_t b200lp_disc_head_bwd(const float* feat, const float* embed, const float* w, const float* inv_sigma, const float* o,
                              const float* grad, float* d_feat, float* d_embed, float* dw, float* ds, float* dbias,
                              int32_t accumulate, int32_t B, int32_t P, int32_t C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Pose encoder (MobileNetV2) BACKWARD — csrc/mobilenet_bwd.cu (FP32 CUDA cores; BatchNorm backward = b200lp_bn_bwd with
+ * the ReLU6 mask mode).  Replaces autograd's backward of Embedder.get_pose_embedding
+ * (embedders/unsupervised_pose_separate_embResNeXt_segmentation.py:56-58) in meta-training.
+ */
+/* dst [C][R] = src [R][C]^T (the 1x1 data gradient runs as b200lp_pw_conv on the transposed weight) */
+int32_t b200lp_transpose2d(const float* src, float* dst, int32_t R, int32_t C, void* stream);
+/* 1x1 conv / linear weight gradient: dw [Cout][Cin] (+)= sum_m dy[m][co] * f(x[m][ci]), f as in b200lp_pw_conv */
+int64_t b200lp_pw_wgrad_workspace(int64_t M, int32_t Cin, int32_t Cout);
+int32_t b200lp_pw_wgrad(const float* dy, const float* x, const float* in_scale, const float* in_shift, int32_t in_relu6,
+                        float* dw, int32_t accumulate, float* workspace, int64_t workspace_bytes, int64_t M, int32_t Cin,
+                        int32_t Cout, void* stream);
+/* depthwise 3x3 (padding 1, stride 1 | 2) backward: data gradient dy [N,Ho,Wo,C] -> dx [N,H,W,C]; weight gradient
+ * dw [C][9] (+)= sum_p dy[p][c] * relu6(x[p (+) tap][c]*in_scale[c] + in_shift[c]) */
+int32_t b200lp_dw_dgrad(const float* dy, const float* w, float* dx, int32_t N, int32_t H, int32_t W, int32_t C,
+                        int32_t stride, void* stream);
+int64_t b200lp_dw_wgrad_workspace(int32_t N, int32_t H, int32_t W, int32_t C, int32_t stride);
+int32_t b200lp_dw_wgrad(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dw,
+                        int32_t accumulate, float* workspace, int64_t workspace_bytes, int32_t N, int32_t H, int32_t W,
+                        int32_t C, int32_t stride, void* stream);
+/* stem (3x3 stride-2 conv on the NCHW image) weight gradient: dw [32][27] (+)= sum_p dy[p][co] * patch(x)[p][27] */
+int64_t b200lp_mbv2_stem_wgrad_workspace(int32_t N, int32_t H, int32_t W);
+int32_t b200lp_mbv2_stem_wgrad(const float* x_nchw, const float* dy, float* dw, int32_t accumulate, float* workspace,
+                               int64_t workspace_bytes, int32_t N, int32_t H, int32_t W, void* stream);
 
 #ifdef __cplusplus
 }

@@ -840,9 +840,12 @@ def sgemm(a, b, trans_a=False, trans_b=False, acc_into=None, alpha=None, bias=No
     sbk, sbj = (1, b.shape[1]) if trans_b else (b.shape[1], 1)
     out = acc_into if acc_into is not None else torch.empty((m, n), dtype=torch.float32, device=a.device)
     assert out.numel() == m * n
+    need = lib.b200lp_sgemm_strided_workspace(m, n, k)
+    ws = _ws(need, a.device) if need > 0 else None
     with _timed("dense_small", flops=2.0 * m * n * k):
         L.check(lib.b200lp_sgemm_strided(L.ptr(a), sai, sak, L.ptr(b), sbk, sbj, L.ptr(out), L.ptr(alpha), L.ptr(bias), m, n,
-                                         k, int(acc_into is not None), L.stream_ptr()), "sgemm_strided")
+                                         k, int(acc_into is not None), L.ptr(ws), ws.numel() * 4 if ws is not None else 0,
+                                         L.stream_ptr()), "sgemm_strided")
     return out
 
 
@@ -949,3 +952,64 @@ def disc_head_bwd(feat, embed, w, inv_sigma, o, grad, need_feat=True, need_embed
                                      L.ptr(d_feat), L.ptr(d_embed), L.ptr(dw), L.ptr(ds), L.ptr(db), acc, b, h * wd, c,
                                      L.stream_ptr()), "disc_head_bwd")
     return d_feat, d_embed, dw, ds, db
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Pose encoder (MobileNetV2) backward — csrc/mobilenet_bwd.cu
+# ---------------------------------------------------------------------------------------------------------------------
+def transpose2d(src):
+    lib = L.load()
+    r, c = src.shape
+    dst = torch.empty((c, r), dtype=torch.float32, device=src.device)
+    L.check(lib.b200lp_transpose2d(L.ptr(src), L.ptr(dst), r, c, L.stream_ptr()), "transpose2d")
+    return dst
+
+
+def pw_wgrad(dy2d, x2d, in_scale=None, in_shift=None, in_relu6=False, acc_into=None):
+    """dw (Cout, Cin) = dy^T f(x), f = producer BatchNorm (+ReLU6) on load; added into `acc_into` when given."""
+    lib = L.load()
+    m, cout = dy2d.shape
+    cin = x2d.shape[1]
+    ws = _ws(lib.b200lp_pw_wgrad_workspace(m, cin, cout), dy2d.device)
+    dw = acc_into if acc_into is not None else torch.empty((cout, cin), dtype=torch.float32, device=dy2d.device)
+    assert dw.numel() == cout * cin
+    with _timed("pose_encoder", flops=2.0 * m * cin * cout):
+        L.check(lib.b200lp_pw_wgrad(L.ptr(dy2d), L.ptr(x2d), L.ptr(in_scale), L.ptr(in_shift), int(in_relu6), L.ptr(dw),
+                                    int(acc_into is not None), L.ptr(ws), ws.numel() * 4, m, cin, cout, L.stream_ptr()),
+                "pw_wgrad")
+    return dw
+
+
+def dw_dgrad(dy, w, in_hw, stride):
+    lib = L.load()
+    n, ho, wo, c = dy.shape
+    h, wd = in_hw
+    dx = torch.empty((n, h, wd, c), dtype=torch.float32, device=dy.device)
+    with _timed("pose_encoder", nbytes=4.0 * (dy.numel() + dx.numel())):
+        L.check(lib.b200lp_dw_dgrad(L.ptr(dy), L.ptr(w), L.ptr(dx), n, h, wd, c, stride, L.stream_ptr()), "dw_dgrad")
+    return dx
+
+
+def dw_wgrad(x, dy, in_scale, in_shift, stride, acc_into=None):
+    """dw (C, 1, 3, 3) = sum_p dy * relu6(x*scale+shift) at the 9 taps; added into `acc_into` when given."""
+    lib = L.load()
+    n, h, wd, c = x.shape
+    ws = _ws(lib.b200lp_dw_wgrad_workspace(n, h, wd, c, stride), x.device)
+    dw = acc_into if acc_into is not None else torch.empty((c, 1, 3, 3), dtype=torch.float32, device=x.device)
+    assert dw.numel() == c * 9
+    with _timed("pose_encoder", nbytes=4.0 * (x.numel() + dy.numel())):
+        L.check(lib.b200lp_dw_wgrad(L.ptr(x), L.ptr(in_scale), L.ptr(in_shift), L.ptr(dy), L.ptr(dw),
+                                    int(acc_into is not None), L.ptr(ws), ws.numel() * 4, n, h, wd, c, stride,
+                                    L.stream_ptr()), "dw_wgrad")
+    return dw
+
+
+def mbv2_stem_wgrad(x_nchw, dy, acc_into=None):
+    lib = L.load()
+    n, _, h, w = x_nchw.shape
+    ws = _ws(lib.b200lp_mbv2_stem_wgrad_workspace(n, h, w), dy.device)
+    dw = acc_into if acc_into is not None else torch.empty((32, 3, 3, 3), dtype=torch.float32, device=dy.device)
+    with _timed("pose_encoder", nbytes=4.0 * (x_nchw.numel() + dy.numel())):
+        L.check(lib.b200lp_mbv2_stem_wgrad(L.ptr(x_nchw), L.ptr(dy), L.ptr(dw), int(acc_into is not None), L.ptr(ws),
+                                           ws.numel() * 4, n, h, w, L.stream_ptr()), "mbv2_stem_wgrad")
+    return dw

@@ -130,7 +130,8 @@ SIGNATURES = {
     "b200lp_scatter_add2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b200lp_avgpool_fwd": (_I, [_P, _P, _I, _I, _I, _P]),
     "b200lp_avgpool_bwd": (_I, [_P, _P, _I, _I, _I, _P]),
-    "b200lp_sgemm_strided": (_I, [_P, _L, _L, _P, _L, _L, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_sgemm_strided_workspace": (_L, [_I, _I, _I]),
+    "b200lp_sgemm_strided": (_I, [_P, _L, _L, _P, _L, _L, _P, _P, _P, _I, _I, _I, _I, _P, _L, _P]),
     "b200lp_dice_workspace": (_L, [_I, _I]),
     "b200lp_dice_fwd": (_I, [_P, _P, _F, _P, _P, _P, _L, _I, _I, _I, _P]),
     "b200lp_dice_bwd": (_I, [_P, _P, _P, _P, _F, _P, _I, _I, _I, _P]),
@@ -140,6 +141,14 @@ SIGNATURES = {
     "b200lp_crop_bilinear_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "b200lp_disc_head_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "b200lp_disc_head_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200lp_transpose2d": (_I, [_P, _P, _I, _I, _P]),
+    "b200lp_pw_wgrad_workspace": (_L, [_L, _I, _I]),
+    "b200lp_pw_wgrad": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _L, _L, _I, _I, _P]),
+    "b200lp_dw_dgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200lp_dw_wgrad_workspace": (_L, [_I, _I, _I, _I, _I]),
+    "b200lp_dw_wgrad": (_I, [_P, _P, _P, _P, _P, _I, _P, _L, _I, _I, _I, _I, _I, _P]),
+    "b200lp_mbv2_stem_wgrad_workspace": (_L, [_I, _I, _I]),
+    "b200lp_mbv2_stem_wgrad": (_I, [_P, _P, _P, _I, _P, _L, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -14,7 +14,7 @@ CSRC = HERE / "csrc"
 LIB_DIR = HERE / "lib"
 LIB_PATH = LIB_DIR / "libb200lp.so"
 SOURCES = ["common.cu", "conv_igemm.cu", "conv_wgrad.cu", "elementwise.cu", "direct_conv.cu", "spectral_norm.cu",
-           "optim.cu", "mobilenet.cu", "encoder.cu", "losses.cu"]
+           "optim.cu", "mobilenet.cu", "encoder.cu", "losses.cu", "mobilenet_bwd.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -812,25 +812,29 @@ template <bool AK, bool BK>
 __global__ void __launch_bounds__(256)
 sgemm_strided_kernel(const float* __restrict__ A, long sai, long sak, const float* __restrict__ B, long sbk, long sbj,
                      float* __restrict__ Cm, const float* __restrict__ alpha_dev, const float* __restrict__ bias, int M, int N,
-                     int K, int accumulate) {
+                     int K, int accumulate, int k_per_split, float* __restrict__ ws) {
     __shared__ float As[16][65], Bs[16][65];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    // split-K (gridDim.z > 1): this block reduces k in [kb, ke) and stores raw partial sums to ws[z][M][N]; a second
+    // kernel merges them in a fixed order (a (8 x 13056) @ (13056 x 768) product would otherwise run on 12 blocks)
+    const int kb = blockIdx.z * k_per_split;
+    const int ke = min(kb + k_per_split, K);
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int k0 = kb; k0 < ke; k0 += 16) {
         for (int e = threadIdx.x; e < 16 * 64; e += 256) {
             const int kk = AK ? (e & 15) : (e >> 6), r = AK ? (e >> 4) : (e & 63);
             const int m = m0 + r, k = k0 + kk;
-            As[kk][r] = (m < M && k < K) ? __ldg(A + m * sai + k * sak) : 0.f;
+            As[kk][r] = (m < M && k < ke) ? __ldg(A + m * sai + k * sak) : 0.f;
         }
         for (int e = threadIdx.x; e < 16 * 64; e += 256) {
             const int kk = BK ? (e & 15) : (e >> 6), r = BK ? (e >> 4) : (e & 63);
             const int n = n0 + r, k = k0 + kk;
-            Bs[kk][r] = (n < N && k < K) ? __ldg(B + k * sbk + n * sbj) : 0.f;
+            Bs[kk][r] = (n < N && k < ke) ? __ldg(B + k * sbk + n * sbj) : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -856,10 +860,26 @@ sgemm_strided_kernel(const float* __restrict__ A, long sai, long sak, const floa
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
             if (n < N) {
-                float* o = Cm + static_cast<size_t>(m) * N + n;
-                *o = (accumulate ? *o : 0.f) + alpha * acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
+                if (gridDim.z > 1) {
+                    ws[(static_cast<size_t>(blockIdx.z) * M + m) * N + n] = acc[i][j];
+                } else {
+                    float* o = Cm + static_cast<size_t>(m) * N + n;
+                    *o = (accumulate ? *o : 0.f) + alpha * acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
+                }
             }
         }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sgemm_splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ Cm, const float* __restrict__ alpha_dev,
+                           const float* __restrict__ bias, int splits, int M, int N, int accumulate) {
+    const float alpha = alpha_dev ? __ldg(alpha_dev) : 1.f;
+    const int total = M * N;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+        float s_ = 0.f;
+        for (int z = 0; z < splits; ++z) s_ += __ldg(ws + static_cast<size_t>(z) * total + i);
+        Cm[i] = (accumulate ? Cm[i] : 0.f) + alpha * s_ + (bias ? __ldg(bias + i % N) : 0.f);
     }
 }
 
@@ -1204,18 +1224,47 @@ extern "C" int32_t b200lp_avgpool_bwd(const float* dy, float* dx, int32_t N, int
     return B200LP_OK;
 }
 
+static int sgemm_splits(int M, int N, int K) {
+    const long tiles = static_cast<long>((M + 63) / 64) * ((N + 63) / 64);
+    if (tiles >= 148 || K < 512) return 1;
+    long s_ = (2 * 148 + tiles - 1) / tiles;
+    if (s_ > K / 128) s_ = K / 128;
+    if (s_ > 128) s_ = 128;
+    return static_cast<int>(s_ < 1 ? 1 : s_);
+}
+
+extern "C" int64_t b200lp_sgemm_strided_workspace(int32_t M, int32_t N, int32_t K) {
+    if (M <= 0 || N <= 0 || K <= 0) return B200LP_EINVAL;
+    const int sp = sgemm_splits(M, N, K);
+    return sp > 1 ? static_cast<int64_t>(sp) * M * N * 4 : 0;
+}
+
 extern "C" int32_t b200lp_sgemm_strided(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj,
                                         float* C, const float* alpha_dev, const float* bias, int32_t M, int32_t N, int32_t K,
-                                        int32_t accumulate, void* stream) {
+                                        int32_t accumulate, float* workspace, int64_t workspace_bytes, void* stream) {
     B200LP_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "sgemm_strided: bad args");
-    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    int splits = sgemm_splits(M, N, K);
+    if (splits > 1 && (!workspace || workspace_bytes < static_cast<int64_t>(splits) * M * N * 4)) splits = 1;
+    int kps = (K + splits - 1) / splits;
+    kps = (kps + 15) / 16 * 16;
+    splits = (K + kps - 1) / kps;
+    dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
     cudaStream_t st = as_stream(stream);
     const bool ak = sak == 1, bk = sbk == 1 && sbj != 1;
-    if (ak && bk) sgemm_strided_kernel<true, true><<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, alpha_dev, bias, M, N, K, accumulate);
-    else if (ak) sgemm_strided_kernel<true, false><<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, alpha_dev, bias, M, N, K, accumulate);
-    else if (bk) sgemm_strided_kernel<false, true><<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, alpha_dev, bias, M, N, K, accumulate);
-    else sgemm_strided_kernel<false, false><<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, alpha_dev, bias, M, N, K, accumulate);
+#define B200LP_SGEMM(AKV, BKV) sgemm_strided_kernel<AKV, BKV><<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, alpha_dev, bias, M, N, K, accumulate, kps, workspace)
+    if (ak && bk) B200LP_SGEMM(true, true);
+    else if (ak) B200LP_SGEMM(true, false);
+    else if (bk) B200LP_SGEMM(false, true);
+    else B200LP_SGEMM(false, false);
+#undef B200LP_SGEMM
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
+    if (splits > 1) {
+        int blocks = (M * N + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        sgemm_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, C, alpha_dev, bias, splits, M, N, accumulate);
+        B200LP_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+    }
     return B200LP_OK;
 }

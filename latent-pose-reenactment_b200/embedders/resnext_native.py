@@ -109,8 +109,9 @@ def forward(net, x_nchw, need_bwd):
     r0 = K.conv_fwd(cols, _stem_packed(net.conv1), 1)
     del cols
     bn0 = _BN(net.bn1, K.col_stats(r0.view(-1, 64)) if _stats_needed(net.bn1) else None, n * h * w)
+    # fp32 copy unrounded like every block output below (the TF32 weight-gradient GEMM reads it as is)
     a_f32, a_split, idx = K.maxpool3x3s2_fwd(r0, bn0.scale, bn0.shift, want_f32=True, want_split=True,
-                                             want_idx=need_bwd, round_tf32=True)
+                                             want_idx=need_bwd, round_tf32=False)
     if need_bwd:
         saved.update(col=col, r0=r0, bn0=bn0, idx=idx, stem_hw=(h, w))
     h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1

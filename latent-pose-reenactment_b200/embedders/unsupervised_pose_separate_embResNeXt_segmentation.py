@@ -57,15 +57,16 @@ class Embedder(nn.Module):
     def get_pose_embedding(self, data_dict):
         x = data_dict['pose_input_rgbs'][:, 0]
         if self._native_pose_path(x):
-            # libb200lp schedule of the same MobileNetV2 (csrc/mobilenet.cu): ~125 launches instead of ~300
+            # libb200lp schedule of the same MobileNetV2 (csrc/mobilenet.cu, mobilenet_bwd.cu): forward, and — when the
+            # encoder's parameters are being trained (meta-training) — backward as one autograd node
             from embedders import mobilenet_native
-            data_dict['pose_embedding'] = mobilenet_native.forward(self.pose_encoder, x)
+            data_dict['pose_embedding'] = mobilenet_native.apply(self.pose_encoder, x)
         else:
             data_dict['pose_embedding'] = self.pose_encoder(x)
 
     def _native_identity_path(self, x):
         """Kernel schedule of the identity encoder (forward + backward) for float32 CUDA frames whose planes the
-        tensor-core kernels tile (powers of two, >= 64 x 64, an even number of frames)."""
+        tensor-core kernels tile (powers of two, >= 64 x 64, a multiple of 8 frames)."""
         if not x.is_cuda or x.dtype != torch.float32 or os.environ.get('B200LP_TORCH_IDENTITY_ENCODER'):
             return False
         n, _, h, w = x.shape
@@ -77,12 +78,11 @@ class Embedder(nn.Module):
         return self.__dict__['_native_id_ok']
 
     def _native_pose_path(self, x):
-        """The kernel schedule has no backward: it serves every call that needs no gradient through the encoder
-        (drive.py, fine-tuning with the encoder frozen, running-average forward passes)."""
+        """Kernel schedule of the pose encoder for float32 CUDA frames (any size the torchvision module takes)."""
         if not x.is_cuda or x.dtype != torch.float32 or os.environ.get('B200LP_TORCH_POSE_ENCODER'):
             return False
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.pose_encoder.parameters())):
-            return False
+        if torch.is_grad_enabled() and x.requires_grad:
+            return False          # no gradient w.r.t. the image is implemented (the reference never needs one)
         from embedders import mobilenet_native
         if self.__dict__.get('_native_ok') is None:
             self.__dict__['_native_ok'] = mobilenet_native.supported(self.pose_encoder)

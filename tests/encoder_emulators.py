@@ -183,8 +183,12 @@ def avgpool_bwd(dy, hw):
     return (dy / (hw[0] * hw[1]))[:, None, None, :].expand(n, hw[0], hw[1], c).contiguous()
 
 
-def sgemm(a, b, trans_a=False, trans_b=False, acc_into=None):
+def sgemm(a, b, trans_a=False, trans_b=False, acc_into=None, alpha=None, bias=None):
     r = (a.t() if trans_a else a) @ (b.t() if trans_b else b)
+    if alpha is not None:
+        r = r * alpha.reshape(()).to(r.dtype)
+    if bias is not None:
+        r = r + bias
     if acc_into is not None:
         acc_into.add_(r.view_as(acc_into))
         return acc_into
@@ -202,7 +206,77 @@ def pw_conv(x2d, weight, in_scale=None, in_shift=None, in_relu6=False, bias=None
     return (y, part) if want_stats else y
 
 
-EMULATED = ["col_stats", "bn_finalize", "bn_act", "bn_bwd", "gconv3x3_fwd", "gconv3x3_dgrad", "gconv3x3_wgrad",
+def mbv2_stem(x_nchw, weight, want_stats=False):
+    y = _nhwc(F.conv2d(x_nchw, weight.to(x_nchw.dtype), stride=2, padding=1))
+    return (y, col_stats(y.reshape(-1, 32))) if want_stats else y
+
+
+def dw_conv3x3(x, weight, in_scale, in_shift, stride, want_stats=False):
+    a = _nchw((x * in_scale + in_shift).clamp(0, 6))
+    y = _nhwc(F.conv2d(a, weight.to(x.dtype), stride=stride, padding=1, groups=x.shape[-1]))
+    return (y, col_stats(y.reshape(-1, y.shape[-1]))) if want_stats else y
+
+
+def bn_apply(x, scale, shift, residual=None, relu6=False):
+    y = x * scale + shift
+    if relu6:
+        y = y.clamp(0, 6)
+    return y + residual if residual is not None else y
+
+
+def bn_relu6_avgpool(x, scale, shift):
+    return (x * scale + shift).clamp(0, 6).mean((1, 2))
+
+
+def transpose2d(src):
+    return src.t().contiguous()
+
+
+def pw_wgrad(dy2d, x2d, in_scale=None, in_shift=None, in_relu6=False, acc_into=None):
+    a = x2d if in_scale is None else x2d * in_scale + in_shift
+    if in_scale is not None and in_relu6:
+        a = a.clamp(0, 6)
+    g = dy2d.t() @ a
+    if acc_into is not None:
+        acc_into.add_(g.view_as(acc_into))
+        return acc_into
+    return g.contiguous()
+
+
+def dw_dgrad(dy, w, in_hw, stride):
+    n, ho, wo, c = dy.shape
+    dx = torch.nn.grad.conv2d_input((n, c, in_hw[0], in_hw[1]), w.to(dy.dtype), _nchw(dy), stride=stride, padding=1, groups=c)
+    return _nhwc(dx)
+
+
+def dw_wgrad(x, dy, in_scale, in_shift, stride, acc_into=None):
+    c = x.shape[-1]
+    a = _nchw((x * in_scale + in_shift).clamp(0, 6))
+    g = torch.nn.grad.conv2d_weight(a, (c, 1, 3, 3), _nchw(dy), stride=stride, padding=1, groups=c)
+    if acc_into is not None:
+        acc_into.add_(g.view_as(acc_into))
+        return acc_into
+    return g.contiguous()
+
+
+def mbv2_stem_wgrad(x_nchw, dy, acc_into=None):
+    g = torch.nn.grad.conv2d_weight(x_nchw, (32, 3, 3, 3), _nchw(dy), stride=2, padding=1)
+    if acc_into is not None:
+        acc_into.add_(g.view_as(acc_into))
+        return acc_into
+    return g.contiguous()
+
+
+def bias_grad(dy, acc_into=None):
+    g = dy.reshape(-1, dy.shape[-1]).sum(0)
+    if acc_into is not None:
+        acc_into.add_(g)
+        return acc_into
+    return g
+
+
+EMULATED = ["mbv2_stem", "dw_conv3x3", "bn_apply", "bn_relu6_avgpool", "transpose2d", "pw_wgrad", "dw_dgrad", "dw_wgrad",
+            "mbv2_stem_wgrad", "bias_grad", "col_stats", "bn_finalize", "bn_act", "bn_bwd", "gconv3x3_fwd", "gconv3x3_dgrad", "gconv3x3_wgrad",
             "im2col7x7_s2", "maxpool3x3s2_fwd", "maxpool3x3s2_bwd", "subsample2", "scatter_add2", "avgpool_fwd",
             "avgpool_bwd", "sgemm", "pw_conv"]
 

@@ -11,7 +11,7 @@ TF32 operands cost on this very step: `profiles/r02_grad_error_study_torch_fp32_
 same error for torch's own kernels run on the B200 in true fp32 and with cuDNN / cuBLAS TF32 (torch's default for
 convolutions) — tools/grad_error_study.py.  torch-TF32 reaches 4.7e-2 on the deepest 4x4-plane discriminator weights
 (32 pixels per weight-gradient element at batch 2) and 1e-2..1.3e-1 on the generator; this path must stay within
-max(8e-3, 1.25 x torch-TF32's error) per parameter, and within 8e-3 for 90 % of them.
+max(1e-2, 1.25 x torch-TF32's error) per parameter, and within 8e-3 for 90 % of them.
 """
 import importlib
 import json
@@ -152,7 +152,7 @@ def test_full_size_training_step(full, gold):
     study = json.loads((ROOT / "profiles" / "r02_grad_error_study_torch_fp32_tf32.json").read_text())["torch_tf32"]
 
     def elem_tol(name):
-        return max(8e-3, 1.25 * study.get(name, {}).get("sub_rel_to_max", 0.0))
+        return max(1e-2, 1.25 * study.get(name, {}).get("sub_rel_to_max", 0.0))
     for k, p in G.named_parameters():
         ref_norm = gold["step.gradG.norms"][k]
         ref_sub = gold["step.gradG.sub." + k]

@@ -147,3 +147,66 @@ def test_embedder_plugin_torch_path_matches_reference_golden():
     with torch.no_grad():
         emb.get_pose_embedding(d)
     torch.testing.assert_close(d["pose_embedding"], gold["eval.pose_embedding"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("use_sinks", [False, True])
+def test_native_backward_matches_autograd(monkeypatch, use_sinks):
+    """The hand-scheduled BACKWARD of the pose encoder (BatchNorm backward with recomputed ReLU6 masks, depthwise / 1x1 /
+    stem weight gradients, residual wiring, gradient sinks) == torch autograd through the torchvision module, float64."""
+    import torchvision
+    import encoder_emulators
+    from b200lp import ops
+    from embedders import mobilenet_native
+    encoder_emulators.install(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "float", lambda self: self)
+    torch.manual_seed(5)
+    net = torchvision.models.mobilenet_v2(num_classes=24).double()
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.2)
+    net.classifier[0].p = 0.0
+    a, b = copy.deepcopy(net).train(), copy.deepcopy(net).train()
+    x = torch.rand(3, 3, 64, 64, dtype=torch.float64)
+    wgt = torch.randn(3, 24, dtype=torch.float64)
+    yb = b(x)
+    (yb * wgt).sum().backward()
+    ya = mobilenet_native.apply(a, x)
+    torch.testing.assert_close(ya, yb, rtol=1e-9, atol=1e-10)
+    if use_sinks:
+        base = {n_: torch.randn_like(p) for n_, p in a.named_parameters()}
+        bufs = {n_: base[n_].clone() for n_ in base}
+        with ops.direct_grads({p.data_ptr(): bufs[n_] for n_, p in a.named_parameters()}):
+            (ya * wgt).sum().backward()
+        got = {n_: bufs[n_] - base[n_] for n_ in base}
+        assert all(p.grad is None for p in a.parameters())
+    else:
+        (ya * wgt).sum().backward()
+        got = {n_: p.grad for n_, p in a.named_parameters()}
+    for (n_, _), q in zip(a.named_parameters(), b.parameters()):
+        scale = float(q.grad.abs().max()) + 1e-30
+        assert float((got[n_] - q.grad).abs().max()) <= 1e-7 * scale + 1e-12, (n_, float((got[n_] - q.grad).abs().max()), scale)
+
+
+def test_native_backward_with_dropout_matches_autograd(monkeypatch):
+    """With Dropout active the schedule draws the mask from torch's generator exactly where the module does (one
+    F.dropout call on the pooled features), so the same seed gives the same outputs and gradients."""
+    import torchvision
+    import encoder_emulators
+    from embedders import mobilenet_native
+    encoder_emulators.install(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "float", lambda self: self)
+    torch.manual_seed(6)
+    net = torchvision.models.mobilenet_v2(num_classes=16).double()
+    a, b = copy.deepcopy(net).train(), copy.deepcopy(net).train()
+    x = torch.rand(2, 3, 64, 64, dtype=torch.float64)
+    torch.manual_seed(77)
+    yb = b(x)
+    yb.square().sum().backward()
+    torch.manual_seed(77)
+    ya = mobilenet_native.apply(a, x)
+    ya.square().sum().backward()
+    torch.testing.assert_close(ya, yb, rtol=1e-9, atol=1e-10)
+    for (n_, p), q in zip(a.named_parameters(), b.parameters()):
+        scale = float(q.grad.abs().max()) + 1e-30
+        assert float((p.grad - q.grad).abs().max()) <= 1e-7 * scale + 1e-12, n_

@@ -1319,7 +1319,7 @@ def identity_encoder():
                 worst_p, worst_name = e, f"block {bi} {nm}"
         per_block.append(row)
     out.append({"case": "identity block-local backward (16 x 256x256, train): parameter gradients vs fp64 autograd on the same "
-                        "block input (relative L2)", "ok": worst_p < 1e-2, "max_abs": worst_p, "rel": worst_p,
+                        "block input (relative L2; TF32 data / weight gradient GEMMs)", "ok": worst_p < 1e-2, "max_abs": worst_p, "rel": worst_p,
                 "nan": worst_p != worst_p, "ref_max": 1.0, "worst": worst_name, "per_block": per_block})
     out.append({"case": "identity block-local backward: input gradients (relative L2)", "ok": worst_in < 1e-2,
                 "max_abs": worst_in, "rel": worst_in, "nan": worst_in != worst_in, "ref_max": 1.0})
@@ -1449,6 +1449,100 @@ def losses_kernels():
             (y2 * g).sum().backward()
         out.append(_cmp(f"linear sink w {m}x{k}x{n}", sinks[wt2.data_ptr()] - 1, w64.grad, 2e-5))
         out.append(_cmp(f"linear sink bias {m}x{k}x{n}", sinks[b2.data_ptr()] - 1, b64.grad, 2e-5))
+    return out
+
+
+@check
+def pose_bwd_kernels():
+    """MobileNetV2 backward kernels (transpose2d, pw_wgrad, dw_dgrad, dw_wgrad, mbv2_stem_wgrad) vs float64 torch, then the
+    whole pose-encoder schedule forward + backward vs the torchvision module in float64 (train mode, dropout off), gradient
+    sinks, and device time at the meta-training shape (8 x 256x256)."""
+    import copy
+    import torch
+    import torchvision
+    from b200lp import kernels as K
+    from b200lp import ops
+    from embedders import mobilenet_native
+    E = _emu()
+    out = []
+    dev = "cuda"
+    torch.manual_seed(31)
+    for (r, c) in [(256, 1280), (24, 144), (33, 7)]:
+        a = torch.randn(r, c, device=dev)
+        out.append(_cmp(f"transpose2d {r}x{c}", K.transpose2d(a), a.t().double(), 1e-7))
+    for (m, cin, cout) in [(8 * 128 * 128, 32, 16), (8 * 64 * 64, 144, 24), (512, 960, 320), (8, 1280, 256), (1000, 24, 144)]:
+        dy = torch.randn(m, cout, device=dev)
+        x = torch.randn(m, cin, device=dev)
+        sc = torch.rand(cin, device=dev) + 0.5
+        sh = torch.randn(cin, device=dev) * 0.3
+        ref = E.pw_wgrad(dy.double(), x.double(), sc.double(), sh.double(), True)
+        out.append(_cmp(f"pw_wgrad relu6 M{m} {cin}->{cout}", K.pw_wgrad(dy, x, sc, sh, True), ref, 3e-5))
+        base = torch.randn(cout, cin, device=dev)
+        acc = base.clone()
+        K.pw_wgrad(dy, x, acc_into=acc)
+        out.append(_cmp(f"pw_wgrad plain(acc) M{m} {cin}->{cout}", acc - base, dy.double().t() @ x.double(), 3e-5))
+    for (n, h, w, c, stride) in [(2, 16, 16, 32, 1), (2, 16, 16, 96, 2), (3, 9, 7, 24, 1), (1, 9, 7, 144, 2), (2, 8, 8, 960, 1)]:
+        x = torch.randn(n, h, w, c, device=dev)
+        wt = torch.randn(c, 1, 3, 3, device=dev) * 0.3
+        sc = torch.rand(c, device=dev) + 0.5
+        sh = torch.randn(c, device=dev) * 0.3
+        ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+        dy = torch.randn(n, ho, wo, c, device=dev)
+        tag = f"N{n} {h}x{w} C{c} s{stride}"
+        out.append(_cmp(f"dw_dgrad {tag}", K.dw_dgrad(dy, wt, (h, w), stride), E.dw_dgrad(dy.double(), wt.double(), (h, w), stride), 1e-5))
+        out.append(_cmp(f"dw_wgrad {tag}", K.dw_wgrad(x, dy, sc, sh, stride),
+                        E.dw_wgrad(x.double(), dy.double(), sc.double(), sh.double(), stride), 3e-5))
+    for (n, h, w) in [(2, 32, 32), (3, 18, 14)]:
+        x = torch.rand(n, 3, h, w, device=dev)
+        dy = torch.randn(n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 32, device=dev)
+        out.append(_cmp(f"mbv2_stem_wgrad N{n} {h}x{w}", K.mbv2_stem_wgrad(x, dy), E.mbv2_stem_wgrad(x.double(), dy.double()), 3e-5))
+    # whole encoder
+    net = torchvision.models.mobilenet_v2(num_classes=256)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.2)
+    net.classifier[0].p = 0.0
+    for (n, s) in ((8, 128), (3, 64)):
+        a = copy.deepcopy(net).to(dev).train()
+        b = copy.deepcopy(net).double().to(dev).train()
+        x = torch.rand(n, 3, s, s, device=dev)
+        wgt = torch.randn(n, 256, device=dev)
+        ya = mobilenet_native.apply(a, x)
+        (ya * wgt).sum().backward()
+        yb = b(x.double())
+        (yb * wgt.double()).sum().backward()
+        torch.cuda.synchronize()
+        out.append(_cmp(f"pose embeddings train N{n} {s}x{s}", ya, yb, 2e-4))
+        rels = sorted((float((p.grad.double() - q.grad).norm() / (q.grad.norm() + 1e-30)), nm)
+                      for (nm, p), q in zip(a.named_parameters(), b.parameters()))
+        out.append({"case": f"pose parameter gradients (relative L2) train N{n} {s}x{s}", "ok": rels[-1][0] < 2e-2,
+                    "max_abs": rels[-1][0], "rel": rels[-1][0], "nan": rels[-1][0] != rels[-1][0], "ref_max": 1.0,
+                    "worst": rels[-1][1], "median": rels[len(rels) // 2][0]})
+        a2 = copy.deepcopy(net).to(dev).train()
+        bufs = {nm: torch.zeros_like(p) for nm, p in a2.named_parameters()}
+        with ops.direct_grads({p.data_ptr(): bufs[nm] for nm, p in a2.named_parameters()}):
+            y2 = mobilenet_native.apply(a2, x)
+            (y2 * wgt).sum().backward()
+        torch.cuda.synchronize()
+        worst = max(float((bufs[nm] - p.grad).abs().max() / (p.grad.abs().max() + 1e-30)) for nm, p in a.named_parameters())
+        out.append({"case": f"pose gradient sinks == autograd path N{n} {s}x{s}", "ok": worst < 1e-5, "max_abs": worst,
+                    "rel": worst, "nan": worst != worst, "ref_max": 1.0})
+    a = copy.deepcopy(net).to(dev).train()
+    x = torch.rand(8, 3, 256, 256, device=dev)
+    wgt = torch.randn(8, 256, device=dev)
+
+    def step_native():
+        (mobilenet_native.apply(a, x) * wgt).sum().backward()
+
+    def step_torch():
+        (a(x) * wgt).sum().backward()
+
+    rec = {"case": "timing pose encoder fwd+bwd 8 x 256x256 (us)", "ok": True, "max_abs": 0.0, "rel": 0.0, "nan": False,
+           "ref_max": 0.0}
+    rec["native_us"] = round(_time_us(step_native, reps=5, warm=2), 0)
+    rec["torch_cudnn_us"] = round(_time_us(step_torch, reps=5, warm=2), 0)
+    out.append(rec)
     return out
 
 
