@@ -363,7 +363,7 @@ def kernel_family(name):
     base = name.split("b200lp::", 1)[1].split("(", 1)[0]
     m = re.match(r"(conv_igemm_kernel|conv_halo_kernel|conv_halo2_kernel)<(.*)>", base)
     if m:
-        mode = m.group(2).split(",")[-1].strip().rstrip(">")
+        mode = m.group(2).split(",")[-1].replace("(int)", "").strip().rstrip(">")      # ncu prints `(int)1`
         return "conv_igemm_bf16x3" if mode.startswith("1") else "conv_igemm_tf32"
     base = base.split("<", 1)[0]
     table = (("splitk_epilogue", "conv_splitk_epilogue"), ("conv_wgrad_tf32", "conv_wgrad_tf32"), ("wgrad_", "wgrad_reduce"),

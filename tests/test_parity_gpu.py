@@ -324,3 +324,35 @@ def test_pose_encoder_native_vs_reference_golden():
     assert rel_err(torch.cat([m.running_mean for m in bns]), gold["train.running_mean"]) < 1e-4
     assert rel_err(torch.cat([m.running_var for m in bns]), gold["train.running_var"]) < 1e-4
     assert int(bns[0].num_batches_tracked) == gold["train.num_batches_tracked"] == 1
+
+
+def test_pose_encoder_train_mode_with_dropout_at_bench_shape():
+    """Train mode at the benchmark's shape (8 x 256x256) WITH the classifier's Dropout(0.2) active: the schedule draws the
+    mask with the same torch op, on the same (N, 1280) shape, from the same CUDA generator state as the torchvision
+    module — so with equal seeds outputs and parameter gradients must agree (fp32 both sides; the reference embedder's
+    pose path is exactly this torchvision module, embedders/unsupervised_pose_separate_embResNeXt_segmentation.py:28,56-58)."""
+    import copy
+    import torchvision
+    from embedders import mobilenet_native
+    torch.manual_seed(3)
+    net = torchvision.models.mobilenet_v2(num_classes=256)
+    net.load_state_dict(synth.pose_encoder_state_dict(256, seed=7))
+    a, b = copy.deepcopy(net).to(DEV).train(), copy.deepcopy(net).to(DEV).train()
+    x = synth.pose_inputs(batch=8, image_size=256, seed=8)[:, 0].to(DEV)
+    wgt = torch.randn(8, 256, device=DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False           # true-fp32 torch reference
+    try:
+        torch.manual_seed(1234)
+        yb = b(x)
+        (yb * wgt).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    torch.manual_seed(1234)
+    ya = mobilenet_native.apply(a, x)
+    (ya * wgt).sum().backward()
+    assert float((ya - yb).abs().max()) <= 2e-4 * float(yb.abs().max())
+    assert float((ya == 0).float().mean()) < 0.5         # dropout really was active on both sides
+    gmax = max(float(q.grad.norm()) for q in b.parameters())
+    rels = sorted(float((p.grad - q.grad).norm() / (q.grad.norm() + 1e-6 * gmax)) for p, q in zip(a.parameters(), b.parameters()))
+    assert rels[len(rels) // 2] < 2e-3 and rels[-1] < 5e-2, (rels[len(rels) // 2], rels[-1])
