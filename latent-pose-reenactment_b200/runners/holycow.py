@@ -293,8 +293,21 @@ def train_step(training_module, data_dict, target_dict, optimizer_G, optimizer_D
     bucket_G.zero()
     with ops.direct_grads(bucket_G.sinks()):      # conv weight / bias gradients are accumulated in place by the kernels
         loss_G.backward(retain_graph=True)
-    bucket_G.all_reduce()
-    optimizer_G.step()
+    # The generator-side exchange and update (NCCL all-reduce of the E+G bucket, fused Adam + EMA, weight re-packing) touch
+    # only E / G parameters, their gradients and optimizer state; the discriminator's backward reads only D weights and
+    # saved activations.  So the two run CONCURRENTLY: the first on a side stream forked here, the second on the main
+    # stream; they join before the running-average buffers are copied.  (Captured as a fork / join inside the CUDA graph.)
+    overlap = bool(losses_D_dict) and bucket_G.flat.is_cuda and not os.environ.get('B200LP_NO_OVERLAP')
+    if overlap:
+        main = torch.cuda.current_stream()
+        side = _side_stream(bucket_G.flat.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            bucket_G.all_reduce()
+            optimizer_G.step()
+    else:
+        bucket_G.all_reduce()
+        optimizer_G.step()
 
     if losses_D_dict:
         bucket_D.zero()
@@ -302,9 +315,21 @@ def train_step(training_module, data_dict, target_dict, optimizer_G, optimizer_D
             loss_D.backward()
         bucket_D.all_reduce()
         optimizer_D.step()
+    if overlap:
+        main.wait_stream(side)
 
     training_module.update_running_average(alpha)
     return all_data_dict, losses_G_dict, losses_D_dict
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
 
 
 class GraphedTrainStep:
