@@ -478,75 +478,75 @@ gconv3x3_dgrad_s2_kernel(const float* __restrict__ dy, const float* __restrict__
 }
 
 // weight gradient: dW[g*CPG+co][ci][tap] = sum_{n,ho,wo} dy[n,ho,wo,g*CPG+co] * f(x[n, ho*s+kh-1, wo*s+kw-1, g*CPG+ci]).
-// A thread owns (group, 2 output channels, 4 input channels, ONE filter row kh) = 24 accumulators and walks the pixels of
-// its chunk two at a time with all eight loads (2 x (dy pair + three taps of x)) issued before the first use — the first
-// version (72 accumulators, a branch per tap) serialised on the L2 latency at 8 warps per SM: 1.2 ms per layer.  Partial
-// sums go to ws[chunk][tap][co_abs][ci] (16-byte stores), merged in a fixed order by the reduce kernel.
-// block = TS owner threads x (256 / TS) pixel lanes;  TS = min(256, 3*C*CPG/8) (a multiple of 3*CPG/4... of 32 here);
-// grid = (chunks, 3*C*CPG/8 / TS)
+// A thread owns (group, 4 output channels, 4 input channels, ONE filter row kh) = 48 accumulators and walks whole output
+// ROWS of its chunk: the (n, ho) decomposition and the input-row test happen once per row, the inner loop over wo has no
+// divisions and keeps 8 loads (2 pixels x (dy quad + three taps of x)) in flight.  (Earlier versions: 72 accumulators with
+// a branch per tap serialised on the L2 latency — 1.2 ms per layer; per-pixel index arithmetic — 0.32 ms.)
+// Partial sums go to ws[chunk][tap][co_abs][ci] (16-byte stores), merged in a fixed order by the reduce kernels.
+// block = TS owner threads x (256 / TS) pixel lanes;  grid = (row chunks, owners / TS)
 template <int CPG>
 __global__ void __launch_bounds__(256)
 gconv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, const float* __restrict__ in_shift,
                       const float* __restrict__ dy, float* __restrict__ ws, int N, int H, int W, int C, int stride, int Ho,
-                      int Wo, int pix_per_chunk, int TS) {
-    extern __shared__ float4 red4[];                  // [lanes-1][TS][6] float4 for the cross-lane merge
+                      int Wo, int rows_per_chunk, int TS) {
+    extern __shared__ float4 red4[];                  // [lanes-1][TS][12] float4 for the cross-lane merge
     const int t = threadIdx.x % TS, lanes = blockDim.x / TS, ln = threadIdx.x / TS;
-    const int owner = blockIdx.y * TS + t;            // (g, co2, ci4, kh): kh fastest, then ci4
+    const int owner = blockIdx.y * TS + t;            // (g, co4, ci4, kh): kh fastest, then ci4
     const int kh = owner % 3;
     const int ci4 = (owner / 3) % (CPG / 4);
-    const int co2 = (owner / (3 * (CPG / 4))) % (CPG / 2);
-    const int g = owner / (3 * (CPG / 4) * (CPG / 2));
-    const int cin = g * CPG + ci4 * 4, cout = g * CPG + co2 * 2;
+    const int co4 = (owner / (3 * (CPG / 4))) % (CPG / 4);
+    const int g = owner / (3 * (CPG / 4) * (CPG / 4));
+    const int cin = g * CPG + ci4 * 4, cout = g * CPG + co4 * 4;
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (in_scale) { sc = ldg4(in_scale + cin); sh = ldg4(in_shift + cin); }
-    float4 acc[2][3];
+    const bool act = in_scale != nullptr;
+    if (act) { sc = ldg4(in_scale + cin); sh = ldg4(in_shift + cin); }
+    float4 acc[4][3];
 #pragma unroll
-    for (int c = 0; c < 2; ++c)
+    for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int k = 0; k < 3; ++k) acc[c][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const unsigned P = static_cast<unsigned>(N) * Ho * Wo;             // < 2^31 (host check): 32-bit index math —
-    const unsigned p0 = blockIdx.x * static_cast<unsigned>(pix_per_chunk);   // 64-bit divisions cost ~100 instructions each
-    const unsigned p1 = min(p0 + static_cast<unsigned>(pix_per_chunk), P);
-    const bool act = in_scale != nullptr;
-    for (unsigned pb = p0 + ln; pb < p1; pb += 2u * lanes) {
-        float2 d[2];
-        float4 v[2][3];
-        bool ok[2][3];
+    const int rows_total = N * Ho;
+    const int r0 = blockIdx.x * rows_per_chunk;
+    const int r1 = min(r0 + rows_per_chunk, rows_total);
+    for (int row = r0; row < r1; ++row) {
+        const int n = row / Ho, ho = row - n * Ho;
+        const int hi = ho * stride + kh - 1;
+        if (hi < 0 || hi >= H) continue;              // this filter row reads padding for the whole output row
+        const float* xrow = x + (static_cast<size_t>(n * H + hi) * W) * C + cin;
+        const float* dyrow = dy + (static_cast<size_t>(row) * Wo) * C + cout;
+        for (int wb = ln * 2; wb < Wo; wb += 2 * lanes) {
+            float4 d[2], v[2][3];
+            bool ok[2][3];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const unsigned p = pb + static_cast<unsigned>(u) * lanes;
-            const bool pv = p < p1;
-            const unsigned pp = pv ? p : p0;
-            const int wo = static_cast<int>(pp % static_cast<unsigned>(Wo));
-            const unsigned t2 = pp / static_cast<unsigned>(Wo);
-            const int ho = static_cast<int>(t2 % static_cast<unsigned>(Ho));
-            const int n = static_cast<int>(t2 / static_cast<unsigned>(Ho));
-            const int hi = ho * stride + kh - 1;
-            const bool hok = pv && hi >= 0 && hi < H;
-            d[u] = __ldg(reinterpret_cast<const float2*>(dy + static_cast<size_t>(pp) * C + cout));
-            const size_t rowbase = static_cast<size_t>(n * H + (hok ? hi : 0)) * W;
+            for (int u = 0; u < 2; ++u) {
+                const int wo = wb + u;
+                const bool pv = wo < Wo;
+                d[u] = ldg4(dyrow + static_cast<size_t>(pv ? wo : wb) * C);
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const int wi = wo * stride + kw - 1;
-                const bool in = hok && wi >= 0 && wi < W;
-                ok[u][kw] = in;
-                v[u][kw] = ldg4(x + (rowbase + (in ? wi : 0)) * C + cin);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                if (!ok[u][kw]) continue;                 // zero padding applies to the activation, not to the raw input
-                float4 a = v[u][kw];
-                if (act) {
-                    a.x = fmaxf(a.x * sc.x + sh.x, 0.f); a.y = fmaxf(a.y * sc.y + sh.y, 0.f);
-                    a.z = fmaxf(a.z * sc.z + sh.z, 0.f); a.w = fmaxf(a.w * sc.w + sh.w, 0.f);
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int wi = wo * stride + kw - 1;
+                    const bool in = pv && wi >= 0 && wi < W;
+                    ok[u][kw] = in;
+                    v[u][kw] = ldg4(xrow + static_cast<size_t>(in ? wi : 0) * C);
                 }
-                float4& a0 = acc[0][kw];
-                float4& a1 = acc[1][kw];
-                a0.x = fmaf(d[u].x, a.x, a0.x); a0.y = fmaf(d[u].x, a.y, a0.y); a0.z = fmaf(d[u].x, a.z, a0.z); a0.w = fmaf(d[u].x, a.w, a0.w);
-                a1.x = fmaf(d[u].y, a.x, a1.x); a1.y = fmaf(d[u].y, a.y, a1.y); a1.z = fmaf(d[u].y, a.z, a1.z); a1.w = fmaf(d[u].y, a.w, a1.w);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float dd[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    if (!ok[u][kw]) continue;             // zero padding applies to the activation, not to the raw input
+                    float4 a = v[u][kw];
+                    if (act) {
+                        a.x = fmaxf(a.x * sc.x + sh.x, 0.f); a.y = fmaxf(a.y * sc.y + sh.y, 0.f);
+                        a.z = fmaxf(a.z * sc.z + sh.z, 0.f); a.w = fmaxf(a.w * sc.w + sh.w, 0.f);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float4& o = acc[c][kw];
+                        o.x = fmaf(dd[c], a.x, o.x); o.y = fmaf(dd[c], a.y, o.y); o.z = fmaf(dd[c], a.z, o.z); o.w = fmaf(dd[c], a.w, o.w);
+                    }
+                }
             }
         }
     }
@@ -554,18 +554,18 @@ gconv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ in_
     if (lanes > 1) {
         if (ln > 0) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
+            for (int c = 0; c < 4; ++c)
 #pragma unroll
-                for (int k = 0; k < 3; ++k) red4[(static_cast<size_t>(ln - 1) * TS + t) * 6 + c * 3 + k] = acc[c][k];
+                for (int k = 0; k < 3; ++k) red4[(static_cast<size_t>(ln - 1) * TS + t) * 12 + c * 3 + k] = acc[c][k];
         }
         __syncthreads();
         if (ln == 0) {
             for (int l = 1; l < lanes; ++l)
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
+                for (int c = 0; c < 4; ++c)
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const float4 o = red4[(static_cast<size_t>(l - 1) * TS + t) * 6 + c * 3 + k];
+                        const float4 o = red4[(static_cast<size_t>(l - 1) * TS + t) * 12 + c * 3 + k];
                         acc[c][k].x += o.x; acc[c][k].y += o.y; acc[c][k].z += o.z; acc[c][k].w += o.w;
                     }
         }
@@ -573,7 +573,7 @@ gconv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ in_
     if (ln == 0) {
         float* base = ws + static_cast<size_t>(blockIdx.x) * 9 * C * CPG;
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int k = 0; k < 3; ++k)
                 *reinterpret_cast<float4*>(base + (static_cast<size_t>(kh * 3 + k) * C + cout + c) * CPG + ci4 * 4) = acc[c][k];
@@ -890,19 +890,19 @@ static int ew_blocks(long total4) {      // callers keep total4 < 2^31 (the kern
     return static_cast<int>(blocks);
 }
 
-// pixel chunks of the grouped weight gradient: about 148 x 16 blocks in total, >= 32 pixels per chunk
-static int gconv_wgrad_plan(long P, int C, int cpg, int* pix_per_chunk, int* TS, int* slices) {
-    const int owners = 3 * (C * cpg / 8);           // (group, output-channel pair, input-channel quad, filter row)
-    int ts = owners < 256 ? owners : 256;           // 3 * 32 * cpg^2 / 8 owners for 32 groups: 192 for cpg = 4, k * 256 above
-    while (owners % ts) --ts;                       // other group counts: the largest divisor <= 256
+// row chunks of the grouped weight gradient: about 148 x 8 blocks in total, whole output rows per chunk
+static int gconv_wgrad_plan(int rows, int C, int cpg, int* rows_per_chunk, int* TS, int* slices) {
+    const int owners = 3 * (C * cpg / 16);          // (group, output-channel quad, input-channel quad, filter row)
+    int ts = owners < 256 ? owners : 256;
+    while (owners % ts) --ts;                       // the largest divisor <= 256 (96 / 192 / 256 / 256 for 32 groups)
     *TS = ts;
     *slices = owners / ts;
-    long chunks = (148L * 16) / *slices;
+    long chunks = (148L * 8) / *slices;
     if (chunks < 1) chunks = 1;
-    long ppc = (P + chunks - 1) / chunks;
-    if (ppc < 32) ppc = 32;
-    *pix_per_chunk = static_cast<int>(ppc);
-    return static_cast<int>((P + ppc - 1) / ppc);
+    int rpc = static_cast<int>((rows + chunks - 1) / chunks);
+    if (rpc < 1) rpc = 1;
+    *rows_per_chunk = rpc;
+    return (rows + rpc - 1) / rpc;
 }
 
 template <int CPG, int STRIDE, bool TR>
@@ -1087,7 +1087,7 @@ extern "C" int64_t b200lp_gconv3x3_wgrad_workspace(int32_t N, int32_t H, int32_t
         return B200LP_EINVAL;
     const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
     int ppc, ts, slices;
-    const int chunks = gconv_wgrad_plan(static_cast<long>(N) * Ho * Wo, C, cpg, &ppc, &ts, &slices);
+    const int chunks = gconv_wgrad_plan(N * Ho, C, cpg, &ppc, &ts, &slices);
     const int cg = chunks < 32 ? chunks : 32;
     return static_cast<int64_t>(chunks + cg) * 9 * C * cpg * 4;       // chunk partials + the stage-1 rows of the reduction
 }
@@ -1097,7 +1097,7 @@ static int launch_gconv_wgrad(const float* x, const float* sc, const float* sh, 
                               int W, int C, int stride, int Ho, int Wo, int chunks, int ppc, int ts, int slices,
                               cudaStream_t st) {
     const int lanes = 256 / ts;
-    const int bytes = (lanes > 1 ? (lanes - 1) * ts * 6 * 16 : 16);
+    const int bytes = (lanes > 1 ? (lanes - 1) * ts * 12 * 16 : 16);
     static bool attr_set = false;
     if (!attr_set) {
         B200LP_CHECK_CUDA(cudaFuncSetAttribute(gconv3x3_wgrad_kernel<CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
@@ -1122,7 +1122,7 @@ extern "C" int32_t b200lp_gconv3x3_wgrad(const float* x, const float* in_scale, 
     B200LP_REQUIRE(static_cast<long>(N) * H * W < (1L << 31), "gconv3x3_wgrad: more than 2^31 pixels");
     const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
     int ppc, ts, slices;
-    const int chunks = gconv_wgrad_plan(static_cast<long>(N) * Ho * Wo, C, cpg, &ppc, &ts, &slices);
+    const int chunks = gconv_wgrad_plan(N * Ho, C, cpg, &ppc, &ts, &slices);
     cudaStream_t st = as_stream(stream);
     int r;
     if (cpg == 4) r = launch_gconv_wgrad<4>(x, in_scale, in_shift, dy, workspace, N, H, W, C, stride, Ho, Wo, chunks, ppc, ts, slices, st);
@@ -1224,6 +1224,81 @@ extern "C" int32_t b200lp_avgpool_bwd(const float* dy, float* dx, int32_t N, int
     return B200LP_OK;
 }
 
+// M <= 8 rows (the batch of a projector / classifier layer): one thread per output column keeps the 8 row sums, the A rows
+// of a 128-wide k chunk sit in shared memory (broadcast reads), B streams once — the 64 x 64 tile kernel above spends 8x
+// the FMAs and A traffic on rows that do not exist.  BK: B(k, n) = B[n*ldb + k] (k contiguous), else B[k*ldb + n].
+// grid = (column blocks of 256, k splits); splits > 1: raw partial sums to ws[z][M][N] (merged by the reduce kernel).
+template <bool BK>
+__global__ void __launch_bounds__(256)
+sgemm_skinny_kernel(const float* __restrict__ A, long lda, const float* __restrict__ B, long ldb, float* __restrict__ Cm,
+                    const float* __restrict__ alpha_dev, const float* __restrict__ bias, int M, int N, int K, int accumulate,
+                    int k_per_split, float* __restrict__ ws) {
+    __shared__ float As[8][128];
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    const int kb = blockIdx.y * k_per_split;
+    const int ke = min(kb + k_per_split, K);
+    float acc[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) acc[m] = 0.f;
+    for (int k0 = kb; k0 < ke; k0 += 128) {
+        for (int e = threadIdx.x; e < 8 * 128; e += 256) {
+            const int m = e >> 7, kk = e & 127;
+            As[m][kk] = (m < M && k0 + kk < ke) ? __ldg(A + m * lda + k0 + kk) : 0.f;
+        }
+        __syncthreads();
+        if (n < N) {
+            const int kn = min(128, ke - k0);
+            if (BK) {
+                const float* bp = B + static_cast<size_t>(n) * ldb + k0;
+                const bool vec = ((reinterpret_cast<uintptr_t>(bp) & 15) == 0);
+                int kk = 0;
+                if (vec)
+                    for (; kk + 4 <= kn; kk += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + kk));
+#pragma unroll
+                        for (int m = 0; m < 8; ++m)
+                            acc[m] = fmaf(As[m][kk], b4.x, fmaf(As[m][kk + 1], b4.y, fmaf(As[m][kk + 2], b4.z, fmaf(As[m][kk + 3], b4.w, acc[m]))));
+                    }
+                for (; kk < kn; ++kk) {
+                    const float b = __ldg(bp + kk);
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) acc[m] = fmaf(As[m][kk], b, acc[m]);
+                }
+            } else {
+                const float* bp = B + static_cast<size_t>(k0) * ldb + n;
+#pragma unroll 4
+                for (int kk = 0; kk < kn; ++kk) {
+                    const float b = __ldg(bp + static_cast<size_t>(kk) * ldb);
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) acc[m] = fmaf(As[m][kk], b, acc[m]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (n >= N) return;
+    const float alpha = alpha_dev ? __ldg(alpha_dev) : 1.f;
+    for (int m = 0; m < M; ++m) {
+        if (gridDim.y > 1) {
+            ws[(static_cast<size_t>(blockIdx.y) * M + m) * N + n] = acc[m];
+        } else {
+            float* o = Cm + static_cast<size_t>(m) * N + n;
+            *o = (accumulate ? *o : 0.f) + alpha * acc[m] + (bias ? __ldg(bias + n) : 0.f);
+        }
+    }
+}
+
+static int skinny_splits(int N, int K, int* k_per_split) {
+    const int nb = (N + 255) / 256;
+    int splits = (2 * 148 + nb - 1) / nb;
+    const int kchunks = (K + 127) / 128;
+    if (splits > kchunks) splits = kchunks;
+    if (splits < 1) splits = 1;
+    int kps = (kchunks + splits - 1) / splits * 128;
+    *k_per_split = kps;
+    return (K + kps - 1) / kps;
+}
+
 static int sgemm_splits(int M, int N, int K) {
     const long tiles = static_cast<long>((M + 63) / 64) * ((N + 63) / 64);
     if (tiles >= 148 || K < 512) return 1;
@@ -1235,7 +1310,12 @@ static int sgemm_splits(int M, int N, int K) {
 
 extern "C" int64_t b200lp_sgemm_strided_workspace(int32_t M, int32_t N, int32_t K) {
     if (M <= 0 || N <= 0 || K <= 0) return B200LP_EINVAL;
-    const int sp = sgemm_splits(M, N, K);
+    int sp = sgemm_splits(M, N, K);
+    if (M <= 8) {
+        int kps;
+        const int sk = skinny_splits(N, K, &kps);
+        if (sk > sp) sp = sk;
+    }
     return sp > 1 ? static_cast<int64_t>(sp) * M * N * 4 : 0;
 }
 
@@ -1243,6 +1323,27 @@ extern "C" int32_t b200lp_sgemm_strided(const float* A, int64_t sai, int64_t sak
                                         float* C, const float* alpha_dev, const float* bias, int32_t M, int32_t N, int32_t K,
                                         int32_t accumulate, float* workspace, int64_t workspace_bytes, void* stream) {
     B200LP_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "sgemm_strided: bad args");
+    if (M <= 8 && sak == 1 && (sbk == 1 || sbj == 1)) {           // skinny path: A row-major, B contiguous along k or n
+        cudaStream_t st = as_stream(stream);
+        int kps;
+        int sp = skinny_splits(N, K, &kps);
+        if (sp > 1 && (!workspace || workspace_bytes < static_cast<int64_t>(sp) * M * N * 4)) { sp = 1; kps = (K + 127) / 128 * 128; }
+        dim3 grid((N + 255) / 256, sp);
+        if (sbk == 1 && sbj != 1)
+            sgemm_skinny_kernel<true><<<grid, 256, 0, st>>>(A, sai, B, sbj, C, alpha_dev, bias, M, N, K, accumulate, kps, workspace);
+        else
+            sgemm_skinny_kernel<false><<<grid, 256, 0, st>>>(A, sai, B, sbk, C, alpha_dev, bias, M, N, K, accumulate, kps, workspace);
+        B200LP_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+        if (sp > 1) {
+            int blocks = (M * N + 255) / 256;
+            if (blocks > 148 * 8) blocks = 148 * 8;
+            sgemm_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, C, alpha_dev, bias, sp, M, N, accumulate);
+            B200LP_CHECK_CUDA(cudaGetLastError());
+            count_launch();
+        }
+        return B200LP_OK;
+    }
     int splits = sgemm_splits(M, N, K);
     if (splits > 1 && (!workspace || workspace_bytes < static_cast<int64_t>(splits) * M * N * 4)) splits = 1;
     int kps = (K + splits - 1) / splits;
