@@ -1224,6 +1224,7 @@ extern "C" int32_t b200lp_avgpool_bwd(const float* dy, float* dx, int32_t N, int
     return B200LP_OK;
 }
 
+namespace b200lp {
 // M <= 8 rows (the batch of a projector / classifier layer): one thread per output column keeps the 8 row sums, the A rows
 // of a 128-wide k chunk sit in shared memory (broadcast reads), B streams once — the 64 x 64 tile kernel above spends 8x
 // the FMAs and A traffic on rows that do not exist.  BK: B(k, n) = B[n*ldb + k] (k contiguous), else B[k*ldb + n].
@@ -1287,6 +1288,8 @@ sgemm_skinny_kernel(const float* __restrict__ A, long lda, const float* __restri
         }
     }
 }
+
+}  // namespace b200lp
 
 static int skinny_splits(int N, int K, int* k_per_split) {
     const int nb = (N + 255) / 256;
