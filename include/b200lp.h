@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 17
+#define B200LP_ABI_VERSION 18
 
 #define B200LP_OK 0
 #define B200LP_EINVAL (-1)   /* bad shape / unsupported configuration */
@@ -76,6 +76,11 @@ typedef struct {
                                accumulators sharing every weight tile.  In the halo kernel `stages` is the depth of the
                                weight-tile ring and `a_stages` that of the slab ring.                               */
     int32_t a_stages;       /* 0 = auto (halo kernel only)                                                          */
+    int32_t grouped;        /* 1 = block-diagonal (grouped) 3x3 convolution, Cin == Cout: `wp` is
+                               [Cout][9][B] (B = 32 tf32 / 64 bf16x3, b200lp_pack_gconv_weight) and output channels
+                               [nB, (n+1)B) read input channels [nB, (n+1)B) only — torchvision ResNeXt's
+                               Conv2d(groups=32) with 4..32 channels per group as dense B x B blocks                 */
+    int32_t reserved0;
     float* workspace;       /* split-K partial sums; NULL = never split.  Size: b200lp_conv_fwd_workspace(args)      */
     int64_t workspace_bytes;
 } b200lp_conv_args;
@@ -103,6 +108,14 @@ int32_t b200lp_pack_conv_weight(const float* w_oihw, const float* scale, void* w
  * [chunk_off[c], chunk_off[c] + chunk_elems). */
 int32_t b200lp_pack_conv_weight_multi(const void* table, const int32_t* chunk_item, const int64_t* chunk_off,
                                       int32_t n_chunks, int64_t chunk_elems, void* stream);
+
+/* Grouped 3x3 weight w[C][cpg][3][3] (groups of cpg channels, cpg divides `block`; block = 32 for tf32, 64 for bf16x3)
+ * as block-diagonal dense tiles for b200lp_conv_fwd(grouped = 1):
+ *   transpose = 0:  wp[co][tap][j]     = w[co][ci - g*cpg][tap]    if ci = (co/block)*block + j lies in co's group g, else 0
+ *   transpose = 1:  wp[ci][8-tap][j]   = w[co][ci - g*cpg][tap]    with co = (ci/block)*block + j           (data-gradient)
+ * precision as in b200lp_pack_conv_weight. */
+int32_t b200lp_pack_gconv_weight(const float* w, void* wp, int32_t C, int32_t cpg, int32_t transpose, int32_t precision,
+                                 void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Spectral normalisation, batched over all weights of a network pass (3 launches instead of ~14 per weight).
@@ -155,7 +168,8 @@ typedef struct {
     int32_t kstep;    /* tuning: pixels per pipeline stage, 0 = auto, else 32 / 64    */
     int32_t stages;   /* tuning: smem ring depth, 0 = auto                            */
     int32_t splits;   /* tuning: split-K factor, 0 = auto (workspace must hold splits * |dw| floats) */
-    int32_t reserved;
+    int32_t grouped;  /* 0 = dense; cpg > 0: grouped 3x3 conv (Cin == Cout, groups of cpg channels) — only
+                         b200lp_gconv3x3_wgrad_tc accepts it */
 } b200lp_wgrad_args;
 
 int64_t b200lp_conv_wgrad_workspace(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize);
@@ -171,6 +185,19 @@ int32_t b200lp_conv_wgrad(const b200lp_wgrad_args* a, void* stream);
 int64_t b200lp_conv_wgrad_sn_acc_workspace(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize);
 int32_t b200lp_conv_wgrad_sn_acc(const b200lp_wgrad_args* a, const float* w, const float* inv_sigma, const float* u,
                                  const float* v, int32_t accumulate, void* stream);
+
+/* Weight gradient of a GROUPED 3x3 convolution (stride 1, padding 1) on tcgen05: per 32-channel block one
+ * [4 taps x 32 ci] x [32 co] TF32 GEMM over the pixels (the off-group products of the block are computed and dropped),
+ * split-K partial sums, then a deterministic reduction that keeps the block-diagonal entries:
+ *   dw[co][cig][tap] (+)= sum_{n,h,w} dy[n,h,w,co] * x[n,h+kh-1,w+kw-1, g(co)*cpg + cig]        (a->dw: [C][cpg][3][3])
+ * a->grouped = cpg, a->Cin == a->Cout == C, a->ksize == 3; tuning knobs 0.  Replaces autograd's backward-filter of
+ * torchvision ResNeXt's conv2 (embedders/unsupervised_pose_separate_embResNeXt_segmentation.py:27). */
+int64_t b200lp_gconv3x3_wgrad_tc_workspace(int32_t N, int32_t H, int32_t W, int32_t C);
+int32_t b200lp_gconv3x3_wgrad_tc(const b200lp_wgrad_args* a, int32_t accumulate, void* stream);
+
+/* out[n, 2i, 2j, c] = x[n, i, j, c], zero elsewhere (out is [N, 2H, 2W, C]): the gradient of a stride-2 convolution's
+ * output placed on the stride-1 grid, so that its data / weight gradients run through the stride-1 tensor-core kernels. */
+int32_t b200lp_zero_stuff2(const float* x, float* out, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Instance-norm statistics, AdaIN affine + ReLU (+ nearest 2x upsample)  — HBM-bound.

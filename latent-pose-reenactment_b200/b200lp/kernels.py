@@ -67,6 +67,22 @@ def pack_conv_weight(w_oihw, scale=None, transpose=False, precision=TF32, out=No
     return out
 
 
+def pack_gconv_weight(w, transpose=False, precision=TF32, out=None):
+    """Grouped 3x3 weight (C, cpg, 3, 3) -> block-diagonal dense tiles for conv_fwd(grouped=cpg): float32 (C, 9, 32)
+    [TF32] or bfloat16 (2, C, 9, 64) [BF16X3]; transpose = data-gradient layout (flipped taps, roles swapped)."""
+    lib = L.load()
+    c, cpg, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    shape = (c, 9, 32) if precision == TF32 else (2, c, 9, 64)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32 if precision == TF32 else torch.bfloat16, device=w.device)
+    assert tuple(out.shape) == shape and out.is_contiguous(), (out.shape, shape)
+    with _timed("pack_conv_weight", nbytes=4.0 * w.numel() + out.numel() * out.element_size()):
+        L.check(lib.b200lp_pack_gconv_weight(L.ptr(w.contiguous()), c_void_p(out.data_ptr()), c, cpg,
+                                             1 if transpose else 0, precision, L.stream_ptr()), "pack_gconv_weight")
+    return out
+
+
 PACK_CHUNK = 16384
 
 
@@ -94,9 +110,11 @@ def pack_conv_weight_multi(plan):
 
 
 def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False, round_tf32=False, block_n=0,
-             out=None, emit_split=False, stages=0, scale=None, ctas_per_sm=0, splits=0, variant=0, a_stages=0):
+             out=None, emit_split=False, stages=0, scale=None, ctas_per_sm=0, splits=0, variant=0, a_stages=0,
+             grouped=0):
     """x NHWC (N,H,W,Cin) float32 [TF32] or (2,N,H,W,Cin) bfloat16 (hi, lo) [BF16X3]; wp packed to match.
     `scale`: optional 1-element device tensor s, y = s * conv(x, wp) (+ bias ...).
+    `grouped` = channels per group (0 = dense): wp from pack_gconv_weight, (Cout, 9, 32) / (2, Cout, 9, 64).
     Returns y (N,H,W,Cout) float32, or (y, y_split) with y_split (2,N,H,W,Cout) bfloat16 when emit_split."""
     lib = L.load()
     split_in = x.dtype == torch.bfloat16
@@ -104,11 +122,13 @@ def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False
         assert x.dim() == 5 and wp.dtype == torch.bfloat16 and wp.dim() == 4, (x.shape, wp.shape)
         _, n, h, w, cin = x.shape
         cout = wp.shape[1]
-        assert wp.shape[2] == ksize * ksize and wp.shape[3] == cin, (wp.shape, ksize, cin)
+        assert wp.shape[2] == ksize * ksize and wp.shape[3] == (64 if grouped else cin), (wp.shape, ksize, cin)
     else:
         n, h, w, cin = x.shape
         cout = wp.shape[0]
-        assert wp.dtype == torch.float32 and wp.shape[1] == ksize * ksize and wp.shape[2] == cin, (wp.shape, ksize, cin)
+        assert wp.dtype == torch.float32 and wp.shape[1] == ksize * ksize and wp.shape[2] == (32 if grouped else cin), \
+            (wp.shape, ksize, cin)
+    kcin = grouped if grouped else cin          # algorithmic contraction length per tap
     y = out if out is not None else torch.empty((n, h, w, cout), dtype=torch.float32, device=x.device)
     y_split = torch.empty((2, n, h, w, cout), dtype=torch.bfloat16, device=x.device) if emit_split else None
     a = L.ConvArgs()
@@ -126,12 +146,13 @@ def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False
     a.precision = BF16X3 if split_in else TF32
     a.splits = splits
     a.variant, a.a_stages = variant, a_stages
+    a.grouped = 1 if grouped else 0
     need = lib.b200lp_conv_fwd_workspace(byref(a))
     if need > 0:                      # few-tile layer: split-K partial sums
         ws = _ws(need, x.device)
         a.workspace, a.workspace_bytes = L.ptr(ws), ws.numel() * 4
-    with _timed("conv_igemm_bf16x3" if split_in else "conv_igemm_tf32",
-                flops=2.0 * n * h * w * cin * cout * ksize * ksize):
+    with _timed("resnext_grouped" if grouped else ("conv_igemm_bf16x3" if split_in else "conv_igemm_tf32"),
+                flops=2.0 * n * h * w * kcin * cout * ksize * ksize):
         L.check(lib.b200lp_conv_fwd(byref(a), L.stream_ptr()), "conv_fwd")
     return (y, y_split) if emit_split else y
 
@@ -712,12 +733,64 @@ def gconv3x3_fwd(x, w, in_scale=None, in_shift=None, stride=1, want_stats=False)
     return (y, part) if want_stats else y
 
 
-def gconv3x3_dgrad(dy, w, in_hw, stride=1):
-    """dy (N,Ho,Wo,C) -> dx (N,H,W,C) with (H, W) = in_hw."""
+def _pow2(v):
+    return v >= 2 and (v & (v - 1)) == 0
+
+
+def gconv_tensor_cores(n, h, w, c, cpg):
+    """True when the grouped 3x3 gradients of this shape run on the tensor cores (block-diagonal 32-channel tiles):
+    power-of-two planes, 32-aligned channels, groups inside one block.  B200LP_GCONV_CUDA_CORES=1 forces the FP32 kernels."""
+    import os
+    if os.environ.get("B200LP_GCONV_CUDA_CORES"):
+        return False
+    return _pow2(h) and _pow2(w) and c % 32 == 0 and cpg in (1, 2, 4, 8, 16, 32) and n * h * w >= 64 and \
+        (h * w >= 64 or n % max(64 // (h * w), 1) == 0)
+
+
+def zero_stuff2(x):
+    """(N,H,W,C) -> (N,2H,2W,C) with x at the even positions, zeros elsewhere."""
+    lib = L.load()
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.float32, device=x.device)
+    with _timed("resnext", nbytes=4.0 * x.numel() + 4.0 * out.numel()):
+        L.check(lib.b200lp_zero_stuff2(L.ptr(x), L.ptr(out), n, h, w, c, L.stream_ptr()), "zero_stuff2")
+    return out
+
+
+def gconv3x3_wgrad_tc(x, dy, cpg, acc_into=None):
+    """dw (C, cpg, 3, 3) (+)= grouped weight gradient of a stride-1 3x3 conv on the TF32 tensor cores; x, dy (N,H,W,C)."""
+    lib = L.load()
+    n, h, wd, c = x.shape
+    assert dy.shape == x.shape, (dy.shape, x.shape)
+    nbytes = lib.b200lp_gconv3x3_wgrad_tc_workspace(n, h, wd, c)
+    if nbytes <= 0:
+        raise L.B200lpError(f"gconv3x3_wgrad_tc: unsupported shape {tuple(x.shape)}: {L.last_error()}")
+    ws = _ws(nbytes, x.device)
+    dw = acc_into if acc_into is not None else torch.empty((c, cpg, 3, 3), dtype=torch.float32, device=x.device)
+    assert tuple(dw.shape) == (c, cpg, 3, 3) and dw.is_contiguous()
+    a = L.WgradArgs()
+    a.x = L.ptr(x); a.dy = L.ptr(dy); a.dw = L.ptr(dw); a.workspace = L.ptr(ws)
+    a.workspace_bytes = ws.numel() * 4
+    a.N, a.H, a.W, a.Cin, a.Cout = n, h, wd, c, c
+    a.ksize = 3
+    a.scale = 1.0
+    a.grouped = cpg
+    with _timed("resnext_grouped", flops=2.0 * n * h * wd * c * cpg * 9):
+        L.check(lib.b200lp_gconv3x3_wgrad_tc(byref(a), int(acc_into is not None), L.stream_ptr()), "gconv3x3_wgrad_tc")
+    return dw
+
+
+def gconv3x3_dgrad(dy, w, in_hw, stride=1, packed=None):
+    """dy (N,Ho,Wo,C) -> dx (N,H,W,C) with (H, W) = in_hw.  `packed`: pack_gconv_weight(w, transpose=True) — then the
+    gradient runs on the TF32 tensor cores (stride 2: on the zero-stuffed gradient `dy` must then already BE, i.e. the
+    caller passes zero_stuff2(dy) and stride=1)."""
     lib = L.load()
     n, ho, wo, c = dy.shape
     h, wd = in_hw
     cpg = w.shape[1]
+    if packed is not None:
+        assert stride == 1 and (ho, wo) == (h, wd)
+        return conv_fwd(dy, packed, 3, grouped=cpg)
     dx = torch.empty((n, h, wd, c), dtype=torch.float32, device=dy.device)
     with _timed("resnext_grouped", flops=2.0 * n * ho * wo * c * cpg * 9):
         L.check(lib.b200lp_gconv3x3_dgrad(L.ptr(dy), L.ptr(w), L.ptr(dx), n, h, wd, c, cpg, stride, L.stream_ptr()),

@@ -13,7 +13,7 @@ import torch
 
 _PKG = Path(__file__).resolve().parent.parent
 LIB_PATH = _PKG / "lib" / "libb200lp.so"
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 
 class B200lpError(RuntimeError):
@@ -27,7 +27,8 @@ class ConvArgs(Structure):
         ("N", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("Cout", c_int32),
         ("ksize", c_int32), ("residual_mode", c_int32), ("relu", c_int32), ("round_tf32", c_int32),
         ("block_n", c_int32), ("precision", c_int32), ("stages", c_int32), ("ctas_per_sm", c_int32),
-        ("splits", c_int32), ("variant", c_int32), ("a_stages", c_int32), ("workspace", c_void_p),
+        ("splits", c_int32), ("variant", c_int32), ("a_stages", c_int32), ("grouped", c_int32), ("reserved0", c_int32),
+        ("workspace", c_void_p),
         ("workspace_bytes", c_int64),
     ]
 
@@ -38,7 +39,7 @@ class WgradArgs(Structure):
         ("workspace_bytes", c_int64),
         ("N", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("Cout", c_int32),
         ("ksize", c_int32), ("scale", c_float),
-        ("kstep", c_int32), ("stages", c_int32), ("splits", c_int32), ("reserved", c_int32),
+        ("kstep", c_int32), ("stages", c_int32), ("splits", c_int32), ("grouped", c_int32),
     ]
 
 
@@ -65,6 +66,7 @@ SIGNATURES = {
     "b200lp_conv_fwd": (_I, [POINTER(ConvArgs), _P]),
     "b200lp_pack_conv_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200lp_pack_conv_weight_multi": (_I, [_P, _P, _P, _I, _L, _P]),
+    "b200lp_pack_gconv_weight": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b200lp_sn_max_tensors": (_I, []),
     "b200lp_sn_scratch_floats": (_L, [_I, _I]),
     "b200lp_sn_sigma_multi": (_I, [POINTER(SnItem), _I, _I, _P]),
@@ -74,6 +76,9 @@ SIGNATURES = {
     "b200lp_conv_wgrad": (_I, [POINTER(WgradArgs), _P]),
     "b200lp_conv_wgrad_sn_acc_workspace": (_L, [_I, _I, _I, _I, _I, _I]),
     "b200lp_conv_wgrad_sn_acc": (_I, [POINTER(WgradArgs), _P, _P, _P, _P, _I, _P]),
+    "b200lp_gconv3x3_wgrad_tc_workspace": (_L, [_I, _I, _I, _I]),
+    "b200lp_gconv3x3_wgrad_tc": (_I, [POINTER(WgradArgs), _I, _P]),
+    "b200lp_zero_stuff2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b200lp_in_stats_workspace": (_L, [_I, _I, _I]),
     "b200lp_in_stats": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _F, _P]),
     "b200lp_adain_relu": (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -55,6 +55,8 @@ struct ConvParams {
     float* ws;             // split-K partial sums [splits][N*H*W][Cout] (raw accumulators), NULL when splits == 1
     long long ws_stride;   // N*H*W*Cout
     int a_stages, b_stages;   // halo kernel: depths of the activation-slab ring and of the weight-tile ring
+    int kcin;              // input channels per filter tap in the packed weights: Cin, or BLOCK_N when grouped
+    int grouped;           // 1: block-diagonal (grouped) convolution — N tile n reads input channels [n*BLOCK_N, (n+1)*BLOCK_N)
 };
 
 template <int BLOCK_N, int MODE>
@@ -209,13 +211,13 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
                     // stage layout: [A plane 0][A plane 1]...[B plane 0][B plane 1]..., every plane 1024-byte aligned
                     uint8_t* sa = smem_al + stage * Cfg::kStageBytes;
                     uint8_t* sb = sa + Cfg::kParts * Cfg::kABytes;
-                    const int kcoord = tap * p.Cin + cb * Cfg::kChanPerRow;   // column of the packed weight matrix
+                    const int kcoord = tap * p.kcin + cb * Cfg::kChanPerRow;   // column of the packed weight matrix
+                    const int ccoord = cb * Cfg::kChanPerRow + (p.grouped ? n_tile * BLOCK_N : 0);
                     if (leader) {
                         mbar_expect_tx(&full_bar[stage], Cfg::kParts * (p.a_bytes + Cfg::kBBytes));
 #pragma unroll
                         for (int q = 0; q < Cfg::kParts; ++q) {
-                            tma_load_4d(sa + q * Cfg::kABytes, &tm.a[q], &full_bar[stage], cb * Cfg::kChanPerRow,
-                                        w0 + dx, h0 + dy, n0);
+                            tma_load_4d(sa + q * Cfg::kABytes, &tm.a[q], &full_bar[stage], ccoord, w0 + dx, h0 + dy, n0);
                             tma_load_2d(sb + q * Cfg::kBBytes, &tm.b[q], &full_bar[stage], kcoord, n_tile * BLOCK_N);
                         }
                     }
@@ -424,6 +426,7 @@ conv_halo_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
                 const int th = m_tile % p.tiles_h;
                 const int n = m_tile / p.tiles_h;
                 const int w0 = tw * 8, h0 = th * Cfg::kPH;
+                const int cbase = p.grouped ? (tile % n_tiles) * BLOCK_N : 0;     // grouped: the N tile's own channels
                 for (int cb = 0; cb < p.cblks; ++cb) {
                     for (int dx = -1; dx <= 1; ++dx) {
                         mbar_wait(&a_empty[stage], phase ^ 1u);
@@ -432,8 +435,8 @@ conv_halo_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
                             mbar_expect_tx(&a_full[stage], Cfg::kAUnitBytes);
 #pragma unroll
                             for (int q = 0; q < Cfg::kParts; ++q)
-                                tma_load_4d(sa + q * Cfg::kSlabBytes, &tm.a[q], &a_full[stage], cb * Cfg::kChanPerRow,
-                                            w0 + dx, h0 - 1, n);
+                                tma_load_4d(sa + q * Cfg::kSlabBytes, &tm.a[q], &a_full[stage],
+                                            cbase + cb * Cfg::kChanPerRow, w0 + dx, h0 - 1, n);
                         }
                         if (++stage == SA) { stage = 0; phase ^= 1u; }
                     }
@@ -453,7 +456,7 @@ conv_halo_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
                         for (int dyi = 0; dyi < 3; ++dyi) {
                             mbar_wait(&b_empty[stage], phase ^ 1u);
                             uint8_t* sb = smem_al + b_ring_off + stage * Cfg::kBUnitBytes;
-                            const int kcoord = (dyi * 3 + dxi) * p.Cin + cb * Cfg::kChanPerRow;
+                            const int kcoord = (dyi * 3 + dxi) * p.kcin + cb * Cfg::kChanPerRow;
                             if (leader) {
                                 mbar_expect_tx(&b_full[stage], Cfg::kBUnitBytes);
 #pragma unroll
@@ -657,6 +660,7 @@ conv_halo2_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
             const int th = m_tile % p.tiles_h;
             const int n = m_tile / p.tiles_h;
             const int w0 = tw * 16 + static_cast<int>(rank) * 8, h0 = th * Cfg::kPH;
+            const int cbase = p.grouped ? (tile % n_tiles) * BLOCK_N : 0;
             for (int cb = 0; cb < p.cblks; ++cb) {
                 for (int dx = -1; dx <= 1; ++dx) {
                     mbar_wait(&a_empty[stage], phase ^ 1u);
@@ -665,8 +669,8 @@ conv_halo2_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
                         if (rank == 0) mbar_expect_tx(&a_full[stage], 2 * Cfg::kAUnitBytes);   // both CTAs' slabs
 #pragma unroll
                         for (int q = 0; q < Cfg::kParts; ++q)
-                            tma_load_4d_2cta(sa + q * Cfg::kSlabBytes, &tm.a[q], &a_full[stage], cb * Cfg::kChanPerRow,
-                                             w0 + dx, h0 - 1, n);
+                            tma_load_4d_2cta(sa + q * Cfg::kSlabBytes, &tm.a[q], &a_full[stage],
+                                             cbase + cb * Cfg::kChanPerRow, w0 + dx, h0 - 1, n);
                     }
                     if (++stage == SA) { stage = 0; phase ^= 1u; }
                 }
@@ -685,7 +689,7 @@ conv_halo2_kernel(const __grid_constant__ ConvMaps tm, const ConvParams p) {
                     for (int dyi = 0; dyi < 3; ++dyi) {
                         mbar_wait(&b_empty[stage], phase ^ 1u);
                         uint8_t* sb = smem_al + b_ring_off + stage * kBHalfUnit;
-                        const int kcoord = (dyi * 3 + dxi) * p.Cin + cb * Cfg::kChanPerRow;
+                        const int kcoord = (dyi * 3 + dxi) * p.kcin + cb * Cfg::kChanPerRow;
                         if (leader) {
                             if (rank == 0) mbar_expect_tx(&b_full[stage], 2 * kBHalfUnit);
 #pragma unroll
@@ -1030,6 +1034,7 @@ using namespace b200lp;
 // geometry shared by b200lp_conv_fwd and b200lp_conv_fwd_workspace
 static int conv_pick_block_n(const b200lp_conv_args* a, int m_tiles) {
     int block_n = a->block_n;
+    if (a->grouped) return a->precision == 0 ? 32 : 64;      // one 128-byte operand row of channels per N tile
     if (block_n == 0) {
         if (a->precision == 0 && a->Cout % 256 == 0 && static_cast<long>(m_tiles) * (a->Cout / 256) >= 100) block_n = 256;
         else if (a->Cout % 128 == 0) block_n = 128;
@@ -1047,7 +1052,8 @@ static int conv_m_tiles(const b200lp_conv_args* a) {
 static int conv_splits(const b200lp_conv_args* a, int block_n, int m_tiles) {
     if (a->splits == 1) return 1;
     const int chan_per_row = a->precision == 0 ? 32 : 64;
-    const int num_kb = a->ksize * a->ksize * ((a->Cin + chan_per_row - 1) / chan_per_row);
+    const int kcin = a->grouped ? block_n : a->Cin;
+    const int num_kb = a->ksize * a->ksize * ((kcin + chan_per_row - 1) / chan_per_row);
     int s = a->splits > 1 ? a->splits : choose_splits(m_tiles * (a->Cout / block_n), num_kb);
     if (s > num_kb) s = num_kb;
     const int per = (num_kb + s - 1) / s;
@@ -1068,7 +1074,7 @@ static int conv_halo_mt(const b200lp_conv_args* a, int block_n, int splits, bool
     }
     // CTA pairs (cta_group::2) first: +4..9 % tf32, +6..19 % bf16x3 over the single-CTA halo kernel on every shape of
     // the sweep (profiles/r01_kernel_diag_pair.log).  Two sub-tiles for block_n <= 128 in tf32; one otherwise.
-    if (a->W % 16 == 0 && block_n >= 64) {
+    if (a->W % 16 == 0 && block_n >= 64 && !a->grouped) {
         int mt = (a->precision == 0 && block_n <= 128) ? 2 : 1;
         const long pair_tiles1 = static_cast<long>(a->N) * (a->H / 16) * (a->W / 16) * (a->Cout / block_n);
         while (mt > 1 && (a->H % (16 * mt) || pair_tiles1 / mt < 60)) mt >>= 1;
@@ -1115,6 +1121,9 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
     const int elem_bytes = mode == 0 ? 4 : 2;
     B200LP_REQUIRE(mode == 0 || a->Cin % 64 == 0 || a->Cin == 32,
                    "conv_fwd: bf16x3 needs Cin %% 64 == 0 (or Cin == 32), got %d", a->Cin);
+    B200LP_REQUIRE(!a->grouped || (a->Cin == a->Cout && a->ksize == 3 && (a->block_n == 0 || a->block_n == chan_per_row)),
+                   "conv_fwd: grouped mode needs Cin == Cout, ksize 3 and block_n auto (got Cin=%d Cout=%d k=%d block_n=%d)",
+                   a->Cin, a->Cout, a->ksize, a->block_n);
 
     ConvParams p;
     p.out_scale = a->out_scale;
@@ -1130,7 +1139,9 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
     p.bn = kBlockM / (p.bw * p.bh);
     p.tiles_w = a->W / p.bw;
     p.tiles_h = a->H / p.bh;
-    p.cblks = (a->Cin + chan_per_row - 1) / chan_per_row;
+    p.grouped = a->grouped ? 1 : 0;
+    p.kcin = a->grouped ? chan_per_row : a->Cin;           // grouped: wp is [Cout][taps][block_n], block_n = one operand row
+    p.cblks = (p.kcin + chan_per_row - 1) / chan_per_row;
     p.num_kb = a->ksize * a->ksize * p.cblks;
     p.residual_mode = a->residual_mode;
     p.relu = a->relu;
@@ -1161,7 +1172,7 @@ extern "C" int32_t b200lp_conv_fwd(const b200lp_conv_args* a, void* stream) {
                    "H %% (16 * sub-tiles) == 0, no split-K", a->variant);
 
     ConvMaps tm;
-    const uint64_t ktot = (uint64_t)a->ksize * a->ksize * a->Cin;
+    const uint64_t ktot = (uint64_t)a->ksize * a->ksize * p.kcin;
     const int parts = mode == 0 ? 1 : 2;
     for (int q = 0; q < parts; ++q) {
         {
@@ -1325,6 +1336,54 @@ extern "C" int32_t b200lp_pack_conv_weight(const float* w_oihw, const float* sca
     else
         pack_conv_weight_kernel<true><<<(int)blocks, threads, 0, as_stream(stream)>>>(w_oihw, scale, wp, Cout, Cin,
                                                                                     ksize * ksize, transpose);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
+
+namespace b200lp {
+// Grouped 3x3 weight [C][cpg][9] -> block-diagonal dense tiles [C][9][B] (B = 32 tf32 / 64 bf16 planes); one thread per
+// packed element (coalesced writes; the source is at most 1.2 MB and stays in L2).
+template <bool SPLIT>
+__global__ void pack_gconv_weight_kernel(const float* __restrict__ w, float* __restrict__ wp, int C, int cpg, int B,
+                                         int transpose) {
+    const long total = static_cast<long>(C) * 9 * B;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int j = static_cast<int>(i % B);
+        const int tap = static_cast<int>((i / B) % 9);
+        const int r = static_cast<int>(i / (9L * B));           // output row: co (forward) or ci (data-gradient)
+        const int other = (r / B) * B + j;                       // the block's j-th channel on the contracted side
+        float f = 0.f;
+        if (other / cpg == r / cpg) {
+            const int co = transpose ? other : r, ci = transpose ? r : other;
+            f = w[(static_cast<long>(co) * cpg + (ci % cpg)) * 9 + (transpose ? 8 - tap : tap)];
+        }
+        if (!SPLIT) {
+            wp[i] = round_tf32(f);
+        } else {
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(wp);
+            const __nv_bfloat16 h = __float2bfloat16_rn(f);
+            out[i] = h;
+            out[total + i] = __float2bfloat16_rn(f - __bfloat162float(h));
+        }
+    }
+}
+}  // namespace b200lp
+
+extern "C" int32_t b200lp_pack_gconv_weight(const float* w, void* wp_out, int32_t C, int32_t cpg, int32_t transpose,
+                                            int32_t precision, void* stream) {
+    const int B = precision == 0 ? 32 : 64;
+    B200LP_REQUIRE(w && wp_out && C > 0 && cpg > 0 && C % B == 0 && B % cpg == 0 && (precision == 0 || precision == 1),
+                   "pack_gconv_weight: C=%d cpg=%d precision=%d (C %% %d == 0 and cpg | %d required)", C, cpg, precision, B, B);
+    const long total = static_cast<long>(C) * 9 * B;
+    long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    float* wp = static_cast<float*>(wp_out);
+    if (precision == 0)
+        pack_gconv_weight_kernel<false><<<(int)blocks, 256, 0, as_stream(stream)>>>(w, wp, C, cpg, B, transpose);
+    else
+        pack_gconv_weight_kernel<true><<<(int)blocks, 256, 0, as_stream(stream)>>>(w, wp, C, cpg, B, transpose);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

@@ -34,6 +34,7 @@ struct WgradParams {
     int cblks;            // Cin / 32
     int rows_total;       // taps * Cin
     int blocks_total;     // taps * cblks
+    int grouped;          // 1: grouped conv — the M blocks of N tile n are the taps of channel block n (cblks == 1)
 };
 
 template <int BLOCK_N>
@@ -102,7 +103,7 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 const int b = m_tile * 4 + j;
                 if (b < p.blocks_total) {
                     const int tap = b / p.cblks;
-                    blk_c[j] = (b - tap * p.cblks) * 32;
+                    blk_c[j] = (b - tap * p.cblks) * 32 + (p.grouped ? n_tile * BLOCK_N : 0);
                     blk_dy[j] = tap / p.ksize - pad;
                     blk_dx[j] = tap % p.ksize - pad;
                     ++nvalid;
@@ -342,10 +343,14 @@ struct WgPlan {
 };
 
 static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int ksize, WgPlan* pl, int kstep_req = 0,
-                      int stages_req = 0, int splits_req = 0) {
+                      int stages_req = 0, int splits_req = 0, bool grouped = false) {
     if (!(ksize == 1 || ksize == 3) || Cin % 32 || Cout % 32 || Cin <= 0 || Cout <= 0 || N <= 0) return -1;
     if (ilog2_exact(H) < 1 || ilog2_exact(W) < 1) return -1;
     pl->block_n = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32));
+    if (grouped) {
+        if (Cin != Cout || ksize != 3) return -1;
+        pl->block_n = 32;                       // one 32-channel block on both sides
+    }
     pl->n_tiles = Cout / pl->block_n;
     // pixels per pipeline stage: 64 amortises the per-stage TMA issue / barrier cost when the whole batch offers
     // enough K (and the tile is not already 48 KB per 32 pixels)
@@ -368,7 +373,7 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int ksize, WgPlan*
     if (stages > kWgMaxStages) stages = kWgMaxStages;
     while (stages > 1 && stages * stage_bytes + 1024 > kWgMaxSmem) --stages;
     pl->stages = stages;
-    const int blocks_total = ksize * ksize * (Cin / 32);
+    const int blocks_total = ksize * ksize * (grouped ? 1 : Cin / 32);
     pl->m_tiles = (blocks_total + 3) / 4;
     const int base = pl->m_tiles * pl->n_tiles;
     // split-K so that the grid is at most one full wave of 2 CTAs x 148 SMs (one CTA over the wave costs a whole
@@ -420,16 +425,18 @@ extern "C" int64_t b200lp_conv_wgrad_workspace(int32_t N, int32_t H, int32_t W, 
 }
 
 // plans and launches the tensor-core kernel (split-K partial sums -> a->workspace); the caller adds the reduction
-static int wgrad_main(const b200lp_wgrad_args* a, void* stream, WgPlan* pl_out, int64_t extra_ws_bytes) {
+static int wgrad_main(const b200lp_wgrad_args* a, void* stream, WgPlan* pl_out, int64_t extra_ws_bytes,
+                      bool grouped = false) {
     B200LP_REQUIRE(a && a->x && a->dy && a->dw && a->workspace, "conv_wgrad: null pointer");
+    B200LP_REQUIRE(grouped || a->grouped == 0, "conv_wgrad: grouped weights go through b200lp_gconv3x3_wgrad_tc");
     WgPlan& pl = *pl_out;
-    B200LP_REQUIRE(plan_wgrad(a->N, a->H, a->W, a->Cin, a->Cout, a->ksize, &pl, a->kstep, a->stages, a->splits) == 0,
+    B200LP_REQUIRE(plan_wgrad(a->N, a->H, a->W, a->Cin, a->Cout, a->ksize, &pl, a->kstep, a->stages, a->splits, grouped) == 0,
                    "conv_wgrad: unsupported shape N=%d H=%d W=%d Cin=%d Cout=%d k=%d", a->N, a->H, a->W, a->Cin,
                    a->Cout, a->ksize);
     B200LP_REQUIRE(a->N % pl.pn == 0, "conv_wgrad: N=%d must be a multiple of %d for %dx%d planes", a->N, pl.pn,
                    a->H, a->W);
     const int taps = a->ksize * a->ksize;
-    const int64_t need = static_cast<int64_t>(pl.splits) * taps * a->Cin * a->Cout * 4 + extra_ws_bytes;
+    const int64_t need = static_cast<int64_t>(pl.splits) * taps * (grouped ? 32 : a->Cin) * a->Cout * 4 + extra_ws_bytes;
     B200LP_REQUIRE(a->workspace_bytes >= need, "conv_wgrad: workspace %lld < %lld bytes",
                    (long long)a->workspace_bytes, (long long)need);
 
@@ -445,8 +452,9 @@ static int wgrad_main(const b200lp_wgrad_args* a, void* stream, WgPlan* pl_out, 
     p.steps_h = a->H / pl.ph;
     p.total_steps = pl.total_steps;
     p.steps_per_split = pl.steps_per_split;
-    p.cblks = a->Cin / 32;
-    p.rows_total = taps * a->Cin;
+    p.grouped = grouped ? 1 : 0;
+    p.cblks = grouped ? 1 : a->Cin / 32;
+    p.rows_total = taps * p.cblks * 32;
     p.blocks_total = taps * p.cblks;
 
     CUtensorMap tmX, tmDY;
@@ -540,5 +548,80 @@ extern "C" int32_t b200lp_conv_wgrad_sn_acc(const b200lp_wgrad_args* a, const fl
         B200LP_CHECK_CUDA(cudaGetLastError());
         count_launch();
     }
+    return B200LP_OK;
+}
+
+namespace b200lp {
+// dw[co][cig][tap] (+)= sum_s ws[s][tap*32 + (co%32/cpg)*cpg + cig][co]: the block-diagonal entries of the per-block
+// [9 x 32 ci] x [32 co] products, summed over the K splits in index order.  One thread per (co, tap, cig) with co fastest
+// across the warp (coalesced workspace reads; the OIHW stores hit a <= 1.2 MB tensor).
+__global__ void __launch_bounds__(256)
+gconv_wgrad_tc_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int C, int cpg, int accumulate) {
+    const long total = static_cast<long>(C) * cpg * 9;
+    const long split_stride = 288L * C;
+    for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += gridDim.x * 256L) {
+        const int co = static_cast<int>(i % C);
+        const int r = static_cast<int>(i / C);
+        const int cig = r % cpg, tap = r / cpg;
+        const int row = tap * 32 + ((co & 31) / cpg) * cpg + cig;
+        const float* src = ws + static_cast<long>(row) * C + co;
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s) acc += __ldg(src + s * split_stride);
+        float* o = dw + (static_cast<long>(co) * cpg + cig) * 9 + tap;
+        *o = accumulate ? *o + acc : acc;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+zero_stuff2_kernel(const float4* __restrict__ x, float4* __restrict__ out, long total4, int W2, int H2, int c4) {
+    for (long i = blockIdx.x * 256L + threadIdx.x; i < total4; i += gridDim.x * 256L) {
+        const int c = static_cast<int>(i % c4);
+        long pix = i / c4;
+        const int w = static_cast<int>(pix % W2);
+        pix /= W2;
+        const int h = static_cast<int>(pix % H2);
+        const long n = pix / H2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (((w | h) & 1) == 0) v = __ldg(x + ((n * (H2 >> 1) + (h >> 1)) * (W2 >> 1) + (w >> 1)) * c4 + c);
+        out[i] = v;
+    }
+}
+}  // namespace b200lp
+
+extern "C" int64_t b200lp_gconv3x3_wgrad_tc_workspace(int32_t N, int32_t H, int32_t W, int32_t C) {
+    WgPlan pl;
+    if (plan_wgrad(N, H, W, C, C, 3, &pl, 0, 0, 0, true)) {
+        set_error("gconv3x3_wgrad_tc_workspace: unsupported shape N=%d H=%d W=%d C=%d", N, H, W, C);
+        return B200LP_EINVAL;
+    }
+    return static_cast<int64_t>(pl.splits) * 288 * C * 4;
+}
+
+extern "C" int32_t b200lp_gconv3x3_wgrad_tc(const b200lp_wgrad_args* a, int32_t accumulate, void* stream) {
+    B200LP_REQUIRE(a && a->grouped > 0 && a->grouped <= 32 && 32 % a->grouped == 0 && a->Cin == a->Cout && a->ksize == 3,
+                   "gconv3x3_wgrad_tc: needs grouped = cpg in {1,2,4,8,16,32}, Cin == Cout, ksize 3");
+    B200LP_REQUIRE(a->splits == 0 && a->kstep == 0 && a->stages == 0, "gconv3x3_wgrad_tc: tuning knobs are not supported");
+    WgPlan pl;
+    int r = wgrad_main(a, stream, &pl, 0, true);
+    if (r) return r;
+    const long total = static_cast<long>(a->Cout) * a->grouped * 9;
+    int blocks = static_cast<int>((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    gconv_wgrad_tc_reduce_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a->workspace, a->dw, pl.splits, a->Cout, a->grouped,
+                                                                        accumulate);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_zero_stuff2(const float* x, float* out, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+    B200LP_REQUIRE(x && out && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "zero_stuff2: bad args");
+    const long total4 = static_cast<long>(N) * (2 * H) * (2 * W) * (C / 4);
+    long blocks = (total4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    zero_stuff2_kernel<<<static_cast<int>(blocks), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(out), total4, 2 * W, 2 * H, C / 4);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return B200LP_OK;
 }

@@ -9,8 +9,9 @@ keys `identity_encoder.*` are torchvision's); this file only sequences kernels o
     GEMM — bf16x3 operands forward (three bf16 MMAs per K step on (hi, lo) planes, ~fp32 accuracy: a single-pass TF32
     forward leaves a 2e-2 relative error in the 512-d embedding after 53 layers of batch-normalised convolutions,
     measured against float64), TF32 for the data and weight gradients;
-  * grouped 3x3 convolutions: FP32 CUDA-core kernels that apply the producer's BatchNorm + ReLU on load and emit the
-    statistics of their own output;
+  * grouped 3x3 convolutions: forward = FP32 CUDA-core kernels that apply the producer's BatchNorm + ReLU on load and
+    emit the statistics of their own output; data and weight gradients = TF32 tensor cores on block-diagonal 32-channel
+    tiles (`conv_fwd(grouped=cpg)`, `gconv3x3_wgrad_tc`; the three stride-2 layers through the zero-stuffed gradient);
   * BatchNorm: statistics partials -> `bn_finalize` (running-statistics updates like nn.BatchNorm2d) -> one
     materialising pass per GEMM operand; backward = reduce / finalize / apply with the ReLU mask recomputed.
 
@@ -69,6 +70,22 @@ def _packed(conv, transpose, precision):
     if cache is None:
         cache = conv.__dict__["_b200lp_pack"] = ops.PackCache()
     return cache.get(conv.weight, transpose, precision)
+
+
+def _gpacked(conv, transpose, precision):
+    """Block-diagonal tensor-core tiles of a grouped 3x3 weight, re-made (in place: the address is baked into captured
+    CUDA graphs) when the weight changed — same validation as ops.PackCache."""
+    cache = conv.__dict__.setdefault("_b200lp_gpack", {})
+    key = (transpose, precision)
+    w = conv.weight
+    stamp = ops._stamp(w)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    reuse = hit[1] if hit is not None and hit[1].device == w.device else None
+    packed = K.pack_gconv_weight(w.detach(), transpose=transpose, precision=precision, out=reuse)
+    cache[key] = (stamp, packed)
+    return packed
 
 
 def _stem_packed(conv):
@@ -252,14 +269,27 @@ def backward(net, saved, d_emb, params):
         d_a2 = K.conv_fwd(dr3, _packed(blk.conv3, True, K.TF32), 1)
         _wgrad_1x1(grads, blk.conv3, rec["a2_f32"], dr3)
         del dr3
-        dr2, _ = _bn_backward(grads, rec["bn2"], d_a2, rec["r2"], 2)
-        del d_a2
         w2 = blk.conv2.weight
-        d_a1 = K.gconv3x3_dgrad(dr2, w2.detach(), (h, w), stride=s)
+        cpg = w2.shape[1]
+        tc = K.gconv_tensor_cores(d_a2.shape[0], h, w, w2.shape[0], cpg)
+        dr2, _ = _bn_backward(grads, rec["bn2"], d_a2, rec["r2"], 2, round_tf32=tc)
+        del d_a2
+        if tc:
+            # tensor cores: stride 2 = the stride-1 kernels on the gradient placed at the even positions of the input grid
+            if s == 2:
+                dr2 = K.zero_stuff2(dr2)
+            d_a1 = K.gconv3x3_dgrad(dr2, w2.detach(), (h, w), packed=_gpacked(blk.conv2, True, K.TF32))
+        else:
+            d_a1 = K.gconv3x3_dgrad(dr2, w2.detach(), (h, w), stride=s)
         if w2.requires_grad:
-            cpg = w2.shape[1]
             sk = grads.sink(w2)
-            g2 = K.gconv3x3_wgrad(rec["r1"], dr2, cpg, rec["bn1"].scale, rec["bn1"].shift, stride=s, acc_into=sk)
+            if tc:
+                a1 = K.bn_act(rec["r1"], rec["bn1"].scale, rec["bn1"].shift, act=1, round_tf32=True, want_f32=True,
+                              want_split=False)
+                g2 = K.gconv3x3_wgrad_tc(a1, dr2, cpg, acc_into=sk)
+                del a1
+            else:
+                g2 = K.gconv3x3_wgrad(rec["r1"], dr2, cpg, rec["bn1"].scale, rec["bn1"].shift, stride=s, acc_into=sk)
             if sk is None:
                 grads.give(w2, g2)
         del dr2

@@ -109,7 +109,26 @@ def gconv3x3_fwd(x, w, in_scale=None, in_shift=None, stride=1, want_stats=False)
     return (y, col_stats(y.reshape(-1, y.shape[-1]))) if want_stats else y
 
 
-def gconv3x3_dgrad(dy, w, in_hw, stride=1):
+def gconv_tensor_cores(n, h, w, c, cpg):
+    return (h & (h - 1)) == 0 and (w & (w - 1)) == 0 and h >= 2 and w >= 2 and c % 32 == 0
+
+
+def pack_gconv_weight(w, transpose=False, precision=0, out=None):
+    return w            # the emulated data-gradient reads the OIHW weight itself
+
+
+def zero_stuff2(x):
+    n, h, w, c = x.shape
+    out = torch.zeros((n, 2 * h, 2 * w, c), dtype=x.dtype, device=x.device)
+    out[:, ::2, ::2] = x
+    return out
+
+
+def gconv3x3_wgrad_tc(x, dy, cpg, acc_into=None):
+    return gconv3x3_wgrad(x, dy, cpg, acc_into=acc_into)
+
+
+def gconv3x3_dgrad(dy, w, in_hw, stride=1, packed=None):
     n, ho, wo, c = dy.shape
     groups = c // w.shape[1]
     dx = torch.nn.grad.conv2d_input((n, c, in_hw[0], in_hw[1]), w.to(dy.dtype), _nchw(dy), stride=stride, padding=1,
@@ -277,6 +296,7 @@ def bias_grad(dy, acc_into=None):
 
 EMULATED = ["mbv2_stem", "dw_conv3x3", "bn_apply", "bn_relu6_avgpool", "transpose2d", "pw_wgrad", "dw_dgrad", "dw_wgrad",
             "mbv2_stem_wgrad", "bias_grad", "col_stats", "bn_finalize", "bn_act", "bn_bwd", "gconv3x3_fwd", "gconv3x3_dgrad", "gconv3x3_wgrad",
+            "gconv_tensor_cores", "pack_gconv_weight", "zero_stuff2", "gconv3x3_wgrad_tc",
             "im2col7x7_s2", "maxpool3x3s2_fwd", "maxpool3x3s2_bwd", "subsample2", "scatter_add2", "avgpool_fwd",
             "avgpool_bwd", "sgemm", "pw_conv"]
 

@@ -33,7 +33,7 @@ def test_binding_covers_header_exactly():
 def test_struct_layouts_match_header():
     from b200lp import lib
     # b200lp_conv_args: 7 pointers + 15 int32 (+pad) + workspace pointer + int64 ; b200lp_wgrad_args: 4 pointers + int64 + 6 int32 + float
-    assert ctypes.sizeof(lib.ConvArgs) == 7 * 8 + 16 * 4 + 2 * 8
+    assert ctypes.sizeof(lib.ConvArgs) == 7 * 8 + 18 * 4 + 2 * 8
     assert ctypes.sizeof(lib.WgradArgs) == 4 * 8 + 8 + 6 * 4 + 4 + 4 * 4 + 4   # + tail padding to 8
     assert lib.ConvArgs.block_n.offset == 7 * 8 + 9 * 4 and lib.ConvArgs.precision.offset == 7 * 8 + 10 * 4
     assert lib.WgradArgs.scale.offset == 4 * 8 + 8 + 6 * 4

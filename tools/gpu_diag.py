@@ -1151,6 +1151,74 @@ def encoder_gconv():
 
 
 @check
+def gconv_tc():
+    """Grouped 3x3 convolution on the tensor cores (block-diagonal 32 / 64-channel tiles): conv_fwd(grouped) forward in
+    tf32 and bf16x3, data gradient through the transposed packing (stride 2 via the zero-stuffed gradient), weight gradient
+    (gconv3x3_wgrad_tc, + accumulation) vs float64 torch on tf32-rounded inputs; then times at the identity encoder's shapes."""
+    import torch
+    from b200lp import kernels as K
+    E = _emu()
+    out = []
+    torch.manual_seed(11)
+    dev = "cuda"
+    for (n, h, w, cpg, c) in [(2, 16, 16, 4, 128), (2, 32, 16, 8, 256), (4, 8, 8, 16, 512), (4, 4, 4, 32, 1024),
+                              (2, 16, 8, 32, 64), (3, 16, 16, 16, 96), (8, 64, 64, 4, 128), (8, 2, 2, 32, 64)]:
+        x = tf32_round(torch.randn(n, h, w, c, device=dev))
+        wt = torch.randn(c, cpg, 3, 3, device=dev) * 0.2
+        wr = tf32_round(wt)
+        tag = f"N{n} H{h} W{w} C{c} cpg{cpg}"
+        y = K.conv_fwd(x, K.pack_gconv_weight(wt), 3, grouped=cpg)
+        out.append(_cmp(f"gconv_tc fwd tf32 {tag}", y, E.gconv3x3_fwd(x.double(), wr.double()), 2e-5))
+        if c % 64 == 0:
+            xs = split_bf16(x)
+            yb = K.conv_fwd(xs, K.pack_gconv_weight(wt, precision=K.BF16X3), 3, grouped=cpg)
+            out.append(_cmp(f"gconv_tc fwd bf16x3 {tag}", yb, E.gconv3x3_fwd(x.double(), wt.double()), 5e-5))
+        dy = tf32_round(torch.randn(n, h, w, c, device=dev))
+        dx = K.gconv3x3_dgrad(dy, wt, (h, w), packed=K.pack_gconv_weight(wt, transpose=True))
+        out.append(_cmp(f"gconv_tc dgrad {tag}", dx, E.gconv3x3_dgrad(dy.double(), wr.double(), (h, w)), 2e-5))
+        if K.gconv_tensor_cores(n, h, w, c, cpg):
+            rg = E.gconv3x3_wgrad(x.double(), dy.double(), cpg)
+            g = K.gconv3x3_wgrad_tc(x, dy, cpg)
+            out.append(_cmp(f"gconv_tc wgrad {tag}", g, rg, 3e-5))
+            base = torch.randn_like(wt)
+            acc = base.clone()
+            K.gconv3x3_wgrad_tc(x, dy, cpg, acc_into=acc)
+            out.append(_cmp(f"gconv_tc wgrad(acc) {tag}", acc - base, rg, 3e-5))
+        if h >= 4 and w >= 4:         # stride 2: gradient of the (h/2, w/2) output on the zero-stuffed grid
+            dys = tf32_round(torch.randn(n, h // 2, w // 2, c, device=dev))
+            up = K.zero_stuff2(dys)
+            dx2 = K.gconv3x3_dgrad(up, wt, (h, w), packed=K.pack_gconv_weight(wt, transpose=True))
+            out.append(_cmp(f"gconv_tc dgrad s2 {tag}", dx2, E.gconv3x3_dgrad(dys.double(), wr.double(), (h, w), stride=2), 2e-5))
+            if K.gconv_tensor_cores(n, h, w, c, cpg):
+                g2 = K.gconv3x3_wgrad_tc(x, up, cpg)
+                out.append(_cmp(f"gconv_tc wgrad s2 {tag}", g2, E.gconv3x3_wgrad(x.double(), dys.double(), cpg, stride=2), 3e-5))
+    for (n, h, cpg, stride) in [(64, 64, 4, 1), (64, 64, 8, 2), (64, 32, 8, 1), (64, 32, 16, 2), (64, 16, 16, 1),
+                                (64, 16, 32, 2), (64, 8, 32, 1)]:
+        c = 32 * cpg
+        x = torch.randn(n, h, h, c, device=dev)
+        wt = torch.randn(c, cpg, 3, 3, device=dev) * 0.1
+        ho = h // stride
+        dy = torch.randn(n, ho, ho, c, device=dev)
+        wpt = K.pack_gconv_weight(wt, transpose=True)
+        wpf = K.pack_gconv_weight(wt, precision=K.BF16X3)
+        xs = split_bf16(x)
+        flops = 2.0 * n * ho * ho * c * cpg * 9
+        rec = {"case": f"timing gconv_tc N{n} H{h} cpg{cpg} s{stride}", "ok": True, "max_abs": 0.0, "rel": 0.0, "nan": False,
+               "ref_max": 0.0}
+        up = K.zero_stuff2(dy) if stride == 2 else dy
+        rec["fwd_s1_bf16x3_us"] = round(_time_us(lambda: K.conv_fwd(xs, wpf, 3, grouped=cpg)), 1)
+        rec["fwd_s1_tf32_us"] = round(_time_us(lambda: K.conv_fwd(x, wpt, 3, grouped=cpg)), 1)
+        if stride == 2:
+            rec["zero_stuff_us"] = round(_time_us(lambda: K.zero_stuff2(dy)), 1)
+        rec["dgrad_us"] = round(_time_us(lambda: K.gconv3x3_dgrad(up, wt, (h, h), packed=wpt)), 1)
+        rec["wgrad_us"] = round(_time_us(lambda: K.gconv3x3_wgrad_tc(x, up, cpg)), 1)
+        rec["dgrad_tflops"] = round(flops / rec["dgrad_us"] / 1e6, 1)
+        rec["wgrad_tflops"] = round(flops / rec["wgrad_us"] / 1e6, 1)
+        out.append(rec)
+    return out
+
+
+@check
 def encoder_misc():
     """im2col7x7_s2, maxpool3x3s2 fwd / bwd, subsample2 / scatter_add2, avgpool fwd / bwd, strided sgemm."""
     import torch
