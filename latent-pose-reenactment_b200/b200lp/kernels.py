@@ -310,6 +310,20 @@ def relu_bwd(y, dy):
     return dx
 
 
+def relu_bwd_fused(y, dy, add=None, want_quarter=False, bias_a=None, bias_b=None):
+    """dx = [y > 0] * (dy + add); optionally dq = 0.25 * dx; bias_a / bias_b (C,) += column sums of dx (in place).
+    Returns dx or (dx, dq)."""
+    lib = L.load()
+    c = y.shape[-1]
+    dx = torch.empty_like(y)
+    dq = torch.empty_like(y) if want_quarter else None
+    nb = 12.0 + (4.0 if add is not None else 0.0) + (4.0 if want_quarter else 0.0)
+    with _timed("elementwise", nbytes=nb * y.numel()):
+        L.check(lib.b200lp_relu_bwd_fused(L.ptr(y), L.ptr(dy), L.ptr(add), L.ptr(dx), L.ptr(dq), L.ptr(bias_a),
+                                          L.ptr(bias_b), y.numel() // c, c, L.stream_ptr()), "relu_bwd_fused")
+    return (dx, dq) if want_quarter else dx
+
+
 def avgpool2(x, addend=None, round_tf32=False):
     lib = L.load()
     n, h2, w2, c = x.shape

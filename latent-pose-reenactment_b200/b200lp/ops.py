@@ -487,6 +487,166 @@ def relu_round(x):
     return ReluRoundFn.apply(x)
 
 
+class DiscBlocksFn(torch.autograd.Function):
+    """The discriminator's chain of ResBlock(norm_layer='none') as ONE autograd node (discriminators/no_landmarks.py:96-100
+    over generators/common/blocks.py:47-111): outputs = the 6 in-place-ReLU'd block inputs (the stored features) + the last
+    block's output.  Forward = the kernels of blocks.PlainResBlock; the hand-scheduled backward removes what autograd
+    cannot fuse across nodes:
+      * a block input feeds the main branch, the skip branch and the feature-matching loss — the three gradients are merged
+        by kernels (skip gradient = residual operand of the first conv's data-gradient epilogue, read at half resolution
+        behind a pooled 1x1 skip; feature-matching gradient = addend of the ReLU-backward pass) instead of two
+        full-tensor `add` launches per block;
+      * ReLU backward, the bias gradients of the convolutions that produced the tensor (column sums at the LOW resolution
+        for pooled outputs) and the 0.25-scaled copy the pooled skip needs are one pass (b200lp_relu_bwd_fused).
+    `specs`: per block dict(down=bool, c0=(w, s, b, cache, sn), c1=(...), sk=(...) or None); weights / biases are ALSO
+    passed in `params` (block order: c0.w, c0.b, c1.w, c1.b[, sk.w, sk.b]) so that autograd routes their gradients when no
+    gradient sink takes them."""
+
+    @staticmethod
+    def forward(ctx, x0, specs, *params):
+        ctx.set_materialize_grads(False)
+        out = x0.contiguous()
+        feats, keep = [], []
+        for sp in specs:
+            w0, s0, b0, c0, _ = sp["c0"]
+            w1, s1, b1, c1, _ = sp["c1"]
+            r = K.relu_round(out)
+            feats.append(r)
+            h = K.conv_fwd(r, _packed(w0, c0, False), 3, bias=b0, relu=True, round_tf32=True, scale=s0)
+            rs = None
+            if sp["sk"] is not None:
+                ws, ss, bs, cs, _ = sp["sk"]
+                rs = K.avgpool2(r, None, round_tf32=True) if sp["down"] else r
+                s = K.conv_fwd(rs, _packed(ws, cs, False), 1, bias=bs, scale=ss)
+            else:
+                s = r
+            if sp["down"]:
+                out = K.avgpool2(K.conv_fwd(h, _packed(w1, c1, False), 3, bias=b1, scale=s1), s)
+            else:
+                out = K.conv_fwd(h, _packed(w1, c1, False), 3, bias=b1, residual=s, residual_mode=1, scale=s1)
+            keep.append((h, rs))
+        ctx.specs = specs
+        ctx.n_params = len(params)
+        ctx.out_shape = tuple(out.shape)
+        flat = list(feats) + [h for h, _ in keep] + [rs for _, rs in keep if rs is not None]
+        ctx.has_rs = [rs is not None for _, rs in keep]
+        ctx.save_for_backward(*flat)
+        return (*feats, out)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        specs = ctx.specs
+        n = len(specs)
+        saved = ctx.saved_tensors
+        feats = saved[:n]
+        rs_it = iter(saved[2 * n:])
+        keep = [(saved[n + i], next(rs_it) if ctx.has_rs[i] else None) for i in range(n)]
+        d_feats, d_o = grads[:n], grads[n]
+        need_x = ctx.needs_input_grad[0]
+        pgrads = [None] * ctx.n_params
+        pidx = []                       # first parameter slot of every block
+        k = 0
+        for sp in specs:
+            pidx.append(k)
+            k += 6 if sp["sk"] is not None else 4
+        wants = ctx.needs_input_grad[2:]
+
+        def bias_into(b, slot, dy):
+            """bias gradient by a separate pass (the chain's end, or no sink): column sums of dy."""
+            if b is None or not wants[slot]:
+                return
+            sink = _sink(b)
+            if sink is not None:
+                K.bias_grad(dy, acc_into=sink)
+            else:
+                g = K.bias_grad(dy)
+                pgrads[slot] = g if pgrads[slot] is None else pgrads[slot] + g
+
+        def wgrad(conv, slot, ksize, x, dy):
+            w, s, _, cache, sn = conv
+            if not wants[slot]:
+                return
+            _, dw, _ = _conv_backward(ksize, x, w, s, dy, False, True, False, cache, sn)
+            pgrads[slot] = dw              # None when a sink took it
+
+        if d_o is None:                    # only features were used downstream
+            d_o = torch.zeros(ctx.out_shape, dtype=torch.float32, device=feats[0].device)
+        d_o = d_o.contiguous()
+        q = None                           # 0.25 * d_o when the current block is pooled and has a skip conv
+        fused_bias = False                 # True when the previous pass already accumulated this block's c1 / sk bias sums
+        dx0 = None
+        for i in reversed(range(n)):
+            sp = specs[i]
+            h, rs = keep[i]
+            r = feats[i]
+            p0 = pidx[i]
+            w0, s0, b0, c0, _ = sp["c0"]
+            w1, s1, b1, c1, _ = sp["c1"]
+            if not fused_bias:
+                bias_into(b1, p0 + 3, d_o)
+                if sp["sk"] is not None:
+                    bias_into(sp["sk"][2], p0 + 5, d_o)
+            # second conv (+ avg-pool): data gradient, weight gradient
+            dh2 = K.avgpool2_bwd(d_o) if sp["down"] else d_o
+            dh = K.conv_fwd(dh2, _packed(w1, c1, True), 3, scale=s1)
+            wgrad(sp["c1"], p0 + 2, 3, h, dh2)
+            del dh2
+            # ReLU between the convs + bias gradient of the first conv, one pass
+            b0_sink = _sink(b0) if (b0 is not None and wants[p0 + 1]) else None
+            dh_m = K.relu_bwd_fused(h, dh, bias_a=b0_sink)
+            del dh
+            if b0_sink is None:
+                bias_into(b0, p0 + 1, dh_m)
+            # skip branch: its gradient w.r.t. the block input becomes the residual operand of the first conv's data gradient
+            if sp["sk"] is not None:
+                ws, ss, bs, cs, _ = sp["sk"]
+                if sp["down"] and q is not None:
+                    d_skip, mode = K.conv_fwd(q, _packed(ws, cs, True), 1, scale=ss), 2          # stays at half resolution
+                else:
+                    d_skip, mode = K.conv_fwd(d_o, _packed(ws, cs, True), 1, scale=ss), 1
+                    if sp["down"]:
+                        d_skip = K.avgpool2_bwd(d_skip)
+                wgrad(sp["sk"], p0 + 4, 1, rs, d_o)
+            else:
+                d_skip, mode = d_o, 1
+            last = i == 0
+            if need_x or not last:
+                dr = K.conv_fwd(dh_m, _packed(w0, c0, True), 3, scale=s0, residual=d_skip, residual_mode=mode)
+            wgrad(sp["c0"], p0, 3, r, dh_m)
+            del dh_m, d_skip
+            if last:
+                if need_x:
+                    dx0 = K.relu_bwd_fused(r, dr, add=d_feats[0].contiguous() if d_feats[0] is not None else None)
+                break
+            # the block input's in-place ReLU + feature-matching gradient + bias sums / quarter copy for the block before
+            pv = specs[i - 1]
+            pp = pidx[i - 1]
+            ba = _sink(pv["c1"][2]) if (pv["c1"][2] is not None and wants[pp + 3]) else None
+            bb = _sink(pv["sk"][2]) if (pv["sk"] is not None and pv["sk"][2] is not None and wants[pp + 5]) else None
+            want_q = pv["down"] and pv["sk"] is not None
+            add = d_feats[i].contiguous() if d_feats[i] is not None else None
+            res = K.relu_bwd_fused(r, dr, add=add, want_quarter=want_q, bias_a=ba, bias_b=bb)
+            d_o, q = res if want_q else (res, None)
+            del dr
+            fused_bias = True
+            # biases the fused pass could not take (no sink): separate column sums
+            if ba is None:
+                bias_into(pv["c1"][2], pp + 3, d_o)
+            if pv["sk"] is not None and bb is None:
+                bias_into(pv["sk"][2], pp + 5, d_o)
+        return (dx0, None, *pgrads)
+
+
+def disc_blocks(x0, specs):
+    params = []
+    for sp in specs:
+        for key in ("c0", "c1", "sk"):
+            if sp[key] is not None:
+                params += [sp[key][0], sp[key][2]]
+    outs = DiscBlocksFn.apply(x0, specs, *params)
+    return list(outs[:-1]), outs[-1]
+
+
 class AvgPool2Fn(torch.autograd.Function):
     """avg_pool2d(x, 2) (+ addend) — nn.AvgPool2d(2) at blocks.py:89-90,101-102, discriminator :62,66."""
 

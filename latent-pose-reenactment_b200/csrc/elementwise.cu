@@ -571,6 +571,58 @@ __global__ void bias_grad_kernel(const float* __restrict__ dy, float* __restrict
     }
 }
 
+// dx[p][c] = y[p][c] > 0 ? dy[p][c] + add[p][c] : 0   (ReLU backward, optionally merging a second incoming gradient),
+// optionally dq = 0.25 * dx (the gradient behind a 2x2 average pool, consumed at the low resolution) and the column sums
+// db_a[c] += sum_p dx, db_b[c] += sum_p dx (bias gradients of the convolutions whose output gradient dx is).
+// Same blocking as bias_grad_kernel: block = (C/4 channel quads) x rows, a pixel range per block, two rows in flight.
+__global__ void __launch_bounds__(kEwThreads)
+relu_bwd_fused_kernel(const float* __restrict__ y, const float* __restrict__ dy, const float* __restrict__ add,
+                      float* __restrict__ dx, float* __restrict__ dq, float* __restrict__ db_a, float* __restrict__ db_b,
+                      long pixels, int C, long pix_per_block) {
+    extern __shared__ float sm[];  // [rows][C]
+    const int cq = C >> 2;
+    const int lane_c = threadIdx.x % cq;
+    const int row = threadIdx.x / cq;
+    const int rows = blockDim.x / cq;
+    const long p0 = blockIdx.x * pix_per_block;
+    long p1 = p0 + pix_per_block;
+    if (p1 > pixels) p1 = pixels;
+    float4 acc = make_float4(0, 0, 0, 0);
+    if (row < rows) {
+        auto one = [&](long p, float4 m, float4 g, float4 a2) {
+            float4 v;
+            v.x = m.x > 0.f ? g.x + a2.x : 0.f; v.y = m.y > 0.f ? g.y + a2.y : 0.f;
+            v.z = m.z > 0.f ? g.z + a2.z : 0.f; v.w = m.w > 0.f ? g.w + a2.w : 0.f;
+            const size_t off = static_cast<size_t>(p) * C + lane_c * 4;
+            st4(dx + off, v);
+            if (dq) st4(dq + off, make_float4(0.25f * v.x, 0.25f * v.y, 0.25f * v.z, 0.25f * v.w));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        };
+        const float4 zero = make_float4(0, 0, 0, 0);
+        long p = p0 + row;
+        for (; p + rows < p1; p += 2L * rows) {
+            const size_t o0 = static_cast<size_t>(p) * C + lane_c * 4, o1 = static_cast<size_t>(p + rows) * C + lane_c * 4;
+            const float4 m0 = ld4(y + o0), m1 = ld4(y + o1), g0 = ld4(dy + o0), g1 = ld4(dy + o1);
+            const float4 a0 = add ? ld4(add + o0) : zero, a1 = add ? ld4(add + o1) : zero;
+            one(p, m0, g0, a0);
+            one(p + rows, m1, g1, a1);
+        }
+        for (; p < p1; p += rows) {
+            const size_t o0 = static_cast<size_t>(p) * C + lane_c * 4;
+            one(p, ld4(y + o0), ld4(dy + o0), add ? ld4(add + o0) : zero);
+        }
+    }
+    if (db_a == nullptr && db_b == nullptr) return;
+    if (row < rows) st4(sm + static_cast<size_t>(row) * C + lane_c * 4, acc);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float t = 0.f;
+        for (int r = 0; r < rows; ++r) t += sm[static_cast<size_t>(r) * C + c];
+        if (db_a) atomicAdd(db_a + c, t);
+        if (db_b) atomicAdd(db_b + c, t);
+    }
+}
+
 // dst[i] <- src[i] for a table of small buffers (one block per buffer): the running-average copies of BatchNorm /
 // spectral-norm buffers (runners/holycow.py:106-109) are ~370 tiny tensors per step
 struct CopyItem {
@@ -853,6 +905,23 @@ extern "C" int32_t b200lp_bias_grad(const float* dy, float* db, int64_t pixels, 
 
 extern "C" int32_t b200lp_bias_grad_acc(const float* dy, float* db, int64_t pixels, int32_t C, void* stream) {
     return bias_grad_impl(dy, db, pixels, C, 1, stream);
+}
+
+extern "C" int32_t b200lp_relu_bwd_fused(const float* y, const float* dy, const float* add, float* dx, float* dq,
+                                         float* db_a, float* db_b, int64_t pixels, int32_t C, void* stream) {
+    B200LP_REQUIRE(y && dy && dx && pixels > 0 && C > 0 && C % 4 == 0 && C / 4 <= kEwThreads,
+                   "relu_bwd_fused: bad args (C=%d must be a multiple of 4, <= %d)", C, 4 * kEwThreads);
+    const int rows = kEwThreads / (C / 4);
+    long blocks = 148 * 4;
+    long ppb = (pixels + blocks - 1) / blocks;
+    if (ppb < 2L * rows) ppb = 2L * rows;
+    blocks = (pixels + ppb - 1) / ppb;
+    const size_t smem = (db_a || db_b) ? static_cast<size_t>(rows) * C * 4 : 0;
+    relu_bwd_fused_kernel<<<static_cast<int>(blocks), kEwThreads, smem, as_stream(stream)>>>(y, dy, add, dx, dq, db_a, db_b,
+                                                                                             pixels, C, ppb);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
 }
 
 static int32_t bias_grad_impl(const float* dy, float* db, int64_t pixels, int32_t C, int32_t accumulate, void* stream) {

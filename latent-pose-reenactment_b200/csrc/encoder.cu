@@ -211,7 +211,8 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, double count,
     const int c = blockIdx.x * 32 + cl;
     double s1 = 0.0, s2 = 0.0;
     if (c < C)
-        for (int i = pl; i < nparts; i += 32) {
+#pragma unroll 8
+        for (int i = pl; i < nparts; i += 32) {          // independent loads: 16 in flight per thread
             s1 += static_cast<double>(part[(static_cast<size_t>(i) * 2 + 0) * C + c]);
             s2 += static_cast<double>(part[(static_cast<size_t>(i) * 2 + 1) * C + c]);
         }

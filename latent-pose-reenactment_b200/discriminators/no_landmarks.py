@@ -7,6 +7,7 @@ more spectral-norm power iteration, like the reference's forward pre-hooks.  Fea
 them without a layout copy.
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -109,16 +110,38 @@ class Discriminator(nn.Module):
         s = ops.conv_c3(xs, torch.nn.functional.pad(ws, (1, 1, 1, 1)), ss, bs)
         out = ops.avgpool2(h2, s)
 
-        feats = []
-        for block in self.blocks:
-            r = ops.relu_round(out)        # the reference's in-place ReLU: this is also what `feats` holds
-            feats.append(r)
-            out = block(r, detach_params)
+        specs = None if os.environ.get('B200LP_NO_DISC_NODE') else self._block_specs(detach_params)
+        if specs is not None:
+            # the whole block chain as one autograd node with a hand-scheduled backward (ops.DiscBlocksFn)
+            feats, out = ops.disc_blocks(out, specs)
+        else:
+            feats = []
+            for block in self.blocks:
+                r = ops.relu_round(out)        # the reference's in-place ReLU: this is also what `feats` holds
+                feats.append(r)
+                out = block(r, detach_params)
         feats.append(out)                  # the last feature stays pre-ReLU (reference :100 is out of place)
         wl, sl, bl = self.linear.operands_edge(detach_params)
         # relu -> spatial sum -> SN-linear + projection onto the label embedding as one kernel (+ two backward)
         score = ops.disc_head(out, embed, wl, sl, bl)
         return score, [f.permute(0, 3, 1, 2) for f in feats]
+
+    def _block_specs(self, detach_params):
+        """Operands of every block for ops.DiscBlocksFn, or None when a layer has no batched spectral-norm result (then
+        1/sigma carries an autograd edge and the per-layer nodes are used)."""
+        for block in self.blocks:
+            if any(conv._pre is None or conv._pre[1] is None for conv in block.tensor_core_convs()):
+                return None
+        specs = []
+        for block in self.blocks:
+            sp = dict(down=block.downsample, sk=None)
+            for key, conv in (("c0", block.block.slot(2)), ("c1", block.block.slot(5)),
+                              ("sk", block.skip.slot(0) if block.skip is not None else None)):
+                if conv is not None:
+                    w, s, b, e = conv.operands(detach_params)
+                    sp[key] = (w, s, b, e["cache"], e["sn"])
+            specs.append(sp)
+        return specs
 
     def _tensor_core_convs(self):
         """The spectral-normalised convs that run on the tensor cores (everything except the two Cin=3 stem convs)."""

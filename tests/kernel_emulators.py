@@ -167,6 +167,15 @@ def relu_bwd(y, dy):
     return dy * (y > 0)
 
 
+def relu_bwd_fused(y, dy, add=None, want_quarter=False, bias_a=None, bias_b=None):
+    dx = (dy if add is None else dy + add) * (y > 0)
+    col = dx.reshape(-1, dx.shape[-1]).sum(0)
+    for b in (bias_a, bias_b):
+        if b is not None:
+            b.add_(col)
+    return (dx, 0.25 * dx) if want_quarter else dx
+
+
 def avgpool2(x, addend=None, round_tf32=False):
     y = F.avg_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).contiguous()
     return y + addend if addend is not None else y
@@ -379,7 +388,7 @@ EMULATED = [
     "sgemm", "dice_fwd", "dice_bwd", "adversarial_fwd", "adversarial_bwd", "crop_bilinear_fwd", "crop_bilinear_bwd",
     "disc_head_fwd", "disc_head_bwd",
     "pack_conv_weight", "conv_fwd", "conv_wgrad", "conv_wgrad_sn_acc", "bias_grad", "sn_scratch", "sn_sigma_multi",
-    "sn_wgrad_fix", "in_stats", "adain_relu", "adain_relu_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "relu_round", "relu_bwd",
+    "sn_wgrad_fix", "in_stats", "adain_relu", "adain_relu_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "relu_round", "relu_bwd", "relu_bwd_fused",
     "avgpool2", "avgpool2_bwd", "upsample2_bwd", "l1_sum", "l1_bwd", "l1_relu_bwd", "conv3x3_c3_fwd", "im2col3x3_c3",
     "col2im3x3_c3", "gen_tail_fwd", "gen_tail_compose", "gen_tail_bwd_act", "gen_tail_bwd", "copy_plan", "copy_multi",
 ]

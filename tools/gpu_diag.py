@@ -1151,6 +1151,37 @@ def encoder_gconv():
 
 
 @check
+def relu_bwd_fused():
+    """b200lp_relu_bwd_fused (mask + second gradient + 0.25 copy + bias column sums) vs float64 torch, ragged pixel counts."""
+    import torch
+    from b200lp import kernels as K
+    out = []
+    torch.manual_seed(13)
+    dev = "cuda"
+    for (pix, c) in [(8 * 128 * 128, 64), (8 * 16 * 16, 512), (3 * 7 * 5, 128), (1, 4), (8 * 4 * 4, 1024), (1000, 36)]:
+        y = torch.randn(pix, c, device=dev).relu()
+        dy = torch.randn(pix, c, device=dev)
+        add = torch.randn(pix, c, device=dev)
+        for use_add, use_q, nb in ((False, False, 0), (True, True, 2), (True, False, 1), (False, True, 1)):
+            ba = torch.randn(c, device=dev) if nb >= 1 else None
+            bb = torch.randn(c, device=dev) if nb >= 2 else None
+            ba0 = ba.clone() if ba is not None else None
+            bb0 = bb.clone() if bb is not None else None
+            res = K.relu_bwd_fused(y, dy, add=add if use_add else None, want_quarter=use_q, bias_a=ba, bias_b=bb)
+            dx, dq = res if use_q else (res, None)
+            ref = (dy.double() + (add.double() if use_add else 0)) * (y > 0)
+            tag = f"pix{pix} C{c} add{int(use_add)} q{int(use_q)} bias{nb}"
+            out.append(_cmp(f"relu_bwd_fused dx {tag}", dx, ref, 1e-6))
+            if use_q:
+                out.append(_cmp(f"relu_bwd_fused dq {tag}", dq, 0.25 * ref, 1e-6))
+            if ba is not None:
+                out.append(_cmp(f"relu_bwd_fused bias_a {tag}", ba - ba0, ref.sum(0), 2e-5))
+            if bb is not None:
+                out.append(_cmp(f"relu_bwd_fused bias_b {tag}", bb - bb0, ref.sum(0), 2e-5))
+    return out
+
+
+@check
 def gconv_tc():
     """Grouped 3x3 convolution on the tensor cores (block-diagonal 32 / 64-channel tiles): conv_fwd(grouped) forward in
     tf32 and bf16x3, data gradient through the transposed packing (stride 2 via the zero-stuffed gradient), weight gradient
