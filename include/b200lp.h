@@ -237,9 +237,10 @@ int32_t b200lp_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, v
  *   dx = [y > 0] * (dy + add)            add (optional): a second gradient of the same tensor (feature-matching term)
  *   dq = 0.25 * dx                       (optional) the gradient behind an AvgPool2d(2), kept at the low resolution
  *   db_a[c] += sum_p dx[p][c], db_b[c] += ...   (optional) bias gradients of the convs that produced the tensor
- * y, dy, add, dx, dq: [pixels][C]; C % 4 == 0, C <= 1024. */
+ * round_tf32: dx (and dq) are stored rounded to nearest tf32 — they only feed tf32 MMAs, which would otherwise truncate;
+ * the bias sums use the unrounded values.   y, dy, add, dx, dq: [pixels][C]; C % 4 == 0, C <= 1024. */
 int32_t b200lp_relu_bwd_fused(const float* y, const float* dy, const float* add, float* dx, float* dq, float* db_a,
-                              float* db_b, int64_t pixels, int32_t C, void* stream);
+                              float* db_b, int64_t pixels, int32_t C, int32_t round_tf32, void* stream);
 /* 2x2 average pool / its backward (nn.AvgPool2d(2): blocks.py:89-90,101-102; perceptual_loss.py:77) */
 int32_t b200lp_avgpool2(const float* x, const float* addend, float* y, int32_t N, int32_t H, int32_t W, int32_t C,
                         int32_t round_tf32, void* stream);

@@ -310,8 +310,9 @@ def relu_bwd(y, dy):
     return dx
 
 
-def relu_bwd_fused(y, dy, add=None, want_quarter=False, bias_a=None, bias_b=None):
-    """dx = [y > 0] * (dy + add); optionally dq = 0.25 * dx; bias_a / bias_b (C,) += column sums of dx (in place).
+def relu_bwd_fused(y, dy, add=None, want_quarter=False, bias_a=None, bias_b=None, round_tf32=False):
+    """dx = [y > 0] * (dy + add); optionally dq = 0.25 * dx; bias_a / bias_b (C,) += column sums of dx (in place);
+    round_tf32: dx / dq stored rounded to tf32 (operands of the following data / weight gradient MMAs).
     Returns dx or (dx, dq)."""
     lib = L.load()
     c = y.shape[-1]
@@ -320,7 +321,8 @@ def relu_bwd_fused(y, dy, add=None, want_quarter=False, bias_a=None, bias_b=None
     nb = 12.0 + (4.0 if add is not None else 0.0) + (4.0 if want_quarter else 0.0)
     with _timed("elementwise", nbytes=nb * y.numel()):
         L.check(lib.b200lp_relu_bwd_fused(L.ptr(y), L.ptr(dy), L.ptr(add), L.ptr(dx), L.ptr(dq), L.ptr(bias_a),
-                                          L.ptr(bias_b), y.numel() // c, c, L.stream_ptr()), "relu_bwd_fused")
+                                          L.ptr(bias_b), y.numel() // c, c, int(round_tf32), L.stream_ptr()),
+                "relu_bwd_fused")
     return (dx, dq) if want_quarter else dx
 
 

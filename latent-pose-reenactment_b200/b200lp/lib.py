@@ -88,7 +88,7 @@ SIGNATURES = {
     "b200lp_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b200lp_relu_round": (_I, [_P, _P, _L, _P]),
     "b200lp_relu_bwd": (_I, [_P, _P, _P, _L, _P]),
-    "b200lp_relu_bwd_fused": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
+    "b200lp_relu_bwd_fused": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
     "b200lp_avgpool2": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200lp_avgpool2_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b200lp_upsample2_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P]),

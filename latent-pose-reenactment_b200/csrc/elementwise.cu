@@ -578,7 +578,7 @@ __global__ void bias_grad_kernel(const float* __restrict__ dy, float* __restrict
 __global__ void __launch_bounds__(kEwThreads)
 relu_bwd_fused_kernel(const float* __restrict__ y, const float* __restrict__ dy, const float* __restrict__ add,
                       float* __restrict__ dx, float* __restrict__ dq, float* __restrict__ db_a, float* __restrict__ db_b,
-                      long pixels, int C, long pix_per_block) {
+                      long pixels, int C, long pix_per_block, int round_out) {
     extern __shared__ float sm[];  // [rows][C]
     const int cq = C >> 2;
     const int lane_c = threadIdx.x % cq;
@@ -594,9 +594,10 @@ relu_bwd_fused_kernel(const float* __restrict__ y, const float* __restrict__ dy,
             v.x = m.x > 0.f ? g.x + a2.x : 0.f; v.y = m.y > 0.f ? g.y + a2.y : 0.f;
             v.z = m.z > 0.f ? g.z + a2.z : 0.f; v.w = m.w > 0.f ? g.w + a2.w : 0.f;
             const size_t off = static_cast<size_t>(p) * C + lane_c * 4;
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;          // bias sums of the unrounded values
+            if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
             st4(dx + off, v);
             if (dq) st4(dq + off, make_float4(0.25f * v.x, 0.25f * v.y, 0.25f * v.z, 0.25f * v.w));
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         };
         const float4 zero = make_float4(0, 0, 0, 0);
         long p = p0 + row;
@@ -908,7 +909,8 @@ extern "C" int32_t b200lp_bias_grad_acc(const float* dy, float* db, int64_t pixe
 }
 
 extern "C" int32_t b200lp_relu_bwd_fused(const float* y, const float* dy, const float* add, float* dx, float* dq,
-                                         float* db_a, float* db_b, int64_t pixels, int32_t C, void* stream) {
+                                         float* db_a, float* db_b, int64_t pixels, int32_t C, int32_t round_tf32,
+                                         void* stream) {
     B200LP_REQUIRE(y && dy && dx && pixels > 0 && C > 0 && C % 4 == 0 && C / 4 <= kEwThreads,
                    "relu_bwd_fused: bad args (C=%d must be a multiple of 4, <= %d)", C, 4 * kEwThreads);
     const int rows = kEwThreads / (C / 4);
@@ -918,7 +920,7 @@ extern "C" int32_t b200lp_relu_bwd_fused(const float* y, const float* dy, const 
     blocks = (pixels + ppb - 1) / ppb;
     const size_t smem = (db_a || db_b) ? static_cast<size_t>(rows) * C * 4 : 0;
     relu_bwd_fused_kernel<<<static_cast<int>(blocks), kEwThreads, smem, as_stream(stream)>>>(y, dy, add, dx, dq, db_a, db_b,
-                                                                                             pixels, C, ppb);
+                                                                                             pixels, C, ppb, round_tf32);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

@@ -17,6 +17,8 @@
 // Reductions are two-stage with a fixed order (no atomics): results are bit-reproducible.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -1327,7 +1329,9 @@ extern "C" int32_t b200lp_sgemm_strided(const float* A, int64_t sai, int64_t sak
                                         float* C, const float* alpha_dev, const float* bias, int32_t M, int32_t N, int32_t K,
                                         int32_t accumulate, float* workspace, int64_t workspace_bytes, void* stream) {
     B200LP_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "sgemm_strided: bad args");
-    if (M <= 8 && sak == 1 && (sbk == 1 || sbj == 1)) {           // skinny path: A row-major, B contiguous along k or n
+    // measurement switch (A/B runs only): B200LP_NO_SKINNY_SGEMM=1 sends batch-sized products through the 64 x 64 tile kernel
+    static const bool no_skinny = getenv("B200LP_NO_SKINNY_SGEMM") != nullptr;
+    if (!no_skinny && M <= 8 && sak == 1 && (sbk == 1 || sbj == 1)) {   // skinny path: A row-major, B contiguous along k or n
         cudaStream_t st = as_stream(stream);
         int kps;
         int sp = skinny_splits(N, K, &kps);

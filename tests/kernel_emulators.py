@@ -167,7 +167,7 @@ def relu_bwd(y, dy):
     return dy * (y > 0)
 
 
-def relu_bwd_fused(y, dy, add=None, want_quarter=False, bias_a=None, bias_b=None):
+def relu_bwd_fused(y, dy, add=None, want_quarter=False, bias_a=None, bias_b=None, round_tf32=False):
     dx = (dy if add is None else dy + add) * (y > 0)
     col = dx.reshape(-1, dx.shape[-1]).sum(0)
     for b in (bias_a, bias_b):

@@ -361,3 +361,43 @@ def test_pose_encoder_train_mode_with_dropout_at_bench_shape():
     gb = torch.cat([q.grad.flatten() for q in b.parameters()]).double()
     cos = float((ga * gb).sum() / (ga.norm() * gb.norm()))
     assert cos > 0.995 and abs(float(ga.norm() / gb.norm()) - 1) < 2e-2, (cos, float(ga.norm() / gb.norm()))
+
+
+def test_discriminator_block_node_equals_per_layer_path(monkeypatch):
+    """ops.DiscBlocksFn (one autograd node, kernel-merged gradients) against the per-layer autograd nodes on the SAME
+    kernels, weights and inputs at the full channel widths (256 x 256, bs 2): scores, features, the image gradient and
+    every parameter gradient.  The merged gradients are summed in another fp32 order and the node stores its ReLU-backward
+    outputs rounded (not truncated) to tf32, so single operands of the following tf32 MMAs move by one tf32 ulp (2^-11):
+    1e-3 of the largest element bounds it; anything structural (a missing term) is O(1)."""
+    import copy
+    from helpers import make_args
+    from b200lp import ops
+    cfg = dict(synth.FULL_CFG)
+    args = make_args(cfg, device=DEV)
+    torch.manual_seed(5)
+    D0 = importlib.import_module("discriminators.no_landmarks").Wrapper.get_net(args).to(DEV).train()
+    x = torch.rand(2, 3, 256, 256, device=DEV)
+    emb = torch.randn(2, 512, device=DEV) * 0.1
+    results = {}
+    for mode in ("node", "layers"):
+        if mode == "layers":
+            monkeypatch.setenv("B200LP_NO_DISC_NODE", "1")
+        else:
+            monkeypatch.delenv("B200LP_NO_DISC_NODE", raising=False)
+        D = copy.deepcopy(D0)
+        xi = x.clone().requires_grad_(True)
+        score, feats = D.pass_inputs(xi, emb)
+        torch.manual_seed(9)
+        loss = (score * torch.randn_like(score)).sum() + sum((f * torch.randn_like(f)).sum() * 1e-3 for f in feats)
+        bufs = {n: torch.zeros_like(p) for n, p in D.named_parameters()}
+        with ops.direct_grads({p.data_ptr(): bufs[n] for n, p in D.named_parameters()}):
+            loss.backward()
+        grads = {n: (bufs[n] + (p.grad if p.grad is not None else 0)) for n, p in D.named_parameters()}
+        results[mode] = (score.detach(), [f.detach() for f in feats], xi.grad.clone(), grads)
+    a, b = results["node"], results["layers"]
+    assert max_abs(a[0], b[0]) == 0.0
+    for fa, fb in zip(a[1], b[1]):
+        assert max_abs(fa, fb) == 0.0
+    assert rel_err(a[2], b[2]) < 1e-3, rel_err(a[2], b[2])
+    worst = max((rel_err(a[3][n], b[3][n]), n) for n in a[3] if float(b[3][n].abs().max()) > 0)
+    assert worst[0] < 1e-3, worst
