@@ -109,6 +109,12 @@ int32_t b200lp_pack_conv_weight(const float* w_oihw, const float* scale, void* w
 int32_t b200lp_pack_conv_weight_multi(const void* table, const int32_t* chunk_item, const int64_t* chunk_off,
                                       int32_t n_chunks, int64_t chunk_elems, void* stream);
 
+/* Tiled form of the multi-tensor packing (same `table` rows; taps <= 9): one block per 32 (co) x 32 (ci) tile, tile t of
+ * row tile_item[t] is tile_index[t] = co_tile * ceil(Cin/32) + ci_tile.  Source rows are read coalesced through shared
+ * memory; results are bit-identical to b200lp_pack_conv_weight. */
+int32_t b200lp_pack_conv_weight_tiles(const void* table, const int32_t* tile_item, const int32_t* tile_index,
+                                      int32_t n_tiles, void* stream);
+
 /* Grouped 3x3 weight w[C][cpg][3][3] (groups of cpg channels, cpg divides `block`; block = 32 for tf32, 64 for bf16x3)
  * as block-diagonal dense tiles for b200lp_conv_fwd(grouped = 1):
  *   transpose = 0:  wp[co][tap][j]     = w[co][ci - g*cpg][tap]    if ci = (co/block)*block + j lies in co's group g, else 0
@@ -256,6 +262,15 @@ int32_t b200lp_l1_bwd(const float* a, const float* b, const float* gscale, float
  *   d_out = [a > 0] * ( (d_in or 0) + sign(a-b) * gscale[0]*scale2 )      = l1_bwd followed by relu_bwd */
 int32_t b200lp_l1_relu_bwd(const float* a, const float* b, const float* gscale, float scale2, const float* d_in,
                            float* d_out, int64_t n, void* stream);
+/* The same tap split so that the backward pass needs neither feature map: the forward pass adds scale * sum|a-b| to out[0]
+ * and writes one code byte per 4 elements (2 bits each: 0 = a <= 0, 1 / 2 / 3 = a > 0 and sign(a-b) = -1 / 0 / +1);
+ *   d_out = code ? tf32( (d_in or 0) + (code - 2) * gscale[0]*scale2 ) : 0
+ * code: [n/4] bytes.  24 -> 16.5 bytes of HBM traffic per element and tap, and the real-image branch's activations are
+ * not kept for the backward pass (criterions/common/perceptual_loss.py:104-110). */
+int32_t b200lp_l1_sum_code(const float* a, const float* b, float* out, uint8_t* code, int64_t n, float scale,
+                           void* stream);
+int32_t b200lp_l1_code_bwd(const uint8_t* code, const float* gscale, float scale2, const float* d_in, float* d_out,
+                           int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Direct (CUDA-core) convolutions for the two degenerate, HBM-bound shapes (SURVEY §7 "Degenerate GEMM shapes").

@@ -89,24 +89,26 @@ PACK_CHUNK = 16384
 def pack_plan(rows, device):
     """Device-side table for `pack_conv_weight_multi`: rows = [(w_ptr, wp_ptr, Cout, Cin, taps, transpose, precision,
     numel), ...] (include/b200lp.h)."""
-    chunk_item, chunk_off = [], []
+    tile_item, tile_index = [], []
     for i, r in enumerate(rows):
-        for o in range(0, r[7], PACK_CHUNK):
-            chunk_item.append(i)
-            chunk_off.append(o)
+        assert r[4] <= 9, r
+        tiles = ((r[2] + 31) // 32) * ((r[3] + 31) // 32)
+        tile_item += [i] * tiles
+        tile_index += list(range(tiles))
     return dict(table=torch.tensor(rows, dtype=torch.int64, device=device),
-                chunk_item=torch.tensor(chunk_item, dtype=torch.int32, device=device),
-                chunk_off=torch.tensor(chunk_off, dtype=torch.int64, device=device), n_chunks=len(chunk_item),
+                tile_item=torch.tensor(tile_item, dtype=torch.int32, device=device),
+                tile_index=torch.tensor(tile_index, dtype=torch.int32, device=device), n_tiles=len(tile_item),
                 nbytes=8.0 * sum(r[7] for r in rows))
 
 
 def pack_conv_weight_multi(plan):
+    """One launch re-packs every copy of the plan: a block per 32 x 32 (co, ci) tile, coalesced on both sides."""
     lib = L.load()
     with _timed("pack_conv_weight", nbytes=plan["nbytes"]):
-        L.check(lib.b200lp_pack_conv_weight_multi(c_void_p(plan["table"].data_ptr()),
-                                                  c_void_p(plan["chunk_item"].data_ptr()),
-                                                  c_void_p(plan["chunk_off"].data_ptr()), plan["n_chunks"], PACK_CHUNK,
-                                                  L.stream_ptr()), "pack_conv_weight_multi")
+        L.check(lib.b200lp_pack_conv_weight_tiles(c_void_p(plan["table"].data_ptr()),
+                                                  c_void_p(plan["tile_item"].data_ptr()),
+                                                  c_void_p(plan["tile_index"].data_ptr()), plan["n_tiles"],
+                                                  L.stream_ptr()), "pack_conv_weight_tiles")
 
 
 def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False, round_tf32=False, block_n=0,
@@ -359,6 +361,28 @@ def l1_sum(a, b, out, scale):
     lib = L.load()
     with _timed("l1", nbytes=8.0 * a.numel()):
         L.check(lib.b200lp_l1_sum(L.ptr(a), L.ptr(b), L.ptr(out), a.numel(), c_float(scale), L.stream_ptr()), "l1_sum")
+
+
+def l1_sum_code(a, b, out, scale):
+    """out[0] += scale * sum|a-b|; returns the backward code tensor (uint8, a.numel() / 4 bytes: 2 bits per element, ReLU mask
+    of `a` and sign(a-b)) that `l1_code_bwd` consumes instead of the two feature maps."""
+    lib = L.load()
+    code = torch.empty((a.numel() // 4,), dtype=torch.uint8, device=a.device)
+    with _timed("l1", nbytes=8.25 * a.numel()):
+        L.check(lib.b200lp_l1_sum_code(L.ptr(a), L.ptr(b), L.ptr(out), L.ptr(code, torch.uint8), a.numel(), c_float(scale),
+                                       L.stream_ptr()), "l1_sum_code")
+    return code
+
+
+def l1_code_bwd(code, shape, gscale, scale2, d_in=None):
+    """d_out = mask * tf32(d_in + sign * gscale[0] * scale2) from the code of l1_sum_code; `shape`: the feature's shape."""
+    lib = L.load()
+    d = torch.empty(shape, dtype=torch.float32, device=code.device)
+    assert d.numel() == 4 * code.numel()
+    with _timed("l1", nbytes=(4.25 + (4.0 if d_in is not None else 0.0)) * d.numel()):
+        L.check(lib.b200lp_l1_code_bwd(L.ptr(code, torch.uint8), L.ptr(gscale), c_float(scale2), L.ptr(d_in), L.ptr(d),
+                                       d.numel(), L.stream_ptr()), "l1_code_bwd")
+    return d
 
 
 def l1_bwd(a, b, gscale, scale2, da=None):

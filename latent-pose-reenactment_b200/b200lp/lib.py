@@ -66,6 +66,7 @@ SIGNATURES = {
     "b200lp_conv_fwd": (_I, [POINTER(ConvArgs), _P]),
     "b200lp_pack_conv_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200lp_pack_conv_weight_multi": (_I, [_P, _P, _P, _I, _L, _P]),
+    "b200lp_pack_conv_weight_tiles": (_I, [_P, _P, _P, _I, _P]),
     "b200lp_pack_gconv_weight": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b200lp_sn_max_tensors": (_I, []),
     "b200lp_sn_scratch_floats": (_L, [_I, _I]),
@@ -95,6 +96,8 @@ SIGNATURES = {
     "b200lp_l1_sum": (_I, [_P, _P, _P, _L, _F, _P]),
     "b200lp_l1_bwd": (_I, [_P, _P, _P, _F, _P, _L, _I, _P]),
     "b200lp_l1_relu_bwd": (_I, [_P, _P, _P, _F, _P, _P, _L, _P]),
+    "b200lp_l1_sum_code": (_I, [_P, _P, _P, _P, _L, _F, _P]),
+    "b200lp_l1_code_bwd": (_I, [_P, _P, _F, _P, _P, _L, _P]),
     "b200lp_conv3x3_c3_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "b200lp_conv3x3_c3_dgrad": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200lp_conv3x3_c3_wgrad": (_I, [_P, _P, _P, _F, _I, _I, _I, _I, _P]),

@@ -771,7 +771,8 @@ class VggPerceptualFn(torch.autograd.Function):
         dev = fake_nchw.device
         loss = torch.zeros(1, dtype=torch.float32, device=dev)
         a = b = None
-        saved = []          # per ReLU tap: (a_feat, b_feat)
+        saved = []          # per ReLU tap: (backward code of l1_sum_code, feature shape)
+        need_bwd = ctx.needs_input_grad[0]
         fake = fake_nchw.contiguous()
         real = real_nchw.contiguous()
         n_taps = 0
@@ -788,8 +789,10 @@ class VggPerceptualFn(torch.autograd.Function):
                 a = K.avgpool2(a, None, round_tf32=True)
                 b = K.avgpool2(b, None, round_tf32=True)
                 continue
-            K.l1_sum(a, b, loss, weight / a.numel())
-            saved.append((a, b))
+            if need_bwd:    # the L1 term and, in the same pass, the 2-bit (ReLU mask, sign) code the backward tap needs
+                saved.append((K.l1_sum_code(a, b, loss, weight / a.numel()), tuple(a.shape)))
+            else:
+                K.l1_sum(a, b, loss, weight / a.numel())
             n_taps += 1
         ctx.packed = packed
         ctx.weight = weight
@@ -809,10 +812,13 @@ class VggPerceptualFn(torch.autograd.Function):
             if kind == "pool":
                 d = K.avgpool2_bwd(d)
                 continue
-            a, b = saved[tap]
+            code, shape = saved[tap]
             tap -= 1
-            # d(loss)/d(a) gets the L1 term of this tap, then passes the ReLU mask (one fused pass)
-            d = K.l1_relu_bwd(a, b, gs, ctx.weight / a.numel(), d_in=d)
+            # d(loss)/d(a) gets the L1 term of this tap, then passes the ReLU mask (one pass over the code + d)
+            numel = 1
+            for v in shape:
+                numel *= v
+            d = K.l1_code_bwd(code, shape, gs, ctx.weight / numel, d_in=d)
             if kind == "conv":
                 d = K.conv_fwd(d, packed["wpt"][idx], 3)
             else:

@@ -523,6 +523,47 @@ __global__ void l1_relu_bwd_kernel(const float4* __restrict__ a, const float4* _
     }
 }
 
+// VGG tap, forward half of the fused L1: out[0] += scale * sum |a-b| AND one code byte per float4 for the backward pass:
+// 2 bits per element — 0: a <= 0 (ReLU mask closed), 1 / 2 / 3: a > 0 and sign(a-b) = -1 / 0 / +1.  The backward tap then
+// needs neither feature map (0.25 B instead of 8 B per element, and the `b` branch's activations are not kept alive).
+__global__ void l1_sum_code_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float* __restrict__ out,
+                                   unsigned char* __restrict__ code, long n4, float scale) {
+    float acc = 0.f;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const float4 u = __ldg(a + i), v = __ldg(b + i);
+        acc += (fabsf(u.x - v.x) + fabsf(u.y - v.y)) + (fabsf(u.z - v.z) + fabsf(u.w - v.w));
+        auto cd = [](float p, float q) -> unsigned { return p > 0.f ? (p > q ? 3u : (p < q ? 1u : 2u)) : 0u; };
+        code[i] = static_cast<unsigned char>(cd(u.x, v.x) | (cd(u.y, v.y) << 2) | (cd(u.z, v.z) << 4) | (cd(u.w, v.w) << 6));
+    }
+    __shared__ float ws[kEwThreads / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < kEwThreads / 32 ? ws[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(out, v * scale);
+    }
+}
+
+// backward half: d_out = code ? tf32(d_in + (code - 2) * g) : 0      (== l1_relu_bwd on the features the code came from)
+template <bool HAS_IN>
+__global__ void l1_code_bwd_kernel(const unsigned char* __restrict__ code, const float* __restrict__ gscale, float scale2,
+                                   const float4* __restrict__ d_in, float4* __restrict__ d_out, long n4) {
+    const float g = (gscale ? __ldg(gscale) : 1.f) * scale2;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const unsigned c = code[i];
+        float4 d = HAS_IN ? __ldg(d_in + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        auto one = [g](float din, unsigned cc) -> float {
+            return cc ? round_tf32(din + (static_cast<float>(cc) - 2.f) * g) : 0.f;
+        };
+        d.x = one(d.x, c & 3u); d.y = one(d.y, (c >> 2) & 3u); d.z = one(d.z, (c >> 4) & 3u); d.w = one(d.w, c >> 6);
+        d_out[i] = d;
+    }
+}
+
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, long total) {
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -819,6 +860,34 @@ extern "C" int32_t b200lp_l1_sum(const float* a, const float* b, float* out, int
     if (g > 148 * 4) g = 148 * 4;
     l1_sum_kernel<<<g, kEwThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a),
                                                           reinterpret_cast<const float4*>(b), out, n / 4, scale);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_l1_sum_code(const float* a, const float* b, float* out, uint8_t* code, int64_t n, float scale,
+                                      void* stream) {
+    B200LP_REQUIRE(a && b && out && code && n > 0 && n % 4 == 0, "l1_sum_code: bad args");
+    int g = grid_for(n / 4, kEwThreads);
+    if (g > 148 * 4) g = 148 * 4;
+    l1_sum_code_kernel<<<g, kEwThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a),
+                                                               reinterpret_cast<const float4*>(b), out, code, n / 4, scale);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_l1_code_bwd(const uint8_t* code, const float* gscale, float scale2, const float* d_in,
+                                      float* d_out, int64_t n, void* stream) {
+    B200LP_REQUIRE(code && d_out && n > 0 && n % 4 == 0, "l1_code_bwd: bad args");
+    const int g = grid_for(n / 4, kEwThreads);
+    if (d_in)
+        l1_code_bwd_kernel<true><<<g, kEwThreads, 0, as_stream(stream)>>>(code, gscale, scale2,
+                                                                          reinterpret_cast<const float4*>(d_in),
+                                                                          reinterpret_cast<float4*>(d_out), n / 4);
+    else
+        l1_code_bwd_kernel<false><<<g, kEwThreads, 0, as_stream(stream)>>>(code, gscale, scale2, nullptr,
+                                                                           reinterpret_cast<float4*>(d_out), n / 4);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

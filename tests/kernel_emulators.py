@@ -194,6 +194,17 @@ def l1_sum(a, b, out, scale):
     out += scale * (a - b).abs().sum()
 
 
+def l1_sum_code(a, b, out, scale):
+    out += scale * (a - b).abs().sum()
+    return torch.where(a > 0, torch.sign(a - b) + 2, torch.zeros_like(a))      # the emulated code keeps one value per element
+
+
+def l1_code_bwd(code, shape, gscale, scale2, d_in=None):
+    g = (gscale.reshape(()) if gscale is not None else 1.0) * scale2
+    d = (code - 2) * g + (d_in if d_in is not None else 0)
+    return torch.where(code > 0, d, torch.zeros_like(d)).reshape(shape)
+
+
 def l1_bwd(a, b, gscale, scale2, da=None):
     g = torch.sign(a - b) * (gscale.reshape(()) * scale2)
     if da is not None:
@@ -389,7 +400,7 @@ EMULATED = [
     "disc_head_fwd", "disc_head_bwd",
     "pack_conv_weight", "conv_fwd", "conv_wgrad", "conv_wgrad_sn_acc", "bias_grad", "sn_scratch", "sn_sigma_multi",
     "sn_wgrad_fix", "in_stats", "adain_relu", "adain_relu_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "relu_round", "relu_bwd", "relu_bwd_fused",
-    "avgpool2", "avgpool2_bwd", "upsample2_bwd", "l1_sum", "l1_bwd", "l1_relu_bwd", "conv3x3_c3_fwd", "im2col3x3_c3",
+    "avgpool2", "avgpool2_bwd", "upsample2_bwd", "l1_sum", "l1_sum_code", "l1_code_bwd", "l1_bwd", "l1_relu_bwd", "conv3x3_c3_fwd", "im2col3x3_c3",
     "col2im3x3_c3", "gen_tail_fwd", "gen_tail_compose", "gen_tail_bwd_act", "gen_tail_bwd", "copy_plan", "copy_multi",
 ]
 
