@@ -638,6 +638,13 @@ def main():
                 own = sum(m for n_, (m, c) in rows.items() if is_own_kernel(n_))
                 also["metatrain"]["libb200lp_share_of_kernel_time"] = round(own / (tot or 1.0), 3)
             sb2.graphed and sb2.graphed.release()
+            try:    # context for the N > 1 lines of a back-to-back scaling run on this box (never an efficiency claim)
+                (ROOT / ".bench_cache").mkdir(exist_ok=True)
+                (ROOT / ".bench_cache" / "metatrain_n1.json").write_text(json.dumps(
+                    {"value": also["metatrain"]["value"], "e2e_value": also["metatrain"]["e2e_value"],
+                     "ms_per_step": also["metatrain"]["ms_per_step"], "unix_time": time.time()}))
+            except OSError:
+                pass
         except Exception as err:
             also["metatrain"] = {"error": f"{type(err).__name__}: {str(err)[:200]}"}
     if dist_on:
@@ -669,6 +676,16 @@ def main():
                         "h2d": "pinned host batch -> device on a copy stream, prefetched one step ahead"},
                 "gpu_launches": int(launches), "clocks": clocks}
         line["e2e"].update(also)
+        if world > 1:
+            try:
+                base = json.loads((ROOT / ".bench_cache" / "metatrain_n1.json").read_text())
+                if time.time() - base.get("unix_time", 0) < 6 * 3600:
+                    line["config"]["n1_same_workload"] = {
+                        "value": base["value"], "e2e_value": base["e2e_value"], "ms_per_step": base["ms_per_step"], "unit": UNIT,
+                        "what": "configs[2] on ONE GPU of this box (written by the N = 1 run of this bench, e2e.metatrain): the "
+                                "weak-scaling base of this line — the N = 1 line's own `value` is configs[1]"}
+            except (OSError, ValueError, KeyError):
+                pass
         line.update(extra)
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline

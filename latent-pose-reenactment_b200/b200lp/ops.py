@@ -550,6 +550,11 @@ class DiscBlocksFn(torch.autograd.Function):
             pidx.append(k)
             k += 6 if sp["sk"] is not None else 4
         wants = ctx.needs_input_grad[2:]
+        # gradients that only feed tf32 MMAs are stored rounded to nearest (the MMA would truncate: a 2^-12 relative bias
+        # per layer that compounds along the chain); B200LP_DISC_NODE_TRUNCATE=1 (A/B test against the per-layer nodes) keeps
+        # the unrounded values
+        import os
+        rnd = not os.environ.get("B200LP_DISC_NODE_TRUNCATE")
 
         def bias_into(b, slot, dy):
             """bias gradient by a separate pass (the chain's end, or no sink): column sums of dy."""
@@ -593,7 +598,7 @@ class DiscBlocksFn(torch.autograd.Function):
             del dh2
             # ReLU between the convs + bias gradient of the first conv, one pass
             b0_sink = _sink(b0) if (b0 is not None and wants[p0 + 1]) else None
-            dh_m = K.relu_bwd_fused(h, dh, bias_a=b0_sink, round_tf32=True)
+            dh_m = K.relu_bwd_fused(h, dh, bias_a=b0_sink, round_tf32=rnd)
             del dh
             if b0_sink is None:
                 bias_into(b0, p0 + 1, dh_m)
@@ -625,7 +630,7 @@ class DiscBlocksFn(torch.autograd.Function):
             bb = _sink(pv["sk"][2]) if (pv["sk"] is not None and pv["sk"][2] is not None and wants[pp + 5]) else None
             want_q = pv["down"] and pv["sk"] is not None
             add = d_feats[i].contiguous() if d_feats[i] is not None else None
-            res = K.relu_bwd_fused(r, dr, add=add, want_quarter=want_q, bias_a=ba, bias_b=bb, round_tf32=True)
+            res = K.relu_bwd_fused(r, dr, add=add, want_quarter=want_q, bias_a=ba, bias_b=bb, round_tf32=rnd)
             d_o, q = res if want_q else (res, None)
             del dr
             fused_bias = True

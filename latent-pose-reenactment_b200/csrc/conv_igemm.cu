@@ -1335,37 +1335,37 @@ pack_conv_weight_tiles_kernel(const PackItem* __restrict__ table, const int* __r
     const int co0 = (t / ci_tiles) << 5, ci0 = (t % ci_tiles) << 5;
     const int nco = min(32, Cout - co0), nci = min(32, Cin - ci0);
     const int run = nci * taps;                                    // contiguous floats per source row
-    for (int e = threadIdx.x; e < nco * run; e += 256) {
-        const int r = e / run, c = e - r * run;
-        tile[r * 289 + c] = it.w[(static_cast<long>(co0 + r) * Cin + ci0) * taps + c];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < nco; r += 8) {                          // a warp per source row, lanes along the contiguous run
+        const float* src = it.w + (static_cast<long>(co0 + r) * Cin + ci0) * taps;
+        for (int c = lane; c < run; c += 32) tile[r * 289 + c] = src[c];
     }
     __syncthreads();
     const bool split = it.precision != 0;
     float* outf = static_cast<float*>(it.wp);
     __nv_bfloat16* outh = static_cast<__nv_bfloat16*>(it.wp);
-    const int n = nco * nci * taps;
-    for (int e = threadIdx.x; e < n; e += 256) {
-        float f;
-        long dst;
-        if (!it.transpose) {             // dest [co][tap][ci], ci fastest
-            const int ci = e % nci;
-            const int rest = e / nci;
-            const int tap = rest % taps, co = rest / taps;
-            f = tile[co * 289 + ci * taps + tap];
-            dst = (static_cast<long>(co0 + co) * taps + tap) * Cin + ci0 + ci;
-        } else {                         // dest [ci][taps-1-tap][co], co fastest
-            const int co = e % nco;
-            const int rest = e / nco;
-            const int tapf = rest % taps, ci = rest / taps;
-            f = tile[co * 289 + ci * taps + (taps - 1 - tapf)];
-            dst = (static_cast<long>(ci0 + ci) * taps + tapf) * Cout + co0 + co;
-        }
-        if (!split) {
-            outf[dst] = round_tf32(f);
-        } else {
-            const __nv_bfloat16 h = __float2bfloat16_rn(f);
-            outh[dst] = h;
-            outh[it.total + dst] = __float2bfloat16_rn(f - __bfloat162float(h));
+    // a warp per 128-byte destination run: (co, tap) rows with lanes along ci (forward), (ci, tap) rows with lanes along
+    // co (transposed); no per-element division
+    const int nrows = (it.transpose ? nci : nco), nlan = (it.transpose ? nco : nci);
+    for (int rr = warp; rr < nrows; rr += 8) {
+        for (int tap = 0; tap < taps; ++tap) {
+            if (lane >= nlan) continue;
+            float f;
+            long dst;
+            if (!it.transpose) {         // rr = co, lane = ci: dest [co][tap][ci]
+                f = tile[rr * 289 + lane * taps + tap];
+                dst = (static_cast<long>(co0 + rr) * taps + tap) * Cin + ci0 + lane;
+            } else {                     // rr = ci, lane = co: dest [ci][taps-1-tap][co]
+                f = tile[lane * 289 + rr * taps + tap];
+                dst = (static_cast<long>(ci0 + rr) * taps + (taps - 1 - tap)) * Cout + co0 + lane;
+            }
+            if (!split) {
+                outf[dst] = round_tf32(f);
+            } else {
+                const __nv_bfloat16 h = __float2bfloat16_rn(f);
+                outh[dst] = h;
+                outh[it.total + dst] = __float2bfloat16_rn(f - __bfloat162float(h));
+            }
         }
     }
 }

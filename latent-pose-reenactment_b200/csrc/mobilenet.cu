@@ -34,7 +34,7 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
                int in_relu6, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
                float* __restrict__ part, int M, int K, int N) {
     constexpr int TM = BM / 16;          // rows per thread
-    constexpr int AL = BM / 64;          // A float4 loads per thread and K tile
+    constexpr int AL = BM >= 64 ? BM / 64 : 1;   // A float4 loads per thread and K tile (BM = 32: threads 0..127 only)
     __shared__ float As[kPwBK][BM + 4];
     __shared__ float Bs[kPwBK][kPwBN + 4];
     __shared__ float red[2][16][kPwBN];
@@ -62,7 +62,7 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
         for (int q = 0; q < AL; ++q) {
             const int m = m0 + lrow + 64 * q;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kin && m < M) {
+            if (kin && m < M && lrow + 64 * q < BM) {
                 a = __ldg(reinterpret_cast<const float4*>(x + static_cast<size_t>(m) * K + k));
                 if (in_scale) {
                     a.x = a.x * sc.x + sh.x; a.y = a.y * sc.y + sh.y; a.z = a.z * sc.z + sh.z; a.w = a.w * sc.w + sh.w;
@@ -77,8 +77,10 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
     auto store_tile = [&]() {
 #pragma unroll
         for (int q = 0; q < AL; ++q) {
-            As[lk + 0][lrow + 64 * q] = ra[q].x; As[lk + 1][lrow + 64 * q] = ra[q].y;
-            As[lk + 2][lrow + 64 * q] = ra[q].z; As[lk + 3][lrow + 64 * q] = ra[q].w;
+            if (lrow + 64 * q < BM) {
+                As[lk + 0][lrow + 64 * q] = ra[q].x; As[lk + 1][lrow + 64 * q] = ra[q].y;
+                As[lk + 2][lrow + 64 * q] = ra[q].z; As[lk + 3][lrow + 64 * q] = ra[q].w;
+            }
         }
         Bs[lk + 0][lrow] = rb.x; Bs[lk + 1][lrow] = rb.y; Bs[lk + 2][lrow] = rb.z; Bs[lk + 3][lrow] = rb.w;
     };
@@ -92,10 +94,15 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
 #pragma unroll
         for (int kk = 0; kk < kPwBK; ++kk) {
             float ar[TM];
+            if (TM >= 4) {
 #pragma unroll
-            for (int q = 0; q < TM / 4; ++q) {
-                const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * TM + 4 * q]);
-                ar[4 * q] = av.x; ar[4 * q + 1] = av.y; ar[4 * q + 2] = av.z; ar[4 * q + 3] = av.w;
+                for (int q = 0; q < TM / 4; ++q) {
+                    const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * TM + 4 * q]);
+                    ar[4 * q] = av.x; ar[4 * q + 1] = av.y; ar[4 * q + 2] = av.z; ar[4 * q + 3] = av.w;
+                }
+            } else {
+                const float2 av = *reinterpret_cast<const float2*>(&As[kk][ty * TM]);
+                ar[0] = av.x; ar[TM - 1] = av.y;
             }
             const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
             const float br[4] = {bv.x, bv.y, bv.z, bv.w};
@@ -141,10 +148,12 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
     }
 }
 
-// row-tile height: 128 while (row tiles x column tiles) still covers the 148 SMs, else 64
+// row-tile height: 128 while (row tiles x column tiles) still covers the 148 SMs, else 64, else 32 (the 16 x 16 and 8 x 8
+// planes of a batch of 8: 64-row tiles left 40..120 blocks of one K-serial loop each — 23 us per layer for ~50 MFLOP)
 static int pw_tile_m(long M, int N) {
-    const long blocks128 = ((M + 127) / 128) * ((N + kPwBN - 1) / kPwBN);
-    return blocks128 >= 148 ? 128 : 64;
+    const long nt = (N + kPwBN - 1) / kPwBN;
+    if (((M + 127) / 128) * nt >= 148) return 128;
+    return ((M + 63) / 64) * nt >= 148 ? 64 : 32;
 }
 
 // ------------------------------------------------------------------------------------------------ depthwise 3x3
@@ -426,6 +435,9 @@ extern "C" int32_t b200lp_pw_conv(const float* x, const float* in_scale, const f
     if (bm == 128)
         pw_conv_kernel<128><<<grid, 256, 0, as_stream(stream)>>>(x, in_scale, in_shift, in_relu6, w, bias, y, part,
                                                                  static_cast<int>(M), Cin, Cout);
+    else if (bm == 32)
+        pw_conv_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(x, in_scale, in_shift, in_relu6, w, bias, y, part,
+                                                                static_cast<int>(M), Cin, Cout);
     else
         pw_conv_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(x, in_scale, in_shift, in_relu6, w, bias, y, part,
                                                                 static_cast<int>(M), Cin, Cout);

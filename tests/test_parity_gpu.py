@@ -366,9 +366,10 @@ def test_pose_encoder_train_mode_with_dropout_at_bench_shape():
 def test_discriminator_block_node_equals_per_layer_path(monkeypatch):
     """ops.DiscBlocksFn (one autograd node, kernel-merged gradients) against the per-layer autograd nodes on the SAME
     kernels, weights and inputs at the full channel widths (256 x 256, bs 2): scores, features, the image gradient and
-    every parameter gradient.  The merged gradients are summed in another fp32 order and the node stores its ReLU-backward
-    outputs rounded (not truncated) to tf32, so single operands of the following tf32 MMAs move by one tf32 ulp (2^-11):
-    1e-3 of the largest element bounds it; anything structural (a missing term) is O(1)."""
+    every parameter gradient.  The node's tf32 rounding of stored gradients is switched off for the comparison (the per-layer
+    path lets the MMA truncate; rounding removes a 2^-12 bias per layer, 2.6e-3 on the first block's weight gradient after
+    12 layers), so what remains is the fp32 summation order of the merged gradients and the occasional operand that lands
+    on the other side of a tf32 truncation boundary: measured 3.3e-4 of the largest element; a missing term is O(1)."""
     import copy
     from helpers import make_args
     from b200lp import ops
@@ -380,6 +381,7 @@ def test_discriminator_block_node_equals_per_layer_path(monkeypatch):
     emb = torch.randn(2, 512, device=DEV) * 0.1
     results = {}
     for mode in ("node", "layers"):
+        monkeypatch.setenv("B200LP_DISC_NODE_TRUNCATE", "1")
         if mode == "layers":
             monkeypatch.setenv("B200LP_NO_DISC_NODE", "1")
         else:
