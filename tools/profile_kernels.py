@@ -79,6 +79,47 @@ def main():
         sh = torch.randn(c, device=dev)
         for _ in range(2):
             K.dw_conv3x3(xd, wd, sc, sh, stride, want_stats=True)
+    # round-2 additions: grouped 3x3 gradients on the tensor cores (ResNeXt layer1 / layer3 shapes, 64 identity frames),
+    # the discriminator's fused ReLU-backward pass, the code-byte VGG tap, BatchNorm backward, tiled weight packing
+    for (h, cpg) in [(64, 4), (16, 16)]:
+        c = 32 * cpg
+        xg = torch.randn(64, h, h, c, device=dev)
+        dyg = torch.randn(64, h, h, c, device=dev)
+        wg = torch.randn(c, cpg, 3, 3, device=dev) * 0.1
+        wpt = K.pack_gconv_weight(wg, transpose=True)
+        for _ in range(2):
+            K.gconv3x3_dgrad(dyg, wg, (h, h), packed=wpt)
+            K.gconv3x3_wgrad_tc(xg, dyg, cpg)
+    yr = torch.randn(8, 128, 128, 64, device=dev).relu()
+    dyr = torch.randn_like(yr)
+    addr = torch.randn_like(yr)
+    ba, bb = torch.zeros(64, device=dev), torch.zeros(64, device=dev)
+    for _ in range(2):
+        K.relu_bwd_fused(yr, dyr, add=addr, want_quarter=True, bias_a=ba, bias_b=bb, round_tf32=True)
+    fa = torch.randn(8, 128, 128, 128, device=dev).relu()
+    fb = torch.randn(8, 128, 128, 128, device=dev).relu()
+    loss = torch.zeros(1, device=dev)
+    gs = torch.ones(1, device=dev)
+    for _ in range(2):
+        code = K.l1_sum_code(fa, fb, loss, 1e-6)
+        K.l1_code_bwd(code, tuple(fa.shape), gs, 1e-6, d_in=fb)
+    xb = torch.randn(64 * 64 * 64, 256, device=dev)
+    dyb = torch.randn_like(xb)
+    mean, rstd = torch.zeros(256, device=dev), torch.ones(256, device=dev)
+    gam = torch.ones(256, device=dev)
+    for _ in range(2):
+        K.bn_bwd(dyb, xb, mean, rstd, gam, gam, mean, mask_mode=2)
+    ws_ = [torch.randn(512, 512, 3, 3, device=dev), torch.randn(256, 128, 3, 3, device=dev)]
+    rows = []
+    keep = []
+    for w_ in ws_:
+        for tr in (False, True):
+            o = K.pack_conv_weight(w_, transpose=tr)
+            keep.append(o)
+            rows.append((w_.data_ptr(), o.data_ptr(), w_.shape[0], w_.shape[1], 9, int(tr), 0, w_.numel()))
+    plan = K.pack_plan(rows, torch.device(dev))
+    for _ in range(2):
+        K.pack_conv_weight_multi(plan)
     torch.cuda.synchronize()
 
 
