@@ -207,6 +207,35 @@ def conv_wgrad_sn_acc(x, dy, ksize, grad, weight=None, inv_sigma=None, u=None, v
     return grad
 
 
+EMA_CHUNK = 16384
+
+
+def ema_plan(pairs):
+    """Device table for ema_multi: pairs = [(avg, cur), ...] of equally shaped contiguous fp32 tensors on one device."""
+    rows, chunk_t, chunk_o = [], [], []
+    for i, (a_, c_) in enumerate(pairs):
+        assert a_.is_contiguous() and c_.is_contiguous() and a_.shape == c_.shape and a_.dtype == c_.dtype == torch.float32
+        n = a_.numel()
+        rows.append([c_.data_ptr(), 0, 0, 0, a_.data_ptr(), n])          # OptTensor {p, g, m, v, ema, n}
+        for o in range(0, n, EMA_CHUNK):
+            chunk_t.append(i)
+            chunk_o.append(o)
+    dev = pairs[0][0].device
+    return dict(table=torch.tensor(rows, dtype=torch.int64, device=dev),
+                chunk_t=torch.tensor(chunk_t, dtype=torch.int32, device=dev),
+                chunk_o=torch.tensor(chunk_o, dtype=torch.int64, device=dev), n_chunks=len(chunk_t),
+                sig=tuple((r[0], r[4], r[5]) for r in rows), nbytes=12.0 * sum(r[5] for r in rows))
+
+
+def ema_multi(plan, alpha):
+    """avg = avg * alpha + cur * (1 - alpha) for every pair of the plan, one launch (runners/holycow.py:99-105)."""
+    lib = L.load()
+    with _timed("optimizer", nbytes=plan["nbytes"]):
+        L.check(lib.b200lp_ema_multi(c_void_p(plan["table"].data_ptr()), c_void_p(plan["chunk_t"].data_ptr()),
+                                     c_void_p(plan["chunk_o"].data_ptr()), plan["n_chunks"], EMA_CHUNK, c_float(alpha),
+                                     L.stream_ptr()), "ema_multi")
+
+
 def copy_plan(pairs):
     """Device table for copy_multi: pairs = [(dst, src), ...] of equally sized contiguous tensors on one device."""
     rows = []

@@ -1338,7 +1338,12 @@ pack_conv_weight_tiles_kernel(const PackItem* __restrict__ table, const int* __r
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int r = warp; r < nco; r += 8) {                          // a warp per source row, lanes along the contiguous run
         const float* src = it.w + (static_cast<long>(co0 + r) * Cin + ci0) * taps;
-        for (int c = lane; c < run; c += 32) tile[r * 289 + c] = src[c];
+        float v[9];                                                // all loads of the row in flight before the first store
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] = lane + 32 * k < run ? __ldg(src + lane + 32 * k) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            if (lane + 32 * k < run) tile[r * 289 + lane + 32 * k] = v[k];
     }
     __syncthreads();
     const bool split = it.precision != 0;

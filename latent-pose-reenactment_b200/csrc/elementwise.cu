@@ -526,16 +526,33 @@ __global__ void l1_relu_bwd_kernel(const float4* __restrict__ a, const float4* _
 // VGG tap, forward half of the fused L1: out[0] += scale * sum |a-b| AND one code byte per float4 for the backward pass:
 // 2 bits per element — 0: a <= 0 (ReLU mask closed), 1 / 2 / 3: a > 0 and sign(a-b) = -1 / 0 / +1.  The backward tap then
 // needs neither feature map (0.25 B instead of 8 B per element, and the `b` branch's activations are not kept alive).
+__device__ __forceinline__ unsigned l1_code4(const float4 u, const float4 v) {
+    auto cd = [](float p, float q) -> unsigned { return p > 0.f ? (p > q ? 3u : (p < q ? 1u : 2u)) : 0u; };
+    return cd(u.x, v.x) | (cd(u.y, v.y) << 2) | (cd(u.z, v.z) << 4) | (cd(u.w, v.w) << 6);
+}
+__device__ __forceinline__ float l1_abs4(const float4 u, const float4 v) {
+    return (fabsf(u.x - v.x) + fabsf(u.y - v.y)) + (fabsf(u.z - v.z) + fabsf(u.w - v.w));
+}
+
+// One thread handles 16 consecutive elements: eight 16-byte loads in flight, one 32-bit store of four code bytes.
 __global__ void l1_sum_code_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float* __restrict__ out,
                                    unsigned char* __restrict__ code, long n4, float scale) {
     float acc = 0.f;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4;
+    const long n16 = n4 >> 2;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n16;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const float4 u = __ldg(a + i), v = __ldg(b + i);
-        acc += (fabsf(u.x - v.x) + fabsf(u.y - v.y)) + (fabsf(u.z - v.z) + fabsf(u.w - v.w));
-        auto cd = [](float p, float q) -> unsigned { return p > 0.f ? (p > q ? 3u : (p < q ? 1u : 2u)) : 0u; };
-        code[i] = static_cast<unsigned char>(cd(u.x, v.x) | (cd(u.y, v.y) << 2) | (cd(u.z, v.z) << 4) | (cd(u.w, v.w) << 6));
+        const float4 u0 = __ldg(a + 4 * i), u1 = __ldg(a + 4 * i + 1), u2 = __ldg(a + 4 * i + 2), u3 = __ldg(a + 4 * i + 3);
+        const float4 v0 = __ldg(b + 4 * i), v1 = __ldg(b + 4 * i + 1), v2 = __ldg(b + 4 * i + 2), v3 = __ldg(b + 4 * i + 3);
+        acc += (l1_abs4(u0, v0) + l1_abs4(u1, v1)) + (l1_abs4(u2, v2) + l1_abs4(u3, v3));
+        reinterpret_cast<unsigned*>(code)[i] =
+            l1_code4(u0, v0) | (l1_code4(u1, v1) << 8) | (l1_code4(u2, v2) << 16) | (l1_code4(u3, v3) << 24);
     }
+    if (blockIdx.x == 0)                                          // ragged tail (n4 % 4 float4s)
+        for (long i = (n16 << 2) + threadIdx.x; i < n4; i += blockDim.x) {
+            const float4 u = __ldg(a + i), v = __ldg(b + i);
+            acc += l1_abs4(u, v);
+            code[i] = static_cast<unsigned char>(l1_code4(u, v));
+        }
     __shared__ float ws[kEwThreads / 32];
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
@@ -552,16 +569,27 @@ template <bool HAS_IN>
 __global__ void l1_code_bwd_kernel(const unsigned char* __restrict__ code, const float* __restrict__ gscale, float scale2,
                                    const float4* __restrict__ d_in, float4* __restrict__ d_out, long n4) {
     const float g = (gscale ? __ldg(gscale) : 1.f) * scale2;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4;
+    auto one = [g](float din, unsigned cc) -> float {
+        return cc ? round_tf32(din + (static_cast<float>(cc) - 2.f) * g) : 0.f;
+    };
+    auto quad = [&](float4 d, unsigned c) -> float4 {
+        return make_float4(one(d.x, c & 3u), one(d.y, (c >> 2) & 3u), one(d.z, (c >> 4) & 3u), one(d.w, (c >> 6) & 3u));
+    };
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long n16 = n4 >> 2;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n16;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const unsigned c = code[i];
-        float4 d = HAS_IN ? __ldg(d_in + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        auto one = [g](float din, unsigned cc) -> float {
-            return cc ? round_tf32(din + (static_cast<float>(cc) - 2.f) * g) : 0.f;
-        };
-        d.x = one(d.x, c & 3u); d.y = one(d.y, (c >> 2) & 3u); d.z = one(d.z, (c >> 4) & 3u); d.w = one(d.w, c >> 6);
-        d_out[i] = d;
+        const unsigned c = __ldg(reinterpret_cast<const unsigned*>(code) + i);
+        const float4 d0 = HAS_IN ? __ldg(d_in + 4 * i) : zero, d1 = HAS_IN ? __ldg(d_in + 4 * i + 1) : zero,
+                     d2 = HAS_IN ? __ldg(d_in + 4 * i + 2) : zero, d3 = HAS_IN ? __ldg(d_in + 4 * i + 3) : zero;
+        d_out[4 * i] = quad(d0, c & 255u);
+        d_out[4 * i + 1] = quad(d1, (c >> 8) & 255u);
+        d_out[4 * i + 2] = quad(d2, (c >> 16) & 255u);
+        d_out[4 * i + 3] = quad(d3, c >> 24);
     }
+    if (blockIdx.x == 0)
+        for (long i = (n16 << 2) + threadIdx.x; i < n4; i += blockDim.x)
+            d_out[i] = quad(HAS_IN ? __ldg(d_in + i) : zero, code[i]);
 }
 
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, long total) {
@@ -868,7 +896,7 @@ extern "C" int32_t b200lp_l1_sum(const float* a, const float* b, float* out, int
 extern "C" int32_t b200lp_l1_sum_code(const float* a, const float* b, float* out, uint8_t* code, int64_t n, float scale,
                                       void* stream) {
     B200LP_REQUIRE(a && b && out && code && n > 0 && n % 4 == 0, "l1_sum_code: bad args");
-    int g = grid_for(n / 4, kEwThreads);
+    int g = grid_for(n / 16 + 1, kEwThreads);          // 16 elements per thread
     if (g > 148 * 4) g = 148 * 4;
     l1_sum_code_kernel<<<g, kEwThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a),
                                                                reinterpret_cast<const float4*>(b), out, code, n / 4, scale);
@@ -880,7 +908,7 @@ extern "C" int32_t b200lp_l1_sum_code(const float* a, const float* b, float* out
 extern "C" int32_t b200lp_l1_code_bwd(const uint8_t* code, const float* gscale, float scale2, const float* d_in,
                                       float* d_out, int64_t n, void* stream) {
     B200LP_REQUIRE(code && d_out && n > 0 && n % 4 == 0, "l1_code_bwd: bad args");
-    const int g = grid_for(n / 4, kEwThreads);
+    const int g = grid_for(n / 16 + 1, kEwThreads);    // 16 elements per thread
     if (d_in)
         l1_code_bwd_kernel<true><<<g, kEwThreads, 0, as_stream(stream)>>>(code, gscale, scale2,
                                                                           reinterpret_cast<const float4*>(d_in),

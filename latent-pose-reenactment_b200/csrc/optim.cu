@@ -129,7 +129,22 @@ ema_multi_kernel(const OptTensor* __restrict__ table, const int* __restrict__ ch
     long long end = off + chunk_elems;
     if (end > t.n) end = t.n;
     if (!t.ema) return;
-    for (long long i = off + threadIdx.x; i < end; i += blockDim.x) t.ema[i] = t.ema[i] * ema_alpha + t.p[i] * (1.f - ema_alpha);
+    const float oma = 1.f - ema_alpha;
+    long long vec_end = off;
+    if (((reinterpret_cast<uintptr_t>(t.ema + off) | reinterpret_cast<uintptr_t>(t.p + off)) & 15) == 0) {
+        const long long n4 = (end - off) >> 2;
+        vec_end = off + (n4 << 2);
+        float4* e4 = reinterpret_cast<float4*>(t.ema + off);
+        const float4* p4 = reinterpret_cast<const float4*>(t.p + off);
+        for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+            float4 e = e4[i];
+            const float4 q = p4[i];
+            e.x = e.x * ema_alpha + q.x * oma; e.y = e.y * ema_alpha + q.y * oma;
+            e.z = e.z * ema_alpha + q.z * oma; e.w = e.w * ema_alpha + q.w * oma;
+            e4[i] = e;
+        }
+    }
+    for (long long i = vec_end + threadIdx.x; i < end; i += blockDim.x) t.ema[i] = t.ema[i] * ema_alpha + t.p[i] * oma;
 }
 
 }  // namespace b200lp

@@ -154,7 +154,7 @@ class TrainingModule(torch.nn.Module):
             for name, avg in self.running_averages.items():
                 cur = getattr(self, name)
                 pairs = [(a, c) for a, c in zip(avg.parameters(), cur.parameters()) if id(c) not in fused]
-                if pairs:
+                if pairs and not self._ema_kernel(name, pairs, alpha):
                     p_avg, p_cur = [a for a, _ in pairs], [c for _, c in pairs]
                     torch._foreach_mul_(p_avg, alpha)
                     torch._foreach_add_(p_avg, p_cur, alpha=1 - alpha)
@@ -163,6 +163,24 @@ class TrainingModule(torch.nn.Module):
                     self._copy_buffers(name, b_avg, b_cur)
                 elif b_avg:
                     torch._foreach_copy_(b_avg, b_cur)
+
+    def _ema_kernel(self, name, pairs, alpha):
+        """Running average of the parameters the fused optimizer does not own (fine-tuning: the frozen embedder's 29 M) as
+        ONE multi-tensor launch (12 B per parameter instead of two `_foreach` passes); False = not applicable here."""
+        if not all(a.is_cuda and a.dtype == torch.float32 and a.is_contiguous() and c.is_contiguous() and a.shape == c.shape
+                   and c.dtype == torch.float32 for a, c in pairs):
+            return False
+        from b200lp import kernels as K
+        sig = tuple((c.data_ptr(), a.data_ptr(), a.numel()) for a, c in pairs)
+        plans = self.__dict__.setdefault('_ema_plans', {})
+        plan = plans.get(name)
+        if plan is None or plan['sig'] != sig:
+            if torch.cuda.is_current_stream_capturing():     # the table upload is not capturable
+                return False
+            plan = K.ema_plan(pairs)
+            plans[name] = plan
+        K.ema_multi(plan, alpha)
+        return True
 
     def _copy_buffers(self, name, b_avg, b_cur):
         """All buffer copies of one module (BatchNorm statistics, spectral-norm vectors: ~370 tiny tensors for E + G) as

