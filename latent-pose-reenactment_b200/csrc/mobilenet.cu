@@ -25,7 +25,9 @@ __device__ __forceinline__ float relu6f(float v) { return fminf(fmaxf(v, 0.f), 6
 // ------------------------------------------------------------------------------------------------ pointwise conv
 // y[m][n] = sum_k f(x[m][k]) * w[n][k] (+ bias[n]);  f = identity | BN | ReLU6(BN) of the producer layer.
 // SIMT SGEMM: BM x 64 tile (BM = 128 when the grid still fills the GPU, else 64), K step 16, 256 threads,
-// (BM/16) x 4 outputs per thread; the next K tile travels global -> registers while the current one is multiplied.
+// (BM/16) x 4 outputs per thread; the NEXT TWO K tiles travel global -> registers while the current one is multiplied
+// (two register sets: the small layers run one 8-warp block per SM, so nothing else hides the load latency — with one
+// tile in flight an iteration cost ~1000 clk against ~320 clk of FMAs; a 32-row tile variant was measured slower).
 constexpr int kPwBN = 64, kPwBK = 16;
 
 template <int BM>
@@ -34,7 +36,7 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
                int in_relu6, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
                float* __restrict__ part, int M, int K, int N) {
     constexpr int TM = BM / 16;          // rows per thread
-    constexpr int AL = BM >= 64 ? BM / 64 : 1;   // A float4 loads per thread and K tile (BM = 32: threads 0..127 only)
+    constexpr int AL = BM / 64;          // A float4 loads per thread and K tile
     __shared__ float As[kPwBK][BM + 4];
     __shared__ float Bs[kPwBK][kPwBN + 4];
     __shared__ float red[2][16][kPwBN];
@@ -49,10 +51,24 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    float4 ra[AL], rb;
-    auto load_tile = [&](int k0) {
+    float4 ra0[AL], rb0, ra1[AL], rb1;
+    // raw loads only: the producer's BatchNorm + ReLU6 is applied when the tile is STORED to shared memory, one or two
+    // iterations later, so that no instruction waits on the load where it is issued
+    auto load_tile = [&](int k0, float4 (&ra)[AL], float4& rb) {
         const int k = k0 + lk;
         const bool kin = k < K;       // K % 4 == 0: a float4 is entirely inside or outside
+#pragma unroll
+        for (int q = 0; q < AL; ++q) {
+            const int m = m0 + lrow + 64 * q;
+            ra[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kin && m < M) ra[q] = __ldg(reinterpret_cast<const float4*>(x + static_cast<size_t>(m) * K + k));
+        }
+        rb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kin && n0 + lrow < N) rb = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(n0 + lrow) * K + k));
+    };
+    auto store_tile = [&](int k0, const float4 (&ra)[AL], const float4& rb) {
+        const int k = k0 + lk;
+        const bool kin = k < K;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (kin && in_scale) {
             sc = __ldg(reinterpret_cast<const float4*>(in_scale + k));
@@ -60,49 +76,25 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
         }
 #pragma unroll
         for (int q = 0; q < AL; ++q) {
-            const int m = m0 + lrow + 64 * q;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kin && m < M && lrow + 64 * q < BM) {
-                a = __ldg(reinterpret_cast<const float4*>(x + static_cast<size_t>(m) * K + k));
-                if (in_scale) {
-                    a.x = a.x * sc.x + sh.x; a.y = a.y * sc.y + sh.y; a.z = a.z * sc.z + sh.z; a.w = a.w * sc.w + sh.w;
-                    if (in_relu6) { a.x = relu6f(a.x); a.y = relu6f(a.y); a.z = relu6f(a.z); a.w = relu6f(a.w); }
-                }
+            float4 a = ra[q];
+            if (in_scale && kin && m0 + lrow + 64 * q < M) {      // rows / columns outside the matrix stay zero
+                a.x = a.x * sc.x + sh.x; a.y = a.y * sc.y + sh.y; a.z = a.z * sc.z + sh.z; a.w = a.w * sc.w + sh.w;
+                if (in_relu6) { a.x = relu6f(a.x); a.y = relu6f(a.y); a.z = relu6f(a.z); a.w = relu6f(a.w); }
             }
-            ra[q] = a;
-        }
-        rb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kin && n0 + lrow < N) rb = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(n0 + lrow) * K + k));
-    };
-    auto store_tile = [&]() {
-#pragma unroll
-        for (int q = 0; q < AL; ++q) {
-            if (lrow + 64 * q < BM) {
-                As[lk + 0][lrow + 64 * q] = ra[q].x; As[lk + 1][lrow + 64 * q] = ra[q].y;
-                As[lk + 2][lrow + 64 * q] = ra[q].z; As[lk + 3][lrow + 64 * q] = ra[q].w;
-            }
+            As[lk + 0][lrow + 64 * q] = a.x; As[lk + 1][lrow + 64 * q] = a.y;
+            As[lk + 2][lrow + 64 * q] = a.z; As[lk + 3][lrow + 64 * q] = a.w;
         }
         Bs[lk + 0][lrow] = rb.x; Bs[lk + 1][lrow] = rb.y; Bs[lk + 2][lrow] = rb.z; Bs[lk + 3][lrow] = rb.w;
     };
 
-    load_tile(0);
-    store_tile();
-    __syncthreads();
-    for (int k0 = 0; k0 < K; k0 += kPwBK) {
-        const bool more = k0 + kPwBK < K;
-        if (more) load_tile(k0 + kPwBK);
+    auto compute = [&]() {
 #pragma unroll
         for (int kk = 0; kk < kPwBK; ++kk) {
             float ar[TM];
-            if (TM >= 4) {
 #pragma unroll
-                for (int q = 0; q < TM / 4; ++q) {
-                    const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * TM + 4 * q]);
-                    ar[4 * q] = av.x; ar[4 * q + 1] = av.y; ar[4 * q + 2] = av.z; ar[4 * q + 3] = av.w;
-                }
-            } else {
-                const float2 av = *reinterpret_cast<const float2*>(&As[kk][ty * TM]);
-                ar[0] = av.x; ar[TM - 1] = av.y;
+            for (int q = 0; q < TM / 4; ++q) {
+                const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * TM + 4 * q]);
+                ar[4 * q] = av.x; ar[4 * q + 1] = av.y; ar[4 * q + 2] = av.z; ar[4 * q + 3] = av.w;
             }
             const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
             const float br[4] = {bv.x, bv.y, bv.z, bv.w};
@@ -111,11 +103,25 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
         }
+    };
+    const int nk = (K + kPwBK - 1) / kPwBK;
+    // iteration `it`: shared memory holds tile it, `rs` holds tile it + 1 (loaded one iteration ago), `rl` is free
+    auto step = [&](float4 (&ral)[AL], float4& rbl, const float4 (&ras)[AL], const float4& rbs, int it) {
+        if (it + 2 < nk) load_tile((it + 2) * kPwBK, ral, rbl);
+        compute();
         __syncthreads();
-        if (more) {
-            store_tile();
+        if (it + 1 < nk) {
+            store_tile((it + 1) * kPwBK, ras, rbs);
             __syncthreads();
         }
+    };
+    load_tile(0, ra0, rb0);
+    store_tile(0, ra0, rb0);
+    if (nk > 1) load_tile(kPwBK, ra1, rb1);
+    __syncthreads();
+    for (int it = 0; it < nk; it += 2) {
+        step(ra0, rb0, ra1, rb1, it);
+        if (it + 1 < nk) step(ra1, rb1, ra0, rb0, it + 1);
     }
 
     const int n = n0 + tx * 4;
@@ -148,12 +154,10 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
     }
 }
 
-// row-tile height: 128 while (row tiles x column tiles) still covers the 148 SMs, else 64, else 32 (the 16 x 16 and 8 x 8
-// planes of a batch of 8: 64-row tiles left 40..120 blocks of one K-serial loop each — 23 us per layer for ~50 MFLOP)
+// row-tile height: 128 while (row tiles x column tiles) still covers the 148 SMs, else 64
 static int pw_tile_m(long M, int N) {
-    const long nt = (N + kPwBN - 1) / kPwBN;
-    if (((M + 127) / 128) * nt >= 148) return 128;
-    return ((M + 63) / 64) * nt >= 148 ? 64 : 32;
+    const long blocks128 = ((M + 127) / 128) * ((N + kPwBN - 1) / kPwBN);
+    return blocks128 >= 148 ? 128 : 64;
 }
 
 // ------------------------------------------------------------------------------------------------ depthwise 3x3
@@ -435,9 +439,6 @@ extern "C" int32_t b200lp_pw_conv(const float* x, const float* in_scale, const f
     if (bm == 128)
         pw_conv_kernel<128><<<grid, 256, 0, as_stream(stream)>>>(x, in_scale, in_shift, in_relu6, w, bias, y, part,
                                                                  static_cast<int>(M), Cin, Cout);
-    else if (bm == 32)
-        pw_conv_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(x, in_scale, in_shift, in_relu6, w, bias, y, part,
-                                                                static_cast<int>(M), Cin, Cout);
     else
         pw_conv_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(x, in_scale, in_shift, in_relu6, w, bias, y, part,
                                                                 static_cast<int>(M), Cin, Cout);
