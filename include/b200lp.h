@@ -366,6 +366,13 @@ int32_t b200lp_copy_multi(const void* table_dev, int32_t count, void* stream);
 int32_t b200lp_pw_conv_parts(int64_t M, int32_t Cout);
 int32_t b200lp_pw_conv(const float* x, const float* in_scale, const float* in_shift, int32_t in_relu6, const float* w,
                        const float* bias, float* y, float* part, int64_t M, int32_t Cin, int32_t Cout, void* stream);
+/* The same product with split-K for layers whose (row tile x column tile) grid leaves most SMs idle (small planes of a
+ * small batch, the classifiers): partial sums in `workspace` (b200lp_pw_conv_workspace bytes; 0 = the layer does not split),
+ * then one reduction pass that also adds the bias and emits the statistics partials.  Deterministic (fixed split order). */
+int64_t b200lp_pw_conv_workspace(int64_t M, int32_t Cin, int32_t Cout);
+int32_t b200lp_pw_conv_ws(const float* x, const float* in_scale, const float* in_shift, int32_t in_relu6, const float* w,
+                          const float* bias, float* y, float* part, int64_t M, int32_t Cin, int32_t Cout,
+                          float* workspace, int64_t workspace_bytes, void* stream);
 /* depthwise 3x3, padding 1, stride 1 or 2, on relu6(x*scale+shift); w [C][1][3][3]; y [N,Ho,Wo,C] raw;
  * `part`: b200lp_dw_conv3x3_parts(N,H,W,stride) x 2 x C floats, or NULL. */
 int32_t b200lp_dw_conv3x3_parts(int32_t N, int32_t H, int32_t W, int32_t stride);

@@ -648,9 +648,12 @@ def pw_conv(x2d, weight, in_scale=None, in_shift=None, in_relu6=False, bias=None
     part = None
     if want_stats:
         part = torch.empty((lib.b200lp_pw_conv_parts(m, cout), 2, cout), dtype=torch.float32, device=x2d.device)
+    need = lib.b200lp_pw_conv_workspace(m, cin, cout)       # > 0: few-tile layer, split-K partial sums
+    ws = _ws(need, x2d.device) if need > 0 else None
     with _timed("pose_encoder", flops=2.0 * m * cin * cout):
-        L.check(lib.b200lp_pw_conv(L.ptr(x2d), L.ptr(in_scale), L.ptr(in_shift), int(in_relu6), L.ptr(weight), L.ptr(bias),
-                                   L.ptr(y), L.ptr(part), m, cin, cout, L.stream_ptr()), "pw_conv")
+        L.check(lib.b200lp_pw_conv_ws(L.ptr(x2d), L.ptr(in_scale), L.ptr(in_shift), int(in_relu6), L.ptr(weight),
+                                      L.ptr(bias), L.ptr(y), L.ptr(part), m, cin, cout, L.ptr(ws),
+                                      ws.numel() * 4 if ws is not None else 0, L.stream_ptr()), "pw_conv")
     return (y, part) if want_stats else y
 
 

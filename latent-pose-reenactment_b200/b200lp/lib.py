@@ -113,6 +113,8 @@ SIGNATURES = {
     "b200lp_copy_multi": (_I, [_P, _I, _P]),
     "b200lp_pw_conv_parts": (_I, [_L, _I]),
     "b200lp_pw_conv": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _L, _I, _I, _P]),
+    "b200lp_pw_conv_workspace": (_L, [_L, _I, _I]),
+    "b200lp_pw_conv_ws": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _L, _I, _I, _P, _L, _P]),
     "b200lp_dw_conv3x3_parts": (_I, [_I, _I, _I, _I]),
     "b200lp_dw_conv3x3": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200lp_mbv2_stem_parts": (_I, [_I, _I, _I]),

@@ -34,7 +34,7 @@ template <int BM>
 __global__ void __launch_bounds__(256)
 pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, const float* __restrict__ in_shift,
                int in_relu6, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
-               float* __restrict__ part, int M, int K, int N) {
+               float* __restrict__ part, int M, int K, int N, int k_per_split, float* __restrict__ ws) {
     constexpr int TM = BM / 16;          // rows per thread
     constexpr int AL = BM / 64;          // A float4 loads per thread and K tile
     __shared__ float As[kPwBK][BM + 4];
@@ -43,6 +43,10 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * kPwBN;
+    // split-K (gridDim.z > 1): this block contracts k in [kb, ke) and leaves raw partial sums in ws[z][M][N]; bias, output
+    // and statistics are produced by pw_splitk_reduce_kernel
+    const int kb = blockIdx.z * k_per_split;
+    const int ke = min(K, kb + k_per_split);
     // loader mapping: one float4 (4 consecutive k) of one row per thread (AL rows of A, one of B)
     const int lrow = tid >> 2, lk = (tid & 3) * 4;
     float acc[TM][4];
@@ -55,8 +59,8 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
     // raw loads only: the producer's BatchNorm + ReLU6 is applied when the tile is STORED to shared memory, one or two
     // iterations later, so that no instruction waits on the load where it is issued
     auto load_tile = [&](int k0, float4 (&ra)[AL], float4& rb) {
-        const int k = k0 + lk;
-        const bool kin = k < K;       // K % 4 == 0: a float4 is entirely inside or outside
+        const int k = kb + k0 + lk;
+        const bool kin = k < ke;      // K % 4 == 0 and k_per_split % 16 == 0: a float4 is entirely inside or outside
 #pragma unroll
         for (int q = 0; q < AL; ++q) {
             const int m = m0 + lrow + 64 * q;
@@ -67,8 +71,8 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
         if (kin && n0 + lrow < N) rb = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(n0 + lrow) * K + k));
     };
     auto store_tile = [&](int k0, const float4 (&ra)[AL], const float4& rb) {
-        const int k = k0 + lk;
-        const bool kin = k < K;
+        const int k = kb + k0 + lk;
+        const bool kin = k < ke;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (kin && in_scale) {
             sc = __ldg(reinterpret_cast<const float4*>(in_scale + k));
@@ -104,7 +108,7 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
         }
     };
-    const int nk = (K + kPwBK - 1) / kPwBK;
+    const int nk = (ke - kb + kPwBK - 1) / kPwBK;
     // iteration `it`: shared memory holds tile it, `rs` holds tile it + 1 (loaded one iteration ago), `rl` is free
     auto step = [&](float4 (&ral)[AL], float4& rbl, const float4 (&ras)[AL], const float4& rbs, int it) {
         if (it + 2 < nk) load_tile((it + 2) * kPwBK, ral, rbl);
@@ -125,6 +129,16 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
     }
 
     const int n = n0 + tx * 4;
+    if (ws) {
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int m = m0 + ty * TM + i;
+            if (m < M && n < N)
+                *reinterpret_cast<float4*>(ws + (static_cast<size_t>(blockIdx.z) * M + m) * N + n) =
+                    make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+        return;
+    }
     float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
@@ -152,6 +166,55 @@ pw_conv_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, 
             if (n0 + c < N) part[(static_cast<size_t>(blockIdx.x) * 2 + which) * N + n0 + c] = s;
         }
     }
+}
+
+// y = sum_z ws[z] (+ bias) and the statistics partials of one BM-row tile, splits summed in index order (deterministic).
+// block = 64 columns x 4 row lanes; grid = (row tiles of `bm`, column tiles of 64)
+__global__ void __launch_bounds__(256)
+pw_splitk_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias, float* __restrict__ y,
+                        float* __restrict__ part, int splits, int M, int N, int bm) {
+    __shared__ float red[2][4][kPwBN];
+    const int c = threadIdx.x & 63, rl = threadIdx.x >> 6;
+    const int n = blockIdx.y * kPwBN + c;
+    const int m0 = blockIdx.x * bm;
+    float s1 = 0.f, s2 = 0.f;
+    if (n < N) {
+        const float b = bias ? __ldg(bias + n) : 0.f;
+        for (int r = rl; r < bm && m0 + r < M; r += 4) {
+            const size_t off = static_cast<size_t>(m0 + r) * N + n;
+            float v = 0.f;
+            for (int z = 0; z < splits; ++z) v += __ldg(ws + static_cast<size_t>(z) * M * N + off);
+            y[off] = v + b;
+            s1 += v;
+            s2 += v * v;
+        }
+    }
+    if (part) {
+        red[0][rl][c] = s1;
+        red[1][rl][c] = s2;
+        __syncthreads();
+        if (threadIdx.x < 2 * kPwBN) {
+            const int which = threadIdx.x >> 6, cc = threadIdx.x & 63;
+            const float t = ((red[which][0][cc] + red[which][1][cc]) + red[which][2][cc]) + red[which][3][cc];
+            if (blockIdx.y * kPwBN + cc < N) part[(static_cast<size_t>(blockIdx.x) * 2 + which) * N + blockIdx.y * kPwBN + cc] = t;
+        }
+    }
+}
+
+// K splits of a layer whose (row tile x column tile) grid leaves most SMs idle: the small planes of a batch of 8 ran 8..64
+// blocks, each walking K = 384..2048 serially at ~1 us per 16-wide step (68 us for 512 x 960 -> 160, 78 us for the 8-row
+// classifier).  At least 64 k per split, at most one wave of blocks.
+static int pw_splits(long M, int N, int K, int bm, int* k_per_split) {
+    const long tiles = ((M + bm - 1) / bm) * ((N + kPwBN - 1) / kPwBN);
+    int s = 1;
+    if (tiles * 2 <= 148 && K >= 128) {
+        s = static_cast<int>(148 / tiles);
+        if (s > K / 64) s = K / 64;
+        if (s < 1) s = 1;
+    }
+    int kps = ((K + s - 1) / s + kPwBK - 1) / kPwBK * kPwBK;
+    *k_per_split = kps;
+    return (K + kps - 1) / kps;
 }
 
 // row-tile height: 128 while (row tiles x column tiles) still covers the 148 SMs, else 64
@@ -413,7 +476,9 @@ bn_relu6_avgpool_kernel(const float* __restrict__ x, const float* __restrict__ s
 
 static int dw_plan(long P, int* pix_per_chunk) {
     long ppc = (P + 1183) / 1184;          // <= 148 x 8 chunks
-    if (ppc < 32) ppc = 32;
+    // >= 8 pixels per chunk (was 32: the 8 x 8 planes of a batch of 8 ran as 16 blocks whose single pixel lane — C = 960
+    // fills the block with channel quads — walked its 32 pixels serially: 38 us per layer)
+    if (ppc < 8) ppc = 8;
     *pix_per_chunk = static_cast<int>(ppc);
     return static_cast<int>((P + ppc - 1) / ppc);
 }
@@ -427,24 +492,48 @@ extern "C" int32_t b200lp_pw_conv_parts(int64_t M, int32_t Cout) {
     return static_cast<int32_t>((M + bm - 1) / bm);
 }
 
-extern "C" int32_t b200lp_pw_conv(const float* x, const float* in_scale, const float* in_shift, int32_t in_relu6,
-                                  const float* w, const float* bias, float* y, float* part, int64_t M, int32_t Cin,
-                                  int32_t Cout, void* stream) {
+extern "C" int64_t b200lp_pw_conv_workspace(int64_t M, int32_t Cin, int32_t Cout) {
+    if (M <= 0 || Cin <= 0 || Cout <= 0) return B200LP_EINVAL;
+    int kps;
+    const int sp = pw_splits(M, Cout, Cin, pw_tile_m(M, Cout), &kps);
+    return sp > 1 ? static_cast<int64_t>(sp) * M * Cout * 4 : 0;
+}
+
+extern "C" int32_t b200lp_pw_conv_ws(const float* x, const float* in_scale, const float* in_shift, int32_t in_relu6,
+                                     const float* w, const float* bias, float* y, float* part, int64_t M, int32_t Cin,
+                                     int32_t Cout, float* workspace, int64_t workspace_bytes, void* stream) {
     B200LP_REQUIRE(x && w && y && M > 0 && Cin > 0 && Cout > 0 && Cin % 4 == 0 && Cout % 4 == 0,
                    "pw_conv: bad args M=%lld Cin=%d Cout=%d (channels must be multiples of 4)", (long long)M, Cin, Cout);
     B200LP_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "pw_conv: in_scale and in_shift go together");
     B200LP_REQUIRE(M < (1LL << 31) - 128, "pw_conv: M too large");
     const int bm = pw_tile_m(M, Cout);
-    dim3 grid(static_cast<unsigned>((M + bm - 1) / bm), static_cast<unsigned>((Cout + kPwBN - 1) / kPwBN));
+    int kps;
+    int sp = pw_splits(M, Cout, Cin, bm, &kps);
+    if (sp > 1 && (!workspace || workspace_bytes < static_cast<int64_t>(sp) * M * Cout * 4)) { sp = 1; kps = (Cin + kPwBK - 1) / kPwBK * kPwBK; }
+    float* ws = sp > 1 ? workspace : nullptr;
+    dim3 grid(static_cast<unsigned>((M + bm - 1) / bm), static_cast<unsigned>((Cout + kPwBN - 1) / kPwBN), sp);
+    cudaStream_t st = as_stream(stream);
     if (bm == 128)
-        pw_conv_kernel<128><<<grid, 256, 0, as_stream(stream)>>>(x, in_scale, in_shift, in_relu6, w, bias, y, part,
-                                                                 static_cast<int>(M), Cin, Cout);
+        pw_conv_kernel<128><<<grid, 256, 0, st>>>(x, in_scale, in_shift, in_relu6, w, bias, y, part, static_cast<int>(M), Cin,
+                                                   Cout, kps, ws);
     else
-        pw_conv_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(x, in_scale, in_shift, in_relu6, w, bias, y, part,
-                                                                static_cast<int>(M), Cin, Cout);
+        pw_conv_kernel<64><<<grid, 256, 0, st>>>(x, in_scale, in_shift, in_relu6, w, bias, y, part, static_cast<int>(M), Cin,
+                                                  Cout, kps, ws);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
+    if (sp > 1) {
+        dim3 g2(grid.x, grid.y);
+        pw_splitk_reduce_kernel<<<g2, 256, 0, st>>>(ws, bias, y, part, sp, static_cast<int>(M), Cout, bm);
+        B200LP_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+    }
     return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_pw_conv(const float* x, const float* in_scale, const float* in_shift, int32_t in_relu6,
+                                  const float* w, const float* bias, float* y, float* part, int64_t M, int32_t Cin,
+                                  int32_t Cout, void* stream) {
+    return b200lp_pw_conv_ws(x, in_scale, in_shift, in_relu6, w, bias, y, part, M, Cin, Cout, nullptr, 0, stream);
 }
 
 extern "C" int32_t b200lp_dw_conv3x3_parts(int32_t N, int32_t H, int32_t W, int32_t stride) {
