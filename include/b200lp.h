@@ -281,6 +281,12 @@ int32_t b200lp_l1_code_bwd(const uint8_t* code, const float* gscale, float scale
 int32_t b200lp_conv3x3_c3_fwd(const float* x_nchw, const float* w_oihw, const float* wscale, const float* bias,
                               const float* pre_scale, const float* pre_shift, float* y_nhwc, int32_t N, int32_t H,
                               int32_t W, int32_t Cout, int32_t relu, int32_t round_tf32, void* stream);
+/* The same layer (Cout = 64) on tcgen05: M = 128 pixels x N = 64 x K = 27 (+5) implicit GEMM whose A tile is built in shared
+ * memory by the pixel threads (swizzled K-major rows, input normalisation + tf32 rounding applied on the way); operands
+ * are tf32 like every other layer of the discriminator / VGG networks. */
+int32_t b200lp_conv3x3_c3_fwd_tc(const float* x_nchw, const float* w_oihw, const float* wscale, const float* bias,
+                                 const float* pre_scale, const float* pre_shift, float* y_nhwc, int32_t N, int32_t H,
+                                 int32_t W, int32_t Cout, int32_t relu, int32_t round_tf32, void* stream);
 /* its data gradient (NHWC dy -> NCHW dx, 3 channels) */
 int32_t b200lp_conv3x3_c3_dgrad(const float* dy_nhwc, const float* w_oihw, const float* wscale,
                                 const float* pre_scale, float* dx_nchw, int32_t N, int32_t H, int32_t W,

@@ -436,16 +436,22 @@ def l1_relu_bwd(a, b, gscale, scale2, d_in=None):
     return d_out
 
 
-def conv3x3_c3_fwd(x_nchw, w, wscale=None, bias=None, pre_scale=None, pre_shift=None, relu=False, round_tf32=False):
+def conv3x3_c3_fwd(x_nchw, w, wscale=None, bias=None, pre_scale=None, pre_shift=None, relu=False, round_tf32=False,
+                   tensor_cores=None):
+    """3x3 conv of a 3-channel NCHW image -> NHWC features.  `tensor_cores` (default: Cout == 64, unless
+    B200LP_C3_CUDA_CORES=1): the tcgen05 implicit GEMM with tf32 operands instead of the FP32 CUDA-core kernel."""
+    import os
     lib = L.load()
     n, c, h, wd = x_nchw.shape
     assert c == 3
     cout = w.shape[0]
+    if tensor_cores is None:
+        tensor_cores = cout == 64 and not os.environ.get("B200LP_C3_CUDA_CORES")
     y = torch.empty((n, h, wd, cout), dtype=torch.float32, device=x_nchw.device)
+    fn = lib.b200lp_conv3x3_c3_fwd_tc if tensor_cores else lib.b200lp_conv3x3_c3_fwd
     with _timed("conv3x3_c3_fwd", nbytes=4.0 * (x_nchw.numel() + y.numel())):
-        L.check(lib.b200lp_conv3x3_c3_fwd(L.ptr(x_nchw), L.ptr(w), L.ptr(wscale), L.ptr(bias), L.ptr(pre_scale),
-                                          L.ptr(pre_shift), L.ptr(y), n, h, wd, cout, int(relu), int(round_tf32),
-                                          L.stream_ptr()), "conv3x3_c3_fwd")
+        L.check(fn(L.ptr(x_nchw), L.ptr(w.contiguous()), L.ptr(wscale), L.ptr(bias), L.ptr(pre_scale), L.ptr(pre_shift),
+                   L.ptr(y), n, h, wd, cout, int(relu), int(round_tf32), L.stream_ptr()), "conv3x3_c3_fwd")
     return y
 
 

@@ -528,6 +528,153 @@ extern "C" int32_t b200lp_col2im3x3_c3(const float* dcol_nhwc32, const float* pr
     return B200LP_OK;
 }
 
+namespace b200lp {
+// ------------------------------------------------------------------------------------------------ Cin = 3 forward, tcgen05
+// The same layer as an implicit GEMM on the tensor cores: M = 128 consecutive pixels, N = 64 output channels, K = 27 taps
+// padded to 32.  There is no TMA-able layout for a 3-channel NCHW patch, so the 128 pixel threads BUILD the A tile:
+// each gathers its 27 inputs (input normalisation applied, zero padding, tf32 rounding) and writes its 128-byte row in
+// the canonical K-major SWIZZLE_128B order (16-byte chunk j of row r at ((j ^ (r & 7)) << 4)), a proxy fence hands the
+// tile to the async proxy, one thread issues four K = 8 MMAs into a 64-column TMEM accumulator, and the same 128 threads
+// run the epilogue (1/sigma, bias, ReLU, tf32 rounding, 256 contiguous bytes per pixel).  The CUDA-core kernel above
+// needs 1728 FMAs per pixel from shared-memory weights (72 us for 8 x 256^2); here the layer is bound by the 134 MB it writes.
+// Several CTAs per SM overlap each other's gather / MMA / store phases (24 KB of shared memory, 64 TMEM columns each).
+constexpr int kC3Cout = 64;
+
+__global__ void __launch_bounds__(128, 4)
+conv3x3_c3_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ wscale,
+                     const float* __restrict__ bias, const float* __restrict__ pre_scale,
+                     const float* __restrict__ pre_shift, float* __restrict__ y, int N, int H, int W, int relu,
+                     int round_out, int total_tiles) {
+    __shared__ __align__(1024) uint8_t sA[128 * 128];
+    __shared__ __align__(1024) uint8_t sB[kC3Cout * 128];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int r = threadIdx.x;                    // pixel row of the tile == TMEM lane
+    const int warp = r >> 5;
+    if (r == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<64>(&tmem_slot);
+    // B tile: row co = 27 (+5 zero) weights, k = c*9 + kh*3 + kw (the OIHW inner order), tf32-rounded, swizzled like A
+    if (r < kC3Cout) {
+        float wk[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) wk[k] = k < 27 ? round_tf32(__ldg(w + r * 27 + k)) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(sB + r * 128 + ((j ^ (r & 7)) << 4)) =
+                make_float4(wk[4 * j], wk[4 * j + 1], wk[4 * j + 2], wk[4 * j + 3]);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const float s = wscale ? __ldg(wscale) : 1.f;
+    float ps[3], pb[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        ps[c] = pre_scale ? __ldg(pre_scale + c) : 1.f;
+        pb[c] = pre_shift ? __ldg(pre_shift + c) : 0.f;
+    }
+    constexpr uint32_t idesc = make_idesc_tf32(128, kC3Cout, 0, 0);
+    const uint64_t desc_hi = make_smem_desc(0, 16, 1024, 2);
+    const uint64_t da0 = desc_hi | ((smem_u32(sA) >> 4) & 0x3FFFu);
+    const uint64_t db0 = desc_hi | ((smem_u32(sB) >> 4) & 0x3FFFu);
+    const long P = static_cast<long>(N) * H * W;
+    const long HW = static_cast<long>(H) * W;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const long p = static_cast<long>(tile) * 128 + r;
+        const bool valid = p < P;
+        const long pp = valid ? p : 0;
+        const int n = static_cast<int>(pp / HW);
+        const int hw = static_cast<int>(pp - n * HW);
+        const int h = hw / W, wq = hw - h * W;
+        // ---- gather: 27 inputs of this pixel (consecutive threads = consecutive w: coalesced, overlaps served by L1)
+        float v[32];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* xc = x + (static_cast<long>(n) * 3 + c) * HW;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const int hh = h + kh - 1;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int ww = wq + kw - 1;
+                    const bool in = valid && hh >= 0 && hh < H && ww >= 0 && ww < W;
+                    const float t = in ? __ldg(xc + static_cast<long>(hh) * W + ww) : 0.f;
+                    v[c * 9 + kh * 3 + kw] = in ? round_tf32(t * ps[c] + pb[c]) : 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 27; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(sA + r * 128 + ((j ^ (r & 7)) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_proxy_async_smem();                 // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncthreads();
+        if (r == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32_ss(tmem, da0 + 2 * k, db0 + 2 * k, idesc, k > 0 ? 1u : 0u);
+            umma_commit(&bar);
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+        // ---- epilogue: this thread's pixel, 64 channels
+        float* yrow = y + p * kC3Cout;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kC3Cout; c0 += 32) {
+            uint32_t a[32];
+            tmem_ld_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, a);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o = make_float4(__uint_as_float(a[j]) * s, __uint_as_float(a[j + 1]) * s,
+                                           __uint_as_float(a[j + 2]) * s, __uint_as_float(a[j + 3]) * s);
+                    if (bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                    *reinterpret_cast<float4*>(yrow + c0 + j) = o;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                          // every lane has drained the accumulator and the A tile is free again
+    }
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<64>(tmem);
+    }
+}
+}  // namespace b200lp
+
+extern "C" int32_t b200lp_conv3x3_c3_fwd_tc(const float* x_nchw, const float* w_oihw, const float* wscale,
+                                            const float* bias, const float* pre_scale, const float* pre_shift,
+                                            float* y_nhwc, int32_t N, int32_t H, int32_t W, int32_t Cout, int32_t relu,
+                                            int32_t round_tf32, void* stream) {
+    B200LP_REQUIRE(x_nchw && w_oihw && y_nhwc && N > 0 && H > 0 && W > 0, "conv3x3_c3_fwd_tc: bad args");
+    B200LP_REQUIRE(Cout == kC3Cout, "conv3x3_c3_fwd_tc: Cout=%d (the tensor-core stem takes 64 output channels)", Cout);
+    const long P = static_cast<long>(N) * H * W;
+    B200LP_REQUIRE(P < (1L << 31) * 64, "conv3x3_c3_fwd_tc: too many pixels");
+    const int total_tiles = static_cast<int>((P + 127) / 128);
+    const int blocks = total_tiles < 148 * 4 ? total_tiles : 148 * 4;
+    conv3x3_c3_tc_kernel<<<blocks, 128, 0, as_stream(stream)>>>(x_nchw, w_oihw, wscale, bias, pre_scale, pre_shift, y_nhwc,
+                                                               N, H, W, relu, round_tf32, total_tiles);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
+
 extern "C" int32_t b200lp_conv3x3_c3_fwd(const float* x_nchw, const float* w_oihw, const float* wscale,
                                          const float* bias, const float* pre_scale, const float* pre_shift,
                                          float* y_nhwc, int32_t N, int32_t H, int32_t W, int32_t Cout, int32_t relu,

@@ -221,7 +221,8 @@ def l1_relu_bwd(a, b, gscale, scale2, d_in=None):
 
 
 # ------------------------------------------------------------------------------------------------ Cin = 3 stems
-def conv3x3_c3_fwd(x_nchw, w, wscale=None, bias=None, pre_scale=None, pre_shift=None, relu=False, round_tf32=False):
+def conv3x3_c3_fwd(x_nchw, w, wscale=None, bias=None, pre_scale=None, pre_shift=None, relu=False, round_tf32=False,
+                   tensor_cores=None):
     x = x_nchw
     if pre_scale is not None:
         x = x * pre_scale[None, :, None, None] + pre_shift[None, :, None, None]

@@ -353,7 +353,7 @@ def direct_convs():
     ref = F.conv2d(xn, wd * 0.7, b.double(), padding=1).relu()
     dy = torch.randn_like(ref)
     ref.backward(dy)
-    y = K.conv3x3_c3_fwd(x, w, sc, b, ps, pb, relu=True)
+    y = K.conv3x3_c3_fwd(x, w, sc, b, ps, pb, relu=True, tensor_cores=False)          # the FP32 CUDA-core kernel
     add("c3_fwd", y.permute(0, 3, 1, 2), ref)
     dyh = (dy * (ref > 0)).float().permute(0, 2, 3, 1).contiguous()
     add("c3_dgrad", K.conv3x3_c3_dgrad(dyh, w, sc, ps), xd.grad)
@@ -1225,6 +1225,44 @@ def l1_code():
               for o, r in zip(outs, refs))
     out.append({"case": f"pack_conv_weight_tiles == pack_conv_weight ({len(rows)} copies)", "ok": bad == 0, "max_abs": float(bad),
                 "rel": float(bad), "nan": False, "ref_max": 0.0})
+    return out
+
+
+@check
+def c3_tensor_core():
+    """Cin = 3 stem forward on tcgen05 (A tile built in shared memory by the pixel threads) vs float64 torch on tf32-rounded
+    operands: input normalisation, bias, ReLU, 1/sigma, ragged pixel counts, the centre-tap (1x1) embedding; timing vs the
+    CUDA-core kernel at the step's shape."""
+    import torch
+    import torch.nn.functional as F
+    from b200lp import kernels as K
+    out = []
+    torch.manual_seed(19)
+    dev = "cuda"
+    for (n, h, w_, pre, relu, bias_on) in [(8, 256, 256, True, True, True), (2, 32, 32, False, False, True), (3, 20, 12, True, True, False),
+                                         (1, 4, 4, False, False, False), (8, 128, 128, False, False, True)]:
+        x = torch.rand(n, 3, h, w_, device=dev)
+        wt = torch.randn(64, 3, 3, 3, device=dev) * 0.2
+        b = torch.randn(64, device=dev) if bias_on else None
+        sc = torch.tensor([0.7], device=dev)
+        psc = torch.tensor([255.0, 255.0, 255.0], device=dev) if pre else None
+        psh = torch.tensor([-103.9, -116.8, -123.7], device=dev) if pre else None
+        y = K.conv3x3_c3_fwd(x, wt, sc, b, psc, psh, relu=relu, round_tf32=False, tensor_cores=True)
+        xin = x.double() if not pre else x.double() * psc.double()[None, :, None, None] + psh.double()[None, :, None, None]
+        xin = tf32_round(xin.float()).double()
+        ref = F.conv2d(xin, tf32_round(wt).double(), padding=1) * 0.7
+        if b is not None:
+            ref = ref + b.double()[None, :, None, None]
+        if relu:
+            ref = ref.relu()
+        out.append(_cmp(f"c3 tensor-core fwd N{n} {h}x{w_} pre{int(pre)} relu{int(relu)}", y, ref.permute(0, 2, 3, 1), 2e-5))
+    x = torch.rand(8, 3, 256, 256, device=dev)
+    wt = torch.randn(64, 3, 3, 3, device=dev) * 0.2
+    b = torch.randn(64, device=dev)
+    rec = {"case": "timing c3 fwd 8x256x256 -> 64 (us)", "ok": True, "max_abs": 0.0, "rel": 0.0, "nan": False, "ref_max": 0.0}
+    rec["tensor_core_us"] = round(_time_us(lambda: K.conv3x3_c3_fwd(x, wt, None, b, relu=True, round_tf32=True, tensor_cores=True)), 1)
+    rec["cuda_core_us"] = round(_time_us(lambda: K.conv3x3_c3_fwd(x, wt, None, b, relu=True, round_tf32=True, tensor_cores=False)), 1)
+    out.append(rec)
     return out
 
 
