@@ -540,7 +540,7 @@ namespace b200lp {
 // Several CTAs per SM overlap each other's gather / MMA / store phases (24 KB of shared memory, 64 TMEM columns each).
 constexpr int kC3Cout = 64;
 
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 6)
 conv3x3_c3_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ wscale,
                      const float* __restrict__ bias, const float* __restrict__ pre_scale,
                      const float* __restrict__ pre_shift, float* __restrict__ y, int N, int H, int W, int relu,
@@ -626,27 +626,36 @@ conv3x3_c3_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, c
         mbar_wait(&bar, phase);
         phase ^= 1u;
         tc_fence_after();
-        // ---- epilogue: this thread's pixel, 64 channels
-        float* yrow = y + p * kC3Cout;
+        // ---- epilogue: 32 channels at a time through the (now free) A tile so that the global stores are coalesced: each
+        // thread parks its pixel's 128 bytes in shared memory (same XOR swizzle: conflict-free), then the block writes the
+        // 128 x 128-byte half-rows with consecutive threads on consecutive 16-byte chunks (a warp = 4 whole lines)
+        const long p0 = static_cast<long>(tile) * 128;
 #pragma unroll 1
         for (int c0 = 0; c0 < kC3Cout; c0 += 32) {
             uint32_t a[32];
             tmem_ld_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, a);
             tmem_ld_wait();
-            if (valid) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o = make_float4(__uint_as_float(a[j]) * s, __uint_as_float(a[j + 1]) * s,
-                                           __uint_as_float(a[j + 2]) * s, __uint_as_float(a[j + 3]) * s);
-                    if (bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                    }
-                    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                    if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-                    *reinterpret_cast<float4*>(yrow + c0 + j) = o;
+            for (int j = 0; j < 32; j += 4) {
+                float4 o = make_float4(__uint_as_float(a[j]) * s, __uint_as_float(a[j + 1]) * s,
+                                       __uint_as_float(a[j + 2]) * s, __uint_as_float(a[j + 3]) * s);
+                if (bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                 }
+                if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                *reinterpret_cast<float4*>(sA + r * 128 + (((j >> 2) ^ (r & 7)) << 4)) = o;
             }
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int q = (r >> 3) + 16 * it, j = r & 7;            // pixel q of the tile, 16-byte chunk j
+                if (p0 + q < P)
+                    *reinterpret_cast<float4*>(y + (p0 + q) * kC3Cout + c0 + 4 * j) =
+                        *reinterpret_cast<const float4*>(sA + q * 128 + ((j ^ (q & 7)) << 4));
+            }
+            __syncthreads();
         }
         tc_fence_before();
         __syncthreads();                          // every lane has drained the accumulator and the A tile is free again
@@ -667,7 +676,7 @@ extern "C" int32_t b200lp_conv3x3_c3_fwd_tc(const float* x_nchw, const float* w_
     const long P = static_cast<long>(N) * H * W;
     B200LP_REQUIRE(P < (1L << 31) * 64, "conv3x3_c3_fwd_tc: too many pixels");
     const int total_tiles = static_cast<int>((P + 127) / 128);
-    const int blocks = total_tiles < 148 * 4 ? total_tiles : 148 * 4;
+    const int blocks = total_tiles < 148 * 6 ? total_tiles : 148 * 6;
     conv3x3_c3_tc_kernel<<<blocks, 128, 0, as_stream(stream)>>>(x_nchw, w_oihw, wscale, bias, pre_scale, pre_shift, y_nhwc,
                                                                N, H, W, relu, round_tf32, total_tiles);
     B200LP_CHECK_CUDA(cudaGetLastError());
