@@ -271,6 +271,13 @@ int32_t b200lp_l1_sum_code(const float* a, const float* b, float* out, uint8_t* 
                            void* stream);
 int32_t b200lp_l1_code_bwd(const uint8_t* code, const float* gscale, float scale2, const float* d_in, float* d_out,
                            int64_t n, void* stream);
+/* The tap in front of an AvgPool2d(2) (a, b: [N,H,W,C], H and W even): the forward pass also writes the pooled, tf32-rounded
+ * maps a_pool, b_pool [N,H/2,W/2,C] (= b200lp_avgpool2 of each); the backward pass takes the gradient of the POOLED map,
+ *   d_out[n,h,w,c] = code ? tf32( 0.25 * d_low[n,h/2,w/2,c] + (code - 2) * gscale[0]*scale2 ) : 0 . */
+int32_t b200lp_l1_sum_code_pool(const float* a, const float* b, float* out, uint8_t* code, float* a_pool, float* b_pool,
+                                int32_t N, int32_t H, int32_t W, int32_t C, float scale, void* stream);
+int32_t b200lp_l1_code_bwd_unpool(const uint8_t* code, const float* gscale, float scale2, const float* d_low, float* d_out,
+                                  int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Direct (CUDA-core) convolutions for the two degenerate, HBM-bound shapes (SURVEY §7 "Degenerate GEMM shapes").

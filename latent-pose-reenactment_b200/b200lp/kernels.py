@@ -414,6 +414,31 @@ def l1_code_bwd(code, shape, gscale, scale2, d_in=None):
     return d
 
 
+def l1_sum_code_pool(a, b, out, scale):
+    """l1_sum_code fused with the 2x2 average pool that follows the tap: -> (code, a_pooled, b_pooled), pooled maps tf32-rounded."""
+    lib = L.load()
+    n, h, w, c = a.shape
+    code = torch.empty((a.numel() // 4,), dtype=torch.uint8, device=a.device)
+    ap = torch.empty((n, h // 2, w // 2, c), dtype=torch.float32, device=a.device)
+    bp = torch.empty_like(ap)
+    with _timed("l1", nbytes=8.25 * a.numel() + 8.0 * ap.numel()):
+        L.check(lib.b200lp_l1_sum_code_pool(L.ptr(a), L.ptr(b), L.ptr(out), L.ptr(code, torch.uint8), L.ptr(ap), L.ptr(bp),
+                                            n, h, w, c, c_float(scale), L.stream_ptr()), "l1_sum_code_pool")
+    return code, ap, bp
+
+
+def l1_code_bwd_unpool(code, shape, gscale, scale2, d_low):
+    """avgpool2_bwd + l1_code_bwd in one pass: d_low is the gradient of the pooled map, `shape` the tap's (N,H,W,C)."""
+    lib = L.load()
+    n, h, w, c = shape
+    d = torch.empty(shape, dtype=torch.float32, device=code.device)
+    assert tuple(d_low.shape) == (n, h // 2, w // 2, c)
+    with _timed("l1", nbytes=4.25 * d.numel() + 4.0 * d_low.numel()):
+        L.check(lib.b200lp_l1_code_bwd_unpool(L.ptr(code, torch.uint8), L.ptr(gscale), c_float(scale2), L.ptr(d_low),
+                                              L.ptr(d), n, h, w, c, L.stream_ptr()), "l1_code_bwd_unpool")
+    return d
+
+
 def l1_bwd(a, b, gscale, scale2, da=None):
     """da (+)= sign(a-b) * gscale[0] * scale2."""
     lib = L.load()

@@ -98,6 +98,8 @@ SIGNATURES = {
     "b200lp_l1_relu_bwd": (_I, [_P, _P, _P, _F, _P, _P, _L, _P]),
     "b200lp_l1_sum_code": (_I, [_P, _P, _P, _P, _L, _F, _P]),
     "b200lp_l1_code_bwd": (_I, [_P, _P, _F, _P, _P, _L, _P]),
+    "b200lp_l1_sum_code_pool": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "b200lp_l1_code_bwd_unpool": (_I, [_P, _P, _F, _P, _P, _I, _I, _I, _I, _P]),
     "b200lp_conv3x3_c3_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "b200lp_conv3x3_c3_fwd_tc": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "b200lp_conv3x3_c3_dgrad": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),

@@ -776,12 +776,12 @@ class VggPerceptualFn(torch.autograd.Function):
         dev = fake_nchw.device
         loss = torch.zeros(1, dtype=torch.float32, device=dev)
         a = b = None
-        saved = []          # per ReLU tap: (backward code of l1_sum_code, feature shape)
+        saved = []          # per ReLU tap: (backward code of l1_sum_code, feature shape, pooled-after flag)
         need_bwd = ctx.needs_input_grad[0]
         fake = fake_nchw.contiguous()
         real = real_nchw.contiguous()
-        n_taps = 0
-        for kind, idx in plan:
+        skip_pool = False
+        for pos, (kind, idx) in enumerate(plan):
             if kind == "conv0":   # conv + relu fused (every VGG conv is followed by a ReLU tap)
                 a = K.conv3x3_c3_fwd(fake, packed["w0"], None, packed["b0"], packed["pre_scale"], packed["pre_shift"],
                                      relu=True, round_tf32=True)
@@ -791,14 +791,23 @@ class VggPerceptualFn(torch.autograd.Function):
                 a = K.conv_fwd(a, packed["wp"][idx], 3, bias=packed["bias"][idx], relu=True, round_tf32=True)
                 b = K.conv_fwd(b, packed["wp"][idx], 3, bias=packed["bias"][idx], relu=True, round_tf32=True)
             elif kind == "pool":
+                if skip_pool:     # already produced by the fused tap before it
+                    skip_pool = False
+                    continue
                 a = K.avgpool2(a, None, round_tf32=True)
                 b = K.avgpool2(b, None, round_tf32=True)
                 continue
-            if need_bwd:    # the L1 term and, in the same pass, the 2-bit (ReLU mask, sign) code the backward tap needs
-                saved.append((K.l1_sum_code(a, b, loss, weight / a.numel()), tuple(a.shape)))
+            pool_next = (need_bwd and pos + 1 < len(plan) and plan[pos + 1][0] == "pool"
+                         and a.shape[1] % 2 == 0 and a.shape[2] % 2 == 0)
+            if pool_next:   # tap + the pool behind it in one pass over both feature maps
+                shape = tuple(a.shape)
+                code, a, b = K.l1_sum_code_pool(a, b, loss, weight / a.numel())
+                saved.append((code, shape, True))
+                skip_pool = True
+            elif need_bwd:  # the L1 term and, in the same pass, the 2-bit (ReLU mask, sign) code the backward tap needs
+                saved.append((K.l1_sum_code(a, b, loss, weight / a.numel()), tuple(a.shape), False))
             else:
                 K.l1_sum(a, b, loss, weight / a.numel())
-            n_taps += 1
         ctx.packed = packed
         ctx.weight = weight
         ctx.saved_feats = saved
@@ -813,17 +822,27 @@ class VggPerceptualFn(torch.autograd.Function):
         d = None                     # gradient w.r.t. the current activation (post-ReLU feature), NHWC
         tap = len(saved) - 1
         dx_img = None
+        pending_pool = False         # a pool entry was passed whose un-pooling the tap before it will do
         for kind, idx in reversed(plan):
             if kind == "pool":
-                d = K.avgpool2_bwd(d)
+                if tap >= 0 and saved[tap][2]:
+                    pending_pool = True
+                else:
+                    d = K.avgpool2_bwd(d)
                 continue
-            code, shape = saved[tap]
+            code, shape, pooled = saved[tap]
             tap -= 1
-            # d(loss)/d(a) gets the L1 term of this tap, then passes the ReLU mask (one pass over the code + d)
             numel = 1
             for v in shape:
                 numel *= v
-            d = K.l1_code_bwd(code, shape, gs, ctx.weight / numel, d_in=d)
+            # d(loss)/d(a) gets the L1 term of this tap, then passes the ReLU mask (one pass over the code + d)
+            if pooled and pending_pool and d is not None:
+                d = K.l1_code_bwd_unpool(code, shape, gs, ctx.weight / numel, d)
+            else:
+                if pending_pool and d is not None:
+                    d = K.avgpool2_bwd(d)
+                d = K.l1_code_bwd(code, shape, gs, ctx.weight / numel, d_in=d)
+            pending_pool = False
             if kind == "conv":
                 d = K.conv_fwd(d, packed["wpt"][idx], 3)
             else:

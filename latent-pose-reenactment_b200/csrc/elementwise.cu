@@ -592,6 +592,81 @@ __global__ void l1_code_bwd_kernel(const unsigned char* __restrict__ code, const
             d_out[i] = quad(HAS_IN ? __ldg(d_in + i) : zero, code[i]);
 }
 
+// The same tap when a 2x2 average pool follows it (VGG conv1_2 / 2_2 / 3_4 / 4_4): one thread owns a 2x2 pixel block of
+// 4 channels, so the pass that already reads both feature maps also writes their pooled (tf32-rounded) versions — the
+// two avgpool2 launches per tap and their 8 B/element of reads disappear.  Codes keep the flat float4 indexing.
+__global__ void l1_sum_code_pool_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float* __restrict__ out,
+                                        unsigned char* __restrict__ code, float4* __restrict__ ap, float4* __restrict__ bp,
+                                        long total, int Ho, int Wo, int C4, float scale) {
+    float acc = 0.f;
+    const long rowq = 2L * Wo * C4;                     // float4s per full-resolution image row
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C4);
+        long t = i / C4;
+        const int wo = static_cast<int>(t % Wo);
+        t /= Wo;
+        const int ho = static_cast<int>(t % Ho);
+        const long n = t / Ho;
+        const long i00 = ((n * 2 * Ho + 2 * ho) * 2L * Wo + 2 * wo) * C4 + c;
+        const long idx[4] = {i00, i00 + C4, i00 + rowq, i00 + rowq + C4};
+        float4 u[4], v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { u[k] = __ldg(a + idx[k]); v[k] = __ldg(b + idx[k]); }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            acc += l1_abs4(u[k], v[k]);
+            code[idx[k]] = static_cast<unsigned char>(l1_code4(u[k], v[k]));
+        }
+        auto pool = [](const float4 (&q)[4]) -> float4 {
+            return make_float4(round_tf32(((q[0].x + q[1].x) + (q[2].x + q[3].x)) * 0.25f),
+                               round_tf32(((q[0].y + q[1].y) + (q[2].y + q[3].y)) * 0.25f),
+                               round_tf32(((q[0].z + q[1].z) + (q[2].z + q[3].z)) * 0.25f),
+                               round_tf32(((q[0].w + q[1].w) + (q[2].w + q[3].w)) * 0.25f));
+        };
+        ap[i] = pool(u);
+        bp[i] = pool(v);
+    }
+    __shared__ float ws[kEwThreads / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < kEwThreads / 32 ? ws[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(out, v * scale);
+    }
+}
+
+// backward of that pair: d_out[2x2 block] = code ? tf32(0.25 * d_low + (code - 2) * g) : 0   (avgpool2_bwd + l1_code_bwd)
+__global__ void l1_code_bwd_unpool_kernel(const unsigned char* __restrict__ code, const float* __restrict__ gscale,
+                                          float scale2, const float4* __restrict__ d_low, float4* __restrict__ d_out,
+                                          long total, int Ho, int Wo, int C4) {
+    const float g = (gscale ? __ldg(gscale) : 1.f) * scale2;
+    auto one = [g](float din, unsigned cc) -> float {
+        return cc ? round_tf32(din + (static_cast<float>(cc) - 2.f) * g) : 0.f;
+    };
+    const long rowq = 2L * Wo * C4;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C4);
+        long t = i / C4;
+        const int wo = static_cast<int>(t % Wo);
+        t /= Wo;
+        const int ho = static_cast<int>(t % Ho);
+        const long n = t / Ho;
+        const long i00 = ((n * 2 * Ho + 2 * ho) * 2L * Wo + 2 * wo) * C4 + c;
+        const long idx[4] = {i00, i00 + C4, i00 + rowq, i00 + rowq + C4};
+        float4 d = __ldg(d_low + i);
+        d.x *= 0.25f; d.y *= 0.25f; d.z *= 0.25f; d.w *= 0.25f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned cc = code[idx[k]];
+            d_out[idx[k]] = make_float4(one(d.x, cc & 3u), one(d.y, (cc >> 2) & 3u), one(d.z, (cc >> 4) & 3u), one(d.w, cc >> 6));
+        }
+    }
+}
+
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, long total) {
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -916,6 +991,35 @@ extern "C" int32_t b200lp_l1_code_bwd(const uint8_t* code, const float* gscale, 
     else
         l1_code_bwd_kernel<false><<<g, kEwThreads, 0, as_stream(stream)>>>(code, gscale, scale2, nullptr,
                                                                            reinterpret_cast<float4*>(d_out), n / 4);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_l1_sum_code_pool(const float* a, const float* b, float* out, uint8_t* code, float* a_pool,
+                                           float* b_pool, int32_t N, int32_t H, int32_t W, int32_t C, float scale,
+                                           void* stream) {
+    B200LP_REQUIRE(a && b && out && code && a_pool && b_pool && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 &&
+                       C > 0 && C % 4 == 0, "l1_sum_code_pool: bad args (H, W even, C %% 4 == 0)");
+    const long total = static_cast<long>(N) * (H / 2) * (W / 2) * (C / 4);
+    int g = grid_for(total, kEwThreads);
+    if (g > 148 * 8) g = 148 * 8;
+    l1_sum_code_pool_kernel<<<g, kEwThreads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), out, code, reinterpret_cast<float4*>(a_pool),
+        reinterpret_cast<float4*>(b_pool), total, H / 2, W / 2, C / 4, scale);
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
+
+extern "C" int32_t b200lp_l1_code_bwd_unpool(const uint8_t* code, const float* gscale, float scale2, const float* d_low,
+                                             float* d_out, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+    B200LP_REQUIRE(code && d_low && d_out && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 4 == 0,
+                   "l1_code_bwd_unpool: bad args (H, W even, C %% 4 == 0)");
+    const long total = static_cast<long>(N) * (H / 2) * (W / 2) * (C / 4);
+    l1_code_bwd_unpool_kernel<<<grid_for(total, kEwThreads), kEwThreads, 0, as_stream(stream)>>>(
+        code, gscale, scale2, reinterpret_cast<const float4*>(d_low), reinterpret_cast<float4*>(d_out), total, H / 2, W / 2,
+        C / 4);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

@@ -205,6 +205,14 @@ def l1_code_bwd(code, shape, gscale, scale2, d_in=None):
     return torch.where(code > 0, d, torch.zeros_like(d)).reshape(shape)
 
 
+def l1_sum_code_pool(a, b, out, scale):
+    return l1_sum_code(a, b, out, scale), avgpool2(a), avgpool2(b)
+
+
+def l1_code_bwd_unpool(code, shape, gscale, scale2, d_low):
+    return l1_code_bwd(code, shape, gscale, scale2, d_in=avgpool2_bwd(d_low))
+
+
 def l1_bwd(a, b, gscale, scale2, da=None):
     g = torch.sign(a - b) * (gscale.reshape(()) * scale2)
     if da is not None:
@@ -401,7 +409,7 @@ EMULATED = [
     "disc_head_fwd", "disc_head_bwd",
     "pack_conv_weight", "conv_fwd", "conv_wgrad", "conv_wgrad_sn_acc", "bias_grad", "sn_scratch", "sn_sigma_multi",
     "sn_wgrad_fix", "in_stats", "adain_relu", "adain_relu_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "relu_round", "relu_bwd", "relu_bwd_fused",
-    "avgpool2", "avgpool2_bwd", "upsample2_bwd", "l1_sum", "l1_sum_code", "l1_code_bwd", "l1_bwd", "l1_relu_bwd", "conv3x3_c3_fwd", "im2col3x3_c3",
+    "avgpool2", "avgpool2_bwd", "upsample2_bwd", "l1_sum", "l1_sum_code", "l1_code_bwd", "l1_sum_code_pool", "l1_code_bwd_unpool", "l1_bwd", "l1_relu_bwd", "conv3x3_c3_fwd", "im2col3x3_c3",
     "col2im3x3_c3", "gen_tail_fwd", "gen_tail_compose", "gen_tail_bwd_act", "gen_tail_bwd", "copy_plan", "copy_multi",
 ]
 

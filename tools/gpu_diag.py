@@ -1206,6 +1206,24 @@ def l1_code():
             ref = K.l1_relu_bwd(a, b, gs, scale, d_in=d_in if has_in else None)
             got = K.l1_code_bwd(code, shape, gs, scale, d_in=d_in if has_in else None)
             out.append(_cmp(f"l1_code_bwd in{int(has_in)} {tag}", got, tf32_round(ref), 1e-6))
+    # the tap in front of a 2x2 average pool: codes, loss and pooled maps in one pass; un-pooling fused into the backward tap
+    for shape in [(8, 64, 64, 256), (2, 6, 10, 64), (1, 2, 2, 4)]:
+        a = tf32_round(torch.randn(shape, device=dev).relu())
+        b = tf32_round(torch.randn(shape, device=dev).relu())
+        gs = torch.tensor([1.3], device=dev)
+        scale = 3e-2 / a.numel()
+        l0 = torch.zeros(1, device=dev); l1 = torch.zeros(1, device=dev)
+        code_ref = K.l1_sum_code(a, b, l0, scale)
+        code, ap, bp = K.l1_sum_code_pool(a, b, l1, scale)
+        tag = "x".join(map(str, shape))
+        out.append(_cmp(f"l1_sum_code_pool loss {tag}", l1, l0, 1e-5))
+        out.append({"case": f"l1_sum_code_pool code {tag}", "ok": bool(torch.equal(code, code_ref)), "max_abs": 0.0, "rel": 0.0,
+                    "nan": False, "ref_max": 0.0})
+        out.append(_cmp(f"l1_sum_code_pool a_pool {tag}", ap, K.avgpool2(a, None, round_tf32=True), 1e-7))
+        out.append(_cmp(f"l1_sum_code_pool b_pool {tag}", bp, K.avgpool2(b, None, round_tf32=True), 1e-7))
+        d_low = torch.randn_like(ap) * 1e-3
+        ref = K.l1_code_bwd(code_ref, shape, gs, scale, d_in=K.avgpool2_bwd(d_low))
+        out.append(_cmp(f"l1_code_bwd_unpool {tag}", K.l1_code_bwd_unpool(code, shape, gs, scale, d_low), ref, 1e-7))
     # tiled multi-tensor packing == per-tensor kernel, bit for bit
     ws = [torch.randn(64, 64, 3, 3, device=dev), torch.randn(512, 256, 3, 3, device=dev), torch.randn(128, 64, 1, 1, device=dev),
           torch.randn(32, 96, 3, 3, device=dev), torch.randn(48, 40, 3, 3, device=dev)]
