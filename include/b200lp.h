@@ -222,12 +222,15 @@ int32_t b200lp_adain_relu(const float* x, const float* mean, const float* rstd, 
                           const float* beta, int64_t affine_stride, float* y, void* y_split, int32_t N, int32_t H,
                           int32_t W, int32_t C, int32_t upsample2, int32_t round_tf32, void* stream);
 /* backward of the above: given dy (w.r.t. the post-ReLU, possibly 2x-upsampled output) produce
- * dx, dgamma[n,c], dbeta[n,c].  The ReLU mask is recomputed from x (no saved activation needed). */
+ * dx, dgamma[n,c], dbeta[n,c].  The ReLU mask is recomputed from x (no saved activation needed).
+ * add (optional, shaped like x): a second gradient of x (the residual block's skip branch) merged into dx;
+ * round_tf32: dx stored rounded to tf32 (it only feeds the previous layer's tf32 gradient MMAs). */
 int64_t b200lp_adain_relu_bwd_workspace(int32_t N, int32_t HW, int32_t C);
 int32_t b200lp_adain_relu_bwd(const float* x, const float* mean, const float* rstd, const float* gamma,
                               const float* beta, int64_t affine_stride, const float* dy, float* dx, float* dgamma,
                               float* dbeta, float* workspace, int64_t workspace_bytes, int32_t N, int32_t H,
-                              int32_t W, int32_t C, int32_t upsample2, void* stream);
+                              int32_t W, int32_t C, int32_t upsample2, const float* add, int32_t round_tf32,
+                              void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Small elementwise / reduction kernels (all NHWC unless stated).

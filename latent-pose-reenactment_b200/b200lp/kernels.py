@@ -294,7 +294,8 @@ def adain_relu(x, mean, rstd, gamma, beta, upsample2=False, round_tf32=True, wan
     return y if want_f32 else ys
 
 
-def adain_relu_bwd(x, mean, rstd, gamma, beta, dy, upsample2=False):
+def adain_relu_bwd(x, mean, rstd, gamma, beta, dy, upsample2=False, add=None, round_tf32=False):
+    """-> (dx, dgamma, dbeta); `add`: a second gradient of x merged into dx, `round_tf32`: dx stored rounded to tf32."""
     lib = L.load()
     n, h, w, c = x.shape
     gp, bp, stride = _affine_views(gamma, beta)
@@ -305,7 +306,7 @@ def adain_relu_bwd(x, mean, rstd, gamma, beta, dy, upsample2=False):
     with _timed("adain_relu_bwd", nbytes=4.0 * (2 * x.numel() + dy.numel())):   # ideal: read x, dy once; write dx
         L.check(lib.b200lp_adain_relu_bwd(L.ptr(x), L.ptr(mean), L.ptr(rstd), gp, bp, stride, L.ptr(dy), L.ptr(dx),
                                           L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), ws.numel() * 4, n, h, w, c,
-                                          int(upsample2), L.stream_ptr()), "adain_relu_bwd")
+                                          int(upsample2), L.ptr(add), int(round_tf32), L.stream_ptr()), "adain_relu_bwd")
     return dx, dgamma, dbeta
 
 

@@ -310,6 +310,104 @@ class AdaINConvFn(torch.autograd.Function):
         return dx, dgm, dbt, dw, ds, dr, None, None, None, None, None, None
 
 
+class AdaResBlockFn(torch.autograd.Function):
+    """A whole generator block as ONE autograd node, bf16x3 precision (generators/common/blocks.py:47-111 with
+    norm_layer='adain'; reference Sequential AdaIN -> ReLU -> [2x] -> conv -> AdaIN -> ReLU -> conv, + skip):
+        y1  = conv3x3( relu(adain(x; g0, b0)) [2x] ; W0/s0 )
+        s   = conv1x1(x; Ws/ss) + bs at the LOW resolution, or x
+        out = conv3x3( relu(adain(y1; g1, b1)) ; W1/s1 ) + s [nearest 2x in the epilogue]
+    Forward = the kernels of two AdaINConvFn + Conv2dFn.  The hand-scheduled backward merges the block input's two
+    gradients (main branch through the first AdaIN, skip branch) inside the AdaIN-backward apply pass instead of an
+    `at::add`, and stores every gradient that only feeds tf32 MMAs rounded to tf32 instead of letting the MMA truncate
+    (the generator's first blocks sit behind 16 gradient convs: truncation alone shrank their gradient norms by 0.5 %).
+    convs: c0 = (w, s, cache, sn), c1 likewise, sk = (w, s, b, cache, sn) or None."""
+
+    @staticmethod
+    def forward(ctx, x, g0, b0, g1, b1, x_split, convs, upsample, emit_split, eps, *params):
+        ctx.set_materialize_grads(False)
+        w0, s0, c0, _ = convs["c0"]
+        w1, s1, c1, _ = convs["c1"]
+        need_bwd = any(ctx.needs_input_grad)
+        mean0, rstd0 = K.in_stats(x, eps)
+        if need_bwd:
+            a0_f32, a0_split = K.adain_relu(x, mean0, rstd0, g0, b0, upsample2=upsample, round_tf32=True, want_f32=True,
+                                            want_split=True)
+        else:
+            a0_f32, a0_split = None, K.adain_relu(x, mean0, rstd0, g0, b0, upsample2=upsample, want_f32=False, want_split=True)
+        y1 = K.conv_fwd(a0_split, _packed(w0, c0, False, K.BF16X3), 3, scale=s0)
+        del a0_split
+        if convs["sk"] is not None:
+            ws, ss, bs, cs, _ = convs["sk"]
+            if x_split is not None:
+                s = K.conv_fwd(x_split, _packed(ws, cs, False, K.BF16X3), 1, bias=bs, scale=ss)
+            else:
+                s = K.conv_fwd(x, _packed(ws, cs, False), 1, bias=bs, scale=ss)
+            mode = 2 if upsample else 1
+        else:
+            s, mode = x, 1
+        mean1, rstd1 = K.in_stats(y1, eps)
+        if need_bwd:
+            a1_f32, a1_split = K.adain_relu(y1, mean1, rstd1, g1, b1, round_tf32=True, want_f32=True, want_split=True)
+        else:
+            a1_f32, a1_split = None, K.adain_relu(y1, mean1, rstd1, g1, b1, want_f32=False, want_split=True)
+        out = K.conv_fwd(a1_split, _packed(w1, c1, False, K.BF16X3), 3, residual=s, residual_mode=mode,
+                         emit_split=emit_split, scale=s1)
+        y, y_split = out if emit_split else (out, None)
+        ctx.convs, ctx.upsample, ctx.mode = convs, upsample, mode
+        ctx.save_for_backward(x, mean0, rstd0, g0, b0, a0_f32, y1, mean1, rstd1, g1, b1, a1_f32)
+        if emit_split:
+            ctx.mark_non_differentiable(y_split)
+            return y, y_split
+        return y
+
+    @staticmethod
+    def backward(ctx, dy, *_unused):
+        x, mean0, rstd0, g0, b0, a0_f32, y1, mean1, rstd1, g1, b1, a1_f32 = ctx.saved_tensors
+        convs = ctx.convs
+        w0, s0, c0, sn0 = convs["c0"]
+        w1, s1, c1, sn1 = convs["c1"]
+        wants = ctx.needs_input_grad[10:]        # params: w0, w1[, ws, bs]
+        pgrads = [None] * len(wants)
+        dy = dy.contiguous()
+
+        def wgrad(slot, ksize, xin, w, s, cache, sn, d):
+            if wants[slot]:
+                _, dw, _ = _conv_backward(ksize, xin, w, s, d, False, True, False, cache, sn)
+                pgrads[slot] = dw
+
+        # second half-block
+        da1 = K.conv_fwd(dy, _packed(w1, c1, True), 3, scale=s1)
+        wgrad(1, 3, a1_f32, w1, s1, c1, sn1, dy)
+        dy1, dg1, db1 = K.adain_relu_bwd(y1, mean1, rstd1, g1, b1, da1, round_tf32=True)
+        del da1
+        # skip branch: gradient w.r.t. the block input
+        dr = dy if ctx.mode == 1 else K.upsample2_bwd(dy)
+        if convs["sk"] is not None:
+            ws, ss, bs, cs, sns = convs["sk"]
+            d_skip = K.conv_fwd(dr, _packed(ws, cs, True), 1, scale=ss)
+            wgrad(2, 1, x, ws, ss, cs, sns, dr)
+            if bs is not None and wants[3]:
+                bsink = _sink(bs)
+                if bsink is not None:
+                    K.bias_grad(dr, acc_into=bsink)
+                else:
+                    pgrads[3] = K.bias_grad(dr)
+        else:
+            d_skip = dr
+        # first half-block; the skip gradient joins in the AdaIN-backward apply pass
+        da0 = K.conv_fwd(dy1, _packed(w0, c0, True), 3, scale=s0)
+        wgrad(0, 3, a0_f32, w0, s0, c0, sn0, dy1)
+        dx, dg0, db0 = K.adain_relu_bwd(x, mean0, rstd0, g0, b0, da0, upsample2=ctx.upsample, add=d_skip, round_tf32=True)
+        return (dx, dg0, db0, dg1, db1, None, None, None, None, None, *pgrads)
+
+
+def ada_res_block(x, g0, b0, g1, b1, x_split, convs, upsample, emit_split, eps=1e-4):
+    params = [convs["c0"][0], convs["c1"][0]]
+    if convs["sk"] is not None:
+        params += [convs["sk"][0], convs["sk"][2]]
+    return AdaResBlockFn.apply(x, g0, b0, g1, b1, x_split, convs, upsample, emit_split, eps, *params)
+
+
 def adain_conv(x, gamma, beta, weight_orig, inv_sigma, residual=None, residual_mode=0, eps=1e-4, upsample2=False,
                emit_split=False, cache=None, sn=None):
     if residual is None:
@@ -452,7 +550,8 @@ class AdaINTailFn(torch.autograd.Function):
         if need_x or need_g or need_bt:
             wpt = K.pack_conv_weight(w32, transpose=True)             # (Cin, 9, 32): data-gradient layout, tf32
             d_a = K.conv_fwd(da, wpt, 3, scale=inv_sigma)
-            dx, dgm, dbt = K.adain_relu_bwd(x, mean, rstd, gamma, beta, d_a)
+            # dx is the last decoder block's output gradient: operand of its tf32 gradient MMAs -> stored rounded
+            dx, dgm, dbt = K.adain_relu_bwd(x, mean, rstd, gamma, beta, d_a, round_tf32=True)
         if need_w or need_s:
             g = K.conv_wgrad(a_f32, da, 3)[:4].contiguous()
             if need_s:

@@ -332,7 +332,7 @@ __global__ void adain_bwd_apply_kernel(const float* __restrict__ x, const float*
                                        const float* __restrict__ beta, long affine_stride,
                                        const float* __restrict__ dy, const float* __restrict__ dgamma,
                                        const float* __restrict__ dbeta, float* __restrict__ dx, int H, int W, int C,
-                                       int pix_per_chunk) {
+                                       int pix_per_chunk, const float* __restrict__ add, int round_out) {
     const int cq = C >> 2;
     const int lane_c = threadIdx.x % cq;
     const int row = threadIdx.x / cq;
@@ -383,7 +383,16 @@ __global__ void adain_bwd_apply_kernel(const float* __restrict__ x, const float*
             const float dz = z > 0.f ? d[j] : 0.f;
             o[j] = r_[j] * g[j] * (dz - mb[j] - xh * mg[j]);
         }
-        st4(dx + (static_cast<size_t>(n) * HW + p) * C + c, make_float4(o[0], o[1], o[2], o[3]));
+        const size_t off = (static_cast<size_t>(n) * HW + p) * C + c;
+        if (add) {          // a second gradient of the same tensor (the block's skip branch): merged here, not by at::add
+            const float4 a4 = ld4(add + off);
+            o[0] += a4.x; o[1] += a4.y; o[2] += a4.z; o[3] += a4.w;
+        }
+        if (round_out) {    // the result only feeds tf32 MMAs (which would truncate)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = round_tf32(o[j]);
+        }
+        st4(dx + off, make_float4(o[0], o[1], o[2], o[3]));
     }
 }
 
@@ -867,7 +876,7 @@ extern "C" int32_t b200lp_adain_relu_bwd(const float* x, const float* mean, cons
                                          const float* beta, int64_t affine_stride, const float* dy, float* dx,
                                          float* dgamma, float* dbeta, float* workspace, int64_t workspace_bytes,
                                          int32_t N, int32_t H, int32_t W, int32_t C, int32_t upsample2,
-                                         void* stream) {
+                                         const float* add, int32_t round_tf32, void* stream) {
     B200LP_REQUIRE(x && mean && rstd && gamma && beta && dy && dx && dgamma && dbeta && workspace,
                    "adain_relu_bwd: null pointer");
     B200LP_REQUIRE(N > 0 && H > 0 && W > 0 && C % 4 == 0 && C / 4 <= kEwThreads, "adain_relu_bwd: bad shape");
@@ -892,10 +901,10 @@ extern "C" int32_t b200lp_adain_relu_bwd(const float* x, const float* mean, cons
     count_launch();
     if (upsample2)
         adain_bwd_apply_kernel<true><<<grid, kEwThreads, 0, s>>>(x, mean, rstd, gamma, beta, affine_stride, dy, dgamma,
-                                                                 dbeta, dx, H, W, C, ppc);
+                                                                 dbeta, dx, H, W, C, ppc, add, round_tf32);
     else
         adain_bwd_apply_kernel<false><<<grid, kEwThreads, 0, s>>>(x, mean, rstd, gamma, beta, affine_stride, dy,
-                                                                  dgamma, dbeta, dx, H, W, C, ppc);
+                                                                  dgamma, dbeta, dx, H, W, C, ppc, add, round_tf32);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;

@@ -184,6 +184,21 @@ class AdaResBlock(nn.Module):
         precision 'tf32'  : adain_relu(tf32) -> conv -> adain_relu(tf32) -> conv(+skip), one TF32 MMA per K step;
         precision 'bf16x3': the same schedule with (hi, lo) bf16 operand planes and three MMAs per K step — generator
                             output within 1e-3 of the fp32 reference for O(1) AdaIN gains."""
+        import os
+        convs = [self.block.slot(self.i0), self.block.slot(self.i1)] + ([self.skip.slot(1)] if self.skip is not None else [])
+        if precision == 'bf16x3' and not os.environ.get('B200LP_NO_GEN_BLOCK_NODE') and \
+                all(m._pre is not None and m._pre[1] is not None for m in convs):
+            # the whole block as one autograd node (ops.AdaResBlockFn): kernel-merged input gradients, tf32-rounded
+            # gradient operands
+            w0, s0, _, e0 = convs[0].operands()
+            w1, s1, _, e1 = convs[1].operands()
+            spec = dict(c0=(w0, s0, e0["cache"], e0["sn"]), c1=(w1, s1, e1["cache"], e1["sn"]), sk=None)
+            if self.skip is not None:
+                ws, ss, bs, es = convs[2].operands()
+                spec["sk"] = (ws, ss, bs, es["cache"], es["sn"])
+            out = ops.ada_res_block(x, gamma0, beta0, gamma1, beta1, x_split if self.skip is not None else None, spec,
+                                    self.upsample, feeds_skip_conv)
+            return out if feeds_skip_conv else (out, None)
         w0, s0, _, e0 = self.block.slot(self.i0).operands()
         w1, s1, _, e1 = self.block.slot(self.i1).operands()
         if precision == 'bf16x3':

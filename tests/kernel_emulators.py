@@ -136,7 +136,7 @@ def adain_relu(x, mean, rstd, gamma, beta, upsample2=False, round_tf32=True, wan
     return y if want_f32 else ys
 
 
-def adain_relu_bwd(x, mean, rstd, gamma, beta, dy, upsample2=False):
+def adain_relu_bwd(x, mean, rstd, gamma, beta, dy, upsample2=False, add=None, round_tf32=False):
     """Autograd through the emulated forward INCLUDING the statistics' dependence on x."""
     with torch.enable_grad():
         xr = x.detach().requires_grad_(True)
@@ -147,6 +147,8 @@ def adain_relu_bwd(x, mean, rstd, gamma, beta, dy, upsample2=False):
         r = (xr.var((1, 2), unbiased=False) + eps).rsqrt()
         y = _adain(xr, m, r, gr, br, upsample2)
         dx, dg, db = torch.autograd.grad(y, [xr, gr, br], dy)
+    if add is not None:
+        dx = dx + add
     return dx, dg, db
 
 
