@@ -151,6 +151,11 @@ def test_full_size_training_step(full, gold):
     worst = []
     study = json.loads((ROOT / "profiles" / "r02_grad_error_study_torch_fp32_tf32.json").read_text())["torch_tf32"]
 
+    # gradient NORMS: 2.5e-3.  Achieved: generator <= 1.1e-3 (median 4e-4), discriminator <= 1.1e-3 — after the gradient
+    # operands of the tf32 MMAs were stored rounded instead of truncated (before: 5.0e-3 on the generator's first block,
+    # a 2^-12 bias per gradient conv compounding over 16 layers; profiles/r02_full_step_gradient_errors*.json)
+    NORM_TOL = 2.5e-3
+
     def elem_tol(name):
         return max(1e-2, 1.25 * study.get(name, {}).get("sub_rel_to_max", 0.0))
     for k, p in G.named_parameters():
@@ -160,7 +165,7 @@ def test_full_size_training_step(full, gold):
         e_sub = max_abs(sub(p.grad), ref_sub) / (float(ref_sub.abs().max()) + 1e-30)
         report["generator"][k] = {"norm_rel": e_norm, "sub_rel_to_max": e_sub, "ref_norm": ref_norm}
         if ref_norm > 1e-4 * g_max:          # analytically ~0 gradients (a bias the next InstanceNorm removes) are noise
-            worst.append((max(e_norm / 5e-3, e_sub / elem_tol(k)), k, e_norm, e_sub))
+            worst.append((max(e_norm / NORM_TOL, e_sub / elem_tol(k)), k, e_norm, e_sub))
     # d loss_G / d (embedder scale): a scalar that aggregates the generator's input gradients.  Those are chaotic at the
     # ~1 % level already between two fp32 implementations (profiles/r02_grad_error_study_torch_fp32_tf32.json: torch fp32
     # on the GPU vs on the CPU moves affine_params_projector.2.weight_orig's gradient by 7e-3 of its maximum); measured
@@ -180,7 +185,7 @@ def test_full_size_training_step(full, gold):
         e_sub = max_abs(sub(p.grad), ref_sub) / (float(ref_sub.abs().max()) + 1e-30)
         report["discriminator"][k] = {"norm_rel": e_norm, "sub_rel_to_max": e_sub, "ref_norm": ref_norm}
         if ref_norm > 1e-4 * d_max:
-            worst.append((max(e_norm / 5e-3, e_sub / elem_tol(k)), k, e_norm, e_sub))
+            worst.append((max(e_norm / NORM_TOL, e_sub / elem_tol(k)), k, e_norm, e_sub))
     opt_D.step()
     tm.update_running_average(0.999)
     out = ROOT / "gpurun_out"
