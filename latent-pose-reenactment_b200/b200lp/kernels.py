@@ -415,13 +415,17 @@ def l1_code_bwd(code, shape, gscale, scale2, d_in=None):
     return d
 
 
-def l1_sum_code_pool(a, b, out, scale):
-    """l1_sum_code fused with the 2x2 average pool that follows the tap: -> (code, a_pooled, b_pooled), pooled maps tf32-rounded."""
+def l1_sum_code_pool(a, b, out, scale, ap=None, bp=None):
+    """l1_sum_code fused with the 2x2 average pool that follows the tap: -> (code, a_pooled, b_pooled), pooled maps tf32-rounded
+    (written into `ap` / `bp` when given: contiguous (N, H/2, W/2, C) buffers, e.g. the two halves of one batch tensor)."""
     lib = L.load()
     n, h, w, c = a.shape
     code = torch.empty((a.numel() // 4,), dtype=torch.uint8, device=a.device)
-    ap = torch.empty((n, h // 2, w // 2, c), dtype=torch.float32, device=a.device)
-    bp = torch.empty_like(ap)
+    if ap is None:
+        ap = torch.empty((n, h // 2, w // 2, c), dtype=torch.float32, device=a.device)
+    if bp is None:
+        bp = torch.empty_like(ap)
+    assert tuple(ap.shape) == tuple(bp.shape) == (n, h // 2, w // 2, c)
     with _timed("l1", nbytes=8.25 * a.numel() + 8.0 * ap.numel()):
         L.check(lib.b200lp_l1_sum_code_pool(L.ptr(a), L.ptr(b), L.ptr(out), L.ptr(code, torch.uint8), L.ptr(ap), L.ptr(bp),
                                             n, h, w, c, c_float(scale), L.stream_ptr()), "l1_sum_code_pool")

@@ -874,33 +874,34 @@ class VggPerceptualFn(torch.autograd.Function):
         plan = packed["plan"]
         dev = fake_nchw.device
         loss = torch.zeros(1, dtype=torch.float32, device=dev)
-        a = b = None
         saved = []          # per ReLU tap: (backward code of l1_sum_code, feature shape, pooled-after flag)
         need_bwd = ctx.needs_input_grad[0]
-        fake = fake_nchw.contiguous()
-        real = real_nchw.contiguous()
+        # fake and real go through the frozen network as ONE batch of 2B images (first half fake, second half real): half
+        # the launches, twice the tiles per launch (the 16 x 16 layers no longer need split-K); a tap compares the halves
+        nb = fake_nchw.shape[0]
+        both = torch.cat([fake_nchw, real_nchw], dim=0).contiguous()
+        f = None
         skip_pool = False
         for pos, (kind, idx) in enumerate(plan):
             if kind == "conv0":   # conv + relu fused (every VGG conv is followed by a ReLU tap)
-                a = K.conv3x3_c3_fwd(fake, packed["w0"], None, packed["b0"], packed["pre_scale"], packed["pre_shift"],
-                                     relu=True, round_tf32=True)
-                b = K.conv3x3_c3_fwd(real, packed["w0"], None, packed["b0"], packed["pre_scale"], packed["pre_shift"],
+                f = K.conv3x3_c3_fwd(both, packed["w0"], None, packed["b0"], packed["pre_scale"], packed["pre_shift"],
                                      relu=True, round_tf32=True)
             elif kind == "conv":
-                a = K.conv_fwd(a, packed["wp"][idx], 3, bias=packed["bias"][idx], relu=True, round_tf32=True)
-                b = K.conv_fwd(b, packed["wp"][idx], 3, bias=packed["bias"][idx], relu=True, round_tf32=True)
+                f = K.conv_fwd(f, packed["wp"][idx], 3, bias=packed["bias"][idx], relu=True, round_tf32=True)
             elif kind == "pool":
                 if skip_pool:     # already produced by the fused tap before it
                     skip_pool = False
                     continue
-                a = K.avgpool2(a, None, round_tf32=True)
-                b = K.avgpool2(b, None, round_tf32=True)
+                f = K.avgpool2(f, None, round_tf32=True)
                 continue
+            a, b = f[:nb], f[nb:]
             pool_next = (need_bwd and pos + 1 < len(plan) and plan[pos + 1][0] == "pool"
                          and a.shape[1] % 2 == 0 and a.shape[2] % 2 == 0)
             if pool_next:   # tap + the pool behind it in one pass over both feature maps
                 shape = tuple(a.shape)
-                code, a, b = K.l1_sum_code_pool(a, b, loss, weight / a.numel())
+                pooled = torch.empty((2 * nb, shape[1] // 2, shape[2] // 2, shape[3]), dtype=torch.float32, device=dev)
+                code, _, _ = K.l1_sum_code_pool(a, b, loss, weight / a.numel(), ap=pooled[:nb], bp=pooled[nb:])
+                f = pooled
                 saved.append((code, shape, True))
                 skip_pool = True
             elif need_bwd:  # the L1 term and, in the same pass, the 2-bit (ReLU mask, sign) code the backward tap needs
@@ -910,7 +911,6 @@ class VggPerceptualFn(torch.autograd.Function):
         ctx.packed = packed
         ctx.weight = weight
         ctx.saved_feats = saved
-        ctx.fake = fake
         return loss[0]
 
     @staticmethod

@@ -207,8 +207,13 @@ def l1_code_bwd(code, shape, gscale, scale2, d_in=None):
     return torch.where(code > 0, d, torch.zeros_like(d)).reshape(shape)
 
 
-def l1_sum_code_pool(a, b, out, scale):
-    return l1_sum_code(a, b, out, scale), avgpool2(a), avgpool2(b)
+def l1_sum_code_pool(a, b, out, scale, ap=None, bp=None):
+    pa, pb = avgpool2(a), avgpool2(b)
+    if ap is not None:
+        ap.copy_(pa); pa = ap
+    if bp is not None:
+        bp.copy_(pb); pb = bp
+    return l1_sum_code(a, b, out, scale), pa, pb
 
 
 def l1_code_bwd_unpool(code, shape, gscale, scale2, d_low):
