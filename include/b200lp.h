@@ -426,18 +426,20 @@ int32_t b200lp_col_stats_parts(int64_t M);
 int32_t b200lp_col_stats(const float* x, float* part, int64_t M, int32_t C, void* stream);
 /* y = act(x*scale + shift (+ res [*res_scale + res_shift]));  act 0 none / 1 relu / 2 relu6.  scale/shift may be NULL
  * (identity).  Outputs (either or both): y fp32 (tf32-rounded when round_tf32) and y_split = (hi, lo) bf16 planes
- * [2][M][C] of the unrounded value (operand of the bf16x3 tensor-core GEMM). */
+ * [2][M][C] of the unrounded value (operand of the bf16x3 tensor-core GEMM).  mask_out (optional): one byte per 4
+ * elements, bit k = element k's activation passed (> 0) — what b200lp_bn_bwd's mask_mode 4 reads instead of y. */
 int32_t b200lp_bn_act(const float* x, const float* scale, const float* shift, const float* res, const float* res_scale,
                       const float* res_shift, float* y, void* y_split, int64_t M, int32_t C, int32_t act,
-                      int32_t round_tf32, void* stream);
+                      int32_t round_tf32, uint8_t* mask_out, void* stream);
 /* BatchNorm (+ activation) backward over [M][C].  dz = dy * mask, mask_mode 0: none; 1: mask_src > 0 (a materialised
- * activation output); 2: relu(x_raw*scale+shift) > 0; 3: 0 < x_raw*scale+shift < 6 (ReLU6).
+ * activation output, fp32 [M][C]); 2: relu(x_raw*scale+shift) > 0; 3: 0 < x_raw*scale+shift < 6 (ReLU6); 4: mask_src is the
+ * uint8 [M*C/4] bit mask written by b200lp_bn_act (0.25 instead of 4 bytes per element in both passes).
  *   dgamma (+)= sum dz*xhat, dbeta (+)= sum dz   (accumulate != 0: added to the buffers; either may be NULL)
  *   dx = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat))  [batch_stats != 0]   or   gamma*rstd*dz  [running statistics]
  *   dz_out (optional) = dz.   xhat = (x_raw - mean)*rstd.   dx tf32-rounded when round_tf32 (it feeds a TF32 GEMM).
  * Three launches (partial sums, fp64 fixed-order merge, apply); workspace >= b200lp_bn_bwd_workspace(M, C) bytes. */
 int64_t b200lp_bn_bwd_workspace(int64_t M, int32_t C);
-int32_t b200lp_bn_bwd(const float* dy, const float* mask_src, const float* x_raw, const float* mean, const float* rstd,
+int32_t b200lp_bn_bwd(const float* dy, const void* mask_src, const float* x_raw, const float* mean, const float* rstd,
                       const float* scale, const float* shift, const float* gamma, float* dgamma, float* dbeta,
                       int32_t accumulate, float* dx, float* dz_out, float* workspace, int64_t workspace_bytes, int64_t M,
                       int32_t C, int32_t mask_mode, int32_t batch_stats, int32_t round_tf32, void* stream);

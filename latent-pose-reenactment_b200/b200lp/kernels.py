@@ -782,22 +782,25 @@ def col_stats(x2d):
 
 
 def bn_act(x, scale=None, shift=None, res=None, res_scale=None, res_shift=None, act=1, round_tf32=True, want_f32=True,
-           want_split=False):
+           want_split=False, want_mask=False):
     """act(x*scale+shift (+ res[*res_scale+res_shift])) over an (..., C) tensor; act 0 none / 1 relu / 2 relu6.
-    Returns y (fp32), (y, y_split) or y_split with y_split (2, ...) bfloat16 (hi, lo) planes of the unrounded value."""
+    Returns y (fp32), (y, y_split) or y_split with y_split (2, ...) bfloat16 (hi, lo) planes of the unrounded value;
+    with want_mask additionally the uint8 (numel / 4,) activation bit mask that bn_bwd(mask_mode=4) reads (appended)."""
     lib = L.load()
     c = x.shape[-1]
     m = x.numel() // c
     y = torch.empty_like(x) if want_f32 else None
     ys = torch.empty((2,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device) if want_split else None
+    mask = torch.empty((x.numel() // 4,), dtype=torch.uint8, device=x.device) if want_mask else None
     n_in = 1 + int(res is not None)
     with _timed("batchnorm", nbytes=4.0 * x.numel() * (n_in + int(want_f32) + int(want_split))):
         L.check(lib.b200lp_bn_act(L.ptr(x), L.ptr(scale), L.ptr(shift), L.ptr(res), L.ptr(res_scale), L.ptr(res_shift),
-                                  L.ptr(y), L.ptr(ys, torch.bfloat16), m, c, int(act), int(round_tf32), L.stream_ptr()),
-                "bn_act")
-    if want_f32 and want_split:
-        return y, ys
-    return y if want_f32 else ys
+                                  L.ptr(y), L.ptr(ys, torch.bfloat16), m, c, int(act), int(round_tf32),
+                                  L.ptr(mask, torch.uint8), L.stream_ptr()), "bn_act")
+    out = (y, ys) if (want_f32 and want_split) else (y if want_f32 else ys)
+    if want_mask:
+        return (out + (mask,)) if isinstance(out, tuple) else (out, mask)
+    return out
 
 
 def bn_bwd(dy, x_raw, mean, rstd, gamma, scale=None, shift=None, mask_src=None, mask_mode=0, dgamma=None, dbeta=None,
@@ -815,7 +818,7 @@ def bn_bwd(dy, x_raw, mean, rstd, gamma, scale=None, shift=None, mask_src=None, 
     dz = torch.empty_like(dy) if want_dz else None
     n_streams = 3 + int(mask_mode == 1)
     with _timed("batchnorm", nbytes=4.0 * dy.numel() * (n_streams + int(want_dz))):   # ideal: dy, x read once, dx written
-        L.check(lib.b200lp_bn_bwd(L.ptr(dy), L.ptr(mask_src), L.ptr(x_raw), L.ptr(mean), L.ptr(rstd), L.ptr(scale),
+        L.check(lib.b200lp_bn_bwd(L.ptr(dy), L.ptr(mask_src, torch.uint8 if mask_mode == 4 else torch.float32), L.ptr(x_raw), L.ptr(mean), L.ptr(rstd), L.ptr(scale),
                                   L.ptr(shift), L.ptr(gamma), L.ptr(dgamma), L.ptr(dbeta), int(accumulate), L.ptr(dx),
                                   L.ptr(dz), L.ptr(ws), ws.numel() * 4, m, c, int(mask_mode), int(batch_stats),
                                   int(round_tf32), L.stream_ptr()), "bn_bwd")

@@ -129,7 +129,7 @@ SIGNATURES = {
     "b200lp_ema_multi": (_I, [_P, _P, _P, _I, _L, _F, _P]),
     "b200lp_col_stats_parts": (_I, [_L]),
     "b200lp_col_stats": (_I, [_P, _P, _L, _I, _P]),
-    "b200lp_bn_act": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P]),
+    "b200lp_bn_act": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P, _P]),
     "b200lp_bn_bwd_workspace": (_L, [_L, _I]),
     "b200lp_bn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _L, _L, _I, _I, _I, _I, _P]),
     "b200lp_gconv3x3_parts": (_I, [_I, _I, _I, _I, _I, _I]),

@@ -238,12 +238,19 @@ class Conv2dFn(torch.autograd.Function):
     def backward(ctx, dy, *_unused):
         x, weight_orig, inv_sigma, y = ctx.saved_tensors
         dy = dy.contiguous()
-        if ctx.relu:
-            dy = K.relu_bwd(y, dy)
         need_x, need_w, need_s, need_b, need_r = ctx.needs_input_grad[:5]
+        bias_done = False
+        if ctx.relu:
+            bsink = _sink(ctx.bias_ref) if (ctx.has_bias and need_b) else None
+            if bsink is not None and y.shape[-1] % 4 == 0 and y.shape[-1] <= 1024:
+                # ReLU mask, bias column sums and tf32 rounding of the gradient operand in one pass
+                dy = K.relu_bwd_fused(y, dy, bias_a=bsink, round_tf32=True)
+                bias_done = True
+            else:
+                dy = K.relu_bwd(y, dy)
         dx, dw, ds = _conv_backward(ctx.ksize, x, weight_orig, inv_sigma, dy, need_x, need_w, need_s, ctx.cache, ctx.sn)
         db = dr = None
-        if ctx.has_bias and need_b:
+        if ctx.has_bias and need_b and not bias_done:
             bsink = _sink(ctx.bias_ref)
             if bsink is not None:
                 K.bias_grad(dy, acc_into=bsink)
@@ -779,6 +786,7 @@ class ConvC3Fn(torch.autograd.Function):
         y = K.conv3x3_c3_fwd(x_nchw, weight_orig, inv_sigma, bias, pre_scale, pre_shift, relu=relu, round_tf32=round_out)
         ctx.relu = relu
         ctx.has_bias = bias is not None
+        ctx.bias_ref = bias.detach() if bias is not None else None      # alias only: identifies the gradient sink
         ctx.save_for_backward(x_nchw, weight_orig, inv_sigma, pre_scale, y if relu else None)
         return y
 
@@ -786,9 +794,15 @@ class ConvC3Fn(torch.autograd.Function):
     def backward(ctx, dy):
         x, weight_orig, inv_sigma, pre_scale, y = ctx.saved_tensors
         dy = dy.contiguous()
-        if ctx.relu:
-            dy = K.relu_bwd(y, dy)
         need_x, need_w, need_s, need_b = ctx.needs_input_grad[:4]
+        bias_done = False
+        if ctx.relu:
+            bsink = _sink(ctx.bias_ref) if (ctx.has_bias and need_b) else None
+            if bsink is not None and y.shape[-1] % 4 == 0 and y.shape[-1] <= 1024:
+                dy = K.relu_bwd_fused(y, dy, bias_a=bsink, round_tf32=True)     # mask + bias sums + tf32 rounding, one pass
+                bias_done = True
+            else:
+                dy = K.relu_bwd(y, dy)
         dx = dw = ds = db = None
         if need_x:
             dx = K.conv3x3_c3_dgrad_tc(dy, K.c3_transposed_weight(weight_orig), inv_sigma, pre_scale)
@@ -802,7 +816,7 @@ class ConvC3Fn(torch.autograd.Function):
                     dw = g * inv_sigma
             else:
                 dw = g
-        if ctx.has_bias and need_b:
+        if ctx.has_bias and need_b and not bias_done:
             db = K.bias_grad(dy)
         return dx, dw, ds, db, None, None, None, None
 

@@ -36,6 +36,10 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 
 // dz = dy * [activation passes]; mode 0: none, 1: mask tensor value > 0, 2: relu(pre) with pre = raw*scale+shift,
 // 3: relu6(pre): 0 < pre < 6 (torch's hardtanh backward: gradient where min < x < max)
+// mode 4: one byte per float4 written by bn_act (bit k = activation k passed) -> +1 / -1 so that `> 0` selects
+__device__ __forceinline__ float4 mask_byte4(unsigned b) {
+    return make_float4((b & 1u) ? 1.f : -1.f, (b & 2u) ? 1.f : -1.f, (b & 4u) ? 1.f : -1.f, (b & 8u) ? 1.f : -1.f);
+}
 __device__ __forceinline__ float mask_apply(float dy, float pre_or_mask, int mode) {
     if (mode == 0) return dy;
     if (mode == 3) return (pre_or_mask > 0.f && pre_or_mask < 6.f) ? dy : 0.f;
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(256)
 bn_act_kernel(const float4* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
               const float4* __restrict__ res, const float* __restrict__ res_scale, const float* __restrict__ res_shift,
               float4* __restrict__ y, __nv_bfloat16* __restrict__ ys, long long split_stride, long total4, int C4, int act,
-              int round_out) {
+              int round_out, unsigned char* __restrict__ mask_out) {
     for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < static_cast<unsigned>(total4); i += gridDim.x * 256u) {   // 32-bit index math
         const int c = static_cast<int>(i % static_cast<unsigned>(C4)) * 4;
         float4 v = __ldg(x + i);
@@ -148,6 +152,10 @@ bn_act_kernel(const float4* __restrict__ x, const float* __restrict__ scale, con
         v.x = act_apply(v.x, act); v.y = act_apply(v.y, act); v.z = act_apply(v.z, act); v.w = act_apply(v.w, act);
         if (ys) store_split4(ys, split_stride, static_cast<size_t>(i) * 4, v);
         if (y) y[i] = round_out ? round4(v) : v;
+        // 4 bits per float4: where the activation passed (the backward pass reads this byte instead of the 16-byte output)
+        if (mask_out)
+            mask_out[i] = static_cast<unsigned char>((v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) |
+                                                     (v.w > 0.f ? 8u : 0u));
     }
 }
 
@@ -177,6 +185,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ mas
                 const float4 g = ldg4(dy + off), xr = ldg4(x_raw + off);
                 float4 m = xr;
                 if (mask_mode == 1) m = ldg4(mask_src + off);
+                else if (mask_mode == 4) m = mask_byte4(reinterpret_cast<const unsigned char*>(mask_src)[off >> 2]);
                 else if (mask_mode >= 2) m = make_float4(xr.x * sc.x + sh.x, xr.y * sc.y + sh.y, xr.z * sc.z + sh.z, xr.w * sc.w + sh.w);
                 const float d0 = mask_apply(g.x, m.x, mask_mode), d1 = mask_apply(g.y, m.y, mask_mode),
                             d2 = mask_apply(g.z, m.z, mask_mode), d3 = mask_apply(g.w, m.w, mask_mode);
@@ -245,6 +254,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ mask
         const float4 g = ldg4(dy + off), xr = ldg4(x_raw + off);
         float4 m = xr;
         if (mask_mode == 1) m = ldg4(mask_src + off);
+        else if (mask_mode == 4) m = mask_byte4(reinterpret_cast<const unsigned char*>(mask_src)[i]);
         else if (mask_mode >= 2) {
             const float4 sc = ldg4(scale + c), sh = ldg4(shift + c);
             m = make_float4(xr.x * sc.x + sh.x, xr.y * sc.y + sh.y, xr.z * sc.z + sh.z, xr.w * sc.w + sh.w);
@@ -965,7 +975,7 @@ extern "C" int32_t b200lp_col_stats(const float* x, float* part, int64_t M, int3
 
 extern "C" int32_t b200lp_bn_act(const float* x, const float* scale, const float* shift, const float* res,
                                  const float* res_scale, const float* res_shift, float* y, void* y_split, int64_t M,
-                                 int32_t C, int32_t act, int32_t round_tf32, void* stream) {
+                                 int32_t C, int32_t act, int32_t round_tf32, uint8_t* mask_out, void* stream) {
     B200LP_REQUIRE(x && (y || y_split) && M > 0 && C > 0 && C % 4 == 0 && act >= 0 && act <= 2, "bn_act: bad args");
     B200LP_REQUIRE((scale == nullptr) == (shift == nullptr) && (res_scale == nullptr) == (res_shift == nullptr) &&
                        (res || !res_scale), "bn_act: scale / shift go together (res_scale needs res)");
@@ -973,21 +983,22 @@ extern "C" int32_t b200lp_bn_act(const float* x, const float* scale, const float
     bn_act_kernel<<<ew_blocks(total4), 256, 0, as_stream(stream)>>>(
         reinterpret_cast<const float4*>(x), scale, shift, reinterpret_cast<const float4*>(res), res_scale, res_shift,
         reinterpret_cast<float4*>(y), static_cast<__nv_bfloat16*>(y_split), static_cast<long long>(M) * C, total4, C / 4,
-        act, round_tf32);
+        act, round_tf32, mask_out);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;
 }
 
-extern "C" int32_t b200lp_bn_bwd(const float* dy, const float* mask_src, const float* x_raw, const float* mean,
+extern "C" int32_t b200lp_bn_bwd(const float* dy, const void* mask_src_v, const float* x_raw, const float* mean,
                                  const float* rstd, const float* scale, const float* shift, const float* gamma,
                                  float* dgamma, float* dbeta, int32_t accumulate, float* dx, float* dz_out, float* workspace,
                                  int64_t workspace_bytes, int64_t M, int32_t C, int32_t mask_mode, int32_t batch_stats,
                                  int32_t round_tf32, void* stream) {
+    const float* mask_src = static_cast<const float*>(mask_src_v);
     B200LP_REQUIRE(dy && x_raw && mean && rstd && gamma && dx && workspace && M > 0 && C > 0 && C % 4 == 0 &&
-                       mask_mode >= 0 && mask_mode <= 3, "bn_bwd: bad args");
-    B200LP_REQUIRE(mask_mode != 1 || mask_src, "bn_bwd: mask_mode 1 needs mask_src");
-    B200LP_REQUIRE(mask_mode < 2 || (scale && shift), "bn_bwd: mask_mode 2/3 needs scale and shift");
+                       mask_mode >= 0 && mask_mode <= 4, "bn_bwd: bad args");
+    B200LP_REQUIRE((mask_mode != 1 && mask_mode != 4) || mask_src, "bn_bwd: mask_mode 1 / 4 needs mask_src");
+    B200LP_REQUIRE(mask_mode < 2 || mask_mode == 4 || (scale && shift), "bn_bwd: mask_mode 2/3 needs scale and shift");
     int rpc;
     const int chunks = row_chunks(M, &rpc);
     const int64_t need = (static_cast<int64_t>(chunks) * 2 * C + 2 * C) * 4;

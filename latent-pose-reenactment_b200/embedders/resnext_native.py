@@ -163,15 +163,17 @@ def forward(net, x_nchw, need_bwd):
             res, res_sc, res_sh = a_f32, None, None
         # block output relu(bn3(r3) + identity): fp32 copy UNROUNDED (it is the next block's exact identity branch; the
         # TF32 weight-gradient GEMM reads it as is) + the (hi, lo) planes for the next block's forward GEMMs
-        if last:
-            out_f32, out_split = K.bn_act(r3, bn3.scale, bn3.shift, res=res, res_scale=res_sc, res_shift=res_sh, act=1,
-                                          round_tf32=False, want_f32=True, want_split=False), None
-        else:
-            out_f32, out_split = K.bn_act(r3, bn3.scale, bn3.shift, res=res, res_scale=res_sc, res_shift=res_sh, act=1,
-                                          round_tf32=False, want_f32=True, want_split=True)
+        # + (for the backward pass) the block's ReLU mask as 4 bits per float4: both BatchNorm-backward passes of bn3 read
+        # that byte instead of the 16-byte output
+        outs = K.bn_act(r3, bn3.scale, bn3.shift, res=res, res_scale=res_sc, res_shift=res_sh, act=1, round_tf32=False,
+                        want_f32=True, want_split=not last, want_mask=need_bwd)
+        outs = outs if isinstance(outs, tuple) else (outs,)
+        out_f32 = outs[0]
+        out_split = outs[1] if not last else None
+        out_mask = outs[-1] if need_bwd else None
         if need_bwd:
             saved["blocks"].append(dict(blk=blk, a_f32=a_f32, sub_f32=sub_f32, r1=r1, bn1=bn1, r2=r2, bn2=bn2, a2_f32=a2_f32,
-                                        r3=r3, bn3=bn3, rd=rd, bnd=bnd, out=out_f32, hw=(h, w), stride=s))
+                                        r3=r3, bn3=bn3, rd=rd, bnd=bnd, out=out_f32, out_mask=out_mask, hw=(h, w), stride=s))
         a_f32, a_split = out_f32, out_split
         h, w = ho, wo
 
@@ -264,7 +266,7 @@ def backward(net, saved, d_emb, params):
         h, w = rec["hw"]
         # final ReLU + bn3 (dz3 = masked gradient, also the identity branch's gradient)
         d_block_out = d_out if TRACE is not None else None
-        dr3, dz3 = _bn_backward(grads, rec["bn3"], d_out, rec["r3"], 1, mask_src=rec["out"], round_tf32=True, want_dz=True)
+        dr3, dz3 = _bn_backward(grads, rec["bn3"], d_out, rec["r3"], 4, mask_src=rec["out_mask"], round_tf32=True, want_dz=True)
         del d_out
         d_a2 = K.conv_fwd(dr3, _packed(blk.conv3, True, K.TF32), 1)
         _wgrad_1x1(grads, blk.conv3, rec["a2_f32"], dr3)

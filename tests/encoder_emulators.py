@@ -57,20 +57,22 @@ def bn_finalize(bn, part, count, training, want_stats=False):
 
 
 def bn_act(x, scale=None, shift=None, res=None, res_scale=None, res_shift=None, act=1, round_tf32=True, want_f32=True,
-           want_split=False):
+           want_split=False, want_mask=False):
     v = x if scale is None else x * scale + shift
     if res is not None:
         v = v + (res if res_scale is None else res * res_scale + res_shift)
     v = _act(v, act)
-    if want_f32 and want_split:
-        return v, _split(v)
-    return v if want_f32 else _split(v)
+    out = (v, _split(v)) if (want_f32 and want_split) else (v if want_f32 else _split(v))
+    if want_mask:       # the emulated mask keeps one value per element (+1 / -1): mask_mode 4 tests `> 0`
+        mask = torch.where(v > 0, torch.ones_like(v), -torch.ones_like(v))
+        return (out + (mask,)) if isinstance(out, tuple) else (out, mask)
+    return out
 
 
 def _mask(dy, mask_mode, mask_src, x_raw, scale, shift):
     if mask_mode == 0:
         return dy
-    if mask_mode == 1:
+    if mask_mode in (1, 4):
         return dy * (mask_src > 0)
     pre = x_raw * scale + shift
     if mask_mode == 2:

@@ -1089,6 +1089,15 @@ def encoder_bn():
                 out.append(_cmp(f"bn_bwd dz mode{mode} M{m} C{c}", dz, rdz, 1e-6))
                 out.append(_cmp(f"bn_bwd dgamma(acc) mode{mode} M{m} C{c}", dg - dg0, rdg, 3e-5))
                 out.append(_cmp(f"bn_bwd dbeta(acc) mode{mode} M{m} C{c}", db - db0, rdb, 3e-5))
+            # mode 4: the byte mask bn_act writes == mode 1 on the materialised output, bit for bit
+            y4, mask = K.bn_act(x, sc, sh, res=res, act=1, round_tf32=False, want_f32=True, want_mask=True)
+            dx1, _, _, dz1 = K.bn_bwd(dy, x, mean, rstd, bn.weight.detach(), sc, sh, mask_src=y4, mask_mode=1,
+                                      batch_stats=training, want_dz=True)
+            dx4, _, _, dz4 = K.bn_bwd(dy, x, mean, rstd, bn.weight.detach(), sc, sh, mask_src=mask, mask_mode=4,
+                                      batch_stats=training, want_dz=True)
+            same = bool(torch.equal(dx1, dx4) and torch.equal(dz1, dz4))
+            out.append({"case": f"bn_bwd byte mask (mode 4) == output mask (mode 1) M{m} C{c}", "ok": same, "max_abs": 0.0,
+                        "rel": 0.0, "nan": False, "ref_max": 0.0})
     return out
 
 
