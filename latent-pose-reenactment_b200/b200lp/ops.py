@@ -140,6 +140,13 @@ def _sink(t):
     return g
 
 
+def _round_gradients():
+    """Gradients that only feed tf32 MMAs are stored rounded to nearest (the MMA would truncate: a 2^-12 relative bias per
+    layer that compounds along the chain).  B200LP_DISC_NODE_TRUNCATE=1 (A/B tests) keeps the unrounded values."""
+    import os
+    return not os.environ.get("B200LP_DISC_NODE_TRUNCATE")
+
+
 def _packed(weight, cache, transpose, precision=K.TF32):
     if cache is not None:
         return cache.get(weight, transpose, precision)
@@ -244,7 +251,7 @@ class Conv2dFn(torch.autograd.Function):
             bsink = _sink(ctx.bias_ref) if (ctx.has_bias and need_b) else None
             if bsink is not None and y.shape[-1] % 4 == 0 and y.shape[-1] <= 1024:
                 # ReLU mask, bias column sums and tf32 rounding of the gradient operand in one pass
-                dy = K.relu_bwd_fused(y, dy, bias_a=bsink, round_tf32=True)
+                dy = K.relu_bwd_fused(y, dy, bias_a=bsink, round_tf32=_round_gradients())
                 bias_done = True
             else:
                 dy = K.relu_bwd(y, dy)
@@ -659,8 +666,7 @@ class DiscBlocksFn(torch.autograd.Function):
         # gradients that only feed tf32 MMAs are stored rounded to nearest (the MMA would truncate: a 2^-12 relative bias
         # per layer that compounds along the chain); B200LP_DISC_NODE_TRUNCATE=1 (A/B test against the per-layer nodes) keeps
         # the unrounded values
-        import os
-        rnd = not os.environ.get("B200LP_DISC_NODE_TRUNCATE")
+        rnd = _round_gradients()
 
         def bias_into(b, slot, dy):
             """bias gradient by a separate pass (the chain's end, or no sink): column sums of dy."""
@@ -799,7 +805,7 @@ class ConvC3Fn(torch.autograd.Function):
         if ctx.relu:
             bsink = _sink(ctx.bias_ref) if (ctx.has_bias and need_b) else None
             if bsink is not None and y.shape[-1] % 4 == 0 and y.shape[-1] <= 1024:
-                dy = K.relu_bwd_fused(y, dy, bias_a=bsink, round_tf32=True)     # mask + bias sums + tf32 rounding, one pass
+                dy = K.relu_bwd_fused(y, dy, bias_a=bsink, round_tf32=_round_gradients())     # mask + bias sums + tf32 rounding, one pass
                 bias_done = True
             else:
                 dy = K.relu_bwd(y, dy)
