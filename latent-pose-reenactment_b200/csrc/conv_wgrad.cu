@@ -10,8 +10,6 @@
 //   Zero padding = TMA out-of-bounds zero fill on the shifted X box.
 //
 // Replaces torch autograd's conv backward-filter for the convs listed in include/b200lp.h.
-#include <cstdlib>
-
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -39,25 +37,20 @@ struct WgradParams {
     int grouped;          // 1: grouped conv — the M blocks of N tile n are the taps of channel block n (cblks == 1)
 };
 
-// MT = M tiles (accumulators of 128 (tap, ci) rows) per CTA that share every dY tile.  The kernel is bound by the L2 -> SM
-// fabric, not by the MMAs (ncu, 512 -> 512 @32x32, MT = 1: 0.9 GB of operand traffic for 34 MB of unique input, 44 B/clk/SM,
-// tensor pipe 63 %): per K step a CTA fetches (128 MT + BLOCK_N) x kstep x 4 bytes for 128 MT x BLOCK_N x kstep MACs, so
-// two accumulators cut the bytes per FLOP by a third at BLOCK_N = 256 (one CTA per SM then: 512 TMEM columns).
-template <int BLOCK_N, int MT>
+template <int BLOCK_N>
 struct WgCfg {
-    static constexpr int kBlocks = 4 * MT + BLOCK_N / 32;          // [kstep][32 ch] boxes per stage (A: 4 MT, B: N/32)
-    static constexpr uint32_t kTmemCols = MT * BLOCK_N < 32 ? 32 : MT * BLOCK_N;
-    static_assert(MT * BLOCK_N <= 512, "accumulators exceed TMEM");
+    static constexpr int kBlocks = 4 + BLOCK_N / 32;               // [kstep][32 ch] boxes per stage (A: 4, B: N/32)
+    static constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
-template <int BLOCK_N, int MT>
-__global__ void __launch_bounds__(kWgThreads, MT == 1 ? 2 : 1)
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kWgThreads, 2)
 conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                        const WgradParams p) {
-    using Cfg = WgCfg<BLOCK_N, MT>;
+    using Cfg = WgCfg<BLOCK_N>;
     const int kStages = p.stages;
     const int kWgBlkBytes = p.blk_bytes;
-    const int kABytes = 4 * MT * kWgBlkBytes;
+    const int kABytes = 4 * kWgBlkBytes;
     const int kBBytes = (BLOCK_N / 32) * kWgBlkBytes;
     const int kStageBytes = kABytes + kBBytes;
 
@@ -73,10 +66,8 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_tile = blockIdx.x;
-    const int m_tile0 = blockIdx.y * MT;             // first of this CTA's MT consecutive M tiles
+    const int m_tile = blockIdx.y;
     const int split = blockIdx.z;
-    // sub-tiles past the end (odd number of M tiles) are neither loaded nor multiplied
-    const int mt_valid = min(MT, (p.blocks_total + 3) / 4 - m_tile0);
 
     const int ks_begin = split * p.steps_per_split;
     int ks_end = ks_begin + p.steps_per_split;
@@ -105,11 +96,11 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const bool leader = elect_one();
         {
             const int pad = p.ksize >> 1;
-            // the 4 MT 32-row blocks of this CTA's M tiles: (tap shift, channel block); blocks past the end are skipped
-            int blk_dx[4 * MT], blk_dy[4 * MT], blk_c[4 * MT];
+            // the four 32-row blocks of this M tile: (tap shift, channel block); blocks past the end are skipped
+            int blk_dx[4], blk_dy[4], blk_c[4];
             int nvalid = 0;
-            for (int j = 0; j < 4 * MT; ++j) {
-                const int b = m_tile0 * 4 + j;
+            for (int j = 0; j < 4; ++j) {
+                const int b = m_tile * 4 + j;
                 if (b < p.blocks_total) {
                     const int tap = b / p.cblks;
                     blk_c[j] = (b - tap * p.cblks) * 32 + (p.grouped ? n_tile * BLOCK_N : 0);
@@ -162,14 +153,9 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     // MN-major 32-bit operands must use SWIZZLE_128B_BASE32B (layout type 1): atoms of 4 K-rows x 128 B;
                     // LBO = stride between 32-channel blocks, SBO = stride between 4-row K groups (512 B);
                     // one K=8 MMA spans two atoms, so stepping K by 8 = +1024 bytes.
+                    const uint64_t da = make_smem_desc(a_addr + k * 1024, kWgBlkBytes, 512, 1);
                     const uint64_t db = make_smem_desc(b_addr + k * 1024, kWgBlkBytes, 512, 1);
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        if (mt < mt_valid) {
-                            const uint64_t da = make_smem_desc(a_addr + mt * 4 * kWgBlkBytes + k * 1024, kWgBlkBytes, 512, 1);
-                            umma_tf32_ss(tmem_base + mt * BLOCK_N, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                        }
-                    }
+                    umma_tf32_ss(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
                 }
                 if (leader) umma_commit(&empty_bar[stage]);
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -179,25 +165,22 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     } else {
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;
+        const int row = m_tile * kWgM + m;
+        const bool valid = row < p.rows_total;
+        float* orow = p.ws + (static_cast<size_t>(split) * p.rows_total + row) * p.Cout + n_tile * BLOCK_N;
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
 #pragma unroll 1
-        for (int mt = 0; mt < mt_valid; ++mt) {
-            const int row = (m_tile0 + mt) * kWgM + m;
-            const bool valid = row < p.rows_total;
-            float* orow = p.ws + (static_cast<size_t>(split) * p.rows_total + row) * p.Cout + n_tile * BLOCK_N;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + mt * BLOCK_N + c0, v);
-                tmem_ld_wait();
-                if (valid) {
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
+            tmem_ld_wait();
+            if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                        *reinterpret_cast<float4*>(orow + c0 + j) = o;
-                    }
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                           __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    *reinterpret_cast<float4*>(orow + c0 + j) = o;
                 }
             }
         }
@@ -357,7 +340,6 @@ sn_rank1_acc_kernel(float* __restrict__ grad, const float* __restrict__ part, in
 
 struct WgPlan {
     int block_n, m_tiles, n_tiles, splits, steps_per_split, total_steps, pw, ph, pn, kstep, stages;
-    int mt;        // M tiles (accumulators) per CTA; grid.y = ceil(m_tiles / mt)
 };
 
 static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int ksize, WgPlan* pl, int kstep_req = 0,
@@ -386,21 +368,17 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int ksize, WgPlan*
     pl->pn = kstep / (pl->pw * pl->ph);
     const int steps_n = (N + pl->pn - 1) / pl->pn;
     pl->total_steps = (W / pl->pw) * (H / pl->ph) * steps_n;
-    const int blocks_total = ksize * ksize * (grouped ? 1 : Cin / 32);
-    pl->m_tiles = (blocks_total + 3) / 4;
-    // two accumulators per CTA for the 256-wide tiles (fabric-bound: a third fewer operand bytes per FLOP); one CTA per SM
-    // then.  B200LP_WGRAD_MT1=1 (A/B runs) keeps the single-accumulator kernel.
-    static const bool mt1_only = getenv("B200LP_WGRAD_MT1") != nullptr;
-    pl->mt = (!mt1_only && !grouped && pl->block_n == 256 && pl->m_tiles >= 2 && kstep == 32) ? 2 : 1;
-    const int stage_bytes = (4 * pl->mt + pl->block_n / 32) * kstep * 128;
-    int stages = stages_req ? stages_req : (pl->mt == 2 ? 3 : ((pl->block_n == 256 || kstep == 64) ? 2 : 3));   // mt 1: <= ~100 KB per CTA, two CTAs share an SM
+    const int stage_bytes = (4 + pl->block_n / 32) * kstep * 128;
+    int stages = stages_req ? stages_req : ((pl->block_n == 256 || kstep == 64) ? 2 : 3);   // <= ~100 KB per CTA: two CTAs share an SM
     if (stages > kWgMaxStages) stages = kWgMaxStages;
     while (stages > 1 && stages * stage_bytes + 1024 > kWgMaxSmem) --stages;
     pl->stages = stages;
-    const int base = ((pl->m_tiles + pl->mt - 1) / pl->mt) * pl->n_tiles;
-    // split-K so that the grid is at most one full wave of 2 CTAs x 148 SMs (mt 2: one CTA per SM) — one CTA over the wave
-    // costs a whole extra wave —, with at least 4 K steps per CTA
-    int splits = splits_req ? splits_req : ((pl->mt == 2 ? 1 : 2) * 148) / base;
+    const int blocks_total = ksize * ksize * (grouped ? 1 : Cin / 32);
+    pl->m_tiles = (blocks_total + 3) / 4;
+    const int base = pl->m_tiles * pl->n_tiles;
+    // split-K so that the grid is at most one full wave of 2 CTAs x 148 SMs (one CTA over the wave costs a whole
+    // extra wave), with at least 4 K steps per CTA
+    int splits = splits_req ? splits_req : (2 * 148) / base;
     if (!splits_req && splits > pl->total_steps / 4) splits = pl->total_steps / 4;
     // at most 64 splits, except for single-tile grids (the Cin = 3 stems' 27(+5)-column patch GEMM at 256 x 256: 64 CTAs
     // ran 49 us): those may take one CTA per SM
@@ -412,20 +390,20 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int ksize, WgPlan*
     return 0;
 }
 
-template <int BLOCK_N, int MT = 1>
+template <int BLOCK_N>
 static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradParams& p, const WgPlan& pl,
                         cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        B200LP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_tf32_kernel<BLOCK_N, MT>,
+        B200LP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_tf32_kernel<BLOCK_N>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, kWgMaxSmem));
-        B200LP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_tf32_kernel<BLOCK_N, MT>,
+        B200LP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_tf32_kernel<BLOCK_N>,
                                                cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
-    const int smem_bytes = pl.stages * (4 * MT + BLOCK_N / 32) * pl.kstep * 128 + 1024;
-    dim3 grid(pl.n_tiles, (pl.m_tiles + MT - 1) / MT, pl.splits);
-    conv_wgrad_tf32_kernel<BLOCK_N, MT><<<grid, kWgThreads, smem_bytes, stream>>>(tmX, tmDY, p);
+    const int smem_bytes = pl.stages * (4 + BLOCK_N / 32) * pl.kstep * 128 + 1024;
+    dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
+    conv_wgrad_tf32_kernel<BLOCK_N><<<grid, kWgThreads, smem_bytes, stream>>>(tmX, tmDY, p);
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return B200LP_OK;
@@ -498,7 +476,7 @@ static int wgrad_main(const b200lp_wgrad_args* a, void* stream, WgPlan* pl_out, 
     cudaStream_t s = as_stream(stream);
     int r;
     switch (pl.block_n) {
-        case 256: r = pl.mt == 2 ? launch_wgrad<256, 2>(tmX, tmDY, p, pl, s) : launch_wgrad<256>(tmX, tmDY, p, pl, s); break;
+        case 256: r = launch_wgrad<256>(tmX, tmDY, p, pl, s); break;
         case 128: r = launch_wgrad<128>(tmX, tmDY, p, pl, s); break;
         case 64: r = launch_wgrad<64>(tmX, tmDY, p, pl, s); break;
         default: r = launch_wgrad<32>(tmX, tmDY, p, pl, s); break;
