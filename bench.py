@@ -386,14 +386,25 @@ def replay_kernel_times(fn):
     CUPTI through torch.profiler: per-kernel durations of the kernels as they run back to back inside the replay, not
     event pairs around eager launches.  Outside every timed region."""
     from torch.profiler import ProfilerActivity, profile
+    multi = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        if multi:
+            # the profiler starts at a different moment on every rank: a barrier INSIDE the profiled region absorbs that
+            # skew (its own NCCL kernel, dropped below), so the step's collectives do not spend their kernel time
+            # waiting for a late peer
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
         fn()
         torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    if multi:
+        evs.sort(key=lambda e: e.time_range.start)
+        first_nccl = next((k for k, e in enumerate(evs) if "nccl" in e.name.lower()), None)
+        if first_nccl is not None:
+            evs = evs[first_nccl + 1:]
     rows = {}
-    for e in prof.events():
-        if e.device_type != torch.autograd.DeviceType.CUDA:
-            continue
+    for e in evs:
         ms, c = rows.get(e.name, (0.0, 0))
         rows[e.name] = (ms + e.device_time / 1e3, c + 1)
     return rows, sum(ms for ms, _ in rows.values())

@@ -183,7 +183,8 @@ pw_splitk_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ 
         for (int r = rl; r < bm && m0 + r < M; r += 4) {
             const size_t off = static_cast<size_t>(m0 + r) * N + n;
             float v = 0.f;
-            for (int z = 0; z < splits; ++z) v += __ldg(ws + static_cast<size_t>(z) * M * N + off);
+#pragma unroll 8
+            for (int z = 0; z < splits; ++z) v += __ldg(ws + static_cast<size_t>(z) * M * N + off);   // independent loads, fixed order
             y[off] = v + b;
             s1 += v;
             s2 += v * v;
