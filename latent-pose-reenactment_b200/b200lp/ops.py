@@ -853,6 +853,38 @@ def l1_mean(a, b):
     return L1MeanFn.apply(a.contiguous(), b.detach().contiguous())
 
 
+class L1MeanSumFn(torch.autograd.Function):
+    """scale * sum_i mean|a_i - b_i| over a list of tensor pairs as ONE node with ONE accumulator (criterions/featmat.py:18-20
+    sums F.l1_loss over the 7 discriminator feature maps): 7 reduction kernels forward, 7 sign kernels backward, and none of
+    the per-pair zero-fills / scalar adds / multiplies of the per-pair form."""
+
+    @staticmethod
+    def forward(ctx, scale, n, *tensors):
+        a, b = tensors[:n], tensors[n:]
+        out = torch.zeros(1, dtype=torch.float32, device=a[0].device)
+        for x, y in zip(a, b):
+            K.l1_sum(x, y, out, scale / x.numel())
+        ctx.scale, ctx.n = scale, n
+        ctx.save_for_backward(*tensors)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        n = ctx.n
+        a, b = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        gs = g.reshape(1).contiguous().float()
+        grads = [K.l1_bwd(x, y, gs, ctx.scale / x.numel()) if ctx.needs_input_grad[2 + i] else None
+                 for i, (x, y) in enumerate(zip(a, b))]
+        return (None, None, *grads, *([None] * n))
+
+
+def l1_mean_sum(pairs, scale):
+    """scale * sum over pairs of mean|a - b.detach()|."""
+    a = [x.contiguous() for x, _ in pairs]
+    b = [y.detach().contiguous() for _, y in pairs]
+    return L1MeanSumFn.apply(float(scale), len(a), *a, *b)
+
+
 class NchwToNhwcFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):

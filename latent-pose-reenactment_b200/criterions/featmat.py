@@ -30,5 +30,6 @@ class Criterion(nn.Module):
     def forward(self, data_dict):
         fake_feats = data_dict['fake_features']
         real_feats = data_dict['real_features']
-        total = sum(ops.l1_mean(_nhwc_memory(f), _nhwc_memory(r)) for f, r in zip(fake_feats, real_feats))
-        return {'feature_matching': total / len(fake_feats) * self.fm_weight}
+        # mean over the layers of the per-layer mean-L1, times the weight: one node, one accumulator (ops.L1MeanSumFn)
+        pairs = [(_nhwc_memory(f), _nhwc_memory(r)) for f, r in zip(fake_feats, real_feats)]
+        return {'feature_matching': ops.l1_mean_sum(pairs, self.fm_weight / len(pairs))}
