@@ -9,9 +9,11 @@ keys `identity_encoder.*` are torchvision's); this file only sequences kernels o
     GEMM — bf16x3 operands forward (three bf16 MMAs per K step on (hi, lo) planes, ~fp32 accuracy: a single-pass TF32
     forward leaves a 2e-2 relative error in the 512-d embedding after 53 layers of batch-normalised convolutions,
     measured against float64), TF32 for the data and weight gradients;
-  * grouped 3x3 convolutions: forward = FP32 CUDA-core kernels that apply the producer's BatchNorm + ReLU on load and
-    emit the statistics of their own output; data and weight gradients = TF32 tensor cores on block-diagonal 32-channel
-    tiles (`conv_fwd(grouped=cpg)`, `gconv3x3_wgrad_tc`; the three stride-2 layers through the zero-stuffed gradient);
+  * grouped 3x3 convolutions: tensor cores on block-diagonal tiles — bf16x3 forward on 64-channel tiles for the 13
+    stride-1 layers (`conv_fwd(grouped=cpg)`; operand materialised by `bn_act` and shared with the weight gradient), TF32
+    data and weight gradients on 32-channel tiles (`gconv3x3_wgrad_tc`; the three stride-2 layers through the
+    zero-stuffed gradient); the three stride-2 forwards and non-power-of-two planes keep the FP32 CUDA-core kernels that
+    apply the producer's BatchNorm + ReLU on load and emit their output statistics;
   * BatchNorm: statistics partials -> `bn_finalize` (running-statistics updates like nn.BatchNorm2d) -> one
     materialising pass per GEMM operand; backward = reduce / finalize / apply with the ReLU mask recomputed.
 
@@ -139,7 +141,17 @@ def forward(net, x_nchw, need_bwd):
         s = blk.conv2.stride[0]
         ho, wo = h // s, w // s
         r1, bn1 = _bn_1x1(a_split, blk.conv1, blk.bn1, n * h * w)
-        if _stats_needed(blk.bn2):
+        cpg = blk.conv2.weight.shape[1]
+        a1_f32 = None
+        if s == 1 and blk.conv2.weight.shape[0] % 64 == 0 and K.gconv_tensor_cores(n, h, w, blk.conv2.weight.shape[0], cpg):
+            # stride-1 grouped conv on the tensor cores (bf16x3, block-diagonal 64-channel tiles): its operand relu(bn1(r1))
+            # is materialised once — (hi, lo) planes for this GEMM and the tf32 copy the weight gradient reads later
+            a1 = K.bn_act(r1, bn1.scale, bn1.shift, act=1, round_tf32=True, want_f32=need_bwd, want_split=True)
+            a1_f32, a1_split = a1 if need_bwd else (None, a1)
+            r2 = K.conv_fwd(a1_split, _gpacked(blk.conv2, False, K.BF16X3), 3, grouped=cpg)
+            del a1_split
+            part2 = K.col_stats(r2.view(-1, r2.shape[-1])) if _stats_needed(blk.bn2) else None
+        elif _stats_needed(blk.bn2):
             r2, part2 = K.gconv3x3_fwd(r1, blk.conv2.weight.detach(), bn1.scale, bn1.shift, stride=s, want_stats=True)
         else:
             r2, part2 = K.gconv3x3_fwd(r1, blk.conv2.weight.detach(), bn1.scale, bn1.shift, stride=s), None
@@ -172,7 +184,7 @@ def forward(net, x_nchw, need_bwd):
         out_split = outs[1] if not last else None
         out_mask = outs[-1] if need_bwd else None
         if need_bwd:
-            saved["blocks"].append(dict(blk=blk, a_f32=a_f32, sub_f32=sub_f32, r1=r1, bn1=bn1, r2=r2, bn2=bn2, a2_f32=a2_f32,
+            saved["blocks"].append(dict(blk=blk, a_f32=a_f32, sub_f32=sub_f32, r1=r1, bn1=bn1, a1_f32=a1_f32, r2=r2, bn2=bn2, a2_f32=a2_f32,
                                         r3=r3, bn3=bn3, rd=rd, bnd=bnd, out=out_f32, out_mask=out_mask, hw=(h, w), stride=s))
         a_f32, a_split = out_f32, out_split
         h, w = ho, wo
@@ -286,8 +298,10 @@ def backward(net, saved, d_emb, params):
         if w2.requires_grad:
             sk = grads.sink(w2)
             if tc:
-                a1 = K.bn_act(rec["r1"], rec["bn1"].scale, rec["bn1"].shift, act=1, round_tf32=True, want_f32=True,
-                              want_split=False)
+                a1 = rec["a1_f32"]        # kept by a tensor-core forward; else materialised here
+                if a1 is None:
+                    a1 = K.bn_act(rec["r1"], rec["bn1"].scale, rec["bn1"].shift, act=1, round_tf32=True, want_f32=True,
+                                  want_split=False)
                 g2 = K.gconv3x3_wgrad_tc(a1, dr2, cpg, acc_into=sk)
                 del a1
             else:

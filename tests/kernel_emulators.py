@@ -38,11 +38,15 @@ def _unpack(wp, ksize):
 
 
 def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False, round_tf32=False, block_n=0,
-             out=None, emit_split=False, stages=0, scale=None, ctas_per_sm=0, splits=0, variant=0, a_stages=0):
+             out=None, emit_split=False, stages=0, scale=None, ctas_per_sm=0, splits=0, variant=0, a_stages=0, grouped=0):
     if x.dim() == 5:
         x = x[0] + x[1]
-    w = _unpack(wp, ksize).to(x.dtype)
-    y = F.conv2d(x.permute(0, 3, 1, 2), w, padding=ksize // 2)
+    if grouped:         # the emulated grouped packing (encoder_emulators.pack_gconv_weight) is the OIHW weight itself
+        w = wp.to(x.dtype)
+        y = F.conv2d(x.permute(0, 3, 1, 2), w, padding=1, groups=x.shape[-1] // grouped)
+    else:
+        w = _unpack(wp, ksize).to(x.dtype)
+        y = F.conv2d(x.permute(0, 3, 1, 2), w, padding=ksize // 2)
     if scale is not None:
         y = y * scale.to(y.dtype)
     if bias is not None:

@@ -119,8 +119,9 @@ def test_gradients_are_chaotic_in_the_forward_rounding(emulated, monkeypatch):
         return ((f + 0x40) & ~0x7F).view(torch.float32).double()
 
     def rounded_conv(x, wp, ksize, **kw):
-        if x.dim() == 5:            # bf16x3 operands = the forward GEMMs
-            return exact_conv(r16(x[0] + x[1]), r16(wp[0] + wp[1]) if wp.dim() == 4 else r16(wp), ksize, **kw)
+        if x.dim() == 5:            # bf16x3 operands = the forward GEMMs (the emulated grouped packing is the 4-D OIHW weight)
+            split_w = wp.dim() == 4 and not kw.get("grouped")
+            return exact_conv(r16(x[0] + x[1]), r16(wp[0] + wp[1]) if split_w else r16(wp), ksize, **kw)
         return exact_conv(x, wp, ksize, **kw)
 
     net = _net(num_classes=64, seed=2).train()
