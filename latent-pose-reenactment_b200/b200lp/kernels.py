@@ -294,6 +294,51 @@ def adain_relu(x, mean, rstd, gamma, beta, upsample2=False, round_tf32=True, wan
     return y if want_f32 else ys
 
 
+_SYNC_BUFFERS = {}
+
+
+def _sync_buffer(device, n):
+    """Zeroed uint32 counters of the per-sample barriers (the kernels leave them zero); one buffer per (device, stream)."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    buf = _SYNC_BUFFERS.get(key)
+    if buf is None or buf.numel() < 2 * n:
+        buf = torch.zeros(max(2 * n, 256), dtype=torch.int32, device=device)
+        _SYNC_BUFFERS[key] = buf
+    return buf
+
+
+def adain_stats_apply(x, gamma, beta, eps, upsample2=False, round_tf32=True, want_f32=True, want_split=False):
+    """Instance-norm statistics + AdaIN + ReLU (+2x) of one site -> (mean, rstd, outputs as adain_relu returns them).
+    ONE launch (b200lp_adain_relu_fused: partials, per-sample barrier, merge, apply) when the grid can be co-resident,
+    else in_stats + adain_relu.  B200LP_NO_ADAIN_FUSED=1 forces the two-kernel form."""
+    import os
+    lib = L.load()
+    n, h, w, c = x.shape
+    if os.environ.get("B200LP_NO_ADAIN_FUSED"):
+        mean, rstd = in_stats(x, eps)
+        return mean, rstd, adain_relu(x, mean, rstd, gamma, beta, upsample2=upsample2, round_tf32=round_tf32,
+                                      want_f32=want_f32, want_split=want_split)
+    gp, bp, stride = _affine_views(gamma, beta)
+    sc = 2 if upsample2 else 1
+    ws = _ws(lib.b200lp_in_stats_workspace(n, h * w, c), x.device)
+    mean = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    y = torch.empty((n, h * sc, w * sc, c), dtype=torch.float32, device=x.device) if want_f32 else None
+    ys = torch.empty((2, n, h * sc, w * sc, c), dtype=torch.bfloat16, device=x.device) if want_split else None
+    sync = _sync_buffer(x.device, n)
+    out_elems = n * h * sc * w * sc * c
+    with _timed("adain_relu", nbytes=4.0 * (x.numel() + out_elems * (int(want_f32) + int(want_split)))):
+        rc = lib.b200lp_adain_relu_fused(L.ptr(x), gp, bp, stride, L.ptr(y), L.ptr(ys, torch.bfloat16), L.ptr(mean),
+                                         L.ptr(rstd), L.ptr(ws), ws.numel() * 4, L.ptr(sync, torch.int32), n, h, w, c,
+                                         c_float(eps), int(upsample2), int(round_tf32), L.stream_ptr())
+    if rc != 0:      # grid not co-resident on this device: the two-kernel form (nothing was launched)
+        mean, rstd = in_stats(x, eps)
+        return mean, rstd, adain_relu(x, mean, rstd, gamma, beta, upsample2=upsample2, round_tf32=round_tf32,
+                                      want_f32=want_f32, want_split=want_split)
+    out = (y, ys) if (want_f32 and want_split) else (y if want_f32 else ys)
+    return mean, rstd, out
+
+
 def adain_relu_bwd(x, mean, rstd, gamma, beta, dy, upsample2=False, add=None, round_tf32=False):
     """-> (dx, dgamma, dbeta); `add`: a second gradient of x merged into dx, `round_tf32`: dx stored rounded to tf32."""
     lib = L.load()

@@ -83,6 +83,7 @@ SIGNATURES = {
     "b200lp_in_stats_workspace": (_L, [_I, _I, _I]),
     "b200lp_in_stats": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _F, _P]),
     "b200lp_adain_relu": (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "b200lp_adain_relu_fused": (_I, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _F, _I, _I, _P]),
     "b200lp_adain_relu_bwd_workspace": (_L, [_I, _I, _I]),
     "b200lp_adain_relu_bwd": (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P, _I, _P]),
     "b200lp_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P]),

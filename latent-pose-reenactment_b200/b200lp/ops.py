@@ -287,14 +287,15 @@ class AdaINConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, weight_orig, inv_sigma, residual, eps, upsample2, residual_mode, emit_split,
                 cache, sn):
-        mean, rstd = K.in_stats(x, eps)
         need_bwd = any(ctx.needs_input_grad)      # False under torch.no_grad() (drive.py, EMA forward)
+        # statistics + AdaIN + ReLU (+2x) + operand planes: ONE launch (K.adain_stats_apply)
         if need_bwd:
-            a_f32, a_split = K.adain_relu(x, mean, rstd, gamma, beta, upsample2=upsample2, round_tf32=True,
-                                          want_f32=True, want_split=True)
+            mean, rstd, (a_f32, a_split) = K.adain_stats_apply(x, gamma, beta, eps, upsample2=upsample2, round_tf32=True,
+                                                               want_f32=True, want_split=True)
         else:
-            a_f32, a_split = None, K.adain_relu(x, mean, rstd, gamma, beta, upsample2=upsample2, want_f32=False,
-                                                want_split=True)
+            mean, rstd, a_split = K.adain_stats_apply(x, gamma, beta, eps, upsample2=upsample2, want_f32=False,
+                                                      want_split=True)
+            a_f32 = None
         wp = _packed(weight_orig, cache, False, K.BF16X3)
         out = K.conv_fwd(a_split, wp, 3, residual=residual, residual_mode=residual_mode, emit_split=emit_split,
                          scale=inv_sigma)
@@ -342,12 +343,13 @@ class AdaResBlockFn(torch.autograd.Function):
         w0, s0, c0, _ = convs["c0"]
         w1, s1, c1, _ = convs["c1"]
         need_bwd = any(ctx.needs_input_grad)
-        mean0, rstd0 = K.in_stats(x, eps)
+        # each half-block = 2 launches: (statistics + AdaIN + ReLU [+2x] -> operand planes) and the tensor-core conv
         if need_bwd:
-            a0_f32, a0_split = K.adain_relu(x, mean0, rstd0, g0, b0, upsample2=upsample, round_tf32=True, want_f32=True,
-                                            want_split=True)
+            mean0, rstd0, (a0_f32, a0_split) = K.adain_stats_apply(x, g0, b0, eps, upsample2=upsample, round_tf32=True,
+                                                                   want_f32=True, want_split=True)
         else:
-            a0_f32, a0_split = None, K.adain_relu(x, mean0, rstd0, g0, b0, upsample2=upsample, want_f32=False, want_split=True)
+            mean0, rstd0, a0_split = K.adain_stats_apply(x, g0, b0, eps, upsample2=upsample, want_f32=False, want_split=True)
+            a0_f32 = None
         y1 = K.conv_fwd(a0_split, _packed(w0, c0, False, K.BF16X3), 3, scale=s0)
         del a0_split
         if convs["sk"] is not None:
@@ -359,11 +361,12 @@ class AdaResBlockFn(torch.autograd.Function):
             mode = 2 if upsample else 1
         else:
             s, mode = x, 1
-        mean1, rstd1 = K.in_stats(y1, eps)
         if need_bwd:
-            a1_f32, a1_split = K.adain_relu(y1, mean1, rstd1, g1, b1, round_tf32=True, want_f32=True, want_split=True)
+            mean1, rstd1, (a1_f32, a1_split) = K.adain_stats_apply(y1, g1, b1, eps, round_tf32=True, want_f32=True,
+                                                                   want_split=True)
         else:
-            a1_f32, a1_split = None, K.adain_relu(y1, mean1, rstd1, g1, b1, want_f32=False, want_split=True)
+            mean1, rstd1, a1_split = K.adain_stats_apply(y1, g1, b1, eps, want_f32=False, want_split=True)
+            a1_f32 = None
         out = K.conv_fwd(a1_split, _packed(w1, c1, False, K.BF16X3), 3, residual=s, residual_mode=mode,
                          emit_split=emit_split, scale=s1)
         y, y_split = out if emit_split else (out, None)
@@ -472,8 +475,7 @@ class AdaINReLUFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, eps, upsample2, round_out):
-        mean, rstd = K.in_stats(x, eps)
-        y = K.adain_relu(x, mean, rstd, gamma, beta, upsample2=upsample2, round_tf32=round_out)
+        mean, rstd, y = K.adain_stats_apply(x, gamma, beta, eps, upsample2=upsample2, round_tf32=round_out)
         ctx.upsample2 = upsample2
         ctx.save_for_backward(x, mean, rstd, gamma, beta)
         return y
@@ -539,12 +541,13 @@ class AdaINTailFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, weight_orig, inv_sigma, bias, eps):
-        mean, rstd = K.in_stats(x, eps)
         need_bwd = any(ctx.needs_input_grad)
         if need_bwd:
-            a_f32, a_split = K.adain_relu(x, mean, rstd, gamma, beta, round_tf32=True, want_f32=True, want_split=True)
+            mean, rstd, (a_f32, a_split) = K.adain_stats_apply(x, gamma, beta, eps, round_tf32=True, want_f32=True,
+                                                               want_split=True)
         else:
-            a_f32, a_split = None, K.adain_relu(x, mean, rstd, gamma, beta, want_f32=False, want_split=True)
+            mean, rstd, a_split = K.adain_stats_apply(x, gamma, beta, eps, want_f32=False, want_split=True)
+            a_f32 = None
         w32 = torch.zeros((32,) + tuple(weight_orig.shape[1:]), dtype=weight_orig.dtype, device=x.device)
         w32[:4].copy_(weight_orig.detach())
         wp = K.pack_conv_weight(w32, precision=K.BF16X3)

@@ -34,16 +34,14 @@ __device__ __forceinline__ Moments merge(Moments a, Moments b) {
     return r;
 }
 
-// grid (chunks, N); block 256 = (C/4 lanes) x (256/(C/4) pixel rows)   [C/4 <= 256]
-__global__ void in_stats_partial_kernel(const float* __restrict__ x, float* __restrict__ part, int HW, int C,
-                                        int pix_per_chunk) {
-    extern __shared__ float sm[];  // [rows][C][3]
+// block 256 = (C/4 lanes) x (256/(C/4) pixel rows)   [C/4 <= 256]; sm: [rows][C][3] floats
+__device__ __forceinline__ void in_stats_partial_body(const float* __restrict__ x, float* __restrict__ part, int HW, int C,
+                                                      int pix_per_chunk, int n, int chunk, int nchunks, float* sm) {
     const int cq = C >> 2;
     const int lane_c = threadIdx.x % cq;
     const int row = threadIdx.x / cq;
     const int rows = blockDim.x / cq;
-    const int n = blockIdx.y;
-    const int p0 = blockIdx.x * pix_per_chunk;
+    const int p0 = chunk * pix_per_chunk;
     int p1 = p0 + pix_per_chunk;
     if (p1 > HW) p1 = HW;
     const float* base = x + (static_cast<size_t>(n) * HW) * C + lane_c * 4;
@@ -99,9 +97,51 @@ __global__ void in_stats_partial_kernel(const float* __restrict__ x, float* __re
             const float* d = sm + (static_cast<size_t>(r) * C + c) * 3;
             acc = merge(acc, Moments{d[0], d[1], d[2]});
         }
-        float* o = part + ((static_cast<size_t>(n) * gridDim.x + blockIdx.x) * C + c) * 3;
+        float* o = part + ((static_cast<size_t>(n) * nchunks + chunk) * C + c) * 3;
         o[0] = acc.cnt; o[1] = acc.mean; o[2] = acc.m2;
     }
+}
+
+// grid (chunks, N)
+__global__ void in_stats_partial_kernel(const float* __restrict__ x, float* __restrict__ part, int HW, int C,
+                                        int pix_per_chunk) {
+    extern __shared__ float sm[];
+    in_stats_partial_body(x, part, HW, C, pix_per_chunk, blockIdx.y, blockIdx.x, gridDim.x, sm);
+}
+
+// mean / rstd of one (n, c) plane from its chunk partials: lanes stride over the chunks, then a shuffle tree of Chan
+// merges (fp64).  Whole warp; every lane returns the same values.  `part_n` = partials of sample n, [chunks][C][3].
+__device__ __forceinline__ void in_stats_merge_warp(const float* part_n, int chunks, int C, int c, float eps, float* mean_out,
+                                                    float* rstd_out) {
+    const int lane = threadIdx.x & 31;
+    double cnt = 0.0, mu = 0.0, m2 = 0.0;
+    for (int k = lane; k < chunks; k += 32) {
+        const float* d = part_n + (static_cast<size_t>(k) * C + c) * 3;
+        const double bc = __ldcg(d), bm = __ldcg(d + 1), b2 = __ldcg(d + 2);
+        if (bc == 0.0) continue;
+        const double tot = cnt + bc;
+        const double dl = bm - mu;
+        mu += dl * (bc / tot);
+        m2 += b2 + dl * dl * cnt * (bc / tot);
+        cnt = tot;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oc = __shfl_xor_sync(0xffffffffu, cnt, o);
+        const double om = __shfl_xor_sync(0xffffffffu, mu, o);
+        const double o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+        const double tot = cnt + oc;
+        if (tot > 0.0) {
+            const double dl = om - mu;
+            const double nm = (cnt * mu + oc * om) / tot;
+            m2 = m2 + o2 + dl * dl * (cnt * oc / tot);
+            mu = nm;
+            cnt = tot;
+        }
+    }
+    const double var = cnt > 0.0 ? m2 / cnt : 0.0;   // biased variance, as nn.InstanceNorm2d
+    *mean_out = static_cast<float>(mu);
+    *rstd_out = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
 }
 
 // one warp per (n, c): lanes stride over the chunk partials, then a shuffle tree of Chan merges (fp64)
@@ -181,25 +221,25 @@ __device__ __forceinline__ void store_f32_and_split(float* y, __nv_bfloat16* ys,
     }
 }
 
+// mean_n / rstd_n: this sample's [C] statistics — global or shared memory (plain loads)
 template <bool UP, bool ROUND>
-__global__ void adain_relu_kernel(const float* __restrict__ x, const float* __restrict__ mean,
-                                  const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                  const float* __restrict__ beta, long affine_stride, float* __restrict__ y,
-                                  __nv_bfloat16* __restrict__ ys, long long split_stride, int H, int W, int C,
-                                  int pix_per_chunk) {
+__device__ __forceinline__ void adain_apply_body(const float* __restrict__ x, const float* mean_n, const float* rstd_n,
+                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                 long affine_stride, float* __restrict__ y, __nv_bfloat16* __restrict__ ys,
+                                                 long long split_stride, int H, int W, int C, int pix_per_chunk, int n,
+                                                 int chunk) {
     const int cq = C >> 2;
     const int lane_c = threadIdx.x % cq;
     const int row = threadIdx.x / cq;
     const int rows = blockDim.x / cq;
     if (row >= rows) return;
-    const int n = blockIdx.y;
     const int HW = H * W;
-    const int p0 = blockIdx.x * pix_per_chunk;
+    const int p0 = chunk * pix_per_chunk;
     int p1 = p0 + pix_per_chunk;
     if (p1 > HW) p1 = HW;
     const int c = lane_c * 4;
-    const float4 mu = ld4(mean + static_cast<size_t>(n) * C + c);
-    const float4 rs = ld4(rstd + static_cast<size_t>(n) * C + c);
+    const float4 mu = *reinterpret_cast<const float4*>(mean_n + c);
+    const float4 rs = *reinterpret_cast<const float4*>(rstd_n + c);
     float4 g, b;
     {
         const float* gp = gamma + n * affine_stride + c;
@@ -235,6 +275,63 @@ __global__ void adain_relu_kernel(const float* __restrict__ x, const float* __re
             }
         }
     }
+}
+
+template <bool UP, bool ROUND>
+__global__ void adain_relu_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                  const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, long affine_stride, float* __restrict__ y,
+                                  __nv_bfloat16* __restrict__ ys, long long split_stride, int H, int W, int C,
+                                  int pix_per_chunk) {
+    adain_apply_body<UP, ROUND>(x, mean + static_cast<size_t>(blockIdx.y) * C, rstd + static_cast<size_t>(blockIdx.y) * C, gamma,
+                                beta, affine_stride, y, ys, split_stride, H, W, C, pix_per_chunk, blockIdx.y, blockIdx.x);
+}
+
+// Barrier among the `expected` CTAs that work on one sample (all co-resident: the host sizes the grid by the occupancy
+// query).  ctr[0] counts arrivals, ctr[1] departures; the last CTA to leave resets both, so the pair is reusable by the next
+// launch on the stream without a memset.
+__device__ __forceinline__ void sample_barrier(unsigned* ctr, unsigned expected) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(ctr, 1u);
+        while (*reinterpret_cast<volatile unsigned*>(ctr) < expected) __nanosleep(40);
+        __threadfence();
+        if (atomicAdd(ctr + 1, 1u) == expected - 1) {      // everyone has seen the full count: safe to reset
+            ctr[1] = 0u;
+            __threadfence();
+            ctr[0] = 0u;
+        }
+    }
+    __syncthreads();
+}
+
+// The AdaIN site as ONE launch: statistics partials -> per-sample barrier -> every CTA merges its sample's partials into
+// shared memory (chunk 0 also publishes mean / rstd for the backward pass) -> apply, re-reading the pixels this very CTA
+// just streamed (L2-resident unless the tensor exceeds the L2).  grid (chunks, N), all CTAs co-resident.
+template <bool UP, bool ROUND>
+__global__ void __launch_bounds__(kEwThreads)
+adain_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   long affine_stride, float* __restrict__ y, __nv_bfloat16* __restrict__ ys, long long split_stride,
+                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ part, unsigned* __restrict__ ctr,
+                   int H, int W, int C, int pix_per_chunk, float eps) {
+    extern __shared__ float sm[];          // phase 1: [rows][C][3]; phase 2: mean [C], rstd [C]
+    const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    in_stats_partial_body(x, part, H * W, C, pix_per_chunk, n, chunk, nchunks, sm);
+    sample_barrier(ctr + 2 * n, nchunks);
+    const float* part_n = part + static_cast<size_t>(n) * nchunks * C * 3;
+    const int warp = threadIdx.x >> 5;
+    for (int c = warp; c < C; c += kEwThreads / 32) {
+        float m, r;
+        in_stats_merge_warp(part_n, nchunks, C, c, eps, &m, &r);
+        if ((threadIdx.x & 31) == 0) {
+            sm[c] = m;
+            sm[C + c] = r;
+            if (chunk == 0) { mean[static_cast<size_t>(n) * C + c] = m; rstd[static_cast<size_t>(n) * C + c] = r; }
+        }
+    }
+    __syncthreads();
+    adain_apply_body<UP, ROUND>(x, sm, sm + C, gamma, beta, affine_stride, y, ys, split_stride, H, W, C, pix_per_chunk, n, chunk);
 }
 
 // Backward pass 1: per-(n,c) partial sums of dz and dz*xhat, dz = dy_in * [z > 0], where dy_in is dy summed over
@@ -859,6 +956,60 @@ extern "C" int32_t b200lp_adain_relu(const float* x, const float* mean, const fl
                                                           split_stride, H, W, C, ppc)
     if (upsample2) { if (round_tf32) LAUNCH(true, true); else LAUNCH(true, false); }
     else { if (round_tf32) LAUNCH(false, true); else LAUNCH(false, false); }
+#undef LAUNCH
+    B200LP_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return B200LP_OK;
+}
+
+// chunk count of a fused (barrier) launch: the plan of the separate kernels, capped so that every CTA of the grid is
+// resident at once (occupancy query of the very kernel that will run)
+template <typename Kern>
+static int fused_chunks(Kern kern, size_t smem, int N, int HW, int C, int* pix_per_chunk) {
+    int chunks, ppc;
+    stats_plan(N, HW, C, &chunks, &ppc);
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            return -1;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kEwThreads, smem) != cudaSuccess || occ < 1) return -1;
+    const int cap = (occ * num_sms) / N;
+    if (cap < 1) return -1;
+    if (chunks > cap) {
+        ppc = (HW + cap - 1) / cap;
+        chunks = (HW + ppc - 1) / ppc;
+    }
+    *pix_per_chunk = ppc;
+    return chunks;
+}
+
+extern "C" int32_t b200lp_adain_relu_fused(const float* x, const float* gamma, const float* beta, int64_t affine_stride,
+                                           float* y, void* y_split, float* mean, float* rstd, float* workspace,
+                                           int64_t workspace_bytes, uint32_t* sync, int32_t N, int32_t H, int32_t W,
+                                           int32_t C, float eps, int32_t upsample2, int32_t round_tf32, void* stream) {
+    B200LP_REQUIRE(x && gamma && beta && (y || y_split) && mean && rstd && workspace && sync, "adain_relu_fused: null pointer");
+    B200LP_REQUIRE(N > 0 && H > 0 && W > 0 && C % 4 == 0 && C / 4 <= kEwThreads, "adain_relu_fused: bad shape");
+    const int rows = kEwThreads / (C / 4);
+    size_t smem = static_cast<size_t>(rows) * C * 3 * 4;
+    if (smem < static_cast<size_t>(2) * C * 4) smem = static_cast<size_t>(2) * C * 4;
+    cudaStream_t s = as_stream(stream);
+    __nv_bfloat16* ys = static_cast<__nv_bfloat16*>(y_split);
+    const long long split_stride = static_cast<long long>(N) * H * W * C * (upsample2 ? 4 : 1);
+    int ppc = 0, chunks = 0;
+#define LAUNCH(UP, RD)                                                                                                  \
+    {                                                                                                                   \
+        chunks = fused_chunks(adain_fused_kernel<UP, RD>, smem, N, H * W, C, &ppc);                                     \
+        B200LP_REQUIRE(chunks >= 1, "adain_relu_fused: the grid cannot be made co-resident (N=%d)", N);                 \
+        B200LP_REQUIRE(workspace_bytes >= static_cast<int64_t>(N) * chunks * C * 12, "adain_relu_fused: workspace too small"); \
+        adain_fused_kernel<UP, RD><<<dim3(chunks, N), kEwThreads, smem, s>>>(x, gamma, beta, affine_stride, y, ys,      \
+                                                                             split_stride, mean, rstd, workspace, sync, \
+                                                                             H, W, C, ppc, eps);                        \
+    }
+    if (upsample2) { if (round_tf32) LAUNCH(true, true) else LAUNCH(true, false) }
+    else { if (round_tf32) LAUNCH(false, true) else LAUNCH(false, false) }
 #undef LAUNCH
     B200LP_CHECK_CUDA(cudaGetLastError());
     count_launch();

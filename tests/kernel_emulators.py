@@ -140,6 +140,12 @@ def adain_relu(x, mean, rstd, gamma, beta, upsample2=False, round_tf32=True, wan
     return y if want_f32 else ys
 
 
+def adain_stats_apply(x, gamma, beta, eps, upsample2=False, round_tf32=True, want_f32=True, want_split=False):
+    mean, rstd = in_stats(x, eps)
+    return mean, rstd, adain_relu(x, mean, rstd, gamma, beta, upsample2=upsample2, round_tf32=round_tf32, want_f32=want_f32,
+                                  want_split=want_split)
+
+
 def adain_relu_bwd(x, mean, rstd, gamma, beta, dy, upsample2=False, add=None, round_tf32=False):
     """Autograd through the emulated forward INCLUDING the statistics' dependence on x."""
     with torch.enable_grad():
@@ -419,7 +425,7 @@ EMULATED = [
     "sgemm", "dice_fwd", "dice_bwd", "adversarial_fwd", "adversarial_bwd", "crop_bilinear_fwd", "crop_bilinear_bwd",
     "disc_head_fwd", "disc_head_bwd",
     "pack_conv_weight", "conv_fwd", "conv_wgrad", "conv_wgrad_sn_acc", "bias_grad", "sn_scratch", "sn_sigma_multi",
-    "sn_wgrad_fix", "in_stats", "adain_relu", "adain_relu_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "relu_round", "relu_bwd", "relu_bwd_fused",
+    "sn_wgrad_fix", "in_stats", "adain_relu", "adain_stats_apply", "adain_relu_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "relu_round", "relu_bwd", "relu_bwd_fused",
     "avgpool2", "avgpool2_bwd", "upsample2_bwd", "l1_sum", "l1_sum_code", "l1_code_bwd", "l1_sum_code_pool", "l1_code_bwd_unpool", "l1_bwd", "l1_relu_bwd", "conv3x3_c3_fwd", "im2col3x3_c3",
     "col2im3x3_c3", "gen_tail_fwd", "gen_tail_compose", "gen_tail_bwd_act", "gen_tail_bwd", "copy_plan", "copy_multi",
 ]

@@ -1294,6 +1294,50 @@ def c3_tensor_core():
 
 
 @check
+def adain_fused():
+    """b200lp_adain_relu_fused (statistics + per-sample barrier + apply in ONE launch) == b200lp_in_stats + b200lp_adain_relu:
+    every output form, upsampling, odd batch sizes, planes from 4x4 to 256x256, repeated launches on one stream (the barrier
+    counters must come back to zero); timing of both forms at the generator's largest sites."""
+    import os
+    import torch
+    from b200lp import kernels as K
+    out = []
+    torch.manual_seed(23)
+    dev = "cuda"
+    for rep_ in range(2):
+        for (n, h, w, c, up) in [(8, 256, 256, 64, False), (8, 128, 128, 128, True), (8, 4, 4, 512, False), (3, 16, 16, 512, True),
+                                 (1, 32, 32, 256, False), (8, 64, 64, 256, True), (5, 8, 8, 64, False)]:
+            x = torch.randn(n, h, w, c, device=dev) * 2 + 0.5
+            aff = torch.randn(n, 2 * c, device=dev)
+            g, b = aff[:, c:], aff[:, :c]
+            mean, rstd = K.in_stats(x, 1e-4)
+            yf, ys = K.adain_relu(x, mean, rstd, g, b, upsample2=up, round_tf32=True, want_f32=True, want_split=True)
+            m2, r2, (yf2, ys2) = K.adain_stats_apply(x, g, b, 1e-4, upsample2=up, round_tf32=True, want_f32=True, want_split=True)
+            tag = f"N{n} {h}x{w} C{c} up{int(up)} rep{rep_}"
+            out.append(_cmp(f"adain_fused mean {tag}", m2, mean, 1e-6))
+            out.append(_cmp(f"adain_fused rstd {tag}", r2, rstd, 1e-6))
+            out.append(_cmp(f"adain_fused y {tag}", yf2, yf, 2e-6))
+            out.append(_cmp(f"adain_fused y_split {tag}", ys2[0].float() + ys2[1].float(), ys[0].float() + ys[1].float(), 2e-6))
+    sync = list(K._SYNC_BUFFERS.values())[0]
+    out.append({"case": "adain_fused barrier counters back to zero", "ok": int(sync.abs().sum()) == 0, "max_abs": 0.0, "rel": 0.0,
+                "nan": False, "ref_max": 0.0})
+    for (n, h, c, up) in [(8, 256, 64, False), (8, 128, 128, True), (8, 64, 256, False)]:
+        x = torch.randn(n, h, h, c, device=dev)
+        aff = torch.randn(n, 2 * c, device=dev)
+        g, b = aff[:, c:], aff[:, :c]
+        rec = {"case": f"timing adain site N{n} {h}x{h} C{c} up{int(up)} (us)", "ok": True, "max_abs": 0.0, "rel": 0.0, "nan": False,
+               "ref_max": 0.0}
+        rec["fused_us"] = round(_time_us(lambda: K.adain_stats_apply(x, g, b, 1e-4, upsample2=up, want_f32=False, want_split=True)), 1)
+
+        def two():
+            mean, rstd = K.in_stats(x, 1e-4)
+            K.adain_relu(x, mean, rstd, g, b, upsample2=up, want_f32=False, want_split=True)
+        rec["two_kernel_us"] = round(_time_us(two), 1)
+        out.append(rec)
+    return out
+
+
+@check
 def gconv_tc():
     """Grouped 3x3 convolution on the tensor cores (block-diagonal 32 / 64-channel tiles): conv_fwd(grouped) forward in
     tf32 and bf16x3, data gradient through the transposed packing (stride 2 via the zero-stuffed gradient), weight gradient
