@@ -224,7 +224,7 @@ int32_t b200lp_adain_relu(const float* x, const float* mean, const float* rstd, 
 /* The AdaIN site as ONE launch (b200lp_in_stats + b200lp_adain_relu): statistics partials, a barrier among the CTAs of a
  * sample, merge, apply — the apply pass re-reads the pixels the same CTA streamed for the statistics (L2-resident unless
  * the tensor exceeds the L2).  mean / rstd [N][C] are outputs (the backward pass needs them).  workspace:
- * b200lp_in_stats_workspace bytes.  sync: 2*N uint32 counters, zero before the FIRST use (the kernel leaves them zero); one
+ * b200lp_in_stats_workspace bytes.  sync: 4*N uint32 counters, zero before the FIRST use (the kernel leaves them zero); one
  * buffer per stream.  Fails (no launch) if the grid cannot be made co-resident — call the two-kernel form then. */
 int32_t b200lp_adain_relu_fused(const float* x, const float* gamma, const float* beta, int64_t affine_stride, float* y,
                                 void* y_split, float* mean, float* rstd, float* workspace, int64_t workspace_bytes,

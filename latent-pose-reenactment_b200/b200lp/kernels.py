@@ -301,8 +301,8 @@ def _sync_buffer(device, n):
     """Zeroed uint32 counters of the per-sample barriers (the kernels leave them zero); one buffer per (device, stream)."""
     key = (str(device), torch.cuda.current_stream(device).cuda_stream)
     buf = _SYNC_BUFFERS.get(key)
-    if buf is None or buf.numel() < 2 * n:
-        buf = torch.zeros(max(2 * n, 256), dtype=torch.int32, device=device)
+    if buf is None or buf.numel() < 4 * n:
+        buf = torch.zeros(max(4 * n, 512), dtype=torch.int32, device=device)
         _SYNC_BUFFERS[key] = buf
     return buf
 

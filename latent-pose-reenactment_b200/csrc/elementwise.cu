@@ -306,32 +306,30 @@ __device__ __forceinline__ void sample_barrier(unsigned* ctr, unsigned expected)
     __syncthreads();
 }
 
-// The AdaIN site as ONE launch: statistics partials -> per-sample barrier -> every CTA merges its sample's partials into
-// shared memory (chunk 0 also publishes mean / rstd for the backward pass) -> apply, re-reading the pixels this very CTA
-// just streamed (L2-resident unless the tensor exceeds the L2).  grid (chunks, N), all CTAs co-resident.
+// The AdaIN site as ONE launch: statistics partials -> per-sample barrier -> CTA `chunk` merges the channels chunk,
+// chunk + nchunks, ... of its sample (one warp per channel; every CTA merging ALL channels in fp64 cost 3x the whole
+// two-kernel form) and publishes mean / rstd -> second barrier -> apply, re-reading the pixels this very CTA just streamed
+// (L2-resident unless the tensor exceeds the L2).  grid (chunks, N), all CTAs co-resident.
 template <bool UP, bool ROUND>
 __global__ void __launch_bounds__(kEwThreads)
 adain_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                    long affine_stride, float* __restrict__ y, __nv_bfloat16* __restrict__ ys, long long split_stride,
                    float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ part, unsigned* __restrict__ ctr,
                    int H, int W, int C, int pix_per_chunk, float eps) {
-    extern __shared__ float sm[];          // phase 1: [rows][C][3]; phase 2: mean [C], rstd [C]
+    extern __shared__ float sm[];          // [rows][C][3]
     const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
     in_stats_partial_body(x, part, H * W, C, pix_per_chunk, n, chunk, nchunks, sm);
-    sample_barrier(ctr + 2 * n, nchunks);
+    sample_barrier(ctr + 4 * n, nchunks);
     const float* part_n = part + static_cast<size_t>(n) * nchunks * C * 3;
     const int warp = threadIdx.x >> 5;
-    for (int c = warp; c < C; c += kEwThreads / 32) {
+    for (int c = chunk + nchunks * warp; c < C; c += nchunks * (kEwThreads / 32)) {
         float m, r;
         in_stats_merge_warp(part_n, nchunks, C, c, eps, &m, &r);
-        if ((threadIdx.x & 31) == 0) {
-            sm[c] = m;
-            sm[C + c] = r;
-            if (chunk == 0) { mean[static_cast<size_t>(n) * C + c] = m; rstd[static_cast<size_t>(n) * C + c] = r; }
-        }
+        if ((threadIdx.x & 31) == 0) { mean[static_cast<size_t>(n) * C + c] = m; rstd[static_cast<size_t>(n) * C + c] = r; }
     }
-    __syncthreads();
-    adain_apply_body<UP, ROUND>(x, sm, sm + C, gamma, beta, affine_stride, y, ys, split_stride, H, W, C, pix_per_chunk, n, chunk);
+    sample_barrier(ctr + 4 * n + 2, nchunks);
+    adain_apply_body<UP, ROUND>(x, mean + static_cast<size_t>(n) * C, rstd + static_cast<size_t>(n) * C, gamma, beta,
+                                affine_stride, y, ys, split_stride, H, W, C, pix_per_chunk, n, chunk);
 }
 
 // Backward pass 1: per-(n,c) partial sums of dz and dz*xhat, dz = dy_in * [z > 0], where dy_in is dy summed over
@@ -993,8 +991,7 @@ extern "C" int32_t b200lp_adain_relu_fused(const float* x, const float* gamma, c
     B200LP_REQUIRE(x && gamma && beta && (y || y_split) && mean && rstd && workspace && sync, "adain_relu_fused: null pointer");
     B200LP_REQUIRE(N > 0 && H > 0 && W > 0 && C % 4 == 0 && C / 4 <= kEwThreads, "adain_relu_fused: bad shape");
     const int rows = kEwThreads / (C / 4);
-    size_t smem = static_cast<size_t>(rows) * C * 3 * 4;
-    if (smem < static_cast<size_t>(2) * C * 4) smem = static_cast<size_t>(2) * C * 4;
+    const size_t smem = static_cast<size_t>(rows) * C * 3 * 4;
     cudaStream_t s = as_stream(stream);
     __nv_bfloat16* ys = static_cast<__nv_bfloat16*>(y_split);
     const long long split_stride = static_cast<long long>(N) * H * W * C * (upsample2 ? 4 : 1);
