@@ -307,14 +307,18 @@ def _sync_buffer(device, n):
     return buf
 
 
-def adain_stats_apply(x, gamma, beta, eps, upsample2=False, round_tf32=True, want_f32=True, want_split=False):
+def adain_stats_apply(x, gamma, beta, eps, upsample2=False, round_tf32=True, want_f32=True, want_split=False, fused=None):
     """Instance-norm statistics + AdaIN + ReLU (+2x) of one site -> (mean, rstd, outputs as adain_relu returns them).
-    ONE launch (b200lp_adain_relu_fused: partials, per-sample barrier, merge, apply) when the grid can be co-resident,
-    else in_stats + adain_relu.  B200LP_NO_ADAIN_FUSED=1 forces the two-kernel form."""
+    Default: in_stats (2 launches) + adain_relu.  `fused=True` / B200LP_ADAIN_FUSED=1: ONE launch
+    (b200lp_adain_relu_fused: partials, per-sample barrier, channel-sliced merge, barrier, apply).  The single launch was
+    measured SLOWER inside the step (17 sites: 1.03 ms vs 0.65 ms) — two grid-wide waits per site cost
+    more than the launch gaps they replace — so it is kept as a tested, opt-in form only."""
     import os
     lib = L.load()
     n, h, w, c = x.shape
-    if os.environ.get("B200LP_NO_ADAIN_FUSED"):
+    if fused is None:
+        fused = bool(os.environ.get("B200LP_ADAIN_FUSED"))
+    if not fused:
         mean, rstd = in_stats(x, eps)
         return mean, rstd, adain_relu(x, mean, rstd, gamma, beta, upsample2=upsample2, round_tf32=round_tf32,
                                       want_f32=want_f32, want_split=want_split)

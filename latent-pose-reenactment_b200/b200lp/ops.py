@@ -288,7 +288,7 @@ class AdaINConvFn(torch.autograd.Function):
     def forward(ctx, x, gamma, beta, weight_orig, inv_sigma, residual, eps, upsample2, residual_mode, emit_split,
                 cache, sn):
         need_bwd = any(ctx.needs_input_grad)      # False under torch.no_grad() (drive.py, EMA forward)
-        # statistics + AdaIN + ReLU (+2x) + operand planes: ONE launch (K.adain_stats_apply)
+        # statistics, then AdaIN + ReLU (+2x) writing the operand planes (K.adain_stats_apply)
         if need_bwd:
             mean, rstd, (a_f32, a_split) = K.adain_stats_apply(x, gamma, beta, eps, upsample2=upsample2, round_tf32=True,
                                                                want_f32=True, want_split=True)
@@ -343,7 +343,7 @@ class AdaResBlockFn(torch.autograd.Function):
         w0, s0, c0, _ = convs["c0"]
         w1, s1, c1, _ = convs["c1"]
         need_bwd = any(ctx.needs_input_grad)
-        # each half-block = 2 launches: (statistics + AdaIN + ReLU [+2x] -> operand planes) and the tensor-core conv
+        # each half-block: statistics (2 launches), AdaIN + ReLU [+2x] -> operand planes, the tensor-core conv
         if need_bwd:
             mean0, rstd0, (a0_f32, a0_split) = K.adain_stats_apply(x, g0, b0, eps, upsample2=upsample, round_tf32=True,
                                                                    want_f32=True, want_split=True)

@@ -1312,7 +1312,8 @@ def adain_fused():
             g, b = aff[:, c:], aff[:, :c]
             mean, rstd = K.in_stats(x, 1e-4)
             yf, ys = K.adain_relu(x, mean, rstd, g, b, upsample2=up, round_tf32=True, want_f32=True, want_split=True)
-            m2, r2, (yf2, ys2) = K.adain_stats_apply(x, g, b, 1e-4, upsample2=up, round_tf32=True, want_f32=True, want_split=True)
+            m2, r2, (yf2, ys2) = K.adain_stats_apply(x, g, b, 1e-4, upsample2=up, round_tf32=True, want_f32=True, want_split=True,
+                                                     fused=True)
             tag = f"N{n} {h}x{w} C{c} up{int(up)} rep{rep_}"
             out.append(_cmp(f"adain_fused mean {tag}", m2, mean, 1e-6))
             out.append(_cmp(f"adain_fused rstd {tag}", r2, rstd, 1e-6))
@@ -1327,7 +1328,8 @@ def adain_fused():
         g, b = aff[:, c:], aff[:, :c]
         rec = {"case": f"timing adain site N{n} {h}x{h} C{c} up{int(up)} (us)", "ok": True, "max_abs": 0.0, "rel": 0.0, "nan": False,
                "ref_max": 0.0}
-        rec["fused_us"] = round(_time_us(lambda: K.adain_stats_apply(x, g, b, 1e-4, upsample2=up, want_f32=False, want_split=True)), 1)
+        rec["fused_us"] = round(_time_us(lambda: K.adain_stats_apply(x, g, b, 1e-4, upsample2=up, want_f32=False, want_split=True,
+                                                                     fused=True)), 1)
 
         def two():
             mean, rstd = K.in_stats(x, 1e-4)
