@@ -367,7 +367,7 @@ def kernel_family(name):
         return "conv_igemm_bf16x3" if mode.startswith("1") else "conv_igemm_tf32"
     base = base.split("<", 1)[0]
     table = (("splitk_epilogue", "conv_splitk_epilogue"), ("conv_wgrad_tf32", "conv_wgrad_tf32"), ("wgrad_", "wgrad_reduce"),
-             ("sn_rank1", "wgrad_reduce"), ("sn_", "spectral_norm"), ("in_stats", "in_stats"), ("adain_bwd", "adain_relu_bwd"),
+             ("sn_rank1", "wgrad_reduce"), ("sn_", "spectral_norm"), ("in_stats", "in_stats"), ("adain_bwd", "adain_relu_bwd"), ("adain_fused", "adain_relu"),
              ("adain_relu", "adain_relu"), ("l1_", "l1"), ("pack_conv_weight", "pack_conv_weight"),
              ("adam_ema", "optimizer"), ("ema_multi", "optimizer"), ("opt_tick", "optimizer"),
              ("gen_tail", "gen_tail"), ("conv3x3_c3", "c3_stem"), ("im2col3x3", "c3_stem"), ("col2im3x3", "c3_stem"),
