@@ -47,6 +47,12 @@ WORKLOADS = {
     "metatrain": dict(desc="configs[2] default: bs=8/GPU 256x256, K=8 identity frames, all six criteria, Adam, EMA 0.999",
                       finetune=False, criteria="idt_embed, perceptual, adversarial, featmat, dis_embed, dice",
                       optimizer="Adam", lr_gen=5e-5, lr_dis=2e-4, k_frames=8, num_labels=16),
+    # BASELINE.json configs[4]: a stress configuration, not the headline — only run when asked for by name
+    # (`--workload metatrain512`; per-GPU batch 4 unless --batch is given).  `value` is then 512x512 frames/s.
+    "metatrain512": dict(desc="configs[4]: bs=4/GPU 512x512 (8 up-blocks, 19 AdaIN sites), K=8 identity frames, all six "
+                              "criteria, Adam, EMA 0.999",
+                         finetune=False, criteria="idt_embed, perceptual, adversarial, featmat, dis_embed, dice",
+                         optimizer="Adam", lr_gen=5e-5, lr_dis=2e-4, k_frames=8, num_labels=16, image_size=512, batch=4),
 }
 
 
@@ -58,7 +64,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS) + ["drive"],
                     help="default: finetune (BASELINE configs[1]) on one GPU, metatrain (configs[2]) under torchrun")
-    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 8; 4 for metatrain512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-roofline", action="store_true")
@@ -76,7 +82,7 @@ def make_namespace(wl, device, vgg_dir, batch):
         num_labels=wl["num_labels"], gan_type="gan", fm_weight=10.0, dice_weight=1.0, perc_weight=3e-2,
         idt_embed_weight=6e-3, dis_embed_weight=1e-2, vgg_weights_dir=vgg_dir, optimizer=wl["optimizer"],
         lr_gen=wl["lr_gen"], lr_dis=wl["lr_dis"], beta1=0.0, finetune=wl["finetune"], num_gpus=1, batch_size=batch,
-        **FULL)
+        **dict(FULL, image_size=wl.get("image_size", FULL["image_size"])))
 
 
 def fabricate_vgg_files(dirname, seed=3):
@@ -181,7 +187,8 @@ def reference_cpu_run(workload, batch, steps, warmup, budget_s):
     # 132.8 s/step with 128 threads (profiles/r01_bench_first_run.json) — use at most 32 and say so
     cores = min(os.cpu_count() or 1, 32)
     cmd = [sys.executable, str(ROOT / "oracle" / "ref_bench.py"), "--workload", workload, "--batch", str(batch), "--steps",
-           str(steps), "--warmup", str(warmup), "--budget-s", str(budget_s), "--threads", str(cores)]
+           str(steps), "--warmup", str(warmup), "--budget-s", str(budget_s), "--threads", str(cores), "--image-size",
+           str(WORKLOADS[workload].get("image_size", FULL["image_size"]))]
     env = dict(os.environ)
     env.pop("OMP_NUM_THREADS", None)
     try:
@@ -202,7 +209,7 @@ def cpu_port_rate(workload, sample_batch, steps, warmup, budget_s=25.0):
     wl = WORKLOADS[workload]
     cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
-    cfg = dict(synth.FULL_CFG)
+    cfg = dict(synth.FULL_CFG, image_size=wl.get("image_size", FULL["image_size"]))
     cfg["num_labels"] = max(wl["num_labels"], 1)
     crit = tuple(c.strip() for c in wl["criteria"].split(","))
     tr = OracleTrainer(cfg, finetune=wl["finetune"], criteria=crit, optimizer=wl["optimizer"], lr_gen=wl["lr_gen"],
@@ -241,6 +248,7 @@ def run_reference_arm(args):
     if wl_name == "drive":
         wl_name = "finetune"
     warmup = 1 if args.warmup > 0 else 0
+    args.batch = args.batch or WORKLOADS[wl_name].get("batch", 8)
     r = cpu_step_rate(wl_name, args.batch, max(args.steps, 3), warmup, budget_s=200.0)
     rate, dt = r["frames_per_s"], r["s_per_step"]
     sample = (f"{r['steps']} step(s) after {r['warmup']} warm-up at batch {r['batch']} = the per-GPU batch of the product arm, "
@@ -250,7 +258,7 @@ def run_reference_arm(args):
             "warmup": r["warmup"], "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[wl_name]["desc"], "global_batch": args.batch, "per_gpu_batch": args.batch,
-                       "image_size": 256,
+                       "image_size": WORKLOADS[wl_name].get("image_size", FULL["image_size"]),
                        "note": ("the UNMODIFIED reference modules (runners.holycow step over the reference's plugins) on the "
                                 "host CPU" if r["kind"] == "reference" else r.get("note", "CPU port")) +
                                f"; requested steps {args.steps} / warm-up {args.warmup} bounded to a ~200 s CPU budget"},
@@ -504,7 +512,8 @@ class StepBench:
         self.runner, self.tm, self.opt_G, self.opt_D, self.ns = build_training(wl, device, batch)
         self.tm.broadcast_parameters()
         self.n_batches = 4
-        self.host = make_host_batches(self.n_batches, batch, wl["k_frames"], wl["num_labels"], rank=rank)
+        self.host = make_host_batches(self.n_batches, batch, wl["k_frames"], wl["num_labels"],
+                                      s=wl.get("image_size", FULL["image_size"]), rank=rank)
         self.dev = [({k: v.to(device) for k, v in d.items()}, {k: v.to(device) for k, v in t.items()}) for d, t in self.host]
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host[0][0].values()) + \
             sum(v.numel() * v.element_size() for v in self.host[0][1].values())
@@ -580,7 +589,8 @@ def main():
     # train.py:98-109) — the N = 1 line carries the meta-training number too (`e2e.metatrain`) as the weak-scaling base.
     wl_name = args.workload or ("finetune" if world == 1 else "metatrain")
     wl = WORKLOADS[wl_name]
-    B = args.batch
+    B = args.batch or wl.get("batch", 8)
+    S = wl.get("image_size", FULL["image_size"])
     from b200lp import lib
     sb = StepBench(wl_name, device, B, rank, use_graph=not args.no_graph)
 
@@ -671,11 +681,12 @@ def main():
             cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {err}"}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": METRIC if S == 256 else METRIC.replace("256x256", f"{S}x{S}"), "value": round(value, 2), "unit": UNIT,
+                "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "tf32 operands / f32 accumulate (f32 storage)",
                 "data": "synthetic",
-                "config": {"workload": wl["desc"], "global_batch": B * world, "per_gpu_batch": B, "image_size": 256,
+                "config": {"workload": wl["desc"], "global_batch": B * world, "per_gpu_batch": B, "image_size": S,
                            "parallelism": f"dp{world}", "weights": "random init, spectral norm converged",
                            "l2": "per-step working set (activations, ~GBs) >> 126 MB L2; 4 distinct input batches cycled",
                            "cuda_graph": sb.graph_note,

@@ -33,6 +33,7 @@ WORKLOADS = {   # mirrors bench.py WORKLOADS (BASELINE.json configs[1] / configs
     "metatrain": dict(finetune=False, criteria="idt_embed, perceptual, adversarial, featmat, dis_embed, dice",
                       optimizer="Adam", lr_gen=5e-5, lr_dis=2e-4, k_frames=8, num_labels=16),
 }
+WORKLOADS["metatrain512"] = WORKLOADS["metatrain"]      # configs[4]: the caller passes --image-size 512 --batch 4
 
 
 def find_reference():
