@@ -480,6 +480,29 @@ def drive_benchmark(device, batch=64, n_batches=6):
                     "(bf16x3), clamp+uint8, async D2H of the frames"}
 
 
+def run_drive_line(args):
+    """`--workload drive`: BASELINE configs[3] as its own line (the default line carries the same number as
+    `e2e.drive`).  End to end by construction: host frames in, host uint8 frames out, wall clock around the loop with a
+    device synchronize on both sides; `--steps` = batches of 64 frames."""
+    from b200lp import lib
+    torch.cuda.set_device(0)
+    l0 = lib.load().b200lp_launch_count()
+    with torch.no_grad():
+        d = drive_benchmark("cuda:0", batch=64, n_batches=max(args.steps, 2))
+    launches = lib.load().b200lp_launch_count() - l0
+    ms = 1e3 * d["batch"] / d["value"]
+    frame_bytes = d["batch"] * 3 * 256 * 256
+    print(json.dumps({
+        "metric": "256x256 reenactment frames/sec (drive.py infer)", "value": d["value"], "unit": UNIT, "n_gpus": 1,
+        "steps": max(args.steps, 2), "warmup": 2, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16x3 operands / f32 accumulate (f32 storage)", "data": "synthetic",
+        "config": {"workload": "configs[3]: drive.py batched inference, bs=64, 256x256 driver frames, fine-tuned generator",
+                   "per_gpu_batch": d["batch"], "image_size": 256, "what": d["what"],
+                   "timing": "wall clock around the loop, device synchronised on both sides (host frames in, host frames out)"},
+        "e2e": {"value": d["value"], "unit": UNIT, "h2d_bytes_per_step": 4 * frame_bytes, "d2h_bytes_per_step": frame_bytes},
+        "gpu_launches": int(launches)}), flush=True)
+
+
 def shutdown_distributed(graphed_steps):
     """Leave a multi-rank run cleanly: the step's CUDA graph holds the communicator's captured all-reduces, and tearing
     the process group down UNDER a live graph hangs — so the graphs (and everything they keep alive) are destroyed first,
@@ -574,7 +597,8 @@ def main():
         run_reference_arm(args)
         return
     if args.workload == "drive":
-        raise SystemExit("use tools/bench_drive.py for the inference loop")
+        run_drive_line(args)
+        return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -159,9 +159,27 @@ def conv_fwd(x, wp, ksize, bias=None, residual=None, residual_mode=0, relu=False
     return (y, y_split) if emit_split else y
 
 
+def wgrad_batch_pad(x, dy):
+    """The weight-gradient kernel's K step is 32 pixels: on planes below 32 pixels one step spans 32 / (H*W) whole
+    samples, so the batch must be a multiple of that (csrc/conv_wgrad.cu, plan_wgrad: pn).  A ragged batch (batch 1 on the
+    generator's 4x4 planes, an odd batch on the discriminator's last blocks) is padded with all-zero samples: zero
+    gradient rows contribute nothing to the sum over pixels.  Returns (x, dy) unchanged when no padding is needed."""
+    n, h, w, _ = x.shape
+    if h * w >= 32:
+        return x, dy
+    m = 32 // (h * w)
+    pad = (-n) % m
+    if pad == 0:
+        return x, dy
+    return (torch.cat((x, x.new_zeros((pad,) + tuple(x.shape[1:]))), 0),
+            torch.cat((dy, dy.new_zeros((pad,) + tuple(dy.shape[1:]))), 0))
+
+
 def conv_wgrad(x, dy, ksize, scale=1.0, kstep=0, stages=0, splits=0):
     """x (N,H,W,Cin), dy (N,H,W,Cout) -> dw OIHW (Cout,Cin,k,k) * scale."""
     lib = L.load()
+    n_alg = x.shape[0]
+    x, dy = wgrad_batch_pad(x, dy)
     n, h, w, cin = x.shape
     cout = dy.shape[3]
     nbytes = lib.b200lp_conv_wgrad_workspace(n, h, w, cin, cout, ksize)
@@ -178,7 +196,7 @@ def conv_wgrad(x, dy, ksize, scale=1.0, kstep=0, stages=0, splits=0):
     a.ksize = ksize
     a.scale = float(scale)
     a.kstep, a.stages, a.splits = kstep, stages, splits
-    with _timed("conv_wgrad_tf32", flops=2.0 * n * h * w * cin * cout * ksize * ksize):
+    with _timed("conv_wgrad_tf32", flops=2.0 * n_alg * h * w * cin * cout * ksize * ksize):
         L.check(lib.b200lp_conv_wgrad(byref(a), L.stream_ptr()), "conv_wgrad")
     return dw
 
@@ -187,6 +205,8 @@ def conv_wgrad_sn_acc(x, dy, ksize, grad, weight=None, inv_sigma=None, u=None, v
     """grad (+)= s*G - s^2 <G, W> u v^T with G = wgrad(x, dy) (s = inv_sigma[0]; without inv_sigma: grad (+)= G).
     `grad`: contiguous OIHW fp32 buffer (the parameter's .grad view inside the gradient bucket) — written in place."""
     lib = L.load()
+    n_alg = x.shape[0]
+    x, dy = wgrad_batch_pad(x, dy)
     n, h, w, cin = x.shape
     cout = dy.shape[3]
     assert tuple(grad.shape) == (cout, cin, ksize, ksize), (grad.shape, cout, cin, ksize)
@@ -201,7 +221,7 @@ def conv_wgrad_sn_acc(x, dy, ksize, grad, weight=None, inv_sigma=None, u=None, v
     a.ksize = ksize
     a.scale = 1.0
     wq = weight.detach() if weight is not None else None
-    with _timed("conv_wgrad_tf32", flops=2.0 * n * h * w * cin * cout * ksize * ksize):
+    with _timed("conv_wgrad_tf32", flops=2.0 * n_alg * h * w * cin * cout * ksize * ksize):
         L.check(lib.b200lp_conv_wgrad_sn_acc(byref(a), L.ptr(wq), L.ptr(inv_sigma), L.ptr(u), L.ptr(v), int(accumulate),
                                              L.stream_ptr()), "conv_wgrad_sn_acc")
     return grad
@@ -920,8 +940,10 @@ def zero_stuff2(x):
 def gconv3x3_wgrad_tc(x, dy, cpg, acc_into=None):
     """dw (C, cpg, 3, 3) (+)= grouped weight gradient of a stride-1 3x3 conv on the TF32 tensor cores; x, dy (N,H,W,C)."""
     lib = L.load()
-    n, h, wd, c = x.shape
     assert dy.shape == x.shape, (dy.shape, x.shape)
+    n_alg = x.shape[0]
+    x, dy = wgrad_batch_pad(x, dy)
+    n, h, wd, c = x.shape
     nbytes = lib.b200lp_gconv3x3_wgrad_tc_workspace(n, h, wd, c)
     if nbytes <= 0:
         raise L.B200lpError(f"gconv3x3_wgrad_tc: unsupported shape {tuple(x.shape)}: {L.last_error()}")
@@ -935,7 +957,7 @@ def gconv3x3_wgrad_tc(x, dy, cpg, acc_into=None):
     a.ksize = 3
     a.scale = 1.0
     a.grouped = cpg
-    with _timed("resnext_grouped", flops=2.0 * n * h * wd * c * cpg * 9):
+    with _timed("resnext_grouped", flops=2.0 * n_alg * h * wd * c * cpg * 9):
         L.check(lib.b200lp_gconv3x3_wgrad_tc(byref(a), int(acc_into is not None), L.stream_ptr()), "gconv3x3_wgrad_tc")
     return dw
 

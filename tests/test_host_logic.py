@@ -296,3 +296,23 @@ def test_fused_optimizer_refuses_disagreeing_param_groups():
         opt._hyper()
     same = FusedAdamEMA([{"params": [a]}, {"params": [b]}], lr=1e-3)
     assert same._hyper()[0] == 1e-3
+
+
+def test_wgrad_batch_pad_fills_the_32_pixel_k_step():
+    """kernels.wgrad_batch_pad: planes below 32 pixels need a batch that is a multiple of 32 / (H*W) (conv_wgrad.cu
+    plan_wgrad: pn); ragged batches get all-zero samples, which leave the sum over pixels unchanged."""
+    from b200lp.kernels import wgrad_batch_pad
+    for n, h, w, want in [(1, 4, 4, 2), (3, 4, 4, 4), (2, 4, 4, 2), (8, 4, 4, 8), (5, 2, 2, 8), (1, 8, 4, 1), (3, 16, 16, 3)]:
+        x, dy = torch.randn(n, h, w, 32), torch.randn(n, h, w, 64)
+        xp, dyp = wgrad_batch_pad(x, dy)
+        assert xp.shape == (want, h, w, 32) and dyp.shape == (want, h, w, 64), (n, h, w, xp.shape)
+        assert xp.is_contiguous() and dyp.is_contiguous()
+        if want == n:
+            assert xp is x and dyp is dy                     # no copy when the batch already fits
+        else:
+            assert torch.equal(xp[:n], x) and torch.equal(dyp[:n], dy)
+            assert not xp[n:].any() and not dyp[n:].any()
+        # the weight gradient is a sum over samples: zero samples add nothing
+        ref = torch.einsum("nhwi,nhwo->oi", x.double(), dy.double())
+        got = torch.einsum("nhwi,nhwo->oi", xp.double(), dyp.double())
+        assert torch.equal(ref, got)

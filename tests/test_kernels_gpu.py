@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 NAMES = ["conv_basic", "conv_3x3", "conv_small_planes", "conv_epilogue", "conv_big", "conv_dgrad_pack", "wgrad_basic",
          "wgrad_3x3", "wgrad_big", "adain_fwd_bwd", "elementwise_misc", "direct_convs", "conv_bf16x3", "adain_split", "sn_kernels", "fused_optim", "conv_splitk", "conv_halo",
          "pack_multi", "conv_pair", "wgrad_sn_acc", "pose_encoder", "tail_tensor_core", "encoder_bn", "encoder_gconv",
-         "encoder_misc", "identity_encoder", "losses_kernels", "pose_bwd_kernels", "gconv_tc", "relu_bwd_fused", "l1_code", "c3_tensor_core", "adain_fused"]
+         "encoder_misc", "identity_encoder", "losses_kernels", "pose_bwd_kernels", "gconv_tc", "relu_bwd_fused", "l1_code", "c3_tensor_core", "adain_fused", "wgrad_ragged_batch"]
 
 
 @pytest.mark.parametrize("name", NAMES)

@@ -255,6 +255,36 @@ def wgrad_3x3():
 
 
 @check
+def wgrad_ragged_batch():
+    """Planes below 32 pixels with a batch that does not fill the kernel's 32-pixel K step (batch 1 on the generator's 4x4
+    planes, odd batches on the discriminator's last blocks): kernels.wgrad_batch_pad appends all-zero samples.
+    Plain, spectral-norm and overwrite forms vs float64 autograd."""
+    import torch
+    import torch.nn.functional as F
+    from b200lp import kernels as K
+    out = [_wgrad_case(1, 4, 4, 64, 64, 3), _wgrad_case(3, 4, 4, 128, 256, 3), _wgrad_case(1, 4, 4, 512, 512, 3),
+           _wgrad_case(3, 4, 4, 32, 32, 1), _wgrad_case(1, 8, 8, 64, 64, 3)]
+    torch.manual_seed(6)
+    for (N, H, W_, Cin, Cout, k) in [(1, 4, 4, 512, 512, 3), (3, 4, 4, 64, 128, 3)]:
+        x = tf32_round(torch.randn(N, Cin, H, W_, device="cuda"))
+        dy = tf32_round(torch.randn(N, Cout, H, W_, device="cuda"))
+        w = torch.randn(Cout, Cin, k, k, device="cuda") * 0.05
+        u = F.normalize(torch.randn(Cout, device="cuda"), dim=0)
+        v = F.normalize(torch.randn(Cin * k * k, device="cuda"), dim=0)
+        wd = w.double().requires_grad_(True)
+        sigma = torch.dot(u.double(), torch.mv(wd.reshape(Cout, -1), v.double()))
+        F.conv2d(x.double(), wd / sigma, padding=k // 2).backward(dy.double())
+        inv_sigma = (1 / sigma.detach()).float().reshape(1)
+        g_prev = torch.randn_like(w)
+        grad = g_prev.clone()
+        K.conv_wgrad_sn_acc(x.permute(0, 2, 3, 1).contiguous(), dy.permute(0, 2, 3, 1).contiguous(), k, grad, w, inv_sigma, u, v)
+        torch.cuda.synchronize()
+        e = _err(grad - g_prev, wd.grad); e["case"] = f"wgrad_sn_acc ragged N{N} H{H} Cin{Cin} Cout{Cout} k{k}"
+        e["ok"] = (not e["nan"]) and e["rel"] < 5e-5; out.append(e)
+    return out
+
+
+@check
 def wgrad_big():
     return [_wgrad_case(8, 256, 256, 64, 64, 3), _wgrad_case(8, 32, 32, 512, 512, 3), _wgrad_case(8, 128, 128, 128, 64, 3),
             _wgrad_case(8, 256, 256, 32, 64, 1)]     # single-tile grid: one split per SM
