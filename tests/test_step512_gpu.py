@@ -6,11 +6,15 @@ blocks and both VGG networks run on 512x512 and 256x256 planes: the backward ker
 weight gradients with 262 144 pixels per sample, AdaIN backward, pooled L1 taps) are reached at plane sizes the 256x256
 tests never produce.
 
-Tolerances: generator RGB max-abs <= 1e-3 (north_star); loss values 3e-3 relative (TF32 operands); gradient NORMS of
-every parameter 5e-3 relative (TF32; the 256x256 batch-2 step achieves 1.3e-3); sub-sampled gradient tensors 5e-2 of the
-tensor's maximum (batch 1 halves the pixels per weight-gradient element against tests/test_parity_full_gpu.py, where
-torch's own TF32 kernels reach 4.7e-2 on the deepest discriminator weights).  The achieved error of every parameter is
-written to gpurun_out/step512_gradient_errors.json BEFORE anything is asserted.
+Tolerances: generator RGB max-abs <= 1e-3 (north_star; achieved 1.7e-4); loss values 3e-3 relative (TF32 operands;
+achieved <= 2.7e-4); gradient NORMS of every parameter 2.5e-3 relative — the bar of tests/test_parity_full_gpu.py (achieved:
+generator <= 1.24e-3, median 4.2e-4; discriminator <= 8.5e-4); sub-sampled gradient tensors 1.5e-2 of the tensor's maximum
+(achieved <= 6.4e-3).  The achieved error of every parameter is written to gpurun_out/step512_gradient_errors.json BEFORE
+anything is asserted (the run behind these numbers: profiles/r02_step512_gradient_errors.json).
+
+Batch 1 matters: the generator's first blocks run on 4x4 planes, where one 32-pixel K step of the weight-gradient kernel
+spans two samples — kernels.wgrad_batch_pad appends a zero sample (the first run of this test failed exactly there:
+profiles/r02_step512_batch1_first_run_failure.log).
 """
 import importlib
 import json
@@ -25,7 +29,7 @@ from oracle import synth
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-LOSS_TOL, NORM_TOL, SUB_TOL = 3e-3, 5e-3, 5e-2
+LOSS_TOL, NORM_TOL, SUB_TOL = 3e-3, 2.5e-3, 1.5e-2
 REPORT_NAME = "step512_gradient_errors.json"
 
 
@@ -110,6 +114,6 @@ def test_512_training_step():
         assert abs(r["got"] - r["reference"]) <= LOSS_TOL * abs(r["reference"]) + 1e-6, (k, r)
     assert report["fake_rgbs_max_abs"] < 1e-3
     assert worst[0][0] <= 1.0, report["worst"][:5]
-    assert e_scale <= 3e-2, report["embedder_scale"]
+    assert e_scale <= 1.5e-2, report["embedder_scale"]
     for p in list(G.parameters()) + list(D.parameters()):
         assert torch.isfinite(p).all()
