@@ -476,7 +476,8 @@ class GraphedTrainStep:
                 v.copy_(target_dict[k], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        self._pending = (id(data_dict), id(target_dict), which, ev)
+        # the dicts themselves (not their ids: a freed dict's id can be handed to the next batch's dict)
+        self._pending = (data_dict, target_dict, which, ev)
         self._last_stage = which
 
     def release(self):
@@ -503,7 +504,7 @@ class GraphedTrainStep:
             if hasattr(o, 'sync_hyper'):
                 o.sync_hyper()
         pend = getattr(self, '_pending', None)
-        if pend is not None and pend[0] == id(data_dict) and pend[1] == id(target_dict):
+        if pend is not None and pend[0] is data_dict and pend[1] is target_dict:
             sd, st = self._staging[pend[2]]
             torch.cuda.current_stream().wait_event(pend[3])
             for k, v in self.static_data.items():
