@@ -188,7 +188,7 @@ def reference_cpu_run(workload, batch, steps, warmup, budget_s):
     cores = min(os.cpu_count() or 1, 32)
     cmd = [sys.executable, str(ROOT / "oracle" / "ref_bench.py"), "--workload", workload, "--batch", str(batch), "--steps",
            str(steps), "--warmup", str(warmup), "--budget-s", str(budget_s), "--threads", str(cores), "--image-size",
-           str(WORKLOADS[workload].get("image_size", FULL["image_size"]))]
+           str(WORKLOADS.get(workload, {}).get("image_size", FULL["image_size"]))]
     env = dict(os.environ)
     env.pop("OMP_NUM_THREADS", None)
     try:
@@ -246,7 +246,8 @@ def run_reference_arm(args):
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     wl_name = args.workload or ("finetune" if world == 1 else "metatrain")
     if wl_name == "drive":
-        wl_name = "finetune"
+        run_reference_drive(args)
+        return
     warmup = 1 if args.warmup > 0 else 0
     args.batch = args.batch or WORKLOADS[wl_name].get("batch", 8)
     r = cpu_step_rate(wl_name, args.batch, max(args.steps, 3), warmup, budget_s=200.0)
@@ -265,6 +266,35 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+DRIVE_METRIC = "256x256 reenactment frames/sec (drive.py infer)"
+
+
+def run_reference_drive(args):
+    """`--impl reference --workload drive`: the reference's drive.py inner loop (drive.py:84-98, through its own embedder
+    / generator modules) on the host cores.  Default batch 1 = BASELINE configs[0] (the reference hard-codes 1,
+    drive.py:57); `--batch 64` = configs[3]'s batch on the CPU."""
+    batch = args.batch or 1
+    r = reference_cpu_run("drive", batch, max(args.steps, 3), 2 if args.warmup > 0 else 0, budget_s=120.0)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "no reference tree (baseline/_ref or /root/reference) for the "
+                                                              "drive loop"}))
+        return
+    rate = r["frames_per_s"]
+    sample = (f"{r['steps']} batch(es) of {r['batch']} frame(s) after {r['warmup']} warm-up, fp32, {r['cores']} torch threads "
+              f"(reference pins 1, utils/utils.py:19: overridden), run-to-run spread {100 * r.get('spread', 0.0):.1f} %")
+    print(json.dumps({
+        "impl": "reference", "metric": DRIVE_METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+        "warmup": r["warmup"], "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": ("configs[0]: drive.py single-frame inference, bs=1, CPU" if batch == 1 else
+                                f"drive.py inference loop, bs={batch}, CPU"),
+                   "per_gpu_batch": batch, "image_size": 256,
+                   "note": "the UNMODIFIED reference modules (pose embedder + fine-tuned generator, drive.py:84-98) on the "
+                           "host CPU; video encoding left out on both arms"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -492,15 +522,25 @@ def run_drive_line(args):
     launches = lib.load().b200lp_launch_count() - l0
     ms = 1e3 * d["batch"] / d["value"]
     frame_bytes = d["batch"] * 3 * 256 * 256
-    print(json.dumps({
-        "metric": "256x256 reenactment frames/sec (drive.py infer)", "value": d["value"], "unit": UNIT, "n_gpus": 1,
+    cpu_baseline = None
+    if not args.no_cpu_baseline:          # BASELINE configs[0]: the reference's loop at its own batch (1) on the host cores
+        r = reference_cpu_run("drive", 1, 20, 2, budget_s=20.0)
+        if r is not None:
+            cpu_baseline = {"value": round(r["frames_per_s"], 3), "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                            "sample": f"{r['steps']} frames at batch 1 (BASELINE configs[0]: drive.py's own batch) after "
+                                      f"{r['warmup']} warm-up, fp32, {r['cores']} torch threads"}
+    line = {
+        "metric": DRIVE_METRIC, "value": d["value"], "unit": UNIT, "n_gpus": 1,
         "steps": max(args.steps, 2), "warmup": 2, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16x3 operands / f32 accumulate (f32 storage)", "data": "synthetic",
         "config": {"workload": "configs[3]: drive.py batched inference, bs=64, 256x256 driver frames, fine-tuned generator",
                    "per_gpu_batch": d["batch"], "image_size": 256, "what": d["what"],
                    "timing": "wall clock around the loop, device synchronised on both sides (host frames in, host frames out)"},
         "e2e": {"value": d["value"], "unit": UNIT, "h2d_bytes_per_step": 4 * frame_bytes, "d2h_bytes_per_step": frame_bytes},
-        "gpu_launches": int(launches)}), flush=True)
+        "gpu_launches": int(launches)}
+    if cpu_baseline is not None:
+        line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line), flush=True)
 
 
 def shutdown_distributed(graphed_steps):

@@ -34,6 +34,8 @@ WORKLOADS = {   # mirrors bench.py WORKLOADS (BASELINE.json configs[1] / configs
                       optimizer="Adam", lr_gen=5e-5, lr_dis=2e-4, k_frames=8, num_labels=16),
 }
 WORKLOADS["metatrain512"] = WORKLOADS["metatrain"]      # configs[4]: the caller passes --image-size 512 --batch 4
+# configs[0] / configs[3]: drive.py's inner loop (drive.py:84-98) — fine-tuned generator + pose embedder, no discriminator
+WORKLOADS["drive"] = dict(WORKLOADS["finetune"], drive=True)
 
 
 def find_reference():
@@ -61,6 +63,47 @@ def fabricate_vgg_files(dirname, torch, seed=3):
     f = torchvision.models.vgg16().features.state_dict()
     torch.save({k: (torch.randn(v.shape, generator=g) * (2.0 / (9 * v.shape[1])) ** 0.5 if v.dim() == 4 else v)
                 for k, v in f.items()}, os.path.join(dirname, "vgg_face_weights.pth"))
+
+
+def drive_loop(args, torch, E, G, cores, ref):
+    """The reference's drive.py inner loop (drive.py:84-98) on synthetic driver frames: pose embedding -> generator in
+    fine-tuned mode (drive.py:52,63-70; eval mode = `set_eval_mode_in_test`) -> permute / clamp_ / mul_ / byte of the
+    result and of the driver frame, concatenated side by side.  One "step" = one batch of `--batch` frames (the
+    reference hard-codes 1, drive.py:57).  Video encoding is left out on both arms."""
+    import numpy as np
+    S, B = args.image_size, args.batch
+    G.enable_finetuning({"embeds": torch.randn(1, 512)})
+    E.enable_finetuning()
+    E.eval(); G.eval()
+    g = torch.Generator().manual_seed(5)
+    frames = [torch.rand(B, 1, 3, S, S, generator=g) for _ in range(2)]
+
+    def to_u8(image):
+        return image.permute(1, 2, 0).clamp_(0, 1).mul_(255).cpu().byte().numpy()
+
+    def step(i):
+        with torch.no_grad():
+            d = {"pose_input_rgbs": frames[i % 2].clone()}
+            E.get_pose_embedding(d)
+            G(d)
+            out = [np.concatenate((to_u8(d["pose_input_rgbs"][b, 0]), to_u8(d["fake_rgbs"][b])), axis=1) for b in range(B)]
+        return out
+
+    for i in range(args.warmup):
+        step(i)
+    times = []
+    t_start = time.perf_counter()
+    for i in range(max(args.steps, 1)):
+        t0 = time.perf_counter()
+        step(i)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > args.budget_s:
+            break
+    dt = sum(times) / len(times)
+    print(json.dumps({"frames_per_s": B / dt, "s_per_step": dt, "steps": len(times), "warmup": args.warmup, "batch": B,
+                      "cores": cores, "reference_tree": str(ref), "kind": "reference",
+                      "spread": (max(times) - min(times)) / dt if len(times) > 1 else 0.0,
+                      "torch_threads": torch.get_num_threads()}))
 
 
 def main():
@@ -106,6 +149,8 @@ def main():
         D = Dm.Wrapper.get_net(ns)
         E = importlib.import_module("embedders.unsupervised_pose_separate_embResNeXt_segmentation").Wrapper.get_net(ns)
         crits = [importlib.import_module(f"criterions.{c.strip()}").Wrapper.get_net(ns) for c in wl["criteria"].split(",")]
+    if wl.get("drive"):
+        return drive_loop(args, torch, E, G, cores, ref)
     if wl["finetune"]:           # train.py:240-279
         e = torch.randn(1, 512)
         G.enable_finetuning({"embeds": e.clone()})
