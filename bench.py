@@ -337,7 +337,10 @@ def build_training(wl, device, batch):
     return runner, tm, opt_G, opt_D, ns
 
 
-def roofline_from_replay(replay_fn, work, peaks):
+TRAFFIC_FILES = {"finetune": "r02_dram_traffic.json", "metatrain": "r02_dram_traffic_metatrain_final.json"}
+
+
+def roofline_from_replay(replay_fn, work, peaks, workload="finetune"):
     """Per-family device time of ONE replay of the captured step (CUPTI kernel durations through torch.profiler: the
     kernels as they run back to back inside the graph, not event pairs around eager launches) against the algorithmic
     FLOPs / bytes the host booked while the step was captured (b200lp.kernels.WORK) -> the dominant
@@ -348,8 +351,10 @@ def roofline_from_replay(replay_fn, work, peaks):
     out = {"families": table, "replay": {"kernel_ms": round(total_ms, 3), "launches": sum(c for _, c in rows.values()),
                                          "libb200lp_share": round(own_ms / (total_ms or 1.0), 3)}}
     traffic = {}
-    tj = ROOT / "profiles" / "r02_dram_traffic.json"      # ncu dram__bytes_{read,write}.sum per launch, same command
-    if tj.exists():
+    # ncu dram__bytes_{read,write}.sum per launch of one replayed step of THIS workload (tools/ncu_traffic.py);
+    # a workload without a committed capture (metatrain512) reports traffic = null
+    tj = ROOT / "profiles" / TRAFFIC_FILES.get(workload, "none")
+    if tj.is_file():
         traffic = json.loads(tj.read_text())
     conv = table.get("conv_igemm_tf32")
     if conv and conv["tflops"]:
@@ -696,7 +701,7 @@ def main():
         pk = ROOT / "MEASURED_PEAKS.json"
         if pk.exists():
             peaks = json.loads(pk.read_text())
-        prof = roofline_from_replay(lambda: sb.graphed(*sb.dev[0]), sb.graphed.work, peaks)
+        prof = roofline_from_replay(lambda: sb.graphed(*sb.dev[0]), sb.graphed.work, peaks, workload=wl_name)
         if rank == 0:
             extra.update(prof)
             extra["peaks_source"] = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
