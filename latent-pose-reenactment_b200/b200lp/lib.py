@@ -5,7 +5,6 @@ device pointers + sizes across the C ABI.  There is NO fallback: if the library 
 sm_100, calls raise.
 """
 import ctypes
-import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_void_p
 from pathlib import Path
 

@@ -20,7 +20,7 @@ for p in (str(ROOT / "latent-pose-reenactment_b200"), str(ROOT), str(ROOT / "tes
 
 
 def main():
-    from helpers import StubEmbedder, make_args, to_dev, write_vgg_files
+    from helpers import StubEmbedder, make_args, write_vgg_files
     from oracle import synth
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)

@@ -1,6 +1,5 @@
 """Host-side logic of the drop-in boundary (no GPU): argument precedence, plugin loading, checkpoint round trip,
 optimizer update rule, meters, the synthetic dataset contract."""
-import argparse
 import importlib
 import math
 import os

@@ -16,7 +16,6 @@ max(1e-2, 1.25 x torch-TF32's error) per parameter, and within 1e-2 for 90 % of 
 import importlib
 import json
 import tempfile
-from pathlib import Path
 
 import pytest
 import torch

@@ -5,7 +5,6 @@ context) and compares one C-ABI entry point with plain torch ops in fp64/fp32.  
     python tools/gpu_diag.py conv wgrad # name filters
 """
 import json
-import os
 import subprocess
 import sys
 import time
@@ -1328,7 +1327,6 @@ def adain_fused():
     """b200lp_adain_relu_fused (statistics + per-sample barrier + apply in ONE launch) == b200lp_in_stats + b200lp_adain_relu:
     every output form, upsampling, odd batch sizes, planes from 4x4 to 256x256, repeated launches on one stream (the barrier
     counters must come back to zero); timing of both forms at the generator's largest sites."""
-    import os
     import torch
     from b200lp import kernels as K
     out = []

@@ -1,6 +1,5 @@
 """Kernel-level device time of the identity encoder's forward + backward (64 x 256x256, train mode) through CUPTI
 (torch.profiler): native schedule vs the torchvision module on cuDNN -> gpurun_out/identity_profile.txt"""
-import copy
 import sys
 from pathlib import Path
 
