@@ -188,3 +188,45 @@ def test_full_size_step_losses_and_gradients():
         ref_norm = gold["step.gradD.norms"][k]
         gn = 0.0 if g is None else float(g.norm())
         assert abs(gn - ref_norm) <= 3e-3 * ref_norm + 1e-5 * d_max, k
+
+
+def test_512_step_losses_and_gradient_norms():
+    """The restatement at BASELINE configs[4]'s shapes (512x512: 19 AdaIN sites, 8 up-blocks; batch 1, train mode) against
+    the full runner step of the unmodified reference (tests/golden/step512.pt, oracle/make_golden_step512.py): every loss,
+    every generator / discriminator gradient norm, the stored sub-sampled gradient tensors."""
+    from conftest import GOLDEN
+    gold = torch.load(GOLDEN / "step512.pt", map_location="cpu", weights_only=False)
+    cfg = gold["cfg"]
+    assert cfg["image_size"] == 512
+    g_sd0, d_sd0 = synth.generator_state_dict(cfg, seed=31), synth.discriminator_state_dict(cfg, seed=32)
+    g_sd = {k: (v.clone().requires_grad_(True) if "weight_orig" in k or k.endswith("bias") or k == "constant.constant"
+                else v.clone()) for k, v in g_sd0.items()}
+    d_sd = {k: (v.clone().requires_grad_(True) if "weight_orig" in k or k.endswith("bias") else v.clone())
+            for k, v in d_sd0.items()}
+    data, target, emb = synth.make_inputs(cfg, batch=1, seed=34)
+    out, lg, ld = R.forward_losses(g_sd, d_sd, synth.vgg_state_dict("vgg19", seed=3), synth.vgg_state_dict("vgg16", seed=5),
+                                   cfg, emb["embeds"], emb["pose_embedding"], data["target_rgbs"][:, 0],
+                                   target["real_segm"][:, 0], target["label"], training=True,
+                                   embeds_elemwise=emb["embeds_elemwise"],
+                                   criteria=("idt_embed", "perceptual", "adversarial", "featmat", "dis_embed", "dice"))
+    for k, v in {**lg, **ld}.items():
+        torch.testing.assert_close(v.detach(), gold["step.loss." + k], rtol=3e-4, atol=1e-6)
+
+    def sub(t):
+        if t.dim() == 4:
+            return t[::max(1, t.shape[0] // 16), ::max(1, t.shape[1] // 16), ::max(1, t.shape[2] // 16), ::max(1, t.shape[2] // 16)]
+        if t.dim() == 2:
+            return t[::max(1, t.shape[0] // 64), ::max(1, t.shape[1] // 64)]
+        return t
+    for sd, losses, key in ((g_sd, lg, "G"), (d_sd, ld, "D")):
+        params = {k: v for k, v in sd.items() if v.requires_grad}
+        grads = torch.autograd.grad(sum(losses.values()), list(params.values()), retain_graph=(key == "G"), allow_unused=True)
+        ref_norms = gold[f"step.grad{key}.norms"]
+        top = max(ref_norms.values())
+        assert set(params) == set(ref_norms), set(params) ^ set(ref_norms)
+        for (k, _), g in zip(params.items(), grads):
+            gn = 0.0 if g is None else float(g.norm())
+            assert abs(gn - ref_norms[k]) <= 3e-3 * ref_norms[k] + 1e-5 * top, (k, gn, ref_norms[k])
+            ref = gold.get(f"step.grad{key}.sub." + k)
+            if ref is not None:
+                assert float((sub(g) - ref).abs().max()) <= 5e-3 * float(ref.abs().max()) + 1e-5 * top, k
