@@ -54,3 +54,25 @@ def test_sass_contains_blackwell_tensor_core_and_tma_instructions():
     assert "UTMALDG" in sass
     assert "LDTM" in sass
     assert "HMMA.16816" not in sass and "HGMMA" not in sass
+
+
+def test_integration_md_stub_matches_the_binding():
+    """The ctypes stub INTEGRATION.md shows a reference maintainer must describe the same struct as the binding this
+    repo uses (field names, order, types) and build its ConvArgs with one positional value per field."""
+    import ctypes
+    import re
+    from conftest import ROOT
+    from b200lp import lib as L
+    text = (ROOT / "INTEGRATION.md").read_text()
+    block = text.split("class ConvArgs(Structure):", 1)[1].split("_lib.b200lp_conv_fwd.argtypes", 1)[0]
+    fields = [(n, getattr(ctypes, t)) for n, t in re.findall(r'\("(\w+)",\s*(c_\w+)\)', block)]   # c_int32 is c_int
+    want = list(L.ConvArgs._fields_)
+    assert fields == want, (fields, want)
+    call = text.split("a = ConvArgs(", 1)[1].split(")  #", 1)[0]
+    depth, n_args = 0, 1
+    for ch in call:
+        depth += ch == "("
+        depth -= ch == ")"
+        n_args += ch == "," and depth == 0
+    assert n_args == len(want), (n_args, len(want))
+    assert ctypes.sizeof(L.ConvArgs) % 8 == 0
