@@ -76,3 +76,70 @@ def test_integration_md_stub_matches_the_binding():
         n_args += ch == "," and depth == 0
     assert n_args == len(want), (n_args, len(want))
     assert ctypes.sizeof(L.ConvArgs) % 8 == 0
+
+
+def test_struct_field_offsets_match_the_c_compiler():
+    """include/b200lp.h compiled by gcc as plain C: sizeof and every field's offsetof must equal the ctypes structures
+    of the binding (the header is the contract a C / cgo / JNI caller would compile against)."""
+    import shutil
+    import subprocess
+    import tempfile
+    import pytest
+    from b200lp import lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    pairs = {"b200lp_conv_args": lib.ConvArgs, "b200lp_wgrad_args": lib.WgradArgs, "b200lp_sn_item": lib.SnItem}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200lp.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        src.append(f'  printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            src.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    src += ['  return 0;', '}']
+    with tempfile.TemporaryDirectory() as d:
+        c = Path(d) / "abi.c"
+        c.write_text("\n".join(src))
+        exe = Path(d) / "abi"
+        r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(c), "-o", str(exe)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr          # the header is valid C99 and names every field the binding names
+        out = subprocess.run([str(exe)], capture_output=True, text=True).stdout
+    got = {}
+    for line in out.strip().splitlines():
+        cname, fname, val = line.split()
+        got[(cname, fname)] = int(val)
+    for cname, cls in pairs.items():
+        assert got[(cname, "sizeof")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_every_prototype_matches_the_ctypes_signature():
+    """Argument by argument: each prototype of include/b200lp.h against the binding's (restype, argtypes) — pointer,
+    int32, int64, float or double in the same position, same count (a silent mismatch would shift every later argument)."""
+    from b200lp import lib
+    text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "b200lp.h").read_text(), flags=re.S)
+    protos = re.findall(r"([\w][\w\s\*]*?)\s*\b(b200lp_\w+)\s*\(([^)]*)\)\s*;", text)
+    assert len(protos) == len(lib.SIGNATURES) >= 100
+
+    def c_kind(t):
+        t = t.strip()
+        if t == "void":
+            return None
+        for key, kind in (("*", "P"), ("int32_t", "I"), ("int64_t", "L"), ("float", "F"), ("double", "D")):
+            if key in t:
+                return kind
+        raise AssertionError(f"unclassified C type {t!r}")
+
+    def ct_kind(t):
+        if t is None:
+            return None
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents"):
+            return "P"
+        return {ctypes.c_int32: "I", ctypes.c_int64: "L", ctypes.c_float: "F", ctypes.c_double: "D"}[t]
+
+    for ret, name, params in protos:
+        want = [k for k in (c_kind(p) for p in params.split(",")) if k is not None]
+        restype, argtypes = lib.SIGNATURES[name]
+        assert [ct_kind(a) for a in argtypes] == want, name
+        assert ct_kind(restype) == c_kind(ret), name
